@@ -1,0 +1,2 @@
+// shim: the external "profi" profiler is not part of the reference repo.
+#pragma once
