@@ -1,0 +1,133 @@
+/* vxb200.h - C ABI of the B200-native Transvoxel polygonizer backend (libvxb200.so).
+ *
+ * This is the thin extern "C" layer between host code and the sm_100a CUDA kernels: plain pointers
+ * and sizes only, no C++/torch types.  It replaces the reference's hot path
+ *     Voxels::Polygonizer::Execute            /root/reference/src/TransVoxelImpl.cpp:74-79, :2153-2169
+ *     TransVoxelRun::Execute (level loop)     /root/reference/src/TransVoxelImpl.cpp:468-538
+ * and consumes exactly what that path reads from the grid store
+ *     VoxelGrid::GetBlockData / GetMaterialBlockData / IsBlockEmpty   src/VoxelGrid.h:49-55
+ *     (public form: Grid::GetBlockDistanceData / GetBlockMaterialData  include/Grid.h:127-139)
+ * The C++ drop-in (voxels_b200/csrc/polygonizer_host.cpp: Voxels::Polygonizer, Modification,
+ * PolygonSurface, BlockPolygons with the reference's vtable order) is built on top of these calls;
+ * INTEGRATION.md shows the binding a maintainer of the reference would add.
+ *
+ * Conventions: grid coordinates are Z-up, x fastest; output vertices are Y-up exactly as the
+ * reference emits them (TransVoxelImpl.cpp:1289-1291, :1336-1360).  All functions return 0 on
+ * success or a negative vxb_status; vxb_last_error() gives the text.  No function falls back to
+ * the CPU: without a CUDA device every call fails with VXB_ERR_CUDA.
+ */
+#ifndef VXB200_H
+#define VXB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct vxb_context vxb_context;
+
+typedef enum vxb_status
+{
+	VXB_OK = 0,
+	VXB_ERR_CUDA = -1,        /* CUDA runtime/driver error (text in vxb_last_error) */
+	VXB_ERR_ARGUMENT = -2,    /* bad size (cube, power of two, >= 16), null pointer, ... */
+	VXB_ERR_STATE = -3,       /* call order (no grid uploaded, no result yet, ...) */
+	VXB_ERR_CAPACITY = -4     /* output arenas too small even after growing */
+} vxb_status;
+
+/* Flags of vxb_polygonize */
+enum
+{
+	VXB_FLAG_NO_TRANSITIONS = 1,  /* do not emit transition meshes (BASELINE config 2); the reference always emits them */
+	VXB_FLAG_KERNEL_TIMES = 2     /* bracket every kernel with CUDA events (vxb_kernel_ms); adds a little stream overhead */
+};
+
+/* One emitted block (a block that produced >= 1 regular vertex; reference: PushBlocksToResult
+ * TransVoxelImpl.cpp:1266-1428).  Offsets index the arrays vxb_result_download fills. */
+typedef struct vxb_block_record
+{
+	uint32_t level;
+	uint32_t coord_id;            /* z*nb*nb + y*nb + x at that level (:399) */
+	uint32_t id;                  /* Block id as the reference assigns it (:395-401) */
+	uint32_t vertex_count;
+	uint32_t index_count;         /* after the degenerate-triangle filter (:1300-1321) */
+	uint32_t vertex_offset;       /* in vertices */
+	uint32_t index_offset;        /* in indices */
+	uint32_t trans_vertex_count[6];   /* face order = BlockPolygons::TransitionFaceId (include/Polygonizer.h:58-68) */
+	uint32_t trans_index_count[6];
+	uint32_t trans_vertex_offset[6];
+	uint32_t trans_index_offset[6];
+	uint32_t reserved;
+} vxb_block_record;               /* 32 x 4 bytes */
+
+typedef struct vxb_result_info
+{
+	uint32_t levels_total;        /* log2(n/16)+1 (:490) */
+	uint32_t levels_computed;
+	uint32_t block_count;         /* number of vxb_block_record */
+	uint32_t pad;
+	uint64_t vertex_span;         /* elements to allocate for each download array (spans include   */
+	uint64_t index_span;          /* the gaps left by removed degenerate triangles)                 */
+	uint64_t trans_vertex_span;
+	uint64_t trans_index_span;
+	uint64_t vertex_total;        /* exact totals over all records */
+	uint64_t index_total;
+	uint64_t trans_vertex_total;
+	uint64_t trans_index_total;
+	/* PolygonizationStatistics (include/Polygonizer.h:110-132): BlocksCalculated, TrivialCells,
+	 * NonTrivialCells, DegenerateTrianglesRemoved, PerCaseCellsCount[16] */
+	uint32_t stats[20];
+	uint32_t used_materials[8];   /* bit per material id that occurs in an emitted vertex */
+	float device_ms;              /* device time of the last vxb_polygonize (CUDA events) */
+	uint32_t kernel_launches;     /* kernels launched by the last vxb_polygonize */
+} vxb_result_info;
+
+/* ---- context ------------------------------------------------------------------------------- */
+int vxb_create(int device, vxb_context** out);
+void vxb_destroy(vxb_context* ctx);
+const char* vxb_last_error(const vxb_context* ctx);   /* ctx may be NULL: error of a failed vxb_create */
+/* cudaStream_t the context launches on (as void*), for callers that time with their own events */
+void* vxb_stream(vxb_context* ctx);
+
+/* ---- grid (input provider side: VoxelGrid accessors, src/VoxelGrid.h:49-55) ------------------ */
+/* n^3 dense volumes in HOST memory, index (z*n + y)*n + x.  mat/blend may be NULL (zeros). */
+int vxb_grid_upload_dense(vxb_context* ctx, uint32_t n, const int8_t* dist, const uint8_t* mat, const uint8_t* blend);
+/* HOST memory, 16^3 blocks exactly as Grid::GetBlockDistanceData/GetBlockMaterialData return them,
+ * concatenated in VoxelGrid block order (id = x + y*nb + z*nb*nb, VoxelGrid.h:139-144; 4096 B each). */
+int vxb_grid_upload_blocks(vxb_context* ctx, uint32_t n, const int8_t* dist_blocks, const uint8_t* mat_blocks, const uint8_t* blend_blocks);
+/* Dense volumes already resident in DEVICE memory (not copied; must stay valid; 16-byte aligned). */
+int vxb_grid_set_device(vxb_context* ctx, uint32_t n, const int8_t* d_dist, const uint8_t* d_mat, const uint8_t* d_blend);
+/* Device pointers of the context-owned dense volumes (after an upload), for tools/benchmarks. */
+int vxb_grid_device_pointers(vxb_context* ctx, const int8_t** d_dist, const uint8_t** d_mat, const uint8_t** d_blend);
+
+/* MaterialMap::GetMaterial pre-tabulated (include/MaterialMap.h:19-30): table = 256 x
+ * {DiffuseIds0[3], DiffuseIds1[3]}, valid = 256 bytes (0 = GetMaterial returned nullptr).
+ * NULL table = identity map, NULL valid = all valid. */
+int vxb_set_materials(vxb_context* ctx, const uint8_t* table, const uint8_t* valid);
+
+/* ---- polygonization -------------------------------------------------------------------------- */
+/* Full run over LOD levels [0, max_levels) (0 = all, as the reference).  Results stay in device
+ * arenas until the next call.  Blocks until the device work is done. */
+int vxb_polygonize(vxb_context* ctx, uint32_t max_levels, uint32_t flags);
+int vxb_result_info_get(vxb_context* ctx, vxb_result_info* out);
+/* Copies the directory (sorted by level, then coord_id = the reference's block order) and the
+ * arenas to HOST memory sized from vxb_result_info spans.  Vertices are 48-byte
+ * Voxels::PolygonVertex (include/Polygonizer.h:14-48).  Any pointer may be NULL to skip it. */
+int vxb_result_download(vxb_context* ctx, vxb_block_record* records, void* vertices, uint32_t* indices,
+	void* trans_vertices, uint32_t* trans_indices);
+
+/* Initial arena capacities in elements (0 = keep default).  Arenas grow and the run repeats
+ * automatically on overflow; this only avoids the retry. */
+int vxb_set_capacity(vxb_context* ctx, uint64_t vertices, uint64_t indices, uint64_t trans_vertices, uint64_t trans_indices);
+
+/* Per-kernel device time of the last vxb_polygonize, for bench.py's roofline line:
+ * which = 0: grid scan (streams the level-0 distance volume once), 1: block selection,
+ * 2: block polygonization (all levels).  Milliseconds, summed over launches of that kind. */
+int vxb_kernel_ms(vxb_context* ctx, int which, float* ms, uint32_t* launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VXB200_H */

@@ -1,0 +1,211 @@
+"""ctypes binding of include/vxb200.h (libvxb200.so).  Mirrors the C ABI one to one."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+FLAG_NO_TRANSITIONS = 1
+FLAG_KERNEL_TIMES = 2
+
+VERTEX_DTYPE = np.dtype([("pos", "<f4", 3), ("sec", "<f4", 4), ("nrm", "<f4", 3), ("tex", "u1", 8)])
+RECORD_DTYPE = np.dtype([("level", "<u4"), ("coord_id", "<u4"), ("id", "<u4"), ("vertex_count", "<u4"),
+                         ("index_count", "<u4"), ("vertex_offset", "<u4"), ("index_offset", "<u4"),
+                         ("trans_vertex_count", "<u4", 6), ("trans_index_count", "<u4", 6),
+                         ("trans_vertex_offset", "<u4", 6), ("trans_index_offset", "<u4", 6), ("reserved", "<u4")])
+assert VERTEX_DTYPE.itemsize == 48 and RECORD_DTYPE.itemsize == 128
+
+# what tests/harness.py calls a block row (the reference-facing view of a block)
+ROW_DTYPE = np.dtype([("id", "<u4"), ("min", "<f4", 3), ("max", "<f4", 3), ("nv", "<u4"), ("ni", "<u4"),
+                      ("tnv", "<u4", 6), ("tni", "<u4", 6)])
+
+
+class ResultInfo(C.Structure):
+    _fields_ = [("levels_total", C.c_uint32), ("levels_computed", C.c_uint32), ("block_count", C.c_uint32),
+                ("pad", C.c_uint32), ("vertex_span", C.c_uint64), ("index_span", C.c_uint64),
+                ("trans_vertex_span", C.c_uint64), ("trans_index_span", C.c_uint64), ("vertex_total", C.c_uint64),
+                ("index_total", C.c_uint64), ("trans_vertex_total", C.c_uint64), ("trans_index_total", C.c_uint64),
+                ("stats", C.c_uint32 * 20), ("used_materials", C.c_uint32 * 8), ("device_ms", C.c_float),
+                ("kernel_launches", C.c_uint32)]
+
+
+class VxbError(RuntimeError):
+    pass
+
+
+def library_path():
+    return os.path.join(_HERE, "lib", "libvxb200.so")
+
+
+_lib = None
+
+
+def load_library():
+    """Loads libvxb200.so; raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not os.path.exists(path):
+        raise VxbError("%s is missing - run `python -c 'import __graft_entry__ as g; g.build()'` (needs nvcc); "
+                       "there is no CPU fallback" % path)
+    L = C.CDLL(path)
+    vp, u32, u64 = C.c_void_p, C.c_uint32, C.c_uint64
+    sig = {
+        "vxb_create": (C.c_int, [C.c_int, C.POINTER(vp)]),
+        "vxb_destroy": (None, [vp]),
+        "vxb_last_error": (C.c_char_p, [vp]),
+        "vxb_stream": (vp, [vp]),
+        "vxb_grid_upload_dense": (C.c_int, [vp, u32, vp, vp, vp]),
+        "vxb_grid_upload_blocks": (C.c_int, [vp, u32, vp, vp, vp]),
+        "vxb_grid_set_device": (C.c_int, [vp, u32, vp, vp, vp]),
+        "vxb_grid_device_pointers": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),
+        "vxb_set_materials": (C.c_int, [vp, vp, vp]),
+        "vxb_polygonize": (C.c_int, [vp, u32, u32]),
+        "vxb_result_info_get": (C.c_int, [vp, C.POINTER(ResultInfo)]),
+        "vxb_result_download": (C.c_int, [vp, vp, vp, vp, vp, vp]),
+        "vxb_set_capacity": (C.c_int, [vp, u64, u64, u64, u64]),
+        "vxb_kernel_ms": (C.c_int, [vp, C.c_int, C.POINTER(C.c_float), C.POINTER(u32)]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)  # AttributeError = a symbol include/vxb200.h declares is not exported
+        fn.restype, fn.argtypes = res, args
+    _lib = L
+    return L
+
+
+EXPORTED_SYMBOLS = ["vxb_create", "vxb_destroy", "vxb_last_error", "vxb_stream", "vxb_grid_upload_dense",
+                    "vxb_grid_upload_blocks", "vxb_grid_set_device", "vxb_grid_device_pointers", "vxb_set_materials",
+                    "vxb_polygonize", "vxb_result_info_get", "vxb_result_download", "vxb_set_capacity", "vxb_kernel_ms"]
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class LevelView:
+    """One LOD level in the layout tests/harness.LevelDump uses (rows + concatenated arrays, block order)."""
+
+    def __init__(self, rows, verts, idx, tverts, tidx):
+        self.rows, self.verts, self.idx, self.tverts, self.tidx = rows, verts, idx, tverts, tidx
+
+
+class Result:
+    def __init__(self, n, info, records, verts, idx, tverts, tidx):
+        self.n, self.info, self.records = n, info, records
+        self.verts, self.idx, self.tverts, self.tidx = verts, idx, tverts, tidx
+        self.stats = np.array(list(info.stats), np.uint32)
+
+    def level(self, level):
+        recs = self.records[self.records["level"] == level]
+        m = 16 << level
+        nb = self.n // m
+        rows = np.zeros(len(recs), ROW_DTYPE)
+        cid = recs["coord_id"].astype(np.int64)
+        bx, by, bz = cid % nb, (cid // nb) % nb, cid // (nb * nb)
+        rows["id"] = recs["id"]
+        rows["min"] = np.stack([bx, bz, by], axis=1).astype(np.float32) * m  # y/z swapped on output
+        rows["max"] = rows["min"] + np.float32(m)
+        rows["nv"], rows["ni"] = recs["vertex_count"], recs["index_count"]
+        rows["tnv"], rows["tni"] = recs["trans_vertex_count"], recs["trans_index_count"]
+
+        def gather(arr, offs, counts):
+            parts = [arr[o:o + c] for o, c in zip(offs, counts) if c]
+            return np.concatenate(parts) if parts else arr[:0]
+
+        verts = gather(self.verts, recs["vertex_offset"], recs["vertex_count"])
+        idx = gather(self.idx, recs["index_offset"], recs["index_count"])
+        tverts = gather(self.tverts, recs["trans_vertex_offset"].ravel(), recs["trans_vertex_count"].ravel())
+        tidx = gather(self.tidx, recs["trans_index_offset"].ravel(), recs["trans_index_count"].ravel())
+        return LevelView(rows, verts, idx, tverts, tidx)
+
+
+class Context:
+    """vxb_context wrapper.  Raises VxbError on any failure (no CUDA device included)."""
+
+    def __init__(self, device=0):
+        self.L = load_library()
+        h = C.c_void_p()
+        rc = self.L.vxb_create(device, C.byref(h))
+        if rc != 0:
+            raise VxbError("vxb_create failed (%d): %s" % (rc, self.L.vxb_last_error(None).decode()))
+        self.h = h
+        self.n = 0
+        self._keep = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.vxb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise VxbError("%s failed (%d): %s" % (what, rc, self.L.vxb_last_error(self.h).decode()))
+
+    def upload_dense(self, dist, mat=None, blend=None):
+        """dist/mat/blend: host arrays (numpy or anything with .ctypes / an int address) indexed [z, y, x]."""
+        n = dist.shape[0]
+        self._check(self.L.vxb_grid_upload_dense(self.h, n, _ptr(dist), _ptr(mat), _ptr(blend)), "vxb_grid_upload_dense")
+        self.n = n
+
+    def upload_dense_ptr(self, n, dist_ptr, mat_ptr, blend_ptr):
+        self._check(self.L.vxb_grid_upload_dense(self.h, n, C.c_void_p(dist_ptr), C.c_void_p(mat_ptr), C.c_void_p(blend_ptr)),
+                    "vxb_grid_upload_dense")
+        self.n = n
+
+    def upload_blocks(self, n, dist_blocks, mat_blocks=None, blend_blocks=None):
+        self._check(self.L.vxb_grid_upload_blocks(self.h, n, _ptr(dist_blocks), _ptr(mat_blocks), _ptr(blend_blocks)),
+                    "vxb_grid_upload_blocks")
+        self.n = n
+
+    def set_device_grid(self, n, d_dist, d_mat, d_blend, keep=None):
+        """Device pointers (ints) of dense volumes that stay resident (e.g. torch tensors' data_ptr())."""
+        self._check(self.L.vxb_grid_set_device(self.h, n, C.c_void_p(d_dist), C.c_void_p(d_mat), C.c_void_p(d_blend)),
+                    "vxb_grid_set_device")
+        self.n = n
+        self._keep = keep
+
+    def set_materials(self, table=None, valid=None):
+        self._check(self.L.vxb_set_materials(self.h, _ptr(table), _ptr(valid)), "vxb_set_materials")
+
+    def set_capacity(self, vertices=0, indices=0, trans_vertices=0, trans_indices=0):
+        self._check(self.L.vxb_set_capacity(self.h, vertices, indices, trans_vertices, trans_indices), "vxb_set_capacity")
+
+    def polygonize(self, max_levels=0, flags=0):
+        self._check(self.L.vxb_polygonize(self.h, max_levels, flags), "vxb_polygonize")
+        return self.info()
+
+    def info(self):
+        info = ResultInfo()
+        self._check(self.L.vxb_result_info_get(self.h, C.byref(info)), "vxb_result_info_get")
+        return info
+
+    def kernel_ms(self, which):
+        ms, launches = C.c_float(0), C.c_uint32(0)
+        self._check(self.L.vxb_kernel_ms(self.h, which, C.byref(ms), C.byref(launches)), "vxb_kernel_ms")
+        return ms.value, launches.value
+
+    def download(self, into=None):
+        """Device -> host copy of the directory and the arenas.  `into` may supply preallocated (pinned) buffers:
+        dict with keys records/verts/idx/tverts/tidx holding int addresses."""
+        info = self.info()
+        records = np.zeros(info.block_count, RECORD_DTYPE)
+        if into is None:
+            verts = np.zeros(info.vertex_span, VERTEX_DTYPE); idx = np.zeros(info.index_span, np.uint32)
+            tverts = np.zeros(info.trans_vertex_span, VERTEX_DTYPE); tidx = np.zeros(info.trans_index_span, np.uint32)
+            self._check(self.L.vxb_result_download(self.h, _ptr(records), _ptr(verts), _ptr(idx), _ptr(tverts), _ptr(tidx)),
+                        "vxb_result_download")
+            return Result(self.n, info, records, verts, idx, tverts, tidx)
+        self._check(self.L.vxb_result_download(self.h, _ptr(records), C.c_void_p(into["verts"]), C.c_void_p(into["idx"]),
+                                               C.c_void_p(into["tverts"]), C.c_void_p(into["tidx"])), "vxb_result_download")
+        return Result(self.n, info, records, None, None, None, None)

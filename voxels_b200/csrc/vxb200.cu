@@ -1,0 +1,492 @@
+// libvxb200.so - host side of the C ABI declared in include/vxb200.h: context, device memory,
+// kernel launches (CUDA stream + events), result directory.  No CPU fallback: every entry point
+// needs a CUDA device.  Kernels live in vxb_kernels.cuh.
+#include <cuda_runtime.h>
+#include <cuda.h> // CUtensorMap types only; cuTensorMapEncodeTiled is resolved through the runtime (no libcuda link)
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/vxb200.h"
+
+#define VXB_TABLE_QUAL __constant__
+#include "vxb_tables_data.h"
+#include "vxb_cell.h"
+#include "vxb_kernels.cuh"
+
+static_assert(sizeof(VxbVertex) == 48, "PolygonVertex layout");
+static_assert(sizeof(vxb_block_record) == 128, "record layout");
+
+namespace
+{
+std::string g_createError;
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+	const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+template <typename T>
+struct DevBuf
+{
+	T* p = nullptr;
+	size_t count = 0;
+	cudaError_t ensure(size_t want)
+	{
+		if (want <= count) return cudaSuccess;
+		if (p) cudaFree(p);
+		p = nullptr; count = 0;
+		const cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&p), want * sizeof(T));
+		if (e == cudaSuccess) count = want;
+		return e;
+	}
+	void release() { if (p) cudaFree(p); p = nullptr; count = 0; }
+};
+}
+
+struct vxb_context
+{
+	int device = 0;
+	int smCount = 0;
+	cudaStream_t stream = nullptr;
+	cudaEvent_t evBegin = nullptr, evEnd = nullptr;
+	std::vector<cudaEvent_t> kevents; // per-kernel timing (pairs)
+	std::string error;
+	EncodeTiledFn encodeTiled = nullptr;
+
+	uint32_t n = 0;
+	int levels = 0;
+	bool haveGrid = false, ownsGrid = false;
+	const int8_t* dDist = nullptr; const uint8_t* dMat = nullptr; const uint8_t* dBlend = nullptr;
+	DevBuf<uint8_t> volDist, volMat, volBlend, staging;
+	DevBuf<unsigned int> scanFlags;
+	DevBuf<unsigned char> blockInfo;
+	DevBuf<unsigned int> consPages;
+	DevBuf<unsigned char> validFlags; // consValid + cacheValid[l] packed
+	DevBuf<unsigned short> cachePages;
+	DevBuf<unsigned int> worklist;
+	DevBuf<VxbVertex> verts, tverts;
+	DevBuf<unsigned int> idx, tidx;
+	DevBuf<vxb_block_record> records;
+	DevBuf<VxbCounters> counters;
+	DevBuf<VxbMaterialLut> lut;
+	uint64_t capV = 0, capI = 0, capTV = 0, capTI = 0;
+	CUtensorMap tmap;
+	int polyGrid0 = 0, polyGridN = 0;
+	size_t validBytes = 0;
+
+	bool haveResult = false;
+	vxb_result_info info;
+	std::vector<vxb_block_record> sortedRecords;
+	float kindMs[3] = { 0, 0, 0 };
+	uint32_t kindLaunches[3] = { 0, 0, 0 };
+};
+
+namespace
+{
+int fail(vxb_context* ctx, int code, const char* what, cudaError_t e = cudaSuccess)
+{
+	char buf[512];
+	if (e != cudaSuccess) snprintf(buf, sizeof(buf), "%s: %s", what, cudaGetErrorString(e));
+	else snprintf(buf, sizeof(buf), "%s", what);
+	if (ctx) ctx->error = buf; else g_createError = buf;
+	return code;
+}
+
+#define VXB_CUDA(ctx, call) do { const cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ctx, VXB_ERR_CUDA, #call, e_); } while (0)
+
+bool validSize(uint32_t n) { return n >= 16 && n <= 4096 && (n & (n - 1)) == 0; }
+
+int levelsFor(uint32_t n) { int l = 1; for (uint32_t v = n >> 4; v >>= 1;) ++l; return l; }
+
+const size_t kPolySmem = sizeof(VxbPolySmem);
+
+int ensureGridStorage(vxb_context* ctx, uint32_t n)
+{
+	const size_t vol = (size_t)n * n * n;
+	VXB_CUDA(ctx, ctx->volDist.ensure(vol));
+	VXB_CUDA(ctx, ctx->volMat.ensure(vol));
+	VXB_CUDA(ctx, ctx->volBlend.ensure(vol));
+	ctx->dDist = reinterpret_cast<const int8_t*>(ctx->volDist.p);
+	ctx->dMat = ctx->volMat.p; ctx->dBlend = ctx->volBlend.p;
+	ctx->n = n; ctx->levels = levelsFor(n);
+	ctx->ownsGrid = true; ctx->haveGrid = true; ctx->haveResult = false;
+	return VXB_OK;
+}
+
+int buildTensorMap(vxb_context* ctx)
+{
+	const cuuint64_t dims[3] = { ctx->n, ctx->n, ctx->n };
+	const cuuint64_t strides[2] = { ctx->n, (cuuint64_t)ctx->n * ctx->n };
+	const cuuint32_t box[3] = { VXB_TILE_PITCH, 17, 17 };
+	const cuuint32_t estr[3] = { 1, 1, 1 };
+	const CUresult r = ctx->encodeTiled(&ctx->tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<int8_t*>(ctx->dDist), dims, strides, box, estr,
+		CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	if (r != CUDA_SUCCESS)
+	{
+		char buf[128]; snprintf(buf, sizeof(buf), "cuTensorMapEncodeTiled failed: CUresult %d", (int)r);
+		return fail(ctx, VXB_ERR_CUDA, buf);
+	}
+	return VXB_OK;
+}
+
+size_t blocksAtLevel(uint32_t n, int level) { const size_t nb = (n / 16) >> level; return nb * nb * nb; }
+
+struct KernelTimer
+{
+	vxb_context* ctx; bool on; size_t used = 0;
+	std::vector<int> kinds;
+	void begin(int kind)
+	{
+		if (!on) return;
+		while (ctx->kevents.size() < used + 2) { cudaEvent_t e; cudaEventCreate(&e); ctx->kevents.push_back(e); }
+		cudaEventRecord(ctx->kevents[used], ctx->stream); kinds.push_back(kind);
+	}
+	void end() { if (!on) return; cudaEventRecord(ctx->kevents[used + 1], ctx->stream); used += 2; }
+	void collect()
+	{
+		for (int k = 0; k < 3; ++k) ctx->kindMs[k] = 0.f;
+		if (!on) return;
+		for (size_t i = 0; i < kinds.size(); ++i)
+		{
+			float ms = 0.f; cudaEventElapsedTime(&ms, ctx->kevents[2 * i], ctx->kevents[2 * i + 1]);
+			ctx->kindMs[kinds[i]] += ms;
+		}
+	}
+};
+}
+
+extern "C"
+{
+
+int vxb_create(int device, vxb_context** out)
+{
+	if (!out) return fail(nullptr, VXB_ERR_ARGUMENT, "vxb_create: out is null");
+	*out = nullptr;
+	int count = 0;
+	cudaError_t e = cudaGetDeviceCount(&count);
+	if (e != cudaSuccess || count == 0) return fail(nullptr, VXB_ERR_CUDA, "vxb_create: no CUDA device (this library has no CPU fallback)", e);
+	if (device < 0 || device >= count) return fail(nullptr, VXB_ERR_ARGUMENT, "vxb_create: bad device index");
+	e = cudaSetDevice(device);
+	if (e != cudaSuccess) return fail(nullptr, VXB_ERR_CUDA, "cudaSetDevice", e);
+	cudaDeviceProp prop;
+	e = cudaGetDeviceProperties(&prop, device);
+	if (e != cudaSuccess) return fail(nullptr, VXB_ERR_CUDA, "cudaGetDeviceProperties", e);
+	if (prop.major < 10) return fail(nullptr, VXB_ERR_CUDA, "vxb_create: the kernels are built for sm_100a (Blackwell) only");
+
+	vxb_context* ctx = new vxb_context;
+	ctx->device = device; ctx->smCount = prop.multiProcessorCount;
+	memset(&ctx->info, 0, sizeof(ctx->info));
+	if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+		(e = cudaEventCreate(&ctx->evBegin)) != cudaSuccess || (e = cudaEventCreate(&ctx->evEnd)) != cudaSuccess)
+	{ fail(nullptr, VXB_ERR_CUDA, "stream/event creation", e); delete ctx; return VXB_ERR_CUDA; }
+
+	void* fn = nullptr;
+	cudaDriverEntryPointQueryResult qres;
+	e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+	if (e != cudaSuccess || !fn) { fail(nullptr, VXB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available", e); delete ctx; return VXB_ERR_CUDA; }
+	ctx->encodeTiled = reinterpret_cast<EncodeTiledFn>(fn);
+
+	e = cudaFuncSetAttribute(vxb_polygonize_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPolySmem);
+	if (e == cudaSuccess) e = cudaFuncSetAttribute(vxb_polygonize_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPolySmem);
+	int occ0 = 0, occN = 0;
+	if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ0, vxb_polygonize_kernel<true>, VXB_THREADS, kPolySmem);
+	if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occN, vxb_polygonize_kernel<false>, VXB_THREADS, kPolySmem);
+	if (e != cudaSuccess || occ0 < 1 || occN < 1) { fail(nullptr, VXB_ERR_CUDA, "polygonize kernel cannot be made resident", e); delete ctx; return VXB_ERR_CUDA; }
+	ctx->polyGrid0 = occ0 * ctx->smCount; ctx->polyGridN = occN * ctx->smCount;
+
+	if (ctx->counters.ensure(1) != cudaSuccess || ctx->lut.ensure(1) != cudaSuccess) { fail(nullptr, VXB_ERR_CUDA, "cudaMalloc"); delete ctx; return VXB_ERR_CUDA; }
+	*out = ctx;
+	const int r = vxb_set_materials(ctx, nullptr, nullptr);
+	if (r != VXB_OK) { g_createError = ctx->error; vxb_destroy(ctx); *out = nullptr; return r; }
+	return VXB_OK;
+}
+
+void vxb_destroy(vxb_context* ctx)
+{
+	if (!ctx) return;
+	cudaSetDevice(ctx->device);
+	if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+	ctx->volDist.release(); ctx->volMat.release(); ctx->volBlend.release(); ctx->staging.release();
+	ctx->scanFlags.release(); ctx->blockInfo.release(); ctx->consPages.release(); ctx->validFlags.release();
+	ctx->cachePages.release(); ctx->worklist.release(); ctx->verts.release(); ctx->tverts.release();
+	ctx->idx.release(); ctx->tidx.release(); ctx->records.release(); ctx->counters.release(); ctx->lut.release();
+	for (cudaEvent_t e : ctx->kevents) cudaEventDestroy(e);
+	if (ctx->evBegin) cudaEventDestroy(ctx->evBegin);
+	if (ctx->evEnd) cudaEventDestroy(ctx->evEnd);
+	if (ctx->stream) cudaStreamDestroy(ctx->stream);
+	delete ctx;
+}
+
+const char* vxb_last_error(const vxb_context* ctx) { return ctx ? ctx->error.c_str() : g_createError.c_str(); }
+
+void* vxb_stream(vxb_context* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int vxb_grid_upload_dense(vxb_context* ctx, uint32_t n, const int8_t* dist, const uint8_t* mat, const uint8_t* blend)
+{
+	if (!ctx) return VXB_ERR_ARGUMENT;
+	if (!validSize(n) || !dist) return fail(ctx, VXB_ERR_ARGUMENT, "vxb_grid_upload_dense: n must be a power of two in [16, 4096] and dist non-null");
+	cudaSetDevice(ctx->device);
+	int r = ensureGridStorage(ctx, n);
+	if (r != VXB_OK) return r;
+	const size_t vol = (size_t)n * n * n;
+	VXB_CUDA(ctx, cudaMemcpyAsync(ctx->volDist.p, dist, vol, cudaMemcpyHostToDevice, ctx->stream));
+	if (mat) VXB_CUDA(ctx, cudaMemcpyAsync(ctx->volMat.p, mat, vol, cudaMemcpyHostToDevice, ctx->stream));
+	else VXB_CUDA(ctx, cudaMemsetAsync(ctx->volMat.p, 0, vol, ctx->stream));
+	if (blend) VXB_CUDA(ctx, cudaMemcpyAsync(ctx->volBlend.p, blend, vol, cudaMemcpyHostToDevice, ctx->stream));
+	else VXB_CUDA(ctx, cudaMemsetAsync(ctx->volBlend.p, 0, vol, ctx->stream));
+	VXB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	return buildTensorMap(ctx);
+}
+
+int vxb_grid_upload_blocks(vxb_context* ctx, uint32_t n, const int8_t* distBlocks, const uint8_t* matBlocks, const uint8_t* blendBlocks)
+{
+	if (!ctx) return VXB_ERR_ARGUMENT;
+	if (!validSize(n) || !distBlocks) return fail(ctx, VXB_ERR_ARGUMENT, "vxb_grid_upload_blocks: bad size or null dist");
+	cudaSetDevice(ctx->device);
+	int r = ensureGridStorage(ctx, n);
+	if (r != VXB_OK) return r;
+	const size_t vol = (size_t)n * n * n;
+	VXB_CUDA(ctx, ctx->staging.ensure(vol));
+	const unsigned blocks = (unsigned)(vol / 4096);
+	const void* src[3] = { distBlocks, matBlocks, blendBlocks };
+	uint8_t* dst[3] = { ctx->volDist.p, ctx->volMat.p, ctx->volBlend.p };
+	for (int c = 0; c < 3; ++c)
+	{
+		if (!src[c]) { VXB_CUDA(ctx, cudaMemsetAsync(dst[c], 0, vol, ctx->stream)); continue; }
+		VXB_CUDA(ctx, cudaMemcpyAsync(ctx->staging.p, src[c], vol, cudaMemcpyHostToDevice, ctx->stream));
+		vxb_unpack_blocks_kernel<<<blocks, VXB_THREADS, 0, ctx->stream>>>(reinterpret_cast<const uint4*>(ctx->staging.p), dst[c], (int)n);
+		VXB_CUDA(ctx, cudaGetLastError());
+	}
+	VXB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	return buildTensorMap(ctx);
+}
+
+int vxb_grid_set_device(vxb_context* ctx, uint32_t n, const int8_t* dDist, const uint8_t* dMat, const uint8_t* dBlend)
+{
+	if (!ctx) return VXB_ERR_ARGUMENT;
+	if (!validSize(n) || !dDist || !dMat || !dBlend) return fail(ctx, VXB_ERR_ARGUMENT, "vxb_grid_set_device: bad size or null pointer");
+	if ((reinterpret_cast<uintptr_t>(dDist) & 15) != 0) return fail(ctx, VXB_ERR_ARGUMENT, "vxb_grid_set_device: dist must be 16-byte aligned");
+	cudaSetDevice(ctx->device);
+	ctx->dDist = dDist; ctx->dMat = dMat; ctx->dBlend = dBlend;
+	ctx->n = n; ctx->levels = levelsFor(n);
+	ctx->ownsGrid = false; ctx->haveGrid = true; ctx->haveResult = false;
+	return buildTensorMap(ctx);
+}
+
+int vxb_grid_device_pointers(vxb_context* ctx, const int8_t** dDist, const uint8_t** dMat, const uint8_t** dBlend)
+{
+	if (!ctx || !ctx->haveGrid) return fail(ctx, VXB_ERR_STATE, "no grid");
+	if (dDist) *dDist = ctx->dDist;
+	if (dMat) *dMat = ctx->dMat;
+	if (dBlend) *dBlend = ctx->dBlend;
+	return VXB_OK;
+}
+
+int vxb_set_materials(vxb_context* ctx, const uint8_t* table, const uint8_t* valid)
+{
+	if (!ctx) return VXB_ERR_ARGUMENT;
+	cudaSetDevice(ctx->device);
+	VxbMaterialLut lut;
+	for (unsigned i = 0; i < 256; ++i)
+	{
+		unsigned d0[3], d1[3];
+		for (int k = 0; k < 3; ++k) { d0[k] = table ? table[i * 6 + k] : i; d1[k] = table ? table[i * 6 + 3 + k] : i; }
+		// byte order of PolygonVertex::Textures: Reserved, Blend, Uxz, Txz | Uny, Upy, Tny, Tpy  (TransVoxelImpl.cpp:1253-1261)
+		lut.tex0[i] = (d1[1] << 16) | (d0[1] << 24);
+		lut.tex1[i] = d1[2] | (d1[0] << 8) | (d0[2] << 16) | (d0[0] << 24);
+		lut.valid[i] = valid ? (valid[i] != 0) : 1;
+	}
+	VXB_CUDA(ctx, cudaMemcpy(ctx->lut.p, &lut, sizeof(lut), cudaMemcpyHostToDevice));
+	return VXB_OK;
+}
+
+int vxb_set_capacity(vxb_context* ctx, uint64_t v, uint64_t i, uint64_t tv, uint64_t ti)
+{
+	if (!ctx) return VXB_ERR_ARGUMENT;
+	if (v) ctx->capV = v;
+	if (i) ctx->capI = i;
+	if (tv) ctx->capTV = tv;
+	if (ti) ctx->capTI = ti;
+	return VXB_OK;
+}
+
+int vxb_polygonize(vxb_context* ctx, uint32_t maxLevels, uint32_t flags)
+{
+	if (!ctx) return VXB_ERR_ARGUMENT;
+	if (!ctx->haveGrid) return fail(ctx, VXB_ERR_STATE, "vxb_polygonize: no grid uploaded");
+	cudaSetDevice(ctx->device);
+	ctx->haveResult = false;
+	const uint32_t n = ctx->n;
+	const int levels = ctx->levels;
+	const int computed = (maxLevels == 0 || (int)maxLevels > levels) ? levels : (int)maxLevels;
+	const size_t nb0 = n / 16, blocks0 = nb0 * nb0 * nb0;
+	const bool kernelTimes = (flags & VXB_FLAG_KERNEL_TIMES) != 0;
+
+	// ---- device state ----
+	VXB_CUDA(ctx, ctx->scanFlags.ensure(blocks0));
+	VXB_CUDA(ctx, ctx->blockInfo.ensure(blocks0));
+	VXB_CUDA(ctx, ctx->consPages.ensure(blocks0 * 128));
+	size_t totalBlocks = 0, validBytes = 0, cacheEntries = 0;
+	size_t validOff[VXB_MAX_LEVELS], cacheOff[VXB_MAX_LEVELS];
+	VxbDev dev;
+	memset(&dev, 0, sizeof(dev));
+	for (int l = 0; l < levels; ++l)
+	{
+		const size_t b = blocksAtLevel(n, l);
+		dev.workBase[l] = (unsigned)totalBlocks;
+		dev.idBase[l] = (unsigned)totalBlocks;
+		totalBlocks += b;
+		validOff[l] = validBytes; validBytes += (b + 15) & ~(size_t)15;
+		cacheOff[l] = cacheEntries; if (l >= 1) cacheEntries += b * 4096;
+	}
+	VXB_CUDA(ctx, ctx->validFlags.ensure(validBytes));
+	VXB_CUDA(ctx, ctx->cachePages.ensure(cacheEntries ? cacheEntries : 1));
+	VXB_CUDA(ctx, ctx->worklist.ensure(totalBlocks));
+	VXB_CUDA(ctx, ctx->records.ensure(totalBlocks));
+
+	const uint64_t vol = (uint64_t)n * n * n;
+	if (!ctx->capV) ctx->capV = std::max<uint64_t>(1u << 20, vol / 24);
+	if (!ctx->capI) ctx->capI = ctx->capV * 6;
+	if (!ctx->capTV) ctx->capTV = std::max<uint64_t>(1u << 18, ctx->capV / 8);
+	if (!ctx->capTI) ctx->capTI = ctx->capTV * 6;
+
+	dev.grid.dist = ctx->dDist; dev.grid.mat = ctx->dMat; dev.grid.blend = ctx->dBlend; dev.grid.n = (int)n;
+	dev.n = (int)n; dev.levels = levels; dev.lastLevel = levels - 1;
+	dev.scanFlags = ctx->scanFlags.p; dev.blockInfo = ctx->blockInfo.p;
+	dev.consPages = ctx->consPages.p;
+	dev.consValid = ctx->validFlags.p + validOff[0];
+	for (int l = 1; l < levels; ++l) { dev.cachePages[l] = ctx->cachePages.p + cacheOff[l]; dev.cacheValid[l] = ctx->validFlags.p + validOff[l]; }
+	dev.worklist = ctx->worklist.p;
+	dev.records = ctx->records.p; dev.rcap = (unsigned)totalBlocks;
+	dev.counters = ctx->counters.p; dev.lut = ctx->lut.p;
+	dev.transitions = (flags & VXB_FLAG_NO_TRANSITIONS) ? 0 : 1;
+
+	VxbCounters hc;
+	for (int attempt = 0; attempt < 6; ++attempt)
+	{
+		const uint64_t lim = 0xFFFFFFF0ull;
+		ctx->capV = std::min(ctx->capV, lim); ctx->capI = std::min(ctx->capI, lim);
+		ctx->capTV = std::min(ctx->capTV, lim); ctx->capTI = std::min(ctx->capTI, lim);
+		VXB_CUDA(ctx, ctx->verts.ensure(ctx->capV));
+		VXB_CUDA(ctx, ctx->idx.ensure(ctx->capI));
+		VXB_CUDA(ctx, ctx->tverts.ensure(ctx->capTV));
+		VXB_CUDA(ctx, ctx->tidx.ensure(ctx->capTI));
+		dev.verts = ctx->verts.p; dev.idx = ctx->idx.p; dev.tverts = ctx->tverts.p; dev.tidx = ctx->tidx.p;
+		dev.vcap = (unsigned)ctx->capV; dev.icap = (unsigned)ctx->capI; dev.tvcap = (unsigned)ctx->capTV; dev.ticap = (unsigned)ctx->capTI;
+
+		KernelTimer timer{ ctx, kernelTimes };
+		uint32_t launches = 0;
+		for (int k = 0; k < 3; ++k) ctx->kindLaunches[k] = 0;
+		VXB_CUDA(ctx, cudaEventRecord(ctx->evBegin, ctx->stream));
+		VXB_CUDA(ctx, cudaMemsetAsync(ctx->counters.p, 0, sizeof(VxbCounters), ctx->stream));
+		VXB_CUDA(ctx, cudaMemsetAsync(ctx->validFlags.p, 0, validBytes, ctx->stream));
+
+		{
+			const dim3 grid((unsigned)((nb0 + 7) / 8), (unsigned)nb0, (unsigned)nb0);
+			timer.begin(0);
+			vxb_scan_kernel<<<grid, VXB_THREADS, 0, ctx->stream>>>(ctx->dDist, (int)n, ctx->scanFlags.p);
+			timer.end(); ++launches; ++ctx->kindLaunches[0];
+			const unsigned g2 = (unsigned)std::min<size_t>((blocks0 + 255) / 256, (size_t)ctx->smCount * 8);
+			timer.begin(1);
+			vxb_block_info_kernel<<<g2, 256, 0, ctx->stream>>>(ctx->dDist, (int)n, ctx->scanFlags.p, ctx->blockInfo.p);
+			timer.end(); ++launches; ++ctx->kindLaunches[1];
+		}
+		for (int l = 0; l < computed; ++l)
+		{
+			const size_t b = blocksAtLevel(n, l);
+			const unsigned gs = (unsigned)std::min<size_t>((b + 255) / 256, (size_t)ctx->smCount * 8);
+			timer.begin(1);
+			vxb_select_kernel<<<gs, 256, 0, ctx->stream>>>(dev, l);
+			timer.end(); ++launches; ++ctx->kindLaunches[1];
+			timer.begin(2);
+			if (l == 0)
+				vxb_polygonize_kernel<true><<<(unsigned)std::min<size_t>(b, ctx->polyGrid0), VXB_THREADS, kPolySmem, ctx->stream>>>(ctx->tmap, dev, l);
+			else
+				vxb_polygonize_kernel<false><<<(unsigned)std::min<size_t>(b, ctx->polyGridN), VXB_THREADS, kPolySmem, ctx->stream>>>(ctx->tmap, dev, l);
+			timer.end(); ++launches; ++ctx->kindLaunches[2];
+		}
+		VXB_CUDA(ctx, cudaGetLastError());
+		VXB_CUDA(ctx, cudaEventRecord(ctx->evEnd, ctx->stream));
+		VXB_CUDA(ctx, cudaMemcpyAsync(&hc, ctx->counters.p, sizeof(hc), cudaMemcpyDeviceToHost, ctx->stream));
+		VXB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		float ms = 0.f;
+		VXB_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->evBegin, ctx->evEnd));
+		timer.collect();
+		ctx->info.device_ms = ms;
+		ctx->info.kernel_launches = launches;
+
+		const bool overflow = hc.vertices > ctx->capV || hc.indices > ctx->capI || hc.transVertices > ctx->capTV || hc.transIndices > ctx->capTI;
+		if (!overflow) break;
+		if (attempt == 5) return fail(ctx, VXB_ERR_CAPACITY, "vxb_polygonize: output arenas overflowed after growing");
+		if (hc.vertices > ctx->capV) ctx->capV = (uint64_t)hc.vertices + hc.vertices / 8 + 1024;
+		if (hc.indices > ctx->capI) ctx->capI = (uint64_t)hc.indices + hc.indices / 8 + 1024;
+		if (hc.transVertices > ctx->capTV) ctx->capTV = (uint64_t)hc.transVertices + hc.transVertices / 8 + 1024;
+		if (hc.transIndices > ctx->capTI) ctx->capTI = (uint64_t)hc.transIndices + hc.transIndices / 8 + 1024;
+	}
+
+	// ---- directory: download + sort into the reference's block order (level, then z,y,x = coord id) ----
+	ctx->sortedRecords.resize(hc.records);
+	if (hc.records)
+		VXB_CUDA(ctx, cudaMemcpy(ctx->sortedRecords.data(), ctx->records.p, sizeof(vxb_block_record) * hc.records, cudaMemcpyDeviceToHost));
+	std::sort(ctx->sortedRecords.begin(), ctx->sortedRecords.end(), [](const vxb_block_record& a, const vxb_block_record& b) {
+		return a.level != b.level ? a.level < b.level : a.coord_id < b.coord_id; });
+
+	vxb_result_info& info = ctx->info;
+	info.levels_total = (uint32_t)levels; info.levels_computed = (uint32_t)computed;
+	info.block_count = hc.records; info.pad = 0;
+	info.vertex_span = hc.vertices; info.index_span = hc.indices;
+	info.trans_vertex_span = hc.transVertices; info.trans_index_span = hc.transIndices;
+	info.vertex_total = info.index_total = info.trans_vertex_total = info.trans_index_total = 0;
+	for (const vxb_block_record& r : ctx->sortedRecords)
+	{
+		info.vertex_total += r.vertex_count; info.index_total += r.index_count;
+		for (int f = 0; f < 6; ++f) { info.trans_vertex_total += r.trans_vertex_count[f]; info.trans_index_total += r.trans_index_count[f]; }
+	}
+	// statistics (TransVoxelImpl.cpp:528-531): BlocksCalculated counts every block of every computed level;
+	// TrivialCells only those of processed (not skipped) blocks
+	uint64_t blocksCalculated = 0, processedCells = (uint64_t)hc.nonSkippedLevel0 * 4096ull;
+	for (int l = 0; l < computed; ++l) { blocksCalculated += blocksAtLevel(n, l); if (l) processedCells += blocksAtLevel(n, l) * 4096ull; }
+	info.stats[0] = (uint32_t)blocksCalculated;
+	info.stats[1] = (uint32_t)(processedCells - hc.nonTrivial);
+	info.stats[2] = hc.nonTrivial;
+	info.stats[3] = hc.degenerate;
+	for (int i = 0; i < 16; ++i) info.stats[4 + i] = hc.perCase[i];
+	for (int i = 0; i < 8; ++i) info.used_materials[i] = hc.usedMaterials[i];
+	ctx->haveResult = true;
+	return VXB_OK;
+}
+
+int vxb_result_info_get(vxb_context* ctx, vxb_result_info* out)
+{
+	if (!ctx || !out) return VXB_ERR_ARGUMENT;
+	if (!ctx->haveResult) return fail(ctx, VXB_ERR_STATE, "no result: call vxb_polygonize first");
+	*out = ctx->info;
+	return VXB_OK;
+}
+
+int vxb_result_download(vxb_context* ctx, vxb_block_record* records, void* vertices, uint32_t* indices, void* transVertices, uint32_t* transIndices)
+{
+	if (!ctx) return VXB_ERR_ARGUMENT;
+	if (!ctx->haveResult) return fail(ctx, VXB_ERR_STATE, "no result: call vxb_polygonize first");
+	cudaSetDevice(ctx->device);
+	const vxb_result_info& info = ctx->info;
+	if (records && info.block_count) memcpy(records, ctx->sortedRecords.data(), sizeof(vxb_block_record) * info.block_count);
+	if (vertices && info.vertex_span) VXB_CUDA(ctx, cudaMemcpyAsync(vertices, ctx->verts.p, info.vertex_span * sizeof(VxbVertex), cudaMemcpyDeviceToHost, ctx->stream));
+	if (indices && info.index_span) VXB_CUDA(ctx, cudaMemcpyAsync(indices, ctx->idx.p, info.index_span * 4, cudaMemcpyDeviceToHost, ctx->stream));
+	if (transVertices && info.trans_vertex_span) VXB_CUDA(ctx, cudaMemcpyAsync(transVertices, ctx->tverts.p, info.trans_vertex_span * sizeof(VxbVertex), cudaMemcpyDeviceToHost, ctx->stream));
+	if (transIndices && info.trans_index_span) VXB_CUDA(ctx, cudaMemcpyAsync(transIndices, ctx->tidx.p, info.trans_index_span * 4, cudaMemcpyDeviceToHost, ctx->stream));
+	VXB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	return VXB_OK;
+}
+
+int vxb_kernel_ms(vxb_context* ctx, int which, float* ms, uint32_t* launches)
+{
+	if (!ctx || which < 0 || which > 2) return VXB_ERR_ARGUMENT;
+	if (ms) *ms = ctx->kindMs[which];
+	if (launches) *launches = ctx->kindLaunches[which];
+	return VXB_OK;
+}
+
+} // extern "C"
