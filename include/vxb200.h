@@ -118,6 +118,16 @@ int vxb_result_info_get(vxb_context* ctx, vxb_result_info* out);
 int vxb_result_download(vxb_context* ctx, vxb_block_record* records, void* vertices, uint32_t* indices,
 	void* trans_vertices, uint32_t* trans_indices);
 
+/* GetMaterial(id) == nullptr handling (TransVoxelImpl.cpp:1364-1368: textures stay zero, one LS_Error log per
+ * vertex): after vxb_result_download the material ids of those vertices, in the reference's logging order
+ * (level, block, regular vertices, then transition faces), can be read here.  Returns the count; copies at
+ * most `capacity` ids. */
+uint64_t vxb_result_unmapped_materials(vxb_context* ctx, uint8_t* ids, uint64_t capacity);
+
+/* Page-locked host memory for the upload/download buffers (plain cudaHostAlloc/cudaFreeHost). */
+void* vxb_host_alloc(size_t bytes);
+void vxb_host_free(void* p);
+
 /* Initial arena capacities in elements (0 = keep default).  Arenas grow and the run repeats
  * automatically on overflow; this only avoids the retry. */
 int vxb_set_capacity(vxb_context* ctx, uint64_t vertices, uint64_t indices, uint64_t trans_vertices, uint64_t trans_indices);

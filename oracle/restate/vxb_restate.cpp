@@ -234,7 +234,7 @@ void processBlock(Run& r, int level, int bx, int by, int bz, bool withTransition
 	if (!raw.empty())
 	{
 		ob.verts.resize(raw.size());
-		for (size_t i = 0; i < raw.size(); ++i) vxb_finish_vertex(raw[i], r.lut, ob.verts[i]);
+		for (size_t i = 0; i < raw.size(); ++i) { vxb_finish_vertex(raw[i], r.lut, ob.verts[i]); if (!r.lut.valid[raw[i].matId]) ob.verts[i].tex[0] = 0; } // unmapped material: textures stay zero (:1364-1368)
 		for (size_t i = 0; i + 2 < rawIdx.size(); i += 3)
 		{
 			if (vxb_triangle_kept(raw[rawIdx[i]].p, raw[rawIdx[i + 1]].p, raw[rawIdx[i + 2]].p))
@@ -323,7 +323,7 @@ void processBlock(Run& r, int level, int bx, int by, int bz, bool withTransition
 			}
 		}
 		ob.tverts[face].resize(traw.size());
-		for (size_t i = 0; i < traw.size(); ++i) vxb_finish_vertex(traw[i], r.lut, ob.tverts[face][i]);
+		for (size_t i = 0; i < traw.size(); ++i) { vxb_finish_vertex(traw[i], r.lut, ob.tverts[face][i]); if (!r.lut.valid[traw[i].matId]) ob.tverts[face][i].tex[0] = 0; }
 	}
 }
 

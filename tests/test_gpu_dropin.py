@@ -1,0 +1,70 @@
+"""The C++ drop-in (libvoxels_b200.so: Voxels::Polygonizer & co.) driven through the reference's own public API
+by the SAME harness source that drives the reference (tests/harness/vxh_capi.cpp), and compared with it."""
+import os
+
+import numpy as np
+import pytest
+
+import compare
+import grids
+import harness
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dropin():
+    if not os.path.exists(harness.B200_LIB):
+        pytest.fail("build/libvxh_b200.so is missing: the drop-in was not built (python -c 'import __graft_entry__ as g; g.build()')")
+    return harness.load(harness.B200_LIB)
+
+
+def both(reference, dropin, make_grid, **kw):
+    out = []
+    for lib in (reference, dropin):
+        g = make_grid(lib)
+        s, sec = lib.polygonize(g, **kw)
+        assert s, "Execute returned nullptr (%s)" % lib.path
+        levels = [lib.surface_level(s, l) for l in range(lib.surface_levels(s))]
+        out.append((levels, lib.surface_stats(s), lib.surface_extents(s), lib.L.vxh_surface_cache_bytes(s), lib.L.vxh_surface_polygon_bytes(s)))
+        lib.surface_destroy(s)
+        lib.grid_destroy(g)
+    return out
+
+
+def assert_same(a, b):
+    (la, sa, ea, ca, pa), (lb, sb, eb, cb, pb) = a, b
+    assert len(la) == len(lb)
+    problems = []
+    for l, (x, y) in enumerate(zip(la, lb)):
+        problems += compare.level_diff(x, y, "L%d" % l)
+    assert not problems, "\n".join(problems[:10])
+    assert np.array_equal(sa, sb), "statistics differ: %s vs %s" % (sa, sb)
+    assert np.array_equal(ea, eb)
+    assert ca == cb, "GetCacheSizeBytes %d vs %d" % (ca, cb)
+    assert pa == pb, "GetPolygonDataSizeBytes %d vs %d" % (pa, pb)
+
+
+def test_client_flow_sphere64(reference, dropin):
+    """BASELINE config 1: Grid::Create(64,64,64,...,&sphere) -> Polygonizer::Execute, exactly as a client would."""
+    a, b = both(reference, dropin, lambda lib: lib.grid_sphere(64, (32, 32, 32), 19.2))
+    assert_same(a, b)
+    assert a[1][0] == 73 and a[1][2] == 9096  # SURVEY.md 8(d) config 1 anchors: blocks calculated, non-trivial cells
+    assert len(a[0][0].verts) == 8832 and len(a[0][0].idx) == 41496
+
+
+@pytest.mark.parametrize("name", ["hostile64", "plane32", "noise32"])
+def test_dense_grids(reference, dropin, name):
+    dist, mat, blend = grids.SMALL[name]()
+    a, b = both(reference, dropin, lambda lib: lib.grid_from_dense(dist, mat, blend))
+    assert_same(a, b)
+
+
+def test_unmapped_material_logs_per_vertex(reference, dropin):
+    dist, mat, blend = grids.SMALL["hostile64"]()
+    valid = np.ones(256, np.uint8); valid[2] = 0
+    before = [lib.L.vxh_error_logs() for lib in (reference, dropin)]
+    a, b = both(reference, dropin, lambda lib: lib.grid_from_dense(dist, mat, blend), valid_mask=valid)
+    assert_same(a, b)
+    after = [lib.L.vxh_error_logs() for lib in (reference, dropin)]
+    assert after[0] - before[0] == after[1] - before[1] > 0  # one LS_Error per vertex with the unmapped material

@@ -66,6 +66,9 @@ def load_library():
         "vxb_result_download": (C.c_int, [vp, vp, vp, vp, vp, vp]),
         "vxb_set_capacity": (C.c_int, [vp, u64, u64, u64, u64]),
         "vxb_kernel_ms": (C.c_int, [vp, C.c_int, C.POINTER(C.c_float), C.POINTER(u32)]),
+        "vxb_result_unmapped_materials": (u64, [vp, vp, u64]),
+        "vxb_host_alloc": (vp, [C.c_size_t]),
+        "vxb_host_free": (None, [vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)  # AttributeError = a symbol include/vxb200.h declares is not exported
@@ -76,7 +79,8 @@ def load_library():
 
 EXPORTED_SYMBOLS = ["vxb_create", "vxb_destroy", "vxb_last_error", "vxb_stream", "vxb_grid_upload_dense",
                     "vxb_grid_upload_blocks", "vxb_grid_set_device", "vxb_grid_device_pointers", "vxb_set_materials",
-                    "vxb_polygonize", "vxb_result_info_get", "vxb_result_download", "vxb_set_capacity", "vxb_kernel_ms"]
+                    "vxb_polygonize", "vxb_result_info_get", "vxb_result_download", "vxb_set_capacity", "vxb_kernel_ms",
+                    "vxb_result_unmapped_materials", "vxb_host_alloc", "vxb_host_free"]
 
 
 def _ptr(a):
@@ -194,6 +198,13 @@ class Context:
         ms, launches = C.c_float(0), C.c_uint32(0)
         self._check(self.L.vxb_kernel_ms(self.h, which, C.byref(ms), C.byref(launches)), "vxb_kernel_ms")
         return ms.value, launches.value
+
+    def unmapped_materials(self):
+        n = self.L.vxb_result_unmapped_materials(self.h, None, 0)
+        out = np.zeros(n, np.uint8)
+        if n:
+            self.L.vxb_result_unmapped_materials(self.h, _ptr(out), n)
+        return out
 
     def download(self, into=None):
         """Device -> host copy of the directory and the arenas.  `into` may supply preallocated (pinned) buffers:

@@ -79,6 +79,8 @@ struct vxb_context
 	bool haveResult = false;
 	vxb_result_info info;
 	std::vector<vxb_block_record> sortedRecords;
+	uint8_t lutValid[256];
+	std::vector<uint8_t> unmapped; // material ids of vertices whose material had no mapping, in logging order
 	float kindMs[3] = { 0, 0, 0 };
 	uint32_t kindLaunches[3] = { 0, 0, 0 };
 };
@@ -299,6 +301,7 @@ int vxb_set_materials(vxb_context* ctx, const uint8_t* table, const uint8_t* val
 		lut.valid[i] = valid ? (valid[i] != 0) : 1;
 	}
 	VXB_CUDA(ctx, cudaMemcpy(ctx->lut.p, &lut, sizeof(lut), cudaMemcpyHostToDevice));
+	memcpy(ctx->lutValid, lut.valid, 256);
 	return VXB_OK;
 }
 
@@ -478,8 +481,44 @@ int vxb_result_download(vxb_context* ctx, vxb_block_record* records, void* verti
 	if (transVertices && info.trans_vertex_span) VXB_CUDA(ctx, cudaMemcpyAsync(transVertices, ctx->tverts.p, info.trans_vertex_span * sizeof(VxbVertex), cudaMemcpyDeviceToHost, ctx->stream));
 	if (transIndices && info.trans_index_span) VXB_CUDA(ctx, cudaMemcpyAsync(transIndices, ctx->tidx.p, info.trans_index_span * 4, cudaMemcpyDeviceToHost, ctx->stream));
 	VXB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+
+	// vertices of unmapped materials carry a marker (vxb_finish_vertex); restore the reference's all-zero textures
+	ctx->unmapped.clear();
+	bool anyUnmapped = false;
+	for (unsigned i = 0; i < 256; ++i) if (!ctx->lutValid[i] && ((info.used_materials[i >> 5] >> (i & 31)) & 1u)) anyUnmapped = true;
+	if (anyUnmapped)
+	{
+		auto fix = [&](void* base, uint64_t off, uint32_t count) {
+			if (!base) return;
+			VxbVertex* v = static_cast<VxbVertex*>(base) + off;
+			for (uint32_t i = 0; i < count; ++i)
+				if ((v[i].tex[0] & 0xFFu) == 0xFFu) { ctx->unmapped.push_back((uint8_t)(v[i].tex[0] >> 8)); v[i].tex[0] = 0; v[i].tex[1] = 0; }
+		};
+		for (const vxb_block_record& r : ctx->sortedRecords)
+		{
+			fix(vertices, r.vertex_offset, r.vertex_count);
+			for (int f = 0; f < 6; ++f) fix(transVertices, r.trans_vertex_offset[f], r.trans_vertex_count[f]);
+		}
+	}
 	return VXB_OK;
 }
+
+uint64_t vxb_result_unmapped_materials(vxb_context* ctx, uint8_t* ids, uint64_t capacity)
+{
+	if (!ctx) return 0;
+	const uint64_t n = ctx->unmapped.size();
+	if (ids) memcpy(ids, ctx->unmapped.data(), (size_t)std::min<uint64_t>(n, capacity));
+	return n;
+}
+
+void* vxb_host_alloc(size_t bytes)
+{
+	void* p = nullptr;
+	if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+	return p;
+}
+
+void vxb_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 int vxb_kernel_ms(vxb_context* ctx, int which, float* ms, uint32_t* launches)
 {

@@ -265,7 +265,8 @@ VXB_FN void vxb_finish_vertex(const VxbRawVertex& r, const VxbMaterialLut& lut, 
 #endif
 	o.nrm[0] = r.n[0]; o.nrm[1] = r.n[1]; o.nrm[2] = r.n[2];
 	if (lut.valid[r.matId]) { o.tex[0] = lut.tex0[r.matId] | (r.blend << 8); o.tex[1] = lut.tex1[r.matId]; }
-	else { o.tex[0] = 0; o.tex[1] = 0; } // GetMaterial returned null: textures stay value-initialised (:1364-1368)
+	else { o.tex[0] = 0xFFu | (r.matId << 8); o.tex[1] = 0; } // GetMaterial returned null (:1364-1368): marker {Reserved=0xFF, Blend=id};
+	                                                          // the host clears it to all-zero textures and logs (vxb_result_download)
 }
 
 // Degenerate-triangle test on the x256 positions (:1300-1321): keep iff |cross|^2 >= FLT_EPSILON.
