@@ -103,3 +103,96 @@ def test_repeatable(gpu_context):
     for l in range(a.info.levels_total):
         assert not compare.level_diff(a.level(l), b.level(l), "L%d" % l)
     assert np.array_equal(a.stats, b.stats)
+
+
+# ---- committed digests of the reference's output (tests/golden): no reference needed at run time ----------------
+import json
+import os
+
+import golden_hash
+
+
+def _golden():
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_hashes.json")) as f:
+        return json.load(f)["grids"]
+
+
+@pytest.mark.parametrize("name", sorted(list(grids.SMALL) + list(grids.MEDIUM)))
+def test_matches_golden_digests(gpu_context, name):
+    dist, mat, blend = (grids.SMALL.get(name) or grids.MEDIUM[name])()
+    want = _golden()[name]
+    assert golden_hash.input_digest(dist, mat, blend) == want["input_sha256"]
+    gpu_context.set_materials(None, None)
+    gpu_context.upload_dense(dist, mat, blend)
+    info = gpu_context.polygonize()
+    res = gpu_context.download()
+    assert [int(v) for v in res.stats] == want["stats"]
+    assert info.levels_total == len(want["levels"])
+    for l, w in enumerate(want["levels"]):
+        got = golden_hash.level_digests(res.level(l))
+        assert got["counts"] == w["counts"], "level %d counts" % l
+        assert got["exact"] == w["exact"], "level %d bit-exact fields" % l
+        assert got["normals"] == w["normals"], "level %d normals differ in bits (contract allows 1e-5, 0 ULP expected)" % l
+
+
+def test_terrain_256_against_reference(reference, gpu_context):
+    from voxels_b200 import synth
+    dist, mat, blend = (t.numpy() for t in synth.terrain(256))
+    problems, res = run_both(reference, gpu_context, dist, mat, blend)
+    assert not problems, "\n".join(problems[:10])
+
+
+def test_full_size_properties_1024(gpu_context):
+    """BASELINE full size (1024^3 terrain, all levels): size-independent properties, no oracle needed."""
+    import torch
+    from voxels_b200 import synth
+    n = 1024
+    dist, mat, blend = synth.terrain(n, "cuda:0")
+    torch.cuda.synchronize()
+    gpu_context.set_materials(None, None)
+    gpu_context.set_device_grid(n, dist.data_ptr(), mat.data_ptr(), blend.data_ptr(), keep=(dist, mat, blend))
+    info = gpu_context.polygonize()
+    res = gpu_context.download()
+    recs = res.records
+    assert info.levels_total == 7 and info.block_count == len(recs) > 1000
+    # directory is in the reference's order: level, then z,y,x
+    key = recs["level"].astype(np.int64) * (1 << 32) + recs["coord_id"]
+    assert np.all(np.diff(key) > 0)
+    # ids follow GenerateBlockListForLevel: running counter over all blocks of all lower levels + coord id
+    base = np.cumsum([0] + [((n // 16) >> l) ** 3 for l in range(7)])
+    assert np.array_equal(recs["id"], base[recs["level"]] + recs["coord_id"])
+    st = res.stats
+    assert st[0] == base[7]                                  # BlocksCalculated = every block of every level
+    assert st[4:].sum() == st[2]                             # per-class histogram sums to NonTrivialCells
+    assert (int(st[1]) + int(st[2])) % 4096 == 0            # whole blocks were classified
+    assert info.vertex_total == recs["vertex_count"].sum() and info.index_total == recs["index_count"].sum()
+    # every index addresses a vertex of its own block; every kept triangle passes the reference's degenerate test
+    rng = np.random.RandomState(1)
+    for i in rng.choice(len(recs), 200, replace=False):
+        r = recs[i]
+        v = res.verts[r["vertex_offset"]:r["vertex_offset"] + r["vertex_count"]]
+        ix = res.idx[r["index_offset"]:r["index_offset"] + r["index_count"]]
+        assert len(ix) % 3 == 0 and (len(ix) == 0 or ix.max() < len(v))
+        m = 16 << int(r["level"]); nb = n // m; c = int(r["coord_id"])
+        lo = np.array([c % nb, c // (nb * nb), (c // nb) % nb], np.float32) * m   # output axes: (x, z, y)
+        assert np.all(v["pos"] >= lo - 1e-3) and np.all(v["pos"] <= lo + m + 1e-3)
+        p = (v["pos"][:, [0, 2, 1]] * np.float32(256)).astype(np.float32)
+        a, b, cc = p[ix[0::3]], p[ix[1::3]], p[ix[2::3]]
+        cr = np.cross((b - a).astype(np.float32), (cc - a).astype(np.float32)).astype(np.float64)
+        assert np.all((cr ** 2).sum(axis=1) >= 1.1920928955078125e-07 * 0.5)
+        nl = np.linalg.norm(v["nrm"].astype(np.float64), axis=1)
+        assert np.all((np.abs(nl - 1) < 1e-5) | (nl == 0))
+        for f in range(6):
+            tv, ti = int(r["trans_vertex_count"][f]), int(r["trans_index_count"][f])
+            tix = res.tidx[r["trans_index_offset"][f]:r["trans_index_offset"][f] + ti]
+            assert ti % 3 == 0 and (ti == 0 or tix.max() < tv)
+    # idempotence: a second run gives the same bytes
+    gpu_context.polygonize()
+    res2 = gpu_context.download()
+    for l in range(7):
+        assert golden_hash.level_digests(res.level(l)) == golden_hash.level_digests(res2.level(l))
+    # level 0 alone (BASELINE config 2 shape) equals level 0 of the full run
+    import voxels_b200
+    gpu_context.polygonize(1, voxels_b200.FLAG_NO_TRANSITIONS)
+    res3 = gpu_context.download()
+    assert golden_hash.level_digests(res.level(0)) == golden_hash.level_digests(res3.level(0))
