@@ -132,9 +132,10 @@ void vxb_host_free(void* p);
  * automatically on overflow; this only avoids the retry. */
 int vxb_set_capacity(vxb_context* ctx, uint64_t vertices, uint64_t indices, uint64_t trans_vertices, uint64_t trans_indices);
 
-/* Per-kernel device time of the last vxb_polygonize, for bench.py's roofline line:
- * which = 0: grid scan (streams the level-0 distance volume once), 1: block selection,
- * 2: block polygonization (all levels).  Milliseconds, summed over launches of that kind. */
+/* Per-kernel device time of the last vxb_polygonize run with VXB_FLAG_KERNEL_TIMES, for bench.py's roofline line:
+ * which = 0: vxb_scan_kernel (streams the level-0 distance volume once), 1: block info + selection kernels,
+ * 2: vxb_classify_kernel (one launch per level), 3: vxb_emit_kernel (all levels, one launch),
+ * 4: overflow tiers (big emit + generic kernel).  Milliseconds, summed over launches of that kind. */
 int vxb_kernel_ms(vxb_context* ctx, int which, float* ms, uint32_t* launches);
 
 #ifdef __cplusplus

@@ -12,10 +12,21 @@
 
 #include "../../include/vxb200.h"
 
+// the Transvoxel tables twice: __constant__ (generic kernel, uniform-ish reads) and plain global memory
+// (vxbG*: divergent per-thread lookups go through L1 instead of serialising in the constant cache)
 #define VXB_TABLE_QUAL __constant__
+#include "vxb_tables_data.h"
+#undef VXB_TABLE_QUAL
+#undef VXB_TABLE_NAME
+#define VXB_TABLE_QUAL __device__
+#define VXB_TABLE_NAME(x) vxbG##x
 #include "vxb_tables_data.h"
 #include "vxb_cell.h"
 #include "vxb_kernels.cuh"
+#include "vxb_emit.cuh"
+
+typedef VxbEmitSmem<1024, 3072> VxbEmitSmemSmall;
+typedef VxbEmitSmem<4096, 12288> VxbEmitSmemBig;
 
 static_assert(sizeof(VxbVertex) == 48, "PolygonVertex layout");
 static_assert(sizeof(vxb_block_record) == 128, "record layout");
@@ -65,7 +76,7 @@ struct vxb_context
 	DevBuf<unsigned int> consPages;
 	DevBuf<unsigned char> validFlags; // consValid + cacheValid[l] packed
 	DevBuf<unsigned short> cachePages;
-	DevBuf<unsigned int> worklist;
+	DevBuf<unsigned int> worklist, emitList, bigList, genList, ntScratch;
 	DevBuf<VxbVertex> verts, tverts;
 	DevBuf<unsigned int> idx, tidx;
 	DevBuf<vxb_block_record> records;
@@ -73,7 +84,7 @@ struct vxb_context
 	DevBuf<VxbMaterialLut> lut;
 	uint64_t capV = 0, capI = 0, capTV = 0, capTI = 0;
 	CUtensorMap tmap;
-	int polyGrid0 = 0, polyGridN = 0;
+	int gridClassify = 0, gridEmitSmall = 0, gridEmitBig = 0, gridGeneric = 0;
 	size_t validBytes = 0;
 
 	bool haveResult = false;
@@ -81,8 +92,8 @@ struct vxb_context
 	std::vector<vxb_block_record> sortedRecords;
 	uint8_t lutValid[256];
 	std::vector<uint8_t> unmapped; // material ids of vertices whose material had no mapping, in logging order
-	float kindMs[3] = { 0, 0, 0 };
-	uint32_t kindLaunches[3] = { 0, 0, 0 };
+	float kindMs[5] = { 0, 0, 0, 0, 0 };
+	uint32_t kindLaunches[5] = { 0, 0, 0, 0, 0 };
 };
 
 namespace
@@ -148,7 +159,7 @@ struct KernelTimer
 	void end() { if (!on) return; cudaEventRecord(ctx->kevents[used + 1], ctx->stream); used += 2; }
 	void collect()
 	{
-		for (int k = 0; k < 3; ++k) ctx->kindMs[k] = 0.f;
+		for (int k = 0; k < 5; ++k) ctx->kindMs[k] = 0.f;
 		if (!on) return;
 		for (size_t i = 0; i < kinds.size(); ++i)
 		{
@@ -190,13 +201,21 @@ int vxb_create(int device, vxb_context** out)
 	if (e != cudaSuccess || !fn) { fail(nullptr, VXB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available", e); delete ctx; return VXB_ERR_CUDA; }
 	ctx->encodeTiled = reinterpret_cast<EncodeTiledFn>(fn);
 
-	e = cudaFuncSetAttribute(vxb_polygonize_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPolySmem);
-	if (e == cudaSuccess) e = cudaFuncSetAttribute(vxb_polygonize_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPolySmem);
-	int occ0 = 0, occN = 0;
-	if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ0, vxb_polygonize_kernel<true>, VXB_THREADS, kPolySmem);
-	if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occN, vxb_polygonize_kernel<false>, VXB_THREADS, kPolySmem);
-	if (e != cudaSuccess || occ0 < 1 || occN < 1) { fail(nullptr, VXB_ERR_CUDA, "polygonize kernel cannot be made resident", e); delete ctx; return VXB_ERR_CUDA; }
-	ctx->polyGrid0 = occ0 * ctx->smCount; ctx->polyGridN = occN * ctx->smCount;
+	struct KernelSetup { const void* fn; size_t smem; int* grid; const char* name; };
+	const KernelSetup setups[4] = {
+		{ (const void*)vxb_classify_kernel, sizeof(VxbClassifySmem), &ctx->gridClassify, "vxb_classify_kernel" },
+		{ (const void*)vxb_emit_kernel<1024, 3072, 0>, sizeof(VxbEmitSmemSmall), &ctx->gridEmitSmall, "vxb_emit_kernel<small>" },
+		{ (const void*)vxb_emit_kernel<4096, 12288, 1>, sizeof(VxbEmitSmemBig), &ctx->gridEmitBig, "vxb_emit_kernel<big>" },
+		{ (const void*)vxb_generic_kernel, kPolySmem, &ctx->gridGeneric, "vxb_generic_kernel" },
+	};
+	for (const KernelSetup& k : setups)
+	{
+		int occ = 0;
+		e = cudaFuncSetAttribute(k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k.smem);
+		if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k.fn, VXB_THREADS, k.smem);
+		if (e != cudaSuccess || occ < 1) { fail(nullptr, VXB_ERR_CUDA, k.name, e); delete ctx; return VXB_ERR_CUDA; }
+		*k.grid = occ * ctx->smCount;
+	}
 
 	if (ctx->counters.ensure(1) != cudaSuccess || ctx->lut.ensure(1) != cudaSuccess) { fail(nullptr, VXB_ERR_CUDA, "cudaMalloc"); delete ctx; return VXB_ERR_CUDA; }
 	*out = ctx;
@@ -212,7 +231,7 @@ void vxb_destroy(vxb_context* ctx)
 	if (ctx->stream) cudaStreamSynchronize(ctx->stream);
 	ctx->volDist.release(); ctx->volMat.release(); ctx->volBlend.release(); ctx->staging.release();
 	ctx->scanFlags.release(); ctx->blockInfo.release(); ctx->consPages.release(); ctx->validFlags.release();
-	ctx->cachePages.release(); ctx->worklist.release(); ctx->verts.release(); ctx->tverts.release();
+	ctx->cachePages.release(); ctx->worklist.release(); ctx->emitList.release(); ctx->bigList.release(); ctx->genList.release(); ctx->ntScratch.release(); ctx->verts.release(); ctx->tverts.release();
 	ctx->idx.release(); ctx->tidx.release(); ctx->records.release(); ctx->counters.release(); ctx->lut.release();
 	for (cudaEvent_t e : ctx->kevents) cudaEventDestroy(e);
 	if (ctx->evBegin) cudaEventDestroy(ctx->evBegin);
@@ -348,6 +367,10 @@ int vxb_polygonize(vxb_context* ctx, uint32_t maxLevels, uint32_t flags)
 	VXB_CUDA(ctx, ctx->cachePages.ensure(cacheEntries ? cacheEntries : 1));
 	VXB_CUDA(ctx, ctx->worklist.ensure(totalBlocks));
 	VXB_CUDA(ctx, ctx->records.ensure(totalBlocks));
+	VXB_CUDA(ctx, ctx->emitList.ensure(totalBlocks));
+	VXB_CUDA(ctx, ctx->bigList.ensure(totalBlocks));
+	VXB_CUDA(ctx, ctx->genList.ensure(totalBlocks));
+	VXB_CUDA(ctx, ctx->ntScratch.ensure(totalBlocks * 128));
 
 	const uint64_t vol = (uint64_t)n * n * n;
 	if (!ctx->capV) ctx->capV = std::max<uint64_t>(1u << 20, vol / 24);
@@ -365,6 +388,7 @@ int vxb_polygonize(vxb_context* ctx, uint32_t maxLevels, uint32_t flags)
 	dev.records = ctx->records.p; dev.rcap = (unsigned)totalBlocks;
 	dev.counters = ctx->counters.p; dev.lut = ctx->lut.p;
 	dev.transitions = (flags & VXB_FLAG_NO_TRANSITIONS) ? 0 : 1;
+	dev.emitList = ctx->emitList.p; dev.bigList = ctx->bigList.p; dev.genList = ctx->genList.p; dev.ntScratch = ctx->ntScratch.p;
 
 	VxbCounters hc;
 	for (int attempt = 0; attempt < 6; ++attempt)
@@ -381,7 +405,7 @@ int vxb_polygonize(vxb_context* ctx, uint32_t maxLevels, uint32_t flags)
 
 		KernelTimer timer{ ctx, kernelTimes };
 		uint32_t launches = 0;
-		for (int k = 0; k < 3; ++k) ctx->kindLaunches[k] = 0;
+		for (int k = 0; k < 5; ++k) ctx->kindLaunches[k] = 0;
 		VXB_CUDA(ctx, cudaEventRecord(ctx->evBegin, ctx->stream));
 		VXB_CUDA(ctx, cudaMemsetAsync(ctx->counters.p, 0, sizeof(VxbCounters), ctx->stream));
 		VXB_CUDA(ctx, cudaMemsetAsync(ctx->validFlags.p, 0, validBytes, ctx->stream));
@@ -404,12 +428,17 @@ int vxb_polygonize(vxb_context* ctx, uint32_t maxLevels, uint32_t flags)
 			vxb_select_kernel<<<gs, 256, 0, ctx->stream>>>(dev, l);
 			timer.end(); ++launches; ++ctx->kindLaunches[1];
 			timer.begin(2);
-			if (l == 0)
-				vxb_polygonize_kernel<true><<<(unsigned)std::min<size_t>(b, ctx->polyGrid0), VXB_THREADS, kPolySmem, ctx->stream>>>(ctx->tmap, dev, l);
-			else
-				vxb_polygonize_kernel<false><<<(unsigned)std::min<size_t>(b, ctx->polyGridN), VXB_THREADS, kPolySmem, ctx->stream>>>(ctx->tmap, dev, l);
+			vxb_classify_kernel<<<(unsigned)std::min<size_t>(b, ctx->gridClassify), VXB_THREADS, sizeof(VxbClassifySmem), ctx->stream>>>(ctx->tmap, dev, l);
 			timer.end(); ++launches; ++ctx->kindLaunches[2];
 		}
+		// emission of ALL computed levels in one launch (largest blocks first), then the two overflow tiers
+		timer.begin(3);
+		vxb_emit_kernel<1024, 3072, 0><<<ctx->gridEmitSmall, VXB_THREADS, sizeof(VxbEmitSmemSmall), ctx->stream>>>(ctx->tmap, dev);
+		timer.end(); ++launches; ++ctx->kindLaunches[3];
+		timer.begin(4);
+		vxb_emit_kernel<4096, 12288, 1><<<ctx->gridEmitBig, VXB_THREADS, sizeof(VxbEmitSmemBig), ctx->stream>>>(ctx->tmap, dev);
+		vxb_generic_kernel<<<ctx->gridGeneric, VXB_THREADS, kPolySmem, ctx->stream>>>(ctx->tmap, dev);
+		timer.end(); launches += 2; ctx->kindLaunches[4] += 2;
 		VXB_CUDA(ctx, cudaGetLastError());
 		VXB_CUDA(ctx, cudaEventRecord(ctx->evEnd, ctx->stream));
 		VXB_CUDA(ctx, cudaMemcpyAsync(&hc, ctx->counters.p, sizeof(hc), cudaMemcpyDeviceToHost, ctx->stream));
@@ -522,7 +551,7 @@ void vxb_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 int vxb_kernel_ms(vxb_context* ctx, int which, float* ms, uint32_t* launches)
 {
-	if (!ctx || which < 0 || which > 2) return VXB_ERR_ARGUMENT;
+	if (!ctx || which < 0 || which > 4) return VXB_ERR_ARGUMENT;
 	if (ms) *ms = ctx->kindMs[which];
 	if (launches) *launches = ctx->kindLaunches[which];
 	return VXB_OK;

@@ -88,10 +88,31 @@ VXB_FN void vxb_normalize_fix_zero(float& x, float& y, float& z)
 // may lie at coordinate n); the result is already in output (Y-up) axes: (d/dx, d/dz, d/dy).
 VXB_FN void vxb_normal(const VxbGrid& g, int x, int y, int z, float n[3])
 {
-	n[0] = (float)(vxb_dist(g, x + 1, y, z) - vxb_dist(g, x - 1, y, z)) * 0.5f;
-	n[1] = (float)(vxb_dist(g, x, y, z + 1) - vxb_dist(g, x, y, z - 1)) * 0.5f;
-	n[2] = (float)(vxb_dist(g, x, y + 1, z) - vxb_dist(g, x, y - 1, z)) * 0.5f;
+	const int m = g.n - 1;
+	const size_t nn = (size_t)g.n;
+	const size_t x0 = (size_t)vxb_clampi(x - 1, 0, m), x1 = (size_t)vxb_clampi(x, 0, m), x2 = (size_t)vxb_clampi(x + 1, 0, m);
+	const size_t y0 = (size_t)vxb_clampi(y - 1, 0, m) * nn, y1 = (size_t)vxb_clampi(y, 0, m) * nn, y2 = (size_t)vxb_clampi(y + 1, 0, m) * nn;
+	const size_t z0 = (size_t)vxb_clampi(z - 1, 0, m) * nn * nn, z1 = (size_t)vxb_clampi(z, 0, m) * nn * nn, z2 = (size_t)vxb_clampi(z + 1, 0, m) * nn * nn;
+	const signed char* d = g.dist;
+	const int ax = d[z1 + y1 + x2], bx = d[z1 + y1 + x0];
+	const int az = d[z2 + y1 + x1], bz = d[z0 + y1 + x1];
+	const int ay = d[z1 + y2 + x1], by = d[z1 + y0 + x1];
+	n[0] = (float)(ax - bx) * 0.5f;
+	n[1] = (float)(az - bz) * 0.5f;
+	n[2] = (float)(ay - by) * 0.5f;
 	vxb_normalize_fix_zero(n[0], n[1], n[2]);
+}
+
+// (b * 256) / (b - a), C integer division (:1591, :1674, :1942, :2025), for int8 samples with b != a.
+// Device: one IEEE float division.  Exact: |b*256| <= 2^15 and |b-a| <= 255, so a non-integer quotient is at
+// least 1/255 away from the next integer while the float result is within 2^-10 of it - truncation cannot flip.
+VXB_FN int vxb_fixed_t(int a, int b)
+{
+#if defined(__CUDA_ARCH__)
+	return __float2int_rz(__fdiv_rn((float)(b * 256), (float)(b - a)));
+#else
+	return (b * 256) / (b - a);
+#endif
 }
 
 // FindBestVertexInLODChain :1484-1509 followed by the t recomputation :1671-1678 / :2022-2029.
@@ -107,7 +128,7 @@ VXB_FN int vxb_lod_descent(const VxbGrid& g, int steps, int p0[3], int p1[3])
 	}
 	const int a = vxb_dist(g, p0[0], p0[1], p0[2]);
 	const int b = vxb_dist(g, p1[0], p1[1], p1[2]);
-	return (a != b) ? (b * 256) / (b - a) : 0;
+	return (a != b) ? vxb_fixed_t(a, b) : 0;
 }
 
 // out-of-range float -> unsigned char the way x86 does it (cvttss2si, low byte) :1699, :2085
@@ -152,23 +173,43 @@ struct VxbVertexDesc
 	bool atC7;     // endpoint at corner 7: never reused, owns slot 0 (:1597, :1653)
 };
 
-VXB_FN VxbVertexDesc vxb_regular_vertex_desc(unsigned vd, const signed char v[8])
+// zero mask of a cell: bit i = (sample i == 0).  A table vertex lies on an edge endpoint iff one of the edge's two
+// samples is 0: t = 256*b/(b-a) with exactly one of a,b negative is 0 iff b == 0 and 256 iff a == 0 (|b| <= |b-a| < 256),
+// so the endpoint logic of :1594-1608 needs no division.
+VXB_FN unsigned vxb_zero_mask(const signed char v[8])
+{
+	unsigned z = 0;
+#pragma unroll
+	for (int i = 0; i < 8; ++i) z |= (v[i] == 0 ? 1u : 0u) << i;
+	return z;
+}
+
+// descriptor without the interpolation parameter (d.t is only valid as 0 / 256 for endpoints, -1 otherwise)
+VXB_FN VxbVertexDesc vxb_regular_vertex_desc_lite(unsigned vd, unsigned zeroMask)
 {
 	VxbVertexDesc d;
 	d.v0 = (vd >> 4) & 0xF;
 	d.v1 = vd & 0xF;
 	d.dir = (vd >> 12) & 0xF;
 	d.slot = (vd >> 8) & 0xF;
-	const int a = v[d.v0], b = v[d.v1];
-	d.t = (b * 256) / (b - a);
-	d.endpoint = (d.t & 0xFF) == 0;
+	const bool z0 = (zeroMask >> d.v0) & 1u, z1 = (zeroMask >> d.v1) & 1u;
+	d.endpoint = z0 || z1;
 	d.atC7 = false;
+	d.t = -1;
 	if (d.endpoint)
 	{
-		d.atC7 = (d.t == 0 && d.v1 == 7);
-		if (!d.atC7) d.dir = ((d.t == 0) ? d.v1 : d.v0) ^ 7;
+		d.t = z1 ? 0 : 256;
+		d.atC7 = (z1 && d.v1 == 7);
+		if (!d.atC7) d.dir = (z1 ? d.v1 : d.v0) ^ 7;
 		d.slot = 0;
 	}
+	return d;
+}
+
+VXB_FN VxbVertexDesc vxb_regular_vertex_desc(unsigned vd, const signed char v[8])
+{
+	VxbVertexDesc d = vxb_regular_vertex_desc_lite(vd, vxb_zero_mask(v));
+	if (!d.endpoint) d.t = vxb_fixed_t(v[d.v0], v[d.v1]); // :1591
 	return d;
 }
 
@@ -380,14 +421,15 @@ VXB_FN VxbTransVertexDesc vxb_transition_vertex_desc(unsigned vd, const signed c
 	d.dir = (vd >> 12) & 0xF;
 	d.slot = (vd >> 8) & 0xF;
 	const int a = v[d.v0], b = v[d.v1];
-	d.t = (b * 256) / (b - a);
-	d.endpoint = (d.t & 0xFF) == 0;
+	d.endpoint = (a == 0) || (b == 0); // t in {0, 256}, see vxb_zero_mask
 	if (d.endpoint)
 	{
-		const int corner = (d.t == 0) ? d.v1 : d.v0;
+		d.t = (b == 0) ? 0 : 256;
+		const int corner = (b == 0) ? d.v1 : d.v0;
 		d.dir = cornerData[corner] >> 4;
 		d.slot = cornerData[corner] & 0xF;
 	}
+	else d.t = vxb_fixed_t(a, b); // :1942
 	return d;
 }
 

@@ -39,6 +39,10 @@ struct VxbCounters
 	unsigned int usedMaterials[8];
 	unsigned int workCount[VXB_MAX_LEVELS];
 	unsigned int workCursor[VXB_MAX_LEVELS];
+	unsigned int emitCount[VXB_MAX_LEVELS]; // blocks with non-trivial cells, per level (vxb_classify_kernel)
+	unsigned int emitCursor;
+	unsigned int bigCount, bigCursor;       // rejected by the small emit tier
+	unsigned int genCount, genCursor;       // rejected by the big emit tier -> generic kernel
 };
 
 struct VxbDev
@@ -60,6 +64,10 @@ struct VxbDev
 	VxbCounters* counters;
 	const VxbMaterialLut* lut;
 	int transitions;
+	unsigned int* emitList;   // [workBase[l] + i] = level<<28 | coordId
+	unsigned int* ntScratch;  // 128 words of non-trivial bits per emit-list entry
+	unsigned int* bigList;    // emit-list indices
+	unsigned int* genList;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -317,6 +325,39 @@ __global__ void vxb_select_kernel(VxbDev d, int level)
 // ------------------------------------------------------------------------------------------------
 // K3: polygonize
 // ------------------------------------------------------------------------------------------------
+// stage the 17^3 sample tile of block (bx,by,bz) at `level` into smem (TMA for level 0, clamped strided gather above)
+__device__ __forceinline__ void vxb_stage_tile(signed char* tile, unsigned long long* mbar, unsigned& phase, const CUtensorMap* tmap,
+	const VxbGrid& g, int n, int level, int bx, int by, int bz)
+{
+	const int tid = threadIdx.x;
+	const int m = 1 << level, nb = n / 16 / m;
+	if (level == 0)
+	{
+		if (tid == 0)
+		{
+			vxb_fence_proxy_async();
+			vxb_mbar_expect_tx(mbar, VXB_TILE_BYTES);
+			vxb_tma_load_3d(tile, tmap, bx * 16, by * 16, bz * 16, mbar);
+		}
+		vxb_mbar_wait(mbar, phase);
+		phase ^= 1;
+		// far grid edge: the +1 plane is outside the volume (TMA zero-fills); the reference clamps (:1037-1047)
+		if (bx == nb - 1) { __syncthreads(); for (int i = tid; i < 17 * 17; i += VXB_THREADS) tile[i * VXB_TILE_PITCH + 16] = tile[i * VXB_TILE_PITCH + 15]; }
+		if (by == nb - 1) { __syncthreads(); for (int i = tid; i < 17 * 17; i += VXB_THREADS) { const int z = i / 17, x = i % 17; tile[(z * 17 + 16) * VXB_TILE_PITCH + x] = tile[(z * 17 + 15) * VXB_TILE_PITCH + x]; } }
+		if (bz == nb - 1) { __syncthreads(); for (int i = tid; i < 17 * 17; i += VXB_THREADS) { const int y = i / 17, x = i % 17; tile[(16 * 17 + y) * VXB_TILE_PITCH + x] = tile[(15 * 17 + y) * VXB_TILE_PITCH + x]; } }
+	}
+	else
+	{
+		const int lim = n - 1;
+		for (int i = tid; i < 17 * 17 * 17; i += VXB_THREADS)
+		{
+			const int x = i % 17, y = (i / 17) % 17, z = i / 289;
+			const int gx = min((bx * 16 + x) * m, lim), gy = min((by * 16 + y) * m, lim), gz = min((bz * 16 + z) * m, lim);
+			tile[(z * 17 + y) * VXB_TILE_PITCH + x] = g.dist[((size_t)gz * n + gy) * n + gx];
+		}
+	}
+}
+
 struct __align__(128) VxbPolySmem
 {
 	signed char tile[VXB_TILE_BYTES + 96]; // 17 x 17 rows of 32 bytes; [z][y][x]
@@ -356,33 +397,51 @@ __device__ __forceinline__ void vxb_cell_samples(const VxbPolySmem& s, int c, si
 	v[4] = p[0]; v[5] = p[1]; v[6] = p[VXB_TILE_PITCH]; v[7] = p[VXB_TILE_PITCH + 1];
 }
 
-// CalculateMaterialForCellCache :753-838 for level >= 1, children read through the page tables
+// CalculateMaterialForCellCache :753-838 for level >= 1, children read through the page tables.
+// The 8 children of a cell share one block of the child level (cell bases are even in child units), so the block
+// lookup and the validity test happen once, and the common all-empty case exits after 4 loads.
 __device__ __forceinline__ bool vxb_vote_cell(const VxbDev& d, int level, const int base[3], unsigned& id, unsigned& blend)
 {
-	const int cm = (1 << level) >> 1, cnb = d.n / 16 / cm, ext = 16 * cm;
+	const int cm = (1 << level) >> 1, cnb = d.n / 16 / cm;
+	const int cx = base[0] / cm, cy = base[1] / cm, cz = base[2] / cm;            // child-level cell coordinates (even)
+	const size_t bid = ((size_t)(cz >> 4) * cnb + (cy >> 4)) * cnb + (cx >> 4);
+	const int lx = cx & 15, ly = cy & 15, lz = cz & 15;
 	VxbVote v;
 	vxb_vote_init(v);
-#pragma unroll
-	for (int q = 0; q < 8; ++q)
+	if (level == 1)
 	{
-		const int cx = base[0] + ((q & 1) ? cm : 0), cy = base[1] + ((q & 2) ? cm : 0), cz = base[2] + ((q & 4) ? cm : 0);
-		const size_t bid = ((size_t)(cz / ext) * cnb + (cy / ext)) * cnb + (cx / ext);
-		const unsigned lid = (unsigned)(((cz % ext) / cm) * 256 + ((cy % ext) / cm) * 16 + ((cx % ext) / cm));
-		unsigned cid = VXB_EMPTY_MATERIAL, cblend = 0;
-		if (level == 1)
+		if (!d.consValid[bid]) return false;
+		const unsigned short* rows = reinterpret_cast<const unsigned short*>(d.consPages + bid * 128); // 16 bits per (z,y) row
+		const unsigned r00 = (rows[lz * 16 + ly] >> lx) & 3u, r01 = (rows[lz * 16 + ly + 1] >> lx) & 3u;
+		const unsigned r10 = (rows[(lz + 1) * 16 + ly] >> lx) & 3u, r11 = (rows[(lz + 1) * 16 + ly + 1] >> lx) & 3u;
+		const unsigned bits = r00 | (r01 << 2) | (r10 << 4) | (r11 << 6); // child q = x + 2y + 4z
+		if (!bits) return false;
+#pragma unroll
+		for (int q = 0; q < 8; ++q)
 		{
-			if (d.consValid[bid] && ((d.consPages[bid * 128 + (lid >> 5)] >> (lid & 31)) & 1u))
+			unsigned cid = VXB_EMPTY_MATERIAL, cblend = 0;
+			if ((bits >> q) & 1u)
 			{
-				const size_t gi = ((size_t)cz * d.n + cy) * d.n + cx;
+				const size_t gi = ((size_t)(base[2] + (q >> 2)) * d.n + (base[1] + ((q >> 1) & 1))) * d.n + (base[0] + (q & 1));
 				cid = d.grid.mat[gi]; cblend = d.grid.blend[gi];
 			}
+			vxb_vote_add(v, cid, cblend);
 		}
-		else if (d.cacheValid[level - 1][bid])
+	}
+	else
+	{
+		if (!d.cacheValid[level - 1][bid]) return false;
+		const unsigned int* page = reinterpret_cast<const unsigned int*>(d.cachePages[level - 1] + bid * 4096); // 2 cells per word
+		const int o = (lz * 256 + ly * 16 + lx) >> 1;
+		const unsigned e0 = page[o], e1 = page[o + 8], e2 = page[o + 128], e3 = page[o + 136];
+		if ((e0 & e1 & e2 & e3 & 0x00FF00FFu) == 0x00FF00FFu) return false; // all eight children EMPTY_MATERIAL
+		const unsigned e[4] = { e0, e1, e2, e3 };
+#pragma unroll
+		for (int q = 0; q < 8; ++q)
 		{
-			const unsigned e = d.cachePages[level - 1][bid * 4096 + lid];
-			cid = e & 0xFF; cblend = e >> 8;
+			const unsigned w = e[q >> 1] >> ((q & 1) * 16);
+			vxb_vote_add(v, w & 0xFF, (w >> 8) & 0xFF);
 		}
-		vxb_vote_add(v, cid, cblend);
 	}
 	return vxb_vote_result(v, id, blend);
 }
@@ -419,59 +478,40 @@ __device__ __forceinline__ void vxb_store_vertex(VxbVertex* dst, const VxbVertex
 	out[0] = src[0]; out[1] = src[1]; out[2] = src[2];
 }
 
-template <bool LEVEL0>
-__global__ void __launch_bounds__(VXB_THREADS) vxb_polygonize_kernel(const __grid_constant__ CUtensorMap tmap, const VxbDev d, const int level)
+// Generic (capacity-unbounded) kernel: processes the blocks the two emit tiers of vxb_emit.cuh rejected
+// (> 4096... rather: > 12288 vertices in one block).  It redoes classification for its block (idempotent) and
+// leaves the per-class / non-trivial statistics to vxb_classify_kernel.
+__global__ void __launch_bounds__(VXB_THREADS) vxb_generic_kernel(const __grid_constant__ CUtensorMap tmap, const VxbDev d)
 {
 	extern __shared__ __align__(128) unsigned char smemRaw[];
 	VxbPolySmem& s = *reinterpret_cast<VxbPolySmem*>(smemRaw);
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	const int m = 1 << level, nb = d.n / 16 / m;
 	const VxbGrid g = d.grid;
-	const bool midLevel = level > 0 && level != d.lastLevel;
 	unsigned phase = 0;
 
 	if (tid == 0) vxb_mbar_init(&s.mbar, 1);
 	if (tid < 16) s.hist[tid] = 0;
 	if (tid < 8) s.used[tid] = 0;
-	unsigned statNonTrivial = 0, statRemoved = 0; // thread 0 accumulates
+	unsigned statRemoved = 0; // thread 0 accumulates
 	__syncthreads();
 
-	const unsigned workCount = d.counters->workCount[level];
+	const unsigned workCount = d.counters->genCount;
 	for (;;)
 	{
-		if (tid == 0) s.item = atomicAdd(&d.counters->workCursor[level], 1u);
+		if (tid == 0) s.item = atomicAdd(&d.counters->genCursor, 1u);
 		__syncthreads();
 		const unsigned item = s.item;
 		if (item >= workCount) break;
-		const unsigned coordId = d.worklist[d.workBase[level] + item];
+		const unsigned packed = d.emitList[d.genList[item]];
+		const int level = (int)(packed >> 28);
+		const bool LEVEL0 = level == 0;
+		const unsigned coordId = packed & 0x0FFFFFFFu;
+		const int m = 1 << level, nb = d.n / 16 / m;
+		const bool midLevel = level > 0 && level != d.lastLevel;
 		const int bx = coordId % nb, by = (coordId / nb) % nb, bz = coordId / (nb * nb);
 
 		// ---- step 0: stage the 17^3 sample tile ----
-		if (LEVEL0)
-		{
-			if (tid == 0)
-			{
-				vxb_fence_proxy_async();
-				vxb_mbar_expect_tx(&s.mbar, VXB_TILE_BYTES);
-				vxb_tma_load_3d(s.tile, &tmap, bx * 16, by * 16, bz * 16, &s.mbar);
-			}
-			vxb_mbar_wait(&s.mbar, phase);
-			phase ^= 1;
-			// far grid edge: the +1 plane is outside the volume (TMA zero-fills); the reference clamps (:1037-1047)
-			if (bx == nb - 1) { __syncthreads(); for (int i = tid; i < 17 * 17; i += VXB_THREADS) s.tile[i * VXB_TILE_PITCH + 16] = s.tile[i * VXB_TILE_PITCH + 15]; }
-			if (by == nb - 1) { __syncthreads(); for (int i = tid; i < 17 * 17; i += VXB_THREADS) { const int z = i / 17, x = i % 17; s.tile[(z * 17 + 16) * VXB_TILE_PITCH + x] = s.tile[(z * 17 + 15) * VXB_TILE_PITCH + x]; } }
-			if (bz == nb - 1) { __syncthreads(); for (int i = tid; i < 17 * 17; i += VXB_THREADS) { const int y = i / 17, x = i % 17; s.tile[(16 * 17 + y) * VXB_TILE_PITCH + x] = s.tile[(15 * 17 + y) * VXB_TILE_PITCH + x]; } }
-		}
-		else
-		{
-			const int lim = d.n - 1;
-			for (int i = tid; i < 17 * 17 * 17; i += VXB_THREADS)
-			{
-				const int x = i % 17, y = (i / 17) % 17, z = i / 289;
-				const int gx = min((bx * 16 + x) * m, lim), gy = min((by * 16 + y) * m, lim), gz = min((bz * 16 + z) * m, lim);
-				s.tile[(z * 17 + y) * VXB_TILE_PITCH + x] = g.dist[((size_t)gz * d.n + gy) * d.n + gx];
-			}
-		}
+		vxb_stage_tile(s.tile, &s.mbar, phase, &tmap, g, d.n, level, bx, by, bz);
 		if (tid == 0) { s.removed = 0; s.pageReady = 0; s.hasChild = 0; s.voff = 0; s.ioff = 0; }
 		__syncthreads();
 
@@ -540,7 +580,6 @@ __global__ void __launch_bounds__(VXB_THREADS) vxb_polygonize_kernel(const __gri
 				vxb_cell_samples(s, c, v);
 				const unsigned code = vxb_case_code(v);
 				const unsigned cls = vxbRegularCellClass[code];
-				atomicAdd(&s.hist[cls], 1u);
 				unsigned matId = VXB_EMPTY_MATERIAL, matBlend = 0;
 				if (LEVEL0)
 				{
@@ -705,12 +744,11 @@ __global__ void __launch_bounds__(VXB_THREADS) vxb_polygonize_kernel(const __gri
 				}
 				if (tid == 0) { statRemoved += removed; }
 			}
-			if (tid == 0) statNonTrivial += ntc;
 		}
 
 		// ---- step 6: transition cells (:1754-2131) + their material-cache side effect (:1859) ----
 		unsigned tvCount[6] = { 0, 0, 0, 0, 0, 0 }, tiCount[6] = { 0, 0, 0, 0, 0, 0 }, tvOff[6] = { 0, 0, 0, 0, 0, 0 }, tiOff[6] = { 0, 0, 0, 0, 0, 0 };
-		if (!LEVEL0 && midLevel)
+		if (midLevel)
 		{
 			if (tid < 8)
 			{
@@ -874,11 +912,6 @@ __global__ void __launch_bounds__(VXB_THREADS) vxb_polygonize_kernel(const __gri
 
 	// ---- statistics ----
 	__syncthreads();
-	if (tid < 16 && s.hist[tid]) atomicAdd(&d.counters->perCase[tid], s.hist[tid]);
 	if (tid < 8 && s.used[tid]) atomicOr(&d.counters->usedMaterials[tid], s.used[tid]);
-	if (tid == 0)
-	{
-		if (statNonTrivial) atomicAdd(&d.counters->nonTrivial, statNonTrivial);
-		if (statRemoved) atomicAdd(&d.counters->degenerate, statRemoved);
-	}
+	if (tid == 0 && statRemoved) atomicAdd(&d.counters->degenerate, statRemoved);
 }
