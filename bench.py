@@ -212,12 +212,12 @@ def main():
     device_ms_inner = info.device_ms
 
     # -- per-kernel times for the roofline (separate steps: the extra events add a little stream overhead) --
-    kind_ms = [0.0] * 5
-    kind_launches = [0] * 5
+    kind_ms = [0.0] * 8
+    kind_launches = [0] * 8
     ksteps = max(3, min(args.steps, 10))
     for _ in range(ksteps):
         ctx.polygonize(args.levels, flags | voxels_b200.FLAG_KERNEL_TIMES)
-        for k in range(5):
+        for k in range(8):
             ms, ln = ctx.kernel_ms(k)
             kind_ms[k] += ms / ksteps
             kind_launches[k] = ln
@@ -232,18 +232,20 @@ def main():
     peak, peak_src = measured_peak_hbm()
     kinds = ["vxb_scan_kernel (streams the level-0 distance volume once)", "vxb_block_info/vxb_select kernels",
              "vxb_classify_kernel (one launch per level: tiles, case codes, material votes)",
-             "vxb_emit_kernel (all levels in one launch: vertices, triangles, transition cells)",
-             "overflow tiers (big emit + generic kernel)"]
+             "vxb_decide_kernel (per block: ordering, reuse decisions, scans; all levels)",
+             "vxb_vertex_kernel (flat, one thread per new vertex)", "vxb_triangle_kernel (flat, one thread per non-trivial cell)",
+             "vxb_transition_kernel (per mid-level block)", "vxb_finish_kernel (compaction + directory)"]
     # SURVEY.md 8(d) split per kernel: level-0 samples are read once by the scan; coarser levels' samples by classify;
-    # materials + output by emit.  Tile re-reads of candidate blocks are overhead, not algorithmic bytes.
-    alg_by_kind = [d_level0, 0.0, float(d_upper), bytes_mat + bytes_out, 0.0]
-    dom = max(range(5), key=lambda k: kind_ms[k])
+    # materials + vertices by the vertex kernel; indices by the triangle kernel; transition output by its kernel.
+    # Tile re-reads of candidate blocks and the intermediate cell records are overhead, not algorithmic bytes.
+    alg_by_kind = [d_level0, 0.0, float(d_upper), 0.0, 52.0 * V, 4.0 * I, 52.0 * TV + 4.0 * TI, 0.0]
+    dom = max(range(8), key=lambda k: kind_ms[k])
     ach = alg_by_kind[dom] / (kind_ms[dom] * 1e-3) / 1e9 if kind_ms[dom] > 0 else 0.0
     roofline = {"bound": "hbm", "kernel": kinds[dom], "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
                 "peak_source": peak_src, "algorithmic_bytes_per_step": alg_by_kind[dom], "kernel_ms_per_step": kind_ms[dom],
                 "launches_per_step": kind_launches[dom],
                 "all_kernels": {kinds[k]: {"ms_per_step": kind_ms[k], "launches": kind_launches[k], "algorithmic_bytes": alg_by_kind[k],
-                                           "achieved_gbs": (alg_by_kind[k] / (kind_ms[k] * 1e-3) / 1e9 if kind_ms[k] > 0 else 0.0)} for k in range(5)},
+                                           "achieved_gbs": (alg_by_kind[k] / (kind_ms[k] * 1e-3) / 1e9 if kind_ms[k] > 0 else 0.0)} for k in range(8)},
                 "job": {"algorithmic_bytes": bytes_alg_total, "device_ms": device_ms_inner,
                         "achieved_gbs": bytes_alg_total / (device_ms_inner * 1e-3) / 1e9, "frac": bytes_alg_total / (device_ms_inner * 1e-3) / 1e9 / peak}}
 

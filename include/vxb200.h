@@ -134,8 +134,8 @@ int vxb_set_capacity(vxb_context* ctx, uint64_t vertices, uint64_t indices, uint
 
 /* Per-kernel device time of the last vxb_polygonize run with VXB_FLAG_KERNEL_TIMES, for bench.py's roofline line:
  * which = 0: vxb_scan_kernel (streams the level-0 distance volume once), 1: block info + selection kernels,
- * 2: vxb_classify_kernel (one launch per level), 3: vxb_emit_kernel (all levels, one launch),
- * 4: overflow tiers (big emit + generic kernel).  Milliseconds, summed over launches of that kind. */
+ * 2: vxb_classify_kernel (one launch per level), 3: vxb_decide_kernel (two capacity tiers), 4: vxb_vertex_kernel,
+ * 5: vxb_triangle_kernel, 6: vxb_transition_kernel, 7: vxb_finish_kernel.  Milliseconds, summed per kind. */
 int vxb_kernel_ms(vxb_context* ctx, int which, float* ms, uint32_t* launches);
 
 #ifdef __cplusplus

@@ -25,8 +25,8 @@
 #include "vxb_kernels.cuh"
 #include "vxb_emit.cuh"
 
-typedef VxbEmitSmem<1024, 3072> VxbEmitSmemSmall;
-typedef VxbEmitSmem<4096, 12288> VxbEmitSmemBig;
+typedef VxbDecideSmem<1024> VxbDecideSmemSmall;
+typedef VxbDecideSmem<4096> VxbDecideSmemBig;
 
 static_assert(sizeof(VxbVertex) == 48, "PolygonVertex layout");
 static_assert(sizeof(vxb_block_record) == 128, "record layout");
@@ -76,7 +76,9 @@ struct vxb_context
 	DevBuf<unsigned int> consPages;
 	DevBuf<unsigned char> validFlags; // consValid + cacheValid[l] packed
 	DevBuf<unsigned short> cachePages;
-	DevBuf<unsigned int> worklist, emitList, bigList, genList, ntScratch;
+	DevBuf<unsigned int> worklist, emitList, bigList, transList, ntScratch, cellBlock, vlist;
+	DevBuf<VxbCellRec> cellRecs;
+	DevBuf<VxbBlockRec> blockRecs;
 	DevBuf<VxbVertex> verts, tverts;
 	DevBuf<unsigned int> idx, tidx;
 	DevBuf<vxb_block_record> records;
@@ -84,7 +86,10 @@ struct vxb_context
 	DevBuf<VxbMaterialLut> lut;
 	uint64_t capV = 0, capI = 0, capTV = 0, capTI = 0;
 	CUtensorMap tmap;
-	int gridClassify = 0, gridEmitSmall = 0, gridEmitBig = 0, gridGeneric = 0;
+	int gridClassify = 0, gridDecideSmall = 0, gridDecideBig = 0, gridTransition = 0;
+	uint64_t capC = 0;
+	bool directoryFetched = false;
+	VxbCounters lastCounters;
 	size_t validBytes = 0;
 
 	bool haveResult = false;
@@ -92,8 +97,8 @@ struct vxb_context
 	std::vector<vxb_block_record> sortedRecords;
 	uint8_t lutValid[256];
 	std::vector<uint8_t> unmapped; // material ids of vertices whose material had no mapping, in logging order
-	float kindMs[5] = { 0, 0, 0, 0, 0 };
-	uint32_t kindLaunches[5] = { 0, 0, 0, 0, 0 };
+	float kindMs[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+	uint32_t kindLaunches[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
 };
 
 namespace
@@ -113,7 +118,6 @@ bool validSize(uint32_t n) { return n >= 16 && n <= 4096 && (n & (n - 1)) == 0; 
 
 int levelsFor(uint32_t n) { int l = 1; for (uint32_t v = n >> 4; v >>= 1;) ++l; return l; }
 
-const size_t kPolySmem = sizeof(VxbPolySmem);
 
 int ensureGridStorage(vxb_context* ctx, uint32_t n)
 {
@@ -159,7 +163,7 @@ struct KernelTimer
 	void end() { if (!on) return; cudaEventRecord(ctx->kevents[used + 1], ctx->stream); used += 2; }
 	void collect()
 	{
-		for (int k = 0; k < 5; ++k) ctx->kindMs[k] = 0.f;
+		for (int k = 0; k < 8; ++k) ctx->kindMs[k] = 0.f;
 		if (!on) return;
 		for (size_t i = 0; i < kinds.size(); ++i)
 		{
@@ -204,9 +208,9 @@ int vxb_create(int device, vxb_context** out)
 	struct KernelSetup { const void* fn; size_t smem; int* grid; const char* name; };
 	const KernelSetup setups[4] = {
 		{ (const void*)vxb_classify_kernel, sizeof(VxbClassifySmem), &ctx->gridClassify, "vxb_classify_kernel" },
-		{ (const void*)vxb_emit_kernel<1024, 3072, 0>, sizeof(VxbEmitSmemSmall), &ctx->gridEmitSmall, "vxb_emit_kernel<small>" },
-		{ (const void*)vxb_emit_kernel<4096, 12288, 1>, sizeof(VxbEmitSmemBig), &ctx->gridEmitBig, "vxb_emit_kernel<big>" },
-		{ (const void*)vxb_generic_kernel, kPolySmem, &ctx->gridGeneric, "vxb_generic_kernel" },
+		{ (const void*)vxb_decide_kernel<1024, 0>, sizeof(VxbDecideSmemSmall), &ctx->gridDecideSmall, "vxb_decide_kernel<1024>" },
+		{ (const void*)vxb_decide_kernel<4096, 1>, sizeof(VxbDecideSmemBig), &ctx->gridDecideBig, "vxb_decide_kernel<4096>" },
+		{ (const void*)vxb_transition_kernel, sizeof(VxbTransSmem), &ctx->gridTransition, "vxb_transition_kernel" },
 	};
 	for (const KernelSetup& k : setups)
 	{
@@ -231,7 +235,7 @@ void vxb_destroy(vxb_context* ctx)
 	if (ctx->stream) cudaStreamSynchronize(ctx->stream);
 	ctx->volDist.release(); ctx->volMat.release(); ctx->volBlend.release(); ctx->staging.release();
 	ctx->scanFlags.release(); ctx->blockInfo.release(); ctx->consPages.release(); ctx->validFlags.release();
-	ctx->cachePages.release(); ctx->worklist.release(); ctx->emitList.release(); ctx->bigList.release(); ctx->genList.release(); ctx->ntScratch.release(); ctx->verts.release(); ctx->tverts.release();
+	ctx->cachePages.release(); ctx->worklist.release(); ctx->emitList.release(); ctx->bigList.release(); ctx->transList.release(); ctx->ntScratch.release(); ctx->cellBlock.release(); ctx->vlist.release(); ctx->cellRecs.release(); ctx->blockRecs.release(); ctx->verts.release(); ctx->tverts.release();
 	ctx->idx.release(); ctx->tidx.release(); ctx->records.release(); ctx->counters.release(); ctx->lut.release();
 	for (cudaEvent_t e : ctx->kevents) cudaEventDestroy(e);
 	if (ctx->evBegin) cudaEventDestroy(ctx->evBegin);
@@ -369,14 +373,16 @@ int vxb_polygonize(vxb_context* ctx, uint32_t maxLevels, uint32_t flags)
 	VXB_CUDA(ctx, ctx->records.ensure(totalBlocks));
 	VXB_CUDA(ctx, ctx->emitList.ensure(totalBlocks));
 	VXB_CUDA(ctx, ctx->bigList.ensure(totalBlocks));
-	VXB_CUDA(ctx, ctx->genList.ensure(totalBlocks));
-	VXB_CUDA(ctx, ctx->ntScratch.ensure(totalBlocks * 128));
+	VXB_CUDA(ctx, ctx->transList.ensure(totalBlocks));
+	VXB_CUDA(ctx, ctx->blockRecs.ensure(totalBlocks));
+	VXB_CUDA(ctx, ctx->ntScratch.ensure(totalBlocks * 256));
 
 	const uint64_t vol = (uint64_t)n * n * n;
 	if (!ctx->capV) ctx->capV = std::max<uint64_t>(1u << 20, vol / 24);
 	if (!ctx->capI) ctx->capI = ctx->capV * 6;
 	if (!ctx->capTV) ctx->capTV = std::max<uint64_t>(1u << 18, ctx->capV / 8);
 	if (!ctx->capTI) ctx->capTI = ctx->capTV * 6;
+	if (!ctx->capC) ctx->capC = ctx->capV + ctx->capV / 4;
 
 	dev.grid.dist = ctx->dDist; dev.grid.mat = ctx->dMat; dev.grid.blend = ctx->dBlend; dev.grid.n = (int)n;
 	dev.n = (int)n; dev.levels = levels; dev.lastLevel = levels - 1;
@@ -388,7 +394,8 @@ int vxb_polygonize(vxb_context* ctx, uint32_t maxLevels, uint32_t flags)
 	dev.records = ctx->records.p; dev.rcap = (unsigned)totalBlocks;
 	dev.counters = ctx->counters.p; dev.lut = ctx->lut.p;
 	dev.transitions = (flags & VXB_FLAG_NO_TRANSITIONS) ? 0 : 1;
-	dev.emitList = ctx->emitList.p; dev.bigList = ctx->bigList.p; dev.genList = ctx->genList.p; dev.ntScratch = ctx->ntScratch.p;
+	dev.emitList = ctx->emitList.p; dev.bigList = ctx->bigList.p; dev.transList = ctx->transList.p; dev.ntScratch = ctx->ntScratch.p;
+	dev.blockRecs = ctx->blockRecs.p;
 
 	VxbCounters hc;
 	for (int attempt = 0; attempt < 6; ++attempt)
@@ -396,16 +403,21 @@ int vxb_polygonize(vxb_context* ctx, uint32_t maxLevels, uint32_t flags)
 		const uint64_t lim = 0xFFFFFFF0ull;
 		ctx->capV = std::min(ctx->capV, lim); ctx->capI = std::min(ctx->capI, lim);
 		ctx->capTV = std::min(ctx->capTV, lim); ctx->capTI = std::min(ctx->capTI, lim);
+		ctx->capV = std::min<uint64_t>(ctx->capV, 0x0FFFFFF0ull); ctx->capC = std::min<uint64_t>(ctx->capC, 0x0FFFFFF0ull); // 28-bit cell index in the vertex list
 		VXB_CUDA(ctx, ctx->verts.ensure(ctx->capV));
 		VXB_CUDA(ctx, ctx->idx.ensure(ctx->capI));
 		VXB_CUDA(ctx, ctx->tverts.ensure(ctx->capTV));
 		VXB_CUDA(ctx, ctx->tidx.ensure(ctx->capTI));
+		VXB_CUDA(ctx, ctx->vlist.ensure(ctx->capV));
+		VXB_CUDA(ctx, ctx->cellRecs.ensure(ctx->capC));
+		VXB_CUDA(ctx, ctx->cellBlock.ensure(ctx->capC));
 		dev.verts = ctx->verts.p; dev.idx = ctx->idx.p; dev.tverts = ctx->tverts.p; dev.tidx = ctx->tidx.p;
 		dev.vcap = (unsigned)ctx->capV; dev.icap = (unsigned)ctx->capI; dev.tvcap = (unsigned)ctx->capTV; dev.ticap = (unsigned)ctx->capTI;
+		dev.vlist = ctx->vlist.p; dev.cellRecs = ctx->cellRecs.p; dev.cellBlock = ctx->cellBlock.p; dev.ccap = (unsigned)ctx->capC;
 
 		KernelTimer timer{ ctx, kernelTimes };
 		uint32_t launches = 0;
-		for (int k = 0; k < 5; ++k) ctx->kindLaunches[k] = 0;
+		for (int k = 0; k < 8; ++k) ctx->kindLaunches[k] = 0;
 		VXB_CUDA(ctx, cudaEventRecord(ctx->evBegin, ctx->stream));
 		VXB_CUDA(ctx, cudaMemsetAsync(ctx->counters.p, 0, sizeof(VxbCounters), ctx->stream));
 		VXB_CUDA(ctx, cudaMemsetAsync(ctx->validFlags.p, 0, validBytes, ctx->stream));
@@ -431,14 +443,24 @@ int vxb_polygonize(vxb_context* ctx, uint32_t maxLevels, uint32_t flags)
 			vxb_classify_kernel<<<(unsigned)std::min<size_t>(b, ctx->gridClassify), VXB_THREADS, sizeof(VxbClassifySmem), ctx->stream>>>(ctx->tmap, dev, l);
 			timer.end(); ++launches; ++ctx->kindLaunches[2];
 		}
-		// emission of ALL computed levels in one launch (largest blocks first), then the two overflow tiers
+		// everything below runs ONCE for the blocks of all computed levels
+		const unsigned flatGrid = (unsigned)ctx->smCount * 8;
 		timer.begin(3);
-		vxb_emit_kernel<1024, 3072, 0><<<ctx->gridEmitSmall, VXB_THREADS, sizeof(VxbEmitSmemSmall), ctx->stream>>>(ctx->tmap, dev);
-		timer.end(); ++launches; ++ctx->kindLaunches[3];
+		vxb_decide_kernel<1024, 0><<<ctx->gridDecideSmall, VXB_THREADS, sizeof(VxbDecideSmemSmall), ctx->stream>>>(ctx->tmap, dev);
+		vxb_decide_kernel<4096, 1><<<ctx->gridDecideBig, VXB_THREADS, sizeof(VxbDecideSmemBig), ctx->stream>>>(ctx->tmap, dev);
+		timer.end(); launches += 2; ctx->kindLaunches[3] += 2;
 		timer.begin(4);
-		vxb_emit_kernel<4096, 12288, 1><<<ctx->gridEmitBig, VXB_THREADS, sizeof(VxbEmitSmemBig), ctx->stream>>>(ctx->tmap, dev);
-		vxb_generic_kernel<<<ctx->gridGeneric, VXB_THREADS, kPolySmem, ctx->stream>>>(ctx->tmap, dev);
-		timer.end(); launches += 2; ctx->kindLaunches[4] += 2;
+		vxb_vertex_kernel<<<flatGrid, VXB_THREADS, 0, ctx->stream>>>(dev);
+		timer.end(); ++launches; ++ctx->kindLaunches[4];
+		timer.begin(5);
+		vxb_triangle_kernel<<<flatGrid, VXB_THREADS, 0, ctx->stream>>>(dev);
+		timer.end(); ++launches; ++ctx->kindLaunches[5];
+		timer.begin(6);
+		if (dev.transitions) { vxb_transition_kernel<<<ctx->gridTransition, VXB_THREADS, sizeof(VxbTransSmem), ctx->stream>>>(dev); ++launches; ++ctx->kindLaunches[6]; }
+		timer.end();
+		timer.begin(7);
+		vxb_finish_kernel<<<(unsigned)ctx->smCount * 2, VXB_THREADS, 0, ctx->stream>>>(dev);
+		timer.end(); ++launches; ++ctx->kindLaunches[7];
 		VXB_CUDA(ctx, cudaGetLastError());
 		VXB_CUDA(ctx, cudaEventRecord(ctx->evEnd, ctx->stream));
 		VXB_CUDA(ctx, cudaMemcpyAsync(&hc, ctx->counters.p, sizeof(hc), cudaMemcpyDeviceToHost, ctx->stream));
@@ -449,33 +471,29 @@ int vxb_polygonize(vxb_context* ctx, uint32_t maxLevels, uint32_t flags)
 		ctx->info.device_ms = ms;
 		ctx->info.kernel_launches = launches;
 
-		const bool overflow = hc.vertices > ctx->capV || hc.indices > ctx->capI || hc.transVertices > ctx->capTV || hc.transIndices > ctx->capTI;
+		const bool overflow = hc.vertices > ctx->capV || hc.indices > ctx->capI || hc.transVertices > ctx->capTV || hc.transIndices > ctx->capTI || hc.cells > ctx->capC;
 		if (!overflow) break;
 		if (attempt == 5) return fail(ctx, VXB_ERR_CAPACITY, "vxb_polygonize: output arenas overflowed after growing");
 		if (hc.vertices > ctx->capV) ctx->capV = (uint64_t)hc.vertices + hc.vertices / 8 + 1024;
 		if (hc.indices > ctx->capI) ctx->capI = (uint64_t)hc.indices + hc.indices / 8 + 1024;
 		if (hc.transVertices > ctx->capTV) ctx->capTV = (uint64_t)hc.transVertices + hc.transVertices / 8 + 1024;
 		if (hc.transIndices > ctx->capTI) ctx->capTI = (uint64_t)hc.transIndices + hc.transIndices / 8 + 1024;
+		if (hc.cells > ctx->capC) ctx->capC = (uint64_t)hc.cells + hc.cells / 8 + 1024;
 	}
 
-	// ---- directory: download + sort into the reference's block order (level, then z,y,x = coord id) ----
-	ctx->sortedRecords.resize(hc.records);
-	if (hc.records)
-		VXB_CUDA(ctx, cudaMemcpy(ctx->sortedRecords.data(), ctx->records.p, sizeof(vxb_block_record) * hc.records, cudaMemcpyDeviceToHost));
-	std::sort(ctx->sortedRecords.begin(), ctx->sortedRecords.end(), [](const vxb_block_record& a, const vxb_block_record& b) {
-		return a.level != b.level ? a.level < b.level : a.coord_id < b.coord_id; });
+	// the directory stays on the device (it is part of the result resident in HBM); vxb_result_download fetches and
+	// sorts it into the reference's block order on demand
+	ctx->lastCounters = hc;
+	ctx->directoryFetched = false;
+	ctx->sortedRecords.clear();
 
 	vxb_result_info& info = ctx->info;
 	info.levels_total = (uint32_t)levels; info.levels_computed = (uint32_t)computed;
 	info.block_count = hc.records; info.pad = 0;
 	info.vertex_span = hc.vertices; info.index_span = hc.indices;
 	info.trans_vertex_span = hc.transVertices; info.trans_index_span = hc.transIndices;
-	info.vertex_total = info.index_total = info.trans_vertex_total = info.trans_index_total = 0;
-	for (const vxb_block_record& r : ctx->sortedRecords)
-	{
-		info.vertex_total += r.vertex_count; info.index_total += r.index_count;
-		for (int f = 0; f < 6; ++f) { info.trans_vertex_total += r.trans_vertex_count[f]; info.trans_index_total += r.trans_index_count[f]; }
-	}
+	info.vertex_total = hc.vertices; info.index_total = (uint64_t)hc.indices - 3ull * hc.degenerate;
+	info.trans_vertex_total = hc.transVertices; info.trans_index_total = hc.transIndices;
 	// statistics (TransVoxelImpl.cpp:528-531): BlocksCalculated counts every block of every computed level;
 	// TrivialCells only those of processed (not skipped) blocks
 	uint64_t blocksCalculated = 0, processedCells = (uint64_t)hc.nonSkippedLevel0 * 4096ull;
@@ -504,6 +522,16 @@ int vxb_result_download(vxb_context* ctx, vxb_block_record* records, void* verti
 	if (!ctx->haveResult) return fail(ctx, VXB_ERR_STATE, "no result: call vxb_polygonize first");
 	cudaSetDevice(ctx->device);
 	const vxb_result_info& info = ctx->info;
+	if (!ctx->directoryFetched)
+	{
+		// directory: device -> host, sorted into the reference's block order (level, then z,y,x = coord id; :395-401, :1278)
+		ctx->sortedRecords.resize(info.block_count);
+		if (info.block_count)
+			VXB_CUDA(ctx, cudaMemcpy(ctx->sortedRecords.data(), ctx->records.p, sizeof(vxb_block_record) * info.block_count, cudaMemcpyDeviceToHost));
+		std::sort(ctx->sortedRecords.begin(), ctx->sortedRecords.end(), [](const vxb_block_record& a, const vxb_block_record& b) {
+			return a.level != b.level ? a.level < b.level : a.coord_id < b.coord_id; });
+		ctx->directoryFetched = true;
+	}
 	if (records && info.block_count) memcpy(records, ctx->sortedRecords.data(), sizeof(vxb_block_record) * info.block_count);
 	if (vertices && info.vertex_span) VXB_CUDA(ctx, cudaMemcpyAsync(vertices, ctx->verts.p, info.vertex_span * sizeof(VxbVertex), cudaMemcpyDeviceToHost, ctx->stream));
 	if (indices && info.index_span) VXB_CUDA(ctx, cudaMemcpyAsync(indices, ctx->idx.p, info.index_span * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -551,7 +579,7 @@ void vxb_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 int vxb_kernel_ms(vxb_context* ctx, int which, float* ms, uint32_t* launches)
 {
-	if (!ctx || which < 0 || which > 4) return VXB_ERR_ARGUMENT;
+	if (!ctx || which < 0 || which > 7) return VXB_ERR_ARGUMENT;
 	if (ms) *ms = ctx->kindMs[which];
 	if (launches) *launches = ctx->kindLaunches[which];
 	return VXB_OK;

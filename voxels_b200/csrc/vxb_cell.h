@@ -13,11 +13,13 @@
 
 #if defined(__CUDACC__)
 #define VXB_FN __device__ __forceinline__
+#define VXB_FN_BIG __device__ __noinline__   // large helpers: one copy each, the kernels must stay I-cache friendly
 #define VXB_SQRT(x) __fsqrt_rn(x)
 #define VXB_DIV(a, b) __fdiv_rn((a), (b))
 #else
 #include <cmath>
 #define VXB_FN inline
+#define VXB_FN_BIG inline
 #define VXB_SQRT(x) std::sqrt(x)
 #define VXB_DIV(a, b) ((a) / (b))
 #endif
@@ -86,7 +88,7 @@ VXB_FN void vxb_normalize_fix_zero(float& x, float& y, float& z)
 
 // CalcNormal :1239-1246 - central differences on the level-0 grid, taps clamped (the point itself
 // may lie at coordinate n); the result is already in output (Y-up) axes: (d/dx, d/dz, d/dy).
-VXB_FN void vxb_normal(const VxbGrid& g, int x, int y, int z, float n[3])
+VXB_FN_BIG void vxb_normal(const VxbGrid& g, int x, int y, int z, float n[3])
 {
 	const int m = g.n - 1;
 	const size_t nn = (size_t)g.n;
@@ -116,7 +118,7 @@ VXB_FN int vxb_fixed_t(int a, int b)
 }
 
 // FindBestVertexInLODChain :1484-1509 followed by the t recomputation :1671-1678 / :2022-2029.
-VXB_FN int vxb_lod_descent(const VxbGrid& g, int steps, int p0[3], int p1[3])
+VXB_FN_BIG int vxb_lod_descent(const VxbGrid& g, int steps, int p0[3], int p1[3])
 {
 	for (int s = 0; s < steps; ++s)
 	{
@@ -231,7 +233,7 @@ struct VxbRawVertex
 };
 
 // Vertex at a cell corner (GenerateVertexFromPoint :1450-1467).
-VXB_FN void vxb_corner_vertex(const VxbGrid& g, int level, const int base[3], const int local[3], int corner,
+VXB_FN_BIG void vxb_corner_vertex(const VxbGrid& g, int level, const int base[3], const int local[3], int corner,
 	unsigned cellMatId, unsigned cellMatBlend, VxbRawVertex& out)
 {
 	const int m = 1 << level;
@@ -246,7 +248,7 @@ VXB_FN void vxb_corner_vertex(const VxbGrid& g, int level, const int base[3], co
 }
 
 // Vertex in the interior of an edge (:1659-1704).
-VXB_FN void vxb_edge_vertex(const VxbGrid& g, int level, const int base[3], const int local[3], const VxbVertexDesc& d,
+VXB_FN_BIG void vxb_edge_vertex(const VxbGrid& g, int level, const int base[3], const int local[3], const VxbVertexDesc& d,
 	unsigned cellMatId, unsigned cellMatBlend, VxbRawVertex& out)
 {
 	const int m = 1 << level;
@@ -293,7 +295,7 @@ VXB_FN void vxb_regular_secondary(int level, VxbRawVertex& v)
 }
 
 // PushBlocksToResult vertex conversion (:1330-1369, :1391-1423): /256, y<->z swap, flag swizzle, textures.
-VXB_FN void vxb_finish_vertex(const VxbRawVertex& r, const VxbMaterialLut& lut, VxbVertex& o)
+VXB_FN_BIG void vxb_finish_vertex(const VxbRawVertex& r, const VxbMaterialLut& lut, VxbVertex& o)
 {
 	const float k = 1.f / 256.f;
 	o.pos[0] = r.p[0] * k; o.pos[1] = r.p[2] * k; o.pos[2] = r.p[1] * k;
@@ -396,6 +398,18 @@ VXB_FN void vxb_transition_sample_pos(int face, int level, const int cellBase[3]
 	p[va] += r;
 }
 
+// the 13 samples of a transition cell (:1867-1911): 0..8 on the half-stride lattice of the face plane, 9..12 = 0,2,6,8
+VXB_FN_BIG void vxb_transition_samples(const VxbGrid& g, int face, int level, const int cellBase[3], signed char v[13])
+{
+	for (int i = 0; i < 9; ++i)
+	{
+		int p[3];
+		vxb_transition_sample_pos(face, level, cellBase, i, p);
+		v[i] = (signed char)vxb_dist(g, p[0], p[1], p[2]);
+	}
+	v[9] = v[0]; v[10] = v[2]; v[11] = v[6]; v[12] = v[8];
+}
+
 VXB_FN unsigned vxb_transition_case_code(const signed char v[9])
 {
 	unsigned code = 0;
@@ -434,7 +448,7 @@ VXB_FN VxbTransVertexDesc vxb_transition_vertex_desc(unsigned vd, const signed c
 }
 
 // New transition vertex (:1980-2092).  local = low-res cell's local coords, base = its base.
-VXB_FN void vxb_transition_vertex(const VxbGrid& g, int face, int level, const int base[3], const int local[3],
+VXB_FN_BIG void vxb_transition_vertex(const VxbGrid& g, int face, int level, const int base[3], const int local[3],
 	const VxbTransVertexDesc& d, unsigned cellMatId, unsigned cellMatBlend, VxbRawVertex& out)
 {
 	const int m = 1 << level;

@@ -5,11 +5,16 @@
 //                         the non-trivial cells and of every transition-face cell into the level's material page
 //                         (CalculateMaterialForCellCache :753-838, called from :1568 and :1859); statistics;
 //                         appends blocks that have non-trivial cells to the emit list together with their bit mask.
-//   vxb_emit_kernel<C,V>  ONE launch for the blocks of ALL levels (largest blocks first): ordered compaction, reuse
-//                         decisions, block scan, thread-per-new-vertex emission, triangles + degenerate filter,
-//                         all six transition faces at once.  Works out of ~40 KB of shared memory for blocks with
-//                         <= C non-trivial cells and <= V vertices; anything larger is forwarded to the next tier
-//                         (C,V = 4096,12288) and finally to the generic kernel of vxb_kernels.cuh.
+//   then ONE launch each for the blocks of ALL levels:
+//   vxb_decide_kernel<C>  per block (largest first): ordered compaction of the non-trivial cells, materials, owned reuse
+//                         slots, new-vs-reuse decisions, block scans -> vertex / triangle bases; reserves the output
+//                         ranges and writes one 16-byte record per cell + the vertex work list.  C = 1024 (34 KB smem),
+//                         larger blocks go to a second launch with C = 4096.
+//   vxb_vertex_kernel     flat, one thread per NEW VERTEX of the whole grid: position, normal, material, secondary.
+//   vxb_triangle_kernel   flat, one thread per non-trivial CELL: vertex ids (own + reused) and triangles with the
+//                         degenerate-triangle test of PushBlocksToResult (:1300-1321).
+//   vxb_transition_kernel per emitted mid-level block: the six transition faces (:1754-2131).
+//   vxb_finish_kernel     per emitted block: order-preserving compaction where triangles were removed + directory.
 //
 // Bit-exactness notes are in vxb_kernels.cuh / vxb_cell.h; the formulation is identical, only the schedule differs.
 #pragma once
@@ -143,7 +148,7 @@ __global__ void __launch_bounds__(VXB_THREADS, 4) vxb_classify_kernel(const __gr
 				}
 			}
 			__syncthreads();
-			if (tid < 128) d.ntScratch[(size_t)s.emitIdx * 128 + tid] = s.nt32[tid];
+			if (tid < 128) { d.ntScratch[(size_t)s.emitIdx * 256 + tid] = s.nt32[tid]; d.ntScratch[(size_t)s.emitIdx * 256 + 128 + tid] = s.wpre[tid]; }
 		}
 
 		// every cell of every transition face votes too, trivial ones included (:1859) - observable at the next level
@@ -159,13 +164,17 @@ __global__ void __launch_bounds__(VXB_THREADS, 4) vxb_classify_kernel(const __gr
 			__syncthreads();
 			if (s.hasChild)
 			{
+				// an all-{EMPTY,0} page is indistinguishable from no page, so it can be created before the votes
+				if (!s.pageReady)
+				{
+					if (!d.cacheValid[level][coordId]) vxb_init_cache_page(d, level, coordId);
+					__syncthreads();
+					if (tid == 0) { d.cacheValid[level][coordId] = 1; s.pageReady = 1; }
+				}
 				const int row = tid >> 4, col = tid & 15;
-				unsigned votes[6]; // matId | blend<<8 | ok<<16
-				bool any = false;
-#pragma unroll
+#pragma unroll 1
 				for (int face = 0; face < 6; ++face)
 				{
-					votes[face] = 0;
 					int axis, ua, va;
 					vxb_face_axes(face, axis, ua, va);
 					const int bc = (axis == 0) ? bx : (axis == 1 ? by : bz);
@@ -174,29 +183,8 @@ __global__ void __launch_bounds__(VXB_THREADS, 4) vxb_classify_kernel(const __gr
 					local[axis] = (face >= 3) ? 15 : 0; local[ua] = col; local[va] = row;
 					const int base[3] = { (bx * 16 + local[0]) * m, (by * 16 + local[1]) * m, (bz * 16 + local[2]) * m };
 					unsigned matId, matBlend;
-					if (vxb_vote_cell(d, level, base, matId, matBlend)) { votes[face] = matId | (matBlend << 8) | (1u << 16); any = true; }
-				}
-				if (!s.pageReady) // block-uniform
-				{
-					if (__syncthreads_or(any ? 1 : 0))
-					{
-						if (!d.cacheValid[level][coordId]) vxb_init_cache_page(d, level, coordId);
-						__syncthreads();
-						if (tid == 0) { d.cacheValid[level][coordId] = 1; s.pageReady = 1; }
-					}
-				}
-				if (any)
-				{
-#pragma unroll
-					for (int face = 0; face < 6; ++face)
-					{
-						if (!(votes[face] >> 16)) continue;
-						int axis, ua, va;
-						vxb_face_axes(face, axis, ua, va);
-						int local[3];
-						local[axis] = (face >= 3) ? 15 : 0; local[ua] = col; local[va] = row;
-						d.cachePages[level][(size_t)coordId * 4096 + local[2] * 256 + local[1] * 16 + local[0]] = (unsigned short)(votes[face] & 0xFFFF);
-					}
+					if (vxb_vote_cell(d, level, base, matId, matBlend))
+						d.cachePages[level][(size_t)coordId * 4096 + local[2] * 256 + local[1] * 16 + local[0]] = (unsigned short)(matId | (matBlend << 8));
 				}
 			}
 		}
@@ -209,10 +197,10 @@ __global__ void __launch_bounds__(VXB_THREADS, 4) vxb_classify_kernel(const __gr
 }
 
 // ------------------------------------------------------------------------------------------------
-// emit
+// decide: everything that needs the block as a unit (ordering, reuse, scans); no vertex math
 // ------------------------------------------------------------------------------------------------
-template <int CAP_C, int CAP_V>
-struct __align__(128) VxbEmitSmem
+template <int CAP_C>
+struct __align__(128) VxbDecideSmem
 {
 	signed char tile[VXB_TILE_BYTES + 96];
 	unsigned int nt32[128];
@@ -221,80 +209,31 @@ struct __align__(128) VxbEmitSmem
 	unsigned char tabCell[256];
 	unsigned short tabVert[3072];
 	unsigned int warpSums[8];
-	unsigned int used[8];
 	unsigned long long mbar;
-	unsigned int item, voff, ioff, removed;
-	unsigned int tvoff[6], tioff[6];
+	unsigned int item, voff, ioff, cellBase, slot;
 	unsigned int levelEnd[VXB_MAX_LEVELS + 1];
-	union
-	{
-		struct
-		{
-			unsigned int recA[CAP_C];     // matId | matBlend<<8 | slotK<<16
-			unsigned int recB[CAP_C];     // newMask | quirkMask<<12
-			unsigned short list[CAP_C];   // compact index -> cell id
-			unsigned short cz[CAP_C];     // case code | zero mask << 8
-			unsigned short vbase[CAP_C];  // exclusive scan of new-vertex counts
-			unsigned short tbase[CAP_C];  // exclusive scan of triangle counts
-			unsigned short vlist[CAP_V];  // new vertex -> compact cell index << 4 | table vertex
-		} r;
-		struct // all six transition faces at once: cell = face*256 + row*16 + col
-		{
-			unsigned long long slots[1536]; // 10 owned-slot nibbles per cell
-			unsigned short newMask[1536];
-			unsigned short vbase[1536];
-			unsigned char mat[1536];
-			unsigned int nt[48];
-		} t;
-	} u;
+	unsigned int recA[CAP_C];     // matId | matBlend<<8 | slotK<<16
+	unsigned int recB[CAP_C];     // newMask | quirkMask<<12 | reuse mask << 24
+	unsigned short list[CAP_C];   // compact index -> cell id
+	unsigned short cz[CAP_C];     // case code | zero mask << 8
+	unsigned short vbase[CAP_C];  // exclusive scan of new-vertex counts
+	unsigned short tbase[CAP_C];  // exclusive scan of triangle counts
 };
 
-template <int CAP_C, int CAP_V>
-__device__ __forceinline__ unsigned vxb_emit_rank(const VxbEmitSmem<CAP_C, CAP_V>& s, int c)
+__device__ __forceinline__ unsigned vxb_rank_of(const unsigned int* nt32, const unsigned int* wpre, int c)
 {
-	return s.wpre[c >> 5] + __popc(s.nt32[c >> 5] & ((1u << (c & 31)) - 1u));
+	return wpre[c >> 5] + __popc(nt32[c >> 5] & ((1u << (c & 31)) - 1u));
 }
 
-// new-vs-reuse decision (:1610-1644) against the owner's record
-template <int CAP_C, int CAP_V>
-__device__ __forceinline__ VxbDecision vxb_emit_decide(const VxbEmitSmem<CAP_C, CAP_V>& s, int c, int mask, const VxbVertexDesc& d, unsigned myMat)
+// TIER 0: items come from the emit list (all levels, top level first); blocks with > CAP_C cells go to bigList.
+// TIER 1: items come from bigList (CAP_C = 4096 = every possible block).
+template <int CAP_C, int TIER>
+__global__ void __launch_bounds__(VXB_THREADS, (CAP_C <= 1024 ? 4 : 2)) vxb_decide_kernel(const __grid_constant__ CUtensorMap tmap, const VxbDev d)
 {
-	VxbDecision r; r.isNew = true; r.quirkV0 = false; r.ownerIdx = 0; r.ok = VXB_NO_SLOT;
-	if (!d.atC7 && (d.dir & mask) == d.dir)
-	{
-		const int oc = c - (d.dir & 1) - ((d.dir >> 1) & 1) * 16 - ((d.dir >> 2) & 1) * 256;
-		int ok = VXB_NO_SLOT; unsigned oi = 0, oa = 0;
-		if ((s.nt32[oc >> 5] >> (oc & 31)) & 1u)
-		{
-			oi = vxb_emit_rank(s, oc);
-			oa = s.u.r.recA[oi];
-			ok = (oa >> (16 + 4 * d.slot)) & 0xF;
-		}
-		if (ok != VXB_NO_SLOT)
-		{
-			if ((oa & 0xFF) == myMat) { r.isNew = false; r.ownerIdx = oi; r.ok = ok; }
-		}
-		else if (d.endpoint) r.quirkV0 = true;
-	}
-	return r;
-}
-
-template <int CAP_C, int CAP_V>
-__device__ __forceinline__ int vxb_emit_mask(const VxbEmitSmem<CAP_C, CAP_V>& s, int c, unsigned i)
-{
-	const unsigned rowStart = vxb_emit_rank(s, c & ~15), sliceStart = s.wpre[(c >> 8) * 8];
-	return (i > rowStart ? 1 : 0) | (rowStart > sliceStart ? 2 : 0) | (sliceStart > 0 ? 4 : 0);
-}
-
-// TIER 0: items come from the emit list (all levels, top level first), rejects go to bigList.
-// TIER 1: items come from bigList, rejects go to genList (generic kernel).
-template <int CAP_C, int CAP_V, int TIER>
-__global__ void __launch_bounds__(VXB_THREADS, (CAP_C <= 1024 ? 4 : 2)) vxb_emit_kernel(const __grid_constant__ CUtensorMap tmap, const VxbDev d)
-{
-	typedef VxbEmitSmem<CAP_C, CAP_V> Smem;
+	typedef VxbDecideSmem<CAP_C> Smem;
 	extern __shared__ __align__(128) unsigned char smemRaw[];
 	Smem& s = *reinterpret_cast<Smem*>(smemRaw);
-	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int tid = threadIdx.x;
 	const VxbGrid g = d.grid;
 	unsigned phase = 0;
 
@@ -304,16 +243,14 @@ __global__ void __launch_bounds__(VXB_THREADS, (CAP_C <= 1024 ? 4 : 2)) vxb_emit
 		unsigned acc = 0; // work id -> level: the top level first (its blocks are the largest)
 		for (int l = d.levels - 1; l >= 0; --l) { acc += d.counters->emitCount[l]; s.levelEnd[d.levels - 1 - l] = acc; }
 	}
-	if (tid < 8) s.used[tid] = 0;
 	for (int i = tid; i < 256; i += VXB_THREADS) { s.tabClass[i] = vxbGRegularCellClass[i]; s.tabCell[i] = vxbGRegularCellData[i]; }
 	for (int i = tid; i < 3072; i += VXB_THREADS) s.tabVert[i] = vxbGRegularVertexData[i];
-	unsigned statRemoved = 0;
 	__syncthreads();
 	const unsigned workCount = (TIER == 0) ? s.levelEnd[d.levels - 1] : d.counters->bigCount;
 
 	for (;;)
 	{
-		if (tid == 0) { s.item = atomicAdd(TIER == 0 ? &d.counters->emitCursor : &d.counters->bigCursor, 1u); s.removed = 0; }
+		if (tid == 0) s.item = atomicAdd(TIER == 0 ? &d.counters->emitCursor : &d.counters->bigCursor, 1u);
 		__syncthreads();
 		const unsigned item = s.item;
 		if (item >= workCount) break;
@@ -331,211 +268,288 @@ __global__ void __launch_bounds__(VXB_THREADS, (CAP_C <= 1024 ? 4 : 2)) vxb_emit
 		const unsigned coordId = packed & 0x0FFFFFFFu;
 		const int m = 1 << level, nb = d.n / 16 / m;
 		const int bx = coordId % nb, by = (coordId / nb) % nb, bz = coordId / (nb * nb);
-		const bool midLevel = level > 0 && level != d.lastLevel;
 
-		if (tid < 128) s.nt32[tid] = d.ntScratch[(size_t)emitIdx * 128 + tid];
-		vxb_stage_tile(s.tile, &s.mbar, phase, &tmap, g, d.n, level, bx, by, bz);
+		if (tid < 128) { s.nt32[tid] = d.ntScratch[(size_t)emitIdx * 256 + tid]; s.wpre[tid] = d.ntScratch[(size_t)emitIdx * 256 + 128 + tid]; }
 		__syncthreads();
-		unsigned ntc;
+		const unsigned ntc = s.wpre[127] + __popc(s.nt32[127]);
+		if (ntc > (unsigned)CAP_C)
 		{
-			const unsigned cnt = (tid < 128) ? __popc(s.nt32[tid]) : 0u;
-			const unsigned ex = vxb_block_scan(cnt, s.warpSums, ntc);
-			if (tid < 128) s.wpre[tid] = ex;
-		}
-		__syncthreads();
-		bool reject = ntc > (unsigned)CAP_C;
-		unsigned nverts = 0, ntris = 0;
-
-		if (!reject)
-		{
-			// ordered compact list of the non-trivial cells: thread = cell row (z, y), 16 bits each
-			{
-				unsigned bits = reinterpret_cast<const unsigned short*>(s.nt32)[tid];
-				unsigned pos = s.wpre[tid >> 1] + ((tid & 1) ? __popc(s.nt32[tid >> 1] & 0xFFFFu) : 0u);
-				while (bits) { const int x = __ffs(bits) - 1; bits &= bits - 1; s.u.r.list[pos++] = (unsigned short)(tid * 16 + x); }
-			}
-			__syncthreads();
-
-			// ---- pass A: material, descriptors, owned slots ----
-			for (unsigned i = tid; i < ntc; i += VXB_THREADS)
-			{
-				const int c = s.u.r.list[i];
-				signed char v[8];
-				vxb_tile_samples(s.tile, c, v);
-				const unsigned code = vxb_case_code(v);
-				const unsigned cls = s.tabClass[code];
-				unsigned matId, matBlend;
-				if (level == 0)
-				{
-					const size_t gi = ((size_t)((bz * 16 + (c >> 8))) * d.n + (by * 16 + ((c >> 4) & 15))) * d.n + (bx * 16 + (c & 15));
-					matId = g.mat[gi]; matBlend = g.blend[gi];
-				}
-				else
-				{
-					const unsigned e = d.cachePages[level][(size_t)coordId * 4096 + c]; // written by vxb_classify_kernel
-					matId = e & 0xFF; matBlend = e >> 8;
-				}
-				unsigned slotK = 0xFFFFu;
-				const unsigned zm = vxb_zero_mask(v);
-				const int nv = s.tabCell[cls * 16] >> 4;
-				for (int k = 0; k < nv; ++k)
-				{
-					const VxbVertexDesc vd = vxb_regular_vertex_desc_lite(s.tabVert[code * 12 + k], zm);
-					const int sl = vxb_regular_owned_slot(vd);
-					if (sl >= 0) slotK = (slotK & ~(0xFu << (4 * sl))) | ((unsigned)k << (4 * sl));
-				}
-				s.u.r.cz[i] = (unsigned short)(code | (zm << 8));
-				s.u.r.recA[i] = matId | (matBlend << 8) | (slotK << 16);
-			}
-			__syncthreads();
-
-			// ---- pass B: new-vs-reuse decisions ----
-			for (unsigned i = tid; i < ntc; i += VXB_THREADS)
-			{
-				const int c = s.u.r.list[i];
-				const unsigned code = s.u.r.cz[i] & 0xFF, zm = s.u.r.cz[i] >> 8;
-				const unsigned geo = s.tabCell[s.tabClass[code] * 16];
-				const int mask = vxb_emit_mask(s, c, i);
-				const unsigned myMat = s.u.r.recA[i] & 0xFF;
-				unsigned newMask = 0, quirkMask = 0;
-				for (int k = 0; k < (int)(geo >> 4); ++k)
-				{
-					const VxbVertexDesc vd = vxb_regular_vertex_desc_lite(s.tabVert[code * 12 + k], zm);
-					const VxbDecision dec = vxb_emit_decide(s, c, mask, vd, myMat);
-					if (dec.isNew) newMask |= 1u << k;
-					if (dec.quirkV0) quirkMask |= 1u << k;
-				}
-				s.u.r.recB[i] = newMask | (quirkMask << 12);
-				s.u.r.vbase[i] = (unsigned short)__popc(newMask);
-				s.u.r.tbase[i] = (unsigned short)(geo & 0xF);
-			}
-			__syncthreads();
-
-			// ---- exclusive scans in serial cell order (contiguous chunk per thread) ----
-			{
-				const unsigned per = (ntc + VXB_THREADS - 1) / VXB_THREADS;
-				const unsigned i0 = min(tid * per, ntc), i1 = min(i0 + per, ntc);
-				unsigned sv = 0, st = 0;
-				for (unsigned i = i0; i < i1; ++i) { sv += s.u.r.vbase[i]; st += s.u.r.tbase[i]; }
-				unsigned total;
-				const unsigned base = vxb_block_scan(sv | (st << 16), s.warpSums, total);
-				nverts = total & 0xFFFF; ntris = total >> 16;
-				unsigned bv = base & 0xFFFF, bt = base >> 16;
-				if (nverts <= (unsigned)CAP_V || CAP_V >= 49152)
-					for (unsigned i = i0; i < i1; ++i)
-					{
-						const unsigned cv = s.u.r.vbase[i], ct = s.u.r.tbase[i];
-						s.u.r.vbase[i] = (unsigned short)bv; s.u.r.tbase[i] = (unsigned short)bt;
-						bv += cv; bt += ct;
-					}
-			}
-			reject = nverts > (unsigned)CAP_V;
-		}
-
-		if (reject)
-		{
-			if (tid == 0)
-			{
-				if (TIER == 0) d.bigList[atomicAdd(&d.counters->bigCount, 1u)] = emitIdx;
-				else d.genList[atomicAdd(&d.counters->genCount, 1u)] = emitIdx;
-			}
+			if (tid == 0) d.bigList[atomicAdd(&d.counters->bigCount, 1u)] = emitIdx; // only reachable in TIER 0
 			__syncthreads();
 			continue;
 		}
+		vxb_stage_tile(s.tile, &s.mbar, phase, &tmap, g, d.n, level, bx, by, bz);
+		// ordered compact list of the non-trivial cells: thread = cell row (z, y), 16 bits each
+		{
+			unsigned bits = reinterpret_cast<const unsigned short*>(s.nt32)[tid];
+			unsigned pos = s.wpre[tid >> 1] + ((tid & 1) ? __popc(s.nt32[tid >> 1] & 0xFFFFu) : 0u);
+			while (bits) { const int x = __ffs(bits) - 1; bits &= bits - 1; s.list[pos++] = (unsigned short)(tid * 16 + x); }
+		}
+		__syncthreads();
 
+		// ---- pass A: material, case code, zero mask, owned slots ----
+		for (unsigned i = tid; i < ntc; i += VXB_THREADS)
+		{
+			const int c = s.list[i];
+			signed char v[8];
+			vxb_tile_samples(s.tile, c, v);
+			const unsigned code = vxb_case_code(v);
+			const unsigned zm = vxb_zero_mask(v);
+			unsigned matId, matBlend;
+			if (level == 0)
+			{
+				const size_t gi = ((size_t)((bz * 16 + (c >> 8))) * d.n + (by * 16 + ((c >> 4) & 15))) * d.n + (bx * 16 + (c & 15));
+				matId = g.mat[gi]; matBlend = g.blend[gi];
+			}
+			else
+			{
+				const unsigned e = d.cachePages[level][(size_t)coordId * 4096 + c]; // written by vxb_classify_kernel
+				matId = e & 0xFF; matBlend = e >> 8;
+			}
+			unsigned slotK = 0xFFFFu;
+			const int nv = s.tabCell[s.tabClass[code] * 16] >> 4;
+			for (int k = 0; k < nv; ++k)
+			{
+				const VxbVertexDesc vd = vxb_regular_vertex_desc_lite(s.tabVert[code * 12 + k], zm);
+				const int sl = vxb_regular_owned_slot(vd);
+				if (sl >= 0) slotK = (slotK & ~(0xFu << (4 * sl))) | ((unsigned)k << (4 * sl));
+			}
+			s.cz[i] = (unsigned short)(code | (zm << 8));
+			s.recA[i] = matId | (matBlend << 8) | (slotK << 16);
+		}
+		__syncthreads();
+
+		// ---- pass B: new-vs-reuse decisions ----
+		for (unsigned i = tid; i < ntc; i += VXB_THREADS)
+		{
+			const int c = s.list[i];
+			const unsigned code = s.cz[i] & 0xFF, zm = s.cz[i] >> 8;
+			const unsigned geo = s.tabCell[s.tabClass[code] * 16];
+			const unsigned rowStart = vxb_rank_of(s.nt32, s.wpre, c & ~15), sliceStart = s.wpre[(c >> 8) * 8];
+			const int mask = (i > rowStart ? 1 : 0) | (rowStart > sliceStart ? 2 : 0) | (sliceStart > 0 ? 4 : 0);
+			const unsigned myMat = s.recA[i] & 0xFF;
+			unsigned newMask = 0, quirkMask = 0;
+			for (int k = 0; k < (int)(geo >> 4); ++k)
+			{
+				// new-vs-reuse decision (:1610-1644) from the owner cell's record
+				const VxbVertexDesc vd = vxb_regular_vertex_desc_lite(s.tabVert[code * 12 + k], zm);
+				bool isNew = true;
+				if (!vd.atC7 && (vd.dir & mask) == vd.dir) // dir == 8 never passes: mask < 8
+				{
+					const int oc = c - (vd.dir & 1) - ((vd.dir >> 1) & 1) * 16 - ((vd.dir >> 2) & 1) * 256;
+					int ok = VXB_NO_SLOT; unsigned oa = 0;
+					if ((s.nt32[oc >> 5] >> (oc & 31)) & 1u)
+					{
+						oa = s.recA[vxb_rank_of(s.nt32, s.wpre, oc)];
+						ok = (oa >> (16 + 4 * vd.slot)) & 0xF;
+					}
+					if (ok != VXB_NO_SLOT) { if ((oa & 0xFF) == myMat) isNew = false; } // else: material split, new at its natural place
+					else if (vd.endpoint) quirkMask |= 1u << k;                            // :1633-1640 creates the vertex at v0
+				}
+				if (isNew) newMask |= 1u << k;
+			}
+			s.recB[i] = newMask | (quirkMask << 12) | ((unsigned)mask << 24);
+			s.vbase[i] = (unsigned short)__popc(newMask);
+			s.tbase[i] = (unsigned short)(geo & 0xF);
+		}
+		__syncthreads();
+
+		// ---- exclusive scans in serial cell order (contiguous chunk per thread) ----
+		unsigned nverts, ntris;
+		{
+			const unsigned per = (ntc + VXB_THREADS - 1) / VXB_THREADS;
+			const unsigned i0 = min(tid * per, ntc), i1 = min(i0 + per, ntc);
+			unsigned sv = 0, st = 0;
+			for (unsigned i = i0; i < i1; ++i) { sv += s.vbase[i]; st += s.tbase[i]; }
+			unsigned total;
+			const unsigned base = vxb_block_scan(sv | (st << 16), s.warpSums, total);
+			nverts = total & 0xFFFF; ntris = total >> 16;
+			unsigned bv = base & 0xFFFF, bt = base >> 16;
+			for (unsigned i = i0; i < i1; ++i)
+			{
+				const unsigned cv = s.vbase[i], ct = s.tbase[i];
+				s.vbase[i] = (unsigned short)bv; s.tbase[i] = (unsigned short)bt;
+				bv += cv; bt += ct;
+			}
+		}
 		if (tid == 0)
 		{
 			s.voff = atomicAdd(&d.counters->vertices, nverts);
 			s.ioff = atomicAdd(&d.counters->indices, ntris * 3);
+			s.cellBase = atomicAdd(&d.counters->cells, ntc);
+			s.slot = atomicAdd(&d.counters->records, 1u);
 		}
 		__syncthreads();
-		const unsigned voff = s.voff, ioff = s.ioff;
-		const bool fits = (unsigned long long)voff + nverts <= d.vcap && (unsigned long long)ioff + ntris * 3ull <= d.icap;
-
+		const unsigned voff = s.voff, ioff = s.ioff, cellBase = s.cellBase, slot = s.slot;
+		const bool fits = (unsigned long long)voff + nverts <= d.vcap && (unsigned long long)ioff + ntris * 3ull <= d.icap
+			&& (unsigned long long)cellBase + ntc <= d.ccap && slot < d.rcap;
 		if (fits)
 		{
-			// new-vertex list: vertex j -> (compact cell, table vertex)
 			for (unsigned i = tid; i < ntc; i += VXB_THREADS)
 			{
-				unsigned nm = s.u.r.recB[i] & 0xFFFu, j = s.u.r.vbase[i];
-				while (nm) { const int k = __ffs(nm) - 1; nm &= nm - 1; s.u.r.vlist[j++] = (unsigned short)((i << 4) | k); }
+				const unsigned rb = s.recB[i];
+				VxbCellRec cr;
+				cr.a = (unsigned)s.list[i] | ((unsigned)s.cz[i] << 12) | ((rb >> 24) << 28);
+				cr.b = s.recA[i];
+				cr.c = rb & 0x00FFFFFFu;
+				cr.d = (unsigned)s.vbase[i] | ((unsigned)s.tbase[i] << 16);
+				*reinterpret_cast<uint4*>(&d.cellRecs[cellBase + i]) = *reinterpret_cast<const uint4*>(&cr);
+				d.cellBlock[cellBase + i] = slot;
+				unsigned nm = rb & 0xFFFu, j = voff + s.vbase[i];
+				while (nm) { const int k = __ffs(nm) - 1; nm &= nm - 1; d.vlist[j++] = ((cellBase + i) << 4) | (unsigned)k; }
 			}
-			__syncthreads();
-
-			// ---- pass C: one thread per new vertex ----
-			for (unsigned j = tid; j < nverts; j += VXB_THREADS)
+			if (tid == 0)
 			{
-				const unsigned e = s.u.r.vlist[j];
-				const unsigned i = e >> 4; const int k = e & 15;
-				const int c = s.u.r.list[i];
-				const int local[3] = { c & 15, (c >> 4) & 15, c >> 8 };
-				const int base[3] = { (bx * 16 + local[0]) * m, (by * 16 + local[1]) * m, (bz * 16 + local[2]) * m };
-				const unsigned code = s.u.r.cz[i] & 0xFF, zm = s.u.r.cz[i] >> 8;
-				const unsigned ra = s.u.r.recA[i];
-				const unsigned matId = ra & 0xFF, matBlend = (ra >> 8) & 0xFF;
-				VxbVertexDesc vd = vxb_regular_vertex_desc_lite(s.tabVert[code * 12 + k], zm);
-				if (!vd.endpoint && level == 0)
+				VxbBlockRec br;
+				br.packed = packed; br.emitIdx = emitIdx; br.voff = voff; br.ioff = ioff; br.cellBase = cellBase;
+				br.ntc = ntc; br.nverts = nverts; br.ntris = ntris; br.removed = 0;
+				for (int f = 0; f < 6; ++f) { br.tvoff[f] = 0; br.tioff[f] = 0; br.tvcount[f] = 0; br.ticount[f] = 0; }
+				br.pad[0] = br.pad[1] = br.pad[2] = 0;
+				d.blockRecs[slot] = br;
+				if (level > 0 && level != d.lastLevel && d.transitions) d.transList[atomicAdd(&d.counters->transBlocks, 1u)] = slot;
+			}
+		}
+		__syncthreads();
+	}
+}
+
+// true when an arena overflowed: the host grows the arenas and repeats the run, the later kernels do nothing
+__device__ __forceinline__ bool vxb_overflowed(const VxbDev& d)
+{
+	const VxbCounters* c = d.counters;
+	return c->vertices > d.vcap || c->indices > d.icap || c->cells > d.ccap || c->records > d.rcap;
+}
+
+// ------------------------------------------------------------------------------------------------
+// flat kernels
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(VXB_THREADS) vxb_vertex_kernel(const VxbDev d)
+{
+	__shared__ unsigned sUsed[8];
+	if (threadIdx.x < 8) sUsed[threadIdx.x] = 0;
+	__syncthreads();
+	if (!vxb_overflowed(d))
+	{
+		const VxbGrid g = d.grid;
+		const unsigned total = d.counters->vertices;
+		for (unsigned j = blockIdx.x * blockDim.x + threadIdx.x; j < total; j += gridDim.x * blockDim.x)
+		{
+			const unsigned e = d.vlist[j];
+			const unsigned ci = e >> 4; const int k = e & 15;
+			const uint4 crv = *reinterpret_cast<const uint4*>(&d.cellRecs[ci]);
+			const unsigned packed = d.blockRecs[d.cellBlock[ci]].packed;
+			const int level = (int)(packed >> 28);
+			const unsigned coordId = packed & 0x0FFFFFFFu;
+			const int m = 1 << level, nb = d.n / 16 / m;
+			const int c = crv.x & 0xFFF;
+			const unsigned code = (crv.x >> 12) & 0xFF, zm = (crv.x >> 20) & 0xFF;
+			const int local[3] = { c & 15, (c >> 4) & 15, c >> 8 };
+			const int base[3] = { (int)((coordId % nb) * 16 + local[0]) * m, (int)(((coordId / nb) % nb) * 16 + local[1]) * m, (int)((coordId / (nb * nb)) * 16 + local[2]) * m };
+			const unsigned matId = crv.y & 0xFF, matBlend = (crv.y >> 8) & 0xFF;
+			VxbVertexDesc vd = vxb_regular_vertex_desc_lite(vxbGRegularVertexData[code * 12 + k], zm);
+			VxbRawVertex rv;
+			if (vd.endpoint)
+			{
+				const bool quirk = (crv.z >> (12 + k)) & 1u;
+				vxb_corner_vertex(g, level, base, local, quirk ? vd.v0 : ((vd.t == 0) ? vd.v1 : vd.v0), matId, matBlend, rv);
+			}
+			else
+			{
+				if (level == 0)
 				{
-					const signed char* p = s.tile + (local[2] * 17 + local[1]) * VXB_TILE_PITCH + local[0];
-					const int a = p[(vd.v0 & 1) + ((vd.v0 >> 1) & 1) * VXB_TILE_PITCH + (vd.v0 >> 2) * 17 * VXB_TILE_PITCH];
-					const int b = p[(vd.v1 & 1) + ((vd.v1 >> 1) & 1) * VXB_TILE_PITCH + (vd.v1 >> 2) * 17 * VXB_TILE_PITCH];
+					const int a = vxb_dist(g, base[0] + (vd.v0 & 1), base[1] + ((vd.v0 >> 1) & 1), base[2] + (vd.v0 >> 2));
+					const int b = vxb_dist(g, base[0] + (vd.v1 & 1), base[1] + ((vd.v1 >> 1) & 1), base[2] + (vd.v1 >> 2));
 					vd.t = vxb_fixed_t(a, b); // :1591 (coarser levels recompute t after the LOD descent)
 				}
-				VxbRawVertex rv;
-				if (vd.endpoint)
-				{
-					const bool quirk = (s.u.r.recB[i] >> (12 + k)) & 1u;
-					vxb_corner_vertex(g, level, base, local, quirk ? vd.v0 : ((vd.t == 0) ? vd.v1 : vd.v0), matId, matBlend, rv);
-				}
-				else vxb_edge_vertex(g, level, base, local, vd, matId, matBlend, rv);
-				vxb_regular_secondary(level, rv);
-				VxbVertex ov;
-				vxb_finish_vertex(rv, *d.lut, ov);
-				vxb_store_vertex(d.verts + voff + j, ov);
-				atomicOr(&s.used[matId >> 5], 1u << (matId & 31));
+				vxb_edge_vertex(g, level, base, local, vd, matId, matBlend, rv);
 			}
-			__syncthreads(); // the block's vertices are visible to the whole CTA
+			vxb_regular_secondary(level, rv);
+			VxbVertex ov;
+			vxb_finish_vertex(rv, *d.lut, ov);
+			vxb_store_vertex(d.verts + j, ov);
+			atomicOr(&sUsed[matId >> 5], 1u << (matId & 31));
+		}
+	}
+	__syncthreads();
+	if (threadIdx.x < 8 && sUsed[threadIdx.x]) atomicOr(&d.counters->usedMaterials[threadIdx.x], sUsed[threadIdx.x]);
+}
 
-			// ---- pass D: triangles + degenerate filter (:1300-1321) ----
-			unsigned myRemoved = 0;
-			for (unsigned i = tid; i < ntc; i += VXB_THREADS)
+__global__ void __launch_bounds__(VXB_THREADS) vxb_triangle_kernel(const VxbDev d)
+{
+	if (vxb_overflowed(d)) return;
+	const unsigned total = d.counters->cells;
+	for (unsigned ci = blockIdx.x * blockDim.x + threadIdx.x; ci < total; ci += gridDim.x * blockDim.x)
+	{
+		const uint4 crv = *reinterpret_cast<const uint4*>(&d.cellRecs[ci]);
+		const unsigned slot = d.cellBlock[ci];
+		const VxbBlockRec* br = &d.blockRecs[slot];
+		const unsigned voff = br->voff, ioff = br->ioff, cellBase = br->cellBase;
+		const unsigned int* nt32 = d.ntScratch + (size_t)br->emitIdx * 256;
+		const unsigned int* wpre = nt32 + 128;
+		const int c = crv.x & 0xFFF;
+		const unsigned code = (crv.x >> 12) & 0xFF, zm = (crv.x >> 20) & 0xFF;
+		const int mask = (int)(crv.x >> 28);
+		const unsigned cls = vxbGRegularCellClass[code];
+		const unsigned char* cd = &vxbGRegularCellData[cls * 16];
+		const unsigned geo = cd[0];
+		const unsigned myMat = crv.y & 0xFF, newMask = crv.z & 0xFFF;
+		unsigned vids[12];
+		unsigned nextNew = crv.w & 0xFFFF;
+		for (int k = 0; k < (int)(geo >> 4); ++k)
+		{
+			if ((newMask >> k) & 1u) { vids[k] = nextNew++; continue; }
+			const VxbVertexDesc vd = vxb_regular_vertex_desc_lite(vxbGRegularVertexData[code * 12 + k], zm);
+			const int oc = c - (vd.dir & 1) - ((vd.dir >> 1) & 1) * 16 - ((vd.dir >> 2) & 1) * 256; // reused => the owner exists
+			const unsigned oi = vxb_rank_of(nt32, wpre, oc);
+			const uint4 orec = *reinterpret_cast<const uint4*>(&d.cellRecs[cellBase + oi]);
+			const unsigned ok = (orec.y >> (16 + 4 * vd.slot)) & 0xF;
+			vids[k] = (orec.w & 0xFFFF) + __popc(orec.z & 0xFFFu & ((1u << ok) - 1u));
+		}
+		(void)mask; (void)myMat;
+		unsigned* out = d.idx + ioff + (crv.w >> 16) * 3;
+		unsigned removed = 0;
+		for (unsigned tr = 0; tr < (geo & 0xF); ++tr, out += 3)
+		{
+			const unsigned a = vids[cd[1 + tr * 3]], b = vids[cd[2 + tr * 3]], cc = vids[cd[3 + tr * 3]];
+			const float* fa = d.verts[voff + a].pos; const float* fb = d.verts[voff + b].pos; const float* fc = d.verts[voff + cc].pos;
+			// back to grid axes, x256 (exact: positions are multiples of 1/256)
+			const float pa[3] = { fa[0] * 256.f, fa[2] * 256.f, fa[1] * 256.f };
+			const float pb[3] = { fb[0] * 256.f, fb[2] * 256.f, fb[1] * 256.f };
+			const float pc[3] = { fc[0] * 256.f, fc[2] * 256.f, fc[1] * 256.f };
+			if (vxb_triangle_kept(pa, pb, pc)) { out[0] = a; out[1] = b; out[2] = cc; }
+			else { out[0] = 0xFFFFFFFFu; out[1] = 0xFFFFFFFFu; out[2] = 0xFFFFFFFFu; ++removed; }
+		}
+		if (removed) atomicAdd(&d.blockRecs[slot].removed, removed);
+	}
+}
+
+// per emitted block: compaction of the triangle list where degenerate triangles were removed + the directory record
+__global__ void __launch_bounds__(VXB_THREADS) vxb_finish_kernel(const VxbDev d)
+{
+	__shared__ unsigned sWarp[8];
+	__shared__ unsigned sItem;
+	if (vxb_overflowed(d)) return;
+	const int tid = threadIdx.x;
+	const unsigned count = d.counters->records;
+	unsigned statRemoved = 0;
+	for (;;)
+	{
+		if (tid == 0) sItem = atomicAdd(&d.counters->finishCursor, VXB_THREADS);
+		__syncthreads();
+		const unsigned first = sItem;
+		if (first >= count) break;
+		// fast path: one thread per block writes the record when nothing was removed
+		const unsigned slot = first + tid;
+		unsigned removed = 0;
+		if (slot < count) removed = d.blockRecs[slot].removed;
+		const unsigned anyRemoved = __syncthreads_or(removed != 0);
+		if (anyRemoved)
+		{
+			for (unsigned q = 0; q < VXB_THREADS && first + q < count; ++q) // block-uniform loop
 			{
-				const int c = s.u.r.list[i];
-				const unsigned code = s.u.r.cz[i] & 0xFF, zm = s.u.r.cz[i] >> 8;
-				const unsigned cls = s.tabClass[code];
-				const unsigned geo = s.tabCell[cls * 16];
-				const unsigned ra = s.u.r.recA[i], rb = s.u.r.recB[i];
-				const int mask = vxb_emit_mask(s, c, i);
-				unsigned vids[12];
-				unsigned nextNew = s.u.r.vbase[i];
-				for (int k = 0; k < (int)(geo >> 4); ++k)
-				{
-					if ((rb >> k) & 1u) { vids[k] = nextNew++; continue; }
-					const VxbVertexDesc vd = vxb_regular_vertex_desc_lite(s.tabVert[code * 12 + k], zm);
-					const VxbDecision dec = vxb_emit_decide(s, c, mask, vd, ra & 0xFF);
-					vids[k] = s.u.r.vbase[dec.ownerIdx] + __popc(s.u.r.recB[dec.ownerIdx] & 0xFFFu & ((1u << dec.ok) - 1u));
-				}
-				unsigned* out = d.idx + ioff + (unsigned)s.u.r.tbase[i] * 3;
-				for (unsigned tr = 0; tr < (geo & 0xF); ++tr, out += 3)
-				{
-					const unsigned a = vids[s.tabCell[cls * 16 + 1 + tr * 3]];
-					const unsigned b = vids[s.tabCell[cls * 16 + 2 + tr * 3]];
-					const unsigned cc = vids[s.tabCell[cls * 16 + 3 + tr * 3]];
-					const float* fa = d.verts[voff + a].pos; const float* fb = d.verts[voff + b].pos; const float* fc = d.verts[voff + cc].pos;
-					// back to grid axes, x256 (exact: positions are multiples of 1/256)
-					const float pa[3] = { fa[0] * 256.f, fa[2] * 256.f, fa[1] * 256.f };
-					const float pb[3] = { fb[0] * 256.f, fb[2] * 256.f, fb[1] * 256.f };
-					const float pc[3] = { fc[0] * 256.f, fc[2] * 256.f, fc[1] * 256.f };
-					if (vxb_triangle_kept(pa, pb, pc)) { out[0] = a; out[1] = b; out[2] = cc; }
-					else { out[0] = 0xFFFFFFFFu; out[1] = 0xFFFFFFFFu; out[2] = 0xFFFFFFFFu; ++myRemoved; }
-				}
-			}
-			if (myRemoved) atomicAdd(&s.removed, myRemoved);
-			__syncthreads();
-			const unsigned removed = s.removed;
-			if (removed)
-			{
-				// order-preserving in-place compaction of this block's triangle list
+				const VxbBlockRec* br = &d.blockRecs[first + q];
+				if (!br->removed) continue;
+				const unsigned ntris = br->ntris, ioff = br->ioff;
 				unsigned written = 0;
 				for (unsigned t0 = 0; t0 < ntris; t0 += VXB_THREADS)
 				{
@@ -544,106 +558,152 @@ __global__ void __launch_bounds__(VXB_THREADS, (CAP_C <= 1024 ? 4 : 2)) vxb_emit
 					if (t < ntris) { const unsigned* in = d.idx + ioff + t * 3; a = in[0]; b = in[1]; cc = in[2]; }
 					const bool keep = (t < ntris) && a != 0xFFFFFFFFu;
 					unsigned chunkTotal;
-					const unsigned pos = vxb_block_scan(keep ? 1u : 0u, s.warpSums, chunkTotal);
+					const unsigned pos = vxb_block_scan(keep ? 1u : 0u, sWarp, chunkTotal);
 					if (keep) { unsigned* out = d.idx + ioff + (written + pos) * 3; out[0] = a; out[1] = b; out[2] = cc; }
 					written += chunkTotal;
 					__syncthreads();
 				}
-				if (tid == 0) statRemoved += removed;
 			}
 		}
-
-		// ---- transition cells, all six faces at once (:1754-2131); materials come from the level's page ----
-		unsigned tvCount[6] = { 0, 0, 0, 0, 0, 0 }, tiCount[6] = { 0, 0, 0, 0, 0, 0 };
-		if (midLevel && d.transitions && fits)
+		if (slot < count)
 		{
-			__syncthreads(); // the regular-cell arrays are dead: their storage becomes the transition scratch
-			const int row = tid >> 4, col = tid & 15;
-			unsigned codes[6], newMasks[6];
-			unsigned activeFaces = 0;
-#pragma unroll
-			for (int face = 0; face < 6; ++face)
+			const VxbBlockRec br = d.blockRecs[slot];
+			vxb_block_record r;
+			const int level = (int)(br.packed >> 28);
+			const unsigned coordId = br.packed & 0x0FFFFFFFu;
+			r.level = level; r.coord_id = coordId; r.id = d.idBase[level] + coordId;
+			r.vertex_count = br.nverts; r.index_count = (br.ntris - br.removed) * 3;
+			r.vertex_offset = br.voff; r.index_offset = br.ioff;
+			for (int f = 0; f < 6; ++f)
 			{
-				int axis, ua, va;
-				vxb_face_axes(face, axis, ua, va);
-				const int bc = (axis == 0) ? bx : (axis == 1 ? by : bz);
-				codes[face] = 0; newMasks[face] = 0;
-				const bool active = !(face < 3 ? (bc == 0) : (bc == nb - 1)); // neighbour block inside the grid (:1829-1835)
-				if (active) activeFaces |= 1u << face;
-				bool nt = false;
-				if (active)
-				{
-					int local[3];
-					local[axis] = (face >= 3) ? 15 : 0; local[ua] = col; local[va] = row;
-					const int base[3] = { (bx * 16 + local[0]) * m, (by * 16 + local[1]) * m, (bz * 16 + local[2]) * m };
-					signed char v[9];
-#pragma unroll
-					for (int q = 0; q < 9; ++q)
-					{
-						int p[3];
-						vxb_transition_sample_pos(face, level, base, q, p);
-						v[q] = (signed char)vxb_dist(g, p[0], p[1], p[2]);
-					}
-					codes[face] = vxb_transition_case_code(v);
-					nt = codes[face] != 0u && codes[face] != 511u;
-				}
-				const unsigned bal = __ballot_sync(0xFFFFFFFFu, nt);
-				if (lane == 0) s.u.t.nt[face * 8 + warp] = bal;
-				if (!nt) codes[face] = 0;
+				// internal face order (z-,y-,x-,z+,y+,x+) is already the output enum order (YNeg,ZNeg,XNeg,YPos,ZPos,XPos)
+				r.trans_vertex_count[f] = br.tvcount[f]; r.trans_index_count[f] = br.ticount[f];
+				r.trans_vertex_offset[f] = br.tvcount[f] ? br.tvoff[f] : 0u; r.trans_index_offset[f] = br.ticount[f] ? br.tioff[f] : 0u;
 			}
-			// owned slots + material per non-trivial transition cell
-#pragma unroll
-			for (int face = 0; face < 6; ++face)
+			r.reserved = 0;
+			d.records[slot] = r;
+			statRemoved += br.removed;
+		}
+		__syncthreads();
+	}
+	if (statRemoved) atomicAdd(&d.counters->degenerate, statRemoved);
+}
+
+// ------------------------------------------------------------------------------------------------
+// transition cells (:1754-2131), one emitted mid-level block per CTA iteration, cell = face*256 + row*16 + col
+// ------------------------------------------------------------------------------------------------
+struct __align__(16) VxbTransSmem
+{
+	unsigned long long slots[1536]; // 10 owned-slot nibbles per cell
+	unsigned short code[1536];      // 9-bit transition case code, 0 = trivial / face without neighbour
+	unsigned short newMask[1536];
+	unsigned short vbase[1536];
+	unsigned short tbase[1536];
+	unsigned char mat[1536];
+	unsigned int nt[48];
+	unsigned int warpSums[8];
+	unsigned int used[8];
+	unsigned int tvoff[6], tioff[6], tvcount[6], ticount[6];
+	unsigned int item;
+};
+
+__global__ void __launch_bounds__(VXB_THREADS, 4) vxb_transition_kernel(const VxbDev d)
+{
+	extern __shared__ __align__(128) unsigned char smemRaw[];
+	VxbTransSmem& s = *reinterpret_cast<VxbTransSmem*>(smemRaw);
+	if (vxb_overflowed(d)) return;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int row = tid >> 4, col = tid & 15;
+	const VxbGrid g = d.grid;
+	if (tid < 8) s.used[tid] = 0;
+	const unsigned workCount = d.counters->transBlocks;
+	for (;;)
+	{
+		if (tid == 0) s.item = atomicAdd(&d.counters->transCursor, 1u);
+		if (tid < 6) { s.tvcount[tid] = 0; s.ticount[tid] = 0; s.tvoff[tid] = 0; s.tioff[tid] = 0; }
+		__syncthreads();
+		if (s.item >= workCount) break;
+		const unsigned slot = d.transList[s.item];
+		const unsigned packed = d.blockRecs[slot].packed;
+		const int level = (int)(packed >> 28);
+		const unsigned coordId = packed & 0x0FFFFFFFu;
+		const int m = 1 << level, nb = d.n / 16 / m;
+		const int bx = coordId % nb, by = (coordId / nb) % nb, bz = coordId / (nb * nb);
+
+		// T1: case codes (cell = thread, one face per iteration; thread order = the reference's row-major order)
+#pragma unroll 1
+		for (int face = 0; face < 6; ++face)
+		{
+			int axis, ua, va;
+			vxb_face_axes(face, axis, ua, va);
+			const int bc = (axis == 0) ? bx : (axis == 1 ? by : bz);
+			unsigned code = 0;
+			if (!(face < 3 ? (bc == 0) : (bc == nb - 1))) // neighbour block inside the grid (:1829-1835)
 			{
-				const int ci = face * 256 + tid;
-				unsigned long long slots = ~0ull;
-				unsigned matId = VXB_EMPTY_MATERIAL;
-				if (codes[face])
-				{
-					int axis, ua, va;
-					vxb_face_axes(face, axis, ua, va);
-					int local[3];
-					local[axis] = (face >= 3) ? 15 : 0; local[ua] = col; local[va] = row;
-					const int c = local[2] * 256 + local[1] * 16 + local[0];
-					matId = d.cachePages[level][(size_t)coordId * 4096 + c] & 0xFF;
-					const int base[3] = { (bx * 16 + local[0]) * m, (by * 16 + local[1]) * m, (bz * 16 + local[2]) * m };
-					signed char v[13];
-					for (int q = 0; q < 9; ++q) { int p[3]; vxb_transition_sample_pos(face, level, base, q, p); v[q] = (signed char)vxb_dist(g, p[0], p[1], p[2]); }
-					v[9] = v[0]; v[10] = v[2]; v[11] = v[6]; v[12] = v[8];
-					const unsigned code = codes[face];
-					const int nv = vxbGTransitionCellData[(vxbGTransitionCellClass[code] & 0x7F) * 40] >> 4;
-					for (int k = 0; k < nv; ++k)
-					{
-						const VxbTransVertexDesc td = vxb_transition_vertex_desc(vxbGTransitionVertexData[code * 12 + k], v, vxbGTransitionCornerData);
-						if (td.dir == 8) slots = (slots & ~(0xFull << (4 * td.slot))) | ((unsigned long long)k << (4 * td.slot)); // stored only when no reuse was attempted (:2097)
-					}
-				}
-				s.u.t.slots[ci] = slots;
-				s.u.t.mat[ci] = (unsigned char)matId;
-			}
-			__syncthreads();
-			// decisions
-			unsigned counts[6];
-#pragma unroll
-			for (int face = 0; face < 6; ++face)
-			{
-				counts[face] = 0;
-				if (!codes[face]) { s.u.t.newMask[face * 256 + tid] = 0; continue; }
-				int axis, ua, va;
-				vxb_face_axes(face, axis, ua, va);
 				int local[3];
 				local[axis] = (face >= 3) ? 15 : 0; local[ua] = col; local[va] = row;
 				const int base[3] = { (bx * 16 + local[0]) * m, (by * 16 + local[1]) * m, (bz * 16 + local[2]) * m };
 				signed char v[13];
-				for (int q = 0; q < 9; ++q) { int p[3]; vxb_transition_sample_pos(face, level, base, q, p); v[q] = (signed char)vxb_dist(g, p[0], p[1], p[2]); }
-				v[9] = v[0]; v[10] = v[2]; v[11] = v[6]; v[12] = v[8];
-				const unsigned code = codes[face];
-				const unsigned cls = vxbGTransitionCellClass[code];
-				const unsigned geo = vxbGTransitionCellData[(cls & 0x7F) * 40];
-				const unsigned rowBits = (s.u.t.nt[face * 8 + warp] >> (lane & 16)) & 0xFFFFu;
+				vxb_transition_samples(g, face, level, base, v);
+				code = vxb_transition_case_code(v);
+				if (code == 511u) code = 0;
+			}
+			const unsigned bal = __ballot_sync(0xFFFFFFFFu, code != 0u);
+			if (lane == 0) s.nt[face * 8 + warp] = bal;
+			s.code[face * 256 + tid] = (unsigned short)code;
+		}
+		// T2: owned slots + material of the non-trivial cells
+#pragma unroll 1
+		for (int face = 0; face < 6; ++face)
+		{
+			const int ci = face * 256 + tid;
+			const unsigned code = s.code[ci];
+			unsigned long long slots = ~0ull;
+			unsigned matId = VXB_EMPTY_MATERIAL;
+			if (code)
+			{
+				int axis, ua, va;
+				vxb_face_axes(face, axis, ua, va);
+				int local[3];
+				local[axis] = (face >= 3) ? 15 : 0; local[ua] = col; local[va] = row;
+				matId = d.cachePages[level][(size_t)coordId * 4096 + local[2] * 256 + local[1] * 16 + local[0]] & 0xFF;
+				const int base[3] = { (bx * 16 + local[0]) * m, (by * 16 + local[1]) * m, (bz * 16 + local[2]) * m };
+				signed char v[13];
+				vxb_transition_samples(g, face, level, base, v);
+				const int nv = vxbGTransitionCellData[(vxbGTransitionCellClass[code] & 0x7F) * 40] >> 4;
+				for (int k = 0; k < nv; ++k)
+				{
+					const VxbTransVertexDesc td = vxb_transition_vertex_desc(vxbGTransitionVertexData[code * 12 + k], v, vxbGTransitionCornerData);
+					if (td.dir == 8) slots = (slots & ~(0xFull << (4 * td.slot))) | ((unsigned long long)k << (4 * td.slot)); // stored only when no reuse was attempted (:2097)
+				}
+			}
+			s.slots[ci] = slots;
+			s.mat[ci] = (unsigned char)matId;
+		}
+		__syncthreads();
+		// T3: decisions + per-face ordered scans
+#pragma unroll 1
+		for (int face = 0; face < 6; ++face)
+		{
+			int axis, ua, va;
+			vxb_face_axes(face, axis, ua, va);
+			const int bc = (axis == 0) ? bx : (axis == 1 ? by : bz);
+			if (face < 3 ? (bc == 0) : (bc == nb - 1)) continue; // block-uniform
+			const int ci = face * 256 + tid;
+			const unsigned code = s.code[ci];
+			unsigned newMask = 0, ntri = 0;
+			if (code)
+			{
+				int local[3];
+				local[axis] = (face >= 3) ? 15 : 0; local[ua] = col; local[va] = row;
+				const int base[3] = { (bx * 16 + local[0]) * m, (by * 16 + local[1]) * m, (bz * 16 + local[2]) * m };
+				signed char v[13];
+				vxb_transition_samples(g, face, level, base, v);
+				const unsigned geo = vxbGTransitionCellData[(vxbGTransitionCellClass[code] & 0x7F) * 40];
+				ntri = geo & 0xF;
+				const unsigned rowBits = (s.nt[face * 8 + warp] >> (lane & 16)) & 0xFFFFu;
 				const int mask = ((row > 0) ? 2 : 0) | ((rowBits & ((1u << col) - 1u)) ? 1 : 0);
-				const unsigned myMat = s.u.t.mat[face * 256 + tid];
-				unsigned newMask = 0;
+				const unsigned myMat = s.mat[ci];
 				for (int k = 0; k < (int)(geo >> 4); ++k)
 				{
 					const VxbTransVertexDesc td = vxb_transition_vertex_desc(vxbGTransitionVertexData[code * 12 + k], v, vxbGTransitionCornerData);
@@ -651,111 +711,86 @@ __global__ void __launch_bounds__(VXB_THREADS, (CAP_C <= 1024 ? 4 : 2)) vxb_emit
 					if ((td.dir & mask) == td.dir)
 					{
 						const int oc = face * 256 + (row - ((td.dir >> 1) & 1)) * 16 + (col - (td.dir & 1));
-						const int ok = (int)((s.u.t.slots[oc] >> (4 * td.slot)) & 0xF); // trivial cells hold all-NO_SLOT
-						if (ok != VXB_NO_SLOT && s.u.t.mat[oc] == myMat) isNew = false;
+						const int ok = (int)((s.slots[oc] >> (4 * td.slot)) & 0xF); // trivial cells hold all-NO_SLOT
+						if (ok != VXB_NO_SLOT && s.mat[oc] == myMat) isNew = false;
 					}
 					if (isNew) newMask |= 1u << k;
 				}
-				newMasks[face] = newMask;
-				s.u.t.newMask[face * 256 + tid] = (unsigned short)newMask;
-				counts[face] = __popc(newMask) | ((geo & 0xF) << 16);
 			}
-			// per-face ordered scans (thread order = row-major cell order)
-			unsigned bases[6];
-#pragma unroll
-			for (int face = 0; face < 6; ++face)
+			s.newMask[ci] = (unsigned short)newMask;
+			unsigned total;
+			const unsigned base2 = vxb_block_scan(__popc(newMask) | (ntri << 16), s.warpSums, total);
+			s.vbase[ci] = (unsigned short)(base2 & 0xFFFF);
+			s.tbase[ci] = (unsigned short)(base2 >> 16);
+			if (tid == 0)
 			{
-				bases[face] = 0;
-				if (!((activeFaces >> face) & 1u)) continue; // block-uniform
-				unsigned total;
-				bases[face] = vxb_block_scan(counts[face], s.warpSums, total);
-				tvCount[face] = total & 0xFFFF; tiCount[face] = (total >> 16) * 3;
-				s.u.t.vbase[face * 256 + tid] = (unsigned short)(bases[face] & 0xFFFF);
-			}
-			if (tid < 6)
-			{
-				s.tvoff[tid] = tvCount[tid] ? atomicAdd(&d.counters->transVertices, tvCount[tid]) : 0u;
-				s.tioff[tid] = tiCount[tid] ? atomicAdd(&d.counters->transIndices, tiCount[tid]) : 0u;
-			}
-			__syncthreads();
-#pragma unroll
-			for (int face = 0; face < 6; ++face)
-			{
-				if (!codes[face]) continue;
-				const unsigned tvoff = s.tvoff[face], tioff = s.tioff[face];
-				if ((unsigned long long)tvoff + tvCount[face] > d.tvcap || (unsigned long long)tioff + tiCount[face] > d.ticap) continue;
-				int axis, ua, va;
-				vxb_face_axes(face, axis, ua, va);
-				int local[3];
-				local[axis] = (face >= 3) ? 15 : 0; local[ua] = col; local[va] = row;
-				const int c = local[2] * 256 + local[1] * 16 + local[0];
-				const int base[3] = { (bx * 16 + local[0]) * m, (by * 16 + local[1]) * m, (bz * 16 + local[2]) * m };
-				signed char v[13];
-				for (int q = 0; q < 9; ++q) { int p[3]; vxb_transition_sample_pos(face, level, base, q, p); v[q] = (signed char)vxb_dist(g, p[0], p[1], p[2]); }
-				v[9] = v[0]; v[10] = v[2]; v[11] = v[6]; v[12] = v[8];
-				const unsigned code = codes[face];
-				const unsigned cls = vxbGTransitionCellClass[code];
-				const unsigned char* cd = &vxbGTransitionCellData[(cls & 0x7F) * 40];
-				const int nv = cd[0] >> 4, ntri = cd[0] & 0xF;
-				const unsigned e = d.cachePages[level][(size_t)coordId * 4096 + c];
-				const unsigned matId = e & 0xFF, matBlend = e >> 8;
-				const unsigned rowBits = (s.u.t.nt[face * 8 + warp] >> (lane & 16)) & 0xFFFFu;
-				const int mask = ((row > 0) ? 2 : 0) | ((rowBits & ((1u << col) - 1u)) ? 1 : 0);
-				unsigned vids[12];
-				unsigned nextNew = bases[face] & 0xFFFF;
-				for (int k = 0; k < nv; ++k)
-				{
-					const VxbTransVertexDesc td = vxb_transition_vertex_desc(vxbGTransitionVertexData[code * 12 + k], v, vxbGTransitionCornerData);
-					if ((newMasks[face] >> k) & 1u)
-					{
-						VxbRawVertex rv;
-						vxb_transition_vertex(g, face, level, base, local, td, matId, matBlend, rv);
-						VxbVertex ov;
-						vxb_finish_vertex(rv, *d.lut, ov);
-						vxb_store_vertex(d.tverts + tvoff + nextNew, ov);
-						vids[k] = nextNew++;
-					}
-					else
-					{
-						const int oc = face * 256 + (row - ((td.dir >> 1) & 1)) * 16 + (col - (td.dir & 1));
-						const unsigned ok = (unsigned)((s.u.t.slots[oc] >> (4 * td.slot)) & 0xF);
-						vids[k] = s.u.t.vbase[oc] + __popc((unsigned)s.u.t.newMask[oc] & ((1u << ok) - 1u));
-					}
-				}
-				atomicOr(&s.used[matId >> 5], 1u << (matId & 31));
-				const bool flip = (((cls >> 7) & 1u) ^ (unsigned)(face & 1)) != 0;
-				unsigned* out = d.tidx + tioff + (bases[face] >> 16) * 3;
-				for (int tr = 0; tr < ntri; ++tr)
-				{
-					const unsigned a = vids[cd[1 + tr * 3]], b = vids[cd[2 + tr * 3]], cc = vids[cd[3 + tr * 3]];
-					out[tr * 3] = a; out[tr * 3 + 1] = flip ? cc : b; out[tr * 3 + 2] = flip ? b : cc;
-				}
-			}
-		}
-
-		// ---- directory record (PushBlocksToResult: blocks with >= 1 vertex, :1278) ----
-		if (tid == 0)
-		{
-			const unsigned slot = atomicAdd(&d.counters->records, 1u);
-			if (slot < d.rcap)
-			{
-				vxb_block_record r;
-				r.level = level; r.coord_id = coordId; r.id = d.idBase[level] + coordId;
-				r.vertex_count = nverts; r.index_count = (ntris - s.removed) * 3;
-				r.vertex_offset = voff; r.index_offset = ioff;
-				for (int f = 0; f < 6; ++f)
-				{
-					r.trans_vertex_count[f] = tvCount[f]; r.trans_index_count[f] = tiCount[f];
-					r.trans_vertex_offset[f] = tvCount[f] ? s.tvoff[f] : 0u; r.trans_index_offset[f] = tiCount[f] ? s.tioff[f] : 0u;
-				}
-				r.reserved = 0;
-				d.records[slot] = r;
+				const unsigned fv = total & 0xFFFF, fi = (total >> 16) * 3;
+				s.tvcount[face] = fv; s.ticount[face] = fi;
+				s.tvoff[face] = fv ? atomicAdd(&d.counters->transVertices, fv) : 0u;
+				s.tioff[face] = fi ? atomicAdd(&d.counters->transIndices, fi) : 0u;
 			}
 		}
 		__syncthreads();
+		// T4: emission
+#pragma unroll 1
+		for (int face = 0; face < 6; ++face)
+		{
+			const int ci = face * 256 + tid;
+			const unsigned code = s.code[ci];
+			if (!code) continue;
+			const unsigned tvoff = s.tvoff[face], tioff = s.tioff[face];
+			if ((unsigned long long)tvoff + s.tvcount[face] > d.tvcap || (unsigned long long)tioff + s.ticount[face] > d.ticap) continue;
+			int axis, ua, va;
+			vxb_face_axes(face, axis, ua, va);
+			int local[3];
+			local[axis] = (face >= 3) ? 15 : 0; local[ua] = col; local[va] = row;
+			const int c = local[2] * 256 + local[1] * 16 + local[0];
+			const int base[3] = { (bx * 16 + local[0]) * m, (by * 16 + local[1]) * m, (bz * 16 + local[2]) * m };
+			signed char v[13];
+			vxb_transition_samples(g, face, level, base, v);
+			const unsigned cls = vxbGTransitionCellClass[code];
+			const unsigned char* cd = &vxbGTransitionCellData[(cls & 0x7F) * 40];
+			const int nv = cd[0] >> 4, ntri = cd[0] & 0xF;
+			const unsigned e = d.cachePages[level][(size_t)coordId * 4096 + c];
+			const unsigned matId = e & 0xFF, matBlend = e >> 8;
+			const unsigned newMask = s.newMask[ci];
+			unsigned vids[12];
+			unsigned nextNew = s.vbase[ci];
+			for (int k = 0; k < nv; ++k)
+			{
+				const VxbTransVertexDesc td = vxb_transition_vertex_desc(vxbGTransitionVertexData[code * 12 + k], v, vxbGTransitionCornerData);
+				if ((newMask >> k) & 1u)
+				{
+					VxbRawVertex rv;
+					vxb_transition_vertex(g, face, level, base, local, td, matId, matBlend, rv);
+					VxbVertex ov;
+					vxb_finish_vertex(rv, *d.lut, ov);
+					vxb_store_vertex(d.tverts + tvoff + nextNew, ov);
+					vids[k] = nextNew++;
+				}
+				else
+				{
+					const int oc = face * 256 + (row - ((td.dir >> 1) & 1)) * 16 + (col - (td.dir & 1));
+					const unsigned ok = (unsigned)((s.slots[oc] >> (4 * td.slot)) & 0xF);
+					vids[k] = s.vbase[oc] + __popc((unsigned)s.newMask[oc] & ((1u << ok) - 1u));
+				}
+			}
+			atomicOr(&s.used[matId >> 5], 1u << (matId & 31));
+			const bool flip = (((cls >> 7) & 1u) ^ (unsigned)(face & 1)) != 0;
+			unsigned* out = d.tidx + tioff + (unsigned)s.tbase[ci] * 3;
+			for (int tr = 0; tr < ntri; ++tr)
+			{
+				const unsigned a = vids[cd[1 + tr * 3]], b = vids[cd[2 + tr * 3]], cc = vids[cd[3 + tr * 3]];
+				out[tr * 3] = a; out[tr * 3 + 1] = flip ? cc : b; out[tr * 3 + 2] = flip ? b : cc;
+			}
+		}
+		if (tid < 6)
+		{
+			VxbBlockRec* br = &d.blockRecs[slot];
+			br->tvoff[tid] = s.tvoff[tid]; br->tioff[tid] = s.tioff[tid]; br->tvcount[tid] = s.tvcount[tid]; br->ticount[tid] = s.ticount[tid];
+		}
+		__syncthreads();
 	}
-
 	__syncthreads();
 	if (tid < 8 && s.used[tid]) atomicOr(&d.counters->usedMaterials[tid], s.used[tid]);
-	if (tid == 0 && statRemoved) atomicAdd(&d.counters->degenerate, statRemoved);
 }

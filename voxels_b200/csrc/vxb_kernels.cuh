@@ -9,11 +9,10 @@
 //   per LOD level:
 //     vxb_select_kernel      block walk (GenerateBlockListForLevel :385-466 + AreBlockAndNeighborsEmpty
 //                            :1511-1527): appends the blocks that can produce output or side effects.
-//     vxb_polygonize_kernel  persistent CTAs, one 16^3 block at a time: TMA-staged 17^3 sample tile,
-//                            case codes, ordered (ballot + scan) compaction that reproduces the
-//                            reference's serial vertex numbering, vertex/triangle emission, degenerate
-//                            filter, transition cells (PolygonizeBlock :1529-1750,
-//                            GenerateTransitionCells :1754-2131, PushBlocksToResult :1266-1428).
+//     vxb_classify_kernel    (vxb_emit.cuh) tiles, case codes, material votes - the only cross-level dependency.
+//   then, once for all levels (vxb_emit.cuh): vxb_decide_kernel, vxb_vertex_kernel, vxb_triangle_kernel,
+//   vxb_transition_kernel, vxb_finish_kernel (PolygonizeBlock :1529-1750, GenerateTransitionCells :1754-2131,
+//   PushBlocksToResult :1266-1428).
 #pragma once
 
 #define VXB_MAX_LEVELS 12
@@ -41,8 +40,29 @@ struct VxbCounters
 	unsigned int workCursor[VXB_MAX_LEVELS];
 	unsigned int emitCount[VXB_MAX_LEVELS]; // blocks with non-trivial cells, per level (vxb_classify_kernel)
 	unsigned int emitCursor;
-	unsigned int bigCount, bigCursor;       // rejected by the small emit tier
-	unsigned int genCount, genCursor;       // rejected by the big emit tier -> generic kernel
+	unsigned int bigCount, bigCursor;       // blocks with > 1024 non-trivial cells (second tier of vxb_decide_kernel)
+	unsigned int cells;                     // cursor of the cell-record arena
+	unsigned int transBlocks, transCursor;  // emitted mid-level blocks (vxb_transition_kernel work list)
+	unsigned int finishCursor;
+};
+
+// One non-trivial cell of an emitted block (written by vxb_decide_kernel, read by the flat kernels)
+struct VxbCellRec
+{
+	unsigned int a; // cell id (0..4095) | case code << 12 | zero mask << 20 | reuse mask << 28
+	unsigned int b; // material id | blend << 8 | owned-slot nibbles << 16
+	unsigned int c; // new-vertex mask | v0-quirk mask << 12
+	unsigned int d; // vertex base | triangle base << 16 (block local, serial cell order)
+};
+
+// One emitted block (slot = directory slot)
+struct VxbBlockRec
+{
+	unsigned int packed;   // level << 28 | coordId
+	unsigned int emitIdx;  // index into emitList / ntScratch
+	unsigned int voff, ioff, cellBase, ntc, nverts, ntris, removed;
+	unsigned int tvoff[6], tioff[6], tvcount[6], ticount[6];
+	unsigned int pad[3];
 };
 
 struct VxbDev
@@ -65,9 +85,12 @@ struct VxbDev
 	const VxbMaterialLut* lut;
 	int transitions;
 	unsigned int* emitList;   // [workBase[l] + i] = level<<28 | coordId
-	unsigned int* ntScratch;  // 128 words of non-trivial bits per emit-list entry
+	unsigned int* ntScratch;  // per emit-list entry: 128 words of non-trivial bits + 128 words of their exclusive prefix
 	unsigned int* bigList;    // emit-list indices
-	unsigned int* genList;
+	unsigned int* transList;  // block slots of emitted mid-level blocks
+	VxbCellRec* cellRecs; unsigned int* cellBlock; unsigned int ccap;
+	unsigned int* vlist;      // vertex (arena index) -> cell record index << 4 | table vertex
+	VxbBlockRec* blockRecs;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -358,49 +381,10 @@ __device__ __forceinline__ void vxb_stage_tile(signed char* tile, unsigned long 
 	}
 }
 
-struct __align__(128) VxbPolySmem
-{
-	signed char tile[VXB_TILE_BYTES + 96]; // 17 x 17 rows of 32 bytes; [z][y][x]
-	unsigned int nt32[128];      // non-trivial cell bits, cell c -> word c>>5 bit c&31 (serial z,y,x order)
-	unsigned int wpre[132];      // exclusive prefix of popc(nt32): compact index base of each word; [128] = total
-	unsigned int recA[4096];     // per non-trivial cell (compact index): matId | matBlend<<8 | slotK<<16
-	unsigned int recB[4096];     // vbase | newMask<<16
-	unsigned short list[4096];   // compact index -> cell id
-	unsigned int warpSums[8];
-	unsigned int hist[16];
-	unsigned int used[8];
-	unsigned long long mbar;
-	unsigned int item;
-	unsigned int voff, ioff, tvoff, tioff;
-	unsigned int removed;
-	unsigned int hasChild;
-	unsigned int pageReady;
-	// transition scratch (one face at a time; cell = row*16 + col = thread id)
-	unsigned char tslot[256][10];
-	unsigned char tmat[256];
-	unsigned short tnew[256];
-	unsigned short tvbase[256];
-	unsigned int tnt[8];
-};
-
-__device__ __forceinline__ unsigned vxb_rank(const VxbPolySmem& s, int c)
-{
-	return s.wpre[c >> 5] + __popc(s.nt32[c >> 5] & ((1u << (c & 31)) - 1u));
-}
-
-__device__ __forceinline__ void vxb_cell_samples(const VxbPolySmem& s, int c, signed char v[8])
-{
-	const int lx = c & 15, ly = (c >> 4) & 15, lz = c >> 8;
-	const signed char* p = s.tile + (lz * 17 + ly) * VXB_TILE_PITCH + lx;
-	v[0] = p[0]; v[1] = p[1]; v[2] = p[VXB_TILE_PITCH]; v[3] = p[VXB_TILE_PITCH + 1];
-	p += 17 * VXB_TILE_PITCH;
-	v[4] = p[0]; v[5] = p[1]; v[6] = p[VXB_TILE_PITCH]; v[7] = p[VXB_TILE_PITCH + 1];
-}
-
 // CalculateMaterialForCellCache :753-838 for level >= 1, children read through the page tables.
 // The 8 children of a cell share one block of the child level (cell bases are even in child units), so the block
 // lookup and the validity test happen once, and the common all-empty case exits after 4 loads.
-__device__ __forceinline__ bool vxb_vote_cell(const VxbDev& d, int level, const int base[3], unsigned& id, unsigned& blend)
+__device__ __noinline__ bool vxb_vote_cell(const VxbDev& d, int level, const int base[3], unsigned& id, unsigned& blend)
 {
 	const int cm = (1 << level) >> 1, cnb = d.n / 16 / cm;
 	const int cx = base[0] / cm, cy = base[1] / cm, cz = base[2] / cm;            // child-level cell coordinates (even)
@@ -448,29 +432,6 @@ __device__ __forceinline__ bool vxb_vote_cell(const VxbDev& d, int level, const 
 
 struct VxbDecision { bool isNew, quirkV0; unsigned ownerIdx; int ok; };
 
-// new-vs-reuse decision for table vertex d of non-trivial cell c (compact index i) - :1610-1644
-__device__ __forceinline__ VxbDecision vxb_decide(const VxbPolySmem& s, int c, int mask, const VxbVertexDesc& d, unsigned myMat)
-{
-	VxbDecision r; r.isNew = true; r.quirkV0 = false; r.ownerIdx = 0; r.ok = VXB_NO_SLOT;
-	if (!d.atC7 && (d.dir & mask) == d.dir)
-	{
-		const int oc = c - (d.dir & 1) - ((d.dir >> 1) & 1) * 16 - ((d.dir >> 2) & 1) * 256;
-		int ok = VXB_NO_SLOT; unsigned oi = 0, oa = 0;
-		if ((s.nt32[oc >> 5] >> (oc & 31)) & 1u)
-		{
-			oi = vxb_rank(s, oc);
-			oa = s.recA[oi];
-			ok = (oa >> (16 + 4 * d.slot)) & 0xF;
-		}
-		if (ok != VXB_NO_SLOT)
-		{
-			if ((oa & 0xFF) == myMat) { r.isNew = false; r.ownerIdx = oi; r.ok = ok; }
-		}
-		else if (d.endpoint) r.quirkV0 = true;
-	}
-	return r;
-}
-
 __device__ __forceinline__ void vxb_store_vertex(VxbVertex* dst, const VxbVertex& v)
 {
 	const uint4* src = reinterpret_cast<const uint4*>(&v);
@@ -478,440 +439,3 @@ __device__ __forceinline__ void vxb_store_vertex(VxbVertex* dst, const VxbVertex
 	out[0] = src[0]; out[1] = src[1]; out[2] = src[2];
 }
 
-// Generic (capacity-unbounded) kernel: processes the blocks the two emit tiers of vxb_emit.cuh rejected
-// (> 4096... rather: > 12288 vertices in one block).  It redoes classification for its block (idempotent) and
-// leaves the per-class / non-trivial statistics to vxb_classify_kernel.
-__global__ void __launch_bounds__(VXB_THREADS) vxb_generic_kernel(const __grid_constant__ CUtensorMap tmap, const VxbDev d)
-{
-	extern __shared__ __align__(128) unsigned char smemRaw[];
-	VxbPolySmem& s = *reinterpret_cast<VxbPolySmem*>(smemRaw);
-	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	const VxbGrid g = d.grid;
-	unsigned phase = 0;
-
-	if (tid == 0) vxb_mbar_init(&s.mbar, 1);
-	if (tid < 16) s.hist[tid] = 0;
-	if (tid < 8) s.used[tid] = 0;
-	unsigned statRemoved = 0; // thread 0 accumulates
-	__syncthreads();
-
-	const unsigned workCount = d.counters->genCount;
-	for (;;)
-	{
-		if (tid == 0) s.item = atomicAdd(&d.counters->genCursor, 1u);
-		__syncthreads();
-		const unsigned item = s.item;
-		if (item >= workCount) break;
-		const unsigned packed = d.emitList[d.genList[item]];
-		const int level = (int)(packed >> 28);
-		const bool LEVEL0 = level == 0;
-		const unsigned coordId = packed & 0x0FFFFFFFu;
-		const int m = 1 << level, nb = d.n / 16 / m;
-		const bool midLevel = level > 0 && level != d.lastLevel;
-		const int bx = coordId % nb, by = (coordId / nb) % nb, bz = coordId / (nb * nb);
-
-		// ---- step 0: stage the 17^3 sample tile ----
-		vxb_stage_tile(s.tile, &s.mbar, phase, &tmap, g, d.n, level, bx, by, bz);
-		if (tid == 0) { s.removed = 0; s.pageReady = 0; s.hasChild = 0; s.voff = 0; s.ioff = 0; }
-		__syncthreads();
-
-		// ---- step 1: case codes, non-trivial ballots (serial order: z slices, 256 cells each) ----
-		unsigned myNt = 0; // bit z = my cell of slice z is non-trivial
-#pragma unroll 4
-		for (int z = 0; z < 16; ++z)
-		{
-			signed char v[8];
-			const int c = z * 256 + tid;
-			vxb_cell_samples(s, c, v);
-			const unsigned code = vxb_case_code(v);
-			const bool nt = (code != 0u && code != 255u);
-			const unsigned bal = __ballot_sync(0xFFFFFFFFu, nt);
-			if (lane == 0) s.nt32[z * 8 + warp] = bal;
-			myNt |= (nt ? 1u : 0u) << z;
-		}
-		__syncthreads();
-		unsigned ntc;
-		{
-			const unsigned cnt = (tid < 128) ? __popc(s.nt32[tid]) : 0u;
-			const unsigned ex = vxb_block_scan(cnt, s.warpSums, ntc);
-			if (tid < 128) s.wpre[tid] = ex;
-			if (tid == 0) s.wpre[128] = ntc;
-		}
-		__syncthreads();
-
-		unsigned nverts = 0, ntris = 0;
-		if (ntc > 0)
-		{
-			// compact list in serial order
-			for (int z = 0; z < 16; ++z)
-				if ((myNt >> z) & 1u) { const int c = z * 256 + tid; s.list[vxb_rank(s, c)] = (unsigned short)c; }
-
-			// pages: consistency bits (level 0) / material cache page (level >= 1)
-			if (LEVEL0)
-			{
-				if (tid < 128)
-				{
-					unsigned* page = d.consPages + (size_t)coordId * 128;
-					page[tid] = d.consValid[coordId] ? (page[tid] | s.nt32[tid]) : s.nt32[tid]; // bits are only ever set (:757)
-				}
-			}
-			else if (!d.cacheValid[level][coordId])
-			{
-				unsigned int* page = reinterpret_cast<unsigned int*>(d.cachePages[level] + (size_t)coordId * 4096);
-				for (int i = tid; i < 2048; i += VXB_THREADS) page[i] = 0x00FF00FFu; // {EMPTY_MATERIAL, 0} x 2  (:424)
-			}
-			__syncthreads();
-			if (tid == 0)
-			{
-				if (LEVEL0) d.consValid[coordId] = 1; else d.cacheValid[level][coordId] = 1;
-				s.pageReady = 1;
-			}
-
-			const unsigned per = (ntc + VXB_THREADS - 1) / VXB_THREADS;
-			const unsigned i0 = min(tid * per, ntc), i1 = min(i0 + per, ntc);
-
-			// ---- step 2: per non-trivial cell: material, table-vertex descriptors, owned slots ----
-			for (unsigned i = i0; i < i1; ++i)
-			{
-				const int c = s.list[i];
-				const int lx = c & 15, ly = (c >> 4) & 15, lz = c >> 8;
-				const int base[3] = { (bx * 16 + lx) * m, (by * 16 + ly) * m, (bz * 16 + lz) * m };
-				signed char v[8];
-				vxb_cell_samples(s, c, v);
-				const unsigned code = vxb_case_code(v);
-				const unsigned cls = vxbRegularCellClass[code];
-				unsigned matId = VXB_EMPTY_MATERIAL, matBlend = 0;
-				if (LEVEL0)
-				{
-					const size_t gi = ((size_t)base[2] * d.n + base[1]) * d.n + base[0];
-					matId = g.mat[gi]; matBlend = g.blend[gi];
-				}
-				else if (vxb_vote_cell(d, level, base, matId, matBlend))
-					d.cachePages[level][(size_t)coordId * 4096 + c] = (unsigned short)(matId | (matBlend << 8));
-				else { matId = VXB_EMPTY_MATERIAL; matBlend = 0; }
-				unsigned slotK = 0xFFFFu;
-				const int nv = vxbRegularCellData[cls * 16] >> 4;
-				for (int k = 0; k < nv; ++k)
-				{
-					const VxbVertexDesc vd = vxb_regular_vertex_desc(vxbRegularVertexData[code * 12 + k], v);
-					const int sl = vxb_regular_owned_slot(vd);
-					if (sl >= 0) slotK = (slotK & ~(0xFu << (4 * sl))) | ((unsigned)k << (4 * sl));
-				}
-				s.recA[i] = matId | (matBlend << 8) | (slotK << 16);
-			}
-			__syncthreads();
-
-			// ---- step 3: new-vs-reuse decisions -> counts ----
-			unsigned myVerts = 0, myTris = 0;
-			for (unsigned i = i0; i < i1; ++i)
-			{
-				const int c = s.list[i];
-				signed char v[8];
-				vxb_cell_samples(s, c, v);
-				const unsigned code = vxb_case_code(v);
-				const unsigned cls = vxbRegularCellClass[code];
-				const unsigned geo = vxbRegularCellData[cls * 16];
-				const unsigned rowStart = vxb_rank(s, c & ~15), sliceStart = s.wpre[(c >> 8) * 8];
-				const int mask = (i > rowStart ? 1 : 0) | (rowStart > sliceStart ? 2 : 0) | (sliceStart > 0 ? 4 : 0);
-				const unsigned myMat = s.recA[i] & 0xFF;
-				unsigned newMask = 0;
-				for (int k = 0; k < (int)(geo >> 4); ++k)
-				{
-					const VxbVertexDesc vd = vxb_regular_vertex_desc(vxbRegularVertexData[code * 12 + k], v);
-					if (vxb_decide(s, c, mask, vd, myMat).isNew) newMask |= 1u << k;
-				}
-				s.recB[i] = newMask << 16;
-				myVerts += __popc(newMask);
-				myTris += geo & 0xF;
-			}
-			unsigned packedTotal;
-			const unsigned packedBase = vxb_block_scan(myVerts | (myTris << 16), s.warpSums, packedTotal);
-			nverts = packedTotal & 0xFFFF; ntris = packedTotal >> 16;
-			{
-				unsigned vb = packedBase & 0xFFFF;
-				for (unsigned i = i0; i < i1; ++i) { const unsigned nm = s.recB[i] >> 16; s.recB[i] = vb | (nm << 16); vb += __popc(nm); }
-			}
-			if (tid == 0)
-			{
-				s.voff = atomicAdd(&d.counters->vertices, nverts);
-				s.ioff = atomicAdd(&d.counters->indices, ntris * 3);
-			}
-			__syncthreads();
-			const unsigned voff = s.voff, ioff = s.ioff;
-			const bool fits = (unsigned long long)voff + nverts <= d.vcap && (unsigned long long)ioff + ntris * 3ull <= d.icap;
-
-			if (fits)
-			{
-				// ---- step 4: emit the new vertices ----
-				for (unsigned i = i0; i < i1; ++i)
-				{
-					const int c = s.list[i];
-					const int lx = c & 15, ly = (c >> 4) & 15, lz = c >> 8;
-					const int local[3] = { lx, ly, lz };
-					const int base[3] = { (bx * 16 + lx) * m, (by * 16 + ly) * m, (bz * 16 + lz) * m };
-					signed char v[8];
-					vxb_cell_samples(s, c, v);
-					const unsigned code = vxb_case_code(v);
-					const unsigned cls = vxbRegularCellClass[code];
-					const unsigned ra = s.recA[i], rb = s.recB[i];
-					const unsigned matId = ra & 0xFF, matBlend = (ra >> 8) & 0xFF, newMask = rb >> 16;
-					if (!newMask) continue;
-					const unsigned rowStart = vxb_rank(s, c & ~15), sliceStart = s.wpre[(c >> 8) * 8];
-					const int mask = (i > rowStart ? 1 : 0) | (rowStart > sliceStart ? 2 : 0) | (sliceStart > 0 ? 4 : 0);
-					unsigned vid = voff + (rb & 0xFFFF);
-					atomicOr(&s.used[matId >> 5], 1u << (matId & 31));
-					const int nv = vxbRegularCellData[cls * 16] >> 4;
-					for (int k = 0; k < nv; ++k)
-					{
-						if (!((newMask >> k) & 1u)) continue;
-						const VxbVertexDesc vd = vxb_regular_vertex_desc(vxbRegularVertexData[code * 12 + k], v);
-						VxbRawVertex rv;
-						if (vd.endpoint)
-						{
-							const bool quirk = vxb_decide(s, c, mask, vd, matId).quirkV0;
-							vxb_corner_vertex(g, level, base, local, quirk ? vd.v0 : ((vd.t == 0) ? vd.v1 : vd.v0), matId, matBlend, rv);
-						}
-						else vxb_edge_vertex(g, level, base, local, vd, matId, matBlend, rv);
-						vxb_regular_secondary(level, rv);
-						VxbVertex ov;
-						vxb_finish_vertex(rv, *d.lut, ov);
-						vxb_store_vertex(d.verts + vid, ov);
-						++vid;
-					}
-				}
-				__syncthreads(); // vertices of this block are visible to the whole CTA
-
-				// ---- step 5: triangles + degenerate filter (:1300-1321); removed ones are marked, compacted below ----
-				unsigned tb = packedBase >> 16, myRemoved = 0;
-				for (unsigned i = i0; i < i1; ++i)
-				{
-					const int c = s.list[i];
-					signed char v[8];
-					vxb_cell_samples(s, c, v);
-					const unsigned code = vxb_case_code(v);
-					const unsigned cls = vxbRegularCellClass[code];
-					const unsigned geo = vxbRegularCellData[cls * 16];
-					const unsigned ra = s.recA[i], rb = s.recB[i];
-					const unsigned rowStart = vxb_rank(s, c & ~15), sliceStart = s.wpre[(c >> 8) * 8];
-					const int mask = (i > rowStart ? 1 : 0) | (rowStart > sliceStart ? 2 : 0) | (sliceStart > 0 ? 4 : 0);
-					unsigned vids[12];
-					unsigned nextNew = rb & 0xFFFF;
-					for (int k = 0; k < (int)(geo >> 4); ++k)
-					{
-						if ((rb >> (16 + k)) & 1u) { vids[k] = nextNew++; continue; }
-						const VxbVertexDesc vd = vxb_regular_vertex_desc(vxbRegularVertexData[code * 12 + k], v);
-						const VxbDecision dec = vxb_decide(s, c, mask, vd, ra & 0xFF);
-						const unsigned ob = s.recB[dec.ownerIdx];
-						vids[k] = (ob & 0xFFFF) + __popc((ob >> 16) & ((1u << dec.ok) - 1u));
-					}
-					for (unsigned tr = 0; tr < (geo & 0xF); ++tr, ++tb)
-					{
-						const unsigned a = vids[vxbRegularCellData[cls * 16 + 1 + tr * 3]];
-						const unsigned b = vids[vxbRegularCellData[cls * 16 + 2 + tr * 3]];
-						const unsigned cc = vids[vxbRegularCellData[cls * 16 + 3 + tr * 3]];
-						float pa[3], pb[3], pc[3];
-						{
-							const float* fa = d.verts[voff + a].pos; const float* fb = d.verts[voff + b].pos; const float* fc = d.verts[voff + cc].pos;
-							// back to grid axes, x256 (exact: positions are multiples of 1/256)
-							pa[0] = fa[0] * 256.f; pa[1] = fa[2] * 256.f; pa[2] = fa[1] * 256.f;
-							pb[0] = fb[0] * 256.f; pb[1] = fb[2] * 256.f; pb[2] = fb[1] * 256.f;
-							pc[0] = fc[0] * 256.f; pc[1] = fc[2] * 256.f; pc[2] = fc[1] * 256.f;
-						}
-						unsigned* out = d.idx + ioff + tb * 3;
-						if (vxb_triangle_kept(pa, pb, pc)) { out[0] = a; out[1] = b; out[2] = cc; }
-						else { out[0] = 0xFFFFFFFFu; out[1] = 0xFFFFFFFFu; out[2] = 0xFFFFFFFFu; ++myRemoved; }
-					}
-				}
-				if (myRemoved) atomicAdd(&s.removed, myRemoved);
-				__syncthreads();
-				const unsigned removed = s.removed;
-				if (removed)
-				{
-					// order-preserving in-place compaction of this block's triangle list
-					unsigned written = 0;
-					for (unsigned t0 = 0; t0 < ntris; t0 += VXB_THREADS)
-					{
-						const unsigned t = t0 + tid;
-						unsigned a = 0xFFFFFFFFu, b = 0, cc = 0;
-						if (t < ntris) { const unsigned* in = d.idx + ioff + t * 3; a = in[0]; b = in[1]; cc = in[2]; }
-						const bool keep = (t < ntris) && a != 0xFFFFFFFFu;
-						unsigned chunkTotal;
-						const unsigned pos = vxb_block_scan(keep ? 1u : 0u, s.warpSums, chunkTotal); // syncs: all reads of this chunk are done
-						if (keep) { unsigned* out = d.idx + ioff + (written + pos) * 3; out[0] = a; out[1] = b; out[2] = cc; }
-						written += chunkTotal;
-						__syncthreads();
-					}
-				}
-				if (tid == 0) { statRemoved += removed; }
-			}
-		}
-
-		// ---- step 6: transition cells (:1754-2131) + their material-cache side effect (:1859) ----
-		unsigned tvCount[6] = { 0, 0, 0, 0, 0, 0 }, tiCount[6] = { 0, 0, 0, 0, 0, 0 }, tvOff[6] = { 0, 0, 0, 0, 0, 0 }, tiOff[6] = { 0, 0, 0, 0, 0, 0 };
-		if (midLevel)
-		{
-			if (tid < 8)
-			{
-				const int cnb = nb * 2;
-				const size_t cb = ((size_t)(bz * 2 + (tid >> 2)) * cnb + (by * 2 + ((tid >> 1) & 1))) * cnb + (bx * 2 + (tid & 1));
-				const bool valid = (level == 1) ? d.consValid[cb] : d.cacheValid[level - 1][cb];
-				if (valid) atomicOr(&s.hasChild, 1u);
-			}
-			__syncthreads();
-			const bool hasChild = s.hasChild != 0;
-			const bool outputTrans = d.transitions && nverts > 0 && ((unsigned long long)s.voff + nverts <= d.vcap);
-			if (hasChild || outputTrans)
-			{
-				const int row = tid >> 4, col = tid & 15;
-				for (int face = 0; face < 6; ++face)
-				{
-					int axis, ua, va;
-					vxb_face_axes(face, axis, ua, va);
-					const int bc = (axis == 0) ? bx : (axis == 1 ? by : bz);
-					if (face < 3 ? (bc == 0) : (bc == nb - 1)) continue; // neighbour block outside the grid (:1829-1835)
-					int local[3];
-					local[axis] = (face >= 3) ? 15 : 0; local[ua] = col; local[va] = row;
-					const int c = local[2] * 256 + local[1] * 16 + local[0];
-					const int base[3] = { (bx * 16 + local[0]) * m, (by * 16 + local[1]) * m, (bz * 16 + local[2]) * m };
-
-					unsigned matId = VXB_EMPTY_MATERIAL, matBlend = 0;
-					bool voted = false;
-					if (hasChild) voted = vxb_vote_cell(d, level, base, matId, matBlend);
-					if (!voted) { matId = VXB_EMPTY_MATERIAL; matBlend = 0; }
-					if (!s.pageReady) // block-uniform
-					{
-						if (__syncthreads_or(voted ? 1 : 0))
-						{
-							if (!d.cacheValid[level][coordId])
-							{
-								unsigned int* page = reinterpret_cast<unsigned int*>(d.cachePages[level] + (size_t)coordId * 4096);
-								for (int i = tid; i < 2048; i += VXB_THREADS) page[i] = 0x00FF00FFu;
-							}
-							__syncthreads();
-							if (tid == 0) { d.cacheValid[level][coordId] = 1; s.pageReady = 1; }
-							__syncthreads();
-						}
-					}
-					if (voted) d.cachePages[level][(size_t)coordId * 4096 + c] = (unsigned short)(matId | (matBlend << 8));
-					if (!outputTrans) continue;
-
-					signed char v[13];
-#pragma unroll
-					for (int i = 0; i < 9; ++i)
-					{
-						int p[3];
-						vxb_transition_sample_pos(face, level, base, i, p);
-						v[i] = (signed char)vxb_dist(g, p[0], p[1], p[2]);
-					}
-					v[9] = v[0]; v[10] = v[2]; v[11] = v[6]; v[12] = v[8];
-					const unsigned code = vxb_transition_case_code(v);
-					const bool nt = (code != 0u && code != 511u);
-					const unsigned bal = __ballot_sync(0xFFFFFFFFu, nt);
-					if (lane == 0) s.tnt[warp] = bal;
-					const unsigned cls = nt ? vxbTransitionCellClass[code] : 0u;
-					const unsigned char* cd = &vxbTransitionCellData[(cls & 0x7F) * 40];
-					const int nv = nt ? (cd[0] >> 4) : 0, ntri = nt ? (cd[0] & 0xF) : 0;
-					s.tmat[tid] = (unsigned char)matId;
-#pragma unroll
-					for (int q = 0; q < 10; ++q) s.tslot[tid][q] = VXB_NO_SLOT;
-					const int mask = ((row > 0) ? 2 : 0) | ((bal >> (lane & 16)) & ((1u << col) - 1u) ? 1 : 0);
-					for (int k = 0; k < nv; ++k)
-					{
-						const VxbTransVertexDesc td = vxb_transition_vertex_desc(vxbTransitionVertexData[code * 12 + k], v, vxbTransitionCornerData);
-						if ((td.dir & mask) != td.dir && td.dir == 8) s.tslot[tid][td.slot] = (unsigned char)k; // stored only when no reuse was attempted (:2097)
-					}
-					__syncthreads();
-					unsigned newMask = 0;
-					unsigned ownerOf[12];
-					for (int k = 0; k < nv; ++k)
-					{
-						const VxbTransVertexDesc td = vxb_transition_vertex_desc(vxbTransitionVertexData[code * 12 + k], v, vxbTransitionCornerData);
-						bool isNew = true;
-						ownerOf[k] = 0;
-						if ((td.dir & mask) == td.dir)
-						{
-							const int oc = (row - ((td.dir >> 1) & 1)) * 16 + (col - (td.dir & 1));
-							const bool ont = (s.tnt[oc >> 5] >> (oc & 31)) & 1u;
-							const int ok = ont ? s.tslot[oc][td.slot] : VXB_NO_SLOT;
-							if (ok != VXB_NO_SLOT && s.tmat[oc] == matId) { isNew = false; ownerOf[k] = (unsigned)oc | ((unsigned)ok << 8); }
-						}
-						if (isNew) newMask |= 1u << k;
-					}
-					s.tnew[tid] = (unsigned short)newMask;
-					unsigned packedTotal;
-					const unsigned packedBase = vxb_block_scan(__popc(newMask) | ((unsigned)ntri << 16), s.warpSums, packedTotal);
-					const unsigned fv = packedTotal & 0xFFFF, ft = packedTotal >> 16;
-					s.tvbase[tid] = (unsigned short)(packedBase & 0xFFFF);
-					if (tid == 0)
-					{
-						s.tvoff = fv ? atomicAdd(&d.counters->transVertices, fv) : 0u;
-						s.tioff = ft ? atomicAdd(&d.counters->transIndices, ft * 3) : 0u;
-					}
-					__syncthreads();
-					const unsigned tvoff = s.tvoff, tioff = s.tioff;
-					const bool tfits = (unsigned long long)tvoff + fv <= d.tvcap && (unsigned long long)tioff + ft * 3ull <= d.ticap;
-					tvCount[face] = fv; tiCount[face] = ft * 3; tvOff[face] = tvoff; tiOff[face] = tioff;
-					if (nt && tfits)
-					{
-						unsigned vids[12];
-						unsigned nextNew = packedBase & 0xFFFF;
-						for (int k = 0; k < nv; ++k)
-						{
-							if ((newMask >> k) & 1u)
-							{
-								const VxbTransVertexDesc td = vxb_transition_vertex_desc(vxbTransitionVertexData[code * 12 + k], v, vxbTransitionCornerData);
-								VxbRawVertex rv;
-								vxb_transition_vertex(g, face, level, base, local, td, matId, matBlend, rv);
-								VxbVertex ov;
-								vxb_finish_vertex(rv, *d.lut, ov);
-								vxb_store_vertex(d.tverts + tvoff + nextNew, ov);
-								vids[k] = nextNew++;
-							}
-							else
-							{
-								const unsigned oc = ownerOf[k] & 0xFF, ok = ownerOf[k] >> 8;
-								vids[k] = s.tvbase[oc] + __popc((unsigned)s.tnew[oc] & ((1u << ok) - 1u));
-							}
-						}
-						atomicOr(&s.used[matId >> 5], 1u << (matId & 31));
-						const bool flip = (((cls >> 7) & 1u) ^ (unsigned)(face & 1)) != 0;
-						unsigned* out = d.tidx + tioff + (packedBase >> 16) * 3;
-						for (int tr = 0; tr < ntri; ++tr)
-						{
-							const unsigned a = vids[cd[1 + tr * 3]], b = vids[cd[2 + tr * 3]], cc = vids[cd[3 + tr * 3]];
-							out[tr * 3] = a; out[tr * 3 + 1] = flip ? cc : b; out[tr * 3 + 2] = flip ? b : cc;
-						}
-					}
-					__syncthreads(); // scratch is reused by the next face
-				}
-			}
-		}
-
-		// ---- step 7: directory record (PushBlocksToResult: only blocks with >= 1 vertex :1278) ----
-		if (tid == 0 && nverts > 0)
-		{
-			const unsigned slot = atomicAdd(&d.counters->records, 1u);
-			if (slot < d.rcap)
-			{
-				vxb_block_record r;
-				r.level = level; r.coord_id = coordId; r.id = d.idBase[level] + coordId;
-				r.vertex_count = nverts; r.index_count = (ntris - s.removed) * 3;
-				r.vertex_offset = s.voff; r.index_offset = s.ioff;
-				for (int f = 0; f < 6; ++f)
-				{
-					// internal face order (z-,y-,x-,z+,y+,x+) is already the output enum order (YNeg,ZNeg,XNeg,YPos,ZPos,XPos)
-					r.trans_vertex_count[f] = tvCount[f]; r.trans_index_count[f] = tiCount[f];
-					r.trans_vertex_offset[f] = tvOff[f]; r.trans_index_offset[f] = tiOff[f];
-				}
-				r.reserved = 0;
-				d.records[slot] = r;
-			}
-		}
-		__syncthreads(); // tile / scratch are free for the next item
-	}
-
-	// ---- statistics ----
-	__syncthreads();
-	if (tid < 8 && s.used[tid]) atomicOr(&d.counters->usedMaterials[tid], s.used[tid]);
-	if (tid == 0 && statRemoved) atomicAdd(&d.counters->degenerate, statRemoved);
-}
