@@ -78,6 +78,7 @@ struct vxb_context
 	DevBuf<unsigned short> cachePages;
 	DevBuf<unsigned int> worklist, emitList, bigList, transList, ntScratch, cellBlock, vlist;
 	DevBuf<VxbCellRec> cellRecs;
+	DevBuf<uint2> tvlist;
 	DevBuf<VxbBlockRec> blockRecs;
 	DevBuf<VxbVertex> verts, tverts;
 	DevBuf<unsigned int> idx, tidx;
@@ -235,7 +236,7 @@ void vxb_destroy(vxb_context* ctx)
 	if (ctx->stream) cudaStreamSynchronize(ctx->stream);
 	ctx->volDist.release(); ctx->volMat.release(); ctx->volBlend.release(); ctx->staging.release();
 	ctx->scanFlags.release(); ctx->blockInfo.release(); ctx->consPages.release(); ctx->validFlags.release();
-	ctx->cachePages.release(); ctx->worklist.release(); ctx->emitList.release(); ctx->bigList.release(); ctx->transList.release(); ctx->ntScratch.release(); ctx->cellBlock.release(); ctx->vlist.release(); ctx->cellRecs.release(); ctx->blockRecs.release(); ctx->verts.release(); ctx->tverts.release();
+	ctx->cachePages.release(); ctx->worklist.release(); ctx->emitList.release(); ctx->bigList.release(); ctx->transList.release(); ctx->ntScratch.release(); ctx->cellBlock.release(); ctx->vlist.release(); ctx->cellRecs.release(); ctx->blockRecs.release(); ctx->tvlist.release(); ctx->verts.release(); ctx->tverts.release();
 	ctx->idx.release(); ctx->tidx.release(); ctx->records.release(); ctx->counters.release(); ctx->lut.release();
 	for (cudaEvent_t e : ctx->kevents) cudaEventDestroy(e);
 	if (ctx->evBegin) cudaEventDestroy(ctx->evBegin);
@@ -409,11 +410,12 @@ int vxb_polygonize(vxb_context* ctx, uint32_t maxLevels, uint32_t flags)
 		VXB_CUDA(ctx, ctx->tverts.ensure(ctx->capTV));
 		VXB_CUDA(ctx, ctx->tidx.ensure(ctx->capTI));
 		VXB_CUDA(ctx, ctx->vlist.ensure(ctx->capV));
+		VXB_CUDA(ctx, ctx->tvlist.ensure(ctx->capTV));
 		VXB_CUDA(ctx, ctx->cellRecs.ensure(ctx->capC));
 		VXB_CUDA(ctx, ctx->cellBlock.ensure(ctx->capC));
 		dev.verts = ctx->verts.p; dev.idx = ctx->idx.p; dev.tverts = ctx->tverts.p; dev.tidx = ctx->tidx.p;
 		dev.vcap = (unsigned)ctx->capV; dev.icap = (unsigned)ctx->capI; dev.tvcap = (unsigned)ctx->capTV; dev.ticap = (unsigned)ctx->capTI;
-		dev.vlist = ctx->vlist.p; dev.cellRecs = ctx->cellRecs.p; dev.cellBlock = ctx->cellBlock.p; dev.ccap = (unsigned)ctx->capC;
+		dev.vlist = ctx->vlist.p; dev.cellRecs = ctx->cellRecs.p; dev.cellBlock = ctx->cellBlock.p; dev.ccap = (unsigned)ctx->capC; dev.tvlist = ctx->tvlist.p;
 
 		KernelTimer timer{ ctx, kernelTimes };
 		uint32_t launches = 0;
@@ -456,7 +458,12 @@ int vxb_polygonize(vxb_context* ctx, uint32_t maxLevels, uint32_t flags)
 		vxb_triangle_kernel<<<flatGrid, VXB_THREADS, 0, ctx->stream>>>(dev);
 		timer.end(); ++launches; ++ctx->kindLaunches[5];
 		timer.begin(6);
-		if (dev.transitions) { vxb_transition_kernel<<<ctx->gridTransition, VXB_THREADS, sizeof(VxbTransSmem), ctx->stream>>>(dev); ++launches; ++ctx->kindLaunches[6]; }
+		if (dev.transitions)
+		{
+			vxb_transition_kernel<<<ctx->gridTransition, VXB_THREADS, sizeof(VxbTransSmem), ctx->stream>>>(dev);
+			vxb_transition_vertex_kernel<<<flatGrid, VXB_THREADS, 0, ctx->stream>>>(dev);
+			launches += 2; ctx->kindLaunches[6] += 2;
+		}
 		timer.end();
 		timer.begin(7);
 		vxb_finish_kernel<<<(unsigned)ctx->smCount * 2, VXB_THREADS, 0, ctx->stream>>>(dev);

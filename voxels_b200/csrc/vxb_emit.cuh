@@ -600,12 +600,23 @@ struct __align__(16) VxbTransSmem
 	unsigned short vbase[1536];
 	unsigned short tbase[1536];
 	unsigned char mat[1536];
+	signed char face[6][1092];      // the 33 x 33 half-stride sample lattice of each face plane (clamped reads)
 	unsigned int nt[48];
 	unsigned int warpSums[8];
 	unsigned int used[8];
 	unsigned int tvoff[6], tioff[6], tvcount[6], ticount[6];
 	unsigned int item;
 };
+
+// the 13 samples of transition cell (row, col) from the staged lattice (:1867-1911)
+__device__ __forceinline__ void vxb_face_cell_samples(const signed char* lattice, int row, int col, signed char v[13])
+{
+	const signed char* p = lattice + (2 * row) * 33 + 2 * col;
+	v[0] = p[0]; v[1] = p[1]; v[2] = p[2];
+	v[3] = p[33]; v[4] = p[34]; v[5] = p[35];
+	v[6] = p[66]; v[7] = p[67]; v[8] = p[68];
+	v[9] = v[0]; v[10] = v[2]; v[11] = v[6]; v[12] = v[8];
+}
 
 __global__ void __launch_bounds__(VXB_THREADS, 4) vxb_transition_kernel(const VxbDev d)
 {
@@ -615,7 +626,6 @@ __global__ void __launch_bounds__(VXB_THREADS, 4) vxb_transition_kernel(const Vx
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int row = tid >> 4, col = tid & 15;
 	const VxbGrid g = d.grid;
-	if (tid < 8) s.used[tid] = 0;
 	const unsigned workCount = d.counters->transBlocks;
 	for (;;)
 	{
@@ -630,6 +640,26 @@ __global__ void __launch_bounds__(VXB_THREADS, 4) vxb_transition_kernel(const Vx
 		const int m = 1 << level, nb = d.n / 16 / m;
 		const int bx = coordId % nb, by = (coordId / nb) % nb, bz = coordId / (nb * nb);
 
+		// T0: stage the half-stride lattices of the faces that have a neighbour block (independent clamped loads)
+		{
+			const int h = m >> 1, lim = d.n - 1;
+			const int origin[3] = { bx * 16 * m, by * 16 * m, bz * 16 * m };
+			for (int idx = tid; idx < 6 * 1089; idx += VXB_THREADS)
+			{
+				const int face = idx / 1089, r = idx - face * 1089;
+				int axis, ua, va;
+				vxb_face_axes(face, axis, ua, va);
+				const int bc = (axis == 0) ? bx : (axis == 1 ? by : bz);
+				if (face < 3 ? (bc == 0) : (bc == nb - 1)) continue; // neighbour block outside the grid (:1829-1835)
+				const int j = r / 33, i = r - j * 33;
+				int p[3];
+				p[axis] = origin[axis] + ((face >= 3) ? 16 * m : 0);
+				p[ua] = origin[ua] + i * h;
+				p[va] = origin[va] + j * h;
+				s.face[face][r] = g.dist[((size_t)min(p[2], lim) * d.n + min(p[1], lim)) * d.n + min(p[0], lim)];
+			}
+		}
+		__syncthreads();
 		// T1: case codes (cell = thread, one face per iteration; thread order = the reference's row-major order)
 #pragma unroll 1
 		for (int face = 0; face < 6; ++face)
@@ -640,11 +670,8 @@ __global__ void __launch_bounds__(VXB_THREADS, 4) vxb_transition_kernel(const Vx
 			unsigned code = 0;
 			if (!(face < 3 ? (bc == 0) : (bc == nb - 1))) // neighbour block inside the grid (:1829-1835)
 			{
-				int local[3];
-				local[axis] = (face >= 3) ? 15 : 0; local[ua] = col; local[va] = row;
-				const int base[3] = { (bx * 16 + local[0]) * m, (by * 16 + local[1]) * m, (bz * 16 + local[2]) * m };
 				signed char v[13];
-				vxb_transition_samples(g, face, level, base, v);
+				vxb_face_cell_samples(s.face[face], row, col, v);
 				code = vxb_transition_case_code(v);
 				if (code == 511u) code = 0;
 			}
@@ -669,7 +696,7 @@ __global__ void __launch_bounds__(VXB_THREADS, 4) vxb_transition_kernel(const Vx
 				matId = d.cachePages[level][(size_t)coordId * 4096 + local[2] * 256 + local[1] * 16 + local[0]] & 0xFF;
 				const int base[3] = { (bx * 16 + local[0]) * m, (by * 16 + local[1]) * m, (bz * 16 + local[2]) * m };
 				signed char v[13];
-				vxb_transition_samples(g, face, level, base, v);
+				vxb_face_cell_samples(s.face[face], row, col, v);
 				const int nv = vxbGTransitionCellData[(vxbGTransitionCellClass[code] & 0x7F) * 40] >> 4;
 				for (int k = 0; k < nv; ++k)
 				{
@@ -698,7 +725,7 @@ __global__ void __launch_bounds__(VXB_THREADS, 4) vxb_transition_kernel(const Vx
 				local[axis] = (face >= 3) ? 15 : 0; local[ua] = col; local[va] = row;
 				const int base[3] = { (bx * 16 + local[0]) * m, (by * 16 + local[1]) * m, (bz * 16 + local[2]) * m };
 				signed char v[13];
-				vxb_transition_samples(g, face, level, base, v);
+				vxb_face_cell_samples(s.face[face], row, col, v);
 				const unsigned geo = vxbGTransitionCellData[(vxbGTransitionCellClass[code] & 0x7F) * 40];
 				ntri = geo & 0xF;
 				const unsigned rowBits = (s.nt[face * 8 + warp] >> (lane & 16)) & 0xFFFFu;
@@ -747,7 +774,7 @@ __global__ void __launch_bounds__(VXB_THREADS, 4) vxb_transition_kernel(const Vx
 			const int c = local[2] * 256 + local[1] * 16 + local[0];
 			const int base[3] = { (bx * 16 + local[0]) * m, (by * 16 + local[1]) * m, (bz * 16 + local[2]) * m };
 			signed char v[13];
-			vxb_transition_samples(g, face, level, base, v);
+			vxb_face_cell_samples(s.face[face], row, col, v);
 			const unsigned cls = vxbGTransitionCellClass[code];
 			const unsigned char* cd = &vxbGTransitionCellData[(cls & 0x7F) * 40];
 			const int nv = cd[0] >> 4, ntri = cd[0] & 0xF;
@@ -758,24 +785,20 @@ __global__ void __launch_bounds__(VXB_THREADS, 4) vxb_transition_kernel(const Vx
 			unsigned nextNew = s.vbase[ci];
 			for (int k = 0; k < nv; ++k)
 			{
-				const VxbTransVertexDesc td = vxb_transition_vertex_desc(vxbGTransitionVertexData[code * 12 + k], v, vxbGTransitionCornerData);
 				if ((newMask >> k) & 1u)
 				{
-					VxbRawVertex rv;
-					vxb_transition_vertex(g, face, level, base, local, td, matId, matBlend, rv);
-					VxbVertex ov;
-					vxb_finish_vertex(rv, *d.lut, ov);
-					vxb_store_vertex(d.tverts + tvoff + nextNew, ov);
+					// the vertex itself is computed by vxb_transition_vertex_kernel, one thread per entry
+					d.tvlist[tvoff + nextNew] = make_uint2(slot, ((unsigned)face << 12) | ((unsigned)tid << 4) | (unsigned)k);
 					vids[k] = nextNew++;
 				}
 				else
 				{
+					const VxbTransVertexDesc td = vxb_transition_vertex_desc(vxbGTransitionVertexData[code * 12 + k], v, vxbGTransitionCornerData);
 					const int oc = face * 256 + (row - ((td.dir >> 1) & 1)) * 16 + (col - (td.dir & 1));
 					const unsigned ok = (unsigned)((s.slots[oc] >> (4 * td.slot)) & 0xF);
 					vids[k] = s.vbase[oc] + __popc((unsigned)s.newMask[oc] & ((1u << ok) - 1u));
 				}
 			}
-			atomicOr(&s.used[matId >> 5], 1u << (matId & 31));
 			const bool flip = (((cls >> 7) & 1u) ^ (unsigned)(face & 1)) != 0;
 			unsigned* out = d.tidx + tioff + (unsigned)s.tbase[ci] * 3;
 			for (int tr = 0; tr < ntri; ++tr)
@@ -791,6 +814,47 @@ __global__ void __launch_bounds__(VXB_THREADS, 4) vxb_transition_kernel(const Vx
 		}
 		__syncthreads();
 	}
+}
+
+// flat: one thread per new transition vertex (:1980-2092)
+__global__ void __launch_bounds__(VXB_THREADS) vxb_transition_vertex_kernel(const VxbDev d)
+{
+	__shared__ unsigned sUsed[8];
+	if (threadIdx.x < 8) sUsed[threadIdx.x] = 0;
 	__syncthreads();
-	if (tid < 8 && s.used[tid]) atomicOr(&d.counters->usedMaterials[tid], s.used[tid]);
+	if (!vxb_overflowed(d) && d.counters->transVertices <= d.tvcap && d.counters->transIndices <= d.ticap)
+	{
+		const VxbGrid g = d.grid;
+		const unsigned total = d.counters->transVertices;
+		for (unsigned j = blockIdx.x * blockDim.x + threadIdx.x; j < total; j += gridDim.x * blockDim.x)
+		{
+			const uint2 e = d.tvlist[j];
+			const unsigned packed = d.blockRecs[e.x].packed;
+			const int level = (int)(packed >> 28);
+			const unsigned coordId = packed & 0x0FFFFFFFu;
+			const int m = 1 << level, nb = d.n / 16 / m;
+			const int bx = coordId % nb, by = (coordId / nb) % nb, bz = coordId / (nb * nb);
+			const int face = (int)(e.y >> 12), cell = (int)((e.y >> 4) & 0xFF), k = (int)(e.y & 15);
+			const int row = cell >> 4, col = cell & 15;
+			int axis, ua, va;
+			vxb_face_axes(face, axis, ua, va);
+			int local[3];
+			local[axis] = (face >= 3) ? 15 : 0; local[ua] = col; local[va] = row;
+			const int base[3] = { (bx * 16 + local[0]) * m, (by * 16 + local[1]) * m, (bz * 16 + local[2]) * m };
+			signed char v[13];
+			vxb_transition_samples(g, face, level, base, v);
+			const unsigned code = vxb_transition_case_code(v);
+			const VxbTransVertexDesc td = vxb_transition_vertex_desc(vxbGTransitionVertexData[code * 12 + k], v, vxbGTransitionCornerData);
+			const unsigned ent = d.cachePages[level][(size_t)coordId * 4096 + local[2] * 256 + local[1] * 16 + local[0]];
+			const unsigned matId = ent & 0xFF, matBlend = ent >> 8;
+			VxbRawVertex rv;
+			vxb_transition_vertex(g, face, level, base, local, td, matId, matBlend, rv);
+			VxbVertex ov;
+			vxb_finish_vertex(rv, *d.lut, ov);
+			vxb_store_vertex(d.tverts + j, ov);
+			atomicOr(&sUsed[matId >> 5], 1u << (matId & 31));
+		}
+	}
+	__syncthreads();
+	if (threadIdx.x < 8 && sUsed[threadIdx.x]) atomicOr(&d.counters->usedMaterials[threadIdx.x], sUsed[threadIdx.x]);
 }

@@ -90,6 +90,7 @@ struct VxbDev
 	unsigned int* transList;  // block slots of emitted mid-level blocks
 	VxbCellRec* cellRecs; unsigned int* cellBlock; unsigned int ccap;
 	unsigned int* vlist;      // vertex (arena index) -> cell record index << 4 | table vertex
+	uint2* tvlist;            // transition vertex (arena index) -> {block slot, face << 12 | cell << 4 | table vertex}
 	VxbBlockRec* blockRecs;
 };
 
