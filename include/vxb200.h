@@ -97,6 +97,17 @@ int vxb_grid_upload_dense(vxb_context* ctx, uint32_t n, const int8_t* dist, cons
 /* HOST memory, 16^3 blocks exactly as Grid::GetBlockDistanceData/GetBlockMaterialData return them,
  * concatenated in VoxelGrid block order (id = x + y*nb + z*nb*nb, VoxelGrid.h:139-144; 4096 B each). */
 int vxb_grid_upload_blocks(vxb_context* ctx, uint32_t n, const int8_t* dist_blocks, const uint8_t* mat_blocks, const uint8_t* blend_blocks);
+/* The grid in the reference's own serialised form, i.e. exactly the bytes Grid::PackForSave() returns
+ * (VoxelGrid::PackForSave src/VoxelGrid.cpp:269-315: {version=1, w, d, h}, 3 x uint32 sizes per block, then per block
+ * {flags, RLE distance, RLE material, RLE blend}; RLE = (length, value) byte pairs, VoxelGrid::CompressBlock :610-672).
+ * HOST memory.  The blob is copied to the device as is (typically 10-30x smaller than the dense volumes) and the
+ * run-length decoding (VoxelGrid::DecompressBlock :674-694) happens on the GPU. */
+int vxb_grid_upload_packed(vxb_context* ctx, const void* blob, size_t size);
+/* Host-side helper (no GPU involved): writes the PackForSave form of dense n^3 volumes into `out` (capacity bytes).
+ * Byte-identical to what the reference produces for the same voxels.  vxb_pack_dense_bound = worst-case size. */
+size_t vxb_pack_dense_bound(uint32_t n);
+int vxb_pack_dense(uint32_t n, const int8_t* dist, const uint8_t* mat, const uint8_t* blend, void* out, size_t capacity, size_t* written);
+
 /* Dense volumes already resident in DEVICE memory (not copied; must stay valid; 16-byte aligned). */
 int vxb_grid_set_device(vxb_context* ctx, uint32_t n, const int8_t* d_dist, const uint8_t* d_mat, const uint8_t* d_blend);
 /* Device pointers of the context-owned dense volumes (after an upload), for tools/benchmarks. */

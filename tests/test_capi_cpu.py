@@ -64,3 +64,15 @@ def test_tables_checksum():
     text = open(path).read()
     assert "VXB_TABLES_FNV1A 0x83E0932026BB2FEEull" in text
     assert "Eric Lengyel's Transvoxel Algorithm" in text and "http://www.terathon.com/voxels/" in text
+
+
+def test_pack_dense_matches_reference_bytes(reference):
+    """vxb_pack_dense (host helper of the C ABI) writes exactly the bytes Grid::PackForSave produces."""
+    import numpy as np
+    import grids
+    for name in ("hostile64", "positive_noise32", "plane32"):
+        dist, mat, blend = grids.SMALL[name]()
+        g = reference.grid_from_dense(dist, mat, blend)
+        blob = reference.grid_pack(g)
+        reference.grid_destroy(g)
+        assert np.array_equal(blob, voxels_b200.pack_dense(dist, mat, blend)), name

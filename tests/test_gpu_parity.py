@@ -81,6 +81,27 @@ def test_block_upload_equals_dense_upload(gpu_context):
         assert not compare.level_diff(a.level(l), b.level(l), "L%d" % l)
 
 
+def test_packed_upload_equals_dense_upload(reference, gpu_context):
+    """vxb_grid_upload_packed: the reference's own PackForSave bytes, run-length decoded on the GPU."""
+    import voxels_b200
+    for name in ("hostile64", "positive_noise32", "noise32"):  # incl. RLE-ineffective (raw) blocks
+        dist, mat, blend = grids.SMALL[name]()
+        g = reference.grid_from_dense(dist, mat, blend)
+        blob = reference.grid_pack(g)
+        reference.grid_destroy(g)
+        assert np.array_equal(blob, voxels_b200.pack_dense(dist, mat, blend)), "host packer differs from Grid::PackForSave"
+        gpu_context.set_materials(None, None)
+        gpu_context.upload_dense(dist, mat, blend)
+        gpu_context.polygonize()
+        a = gpu_context.download()
+        gpu_context.upload_packed(blob)
+        gpu_context.polygonize()
+        b = gpu_context.download()
+        for l in range(a.info.levels_total):
+            assert not compare.level_diff(a.level(l), b.level(l), "%s L%d" % (name, l))
+        assert np.array_equal(a.stats, b.stats)
+
+
 def test_arena_growth_retry(reference, gpu_context):
     """Tiny initial arenas: the run must detect the overflow, grow and still match."""
     import voxels_b200

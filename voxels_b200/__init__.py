@@ -5,8 +5,8 @@ C++ drop-in for the reference's Polygonizer API (libvoxels_b200.so).  This packa
 host side (ctypes) used by the tests and bench.py.  There is no CPU fallback: importing works without
 a GPU, creating a `Context` does not.
 """
-from .capi import (Context, Result, VxbError, library_path, load_library, FLAG_NO_TRANSITIONS, FLAG_KERNEL_TIMES,
+from .capi import (Context, Result, VxbError, library_path, load_library, pack_dense, FLAG_NO_TRANSITIONS, FLAG_KERNEL_TIMES,
                    RECORD_DTYPE, VERTEX_DTYPE)
 
-__all__ = ["Context", "Result", "VxbError", "library_path", "load_library", "FLAG_NO_TRANSITIONS",
+__all__ = ["Context", "Result", "VxbError", "library_path", "load_library", "pack_dense", "FLAG_NO_TRANSITIONS",
            "FLAG_KERNEL_TIMES", "RECORD_DTYPE", "VERTEX_DTYPE"]

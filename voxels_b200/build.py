@@ -26,7 +26,7 @@ LIBVXH = os.path.join(REPO, "build", "libvxh_b200.so")
 CXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
 NVCC = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-fmad=false",
-              "-Xcompiler", "-fPIC", "-ccbin", CXX]
+              "-Xcompiler", "-fPIC,-fopenmp", "-ccbin", CXX]
 
 
 def _run(cmd, **kw):

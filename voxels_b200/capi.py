@@ -59,6 +59,9 @@ def load_library():
         "vxb_grid_upload_dense": (C.c_int, [vp, u32, vp, vp, vp]),
         "vxb_grid_upload_blocks": (C.c_int, [vp, u32, vp, vp, vp]),
         "vxb_grid_set_device": (C.c_int, [vp, u32, vp, vp, vp]),
+        "vxb_grid_upload_packed": (C.c_int, [vp, vp, C.c_size_t]),
+        "vxb_pack_dense_bound": (C.c_size_t, [u32]),
+        "vxb_pack_dense": (C.c_int, [u32, vp, vp, vp, vp, C.c_size_t, C.POINTER(C.c_size_t)]),
         "vxb_grid_device_pointers": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),
         "vxb_set_materials": (C.c_int, [vp, vp, vp]),
         "vxb_polygonize": (C.c_int, [vp, u32, u32]),
@@ -78,7 +81,7 @@ def load_library():
 
 
 EXPORTED_SYMBOLS = ["vxb_create", "vxb_destroy", "vxb_last_error", "vxb_stream", "vxb_grid_upload_dense",
-                    "vxb_grid_upload_blocks", "vxb_grid_set_device", "vxb_grid_device_pointers", "vxb_set_materials",
+                    "vxb_grid_upload_blocks", "vxb_grid_upload_packed", "vxb_pack_dense_bound", "vxb_pack_dense", "vxb_grid_set_device", "vxb_grid_device_pointers", "vxb_set_materials",
                     "vxb_polygonize", "vxb_result_info_get", "vxb_result_download", "vxb_set_capacity", "vxb_kernel_ms",
                     "vxb_result_unmapped_materials", "vxb_host_alloc", "vxb_host_free"]
 
@@ -89,6 +92,19 @@ def _ptr(a):
     if isinstance(a, int):
         return C.c_void_p(a)
     return a.ctypes.data_as(C.c_void_p)
+
+
+def pack_dense(dist, mat, blend, out=None):
+    """Host helper: the reference's PackForSave bytes for dense [z,y,x] volumes (numpy uint8 array).  No GPU needed."""
+    L = load_library()
+    n = dist.shape[0]
+    bound = L.vxb_pack_dense_bound(n)
+    buf = np.empty(bound, np.uint8) if out is None else out
+    written = C.c_size_t(0)
+    rc = L.vxb_pack_dense(n, _ptr(dist), _ptr(mat), _ptr(blend), _ptr(buf), buf.size, C.byref(written))
+    if rc != 0:
+        raise VxbError("vxb_pack_dense failed (%d)" % rc)
+    return buf[:written.value]
 
 
 class LevelView:
@@ -171,6 +187,18 @@ class Context:
         self._check(self.L.vxb_grid_upload_blocks(self.h, n, _ptr(dist_blocks), _ptr(mat_blocks), _ptr(blend_blocks)),
                     "vxb_grid_upload_blocks")
         self.n = n
+
+    def upload_packed(self, blob, size=None):
+        """blob: the bytes of Grid::PackForSave (numpy uint8 array, bytes, or an int address with `size`)."""
+        if isinstance(blob, int):
+            ptr, nbytes = C.c_void_p(blob), size
+        elif isinstance(blob, (bytes, bytearray)):
+            arr = np.frombuffer(blob, np.uint8); ptr, nbytes = _ptr(arr), arr.size
+            self._blob_keep = arr
+        else:
+            ptr, nbytes = _ptr(blob), blob.size
+        self._check(self.L.vxb_grid_upload_packed(self.h, ptr, nbytes), "vxb_grid_upload_packed")
+        self.n = int(np.frombuffer(C.string_at(ptr, 8), np.uint32)[1])
 
     def set_device_grid(self, n, d_dist, d_mat, d_blend, keep=None):
         """Device pointers (ints) of dense volumes that stay resident (e.g. torch tensors' data_ptr())."""

@@ -71,6 +71,8 @@ struct vxb_context
 	bool haveGrid = false, ownsGrid = false;
 	const int8_t* dDist = nullptr; const uint8_t* dMat = nullptr; const uint8_t* dBlend = nullptr;
 	DevBuf<uint8_t> volDist, volMat, volBlend, staging;
+	DevBuf<unsigned long long> packOffsets;
+	std::vector<unsigned long long> hostOffsets;
 	DevBuf<unsigned int> scanFlags;
 	DevBuf<unsigned char> blockInfo;
 	DevBuf<unsigned int> consPages;
@@ -234,7 +236,7 @@ void vxb_destroy(vxb_context* ctx)
 	if (!ctx) return;
 	cudaSetDevice(ctx->device);
 	if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-	ctx->volDist.release(); ctx->volMat.release(); ctx->volBlend.release(); ctx->staging.release();
+	ctx->volDist.release(); ctx->volMat.release(); ctx->volBlend.release(); ctx->staging.release(); ctx->packOffsets.release();
 	ctx->scanFlags.release(); ctx->blockInfo.release(); ctx->consPages.release(); ctx->validFlags.release();
 	ctx->cachePages.release(); ctx->worklist.release(); ctx->emitList.release(); ctx->bigList.release(); ctx->transList.release(); ctx->ntScratch.release(); ctx->cellBlock.release(); ctx->vlist.release(); ctx->cellRecs.release(); ctx->blockRecs.release(); ctx->tvlist.release(); ctx->verts.release(); ctx->tverts.release();
 	ctx->idx.release(); ctx->tidx.release(); ctx->records.release(); ctx->counters.release(); ctx->lut.release();
@@ -287,6 +289,138 @@ int vxb_grid_upload_blocks(vxb_context* ctx, uint32_t n, const int8_t* distBlock
 	}
 	VXB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	return buildTensorMap(ctx);
+}
+
+int vxb_grid_upload_packed(vxb_context* ctx, const void* blob, size_t size)
+{
+	if (!ctx) return VXB_ERR_ARGUMENT;
+	if (!blob || size < 16) return fail(ctx, VXB_ERR_ARGUMENT, "vxb_grid_upload_packed: null or truncated blob");
+	const unsigned char* bytes = static_cast<const unsigned char*>(blob);
+	uint32_t header[4];
+	memcpy(header, bytes, 16);
+	if (header[0] != 1) return fail(ctx, VXB_ERR_ARGUMENT, "vxb_grid_upload_packed: unsupported file version (VoxelGrid.cpp:227-231)");
+	const uint32_t n = header[1];
+	if (!validSize(n) || header[2] != n || header[3] != n) return fail(ctx, VXB_ERR_ARGUMENT, "vxb_grid_upload_packed: the grid must be a cube with a power-of-two edge");
+	const size_t nb = n / 16, blocks = nb * nb * nb;
+	const size_t tableBytes = blocks * 12;
+	if (size < 16 + tableBytes) return fail(ctx, VXB_ERR_ARGUMENT, "vxb_grid_upload_packed: truncated size table");
+	// per-block byte offsets (prefix sum of the size table); the data itself is only touched by the GPU
+	ctx->hostOffsets.resize(blocks);
+	{
+		const unsigned char* table = bytes + 16;
+		unsigned long long off = 16 + tableBytes;
+		for (size_t b = 0; b < blocks; ++b)
+		{
+			uint32_t sz[3];
+			memcpy(sz, table + b * 12, 12);
+			if (sz[0] > 4096 || sz[1] > 4096 || sz[2] > 4096) return fail(ctx, VXB_ERR_ARGUMENT, "vxb_grid_upload_packed: corrupt size table");
+			ctx->hostOffsets[b] = off;
+			off += 4ull + sz[0] + sz[1] + sz[2];
+		}
+		if (off > size) return fail(ctx, VXB_ERR_ARGUMENT, "vxb_grid_upload_packed: truncated block data");
+	}
+	cudaSetDevice(ctx->device);
+	int r = ensureGridStorage(ctx, n);
+	if (r != VXB_OK) return r;
+	VXB_CUDA(ctx, ctx->staging.ensure(size + 16));
+	VXB_CUDA(ctx, ctx->packOffsets.ensure(blocks));
+	VXB_CUDA(ctx, cudaMemcpyAsync(ctx->staging.p, blob, size, cudaMemcpyHostToDevice, ctx->stream));
+	VXB_CUDA(ctx, cudaMemcpyAsync(ctx->packOffsets.p, ctx->hostOffsets.data(), blocks * sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream));
+	vxb_unpack_rle_kernel<<<(unsigned)blocks, VXB_THREADS, 0, ctx->stream>>>(ctx->staging.p, ctx->packOffsets.p,
+		reinterpret_cast<const unsigned int*>(ctx->staging.p + 16), ctx->volDist.p, ctx->volMat.p, ctx->volBlend.p, (int)n);
+	VXB_CUDA(ctx, cudaGetLastError());
+	VXB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	return buildTensorMap(ctx);
+}
+
+size_t vxb_pack_dense_bound(uint32_t n)
+{
+	const size_t nb = n / 16, blocks = nb * nb * nb;
+	return 16 + blocks * 12 + blocks * (4 + 3 * 4096);
+}
+
+namespace
+{
+// VoxelGrid::CompressBlock (VoxelGrid.cpp:610-672): returns the stored size; raw 4096 bytes when RLE would be larger
+unsigned compressChannel(const unsigned char* data, unsigned char* out, bool signedValues, bool* uncompressed, bool* isEmpty)
+{
+	unsigned counter = 0, size = 1;
+	const int initial = signedValues ? (int)(signed char)data[0] : (int)data[0];
+	unsigned char last = data[0];
+	bool empty = true, effective = true;
+	unsigned ctrPos = 0;
+	for (unsigned i = 0; i < 4096; ++i)
+	{
+		const unsigned char cur = data[i];
+		if (last == cur && counter < 0xFF) { ++counter; continue; }
+		out[ctrPos] = (unsigned char)counter;
+		out[size++] = last;
+		ctrPos = size++;
+		counter = 1;
+		last = cur;
+		const int lv = signedValues ? (int)(signed char)last : (int)last;
+		if (initial * lv <= 0) empty = false;
+		if (size > 4096) { effective = false; break; }
+	}
+	if (effective)
+	{
+		out[ctrPos] = (unsigned char)counter;
+		out[size++] = last;
+		*uncompressed = false;
+		if (isEmpty) *isEmpty = empty;
+		return size;
+	}
+	memcpy(out, data, 4096);
+	*uncompressed = true;
+	if (isEmpty) *isEmpty = false;
+	return 4096;
+}
+}
+
+int vxb_pack_dense(uint32_t n, const int8_t* dist, const uint8_t* mat, const uint8_t* blend, void* out, size_t capacity, size_t* written)
+{
+	if (!validSize(n) || !dist || !mat || !blend || !out) return VXB_ERR_ARGUMENT;
+	const size_t nb = n / 16, blocks = nb * nb * nb;
+	if (capacity < 16 + blocks * 12) return VXB_ERR_CAPACITY;
+	unsigned char* bytes = static_cast<unsigned char*>(out);
+	const uint32_t header[4] = { 1u, n, n, n };
+	memcpy(bytes, header, 16);
+	// pass 1 (parallel): compress every block into a private slot of a scratch area; pass 2: concatenate
+	std::vector<unsigned char> scratch(blocks * (4 + 3 * 4096));
+	std::vector<uint32_t> sizes(blocks * 3);
+	const uint8_t* chans[3] = { reinterpret_cast<const uint8_t*>(dist), mat, blend };
+	#pragma omp parallel for schedule(static)
+	for (long b = 0; b < (long)blocks; ++b)
+	{
+		const size_t bx = b % nb, by = (b / nb) % nb, bz = b / (nb * nb);
+		unsigned char raw[4096];
+		unsigned char* slot = scratch.data() + (size_t)b * (4 + 3 * 4096);
+		uint32_t flags = 0;
+		unsigned pos = 4;
+		for (int ch = 0; ch < 3; ++ch)
+		{
+			for (int z = 0; z < 16; ++z) for (int y = 0; y < 16; ++y)
+				memcpy(raw + z * 256 + y * 16, chans[ch] + ((bz * 16 + z) * n + by * 16 + y) * n + bx * 16, 16);
+			bool uncompressed = false, isEmpty = false;
+			const unsigned sz = compressChannel(raw, slot + pos, ch == 0, &uncompressed, ch == 0 ? &isEmpty : nullptr);
+			if (uncompressed) flags |= 2u << ch;         // BF_DistanceUncompressed / Material / Blend (VoxelGrid.h:70-79)
+			if (ch == 0 && isEmpty) flags |= 1u;         // BF_Empty
+			sizes[b * 3 + ch] = sz;
+			pos += sz;
+		}
+		memcpy(slot, &flags, 4);
+	}
+	memcpy(bytes + 16, sizes.data(), blocks * 12);
+	size_t off = 16 + blocks * 12;
+	for (size_t b = 0; b < blocks; ++b)
+	{
+		const size_t len = 4ull + sizes[b * 3] + sizes[b * 3 + 1] + sizes[b * 3 + 2];
+		if (off + len > capacity) return VXB_ERR_CAPACITY;
+		memcpy(bytes + off, scratch.data() + b * (4 + 3 * 4096), len);
+		off += len;
+	}
+	if (written) *written = off;
+	return VXB_OK;
 }
 
 int vxb_grid_set_device(vxb_context* ctx, uint32_t n, const int8_t* dDist, const uint8_t* dMat, const uint8_t* dBlend)

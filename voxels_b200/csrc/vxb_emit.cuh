@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(VXB_THREADS, 4) vxb_classify_kernel(const __gr
 {
 	extern __shared__ __align__(128) unsigned char smemRaw[];
 	VxbClassifySmem& s = *reinterpret_cast<VxbClassifySmem*>(smemRaw);
-	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int tid = threadIdx.x;
 	const int m = 1 << level, nb = d.n / 16 / m;
 	const bool midLevel = level > 0 && level != d.lastLevel;
 	unsigned phase = 0;

@@ -277,6 +277,60 @@ __global__ void __launch_bounds__(VXB_THREADS) vxb_unpack_blocks_kernel(const ui
 	*reinterpret_cast<uint4*>(dense + (((size_t)bz * 16 + z) * n + (size_t)by * 16 + y) * n + (size_t)bx * 16) = v;
 }
 
+// Upload helper: run-length decoding of one packed 16^3 block per CTA, all three channels
+// (VoxelGrid::DecompressBlock, VoxelGrid.cpp:674-694; block layout of PackForSave :304-312).
+// Thread t produces the 16 bytes of row t (x fastest): binary search of the run that covers its first byte.
+__global__ void __launch_bounds__(VXB_THREADS) vxb_unpack_rle_kernel(const unsigned char* __restrict__ blob, const unsigned long long* __restrict__ blockOffsets,
+	const unsigned int* __restrict__ sizes, unsigned char* __restrict__ dist, unsigned char* __restrict__ mat, unsigned char* __restrict__ blend, int n)
+{
+	__shared__ unsigned short start[2049];
+	__shared__ unsigned char value[2048];
+	__shared__ unsigned warpSums[8];
+	const int nb = n >> 4;
+	const size_t b = blockIdx.x;
+	const int bx = (int)(b % nb), by = (int)((b / nb) % nb), bz = (int)(b / ((size_t)nb * nb));
+	const int tid = threadIdx.x, y = tid & 15, z = tid >> 4;
+	const unsigned char* src = blob + blockOffsets[b];
+	const unsigned flags = src[0] | (src[1] << 8) | (src[2] << 16) | ((unsigned)src[3] << 24);
+	src += 4;
+	unsigned char* const outs[3] = { dist, mat, blend };
+	for (int ch = 0; ch < 3; ++ch)
+	{
+		const unsigned size = sizes[b * 3 + ch];
+		uint4 row;
+		unsigned char* rb = reinterpret_cast<unsigned char*>(&row);
+		if ((flags >> (1 + ch)) & 1u) // BF_*Uncompressed (VoxelGrid.h:70-79): 4096 raw bytes
+		{
+			for (int i = 0; i < 16; ++i) rb[i] = src[tid * 16 + i];
+		}
+		else
+		{
+			const unsigned runs = min(size >> 1, 2048u);
+			const unsigned per = (runs + VXB_THREADS - 1) / VXB_THREADS;
+			const unsigned r0 = min(tid * per, runs), r1 = min(r0 + per, runs);
+			unsigned sum = 0;
+			for (unsigned r = r0; r < r1; ++r) sum += src[2 * r];
+			unsigned total;
+			unsigned base = vxb_block_scan(sum, warpSums, total);
+			for (unsigned r = r0; r < r1; ++r) { start[r] = (unsigned short)min(base, 4096u); value[r] = src[2 * r + 1]; base += src[2 * r]; }
+			if (tid == 0) start[runs] = 4096;
+			__syncthreads();
+			const unsigned p0 = tid * 16;
+			unsigned lo = 0, hi = runs; // last run with start <= p0
+			while (hi - lo > 1) { const unsigned mid = (lo + hi) >> 1; if (start[mid] <= p0) lo = mid; else hi = mid; }
+			unsigned r = lo;
+			for (int i = 0; i < 16; ++i)
+			{
+				while (r + 1 < runs && start[r + 1] <= p0 + i) ++r;
+				rb[i] = value[r];
+			}
+			__syncthreads();
+		}
+		*reinterpret_cast<uint4*>(outs[ch] + (((size_t)bz * 16 + z) * n + (size_t)by * 16 + y) * n + (size_t)bx * 16) = row;
+		src += size;
+	}
+}
+
 // ------------------------------------------------------------------------------------------------
 // K2: block selection for one level
 // ------------------------------------------------------------------------------------------------
