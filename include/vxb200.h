@@ -123,6 +123,33 @@ int vxb_set_materials(vxb_context* ctx, const uint8_t* table, const uint8_t* val
  * arenas until the next call.  Blocks until the device work is done. */
 int vxb_polygonize(vxb_context* ctx, uint32_t max_levels, uint32_t flags);
 int vxb_result_info_get(vxb_context* ctx, vxb_result_info* out);
+
+/* ---- incremental re-polygonization (Execute with a Modification, TransVoxelImpl.cpp:362-364, :429-465) ---- */
+/* Replaces `count` 16^3 blocks of the context-owned grid (after an edit such as Grid::InjectSurface).
+ * block_coords = count x {x, y, z} block coordinates; dist/mat/blend = count x 4096 bytes each in the same order
+ * (Grid::GetBlockDistanceData / GetBlockMaterialData layout); mat and blend may be NULL (unchanged). HOST memory. */
+int vxb_grid_update_blocks(vxb_context* ctx, uint32_t count, const uint32_t* block_coords, const int8_t* dist, const uint8_t* mat, const uint8_t* blend);
+
+/* Per level: the dirty box of the last vxb_polygonize_region and the ids it handed out.  A caller that keeps a
+ * surface erases its blocks whose minimal corner lies in [min_dirty, max_dirty) (:443-450) and appends the new ones;
+ * ids id_start .. id_start+block_count-1 are Modification::GetModifiedBlocks (:463). Corners are OUTPUT (Y-up) coordinates. */
+typedef struct vxb_region_info
+{
+	uint32_t levels;
+	uint32_t pad;
+	float min_dirty[12][3];
+	float max_dirty[12][3];
+	uint32_t id_start[12];
+	uint32_t block_count[12];
+} vxb_region_info;
+
+/* Re-polygonizes the blocks of every level around the box [min_corner, max_corner] (Modification::MinCornerModified /
+ * MaxCornerModified, OUTPUT coordinates: the box Grid::InjectSurface returns).  Needs a preceding full vxb_polygonize of
+ * the same context: its consistency / material caches are updated in place exactly like the reference's PolygonMap
+ * caches (bits are only ever set, votes only overwrite), block ids continue the context's running counter.  The
+ * result (vxb_result_info / vxb_result_download) holds ONLY the re-created blocks. */
+int vxb_polygonize_region(vxb_context* ctx, const float min_corner[3], const float max_corner[3], uint32_t flags);
+int vxb_region_info_get(vxb_context* ctx, vxb_region_info* out);
 /* Copies the directory (sorted by level, then coord_id = the reference's block order) and the
  * arenas to HOST memory sized from vxb_result_info spans.  Vertices are 48-byte
  * Voxels::PolygonVertex (include/Polygonizer.h:14-48).  Any pointer may be NULL to skip it. */

@@ -68,3 +68,51 @@ def test_unmapped_material_logs_per_vertex(reference, dropin):
     assert_same(a, b)
     after = [lib.L.vxh_error_logs() for lib in (reference, dropin)]
     assert after[0] - before[0] == after[1] - before[1] > 0  # one LS_Error per vertex with the unmapped material
+
+
+def _edit_sequence(n, count, seed=42):
+    """BASELINE config 5 shape: seeded sphere add/subtract edits with integer centres and even extents."""
+    rng = np.random.RandomState(seed)
+    edits = []
+    for i in range(count):
+        r = int(rng.choice([4, 6, 8, 10]))
+        pos = [int(v) for v in rng.randint(24, n - 24, size=3)]
+        pos[2] = int(n // 2 + rng.randint(-10, 10))  # near the terrain surface
+        edits.append((pos, float(r), float(2 * r + 4), harness.IT_ADD if i % 2 == 0 else harness.IT_SUBTRACT))
+    return edits
+
+
+@pytest.mark.parametrize("name,n,count", [("hostile", 64, 12), ("terrain", 128, 20)])
+def test_incremental_edits_match_reference(reference, dropin, name, n, count):
+    """Execute(grid, materials, modification) after Grid::InjectSurface: the drop-in must follow the reference's
+    INCREMENTAL behaviour (stale consistency bits, vote-only cache overwrites, id continuation, erase + append order),
+    which is not the same as a fresh polygonization."""
+    if name == "hostile":
+        import gridgen
+        dist, mat, blend = gridgen.hostile(n, seed=3)
+    else:
+        from voxels_b200 import synth
+        dist, mat, blend = (t.numpy() for t in synth.terrain(n))
+    state = []
+    for lib in (reference, dropin):
+        g = lib.grid_from_dense(dist, mat, blend)
+        s, _ = lib.polygonize(g)
+        state.append([lib, g, s, lib.modification_create()])
+    for step, (pos, radius, extent, kind) in enumerate(_edit_sequence(n, count)):
+        dumps = []
+        for st in state:
+            lib, g, s, mod = st
+            box = lib.grid_inject_sphere(g, pos, radius, extent, kind)
+            s2, _ = lib.polygonize(g, modification=mod, surface=s, box=box)
+            assert s2 == s, "Execute must return the surface it was given"
+            dumps.append(([lib.surface_level(s, l) for l in range(lib.surface_levels(s))], lib.surface_stats(s), lib.modification_blocks(mod), box))
+        (la, sa, ma, ba), (lb, sb, mb, bb) = dumps
+        assert np.array_equal(ba, bb)
+        problems = []
+        for l, (x, y) in enumerate(zip(la, lb)):
+            problems += compare.level_diff(x, y, "edit %d L%d" % (step, l))
+        assert not problems, "\n".join(problems[:10])
+        assert np.array_equal(sa, sb), "edit %d statistics: %s vs %s" % (step, sa, sb)
+        assert np.array_equal(ma, mb), "edit %d ModifiedBlocks differ" % step
+    for lib, g, s, mod in state:
+        lib.modification_destroy(mod); lib.surface_destroy(s); lib.grid_destroy(g)

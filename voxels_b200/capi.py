@@ -29,6 +29,11 @@ class ResultInfo(C.Structure):
                 ("kernel_launches", C.c_uint32)]
 
 
+class RegionInfo(C.Structure):
+    _fields_ = [("levels", C.c_uint32), ("pad", C.c_uint32), ("min_dirty", (C.c_float * 3) * 12), ("max_dirty", (C.c_float * 3) * 12),
+                ("id_start", C.c_uint32 * 12), ("block_count", C.c_uint32 * 12)]
+
+
 class VxbError(RuntimeError):
     pass
 
@@ -66,6 +71,9 @@ def load_library():
         "vxb_set_materials": (C.c_int, [vp, vp, vp]),
         "vxb_polygonize": (C.c_int, [vp, u32, u32]),
         "vxb_result_info_get": (C.c_int, [vp, C.POINTER(ResultInfo)]),
+        "vxb_grid_update_blocks": (C.c_int, [vp, u32, vp, vp, vp, vp]),
+        "vxb_polygonize_region": (C.c_int, [vp, vp, vp, u32]),
+        "vxb_region_info_get": (C.c_int, [vp, C.POINTER(RegionInfo)]),
         "vxb_result_download": (C.c_int, [vp, vp, vp, vp, vp, vp]),
         "vxb_set_capacity": (C.c_int, [vp, u64, u64, u64, u64]),
         "vxb_kernel_ms": (C.c_int, [vp, C.c_int, C.POINTER(C.c_float), C.POINTER(u32)]),
@@ -82,7 +90,7 @@ def load_library():
 
 EXPORTED_SYMBOLS = ["vxb_create", "vxb_destroy", "vxb_last_error", "vxb_stream", "vxb_grid_upload_dense",
                     "vxb_grid_upload_blocks", "vxb_grid_upload_packed", "vxb_pack_dense_bound", "vxb_pack_dense", "vxb_grid_set_device", "vxb_grid_device_pointers", "vxb_set_materials",
-                    "vxb_polygonize", "vxb_result_info_get", "vxb_result_download", "vxb_set_capacity", "vxb_kernel_ms",
+                    "vxb_polygonize", "vxb_polygonize_region", "vxb_region_info_get", "vxb_grid_update_blocks", "vxb_result_info_get", "vxb_result_download", "vxb_set_capacity", "vxb_kernel_ms",
                     "vxb_result_unmapped_materials", "vxb_host_alloc", "vxb_host_free"]
 
 
@@ -216,6 +224,22 @@ class Context:
     def polygonize(self, max_levels=0, flags=0):
         self._check(self.L.vxb_polygonize(self.h, max_levels, flags), "vxb_polygonize")
         return self.info()
+
+    def update_blocks(self, coords, dist_blocks, mat_blocks=None, blend_blocks=None):
+        """coords: uint32 [count, 3] block coordinates (x, y, z); *_blocks: uint8/int8 [count, 4096]."""
+        coords = np.ascontiguousarray(coords, np.uint32)
+        self._check(self.L.vxb_grid_update_blocks(self.h, len(coords), _ptr(coords), _ptr(dist_blocks), _ptr(mat_blocks), _ptr(blend_blocks)),
+                    "vxb_grid_update_blocks")
+
+    def polygonize_region(self, min_corner, max_corner, flags=0):
+        lo = np.ascontiguousarray(min_corner, np.float32); hi = np.ascontiguousarray(max_corner, np.float32)
+        self._check(self.L.vxb_polygonize_region(self.h, _ptr(lo), _ptr(hi), flags), "vxb_polygonize_region")
+        return self.info()
+
+    def region_info(self):
+        ri = RegionInfo()
+        self._check(self.L.vxb_region_info_get(self.h, C.byref(ri)), "vxb_region_info_get")
+        return ri
 
     def info(self):
         info = ResultInfo()

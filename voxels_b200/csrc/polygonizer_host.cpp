@@ -20,8 +20,11 @@
 #include <MaterialMap.h>
 #include <Polygonizer.h>
 
+#include <algorithm>
 #include <cstdint>
 #include <cstring>
+#include <memory>
+#include <mutex>
 #include <new>
 #include <vector>
 
@@ -72,14 +75,46 @@ struct BlockView : public BlockPolygons
 	virtual float3 GetMaximalCorner() const override { return MaximalCorner; }
 };
 
-// The polygonized surface: block views over four host arenas filled by one vxb_result_download.
+// Device contexts are expensive to create (stream, events, GBs of device memory), so destroyed surfaces hand theirs
+// back to a process-wide pool.
+std::mutex g_PoolLock;
+std::vector<vxb_context*> g_ContextPool;
+
+vxb_context* acquireContext()
+{
+	{
+		std::lock_guard<std::mutex> guard(g_PoolLock);
+		if (!g_ContextPool.empty()) { vxb_context* c = g_ContextPool.back(); g_ContextPool.pop_back(); return c; }
+	}
+	vxb_context* c = nullptr;
+	return vxb_create(0, &c) == VXB_OK ? c : nullptr;
+}
+
+void releaseContext(vxb_context* c)
+{
+	if (!c) return;
+	std::lock_guard<std::mutex> guard(g_PoolLock);
+	if (g_ContextPool.size() < 2) g_ContextPool.push_back(c); else vxb_destroy(c);
+}
+
+// host copy of the output of ONE device run
+struct Arena
+{
+	HostBuffer Verts, Idx, TransVerts, TransIdx;
+};
+
+// The polygonized surface: block views over host arenas (one per run: the full run + one small one per edit).
+// It owns the device context that holds the grid copy and the material caches of this surface, the way the
+// reference's PolygonMap owns its MaterialCache (TransVoxelImpl.h:81-95), so later incremental runs find them.
 struct SurfaceImpl : public PolygonSurface
 {
 	float3 Extents;
 	std::vector<std::vector<BlockView>> Levels;
 	PolygonizationStatistics Stats;
 	unsigned CacheBytes = 0;
-	HostBuffer Verts, Idx, TransVerts, TransIdx;
+	std::vector<std::unique_ptr<Arena>> Arenas;
+	vxb_context* Context = nullptr;
+	~SurfaceImpl() { releaseContext(Context); }
 
 	virtual float3 GetExtents() const override { return Extents; }
 	virtual unsigned GetLevelsCount() const override { return unsigned(Levels.size()); }
@@ -114,32 +149,83 @@ struct ModificationImpl : public Modification
 class TransVoxelImpl
 {
 public:
-	TransVoxelImpl() : Context(nullptr), Failed(false) {}
-	~TransVoxelImpl() { if (Context) vxb_destroy(Context); }
-
 	PolygonSurface* Execute(const Grid& grid, const MaterialMap* materials, Modification* modification);
 
 private:
-	bool EnsureContext();
-	vxb_context* Context;
-	bool Failed;
+	PolygonSurface* ExecuteIncremental(const Grid& grid, SurfaceImpl* surface, ModificationImpl* modification);
 	HostBuffer StageDist, StageMat, StageBlend;
 };
 
-bool TransVoxelImpl::EnsureContext()
+namespace
 {
-	if (Context) return true;
-	if (Failed) return false;
-	const int rc = vxb_create(0, &Context);
-	if (rc != VXB_OK)
-	{
-		char buffer[VOXELS_LOG_SIZE];
-		snprintf(buffer, VOXELS_LOG_SIZE, "Unable to polygonize grid: the B200 backend could not be initialised (%s)", vxb_last_error(nullptr));
-		logMessage(LS_Error, buffer);
-		Context = nullptr; Failed = true;
+// appends the blocks of the context's current result to the surface (views over a new arena)
+bool appendResult(vxb_context* ctx, SurfaceImpl* surface, unsigned n, const vxb_result_info& info)
+{
+	std::unique_ptr<Arena> arena(new Arena);
+	if (!arena->Verts.ensure(size_t(info.vertex_span) * sizeof(PolygonVertex) + 16) || !arena->Idx.ensure(size_t(info.index_span) * 4 + 16)
+		|| !arena->TransVerts.ensure(size_t(info.trans_vertex_span) * sizeof(PolygonVertex) + 16) || !arena->TransIdx.ensure(size_t(info.trans_index_span) * 4 + 16))
 		return false;
+	std::vector<vxb_block_record> records(info.block_count);
+	if (vxb_result_download(ctx, records.data(), arena->Verts.p, static_cast<uint32_t*>(arena->Idx.p), arena->TransVerts.p,
+		static_cast<uint32_t*>(arena->TransIdx.p)) != VXB_OK)
+		return false;
+	const PolygonVertex* verts = static_cast<const PolygonVertex*>(arena->Verts.p);
+	const unsigned* idx = static_cast<const unsigned*>(arena->Idx.p);
+	const PolygonVertex* tverts = static_cast<const PolygonVertex*>(arena->TransVerts.p);
+	const unsigned* tidx = static_cast<const unsigned*>(arena->TransIdx.p);
+	for (const vxb_block_record& r : records) // sorted: level, then z,y,x = the order PushBlocksToResult appends in (:1274-1293)
+	{
+		BlockView b;
+		b.Id = r.id;
+		b.Vertices = verts + r.vertex_offset; b.VertexCount = r.vertex_count;
+		b.Indices = idx + r.index_offset; b.IndexCount = r.index_count;
+		for (int f = 0; f < 6; ++f)
+		{
+			b.TransVertices[f] = tverts + r.trans_vertex_offset[f]; b.TransVertexCount[f] = r.trans_vertex_count[f];
+			b.TransIndices[f] = tidx + r.trans_index_offset[f]; b.TransIndexCount[f] = r.trans_index_count[f];
+		}
+		const unsigned m = 16u << r.level, nbl = n / m;
+		const unsigned bx = r.coord_id % nbl, by = (r.coord_id / nbl) % nbl, bz = r.coord_id / (nbl * nbl);
+		b.MinimalCorner = float3(float(bx * m), float(bz * m), float(by * m)); // y/z swapped on output (:1289-1291)
+		b.MaximalCorner = float3(float(bx * m + m), float(bz * m + m), float(by * m + m));
+		surface->Levels[r.level].push_back(b);
 	}
+	surface->Arenas.push_back(std::move(arena));
+	surface->Stats.BlocksCalculated = info.stats[0];
+	surface->Stats.TrivialCells = info.stats[1];
+	surface->Stats.NonTrivialCells = info.stats[2];
+	surface->Stats.DegenerateTrianglesRemoved = info.stats[3];
+	for (unsigned i = 0; i < PolygonizationStatistics::CASES_COUNT; ++i) surface->Stats.PerCaseCellsCount[i] = info.stats[4 + i];
 	return true;
+}
+
+// one LS_Error per vertex whose material has no mapping, as the reference logs them (:1364-1368)
+void logUnmapped(vxb_context* ctx)
+{
+	const uint64_t unmapped = vxb_result_unmapped_materials(ctx, nullptr, 0);
+	if (!unmapped) return;
+	std::vector<uint8_t> ids(unmapped);
+	vxb_result_unmapped_materials(ctx, ids.data(), unmapped);
+	char buffer[VOXELS_LOG_SIZE];
+	for (uint8_t id : ids)
+	{
+		snprintf(buffer, VOXELS_LOG_SIZE, "Unable to assign textures on vertex with material id %u", unsigned(id));
+		logMessage(LS_Error, buffer);
+	}
+}
+
+bool uploadMaterials(vxb_context* ctx, const MaterialMap* materials)
+{
+	// MaterialMap::GetMaterial pre-tabulated (the reference calls it per output vertex, :1249)
+	uint8_t table[256 * 6], valid[256];
+	for (unsigned id = 0; id < 256; ++id)
+	{
+		const MaterialMap::Material* m = materials ? materials->GetMaterial((unsigned char)id) : nullptr;
+		valid[id] = m ? 1 : 0;
+		for (int k = 0; k < 3; ++k) { table[id * 6 + k] = m ? m->DiffuseIds0[k] : 0; table[id * 6 + 3 + k] = m ? m->DiffuseIds1[k] : 0; }
+	}
+	return vxb_set_materials(ctx, table, valid) == VXB_OK;
+}
 }
 
 PolygonSurface* TransVoxelImpl::Execute(const Grid& grid, const MaterialMap* materials, Modification* modification)
@@ -152,22 +238,31 @@ PolygonSurface* TransVoxelImpl::Execute(const Grid& grid, const MaterialMap* mat
 		logMessage(LS_Error, buffer);
 		return nullptr;
 	}
-	if (!EnsureContext()) return nullptr;
-	auto fail = [&](const char* what) -> PolygonSurface* {
-		snprintf(buffer, VOXELS_LOG_SIZE, "Unable to polygonize grid: %s (%s)", what, vxb_last_error(Context));
+	// Execute(grid, materials, modification) with a surface to update: incremental path (:362-364, :429-465)
+	if (modification && modification->Map)
+	{
+		SurfaceImpl* surface = static_cast<SurfaceImpl*>(modification->Map);
+		if (surface->Context && unsigned(surface->Extents.x) == n)
+		{
+			if (!uploadMaterials(surface->Context, materials)) { logMessage(LS_Error, "Unable to polygonize grid: material table upload failed"); return nullptr; }
+			return ExecuteIncremental(grid, surface, static_cast<ModificationImpl*>(modification));
+		}
+	}
+
+	vxb_context* ctx = acquireContext();
+	if (!ctx)
+	{
+		snprintf(buffer, VOXELS_LOG_SIZE, "Unable to polygonize grid: the B200 backend could not be initialised (%s)", vxb_last_error(nullptr));
 		logMessage(LS_Error, buffer);
 		return nullptr;
-	};
-
-	// ---- MaterialMap::GetMaterial pre-tabulated (the reference calls it per output vertex, :1249) ----
-	uint8_t table[256 * 6], valid[256];
-	for (unsigned id = 0; id < 256; ++id)
-	{
-		const MaterialMap::Material* m = materials ? materials->GetMaterial((unsigned char)id) : nullptr;
-		valid[id] = m ? 1 : 0;
-		for (int k = 0; k < 3; ++k) { table[id * 6 + k] = m ? m->DiffuseIds0[k] : 0; table[id * 6 + 3 + k] = m ? m->DiffuseIds1[k] : 0; }
 	}
-	if (vxb_set_materials(Context, table, valid) != VXB_OK) return fail("material table upload failed");
+	auto fail = [&](const char* what) -> PolygonSurface* {
+		snprintf(buffer, VOXELS_LOG_SIZE, "Unable to polygonize grid: %s (%s)", what, vxb_last_error(ctx));
+		logMessage(LS_Error, buffer);
+		releaseContext(ctx);
+		return nullptr;
+	};
+	if (!uploadMaterials(ctx, materials)) return fail("material table upload failed");
 
 	// ---- grid -> device: every block through the public accessors, decompressed in parallel into pinned staging ----
 	const unsigned nb = n / 16;
@@ -186,81 +281,87 @@ PolygonSurface* TransVoxelImpl::Execute(const Grid& grid, const MaterialMap* mat
 			grid.GetBlockMaterialData(coords, sm + size_t(b) * 4096, sb + size_t(b) * 4096);
 		}
 	}
-	if (vxb_grid_upload_blocks(Context, n, static_cast<const int8_t*>(StageDist.p), static_cast<const uint8_t*>(StageMat.p),
+	if (vxb_grid_upload_blocks(ctx, n, static_cast<const int8_t*>(StageDist.p), static_cast<const uint8_t*>(StageMat.p),
 		static_cast<const uint8_t*>(StageBlend.p)) != VXB_OK) return fail("grid upload failed");
 
 	// ---- polygonize on the device ----
-	// Incremental updates (a Modification) are served by a full re-polygonization for now: the result is a valid
-	// surface for the edited grid, but block ids restart and the reference's stale-cache quirks are not reproduced.
-	if (vxb_polygonize(Context, 0, 0) != VXB_OK) return fail("polygonization failed");
+	if (vxb_polygonize(ctx, 0, 0) != VXB_OK) return fail("polygonization failed");
 	vxb_result_info info;
-	if (vxb_result_info_get(Context, &info) != VXB_OK) return fail("no result");
+	if (vxb_result_info_get(ctx, &info) != VXB_OK) return fail("no result");
 
 	SurfaceImpl* surface = new SurfaceImpl;
-	if (!surface->Verts.ensure(size_t(info.vertex_span) * sizeof(PolygonVertex) + 16) || !surface->Idx.ensure(size_t(info.index_span) * 4 + 16)
-		|| !surface->TransVerts.ensure(size_t(info.trans_vertex_span) * sizeof(PolygonVertex) + 16) || !surface->TransIdx.ensure(size_t(info.trans_index_span) * 4 + 16))
-	{ delete surface; return fail("host arena allocation failed"); }
-	std::vector<vxb_block_record> records(info.block_count);
-	if (vxb_result_download(Context, records.data(), surface->Verts.p, static_cast<uint32_t*>(surface->Idx.p), surface->TransVerts.p,
-		static_cast<uint32_t*>(surface->TransIdx.p)) != VXB_OK)
-	{ delete surface; return fail("result download failed"); }
-
-	// ---- views ----
 	surface->Extents = float3(float(n), float(n), float(n)); // (W, H, D) :481
 	surface->Levels.resize(info.levels_total);
-	const PolygonVertex* verts = static_cast<const PolygonVertex*>(surface->Verts.p);
-	const unsigned* idx = static_cast<const unsigned*>(surface->Idx.p);
-	const PolygonVertex* tverts = static_cast<const PolygonVertex*>(surface->TransVerts.p);
-	const unsigned* tidx = static_cast<const unsigned*>(surface->TransIdx.p);
-	for (const vxb_block_record& r : records)
-	{
-		BlockView b;
-		b.Id = r.id;
-		b.Vertices = verts + r.vertex_offset; b.VertexCount = r.vertex_count;
-		b.Indices = idx + r.index_offset; b.IndexCount = r.index_count;
-		for (int f = 0; f < 6; ++f)
-		{
-			b.TransVertices[f] = tverts + r.trans_vertex_offset[f]; b.TransVertexCount[f] = r.trans_vertex_count[f];
-			b.TransIndices[f] = tidx + r.trans_index_offset[f]; b.TransIndexCount[f] = r.trans_index_count[f];
-		}
-		const unsigned m = 16u << r.level, nbl = n / m;
-		const unsigned bx = r.coord_id % nbl, by = (r.coord_id / nbl) % nbl, bz = r.coord_id / (nbl * nbl);
-		b.MinimalCorner = float3(float(bx * m), float(bz * m), float(by * m)); // y/z swapped on output (:1289-1291)
-		b.MaximalCorner = float3(float(bx * m + m), float(bz * m + m), float(by * m + m));
-		surface->Levels[r.level].push_back(b);
-	}
-	surface->Stats.BlocksCalculated = info.stats[0];
-	surface->Stats.TrivialCells = info.stats[1];
-	surface->Stats.NonTrivialCells = info.stats[2];
-	surface->Stats.DegenerateTrianglesRemoved = info.stats[3];
-	for (unsigned i = 0; i < PolygonizationStatistics::CASES_COUNT; ++i) surface->Stats.PerCaseCellsCount[i] = info.stats[4 + i];
+	if (!appendResult(ctx, surface, n, info)) { delete surface; return fail("result download failed"); }
+	surface->Context = ctx; // from here on the surface owns the device state
 	{
 		// PolygonMap::GetCacheSizeBytes (:196-220): consistency bits of every level-0 block + {id, blend} of every coarser cell
 		size_t total = (size_t(nb) * nb * nb * 4096) >> 3;
 		for (unsigned l = 1; l < info.levels_total; ++l) { const size_t c = nb >> l; total += c * c * c * 4096 * 2; }
 		surface->CacheBytes = unsigned(total);
 	}
+	logUnmapped(ctx);
+	if (modification) modification->Map = surface; // (the reference would have dereferenced the null Map, :443)
+	return surface;
+}
 
-	// one LS_Error per vertex whose material has no mapping, as the reference logs them (:1364-1368)
-	const uint64_t unmapped = vxb_result_unmapped_materials(Context, nullptr, 0);
-	if (unmapped)
+PolygonSurface* TransVoxelImpl::ExecuteIncremental(const Grid& grid, SurfaceImpl* surface, ModificationImpl* modification)
+{
+	char buffer[VOXELS_LOG_SIZE];
+	vxb_context* ctx = surface->Context;
+	const unsigned n = grid.GetWidth(), nb = n / 16;
+	auto fail = [&](const char* what) -> PolygonSurface* {
+		snprintf(buffer, VOXELS_LOG_SIZE, "Unable to polygonize grid: %s (%s)", what, vxb_last_error(ctx));
+		logMessage(LS_Error, buffer);
+		return nullptr;
+	};
+	// ---- refresh the device copy of the edited region: the dirty box is in OUTPUT coordinates (x, grid z, grid y) ----
+	const float3 lo = modification->MinCornerModified, hi = modification->MaxCornerModified;
+	const float gmin[3] = { lo.x, lo.z, lo.y }, gmax[3] = { hi.x, hi.z, hi.y };
+	unsigned b0[3], b1[3];
+	for (int a = 0; a < 3; ++a)
 	{
-		std::vector<uint8_t> ids(unmapped);
-		vxb_result_unmapped_materials(Context, ids.data(), unmapped);
-		for (uint8_t id : ids)
+		const float mn = gmin[a] < 0.f ? 0.f : gmin[a], mx = gmax[a] < 0.f ? 0.f : gmax[a];
+		b0[a] = std::min(unsigned(mn) / 16u, nb - 1);
+		b1[a] = std::min(unsigned(mx) / 16u, nb - 1);
+		if (b1[a] < b0[a]) b1[a] = b0[a];
+	}
+	const size_t count = size_t(b1[0] - b0[0] + 1) * (b1[1] - b0[1] + 1) * (b1[2] - b0[2] + 1);
+	if (!StageDist.ensure(count * 4096) || !StageMat.ensure(count * 4096) || !StageBlend.ensure(count * 4096)) return fail("pinned staging allocation failed");
+	std::vector<uint32_t> coords(count * 3);
+	{
+		size_t i = 0;
+		for (unsigned z = b0[2]; z <= b1[2]; ++z) for (unsigned y = b0[1]; y <= b1[1]; ++y) for (unsigned x = b0[0]; x <= b1[0]; ++x, ++i)
 		{
-			snprintf(buffer, VOXELS_LOG_SIZE, "Unable to assign textures on vertex with material id %u", unsigned(id));
-			logMessage(LS_Error, buffer);
+			coords[i * 3] = x; coords[i * 3 + 1] = y; coords[i * 3 + 2] = z;
+			const float3 c = float3(float(x), float(y), float(z));
+			grid.GetBlockDistanceData(c, static_cast<char*>(StageDist.p) + i * 4096);
+			grid.GetBlockMaterialData(c, static_cast<unsigned char*>(StageMat.p) + i * 4096, static_cast<unsigned char*>(StageBlend.p) + i * 4096);
 		}
 	}
+	if (vxb_grid_update_blocks(ctx, uint32_t(count), coords.data(), static_cast<const int8_t*>(StageDist.p), static_cast<const uint8_t*>(StageMat.p),
+		static_cast<const uint8_t*>(StageBlend.p)) != VXB_OK) return fail("grid update failed");
 
-	if (modification)
+	// ---- re-polygonize the dirty boxes of all levels ----
+	const float minCorner[3] = { lo.x, lo.y, lo.z }, maxCorner[3] = { hi.x, hi.y, hi.z };
+	if (vxb_polygonize_region(ctx, minCorner, maxCorner, 0) != VXB_OK) return fail("incremental polygonization failed");
+	vxb_result_info info;
+	vxb_region_info region;
+	if (vxb_result_info_get(ctx, &info) != VXB_OK || vxb_region_info_get(ctx, &region) != VXB_OK) return fail("no result");
+
+	// ---- splice: drop the old blocks of each level's dirty box (:443-450), append the new ones (:1293) ----
+	for (unsigned l = 0; l < region.levels && l < surface->Levels.size(); ++l)
 	{
-		ModificationImpl* mod = static_cast<ModificationImpl*>(modification);
-		for (const auto& level : surface->Levels) for (const BlockView& b : level) mod->ModifiedBlocks.push_back(b.Id);
-		if (modification->Map) modification->Map->Destroy(); // the caller's old surface is replaced
-		modification->Map = surface;
+		const float* mn = region.min_dirty[l]; const float* mx = region.max_dirty[l];
+		auto& blocks = surface->Levels[l];
+		blocks.erase(std::remove_if(blocks.begin(), blocks.end(), [&](const BlockView& b) {
+			const float3& c = b.MinimalCorner;
+			return c.x >= mn[0] && c.y >= mn[1] && c.z >= mn[2] && c.x < mx[0] && c.y < mx[1] && c.z < mx[2];
+		}), blocks.end());
+		for (uint32_t i = 0; i < region.block_count[l]; ++i) modification->ModifiedBlocks.push_back(region.id_start[l] + i); // :463
 	}
+	if (!appendResult(ctx, surface, n, info)) return fail("result download failed");
+	logUnmapped(ctx);
 	return surface;
 }
 

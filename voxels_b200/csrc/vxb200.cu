@@ -91,6 +91,10 @@ struct vxb_context
 	CUtensorMap tmap;
 	int gridClassify = 0, gridDecideSmall = 0, gridDecideBig = 0, gridTransition = 0;
 	uint64_t capC = 0;
+	bool haveFullRun = false;      // device caches (consistency / material pages) describe the current grid
+	uint32_t nextId = 0;           // PolygonMap::GetNextBlockId (TransVoxelImpl.cpp:149-152)
+	vxb_region_info region;
+	DevBuf<unsigned int> updCoords;
 	bool directoryFetched = false;
 	VxbCounters lastCounters;
 	size_t validBytes = 0;
@@ -131,7 +135,7 @@ int ensureGridStorage(vxb_context* ctx, uint32_t n)
 	ctx->dDist = reinterpret_cast<const int8_t*>(ctx->volDist.p);
 	ctx->dMat = ctx->volMat.p; ctx->dBlend = ctx->volBlend.p;
 	ctx->n = n; ctx->levels = levelsFor(n);
-	ctx->ownsGrid = true; ctx->haveGrid = true; ctx->haveResult = false;
+	ctx->ownsGrid = true; ctx->haveGrid = true; ctx->haveResult = false; ctx->haveFullRun = false;
 	return VXB_OK;
 }
 
@@ -152,6 +156,14 @@ int buildTensorMap(vxb_context* ctx)
 }
 
 size_t blocksAtLevel(uint32_t n, int level) { const size_t nb = (n / 16) >> level; return nb * nb * nb; }
+
+// dirty box of an incremental run, per level (GenerateBlockListForLevel :429-465)
+struct Region
+{
+	int rangeMin[VXB_MAX_LEVELS][3], rangeMax[VXB_MAX_LEVELS][3]; // grid (x, y, z) block coordinates, [min, max)
+	unsigned idStart[VXB_MAX_LEVELS];
+	size_t count[VXB_MAX_LEVELS];
+};
 
 struct KernelTimer
 {
@@ -236,7 +248,7 @@ void vxb_destroy(vxb_context* ctx)
 	if (!ctx) return;
 	cudaSetDevice(ctx->device);
 	if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-	ctx->volDist.release(); ctx->volMat.release(); ctx->volBlend.release(); ctx->staging.release(); ctx->packOffsets.release();
+	ctx->volDist.release(); ctx->volMat.release(); ctx->volBlend.release(); ctx->staging.release(); ctx->packOffsets.release(); ctx->updCoords.release();
 	ctx->scanFlags.release(); ctx->blockInfo.release(); ctx->consPages.release(); ctx->validFlags.release();
 	ctx->cachePages.release(); ctx->worklist.release(); ctx->emitList.release(); ctx->bigList.release(); ctx->transList.release(); ctx->ntScratch.release(); ctx->cellBlock.release(); ctx->vlist.release(); ctx->cellRecs.release(); ctx->blockRecs.release(); ctx->tvlist.release(); ctx->verts.release(); ctx->tverts.release();
 	ctx->idx.release(); ctx->tidx.release(); ctx->records.release(); ctx->counters.release(); ctx->lut.release();
@@ -431,7 +443,7 @@ int vxb_grid_set_device(vxb_context* ctx, uint32_t n, const int8_t* dDist, const
 	cudaSetDevice(ctx->device);
 	ctx->dDist = dDist; ctx->dMat = dMat; ctx->dBlend = dBlend;
 	ctx->n = n; ctx->levels = levelsFor(n);
-	ctx->ownsGrid = false; ctx->haveGrid = true; ctx->haveResult = false;
+	ctx->ownsGrid = false; ctx->haveGrid = true; ctx->haveResult = false; ctx->haveFullRun = false;
 	return buildTensorMap(ctx);
 }
 
@@ -473,7 +485,7 @@ int vxb_set_capacity(vxb_context* ctx, uint64_t v, uint64_t i, uint64_t tv, uint
 	return VXB_OK;
 }
 
-int vxb_polygonize(vxb_context* ctx, uint32_t maxLevels, uint32_t flags)
+static int runPolygonize(vxb_context* ctx, uint32_t maxLevels, uint32_t flags, const Region* region)
 {
 	if (!ctx) return VXB_ERR_ARGUMENT;
 	if (!ctx->haveGrid) return fail(ctx, VXB_ERR_STATE, "vxb_polygonize: no grid uploaded");
@@ -531,6 +543,13 @@ int vxb_polygonize(vxb_context* ctx, uint32_t maxLevels, uint32_t flags)
 	dev.transitions = (flags & VXB_FLAG_NO_TRANSITIONS) ? 0 : 1;
 	dev.emitList = ctx->emitList.p; dev.bigList = ctx->bigList.p; dev.transList = ctx->transList.p; dev.ntScratch = ctx->ntScratch.p;
 	dev.blockRecs = ctx->blockRecs.p;
+	dev.incremental = region ? 1 : 0;
+	if (region)
+		for (int l = 0; l < levels; ++l)
+		{
+			for (int a = 0; a < 3; ++a) { dev.rangeMin[l][a] = region->rangeMin[l][a]; dev.rangeMax[l][a] = region->rangeMax[l][a]; }
+			dev.idStart[l] = region->idStart[l];
+		}
 
 	VxbCounters hc;
 	for (int attempt = 0; attempt < 6; ++attempt)
@@ -556,7 +575,7 @@ int vxb_polygonize(vxb_context* ctx, uint32_t maxLevels, uint32_t flags)
 		for (int k = 0; k < 8; ++k) ctx->kindLaunches[k] = 0;
 		VXB_CUDA(ctx, cudaEventRecord(ctx->evBegin, ctx->stream));
 		VXB_CUDA(ctx, cudaMemsetAsync(ctx->counters.p, 0, sizeof(VxbCounters), ctx->stream));
-		VXB_CUDA(ctx, cudaMemsetAsync(ctx->validFlags.p, 0, validBytes, ctx->stream));
+		if (!region) VXB_CUDA(ctx, cudaMemsetAsync(ctx->validFlags.p, 0, validBytes, ctx->stream)); // incremental runs keep the caches (:362-364)
 
 		{
 			const dim3 grid((unsigned)((nb0 + 7) / 8), (unsigned)nb0, (unsigned)nb0);
@@ -570,7 +589,8 @@ int vxb_polygonize(vxb_context* ctx, uint32_t maxLevels, uint32_t flags)
 		}
 		for (int l = 0; l < computed; ++l)
 		{
-			const size_t b = blocksAtLevel(n, l);
+			const size_t b = region ? region->count[l] : blocksAtLevel(n, l);
+			if (!b) continue;
 			const unsigned gs = (unsigned)std::min<size_t>((b + 255) / 256, (size_t)ctx->smCount * 8);
 			timer.begin(1);
 			vxb_select_kernel<<<gs, 256, 0, ctx->stream>>>(dev, l);
@@ -638,7 +658,12 @@ int vxb_polygonize(vxb_context* ctx, uint32_t maxLevels, uint32_t flags)
 	// statistics (TransVoxelImpl.cpp:528-531): BlocksCalculated counts every block of every computed level;
 	// TrivialCells only those of processed (not skipped) blocks
 	uint64_t blocksCalculated = 0, processedCells = (uint64_t)hc.nonSkippedLevel0 * 4096ull;
-	for (int l = 0; l < computed; ++l) { blocksCalculated += blocksAtLevel(n, l); if (l) processedCells += blocksAtLevel(n, l) * 4096ull; }
+	for (int l = 0; l < computed; ++l)
+	{
+		const size_t b = region ? region->count[l] : blocksAtLevel(n, l);
+		blocksCalculated += b;
+		if (l) processedCells += b * 4096ull;
+	}
 	info.stats[0] = (uint32_t)blocksCalculated;
 	info.stats[1] = (uint32_t)(processedCells - hc.nonTrivial);
 	info.stats[2] = hc.nonTrivial;
@@ -646,6 +671,87 @@ int vxb_polygonize(vxb_context* ctx, uint32_t maxLevels, uint32_t flags)
 	for (int i = 0; i < 16; ++i) info.stats[4 + i] = hc.perCase[i];
 	for (int i = 0; i < 8; ++i) info.used_materials[i] = hc.usedMaterials[i];
 	ctx->haveResult = true;
+	if (!region) { ctx->haveFullRun = (computed == levels); ctx->nextId = (uint32_t)totalBlocks; }
+	return VXB_OK;
+}
+
+int vxb_polygonize(vxb_context* ctx, uint32_t maxLevels, uint32_t flags)
+{
+	return runPolygonize(ctx, maxLevels, flags, nullptr);
+}
+
+int vxb_polygonize_region(vxb_context* ctx, const float minCorner[3], const float maxCorner[3], uint32_t flags)
+{
+	if (!ctx || !minCorner || !maxCorner) return VXB_ERR_ARGUMENT;
+	if (!ctx->haveGrid || !ctx->haveFullRun) return fail(ctx, VXB_ERR_STATE, "vxb_polygonize_region: needs a full vxb_polygonize of this grid first (the caches of that run are updated in place)");
+	// GenerateBlockListForLevel, modification branch (TransVoxelImpl.cpp:429-465); corners are in OUTPUT (Y-up) coordinates
+	Region region;
+	vxb_region_info& ri = ctx->region;
+	memset(&ri, 0, sizeof(ri));
+	ri.levels = (uint32_t)ctx->levels;
+	const float extent = (float)ctx->n;
+	uint32_t id = ctx->nextId;
+	for (int l = 0; l < ctx->levels; ++l)
+	{
+		const float blockMult = (float)((1 << l) * 16);
+		float minBlock[3], maxBlock[3];
+		for (int c = 0; c < 3; ++c)
+		{
+			float lo = floorf(minCorner[c] / blockMult - 1.0f) * blockMult, hi = floorf(maxCorner[c] / blockMult + 2.0f) * blockMult;
+			lo = lo < 0.f ? 0.f : (lo > extent ? extent : lo);
+			hi = hi < 0.f ? 0.f : (hi > extent ? extent : hi);
+			ri.min_dirty[l][c] = lo; ri.max_dirty[l][c] = hi;
+			minBlock[c] = lo / blockMult; maxBlock[c] = hi / blockMult;
+		}
+		// back to grid (Z-up) axes: x <- x, y <- output z, z <- output y  (:455-458)
+		const unsigned lo3[3] = { (unsigned)minBlock[0], (unsigned)minBlock[2], (unsigned)minBlock[1] };
+		const unsigned hi3[3] = { (unsigned)maxBlock[0], (unsigned)maxBlock[2], (unsigned)maxBlock[1] };
+		size_t count = 1;
+		for (int a = 0; a < 3; ++a)
+		{
+			region.rangeMin[l][a] = (int)lo3[a]; region.rangeMax[l][a] = (int)hi3[a];
+			count *= hi3[a] > lo3[a] ? hi3[a] - lo3[a] : 0;
+		}
+		region.idStart[l] = id; region.count[l] = count;
+		ri.id_start[l] = id; ri.block_count[l] = (uint32_t)count;
+		id += (uint32_t)count;
+	}
+	const int r = runPolygonize(ctx, 0, flags, &region);
+	if (r == VXB_OK) ctx->nextId = id;
+	return r;
+}
+
+int vxb_region_info_get(vxb_context* ctx, vxb_region_info* out)
+{
+	if (!ctx || !out) return VXB_ERR_ARGUMENT;
+	*out = ctx->region;
+	return VXB_OK;
+}
+
+int vxb_grid_update_blocks(vxb_context* ctx, uint32_t count, const uint32_t* blockCoords, const int8_t* dist, const uint8_t* mat, const uint8_t* blend)
+{
+	if (!ctx) return VXB_ERR_ARGUMENT;
+	if (!ctx->haveGrid || !ctx->ownsGrid) return fail(ctx, VXB_ERR_STATE, "vxb_grid_update_blocks: needs a grid uploaded into context-owned storage");
+	if (!count) return VXB_OK;
+	if (!blockCoords || !dist) return fail(ctx, VXB_ERR_ARGUMENT, "vxb_grid_update_blocks: null pointer");
+	cudaSetDevice(ctx->device);
+	const size_t bytes = (size_t)count * 4096;
+	VXB_CUDA(ctx, ctx->staging.ensure(bytes));
+	VXB_CUDA(ctx, ctx->updCoords.ensure((size_t)count * 3));
+	const uint32_t nb = ctx->n / 16;
+	for (uint32_t i = 0; i < count * 3; ++i) if (blockCoords[i] >= nb) return fail(ctx, VXB_ERR_ARGUMENT, "vxb_grid_update_blocks: block coordinate out of range");
+	VXB_CUDA(ctx, cudaMemcpyAsync(ctx->updCoords.p, blockCoords, (size_t)count * 12, cudaMemcpyHostToDevice, ctx->stream));
+	const void* src[3] = { dist, mat, blend };
+	uint8_t* dst[3] = { ctx->volDist.p, ctx->volMat.p, ctx->volBlend.p };
+	for (int c = 0; c < 3; ++c)
+	{
+		if (!src[c]) continue; // channel unchanged
+		VXB_CUDA(ctx, cudaMemcpyAsync(ctx->staging.p, src[c], bytes, cudaMemcpyHostToDevice, ctx->stream));
+		vxb_unpack_block_list_kernel<<<count, VXB_THREADS, 0, ctx->stream>>>(reinterpret_cast<const uint4*>(ctx->staging.p), ctx->updCoords.p, dst[c], (int)ctx->n);
+		VXB_CUDA(ctx, cudaGetLastError());
+		VXB_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // staging is reused by the next channel
+	}
+	ctx->haveResult = false;
 	return VXB_OK;
 }
 

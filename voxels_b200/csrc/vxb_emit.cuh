@@ -571,7 +571,7 @@ __global__ void __launch_bounds__(VXB_THREADS) vxb_finish_kernel(const VxbDev d)
 			vxb_block_record r;
 			const int level = (int)(br.packed >> 28);
 			const unsigned coordId = br.packed & 0x0FFFFFFFu;
-			r.level = level; r.coord_id = coordId; r.id = d.idBase[level] + coordId;
+			r.level = level; r.coord_id = coordId; r.id = vxb_block_id(d, level, coordId);
 			r.vertex_count = br.nverts; r.index_count = (br.ntris - br.removed) * 3;
 			r.vertex_offset = br.voff; r.index_offset = br.ioff;
 			for (int f = 0; f < 6; ++f)

@@ -78,6 +78,11 @@ struct VxbDev
 	unsigned int* worklist;
 	unsigned int workBase[VXB_MAX_LEVELS];
 	unsigned int idBase[VXB_MAX_LEVELS];
+	// incremental runs (GenerateBlockListForLevel, modification branch :429-465): per level a box of blocks and the
+	// id of its first block; ids follow the z,y,x loop order of :456-464
+	int incremental;
+	int rangeMin[VXB_MAX_LEVELS][3], rangeMax[VXB_MAX_LEVELS][3];
+	unsigned int idStart[VXB_MAX_LEVELS];
 	VxbVertex* verts; unsigned int* idx; VxbVertex* tverts; unsigned int* tidx;
 	vxb_block_record* records;
 	unsigned int vcap, icap, tvcap, ticap, rcap;
@@ -277,6 +282,16 @@ __global__ void __launch_bounds__(VXB_THREADS) vxb_unpack_blocks_kernel(const ui
 	*reinterpret_cast<uint4*>(dense + (((size_t)bz * 16 + z) * n + (size_t)by * 16 + y) * n + (size_t)bx * 16) = v;
 }
 
+// Incremental grid update: a list of 16^3 blocks -> their places in the dense volume
+__global__ void __launch_bounds__(VXB_THREADS) vxb_unpack_block_list_kernel(const uint4* __restrict__ blocks, const unsigned int* __restrict__ coords,
+	unsigned char* __restrict__ dense, int n)
+{
+	const size_t b = blockIdx.x;
+	const int bx = (int)coords[b * 3], by = (int)coords[b * 3 + 1], bz = (int)coords[b * 3 + 2];
+	const int row = threadIdx.x, y = row & 15, z = row >> 4;
+	*reinterpret_cast<uint4*>(dense + (((size_t)bz * 16 + z) * n + (size_t)by * 16 + y) * n + (size_t)bx * 16) = blocks[b * 256 + row];
+}
+
 // Upload helper: run-length decoding of one packed 16^3 block per CTA, all three channels
 // (VoxelGrid::DecompressBlock, VoxelGrid.cpp:674-694; block layout of PackForSave :304-312).
 // Thread t produces the 16 bytes of row t (x fastest): binary search of the run that covers its first byte.
@@ -337,14 +352,19 @@ __global__ void __launch_bounds__(VXB_THREADS) vxb_unpack_rle_kernel(const unsig
 __global__ void vxb_select_kernel(VxbDev d, int level)
 {
 	const int m = 1 << level, nb = d.n / 16 / m, nb0 = d.n / 16;
-	const unsigned total = (unsigned)nb * nb * nb;
+	// full run: every block of the level; incremental run: the dirty box of the level
+	const int x0 = d.incremental ? d.rangeMin[level][0] : 0, y0 = d.incremental ? d.rangeMin[level][1] : 0, z0 = d.incremental ? d.rangeMin[level][2] : 0;
+	const int nx = d.incremental ? d.rangeMax[level][0] - x0 : nb, ny = d.incremental ? d.rangeMax[level][1] - y0 : nb, nz = d.incremental ? d.rangeMax[level][2] - z0 : nb;
+	const unsigned total = (nx > 0 && ny > 0 && nz > 0) ? (unsigned)nx * ny * nz : 0u;
 	for (unsigned base = blockIdx.x * blockDim.x; base < total; base += gridDim.x * blockDim.x)
 	{
-		const unsigned b = base + threadIdx.x;
+		const unsigned q = base + threadIdx.x;
+		unsigned b = 0;
 		bool take = false, counted = false;
-		if (b < total)
+		if (q < total)
 		{
-			const int bx = b % nb, by = (b / nb) % nb, bz = b / (nb * nb);
+			const int bx = x0 + (int)(q % nx), by = y0 + (int)((q / nx) % ny), bz = z0 + (int)(q / ((unsigned)nx * ny));
+			b = ((unsigned)bz * nb + by) * nb + bx;
 			if (level == 0)
 			{
 				// AreBlockAndNeighborsEmpty :1511-1527
@@ -486,6 +506,17 @@ __device__ __noinline__ bool vxb_vote_cell(const VxbDev& d, int level, const int
 }
 
 struct VxbDecision { bool isNew, quirkV0; unsigned ownerIdx; int ok; };
+
+// Block id as the reference assigns it: full run = running counter over levels in z,y,x order (:395-401);
+// incremental run = continuation of that counter over the level's dirty box (:456-464)
+__device__ __forceinline__ unsigned vxb_block_id(const VxbDev& d, int level, unsigned coordId)
+{
+	if (!d.incremental) return d.idBase[level] + coordId;
+	const int nb = d.n / 16 >> level;
+	const int bx = coordId % nb, by = (coordId / nb) % nb, bz = coordId / (nb * nb);
+	const int nx = d.rangeMax[level][0] - d.rangeMin[level][0], ny = d.rangeMax[level][1] - d.rangeMin[level][1];
+	return d.idStart[level] + (unsigned)(((bz - d.rangeMin[level][2]) * ny + (by - d.rangeMin[level][1])) * nx + (bx - d.rangeMin[level][0]));
+}
 
 __device__ __forceinline__ void vxb_store_vertex(VxbVertex* dst, const VxbVertex& v)
 {
