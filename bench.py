@@ -156,32 +156,23 @@ def main():
         return 2
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    dist_ok = world > 1
-    if dist_ok:
-        import torch.distributed as td
-        td.init_process_group(backend="nccl", device_id=dev)
-
     import voxels_b200
     from voxels_b200 import synth
+    from voxels_b200.dist import Ranks, tile_origin, whole_job_throughput
+    ranks = Ranks("nccl", dev)
 
     flags = voxels_b200.FLAG_NO_TRANSITIONS if args.no_transitions else 0
-    dist, mat, blend = synth.terrain(n, dev, origin=(rank * n, 0))
+    dist, mat, blend = synth.terrain(n, dev, origin=tile_origin(rank, n))
     torch.cuda.synchronize()
     ctx = voxels_b200.Context(local_rank)
     ctx.set_device_grid(n, dist.data_ptr(), mat.data_ptr(), blend.data_ptr(), keep=(dist, mat, blend))
     stream = torch.cuda.ExternalStream(ctx.L.vxb_stream(ctx.h), device=dev)
 
     def barrier():
-        if dist_ok:
-            td.barrier(device_ids=[local_rank])
+        ranks.barrier()
         torch.cuda.synchronize()
 
-    def max_over_ranks(x):
-        if not dist_ok:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        td.all_reduce(t, op=td.ReduceOp.MAX)
-        return float(t.item())
+    max_over_ranks = ranks.max_over_ranks
 
     def timed(fn, steps):
         """K steps bracketed by barrier+synchronize; CUDA events on the launching stream; max over ranks."""
@@ -297,14 +288,14 @@ def main():
         for _ in range(2):
             step_e2e_packed()
         ms_e2e = timed(step_e2e_packed, esteps)
-        e2e = {"value": float(n) ** 3 * world / (ms_e2e * 1e-3) / 1e6, "unit": "Mvoxels/s", "ms_per_step": ms_e2e, "steps": esteps,
+        e2e = {"value": whole_job_throughput(n, world, ms_e2e), "unit": "Mvoxels/s", "ms_per_step": ms_e2e, "steps": esteps,
                "h2d_bytes_per_step": blob_bytes + 8 * (n // 16) ** 3, "d2h_bytes_per_step": int(d2h[0]),
                "path": "vxb_grid_upload_packed (PackForSave bytes, pinned host -> HBM, RLE decode on the GPU) + vxb_polygonize + "
                        "vxb_result_download (directory + arenas, HBM -> pinned host)"}
         for _ in range(2):
             step_e2e_dense()
         ms_dense = timed(step_e2e_dense, esteps)
-        e2e_dense = {"value": float(n) ** 3 * world / (ms_dense * 1e-3) / 1e6, "unit": "Mvoxels/s", "ms_per_step": ms_dense, "steps": esteps,
+        e2e_dense = {"value": whole_job_throughput(n, world, ms_dense), "unit": "Mvoxels/s", "ms_per_step": ms_dense, "steps": esteps,
                      "h2d_bytes_per_step": 3 * n ** 3, "d2h_bytes_per_step": int(d2h[0]),
                      "path": "vxb_grid_upload_dense (3 dense volumes, pinned host -> HBM) + vxb_polygonize + vxb_result_download"}
         stream = stream_saved
@@ -324,7 +315,7 @@ def main():
         else:
             cpu = {"value": None, "unit": "Mvoxels/s", "cores": 0, "kind": "reference", "sample": ci["unavailable"]}
 
-    value = float(n) ** 3 * world / (ms_resident * 1e-3) / 1e6
+    value = whole_job_throughput(n, world, ms_resident)
     if rank == 0:
         line = {
             "metric": "Mvoxels/s polygonized", "value": value, "unit": "Mvoxels/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -340,8 +331,7 @@ def main():
         }
         print(json.dumps(line))
     ctx.close()
-    if dist_ok:
-        td.destroy_process_group()
+    ranks.close()
     return 0
 
 
