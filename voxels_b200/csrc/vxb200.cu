@@ -60,8 +60,8 @@ struct vxb_context
 {
 	int device = 0;
 	int smCount = 0;
-	cudaStream_t stream = nullptr;
-	cudaEvent_t evBegin = nullptr, evEnd = nullptr;
+	cudaStream_t stream = nullptr, stream2 = nullptr;
+	cudaEvent_t evBegin = nullptr, evEnd = nullptr, evFork = nullptr, evDecide0 = nullptr, evJoin = nullptr;
 	std::vector<cudaEvent_t> kevents; // per-kernel timing (pairs)
 	std::string error;
 	EncodeTiledFn encodeTiled = nullptr;
@@ -211,7 +211,11 @@ int vxb_create(int device, vxb_context** out)
 	ctx->device = device; ctx->smCount = prop.multiProcessorCount;
 	memset(&ctx->info, 0, sizeof(ctx->info));
 	if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
-		(e = cudaEventCreate(&ctx->evBegin)) != cudaSuccess || (e = cudaEventCreate(&ctx->evEnd)) != cudaSuccess)
+		(e = cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking)) != cudaSuccess ||
+		(e = cudaEventCreate(&ctx->evBegin)) != cudaSuccess || (e = cudaEventCreate(&ctx->evEnd)) != cudaSuccess ||
+		(e = cudaEventCreateWithFlags(&ctx->evFork, cudaEventDisableTiming)) != cudaSuccess ||
+		(e = cudaEventCreateWithFlags(&ctx->evDecide0, cudaEventDisableTiming)) != cudaSuccess ||
+		(e = cudaEventCreateWithFlags(&ctx->evJoin, cudaEventDisableTiming)) != cudaSuccess)
 	{ fail(nullptr, VXB_ERR_CUDA, "stream/event creation", e); delete ctx; return VXB_ERR_CUDA; }
 
 	void* fn = nullptr;
@@ -255,6 +259,10 @@ void vxb_destroy(vxb_context* ctx)
 	for (cudaEvent_t e : ctx->kevents) cudaEventDestroy(e);
 	if (ctx->evBegin) cudaEventDestroy(ctx->evBegin);
 	if (ctx->evEnd) cudaEventDestroy(ctx->evEnd);
+	if (ctx->evFork) cudaEventDestroy(ctx->evFork);
+	if (ctx->evDecide0) cudaEventDestroy(ctx->evDecide0);
+	if (ctx->evJoin) cudaEventDestroy(ctx->evJoin);
+	if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
 	if (ctx->stream) cudaStreamDestroy(ctx->stream);
 	delete ctx;
 }
@@ -587,38 +595,71 @@ static int runPolygonize(vxb_context* ctx, uint32_t maxLevels, uint32_t flags, c
 			vxb_block_info_kernel<<<g2, 256, 0, ctx->stream>>>(ctx->dDist, (int)n, ctx->scanFlags.p, ctx->blockInfo.p);
 			timer.end(); ++launches; ++ctx->kindLaunches[1];
 		}
-		for (int l = 0; l < computed; ++l)
-		{
+		const unsigned flatGrid = (unsigned)ctx->smCount * 8;
+		auto classifyLevel = [&](int l, cudaStream_t st) {
 			const size_t b = region ? region->count[l] : blocksAtLevel(n, l);
-			if (!b) continue;
+			if (!b) return;
 			const unsigned gs = (unsigned)std::min<size_t>((b + 255) / 256, (size_t)ctx->smCount * 8);
 			timer.begin(1);
-			vxb_select_kernel<<<gs, 256, 0, ctx->stream>>>(dev, l);
+			vxb_select_kernel<<<gs, 256, 0, st>>>(dev, l);
 			timer.end(); ++launches; ++ctx->kindLaunches[1];
 			timer.begin(2);
-			vxb_classify_kernel<<<(unsigned)std::min<size_t>(b, ctx->gridClassify), VXB_THREADS, sizeof(VxbClassifySmem), ctx->stream>>>(ctx->tmap, dev, l);
+			vxb_classify_kernel<<<(unsigned)std::min<size_t>(b, ctx->gridClassify), VXB_THREADS, sizeof(VxbClassifySmem), st>>>(ctx->tmap, dev, l);
 			timer.end(); ++launches; ++ctx->kindLaunches[2];
-		}
-		// everything below runs ONCE for the blocks of all computed levels
-		const unsigned flatGrid = (unsigned)ctx->smCount * 8;
-		timer.begin(3);
-		vxb_decide_kernel<1024, 0><<<ctx->gridDecideSmall, VXB_THREADS, sizeof(VxbDecideSmemSmall), ctx->stream>>>(ctx->tmap, dev);
-		vxb_decide_kernel<4096, 1><<<ctx->gridDecideBig, VXB_THREADS, sizeof(VxbDecideSmemBig), ctx->stream>>>(ctx->tmap, dev);
-		timer.end(); launches += 2; ctx->kindLaunches[3] += 2;
-		timer.begin(4);
-		vxb_vertex_kernel<<<flatGrid, VXB_THREADS, 0, ctx->stream>>>(dev);
-		timer.end(); ++launches; ++ctx->kindLaunches[4];
-		timer.begin(5);
-		vxb_triangle_kernel<<<flatGrid, VXB_THREADS, 0, ctx->stream>>>(dev);
-		timer.end(); ++launches; ++ctx->kindLaunches[5];
-		timer.begin(6);
-		if (dev.transitions)
+		};
+		auto decideGroup = [&](int group, cudaStream_t st) {
+			timer.begin(3);
+			vxb_decide_kernel<1024, 0><<<ctx->gridDecideSmall, VXB_THREADS, sizeof(VxbDecideSmemSmall), st>>>(ctx->tmap, dev, group);
+			vxb_decide_kernel<4096, 1><<<ctx->gridDecideBig, VXB_THREADS, sizeof(VxbDecideSmemBig), st>>>(ctx->tmap, dev, group);
+			timer.end(); launches += 2; ctx->kindLaunches[3] += 2;
+		};
+		auto flatGroup = [&](int part, cudaStream_t st) {
+			timer.begin(4);
+			vxb_vertex_kernel<<<flatGrid, VXB_THREADS, 0, st>>>(dev, part);
+			timer.end(); ++launches; ++ctx->kindLaunches[4];
+			timer.begin(5);
+			vxb_triangle_kernel<<<flatGrid, VXB_THREADS, 0, st>>>(dev, part);
+			timer.end(); ++launches; ++ctx->kindLaunches[5];
+		};
+		auto transitions = [&](cudaStream_t st) {
+			timer.begin(6);
+			if (dev.transitions)
+			{
+				vxb_transition_kernel<<<ctx->gridTransition, VXB_THREADS, sizeof(VxbTransSmem), st>>>(dev);
+				vxb_transition_vertex_kernel<<<flatGrid, VXB_THREADS, 0, st>>>(dev);
+				launches += 2; ctx->kindLaunches[6] += 2;
+			}
+			timer.end();
+		};
+		// Levels depend on each other only through vxb_classify_kernel, so with more than one level the work forks:
+		//   stream : level 0 -> decide -> vertices -> triangles
+		//   stream2: classify levels 1.. (a latency-bound chain of small launches) -> decide -> vertices -> triangles -> transitions
+		// and joins before vxb_finish_kernel.  Per-kernel timing (VXB_FLAG_KERNEL_TIMES) runs everything on one stream.
+		const bool fork = computed > 1 && !kernelTimes;
+		classifyLevel(0, ctx->stream);
+		if (!fork)
 		{
-			vxb_transition_kernel<<<ctx->gridTransition, VXB_THREADS, sizeof(VxbTransSmem), ctx->stream>>>(dev);
-			vxb_transition_vertex_kernel<<<flatGrid, VXB_THREADS, 0, ctx->stream>>>(dev);
-			launches += 2; ctx->kindLaunches[6] += 2;
+			for (int l = 1; l < computed; ++l) classifyLevel(l, ctx->stream);
+			decideGroup(2, ctx->stream);
+			flatGroup(2, ctx->stream);
+			transitions(ctx->stream);
 		}
-		timer.end();
+		else
+		{
+			VXB_CUDA(ctx, cudaEventRecord(ctx->evFork, ctx->stream));
+			VXB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->evFork, 0));
+			for (int l = 1; l < computed; ++l) classifyLevel(l, ctx->stream2);
+			decideGroup(0, ctx->stream);
+			vxb_mark_split_kernel<<<1, 1, 0, ctx->stream>>>(dev); ++launches;
+			VXB_CUDA(ctx, cudaEventRecord(ctx->evDecide0, ctx->stream));
+			flatGroup(0, ctx->stream);
+			VXB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->evDecide0, 0)); // arena cursors are shared: group 1 allocates after group 0
+			decideGroup(1, ctx->stream2);
+			flatGroup(1, ctx->stream2);
+			transitions(ctx->stream2);
+			VXB_CUDA(ctx, cudaEventRecord(ctx->evJoin, ctx->stream2));
+			VXB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->evJoin, 0));
+		}
 		timer.begin(7);
 		vxb_finish_kernel<<<(unsigned)ctx->smCount * 2, VXB_THREADS, 0, ctx->stream>>>(dev);
 		timer.end(); ++launches; ++ctx->kindLaunches[7];

@@ -21,14 +21,14 @@
 
 struct __align__(128) VxbClassifySmem
 {
-	signed char tile[VXB_TILE_BYTES + 96];
+	signed char tiles[2][VXB_TILE_BYTES + 96]; // double buffered: the next block's tile lands while this one is classified
 	unsigned int rowSign[17 * 17 + 3]; // bit x = sample (x, y, z) of the tile is negative
 	unsigned int nt32[128];
 	unsigned int wpre[132];
 	unsigned short list[4096];
 	unsigned int warpSums[8];
 	unsigned int hist[16];
-	unsigned long long mbar;
+	unsigned long long mbar[2];
 	unsigned int item, hasChild, pageReady, emitIdx;
 };
 
@@ -77,25 +77,34 @@ __global__ void __launch_bounds__(VXB_THREADS, 4) vxb_classify_kernel(const __gr
 	const int tid = threadIdx.x;
 	const int m = 1 << level, nb = d.n / 16 / m;
 	const bool midLevel = level > 0 && level != d.lastLevel;
-	unsigned phase = 0;
-	if (tid == 0) vxb_mbar_init(&s.mbar, 1);
+	unsigned phase[2] = { 0, 0 };
+	VxbVoteSource voteSrc;
+	if (level > 0) voteSrc = vxb_vote_source(d, level);
+	if (tid == 0) { vxb_mbar_init(&s.mbar[0], 1); vxb_mbar_init(&s.mbar[1], 1); }
 	if (tid < 16) s.hist[tid] = 0;
 	unsigned statNonTrivial = 0;
+	const unsigned workCount = d.counters->workCount[level];
+	const unsigned* worklist = d.worklist + d.workBase[level];
+	if (tid == 0) s.item = atomicAdd(&d.counters->workCursor[level], 1u);
+	__syncthreads();
+	unsigned item = s.item;
+	int buf = 0;
+	if (item < workCount) { const unsigned c0 = worklist[item]; vxb_tile_issue(s.tiles[0], &s.mbar[0], &tmap, level, c0 % nb, (c0 / nb) % nb, c0 / (nb * nb)); }
 	__syncthreads();
 
-	const unsigned workCount = d.counters->workCount[level];
-	for (;;)
+	while (item < workCount)
 	{
 		if (tid == 0) { s.item = atomicAdd(&d.counters->workCursor[level], 1u); s.hasChild = 0; s.pageReady = 0; }
 		__syncthreads();
-		const unsigned item = s.item;
-		if (item >= workCount) break;
-		const unsigned coordId = d.worklist[d.workBase[level] + item];
+		const unsigned nextItem = s.item;
+		if (nextItem < workCount) { const unsigned c1 = worklist[nextItem]; vxb_tile_issue(s.tiles[buf ^ 1], &s.mbar[buf ^ 1], &tmap, level, c1 % nb, (c1 / nb) % nb, c1 / (nb * nb)); }
+		const unsigned coordId = worklist[item];
 		const int bx = coordId % nb, by = (coordId / nb) % nb, bz = coordId / (nb * nb);
-		vxb_stage_tile(s.tile, &s.mbar, phase, &tmap, d.grid, d.n, level, bx, by, bz);
+		signed char* const tile = s.tiles[buf];
+		vxb_tile_complete(tile, &s.mbar[buf], phase[buf], d.grid, d.n, level, bx, by, bz);
 		__syncthreads();
 
-		vxb_classify_bits(s.tile, s.rowSign, s.nt32);
+		vxb_classify_bits(tile, s.rowSign, s.nt32);
 		__syncthreads();
 		unsigned ntc;
 		{
@@ -136,14 +145,14 @@ __global__ void __launch_bounds__(VXB_THREADS, 4) vxb_classify_kernel(const __gr
 			{
 				const int c = s.list[i];
 				signed char v[8];
-				vxb_tile_samples(s.tile, c, v);
+				vxb_tile_samples(tile, c, v);
 				atomicAdd(&s.hist[vxbGRegularCellClass[vxb_case_code(v)]], 1u); // PerCaseCellsCount (:1574)
 				if (level > 0)
 				{
 					// material of every non-trivial cell (:1568): majority vote of its 8 children, stored in the level's page
 					const int base[3] = { (bx * 16 + (c & 15)) * m, (by * 16 + ((c >> 4) & 15)) * m, (bz * 16 + (c >> 8)) * m };
 					unsigned matId, matBlend;
-					if (vxb_vote_cell(d, level, base, matId, matBlend))
+					if (vxb_vote_cell(voteSrc, base[0], base[1], base[2], matId, matBlend))
 						d.cachePages[level][(size_t)coordId * 4096 + c] = (unsigned short)(matId | (matBlend << 8));
 				}
 			}
@@ -183,12 +192,14 @@ __global__ void __launch_bounds__(VXB_THREADS, 4) vxb_classify_kernel(const __gr
 					local[axis] = (face >= 3) ? 15 : 0; local[ua] = col; local[va] = row;
 					const int base[3] = { (bx * 16 + local[0]) * m, (by * 16 + local[1]) * m, (bz * 16 + local[2]) * m };
 					unsigned matId, matBlend;
-					if (vxb_vote_cell(d, level, base, matId, matBlend))
+					if (vxb_vote_cell(voteSrc, base[0], base[1], base[2], matId, matBlend))
 						d.cachePages[level][(size_t)coordId * 4096 + local[2] * 256 + local[1] * 16 + local[0]] = (unsigned short)(matId | (matBlend << 8));
 				}
 			}
 		}
 		__syncthreads();
+		item = nextItem;
+		buf ^= 1;
 	}
 
 	__syncthreads();
@@ -227,9 +238,12 @@ __device__ __forceinline__ unsigned vxb_rank_of(const unsigned int* nt32, const 
 
 // TIER 0: items come from the emit list (all levels, top level first); blocks with > CAP_C cells go to bigList.
 // TIER 1: items come from bigList (CAP_C = 4096 = every possible block).
+// group 0 = level 0 only, group 1 = levels >= 1, group 2 = all levels (single-stream runs)
 template <int CAP_C, int TIER>
-__global__ void __launch_bounds__(VXB_THREADS, (CAP_C <= 1024 ? 4 : 2)) vxb_decide_kernel(const __grid_constant__ CUtensorMap tmap, const VxbDev d)
+__global__ void __launch_bounds__(VXB_THREADS, (CAP_C <= 1024 ? 4 : 2)) vxb_decide_kernel(const __grid_constant__ CUtensorMap tmap, const VxbDev d, const int group)
 {
+	const int levelLo = (group == 1) ? 1 : 0, levelHi = (group == 0) ? 0 : d.levels - 1, g2 = group & 1;
+	const int levelCount = levelHi - levelLo + 1;
 	typedef VxbDecideSmem<CAP_C> Smem;
 	extern __shared__ __align__(128) unsigned char smemRaw[];
 	Smem& s = *reinterpret_cast<Smem*>(smemRaw);
@@ -241,16 +255,17 @@ __global__ void __launch_bounds__(VXB_THREADS, (CAP_C <= 1024 ? 4 : 2)) vxb_deci
 	{
 		vxb_mbar_init(&s.mbar, 1);
 		unsigned acc = 0; // work id -> level: the top level first (its blocks are the largest)
-		for (int l = d.levels - 1; l >= 0; --l) { acc += d.counters->emitCount[l]; s.levelEnd[d.levels - 1 - l] = acc; }
+		for (int l = levelHi; l >= levelLo; --l) { acc += d.counters->emitCount[l]; s.levelEnd[levelHi - l] = acc; }
 	}
 	for (int i = tid; i < 256; i += VXB_THREADS) { s.tabClass[i] = vxbGRegularCellClass[i]; s.tabCell[i] = vxbGRegularCellData[i]; }
 	for (int i = tid; i < 3072; i += VXB_THREADS) s.tabVert[i] = vxbGRegularVertexData[i];
 	__syncthreads();
-	const unsigned workCount = (TIER == 0) ? s.levelEnd[d.levels - 1] : d.counters->bigCount;
+	const unsigned workCount = (TIER == 0) ? s.levelEnd[levelCount - 1] : d.counters->bigCount[g2];
+	unsigned int* const bigList = d.bigList + (g2 ? d.workBase[1] : 0u); // group 1's rejects live behind level 0's segment
 
 	for (;;)
 	{
-		if (tid == 0) s.item = atomicAdd(TIER == 0 ? &d.counters->emitCursor : &d.counters->bigCursor, 1u);
+		if (tid == 0) s.item = atomicAdd(TIER == 0 ? &d.counters->emitCursor[g2] : &d.counters->bigCursor[g2], 1u);
 		__syncthreads();
 		const unsigned item = s.item;
 		if (item >= workCount) break;
@@ -259,10 +274,10 @@ __global__ void __launch_bounds__(VXB_THREADS, (CAP_C <= 1024 ? 4 : 2)) vxb_deci
 		{
 			int q = 0;
 			while (item >= s.levelEnd[q]) ++q;
-			const int lv = d.levels - 1 - q;
+			const int lv = levelHi - q;
 			emitIdx = d.workBase[lv] + (item - (q ? s.levelEnd[q - 1] : 0u));
 		}
-		else emitIdx = d.bigList[item];
+		else emitIdx = bigList[item];
 		const unsigned packed = d.emitList[emitIdx];
 		const int level = (int)(packed >> 28);
 		const unsigned coordId = packed & 0x0FFFFFFFu;
@@ -274,11 +289,12 @@ __global__ void __launch_bounds__(VXB_THREADS, (CAP_C <= 1024 ? 4 : 2)) vxb_deci
 		const unsigned ntc = s.wpre[127] + __popc(s.nt32[127]);
 		if (ntc > (unsigned)CAP_C)
 		{
-			if (tid == 0) d.bigList[atomicAdd(&d.counters->bigCount, 1u)] = emitIdx; // only reachable in TIER 0
+			if (tid == 0) bigList[atomicAdd(&d.counters->bigCount[g2], 1u)] = emitIdx; // only reachable in TIER 0
 			__syncthreads();
 			continue;
 		}
-		vxb_stage_tile(s.tile, &s.mbar, phase, &tmap, g, d.n, level, bx, by, bz);
+		vxb_tile_issue(s.tile, &s.mbar, &tmap, level, bx, by, bz);
+		vxb_tile_complete(s.tile, &s.mbar, phase, g, d.n, level, bx, by, bz);
 		// ordered compact list of the non-trivial cells: thread = cell row (z, y), 16 bits each
 		{
 			unsigned bits = reinterpret_cast<const unsigned short*>(s.nt32)[tid];
@@ -421,9 +437,15 @@ __device__ __forceinline__ bool vxb_overflowed(const VxbDev& d)
 }
 
 // ------------------------------------------------------------------------------------------------
-// flat kernels
+// flat kernels.  part 0 = [0, split) (group 0), part 1 = [split, total) (group 1), part 2 = everything
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(VXB_THREADS) vxb_vertex_kernel(const VxbDev d)
+__global__ void vxb_mark_split_kernel(const VxbDev d)
+{
+	d.counters->splitVertices = d.counters->vertices;
+	d.counters->splitCells = d.counters->cells;
+}
+
+__global__ void __launch_bounds__(VXB_THREADS) vxb_vertex_kernel(const VxbDev d, const int part)
 {
 	__shared__ unsigned sUsed[8];
 	if (threadIdx.x < 8) sUsed[threadIdx.x] = 0;
@@ -431,8 +453,9 @@ __global__ void __launch_bounds__(VXB_THREADS) vxb_vertex_kernel(const VxbDev d)
 	if (!vxb_overflowed(d))
 	{
 		const VxbGrid g = d.grid;
-		const unsigned total = d.counters->vertices;
-		for (unsigned j = blockIdx.x * blockDim.x + threadIdx.x; j < total; j += gridDim.x * blockDim.x)
+		const unsigned begin = (part == 1) ? d.counters->splitVertices : 0u;
+		const unsigned total = (part == 0) ? d.counters->splitVertices : d.counters->vertices;
+		for (unsigned j = begin + blockIdx.x * blockDim.x + threadIdx.x; j < total; j += gridDim.x * blockDim.x)
 		{
 			const unsigned e = d.vlist[j];
 			const unsigned ci = e >> 4; const int k = e & 15;
@@ -474,11 +497,12 @@ __global__ void __launch_bounds__(VXB_THREADS) vxb_vertex_kernel(const VxbDev d)
 	if (threadIdx.x < 8 && sUsed[threadIdx.x]) atomicOr(&d.counters->usedMaterials[threadIdx.x], sUsed[threadIdx.x]);
 }
 
-__global__ void __launch_bounds__(VXB_THREADS) vxb_triangle_kernel(const VxbDev d)
+__global__ void __launch_bounds__(VXB_THREADS) vxb_triangle_kernel(const VxbDev d, const int part)
 {
 	if (vxb_overflowed(d)) return;
-	const unsigned total = d.counters->cells;
-	for (unsigned ci = blockIdx.x * blockDim.x + threadIdx.x; ci < total; ci += gridDim.x * blockDim.x)
+	const unsigned begin = (part == 1) ? d.counters->splitCells : 0u;
+	const unsigned total = (part == 0) ? d.counters->splitCells : d.counters->cells;
+	for (unsigned ci = begin + blockIdx.x * blockDim.x + threadIdx.x; ci < total; ci += gridDim.x * blockDim.x)
 	{
 		const uint4 crv = *reinterpret_cast<const uint4*>(&d.cellRecs[ci]);
 		const unsigned slot = d.cellBlock[ci];

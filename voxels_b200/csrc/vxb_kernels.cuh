@@ -39,9 +39,10 @@ struct VxbCounters
 	unsigned int workCount[VXB_MAX_LEVELS];
 	unsigned int workCursor[VXB_MAX_LEVELS];
 	unsigned int emitCount[VXB_MAX_LEVELS]; // blocks with non-trivial cells, per level (vxb_classify_kernel)
-	unsigned int emitCursor;
-	unsigned int bigCount, bigCursor;       // blocks with > 1024 non-trivial cells (second tier of vxb_decide_kernel)
+	unsigned int emitCursor[2];             // per group: 0 = level 0, 1 = levels >= 1 (the groups run on two streams)
+	unsigned int bigCount[2], bigCursor[2]; // blocks with > 1024 non-trivial cells (second tier of vxb_decide_kernel)
 	unsigned int cells;                     // cursor of the cell-record arena
+	unsigned int splitVertices, splitCells; // arena cursors after group 0: the flat kernels of the two groups split there
 	unsigned int transBlocks, transCursor;  // emitted mid-level blocks (vxb_transition_kernel work list)
 	unsigned int finishCursor;
 };
@@ -423,20 +424,25 @@ __global__ void vxb_select_kernel(VxbDev d, int level)
 // ------------------------------------------------------------------------------------------------
 // K3: polygonize
 // ------------------------------------------------------------------------------------------------
-// stage the 17^3 sample tile of block (bx,by,bz) at `level` into smem (TMA for level 0, clamped strided gather above)
-__device__ __forceinline__ void vxb_stage_tile(signed char* tile, unsigned long long* mbar, unsigned& phase, const CUtensorMap* tmap,
+// 17^3 sample tile of block (bx,by,bz) at `level` -> smem: level 0 by one 3-D TMA load (issued early by thread 0, so
+// it can be in flight while the CTA still works on the previous block), coarser levels by a clamped strided gather.
+__device__ __forceinline__ void vxb_tile_issue(signed char* tile, unsigned long long* mbar, const CUtensorMap* tmap, int level, int bx, int by, int bz)
+{
+	if (level == 0 && threadIdx.x == 0)
+	{
+		vxb_fence_proxy_async();
+		vxb_mbar_expect_tx(mbar, VXB_TILE_BYTES);
+		vxb_tma_load_3d(tile, tmap, bx * 16, by * 16, bz * 16, mbar);
+	}
+}
+
+__device__ __forceinline__ void vxb_tile_complete(signed char* tile, unsigned long long* mbar, unsigned& phase,
 	const VxbGrid& g, int n, int level, int bx, int by, int bz)
 {
 	const int tid = threadIdx.x;
 	const int m = 1 << level, nb = n / 16 / m;
 	if (level == 0)
 	{
-		if (tid == 0)
-		{
-			vxb_fence_proxy_async();
-			vxb_mbar_expect_tx(mbar, VXB_TILE_BYTES);
-			vxb_tma_load_3d(tile, tmap, bx * 16, by * 16, bz * 16, mbar);
-		}
 		vxb_mbar_wait(mbar, phase);
 		phase ^= 1;
 		// far grid edge: the +1 plane is outside the volume (TMA zero-fills); the reference clamps (:1037-1047)
@@ -459,18 +465,37 @@ __device__ __forceinline__ void vxb_stage_tile(signed char* tile, unsigned long 
 // CalculateMaterialForCellCache :753-838 for level >= 1, children read through the page tables.
 // The 8 children of a cell share one block of the child level (cell bases are even in child units), so the block
 // lookup and the validity test happen once, and the common all-empty case exits after 4 loads.
-__device__ __noinline__ bool vxb_vote_cell(const VxbDev& d, int level, const int base[3], unsigned& id, unsigned& blend)
+struct VxbVoteSource // what a vote at `level` reads: the child level's validity flags + pages (+ level-0 materials)
 {
+	const unsigned char* valid;  // consValid (level 1) / cacheValid[level - 1]
+	const void* pages;           // consPages (level 1) / cachePages[level - 1]
+	const unsigned char* mat;
+	const unsigned char* blend;
+	int n, level;
+};
+
+__device__ __forceinline__ VxbVoteSource vxb_vote_source(const VxbDev& d, int level)
+{
+	VxbVoteSource v;
+	v.valid = (level == 1) ? d.consValid : d.cacheValid[level - 1];
+	v.pages = (level == 1) ? (const void*)d.consPages : (const void*)d.cachePages[level - 1];
+	v.mat = d.grid.mat; v.blend = d.grid.blend; v.n = d.n; v.level = level;
+	return v;
+}
+
+__device__ __noinline__ bool vxb_vote_cell(const VxbVoteSource d, const int bx0, const int by0, const int bz0, unsigned& id, unsigned& blend)
+{
+	const int level = d.level;
+	const int base[3] = { bx0, by0, bz0 };
 	const int cm = (1 << level) >> 1, cnb = d.n / 16 / cm;
 	const int cx = base[0] / cm, cy = base[1] / cm, cz = base[2] / cm;            // child-level cell coordinates (even)
 	const size_t bid = ((size_t)(cz >> 4) * cnb + (cy >> 4)) * cnb + (cx >> 4);
 	const int lx = cx & 15, ly = cy & 15, lz = cz & 15;
-	VxbVote v;
-	vxb_vote_init(v);
+	unsigned cid[8], cbl[8]; // children, x fastest (:773-775); fully unrolled below so they live in registers
 	if (level == 1)
 	{
-		if (!d.consValid[bid]) return false;
-		const unsigned short* rows = reinterpret_cast<const unsigned short*>(d.consPages + bid * 128); // 16 bits per (z,y) row
+		if (!d.valid[bid]) return false;
+		const unsigned short* rows = reinterpret_cast<const unsigned short*>(static_cast<const unsigned int*>(d.pages) + bid * 128); // 16 bits per (z,y) row
 		const unsigned r00 = (rows[lz * 16 + ly] >> lx) & 3u, r01 = (rows[lz * 16 + ly + 1] >> lx) & 3u;
 		const unsigned r10 = (rows[(lz + 1) * 16 + ly] >> lx) & 3u, r11 = (rows[(lz + 1) * 16 + ly + 1] >> lx) & 3u;
 		const unsigned bits = r00 | (r01 << 2) | (r10 << 4) | (r11 << 6); // child q = x + 2y + 4z
@@ -478,31 +503,44 @@ __device__ __noinline__ bool vxb_vote_cell(const VxbDev& d, int level, const int
 #pragma unroll
 		for (int q = 0; q < 8; ++q)
 		{
-			unsigned cid = VXB_EMPTY_MATERIAL, cblend = 0;
+			cid[q] = VXB_EMPTY_MATERIAL; cbl[q] = 0;
 			if ((bits >> q) & 1u)
 			{
 				const size_t gi = ((size_t)(base[2] + (q >> 2)) * d.n + (base[1] + ((q >> 1) & 1))) * d.n + (base[0] + (q & 1));
-				cid = d.grid.mat[gi]; cblend = d.grid.blend[gi];
+				cid[q] = d.mat[gi]; cbl[q] = d.blend[gi];
 			}
-			vxb_vote_add(v, cid, cblend);
 		}
 	}
 	else
 	{
-		if (!d.cacheValid[level - 1][bid]) return false;
-		const unsigned int* page = reinterpret_cast<const unsigned int*>(d.cachePages[level - 1] + bid * 4096); // 2 cells per word
+		if (!d.valid[bid]) return false;
+		const unsigned int* page = reinterpret_cast<const unsigned int*>(static_cast<const unsigned short*>(d.pages) + bid * 4096); // 2 cells per word
 		const int o = (lz * 256 + ly * 16 + lx) >> 1;
 		const unsigned e0 = page[o], e1 = page[o + 8], e2 = page[o + 128], e3 = page[o + 136];
 		if ((e0 & e1 & e2 & e3 & 0x00FF00FFu) == 0x00FF00FFu) return false; // all eight children EMPTY_MATERIAL
-		const unsigned e[4] = { e0, e1, e2, e3 };
-#pragma unroll
-		for (int q = 0; q < 8; ++q)
-		{
-			const unsigned w = e[q >> 1] >> ((q & 1) * 16);
-			vxb_vote_add(v, w & 0xFF, (w >> 8) & 0xFF);
-		}
+		cid[0] = e0 & 0xFF; cbl[0] = (e0 >> 8) & 0xFF; cid[1] = (e0 >> 16) & 0xFF; cbl[1] = e0 >> 24;
+		cid[2] = e1 & 0xFF; cbl[2] = (e1 >> 8) & 0xFF; cid[3] = (e1 >> 16) & 0xFF; cbl[3] = e1 >> 24;
+		cid[4] = e2 & 0xFF; cbl[4] = (e2 >> 8) & 0xFF; cid[5] = (e2 >> 16) & 0xFF; cbl[5] = e2 >> 24;
+		cid[6] = e3 & 0xFF; cbl[6] = (e3 >> 8) & 0xFF; cid[7] = (e3 >> 16) & 0xFF; cbl[7] = e3 >> 24;
 	}
-	return vxb_vote_result(v, id, blend);
+	// majority vote (:812-834) without the candidate arrays: candidate = first occurrence of an id, in order of first
+	// appearance; a later candidate wins only with a strictly larger count (std::max_element keeps the first maximum)
+	int bestCount = 0; unsigned bestId = 0, bestBlend = 0;
+#pragma unroll
+	for (int q = 0; q < 8; ++q)
+	{
+		bool first = cid[q] != VXB_EMPTY_MATERIAL;
+#pragma unroll
+		for (int p = 0; p < q; ++p) first = first && (cid[p] != cid[q]);
+		int cnt = 0; unsigned bsum = 0;
+#pragma unroll
+		for (int p = q; p < 8; ++p) if (cid[p] == cid[q]) { ++cnt; bsum += cbl[p]; }
+		if (first && cnt > bestCount) { bestCount = cnt; bestId = cid[q]; bestBlend = bsum; }
+	}
+	if (!bestCount) return false;
+	id = bestId;
+	blend = (bestBlend / (unsigned)bestCount) & 0xFFu;
+	return true;
 }
 
 struct VxbDecision { bool isNew, quirkV0; unsigned ownerIdx; int ok; };
