@@ -618,16 +618,19 @@ __global__ void __launch_bounds__(VXB_THREADS) vxb_finish_kernel(const VxbDev d)
 // ------------------------------------------------------------------------------------------------
 struct __align__(16) VxbTransSmem
 {
-	unsigned long long slots[1536]; // 10 owned-slot nibbles per cell
-	unsigned short code[1536];      // 9-bit transition case code, 0 = trivial / face without neighbour
+	// per NON-TRIVIAL transition cell, in the reference's serial order (face, row, col) = compact index
+	unsigned long long slots[1536]; // 10 owned-slot nibbles
+	unsigned short cell[1536];      // face * 256 + row * 16 + col
 	unsigned short newMask[1536];
-	unsigned short vbase[1536];
-	unsigned short tbase[1536];
+	unsigned short vbase[1536];     // new-vertex count, then its exclusive scan (running over all faces)
+	unsigned short tbase[1536];     // triangle count, then its exclusive scan
 	unsigned char mat[1536];
+	unsigned short code[1536];      // per CELL (not compact): 9-bit transition case code, 0 = trivial / face without neighbour
 	signed char face[6][1092];      // the 33 x 33 half-stride sample lattice of each face plane (clamped reads)
-	unsigned int nt[48];
+	unsigned int nt[48];            // non-trivial bits, cell order
+	unsigned int pre[49];           // exclusive prefix of popc(nt): compact index base of each word
 	unsigned int warpSums[8];
-	unsigned int used[8];
+	unsigned int faceV[7], faceT[7]; // scan value at the first compact entry of each face (+ grand total)
 	unsigned int tvoff[6], tioff[6], tvcount[6], ticount[6];
 	unsigned int item;
 };
@@ -648,13 +651,11 @@ __global__ void __launch_bounds__(VXB_THREADS, 4) vxb_transition_kernel(const Vx
 	VxbTransSmem& s = *reinterpret_cast<VxbTransSmem*>(smemRaw);
 	if (vxb_overflowed(d)) return;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	const int row = tid >> 4, col = tid & 15;
 	const VxbGrid g = d.grid;
 	const unsigned workCount = d.counters->transBlocks;
 	for (;;)
 	{
 		if (tid == 0) s.item = atomicAdd(&d.counters->transCursor, 1u);
-		if (tid < 6) { s.tvcount[tid] = 0; s.ticount[tid] = 0; s.tvoff[tid] = 0; s.tioff[tid] = 0; }
 		__syncthreads();
 		if (s.item >= workCount) break;
 		const unsigned slot = d.transList[s.item];
@@ -684,7 +685,7 @@ __global__ void __launch_bounds__(VXB_THREADS, 4) vxb_transition_kernel(const Vx
 			}
 		}
 		__syncthreads();
-		// T1: case codes (cell = thread, one face per iteration; thread order = the reference's row-major order)
+		// T1: case code of every cell (cell = face * 256 + thread: thread order = the reference's row-major order)
 #pragma unroll 1
 		for (int face = 0; face < 6; ++face)
 		{
@@ -695,7 +696,7 @@ __global__ void __launch_bounds__(VXB_THREADS, 4) vxb_transition_kernel(const Vx
 			if (!(face < 3 ? (bc == 0) : (bc == nb - 1))) // neighbour block inside the grid (:1829-1835)
 			{
 				signed char v[13];
-				vxb_face_cell_samples(s.face[face], row, col, v);
+				vxb_face_cell_samples(s.face[face], tid >> 4, tid & 15, v);
 				code = vxb_transition_case_code(v);
 				if (code == 511u) code = 0;
 			}
@@ -703,134 +704,157 @@ __global__ void __launch_bounds__(VXB_THREADS, 4) vxb_transition_kernel(const Vx
 			if (lane == 0) s.nt[face * 8 + warp] = bal;
 			s.code[face * 256 + tid] = (unsigned short)code;
 		}
-		// T2: owned slots + material of the non-trivial cells
-#pragma unroll 1
-		for (int face = 0; face < 6; ++face)
+		__syncthreads();
+		unsigned ntc;
 		{
-			const int ci = face * 256 + tid;
-			const unsigned code = s.code[ci];
-			unsigned long long slots = ~0ull;
-			unsigned matId = VXB_EMPTY_MATERIAL;
-			if (code)
+			const unsigned cnt = (tid < 48) ? __popc(s.nt[tid]) : 0u;
+			const unsigned ex = vxb_block_scan(cnt, s.warpSums, ntc);
+			if (tid < 48) s.pre[tid] = ex;
+			if (tid == 0) s.pre[48] = ntc;
+		}
+		__syncthreads();
+		if (tid < 6) { s.tvcount[tid] = 0; s.ticount[tid] = 0; s.tvoff[tid] = 0; s.tioff[tid] = 0; }
+		if (ntc > 0) // block-uniform
+		{
+			// ordered compact list of the non-trivial cells
+#pragma unroll 1
+			for (int face = 0; face < 6; ++face)
 			{
+				const int ci = face * 256 + tid;
+				if (s.code[ci]) s.cell[s.pre[ci >> 5] + __popc(s.nt[ci >> 5] & ((1u << (ci & 31)) - 1u))] = (unsigned short)ci;
+			}
+			__syncthreads();
+			// T2: owned slots + material, one thread per non-trivial cell
+			for (unsigned i = tid; i < ntc; i += VXB_THREADS)
+			{
+				const int ci = s.cell[i], face = ci >> 8, row = (ci >> 4) & 15, col = ci & 15;
+				const unsigned code = s.code[ci];
 				int axis, ua, va;
 				vxb_face_axes(face, axis, ua, va);
 				int local[3];
 				local[axis] = (face >= 3) ? 15 : 0; local[ua] = col; local[va] = row;
-				matId = d.cachePages[level][(size_t)coordId * 4096 + local[2] * 256 + local[1] * 16 + local[0]] & 0xFF;
-				const int base[3] = { (bx * 16 + local[0]) * m, (by * 16 + local[1]) * m, (bz * 16 + local[2]) * m };
 				signed char v[13];
 				vxb_face_cell_samples(s.face[face], row, col, v);
+				unsigned long long slots = ~0ull;
 				const int nv = vxbGTransitionCellData[(vxbGTransitionCellClass[code] & 0x7F) * 40] >> 4;
 				for (int k = 0; k < nv; ++k)
 				{
 					const VxbTransVertexDesc td = vxb_transition_vertex_desc(vxbGTransitionVertexData[code * 12 + k], v, vxbGTransitionCornerData);
 					if (td.dir == 8) slots = (slots & ~(0xFull << (4 * td.slot))) | ((unsigned long long)k << (4 * td.slot)); // stored only when no reuse was attempted (:2097)
 				}
+				s.slots[i] = slots;
+				s.mat[i] = (unsigned char)(d.cachePages[level][(size_t)coordId * 4096 + local[2] * 256 + local[1] * 16 + local[0]] & 0xFF);
 			}
-			s.slots[ci] = slots;
-			s.mat[ci] = (unsigned char)matId;
-		}
-		__syncthreads();
-		// T3: decisions + per-face ordered scans
-#pragma unroll 1
-		for (int face = 0; face < 6; ++face)
-		{
-			int axis, ua, va;
-			vxb_face_axes(face, axis, ua, va);
-			const int bc = (axis == 0) ? bx : (axis == 1 ? by : bz);
-			if (face < 3 ? (bc == 0) : (bc == nb - 1)) continue; // block-uniform
-			const int ci = face * 256 + tid;
-			const unsigned code = s.code[ci];
-			unsigned newMask = 0, ntri = 0;
-			if (code)
+			__syncthreads();
+			// T3: new-vs-reuse decisions (owner = previous row / previous column of the same face, :1958-1978)
+			for (unsigned i = tid; i < ntc; i += VXB_THREADS)
 			{
-				int local[3];
-				local[axis] = (face >= 3) ? 15 : 0; local[ua] = col; local[va] = row;
-				const int base[3] = { (bx * 16 + local[0]) * m, (by * 16 + local[1]) * m, (bz * 16 + local[2]) * m };
+				const int ci = s.cell[i], face = ci >> 8, row = (ci >> 4) & 15, col = ci & 15;
+				const unsigned code = s.code[ci];
 				signed char v[13];
 				vxb_face_cell_samples(s.face[face], row, col, v);
 				const unsigned geo = vxbGTransitionCellData[(vxbGTransitionCellClass[code] & 0x7F) * 40];
-				ntri = geo & 0xF;
-				const unsigned rowBits = (s.nt[face * 8 + warp] >> (lane & 16)) & 0xFFFFu;
+				const unsigned rowBits = (s.nt[ci >> 5] >> (ci & 16)) & 0xFFFFu;
 				const int mask = ((row > 0) ? 2 : 0) | ((rowBits & ((1u << col) - 1u)) ? 1 : 0);
-				const unsigned myMat = s.mat[ci];
+				const unsigned myMat = s.mat[i];
+				unsigned newMask = 0;
 				for (int k = 0; k < (int)(geo >> 4); ++k)
 				{
 					const VxbTransVertexDesc td = vxb_transition_vertex_desc(vxbGTransitionVertexData[code * 12 + k], v, vxbGTransitionCornerData);
 					bool isNew = true;
 					if ((td.dir & mask) == td.dir)
 					{
-						const int oc = face * 256 + (row - ((td.dir >> 1) & 1)) * 16 + (col - (td.dir & 1));
-						const int ok = (int)((s.slots[oc] >> (4 * td.slot)) & 0xF); // trivial cells hold all-NO_SLOT
-						if (ok != VXB_NO_SLOT && s.mat[oc] == myMat) isNew = false;
+						const int oc = ci - ((td.dir >> 1) & 1) * 16 - (td.dir & 1);
+						if ((s.nt[oc >> 5] >> (oc & 31)) & 1u)
+						{
+							const unsigned oi = s.pre[oc >> 5] + __popc(s.nt[oc >> 5] & ((1u << (oc & 31)) - 1u));
+							const int ok = (int)((s.slots[oi] >> (4 * td.slot)) & 0xF);
+							if (ok != VXB_NO_SLOT && s.mat[oi] == myMat) isNew = false;
+						}
 					}
 					if (isNew) newMask |= 1u << k;
 				}
+				s.newMask[i] = (unsigned short)newMask;
+				s.vbase[i] = (unsigned short)__popc(newMask);
+				s.tbase[i] = (unsigned short)(geo & 0xF);
 			}
-			s.newMask[ci] = (unsigned short)newMask;
-			unsigned total;
-			const unsigned base2 = vxb_block_scan(__popc(newMask) | (ntri << 16), s.warpSums, total);
-			s.vbase[ci] = (unsigned short)(base2 & 0xFFFF);
-			s.tbase[ci] = (unsigned short)(base2 >> 16);
-			if (tid == 0)
+			__syncthreads();
+			// one exclusive scan over all non-trivial cells (serial order); per-face bases are differences to the face start
 			{
-				const unsigned fv = total & 0xFFFF, fi = (total >> 16) * 3;
-				s.tvcount[face] = fv; s.ticount[face] = fi;
-				s.tvoff[face] = fv ? atomicAdd(&d.counters->transVertices, fv) : 0u;
-				s.tioff[face] = fi ? atomicAdd(&d.counters->transIndices, fi) : 0u;
+				const unsigned per = (ntc + VXB_THREADS - 1) / VXB_THREADS;
+				const unsigned i0 = min(tid * per, ntc), i1 = min(i0 + per, ntc);
+				unsigned sv = 0, st = 0;
+				for (unsigned i = i0; i < i1; ++i) { sv += s.vbase[i]; st += s.tbase[i]; }
+				unsigned total;
+				const unsigned base = vxb_block_scan(sv | (st << 16), s.warpSums, total);
+				unsigned bv = base & 0xFFFF, bt = base >> 16;
+				for (unsigned i = i0; i < i1; ++i)
+				{
+					const unsigned cv = s.vbase[i], ct = s.tbase[i];
+					s.vbase[i] = (unsigned short)bv; s.tbase[i] = (unsigned short)bt;
+					bv += cv; bt += ct;
+				}
+				if (tid == 0) { s.faceV[6] = total & 0xFFFF; s.faceT[6] = total >> 16; }
+			}
+			__syncthreads();
+			if (tid < 6)
+			{
+				const unsigned first = s.pre[tid * 8]; // compact index of the face's first non-trivial cell
+				s.faceV[tid] = first < ntc ? s.vbase[first] : s.faceV[6];
+				s.faceT[tid] = first < ntc ? s.tbase[first] : s.faceT[6];
+			}
+			__syncthreads();
+			if (tid < 6)
+			{
+				const unsigned fv = s.faceV[tid + 1] - s.faceV[tid], fi = (s.faceT[tid + 1] - s.faceT[tid]) * 3;
+				s.tvcount[tid] = fv; s.ticount[tid] = fi;
+				s.tvoff[tid] = fv ? atomicAdd(&d.counters->transVertices, fv) : 0u;
+				s.tioff[tid] = fi ? atomicAdd(&d.counters->transIndices, fi) : 0u;
+			}
+			__syncthreads();
+			// T4: indices + the vertex work list
+			for (unsigned i = tid; i < ntc; i += VXB_THREADS)
+			{
+				const int ci = s.cell[i], face = ci >> 8, row = (ci >> 4) & 15, col = ci & 15;
+				const unsigned tvoff = s.tvoff[face], tioff = s.tioff[face];
+				if ((unsigned long long)tvoff + s.tvcount[face] > d.tvcap || (unsigned long long)tioff + s.ticount[face] > d.ticap) continue;
+				const unsigned code = s.code[ci];
+				signed char v[13];
+				vxb_face_cell_samples(s.face[face], row, col, v);
+				const unsigned cls = vxbGTransitionCellClass[code];
+				const unsigned char* cd = &vxbGTransitionCellData[(cls & 0x7F) * 40];
+				const int nv = cd[0] >> 4, ntri = cd[0] & 0xF;
+				const unsigned newMask = s.newMask[i];
+				const unsigned faceV = s.faceV[face];
+				unsigned vids[12];
+				unsigned nextNew = s.vbase[i] - faceV;
+				for (int k = 0; k < nv; ++k)
+				{
+					if ((newMask >> k) & 1u)
+					{
+						// the vertex itself is computed by vxb_transition_vertex_kernel, one thread per entry
+						d.tvlist[tvoff + nextNew] = make_uint2(slot, ((unsigned)face << 12) | ((unsigned)(ci & 255) << 4) | (unsigned)k);
+						vids[k] = nextNew++;
+					}
+					else
+					{
+						const VxbTransVertexDesc td = vxb_transition_vertex_desc(vxbGTransitionVertexData[code * 12 + k], v, vxbGTransitionCornerData);
+						const int oc = ci - ((td.dir >> 1) & 1) * 16 - (td.dir & 1);
+						const unsigned oi = s.pre[oc >> 5] + __popc(s.nt[oc >> 5] & ((1u << (oc & 31)) - 1u));
+						const unsigned ok = (unsigned)((s.slots[oi] >> (4 * td.slot)) & 0xF);
+						vids[k] = (s.vbase[oi] - faceV) + __popc((unsigned)s.newMask[oi] & ((1u << ok) - 1u));
+					}
+				}
+				const bool flip = (((cls >> 7) & 1u) ^ (unsigned)(face & 1)) != 0;
+				unsigned* out = d.tidx + tioff + ((unsigned)s.tbase[i] - s.faceT[face]) * 3;
+				for (int tr = 0; tr < ntri; ++tr)
+				{
+					const unsigned a = vids[cd[1 + tr * 3]], b = vids[cd[2 + tr * 3]], cc = vids[cd[3 + tr * 3]];
+					out[tr * 3] = a; out[tr * 3 + 1] = flip ? cc : b; out[tr * 3 + 2] = flip ? b : cc;
+				}
 			}
 		}
 		__syncthreads();
-		// T4: emission
-#pragma unroll 1
-		for (int face = 0; face < 6; ++face)
-		{
-			const int ci = face * 256 + tid;
-			const unsigned code = s.code[ci];
-			if (!code) continue;
-			const unsigned tvoff = s.tvoff[face], tioff = s.tioff[face];
-			if ((unsigned long long)tvoff + s.tvcount[face] > d.tvcap || (unsigned long long)tioff + s.ticount[face] > d.ticap) continue;
-			int axis, ua, va;
-			vxb_face_axes(face, axis, ua, va);
-			int local[3];
-			local[axis] = (face >= 3) ? 15 : 0; local[ua] = col; local[va] = row;
-			const int c = local[2] * 256 + local[1] * 16 + local[0];
-			const int base[3] = { (bx * 16 + local[0]) * m, (by * 16 + local[1]) * m, (bz * 16 + local[2]) * m };
-			signed char v[13];
-			vxb_face_cell_samples(s.face[face], row, col, v);
-			const unsigned cls = vxbGTransitionCellClass[code];
-			const unsigned char* cd = &vxbGTransitionCellData[(cls & 0x7F) * 40];
-			const int nv = cd[0] >> 4, ntri = cd[0] & 0xF;
-			const unsigned e = d.cachePages[level][(size_t)coordId * 4096 + c];
-			const unsigned matId = e & 0xFF, matBlend = e >> 8;
-			const unsigned newMask = s.newMask[ci];
-			unsigned vids[12];
-			unsigned nextNew = s.vbase[ci];
-			for (int k = 0; k < nv; ++k)
-			{
-				if ((newMask >> k) & 1u)
-				{
-					// the vertex itself is computed by vxb_transition_vertex_kernel, one thread per entry
-					d.tvlist[tvoff + nextNew] = make_uint2(slot, ((unsigned)face << 12) | ((unsigned)tid << 4) | (unsigned)k);
-					vids[k] = nextNew++;
-				}
-				else
-				{
-					const VxbTransVertexDesc td = vxb_transition_vertex_desc(vxbGTransitionVertexData[code * 12 + k], v, vxbGTransitionCornerData);
-					const int oc = face * 256 + (row - ((td.dir >> 1) & 1)) * 16 + (col - (td.dir & 1));
-					const unsigned ok = (unsigned)((s.slots[oc] >> (4 * td.slot)) & 0xF);
-					vids[k] = s.vbase[oc] + __popc((unsigned)s.newMask[oc] & ((1u << ok) - 1u));
-				}
-			}
-			const bool flip = (((cls >> 7) & 1u) ^ (unsigned)(face & 1)) != 0;
-			unsigned* out = d.tidx + tioff + (unsigned)s.tbase[ci] * 3;
-			for (int tr = 0; tr < ntri; ++tr)
-			{
-				const unsigned a = vids[cd[1 + tr * 3]], b = vids[cd[2 + tr * 3]], cc = vids[cd[3 + tr * 3]];
-				out[tr * 3] = a; out[tr * 3 + 1] = flip ? cc : b; out[tr * 3 + 2] = flip ? b : cc;
-			}
-		}
 		if (tid < 6)
 		{
 			VxbBlockRec* br = &d.blockRecs[slot];
