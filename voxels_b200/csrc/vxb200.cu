@@ -88,7 +88,9 @@ struct vxb_context
 	DevBuf<VxbCounters> counters;
 	DevBuf<VxbMaterialLut> lut;
 	uint64_t capV = 0, capI = 0, capTV = 0, capTI = 0;
-	CUtensorMap tmap;
+	CUtensorMap tmap, tmap1;
+	DevBuf<uint8_t> lattice1;
+	bool haveLattice1 = false;
 	int gridClassify = 0, gridDecideSmall = 0, gridDecideBig = 0, gridTransition = 0;
 	uint64_t capC = 0;
 	bool haveFullRun = false;      // device caches (consistency / material pages) describe the current grid
@@ -139,13 +141,13 @@ int ensureGridStorage(vxb_context* ctx, uint32_t n)
 	return VXB_OK;
 }
 
-int buildTensorMap(vxb_context* ctx)
+int encodeTileMap(vxb_context* ctx, CUtensorMap* map, const void* base, uint32_t n)
 {
-	const cuuint64_t dims[3] = { ctx->n, ctx->n, ctx->n };
-	const cuuint64_t strides[2] = { ctx->n, (cuuint64_t)ctx->n * ctx->n };
+	const cuuint64_t dims[3] = { n, n, n };
+	const cuuint64_t strides[2] = { n, (cuuint64_t)n * n };
 	const cuuint32_t box[3] = { VXB_TILE_PITCH, 17, 17 };
 	const cuuint32_t estr[3] = { 1, 1, 1 };
-	const CUresult r = ctx->encodeTiled(&ctx->tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<int8_t*>(ctx->dDist), dims, strides, box, estr,
+	const CUresult r = ctx->encodeTiled(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(base), dims, strides, box, estr,
 		CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 	if (r != CUDA_SUCCESS)
 	{
@@ -153,6 +155,22 @@ int buildTensorMap(vxb_context* ctx)
 		return fail(ctx, VXB_ERR_CUDA, buf);
 	}
 	return VXB_OK;
+}
+
+int buildTensorMap(vxb_context* ctx)
+{
+	int r = encodeTileMap(ctx, &ctx->tmap, ctx->dDist, ctx->n);
+	if (r != VXB_OK) return r;
+	// even-lattice copy for level 1 (written by vxb_scan_kernel each run); needs at least one 16-sample row
+	ctx->haveLattice1 = ctx->n >= 64;
+	if (ctx->haveLattice1)
+	{
+		const size_t h = ctx->n / 2;
+		VXB_CUDA(ctx, ctx->lattice1.ensure(h * h * h));
+		r = encodeTileMap(ctx, &ctx->tmap1, ctx->lattice1.p, (uint32_t)h);
+	}
+	else ctx->tmap1 = ctx->tmap;
+	return r;
 }
 
 size_t blocksAtLevel(uint32_t n, int level) { const size_t nb = (n / 16) >> level; return nb * nb * nb; }
@@ -252,7 +270,7 @@ void vxb_destroy(vxb_context* ctx)
 	if (!ctx) return;
 	cudaSetDevice(ctx->device);
 	if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-	ctx->volDist.release(); ctx->volMat.release(); ctx->volBlend.release(); ctx->staging.release(); ctx->packOffsets.release(); ctx->updCoords.release();
+	ctx->volDist.release(); ctx->volMat.release(); ctx->volBlend.release(); ctx->staging.release(); ctx->packOffsets.release(); ctx->updCoords.release(); ctx->lattice1.release();
 	ctx->scanFlags.release(); ctx->blockInfo.release(); ctx->consPages.release(); ctx->validFlags.release();
 	ctx->cachePages.release(); ctx->worklist.release(); ctx->emitList.release(); ctx->bigList.release(); ctx->transList.release(); ctx->ntScratch.release(); ctx->cellBlock.release(); ctx->vlist.release(); ctx->cellRecs.release(); ctx->blockRecs.release(); ctx->tvlist.release(); ctx->verts.release(); ctx->tverts.release();
 	ctx->idx.release(); ctx->tidx.release(); ctx->records.release(); ctx->counters.release(); ctx->lut.release();
@@ -551,6 +569,7 @@ static int runPolygonize(vxb_context* ctx, uint32_t maxLevels, uint32_t flags, c
 	dev.transitions = (flags & VXB_FLAG_NO_TRANSITIONS) ? 0 : 1;
 	dev.emitList = ctx->emitList.p; dev.bigList = ctx->bigList.p; dev.transList = ctx->transList.p; dev.ntScratch = ctx->ntScratch.p;
 	dev.blockRecs = ctx->blockRecs.p;
+	dev.lattice1 = ctx->haveLattice1 ? ctx->lattice1.p : nullptr;
 	dev.incremental = region ? 1 : 0;
 	if (region)
 		for (int l = 0; l < levels; ++l)
@@ -588,7 +607,7 @@ static int runPolygonize(vxb_context* ctx, uint32_t maxLevels, uint32_t flags, c
 		{
 			const dim3 grid((unsigned)((nb0 + 7) / 8), (unsigned)nb0, (unsigned)nb0);
 			timer.begin(0);
-			vxb_scan_kernel<<<grid, VXB_THREADS, 0, ctx->stream>>>(ctx->dDist, (int)n, ctx->scanFlags.p);
+			vxb_scan_kernel<<<grid, VXB_THREADS, 0, ctx->stream>>>(ctx->dDist, (int)n, ctx->scanFlags.p, ctx->haveLattice1 ? ctx->lattice1.p : nullptr);
 			timer.end(); ++launches; ++ctx->kindLaunches[0];
 			const unsigned g2 = (unsigned)std::min<size_t>((blocks0 + 255) / 256, (size_t)ctx->smCount * 8);
 			timer.begin(1);
@@ -604,13 +623,13 @@ static int runPolygonize(vxb_context* ctx, uint32_t maxLevels, uint32_t flags, c
 			vxb_select_kernel<<<gs, 256, 0, st>>>(dev, l);
 			timer.end(); ++launches; ++ctx->kindLaunches[1];
 			timer.begin(2);
-			vxb_classify_kernel<<<(unsigned)std::min<size_t>(b, ctx->gridClassify), VXB_THREADS, sizeof(VxbClassifySmem), st>>>(ctx->tmap, dev, l);
+			vxb_classify_kernel<<<(unsigned)std::min<size_t>(b, ctx->gridClassify), VXB_THREADS, sizeof(VxbClassifySmem), st>>>(ctx->tmap, ctx->tmap1, dev, l);
 			timer.end(); ++launches; ++ctx->kindLaunches[2];
 		};
 		auto decideGroup = [&](int group, cudaStream_t st) {
 			timer.begin(3);
-			vxb_decide_kernel<1024, 0><<<ctx->gridDecideSmall, VXB_THREADS, sizeof(VxbDecideSmemSmall), st>>>(ctx->tmap, dev, group);
-			vxb_decide_kernel<4096, 1><<<ctx->gridDecideBig, VXB_THREADS, sizeof(VxbDecideSmemBig), st>>>(ctx->tmap, dev, group);
+			vxb_decide_kernel<1024, 0><<<ctx->gridDecideSmall, VXB_THREADS, sizeof(VxbDecideSmemSmall), st>>>(ctx->tmap, ctx->tmap1, dev, group);
+			vxb_decide_kernel<4096, 1><<<ctx->gridDecideBig, VXB_THREADS, sizeof(VxbDecideSmemBig), st>>>(ctx->tmap, ctx->tmap1, dev, group);
 			timer.end(); launches += 2; ctx->kindLaunches[3] += 2;
 		};
 		auto flatGroup = [&](int part, cudaStream_t st) {

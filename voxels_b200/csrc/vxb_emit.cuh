@@ -70,7 +70,7 @@ __device__ __forceinline__ void vxb_init_cache_page(const VxbDev& d, int level, 
 	for (int i = threadIdx.x; i < 2048; i += VXB_THREADS) page[i] = 0x00FF00FFu; // {EMPTY_MATERIAL, 0} x 2  (:424)
 }
 
-__global__ void __launch_bounds__(VXB_THREADS, 4) vxb_classify_kernel(const __grid_constant__ CUtensorMap tmap, const VxbDev d, const int level)
+__global__ void __launch_bounds__(VXB_THREADS, 4) vxb_classify_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap1, const VxbDev d, const int level)
 {
 	extern __shared__ __align__(128) unsigned char smemRaw[];
 	VxbClassifySmem& s = *reinterpret_cast<VxbClassifySmem*>(smemRaw);
@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(VXB_THREADS, 4) vxb_classify_kernel(const __gr
 	__syncthreads();
 	unsigned item = s.item;
 	int buf = 0;
-	if (item < workCount) { const unsigned c0 = worklist[item]; vxb_tile_issue(s.tiles[0], &s.mbar[0], &tmap, level, c0 % nb, (c0 / nb) % nb, c0 / (nb * nb)); }
+	if (item < workCount) { const unsigned c0 = worklist[item]; vxb_tile_issue(s.tiles[0], &s.mbar[0], &tmap, &tmap1, d, level, c0 % nb, (c0 / nb) % nb, c0 / (nb * nb)); }
 	__syncthreads();
 
 	while (item < workCount)
@@ -97,11 +97,11 @@ __global__ void __launch_bounds__(VXB_THREADS, 4) vxb_classify_kernel(const __gr
 		if (tid == 0) { s.item = atomicAdd(&d.counters->workCursor[level], 1u); s.hasChild = 0; s.pageReady = 0; }
 		__syncthreads();
 		const unsigned nextItem = s.item;
-		if (nextItem < workCount) { const unsigned c1 = worklist[nextItem]; vxb_tile_issue(s.tiles[buf ^ 1], &s.mbar[buf ^ 1], &tmap, level, c1 % nb, (c1 / nb) % nb, c1 / (nb * nb)); }
+		if (nextItem < workCount) { const unsigned c1 = worklist[nextItem]; vxb_tile_issue(s.tiles[buf ^ 1], &s.mbar[buf ^ 1], &tmap, &tmap1, d, level, c1 % nb, (c1 / nb) % nb, c1 / (nb * nb)); }
 		const unsigned coordId = worklist[item];
 		const int bx = coordId % nb, by = (coordId / nb) % nb, bz = coordId / (nb * nb);
 		signed char* const tile = s.tiles[buf];
-		vxb_tile_complete(tile, &s.mbar[buf], phase[buf], d.grid, d.n, level, bx, by, bz);
+		vxb_tile_complete(tile, &s.mbar[buf], phase[buf], d, level, bx, by, bz);
 		__syncthreads();
 
 		vxb_classify_bits(tile, s.rowSign, s.nt32);
@@ -240,7 +240,7 @@ __device__ __forceinline__ unsigned vxb_rank_of(const unsigned int* nt32, const 
 // TIER 1: items come from bigList (CAP_C = 4096 = every possible block).
 // group 0 = level 0 only, group 1 = levels >= 1, group 2 = all levels (single-stream runs)
 template <int CAP_C, int TIER>
-__global__ void __launch_bounds__(VXB_THREADS, (CAP_C <= 1024 ? 4 : 2)) vxb_decide_kernel(const __grid_constant__ CUtensorMap tmap, const VxbDev d, const int group)
+__global__ void __launch_bounds__(VXB_THREADS, (CAP_C <= 1024 ? 4 : 2)) vxb_decide_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap1, const VxbDev d, const int group)
 {
 	const int levelLo = (group == 1) ? 1 : 0, levelHi = (group == 0) ? 0 : d.levels - 1, g2 = group & 1;
 	const int levelCount = levelHi - levelLo + 1;
@@ -293,8 +293,8 @@ __global__ void __launch_bounds__(VXB_THREADS, (CAP_C <= 1024 ? 4 : 2)) vxb_deci
 			__syncthreads();
 			continue;
 		}
-		vxb_tile_issue(s.tile, &s.mbar, &tmap, level, bx, by, bz);
-		vxb_tile_complete(s.tile, &s.mbar, phase, g, d.n, level, bx, by, bz);
+		vxb_tile_issue(s.tile, &s.mbar, &tmap, &tmap1, d, level, bx, by, bz);
+		vxb_tile_complete(s.tile, &s.mbar, phase, d, level, bx, by, bz);
 		// ordered compact list of the non-trivial cells: thread = cell row (z, y), 16 bits each
 		{
 			unsigned bits = reinterpret_cast<const unsigned short*>(s.nt32)[tid];

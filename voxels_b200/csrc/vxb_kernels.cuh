@@ -98,6 +98,7 @@ struct VxbDev
 	unsigned int* vlist;      // vertex (arena index) -> cell record index << 4 | table vertex
 	uint2* tvlist;            // transition vertex (arena index) -> {block slot, face << 12 | cell << 4 | table vertex}
 	VxbBlockRec* blockRecs;
+	const unsigned char* lattice1; // (n/2)^3 even-lattice copy of the distance volume (level-1 samples), or null
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -179,7 +180,8 @@ __device__ __forceinline__ unsigned vxb_zero_bytes(unsigned w) // 0x80 in every 
 	return ~(((w & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | w) & 0x80808080u;
 }
 
-__global__ void __launch_bounds__(VXB_THREADS) vxb_scan_kernel(const signed char* __restrict__ dist, int n, unsigned int* __restrict__ scanFlags)
+__global__ void __launch_bounds__(VXB_THREADS) vxb_scan_kernel(const signed char* __restrict__ dist, int n, unsigned int* __restrict__ scanFlags,
+	unsigned char* __restrict__ lattice1 /* (n/2)^3: the samples at even coordinates = the level-1 lattice, or null */)
 {
 	__shared__ unsigned sFlags[8];
 	__shared__ unsigned sChanges[8];
@@ -207,6 +209,18 @@ __global__ void __launch_bounds__(VXB_THREADS) vxb_scan_kernel(const signed char
 			const int row = i * 32 + rg, y = row & 15, z = row >> 4;
 			const unsigned w[4] = { rows[i].x, rows[i].y, rows[i].z, rows[i].w };
 			const bool even = !((y | z) & 1);
+			// a row of 16 equal bytes (the common case away from the surface) has no value change inside it
+			const unsigned splat = (w[0] & 0xFFu) * 0x01010101u;
+			const bool flat = (w[0] == splat) & (w[1] == splat) & (w[2] == splat) & (w[3] == splat);
+			if (even && lattice1)
+			{
+				// by-product: the even-x bytes of the even rows, so that level 1 can stage its tiles with TMA too
+				const int h = n >> 1;
+				uint2 e;
+				e.x = __byte_perm(w[0], w[1], 0x6420);
+				e.y = __byte_perm(w[2], w[3], 0x6420);
+				*reinterpret_cast<uint2*>(lattice1 + (((size_t)(bz * 8 + (z >> 1))) * h + (by * 8 + (y >> 1))) * h + (size_t)(bx0 + j) * 8) = e;
+			}
 #pragma unroll
 			for (int q = 0; q < 4; ++q)
 			{
@@ -215,13 +229,20 @@ __global__ void __launch_bounds__(VXB_THREADS) vxb_scan_kernel(const signed char
 				zero |= zb;
 				pos |= ~w[q] & 0x80808080u & ~zb;
 				if (even) { negE |= w[q] & 0x00800080u; nonnegE |= ~w[q] & 0x00800080u; }
-				// adjacent-byte changes inside the 16-byte row: compare byte k with byte k+1
-				const unsigned nxt = (q < 3) ? w[q + 1] : (w[3] >> 24);
-				const unsigned shifted = (w[q] >> 8) | (nxt << 24);
-				const unsigned x = w[q] ^ shifted;
-				unsigned diff = ((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x; // bit 7 of each byte set iff byte != 0
-				diff &= (q < 3) ? 0x80808080u : 0x00808080u;               // byte 15 has no right neighbour in the row
-				changes += __popc(diff);
+			}
+			if (!flat)
+			{
+#pragma unroll
+				for (int q = 0; q < 4; ++q)
+				{
+					// adjacent-byte changes inside the 16-byte row: compare byte k with byte k+1
+					const unsigned nxt = (q < 3) ? w[q + 1] : (w[3] >> 24);
+					const unsigned shifted = (w[q] >> 8) | (nxt << 24);
+					const unsigned x = w[q] ^ shifted;
+					unsigned diff = ((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x; // bit 7 of each byte set iff byte != 0
+					diff &= (q < 3) ? 0x80808080u : 0x00808080u;               // byte 15 has no right neighbour in the row
+					changes += __popc(diff);
+				}
 			}
 		}
 	}
@@ -426,26 +447,37 @@ __global__ void vxb_select_kernel(VxbDev d, int level)
 // ------------------------------------------------------------------------------------------------
 // 17^3 sample tile of block (bx,by,bz) at `level` -> smem: level 0 by one 3-D TMA load (issued early by thread 0, so
 // it can be in flight while the CTA still works on the previous block), coarser levels by a clamped strided gather.
-__device__ __forceinline__ void vxb_tile_issue(signed char* tile, unsigned long long* mbar, const CUtensorMap* tmap, int level, int bx, int by, int bz)
+// level 0 reads the distance volume itself, level 1 (away from the far grid edge, where the reference clamps to the odd
+// coordinate n-1) reads the even-lattice copy written by vxb_scan_kernel; both through the same 32x17x17 TMA box
+__device__ __forceinline__ bool vxb_tile_uses_tma(const VxbDev& d, int level, int bx, int by, int bz)
 {
-	if (level == 0 && threadIdx.x == 0)
+	if (level == 0) return true;
+	if (level != 1 || !d.lattice1) return false;
+	const int nb = d.n / 32;
+	return bx != nb - 1 && by != nb - 1 && bz != nb - 1;
+}
+
+__device__ __forceinline__ void vxb_tile_issue(signed char* tile, unsigned long long* mbar, const CUtensorMap* tmap0, const CUtensorMap* tmap1,
+	const VxbDev& d, int level, int bx, int by, int bz)
+{
+	if (threadIdx.x == 0 && vxb_tile_uses_tma(d, level, bx, by, bz))
 	{
 		vxb_fence_proxy_async();
 		vxb_mbar_expect_tx(mbar, VXB_TILE_BYTES);
-		vxb_tma_load_3d(tile, tmap, bx * 16, by * 16, bz * 16, mbar);
+		vxb_tma_load_3d(tile, level == 0 ? tmap0 : tmap1, bx * 16, by * 16, bz * 16, mbar);
 	}
 }
 
 __device__ __forceinline__ void vxb_tile_complete(signed char* tile, unsigned long long* mbar, unsigned& phase,
-	const VxbGrid& g, int n, int level, int bx, int by, int bz)
+	const VxbDev& d, int level, int bx, int by, int bz)
 {
 	const int tid = threadIdx.x;
-	const int m = 1 << level, nb = n / 16 / m;
-	if (level == 0)
+	const int n = d.n, m = 1 << level, nb = n / 16 / m;
+	if (vxb_tile_uses_tma(d, level, bx, by, bz))
 	{
 		vxb_mbar_wait(mbar, phase);
 		phase ^= 1;
-		// far grid edge: the +1 plane is outside the volume (TMA zero-fills); the reference clamps (:1037-1047)
+		// level 0, far grid edge: the +1 plane is outside the volume (TMA zero-fills); the reference clamps (:1037-1047)
 		if (bx == nb - 1) { __syncthreads(); for (int i = tid; i < 17 * 17; i += VXB_THREADS) tile[i * VXB_TILE_PITCH + 16] = tile[i * VXB_TILE_PITCH + 15]; }
 		if (by == nb - 1) { __syncthreads(); for (int i = tid; i < 17 * 17; i += VXB_THREADS) { const int z = i / 17, x = i % 17; tile[(z * 17 + 16) * VXB_TILE_PITCH + x] = tile[(z * 17 + 15) * VXB_TILE_PITCH + x]; } }
 		if (bz == nb - 1) { __syncthreads(); for (int i = tid; i < 17 * 17; i += VXB_THREADS) { const int y = i / 17, x = i % 17; tile[(16 * 17 + y) * VXB_TILE_PITCH + x] = tile[(15 * 17 + y) * VXB_TILE_PITCH + x]; } }
@@ -453,18 +485,16 @@ __device__ __forceinline__ void vxb_tile_complete(signed char* tile, unsigned lo
 	else
 	{
 		const int lim = n - 1;
+		const signed char* dist = d.grid.dist;
 		for (int i = tid; i < 17 * 17 * 17; i += VXB_THREADS)
 		{
 			const int x = i % 17, y = (i / 17) % 17, z = i / 289;
 			const int gx = min((bx * 16 + x) * m, lim), gy = min((by * 16 + y) * m, lim), gz = min((bz * 16 + z) * m, lim);
-			tile[(z * 17 + y) * VXB_TILE_PITCH + x] = g.dist[((size_t)gz * n + gy) * n + gx];
+			tile[(z * 17 + y) * VXB_TILE_PITCH + x] = dist[((size_t)gz * n + gy) * n + gx];
 		}
 	}
 }
 
-// CalculateMaterialForCellCache :753-838 for level >= 1, children read through the page tables.
-// The 8 children of a cell share one block of the child level (cell bases are even in child units), so the block
-// lookup and the validity test happen once, and the common all-empty case exits after 4 loads.
 struct VxbVoteSource // what a vote at `level` reads: the child level's validity flags + pages (+ level-0 materials)
 {
 	const unsigned char* valid;  // consValid (level 1) / cacheValid[level - 1]
