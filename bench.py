@@ -239,7 +239,18 @@ def main():
     alg_by_kind = [d_level0, 0.0, float(d_upper), 0.0, 52.0 * V, 4.0 * I, 52.0 * TV + 4.0 * TI, 0.0]
     dom = max(range(8), key=lambda k: kind_ms[k])
     ach = alg_by_kind[dom] / (kind_ms[dom] * 1e-3) / 1e9 if kind_ms[dom] > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": kinds[dom], "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+    # DRAM traffic of that kernel kind per step from the committed `ncu --set full` capture (only valid for the default workload)
+    traffic, traffic_src = None, None
+    try:
+        kind_keys = ["scan", "select", "classify", "decide", "vertex", "triangle", "transition", "finish"]
+        with open(os.path.join(REPO, "profiles", "r01b_traffic.json")) as f:
+            tj = json.load(f)
+        if n == 1024 and args.levels == 0 and not args.no_transitions:
+            e = tj["per_kind"][kind_keys[dom]]
+            traffic, traffic_src = e["dram_read"] + e["dram_write"], tj["capture"]
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": kinds[dom], "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": peak_src, "algorithmic_bytes_per_step": alg_by_kind[dom], "kernel_ms_per_step": kind_ms[dom],
                 "launches_per_step": kind_launches[dom],
                 "all_kernels": {kinds[k]: {"ms_per_step": kind_ms[k], "launches": kind_launches[k], "algorithmic_bytes": alg_by_kind[k],
