@@ -88,7 +88,8 @@ struct vxb_context
 	DevBuf<VxbCounters> counters;
 	DevBuf<VxbMaterialLut> lut;
 	uint64_t capV = 0, capI = 0, capTV = 0, capTI = 0;
-	CUtensorMap tmap, tmap1;
+	CUtensorMap tmap, tmap1, tmapDist19, tmapMat, tmapBlend;
+	int gridVertexBlock = 0;
 	DevBuf<uint8_t> lattice1;
 	bool haveLattice1 = false;
 	int gridClassify = 0, gridDecideSmall = 0, gridDecideBig = 0, gridTransition = 0;
@@ -141,11 +142,11 @@ int ensureGridStorage(vxb_context* ctx, uint32_t n)
 	return VXB_OK;
 }
 
-int encodeTileMap(vxb_context* ctx, CUtensorMap* map, const void* base, uint32_t n)
+int encodeTileMap(vxb_context* ctx, CUtensorMap* map, const void* base, uint32_t n, uint32_t rows = 17)
 {
 	const cuuint64_t dims[3] = { n, n, n };
 	const cuuint64_t strides[2] = { n, (cuuint64_t)n * n };
-	const cuuint32_t box[3] = { VXB_TILE_PITCH, 17, 17 };
+	const cuuint32_t box[3] = { VXB_TILE_PITCH, rows, rows };
 	const cuuint32_t estr[3] = { 1, 1, 1 };
 	const CUresult r = ctx->encodeTiled(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(base), dims, strides, box, estr,
 		CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -160,6 +161,9 @@ int encodeTileMap(vxb_context* ctx, CUtensorMap* map, const void* base, uint32_t
 int buildTensorMap(vxb_context* ctx)
 {
 	int r = encodeTileMap(ctx, &ctx->tmap, ctx->dDist, ctx->n);
+	if (r == VXB_OK) r = encodeTileMap(ctx, &ctx->tmapDist19, ctx->dDist, ctx->n, 19);
+	if (r == VXB_OK) r = encodeTileMap(ctx, &ctx->tmapMat, ctx->dMat, ctx->n);
+	if (r == VXB_OK) r = encodeTileMap(ctx, &ctx->tmapBlend, ctx->dBlend, ctx->n);
 	if (r != VXB_OK) return r;
 	// even-lattice copy for level 1 (written by vxb_scan_kernel each run); needs at least one 16-sample row
 	ctx->haveLattice1 = ctx->n >= 64;
@@ -243,11 +247,12 @@ int vxb_create(int device, vxb_context** out)
 	ctx->encodeTiled = reinterpret_cast<EncodeTiledFn>(fn);
 
 	struct KernelSetup { const void* fn; size_t smem; int* grid; const char* name; };
-	const KernelSetup setups[4] = {
+	const KernelSetup setups[5] = {
 		{ (const void*)vxb_classify_kernel, sizeof(VxbClassifySmem), &ctx->gridClassify, "vxb_classify_kernel" },
 		{ (const void*)vxb_decide_kernel<1024, 0>, sizeof(VxbDecideSmemSmall), &ctx->gridDecideSmall, "vxb_decide_kernel<1024>" },
 		{ (const void*)vxb_decide_kernel<4096, 1>, sizeof(VxbDecideSmemBig), &ctx->gridDecideBig, "vxb_decide_kernel<4096>" },
 		{ (const void*)vxb_transition_kernel, sizeof(VxbTransSmem), &ctx->gridTransition, "vxb_transition_kernel" },
+		{ (const void*)vxb_vertex_block_kernel, sizeof(VxbVertexBlockSmem), &ctx->gridVertexBlock, "vxb_vertex_block_kernel" },
 	};
 	for (const KernelSetup& k : setups)
 	{
@@ -634,7 +639,8 @@ static int runPolygonize(vxb_context* ctx, uint32_t maxLevels, uint32_t flags, c
 		};
 		auto flatGroup = [&](int part, cudaStream_t st) {
 			timer.begin(4);
-			vxb_vertex_kernel<<<flatGrid, VXB_THREADS, 0, st>>>(dev, part);
+			if (part == 0) vxb_vertex_block_kernel<<<ctx->gridVertexBlock, VXB_THREADS, sizeof(VxbVertexBlockSmem), st>>>(ctx->tmapDist19, ctx->tmapMat, ctx->tmapBlend, dev);
+			else vxb_vertex_kernel<<<flatGrid, VXB_THREADS, 0, st>>>(dev, part);
 			timer.end(); ++launches; ++ctx->kindLaunches[4];
 			timer.begin(5);
 			vxb_triangle_kernel<<<flatGrid, VXB_THREADS, 0, st>>>(dev, part);
@@ -659,9 +665,15 @@ static int runPolygonize(vxb_context* ctx, uint32_t maxLevels, uint32_t flags, c
 		if (!fork)
 		{
 			for (int l = 1; l < computed; ++l) classifyLevel(l, ctx->stream);
-			decideGroup(2, ctx->stream);
-			flatGroup(2, ctx->stream);
-			transitions(ctx->stream);
+			decideGroup(0, ctx->stream); // level 0 first: its blocks own the first directory slots / arena ranges
+			vxb_mark_split_kernel<<<1, 1, 0, ctx->stream>>>(dev); ++launches;
+			flatGroup(0, ctx->stream);
+			if (computed > 1)
+			{
+				decideGroup(1, ctx->stream);
+				flatGroup(1, ctx->stream);
+				transitions(ctx->stream);
+			}
 		}
 		else
 		{

@@ -69,6 +69,23 @@ VXB_FN size_t vxb_index(const VxbGrid& g, int x, int y, int z)
 // GridBlocksCache::GetGridValue(coord) :1140-1151 - coordinates are clamped to the grid.
 VXB_FN int vxb_dist(const VxbGrid& g, int x, int y, int z) { return g.dist[vxb_index(g, x, y, z)]; }
 
+// Level-0 block neighbourhood staged in shared memory (device only): distance samples for coordinates
+// [origin-1, origin+17] per axis (19^3, rows of 32 bytes), material / blend for [origin, origin+16] (17^3).
+// Clamping at the grid edges is baked in when the tile is filled, so reads need no clamp.
+struct VxbTileView
+{
+	const signed char* dist;     // index ((z - oz + 1) * 19 + (y - oy + 1)) * 32 + (x - ox + 1)
+	const unsigned char* mat;    // index ((z - oz) * 17 + (y - oy)) * 32 + (x - ox)
+	const unsigned char* blend;
+	int ox, oy, oz;              // block origin (grid coordinates of its first voxel)
+};
+
+VXB_FN int vxb_dist(const VxbTileView& g, int x, int y, int z) { return g.dist[((z - g.oz + 1) * 19 + (y - g.oy + 1)) * 32 + (x - g.ox + 1)]; }
+VXB_FN unsigned vxb_mat(const VxbTileView& g, int x, int y, int z) { return g.mat[((z - g.oz) * 17 + (y - g.oy)) * 32 + (x - g.ox)]; }
+VXB_FN unsigned vxb_blend(const VxbTileView& g, int x, int y, int z) { return g.blend[((z - g.oz) * 17 + (y - g.oy)) * 32 + (x - g.ox)]; }
+VXB_FN unsigned vxb_mat(const VxbGrid& g, int x, int y, int z) { return g.mat[vxb_index(g, x, y, z)]; }
+VXB_FN unsigned vxb_blend(const VxbGrid& g, int x, int y, int z) { return g.blend[vxb_index(g, x, y, z)]; }
+
 // Case code: bit i = sign bit of corner i (Cell::CalcCaseCode :741-750)
 VXB_FN unsigned vxb_case_code(const signed char v[8])
 {
@@ -105,6 +122,14 @@ VXB_FN_BIG void vxb_normal(const VxbGrid& g, int x, int y, int z, float n[3])
 	vxb_normalize_fix_zero(n[0], n[1], n[2]);
 }
 
+VXB_FN void vxb_normal(const VxbTileView& g, int x, int y, int z, float n[3])
+{
+	n[0] = (float)(vxb_dist(g, x + 1, y, z) - vxb_dist(g, x - 1, y, z)) * 0.5f;
+	n[1] = (float)(vxb_dist(g, x, y, z + 1) - vxb_dist(g, x, y, z - 1)) * 0.5f;
+	n[2] = (float)(vxb_dist(g, x, y + 1, z) - vxb_dist(g, x, y - 1, z)) * 0.5f;
+	vxb_normalize_fix_zero(n[0], n[1], n[2]);
+}
+
 // (b * 256) / (b - a), C integer division (:1591, :1674, :1942, :2025), for int8 samples with b != a.
 // Device: one IEEE float division.  Exact: |b*256| <= 2^15 and |b-a| <= 255, so a non-integer quotient is at
 // least 1/255 away from the next integer while the float result is within 2^-10 of it - truncation cannot flip.
@@ -118,7 +143,8 @@ VXB_FN int vxb_fixed_t(int a, int b)
 }
 
 // FindBestVertexInLODChain :1484-1509 followed by the t recomputation :1671-1678 / :2022-2029.
-VXB_FN_BIG int vxb_lod_descent(const VxbGrid& g, int steps, int p0[3], int p1[3])
+template <class G>
+VXB_FN_BIG int vxb_lod_descent(const G& g, int steps, int p0[3], int p1[3])
 {
 	for (int s = 0; s < steps; ++s)
 	{
@@ -233,22 +259,23 @@ struct VxbRawVertex
 };
 
 // Vertex at a cell corner (GenerateVertexFromPoint :1450-1467).
-VXB_FN_BIG void vxb_corner_vertex(const VxbGrid& g, int level, const int base[3], const int local[3], int corner,
+template <class G>
+VXB_FN_BIG void vxb_corner_vertex(const G& g, int level, const int base[3], const int local[3], int corner,
 	unsigned cellMatId, unsigned cellMatBlend, VxbRawVertex& out)
 {
 	const int m = 1 << level;
 	const int px = base[0] + ((corner & 1) ? m : 0), py = base[1] + ((corner & 2) ? m : 0), pz = base[2] + ((corner & 4) ? m : 0);
 	vxb_normal(g, px, py, pz, out.n);
-	const size_t gi = vxb_index(g, px, py, pz);
-	const unsigned myId = g.mat[gi];
+	const unsigned myId = vxb_mat(g, px, py, pz);
 	out.matId = cellMatId;
-	out.blend = (myId != cellMatId) ? cellMatBlend : g.blend[gi];
+	out.blend = (myId != cellMatId) ? cellMatBlend : vxb_blend(g, px, py, pz);
 	out.p[0] = (float)px * 256.f; out.p[1] = (float)py * 256.f; out.p[2] = (float)pz * 256.f;
 	out.flags = vxb_corner_flags(level, local[0], local[1], local[2], corner);
 }
 
 // Vertex in the interior of an edge (:1659-1704).
-VXB_FN_BIG void vxb_edge_vertex(const VxbGrid& g, int level, const int base[3], const int local[3], const VxbVertexDesc& d,
+template <class G>
+VXB_FN_BIG void vxb_edge_vertex(const G& g, int level, const int base[3], const int local[3], const VxbVertexDesc& d,
 	unsigned cellMatId, unsigned cellMatBlend, VxbRawVertex& out)
 {
 	const int m = 1 << level;
@@ -262,8 +289,7 @@ VXB_FN_BIG void vxb_edge_vertex(const VxbGrid& g, int level, const int base[3], 
 	float n0[3], n1[3];
 	vxb_normal(g, p0[0], p0[1], p0[2], n0);
 	vxb_normal(g, p1[0], p1[1], p1[2], n1);
-	const size_t i0 = vxb_index(g, p0[0], p0[1], p0[2]), i1 = vxb_index(g, p1[0], p1[1], p1[2]);
-	const unsigned m0 = g.mat[i0], m1 = g.mat[i1];
+	const unsigned m0 = vxb_mat(g, p0[0], p0[1], p0[2]), m1 = vxb_mat(g, p1[0], p1[1], p1[2]);
 
 	out.p[0] = ft * (float)p0[0] + fu * (float)p1[0];
 	out.p[1] = ft * (float)p0[1] + fu * (float)p1[1];
@@ -272,7 +298,7 @@ VXB_FN_BIG void vxb_edge_vertex(const VxbGrid& g, int level, const int base[3], 
 
 	out.matId = cellMatId;
 	if (m0 == m1 && m0 == cellMatId)
-		out.blend = vxb_blend_u8((ft * (float)(int)g.blend[i0] + fu * (float)(int)g.blend[i1]) / 256.f);
+		out.blend = vxb_blend_u8((ft * (float)(int)vxb_blend(g, p0[0], p0[1], p0[2]) + fu * (float)(int)vxb_blend(g, p1[0], p1[1], p1[2])) / 256.f);
 	else
 		out.blend = cellMatBlend;
 

@@ -443,6 +443,7 @@ __global__ void vxb_mark_split_kernel(const VxbDev d)
 {
 	d.counters->splitVertices = d.counters->vertices;
 	d.counters->splitCells = d.counters->cells;
+	d.counters->splitRecords = d.counters->records;
 }
 
 __global__ void __launch_bounds__(VXB_THREADS) vxb_vertex_kernel(const VxbDev d, const int part)
@@ -497,6 +498,138 @@ __global__ void __launch_bounds__(VXB_THREADS) vxb_vertex_kernel(const VxbDev d,
 	if (threadIdx.x < 8 && sUsed[threadIdx.x]) atomicOr(&d.counters->usedMaterials[threadIdx.x], sUsed[threadIdx.x]);
 }
 
+// Level-0 vertices, one emitted block per CTA iteration: the block's distance neighbourhood (19^3) and its material /
+// blend samples (17^3) are staged by three TMA loads, so the 16 one-byte taps of a vertex come from shared memory
+// instead of 16 separate 32-byte DRAM sectors.  Grid-edge clamping (:1198, :1242-1244) is baked into the tiles.
+#define VXB_DTILE_BYTES (19 * 19 * VXB_TILE_PITCH)
+struct __align__(128) VxbVertexBlockSmem
+{
+	signed char dist[VXB_DTILE_BYTES + 96];
+	unsigned char mat[VXB_TILE_BYTES + 96];
+	unsigned char blend[VXB_TILE_BYTES + 96];
+	unsigned long long mbar;
+	unsigned int item;
+	unsigned int used[8];
+};
+
+__global__ void __launch_bounds__(VXB_THREADS, 4) vxb_vertex_block_kernel(const __grid_constant__ CUtensorMap tmapDist19, const __grid_constant__ CUtensorMap tmapMat,
+	const __grid_constant__ CUtensorMap tmapBlend, const VxbDev d)
+{
+	extern __shared__ __align__(128) unsigned char smemRaw[];
+	VxbVertexBlockSmem& s = *reinterpret_cast<VxbVertexBlockSmem*>(smemRaw);
+	const int tid = threadIdx.x;
+	if (tid == 0) vxb_mbar_init(&s.mbar, 1);
+	if (tid < 8) s.used[tid] = 0;
+	__syncthreads();
+	unsigned phase = 0;
+	const bool live = !vxb_overflowed(d);
+	const unsigned count = live ? d.counters->splitRecords : 0u; // level-0 blocks own the first directory slots
+	const int nb = d.n / 16;
+	for (;;)
+	{
+		if (tid == 0) s.item = atomicAdd(&d.counters->vertexBlockCursor, 1u);
+		__syncthreads();
+		const unsigned slot = s.item;
+		if (slot >= count) break;
+		const VxbBlockRec* br = &d.blockRecs[slot];
+		const unsigned coordId = br->packed & 0x0FFFFFFFu;
+		const unsigned voff = br->voff, nverts = br->nverts;
+		const int bx = coordId % nb, by = (coordId / nb) % nb, bz = coordId / (nb * nb);
+		if (tid == 0)
+		{
+			vxb_fence_proxy_async();
+			vxb_mbar_expect_tx(&s.mbar, VXB_DTILE_BYTES + 2 * VXB_TILE_BYTES);
+			vxb_tma_load_3d(s.dist, &tmapDist19, bx * 16 - 1, by * 16 - 1, bz * 16 - 1, &s.mbar);
+			vxb_tma_load_3d(s.mat, &tmapMat, bx * 16, by * 16, bz * 16, &s.mbar);
+			vxb_tma_load_3d(s.blend, &tmapBlend, bx * 16, by * 16, bz * 16, &s.mbar);
+		}
+		vxb_mbar_wait(&s.mbar, phase);
+		phase ^= 1;
+		// grid edges: TMA zero-fills outside the volume, the reference clamps the coordinate
+		if (bx == 0 || bx == nb - 1)
+		{
+			__syncthreads();
+			for (int i = tid; i < 19 * 19; i += VXB_THREADS)
+			{
+				signed char* r = s.dist + i * VXB_TILE_PITCH;
+				if (bx == 0) r[0] = r[1];
+				if (bx == nb - 1) { r[17] = r[16]; r[18] = r[16]; }
+			}
+			if (bx == nb - 1) for (int i = tid; i < 17 * 17; i += VXB_THREADS) { s.mat[i * VXB_TILE_PITCH + 16] = s.mat[i * VXB_TILE_PITCH + 15]; s.blend[i * VXB_TILE_PITCH + 16] = s.blend[i * VXB_TILE_PITCH + 15]; }
+		}
+		if (by == 0 || by == nb - 1)
+		{
+			__syncthreads();
+			for (int i = tid; i < 19 * 19; i += VXB_THREADS)
+			{
+				const int z = i / 19, x = i % 19;
+				signed char* p = s.dist + z * 19 * VXB_TILE_PITCH + x;
+				if (by == 0) p[0] = p[VXB_TILE_PITCH];
+				if (by == nb - 1) { p[17 * VXB_TILE_PITCH] = p[16 * VXB_TILE_PITCH]; p[18 * VXB_TILE_PITCH] = p[16 * VXB_TILE_PITCH]; }
+			}
+			if (by == nb - 1) for (int i = tid; i < 17 * 17; i += VXB_THREADS)
+			{
+				const int z = i / 17, x = i % 17;
+				s.mat[(z * 17 + 16) * VXB_TILE_PITCH + x] = s.mat[(z * 17 + 15) * VXB_TILE_PITCH + x];
+				s.blend[(z * 17 + 16) * VXB_TILE_PITCH + x] = s.blend[(z * 17 + 15) * VXB_TILE_PITCH + x];
+			}
+		}
+		if (bz == 0 || bz == nb - 1)
+		{
+			__syncthreads();
+			for (int i = tid; i < 19 * 19; i += VXB_THREADS)
+			{
+				const int y = i / 19, x = i % 19;
+				signed char* p = s.dist + y * VXB_TILE_PITCH + x;
+				if (bz == 0) p[0] = p[19 * VXB_TILE_PITCH];
+				if (bz == nb - 1) { p[17 * 19 * VXB_TILE_PITCH] = p[16 * 19 * VXB_TILE_PITCH]; p[18 * 19 * VXB_TILE_PITCH] = p[16 * 19 * VXB_TILE_PITCH]; }
+			}
+			if (bz == nb - 1) for (int i = tid; i < 17 * 17; i += VXB_THREADS)
+			{
+				const int y = i / 17, x = i % 17;
+				s.mat[(16 * 17 + y) * VXB_TILE_PITCH + x] = s.mat[(15 * 17 + y) * VXB_TILE_PITCH + x];
+				s.blend[(16 * 17 + y) * VXB_TILE_PITCH + x] = s.blend[(15 * 17 + y) * VXB_TILE_PITCH + x];
+			}
+		}
+		__syncthreads();
+		VxbTileView g;
+		g.dist = s.dist; g.mat = s.mat; g.blend = s.blend; g.ox = bx * 16; g.oy = by * 16; g.oz = bz * 16;
+		for (unsigned j = tid; j < nverts; j += VXB_THREADS)
+		{
+			const unsigned e = d.vlist[voff + j];
+			const unsigned ci = e >> 4; const int k = e & 15;
+			const uint4 crv = *reinterpret_cast<const uint4*>(&d.cellRecs[ci]);
+			const int c = crv.x & 0xFFF;
+			const unsigned code = (crv.x >> 12) & 0xFF, zm = (crv.x >> 20) & 0xFF;
+			const int local[3] = { c & 15, (c >> 4) & 15, c >> 8 };
+			const int base[3] = { bx * 16 + local[0], by * 16 + local[1], bz * 16 + local[2] };
+			const unsigned matId = crv.y & 0xFF, matBlend = (crv.y >> 8) & 0xFF;
+			VxbVertexDesc vd = vxb_regular_vertex_desc_lite(vxbGRegularVertexData[code * 12 + k], zm);
+			VxbRawVertex rv;
+			if (vd.endpoint)
+			{
+				const bool quirk = (crv.z >> (12 + k)) & 1u;
+				vxb_corner_vertex(g, 0, base, local, quirk ? vd.v0 : ((vd.t == 0) ? vd.v1 : vd.v0), matId, matBlend, rv);
+			}
+			else
+			{
+				const int a = vxb_dist(g, base[0] + (vd.v0 & 1), base[1] + ((vd.v0 >> 1) & 1), base[2] + (vd.v0 >> 2));
+				const int b = vxb_dist(g, base[0] + (vd.v1 & 1), base[1] + ((vd.v1 >> 1) & 1), base[2] + (vd.v1 >> 2));
+				vd.t = vxb_fixed_t(a, b); // :1591
+				vxb_edge_vertex(g, 0, base, local, vd, matId, matBlend, rv);
+			}
+			vxb_regular_secondary(0, rv);
+			VxbVertex ov;
+			vxb_finish_vertex(rv, *d.lut, ov);
+			vxb_store_vertex(d.verts + voff + j, ov);
+			atomicOr(&s.used[matId >> 5], 1u << (matId & 31));
+		}
+		__syncthreads();
+	}
+	__syncthreads();
+	if (tid < 8 && s.used[tid]) atomicOr(&d.counters->usedMaterials[tid], s.used[tid]);
+}
+
 __global__ void __launch_bounds__(VXB_THREADS) vxb_triangle_kernel(const VxbDev d, const int part)
 {
 	if (vxb_overflowed(d)) return;
@@ -532,15 +665,24 @@ __global__ void __launch_bounds__(VXB_THREADS) vxb_triangle_kernel(const VxbDev 
 		(void)mask; (void)myMat;
 		unsigned* out = d.idx + ioff + (crv.w >> 16) * 3;
 		unsigned removed = 0;
+		// A level-0 cell without a zero sample has every table vertex strictly inside a distinct cell edge (t in 1..255):
+		// no two coincide and no three are collinear, and with |coordinates differences| <= 256 the reference's float cross
+		// product is exact, so its degenerate test (:1309-1311) cannot fire - the positions need not be read back.
+		const bool cannotDegenerate = (br->packed >> 28) == 0u && zm == 0u;
 		for (unsigned tr = 0; tr < (geo & 0xF); ++tr, out += 3)
 		{
 			const unsigned a = vids[cd[1 + tr * 3]], b = vids[cd[2 + tr * 3]], cc = vids[cd[3 + tr * 3]];
-			const float* fa = d.verts[voff + a].pos; const float* fb = d.verts[voff + b].pos; const float* fc = d.verts[voff + cc].pos;
-			// back to grid axes, x256 (exact: positions are multiples of 1/256)
-			const float pa[3] = { fa[0] * 256.f, fa[2] * 256.f, fa[1] * 256.f };
-			const float pb[3] = { fb[0] * 256.f, fb[2] * 256.f, fb[1] * 256.f };
-			const float pc[3] = { fc[0] * 256.f, fc[2] * 256.f, fc[1] * 256.f };
-			if (vxb_triangle_kept(pa, pb, pc)) { out[0] = a; out[1] = b; out[2] = cc; }
+			bool kept = true;
+			if (!cannotDegenerate)
+			{
+				const float* fa = d.verts[voff + a].pos; const float* fb = d.verts[voff + b].pos; const float* fc = d.verts[voff + cc].pos;
+				// back to grid axes, x256 (exact: positions are multiples of 1/256)
+				const float pa[3] = { fa[0] * 256.f, fa[2] * 256.f, fa[1] * 256.f };
+				const float pb[3] = { fb[0] * 256.f, fb[2] * 256.f, fb[1] * 256.f };
+				const float pc[3] = { fc[0] * 256.f, fc[2] * 256.f, fc[1] * 256.f };
+				kept = vxb_triangle_kept(pa, pb, pc);
+			}
+			if (kept) { out[0] = a; out[1] = b; out[2] = cc; }
 			else { out[0] = 0xFFFFFFFFu; out[1] = 0xFFFFFFFFu; out[2] = 0xFFFFFFFFu; ++removed; }
 		}
 		if (removed) atomicAdd(&d.blockRecs[slot].removed, removed);

@@ -42,7 +42,8 @@ struct VxbCounters
 	unsigned int emitCursor[2];             // per group: 0 = level 0, 1 = levels >= 1 (the groups run on two streams)
 	unsigned int bigCount[2], bigCursor[2]; // blocks with > 1024 non-trivial cells (second tier of vxb_decide_kernel)
 	unsigned int cells;                     // cursor of the cell-record arena
-	unsigned int splitVertices, splitCells; // arena cursors after group 0: the flat kernels of the two groups split there
+	unsigned int splitVertices, splitCells, splitRecords; // cursors after group 0 (level 0): later kernels split their ranges there
+	unsigned int vertexBlockCursor;
 	unsigned int transBlocks, transCursor;  // emitted mid-level blocks (vxb_transition_kernel work list)
 	unsigned int finishCursor;
 };
