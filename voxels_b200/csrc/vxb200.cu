@@ -142,11 +142,11 @@ int ensureGridStorage(vxb_context* ctx, uint32_t n)
 	return VXB_OK;
 }
 
-int encodeTileMap(vxb_context* ctx, CUtensorMap* map, const void* base, uint32_t n, uint32_t rows = 17)
+int encodeTileMap(vxb_context* ctx, CUtensorMap* map, const void* base, uint32_t n, uint32_t rows = 17, uint32_t pitch = VXB_TILE_PITCH)
 {
 	const cuuint64_t dims[3] = { n, n, n };
 	const cuuint64_t strides[2] = { n, (cuuint64_t)n * n };
-	const cuuint32_t box[3] = { VXB_TILE_PITCH, rows, rows };
+	const cuuint32_t box[3] = { pitch, rows, rows };
 	const cuuint32_t estr[3] = { 1, 1, 1 };
 	const CUresult r = ctx->encodeTiled(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(base), dims, strides, box, estr,
 		CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -161,7 +161,7 @@ int encodeTileMap(vxb_context* ctx, CUtensorMap* map, const void* base, uint32_t
 int buildTensorMap(vxb_context* ctx)
 {
 	int r = encodeTileMap(ctx, &ctx->tmap, ctx->dDist, ctx->n);
-	if (r == VXB_OK) r = encodeTileMap(ctx, &ctx->tmapDist19, ctx->dDist, ctx->n, 19);
+	if (r == VXB_OK) r = encodeTileMap(ctx, &ctx->tmapDist19, ctx->dDist, ctx->n, 19, VXB_DTILE_PITCH);
 	if (r == VXB_OK) r = encodeTileMap(ctx, &ctx->tmapMat, ctx->dMat, ctx->n);
 	if (r == VXB_OK) r = encodeTileMap(ctx, &ctx->tmapBlend, ctx->dBlend, ctx->n);
 	if (r != VXB_OK) return r;

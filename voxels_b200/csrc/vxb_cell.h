@@ -74,13 +74,20 @@ VXB_FN int vxb_dist(const VxbGrid& g, int x, int y, int z) { return g.dist[vxb_i
 // Clamping at the grid edges is baked in when the tile is filled, so reads need no clamp.
 struct VxbTileView
 {
-	const signed char* dist;     // index ((z - oz + 1) * 19 + (y - oy + 1)) * 32 + (x - ox + 1)
+	const signed char* dist;     // 19 x 19 rows of 48 bytes, first sample = (sx, sy, sz)
 	const unsigned char* mat;    // index ((z - oz) * 17 + (y - oy)) * 32 + (x - ox)
 	const unsigned char* blend;
 	int ox, oy, oz;              // block origin (grid coordinates of its first voxel)
+	int sx, sy, sz;              // first coordinate held by the distance tile: (origin.x - 16, origin.y - 1, origin.z - 1)
+	                             // - TMA needs a 16-byte aligned innermost start -, or 0 on the low grid edge
 };
 
-VXB_FN int vxb_dist(const VxbTileView& g, int x, int y, int z) { return g.dist[((z - g.oz + 1) * 19 + (y - g.oy + 1)) * 32 + (x - g.ox + 1)]; }
+// low edge: coordinate -1 clamps to 0 = the tile's first sample; the far edge is replicated when the tile is filled
+VXB_FN int vxb_dist(const VxbTileView& g, int x, int y, int z)
+{
+	const int xi = (x < g.sx ? g.sx : x) - g.sx, yi = (y < g.sy ? g.sy : y) - g.sy, zi = (z < g.sz ? g.sz : z) - g.sz;
+	return g.dist[(zi * 19 + yi) * 48 + xi];
+}
 VXB_FN unsigned vxb_mat(const VxbTileView& g, int x, int y, int z) { return g.mat[((z - g.oz) * 17 + (y - g.oy)) * 32 + (x - g.ox)]; }
 VXB_FN unsigned vxb_blend(const VxbTileView& g, int x, int y, int z) { return g.blend[((z - g.oz) * 17 + (y - g.oy)) * 32 + (x - g.ox)]; }
 VXB_FN unsigned vxb_mat(const VxbGrid& g, int x, int y, int z) { return g.mat[vxb_index(g, x, y, z)]; }

@@ -501,10 +501,11 @@ __global__ void __launch_bounds__(VXB_THREADS) vxb_vertex_kernel(const VxbDev d,
 // Level-0 vertices, one emitted block per CTA iteration: the block's distance neighbourhood (19^3) and its material /
 // blend samples (17^3) are staged by three TMA loads, so the 16 one-byte taps of a vertex come from shared memory
 // instead of 16 separate 32-byte DRAM sectors.  Grid-edge clamping (:1198, :1242-1244) is baked into the tiles.
-#define VXB_DTILE_BYTES (19 * 19 * VXB_TILE_PITCH)
+#define VXB_DTILE_PITCH 48
+#define VXB_DTILE_BYTES (19 * 19 * VXB_DTILE_PITCH)
 struct __align__(128) VxbVertexBlockSmem
 {
-	signed char dist[VXB_DTILE_BYTES + 96];
+	signed char dist[VXB_DTILE_BYTES + 80];
 	unsigned char mat[VXB_TILE_BYTES + 96];
 	unsigned char blend[VXB_TILE_BYTES + 96];
 	unsigned long long mbar;
@@ -535,56 +536,56 @@ __global__ void __launch_bounds__(VXB_THREADS, 4) vxb_vertex_block_kernel(const 
 		const unsigned coordId = br->packed & 0x0FFFFFFFu;
 		const unsigned voff = br->voff, nverts = br->nverts;
 		const int bx = coordId % nb, by = (coordId / nb) % nb, bz = coordId / (nb * nb);
+		// the distance tile starts one sample before the block, except on the low grid edge (all TMA coordinates stay >= 0)
+		const int sx = bx ? bx * 16 - 16 : 0, sy = by ? by * 16 - 1 : 0, sz = bz ? bz * 16 - 1 : 0; // x start 16-byte aligned
 		if (tid == 0)
 		{
 			vxb_fence_proxy_async();
 			vxb_mbar_expect_tx(&s.mbar, VXB_DTILE_BYTES + 2 * VXB_TILE_BYTES);
-			vxb_tma_load_3d(s.dist, &tmapDist19, bx * 16 - 1, by * 16 - 1, bz * 16 - 1, &s.mbar);
+			vxb_tma_load_3d(s.dist, &tmapDist19, sx, sy, sz, &s.mbar);
 			vxb_tma_load_3d(s.mat, &tmapMat, bx * 16, by * 16, bz * 16, &s.mbar);
 			vxb_tma_load_3d(s.blend, &tmapBlend, bx * 16, by * 16, bz * 16, &s.mbar);
 		}
 		vxb_mbar_wait(&s.mbar, phase);
 		phase ^= 1;
-		// grid edges: TMA zero-fills outside the volume, the reference clamps the coordinate
-		if (bx == 0 || bx == nb - 1)
+		// far grid edge: TMA zero-fills outside the volume, the reference clamps the coordinate to n-1
+		const int lastX = d.n - 1 - sx, lastY = d.n - 1 - sy, lastZ = d.n - 1 - sz; // tile index of coordinate n-1
+		if (bx == nb - 1)
 		{
 			__syncthreads();
 			for (int i = tid; i < 19 * 19; i += VXB_THREADS)
 			{
-				signed char* r = s.dist + i * VXB_TILE_PITCH;
-				if (bx == 0) r[0] = r[1];
-				if (bx == nb - 1) { r[17] = r[16]; r[18] = r[16]; }
+				signed char* r = s.dist + i * VXB_DTILE_PITCH;
+				r[lastX + 1] = r[lastX]; r[lastX + 2] = r[lastX];
 			}
-			if (bx == nb - 1) for (int i = tid; i < 17 * 17; i += VXB_THREADS) { s.mat[i * VXB_TILE_PITCH + 16] = s.mat[i * VXB_TILE_PITCH + 15]; s.blend[i * VXB_TILE_PITCH + 16] = s.blend[i * VXB_TILE_PITCH + 15]; }
+			for (int i = tid; i < 17 * 17; i += VXB_THREADS) { s.mat[i * VXB_TILE_PITCH + 16] = s.mat[i * VXB_TILE_PITCH + 15]; s.blend[i * VXB_TILE_PITCH + 16] = s.blend[i * VXB_TILE_PITCH + 15]; }
 		}
-		if (by == 0 || by == nb - 1)
+		if (by == nb - 1)
 		{
 			__syncthreads();
-			for (int i = tid; i < 19 * 19; i += VXB_THREADS)
+			for (int i = tid; i < 19 * VXB_DTILE_PITCH; i += VXB_THREADS)
 			{
-				const int z = i / 19, x = i % 19;
-				signed char* p = s.dist + z * 19 * VXB_TILE_PITCH + x;
-				if (by == 0) p[0] = p[VXB_TILE_PITCH];
-				if (by == nb - 1) { p[17 * VXB_TILE_PITCH] = p[16 * VXB_TILE_PITCH]; p[18 * VXB_TILE_PITCH] = p[16 * VXB_TILE_PITCH]; }
+				const int z = i / VXB_DTILE_PITCH, x = i % VXB_DTILE_PITCH;
+				signed char* p = s.dist + z * 19 * VXB_DTILE_PITCH + x;
+				for (int q = lastY + 1; q < 19; ++q) p[q * VXB_DTILE_PITCH] = p[lastY * VXB_DTILE_PITCH];
 			}
-			if (by == nb - 1) for (int i = tid; i < 17 * 17; i += VXB_THREADS)
+			for (int i = tid; i < 17 * 17; i += VXB_THREADS)
 			{
 				const int z = i / 17, x = i % 17;
 				s.mat[(z * 17 + 16) * VXB_TILE_PITCH + x] = s.mat[(z * 17 + 15) * VXB_TILE_PITCH + x];
 				s.blend[(z * 17 + 16) * VXB_TILE_PITCH + x] = s.blend[(z * 17 + 15) * VXB_TILE_PITCH + x];
 			}
 		}
-		if (bz == 0 || bz == nb - 1)
+		if (bz == nb - 1)
 		{
 			__syncthreads();
-			for (int i = tid; i < 19 * 19; i += VXB_THREADS)
+			for (int i = tid; i < 19 * VXB_DTILE_PITCH; i += VXB_THREADS)
 			{
-				const int y = i / 19, x = i % 19;
-				signed char* p = s.dist + y * VXB_TILE_PITCH + x;
-				if (bz == 0) p[0] = p[19 * VXB_TILE_PITCH];
-				if (bz == nb - 1) { p[17 * 19 * VXB_TILE_PITCH] = p[16 * 19 * VXB_TILE_PITCH]; p[18 * 19 * VXB_TILE_PITCH] = p[16 * 19 * VXB_TILE_PITCH]; }
+				const int y = i / VXB_DTILE_PITCH, x = i % VXB_DTILE_PITCH;
+				signed char* p = s.dist + y * VXB_DTILE_PITCH + x;
+				for (int q = lastZ + 1; q < 19; ++q) p[q * 19 * VXB_DTILE_PITCH] = p[lastZ * 19 * VXB_DTILE_PITCH];
 			}
-			if (bz == nb - 1) for (int i = tid; i < 17 * 17; i += VXB_THREADS)
+			for (int i = tid; i < 17 * 17; i += VXB_THREADS)
 			{
 				const int y = i / 17, x = i % 17;
 				s.mat[(16 * 17 + y) * VXB_TILE_PITCH + x] = s.mat[(15 * 17 + y) * VXB_TILE_PITCH + x];
@@ -593,7 +594,7 @@ __global__ void __launch_bounds__(VXB_THREADS, 4) vxb_vertex_block_kernel(const 
 		}
 		__syncthreads();
 		VxbTileView g;
-		g.dist = s.dist; g.mat = s.mat; g.blend = s.blend; g.ox = bx * 16; g.oy = by * 16; g.oz = bz * 16;
+		g.dist = s.dist; g.mat = s.mat; g.blend = s.blend; g.ox = bx * 16; g.oy = by * 16; g.oz = bz * 16; g.sx = sx; g.sy = sy; g.sz = sz;
 		for (unsigned j = tid; j < nverts; j += VXB_THREADS)
 		{
 			const unsigned e = d.vlist[voff + j];
