@@ -27,6 +27,7 @@
 #include <mutex>
 #include <new>
 #include <vector>
+#include <chrono>
 
 #include "../../include/vxb200.h"
 
@@ -40,19 +41,25 @@ void logMessage(LogSeverity severity, const char* text)
 	if (Logger::Get()) Logger::Get()->Log(severity, text);
 }
 
-struct HostBuffer // pinned, grows, never shrinks
+// Host memory that grows and never shrinks.  Large buffers are page-locked (full-speed DMA for the GB-sized uploads
+// and downloads of a full run); small ones - the arenas of incremental runs, a few hundred KB per edit - are plain
+// malloc, because pinning costs milliseconds per allocation.
+struct HostBuffer
 {
 	void* p = nullptr;
 	size_t bytes = 0;
+	bool pinned = false;
 	bool ensure(size_t want)
 	{
 		if (want <= bytes) return true;
-		if (p) vxb_host_free(p);
-		p = vxb_host_alloc(want);
+		release();
+		pinned = want >= (size_t(8) << 20);
+		p = pinned ? vxb_host_alloc(want) : malloc(want ? want : 1);
 		bytes = p ? want : 0;
 		return p != nullptr;
 	}
-	~HostBuffer() { if (p) vxb_host_free(p); }
+	void release() { if (p) { if (pinned) vxb_host_free(p); else free(p); } p = nullptr; bytes = 0; }
+	~HostBuffer() { release(); }
 };
 
 struct BlockView : public BlockPolygons
@@ -305,9 +312,36 @@ PolygonSurface* TransVoxelImpl::Execute(const Grid& grid, const MaterialMap* mat
 	return surface;
 }
 
+namespace
+{
+// VXB200_TRACE=1: cumulative host-side stage times of the incremental path, printed at exit
+struct StageTrace
+{
+	bool on = getenv("VXB200_TRACE") != nullptr;
+	double seconds[5] = { 0, 0, 0, 0, 0 };
+	unsigned long runs = 0;
+	std::chrono::steady_clock::time_point last;
+	void start() { if (on) last = std::chrono::steady_clock::now(); }
+	void mark(int stage)
+	{
+		if (!on) return;
+		const auto now = std::chrono::steady_clock::now();
+		seconds[stage] += std::chrono::duration<double>(now - last).count();
+		last = now;
+	}
+	~StageTrace()
+	{
+		if (on && runs)
+			fprintf(stderr, "[vxb200] incremental runs %lu: read blocks %.3f ms, update %.3f ms, polygonize %.3f ms, splice %.3f ms, download %.3f ms (per run)\n",
+				runs, 1e3 * seconds[0] / runs, 1e3 * seconds[1] / runs, 1e3 * seconds[2] / runs, 1e3 * seconds[3] / runs, 1e3 * seconds[4] / runs);
+	}
+} g_Trace;
+}
+
 PolygonSurface* TransVoxelImpl::ExecuteIncremental(const Grid& grid, SurfaceImpl* surface, ModificationImpl* modification)
 {
 	char buffer[VOXELS_LOG_SIZE];
+	g_Trace.start();
 	vxb_context* ctx = surface->Context;
 	const unsigned n = grid.GetWidth(), nb = n / 16;
 	auto fail = [&](const char* what) -> PolygonSurface* {
@@ -339,9 +373,11 @@ PolygonSurface* TransVoxelImpl::ExecuteIncremental(const Grid& grid, SurfaceImpl
 			grid.GetBlockMaterialData(c, static_cast<unsigned char*>(StageMat.p) + i * 4096, static_cast<unsigned char*>(StageBlend.p) + i * 4096);
 		}
 	}
+	g_Trace.mark(0);
 	if (vxb_grid_update_blocks(ctx, uint32_t(count), coords.data(), static_cast<const int8_t*>(StageDist.p), static_cast<const uint8_t*>(StageMat.p),
 		static_cast<const uint8_t*>(StageBlend.p)) != VXB_OK) return fail("grid update failed");
 
+	g_Trace.mark(1);
 	// ---- re-polygonize the dirty boxes of all levels ----
 	const float minCorner[3] = { lo.x, lo.y, lo.z }, maxCorner[3] = { hi.x, hi.y, hi.z };
 	if (vxb_polygonize_region(ctx, minCorner, maxCorner, 0) != VXB_OK) return fail("incremental polygonization failed");
@@ -349,6 +385,7 @@ PolygonSurface* TransVoxelImpl::ExecuteIncremental(const Grid& grid, SurfaceImpl
 	vxb_region_info region;
 	if (vxb_result_info_get(ctx, &info) != VXB_OK || vxb_region_info_get(ctx, &region) != VXB_OK) return fail("no result");
 
+	g_Trace.mark(2);
 	// ---- splice: drop the old blocks of each level's dirty box (:443-450), append the new ones (:1293) ----
 	for (unsigned l = 0; l < region.levels && l < surface->Levels.size(); ++l)
 	{
@@ -360,8 +397,11 @@ PolygonSurface* TransVoxelImpl::ExecuteIncremental(const Grid& grid, SurfaceImpl
 		}), blocks.end());
 		for (uint32_t i = 0; i < region.block_count[l]; ++i) modification->ModifiedBlocks.push_back(region.id_start[l] + i); // :463
 	}
+	g_Trace.mark(3);
 	if (!appendResult(ctx, surface, n, info)) return fail("result download failed");
 	logUnmapped(ctx);
+	g_Trace.mark(4);
+	++g_Trace.runs;
 	return surface;
 }
 
