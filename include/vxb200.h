@@ -150,6 +150,55 @@ typedef struct vxb_region_info
  * result (vxb_result_info / vxb_result_download) holds ONLY the re-created blocks. */
 int vxb_polygonize_region(vxb_context* ctx, const float min_corner[3], const float max_corner[3], uint32_t flags);
 int vxb_region_info_get(vxb_context* ctx, vxb_region_info* out);
+
+/* ---- Sharded runs: ONE grid polygonized by `world` ranks, one GPU each (BASELINE configs[3]) ----
+ * Rank r owns the z-slab of n/world planes [r*n/world, (r+1)*n/world) and produces every block that nests in it
+ * (levels with 16*2^l <= n/world); rank 0 also produces the few blocks of the coarser levels, which span slabs.
+ * Blocks are a pure function of the level-0 volumes plus the material pages of their child level
+ * (TransVoxelImpl.cpp:763-837), so the only data-path exchange is ONE all-gather of the material pages of the last
+ * nested level, between the two phases; block ids are the reference's full-run ids (:395-401), so the directories of
+ * the ranks concatenate and sort into exactly the single-GPU directory.
+ *
+ * Every rank's context must see the whole cube through its grid pointers (vxb_cube_create below maps the peers'
+ * slabs over NVLink; a single-process caller can simply share one dense upload through vxb_grid_set_device).  A rank
+ * reads outside its slab only the first planes of the next slab (far cell corners, normals) and - rank 0 - the sparse
+ * samples of the coarse levels.
+ *
+ *   vxb_polygonize_sharded(ctx, r, w, 0, flags)   enqueue: scan of the slab (+1 block layer either side), classification
+ *                                                 of the nested levels.  Does not synchronise.
+ *   vxb_shard_exchange_info(ctx, r, w, &x)        the two device buffers to all-gather IN PLACE on vxb_stream(ctx):
+ *                                                 rank r contributed bytes [r*bytes/w, (r+1)*bytes/w) of each
+ *                                                 (ncclAllGather; torch.distributed.all_gather_into_tensor)
+ *   vxb_polygonize_sharded(ctx, r, w, 1, flags)   the coarse levels (rank 0), vertices, triangles, transition cells,
+ *                                                 directory.  Result = this rank's blocks (vxb_result_info_get / download).
+ * VXB_ERR_CAPACITY from phase 1 means the arenas were grown: every rank repeats both phases. */
+typedef struct vxb_shard_exchange
+{
+	uint32_t split_level;   /* levels [0, split_level) nest in a slab; == levels when world == 1 (nothing to exchange) */
+	uint32_t level;         /* the level whose pages are exchanged (split_level - 1) */
+	void* pages;            /* device: {material id, blend} of every cell of every block of `level`, block-major (z,y,x) */
+	uint64_t pages_bytes;
+	void* valid;            /* device: one byte per block of `level` */
+	uint64_t valid_bytes;
+} vxb_shard_exchange;
+int vxb_polygonize_sharded(vxb_context* ctx, uint32_t rank, uint32_t world, uint32_t phase, uint32_t flags);
+int vxb_shard_exchange_info(vxb_context* ctx, uint32_t rank, uint32_t world, vxb_shard_exchange* out);
+
+/* The cube of a sharded run in device memory: each of the three volumes is ONE contiguous n^3 virtual range
+ * (cuMemAddressReserve); this rank's z-slab is backed by its own HBM (cuMemCreate + cuMemMap), the other slabs are the
+ * peers' allocations imported through POSIX file descriptors and mapped over NVLink / NVSwitch.  Kernels and TMA
+ * tensor maps address the cube exactly like a single-GPU grid.  n^2 * n/world bytes must be a multiple of the
+ * allocation granularity (2 MiB).
+ *   vxb_cube_create   reserve + back + map the local slab; the context's grid becomes the cube
+ *   vxb_cube_export   channel 0/1/2 = distance / material / blend: a file descriptor for the local slab (caller closes it
+ *                     after sending it to the peers, e.g. over a Unix socket with SCM_RIGHTS)
+ *   vxb_cube_import   map peer `peer`'s slab of `channel` from a received descriptor (the descriptor can be closed after)
+ *   vxb_cube_slab     device pointers and byte size of the local slab (fill it with cudaMemcpy / a generator kernel)
+ * All slabs must be mapped and filled (a barrier across the ranks) before vxb_polygonize_sharded. */
+int vxb_cube_create(vxb_context* ctx, uint32_t n, uint32_t rank, uint32_t world);
+int vxb_cube_export(vxb_context* ctx, uint32_t channel, int* fd);
+int vxb_cube_import(vxb_context* ctx, uint32_t peer, uint32_t channel, int fd);
+int vxb_cube_slab(vxb_context* ctx, int8_t** dist, uint8_t** mat, uint8_t** blend, uint64_t* bytes_per_channel);
 /* Copies the directory (sorted by level, then coord_id = the reference's block order) and the
  * arenas to HOST memory sized from vxb_result_info spans.  Vertices are 48-byte
  * Voxels::PolygonVertex (include/Polygonizer.h:14-48).  Any pointer may be NULL to skip it. */

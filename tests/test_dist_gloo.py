@@ -56,3 +56,62 @@ def test_two_ranks_gloo(tmp_path):
     assert fields[0]["tile_digest"] != fields[1]["tile_digest"]          # independent tiles (different origins)
     assert fields[0]["total"] == fields[1]["total"] == str(int(fields[0]["verts"]) + int(fields[1]["verts"]))
     assert abs(float(fields[0]["mvox"]) - 2 * 32 ** 3 / 15e-3 / 1e6) < 1e-3  # whole-job throughput counts both tiles
+
+
+SHARD_WORKER = r'''
+import os, sys, tempfile
+sys.path.insert(0, os.environ["VXB_REPO"])
+import numpy as np, torch
+from voxels_b200 import capi
+from voxels_b200.dist import Ranks, exchange_fds, gather_directories, slab_planes, split_level
+r = Ranks("gloo", torch.device("cpu"))
+assert r.world == 2
+# 1. descriptors travel between the ranks (what carries the cuMemExportToShareableHandle handles of the slabs)
+mine = []
+for c in range(3):
+    f = tempfile.TemporaryFile()
+    f.write(b"rank%d-channel%d" % (r.rank, c)); f.flush()
+    mine.append(f)
+got = exchange_fds(r.rank, r.world, [f.fileno() for f in mine], os.environ["MASTER_PORT"])
+peer = 1 - r.rank
+texts = []
+for c, fd in enumerate(got[peer]):
+    with os.fdopen(fd, "rb") as f:
+        f.seek(0); texts.append(f.read().decode())
+assert texts == ["rank%d-channel%d" % (peer, c) for c in range(3)], texts
+# 2. directory all-gather: counts, then padded payload; reference order = (level, coord_id)
+n = 256
+z0, z1 = slab_planes(n, r.rank, r.world)
+recs = np.zeros(3 + r.rank, capi.RECORD_DTYPE)
+recs["level"] = [0, 0, 1] + [2] * r.rank
+recs["coord_id"] = [10 + 100 * r.rank, 5 + 100 * r.rank, 7 + r.rank] + [0] * r.rank
+recs["id"] = recs["coord_id"] + 1000 * recs["level"]
+allrec, owner = gather_directories(r, recs)
+assert len(allrec) == 7 and list(allrec["level"]) == sorted(allrec["level"])
+keys = list(zip(allrec["level"].tolist(), allrec["coord_id"].tolist()))
+assert keys == sorted(keys)
+assert owner.tolist() == [0, 0, 1, 1, 0, 1, 1], owner.tolist()
+print("RESULT rank=%d slab=%d-%d split=%d blocks=%d" % (r.rank, z0, z1, split_level(n, r.world), len(allrec)))
+r.close()
+'''
+
+
+def test_sharded_plumbing_two_ranks_gloo(tmp_path):
+    script = tmp_path / "shard_worker.py"
+    script.write_text(SHARD_WORKER)
+    env = dict(os.environ, VXB_REPO=REPO, OMP_NUM_THREADS="1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", str(_free_port()), str(script)]
+    out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    lines = sorted(l for l in out.stdout.splitlines() if l.startswith("RESULT"))
+    assert lines == ["RESULT rank=0 slab=0-128 split=4 blocks=7", "RESULT rank=1 slab=128-256 split=4 blocks=7"], out.stdout + out.stderr
+
+
+def test_split_level_matches_the_reference_block_sizes():
+    sys.path.insert(0, REPO)
+    from voxels_b200.dist import split_level
+    assert split_level(2048, 8) == 5      # 16,32,64,128,256-voxel blocks nest in 256-plane slabs (SURVEY.md 8e)
+    assert split_level(1024, 8) == 4
+    assert split_level(1024, 1) == 7      # one rank: every level nests, nothing to exchange
+    assert split_level(64, 2) == 2

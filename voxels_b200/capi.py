@@ -34,6 +34,23 @@ class RegionInfo(C.Structure):
                 ("id_start", C.c_uint32 * 12), ("block_count", C.c_uint32 * 12)]
 
 
+class ShardExchange(C.Structure):
+    _fields_ = [("split_level", C.c_uint32), ("level", C.c_uint32), ("pages", C.c_void_p), ("pages_bytes", C.c_uint64),
+                ("valid", C.c_void_p), ("valid_bytes", C.c_uint64)]
+
+
+ERR_CAPACITY = -4
+
+
+class DevicePointer:
+    """A raw device range as a CUDA-array-interface object: torch.as_tensor(DevicePointer(p, nbytes), device=...) is a
+    zero-copy uint8 view (how dist.py hands the exchange buffers of a sharded run to torch.distributed)."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 3,
+                                         "strides": None}
+
+
 class VxbError(RuntimeError):
     pass
 
@@ -74,6 +91,12 @@ def load_library():
         "vxb_grid_update_blocks": (C.c_int, [vp, u32, vp, vp, vp, vp]),
         "vxb_polygonize_region": (C.c_int, [vp, vp, vp, u32]),
         "vxb_region_info_get": (C.c_int, [vp, C.POINTER(RegionInfo)]),
+        "vxb_polygonize_sharded": (C.c_int, [vp, u32, u32, u32, u32]),
+        "vxb_shard_exchange_info": (C.c_int, [vp, u32, u32, C.POINTER(ShardExchange)]),
+        "vxb_cube_create": (C.c_int, [vp, u32, u32, u32]),
+        "vxb_cube_export": (C.c_int, [vp, u32, C.POINTER(C.c_int)]),
+        "vxb_cube_import": (C.c_int, [vp, u32, u32, C.c_int]),
+        "vxb_cube_slab": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(u64)]),
         "vxb_result_download": (C.c_int, [vp, vp, vp, vp, vp, vp]),
         "vxb_set_capacity": (C.c_int, [vp, u64, u64, u64, u64]),
         "vxb_kernel_ms": (C.c_int, [vp, C.c_int, C.POINTER(C.c_float), C.POINTER(u32)]),
@@ -91,7 +114,8 @@ def load_library():
 EXPORTED_SYMBOLS = ["vxb_create", "vxb_destroy", "vxb_last_error", "vxb_stream", "vxb_grid_upload_dense",
                     "vxb_grid_upload_blocks", "vxb_grid_upload_packed", "vxb_pack_dense_bound", "vxb_pack_dense", "vxb_grid_set_device", "vxb_grid_device_pointers", "vxb_set_materials",
                     "vxb_polygonize", "vxb_polygonize_region", "vxb_region_info_get", "vxb_grid_update_blocks", "vxb_result_info_get", "vxb_result_download", "vxb_set_capacity", "vxb_kernel_ms",
-                    "vxb_result_unmapped_materials", "vxb_host_alloc", "vxb_host_free"]
+                    "vxb_result_unmapped_materials", "vxb_host_alloc", "vxb_host_free", "vxb_polygonize_sharded", "vxb_shard_exchange_info",
+                    "vxb_cube_create", "vxb_cube_export", "vxb_cube_import", "vxb_cube_slab"]
 
 
 def _ptr(a):
@@ -150,6 +174,27 @@ class Result:
         tverts = gather(self.tverts, recs["trans_vertex_offset"].ravel(), recs["trans_vertex_count"].ravel())
         tidx = gather(self.tidx, recs["trans_index_offset"].ravel(), recs["trans_index_count"].ravel())
         return LevelView(rows, verts, idx, tverts, tidx)
+
+
+def merge_results(results):
+    """The per-rank results of a sharded run as ONE result: arenas concatenated in rank order, directory offsets
+    rebased and sorted by (level, coord_id) - the reference's block order - statistics summed.  Block ids need no
+    fixing: they are a function of (level, coordinate) in a full run (TransVoxelImpl.cpp:395-401)."""
+    recs, bases = [], [0, 0, 0, 0]
+    for r in results:
+        rr = r.records.copy()
+        rr["vertex_offset"] += np.uint32(bases[0]); rr["index_offset"] += np.uint32(bases[1])
+        rr["trans_vertex_offset"] += np.uint32(bases[2]); rr["trans_index_offset"] += np.uint32(bases[3])
+        recs.append(rr)
+        bases = [bases[0] + len(r.verts), bases[1] + len(r.idx), bases[2] + len(r.tverts), bases[3] + len(r.tidx)]
+    records = np.concatenate(recs)
+    records = records[np.lexsort((records["coord_id"], records["level"]))]
+    merged = Result.__new__(Result)
+    merged.n, merged.info, merged.records = results[0].n, None, records
+    merged.verts = np.concatenate([r.verts for r in results]); merged.idx = np.concatenate([r.idx for r in results])
+    merged.tverts = np.concatenate([r.tverts for r in results]); merged.tidx = np.concatenate([r.tidx for r in results])
+    merged.stats = np.sum([r.stats.astype(np.uint64) for r in results], axis=0).astype(np.uint32)
+    return merged
 
 
 class Context:
@@ -235,6 +280,46 @@ class Context:
         lo = np.ascontiguousarray(min_corner, np.float32); hi = np.ascontiguousarray(max_corner, np.float32)
         self._check(self.L.vxb_polygonize_region(self.h, _ptr(lo), _ptr(hi), flags), "vxb_polygonize_region")
         return self.info()
+
+    # ---- sharded runs (include/vxb200.h: vxb_polygonize_sharded, vxb_cube_*) ----
+    def polygonize_sharded(self, rank, world, phase, flags=0):
+        """Returns 0, or ERR_CAPACITY from phase 1 (arenas grown: every rank repeats both phases)."""
+        rc = self.L.vxb_polygonize_sharded(self.h, rank, world, phase, flags)
+        if rc == ERR_CAPACITY and phase == 1:
+            return rc
+        self._check(rc, "vxb_polygonize_sharded")
+        return 0
+
+    def shard_exchange_info(self, rank, world):
+        x = ShardExchange()
+        self._check(self.L.vxb_shard_exchange_info(self.h, rank, world, C.byref(x)), "vxb_shard_exchange_info")
+        return x
+
+    def cube_create(self, n, rank, world):
+        self._check(self.L.vxb_cube_create(self.h, n, rank, world), "vxb_cube_create")
+        self.n = n
+
+    def cube_export(self, channel):
+        fd = C.c_int(-1)
+        self._check(self.L.vxb_cube_export(self.h, channel, C.byref(fd)), "vxb_cube_export")
+        return fd.value
+
+    def cube_import(self, peer, channel, fd):
+        self._check(self.L.vxb_cube_import(self.h, peer, channel, fd), "vxb_cube_import")
+
+    def cube_slab(self):
+        """(dist, mat, blend) device addresses of the local slab and its size in bytes per channel."""
+        d, m, b, size = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_uint64(0)
+        self._check(self.L.vxb_cube_slab(self.h, C.byref(d), C.byref(m), C.byref(b), C.byref(size)), "vxb_cube_slab")
+        return d.value, m.value, b.value, size.value
+
+    def device_pointers(self):
+        d, m, b = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self._check(self.L.vxb_grid_device_pointers(self.h, C.byref(d), C.byref(m), C.byref(b)), "vxb_grid_device_pointers")
+        return d.value, m.value, b.value
+
+    def stream(self):
+        return self.L.vxb_stream(self.h)
 
     def region_info(self):
         ri = RegionInfo()

@@ -99,6 +99,18 @@ struct vxb_context
 	vxb_region_info region;
 	DevBuf<unsigned int> updCoords;
 	bool directoryFetched = false;
+	uint32_t shardLaunches = 0;
+	// the cube of a sharded run (vxb_cube_*): one virtual range per volume, this rank's slab local, peers' slabs imported
+	struct Cube
+	{
+		bool active = false;
+		uint32_t rank = 0, world = 1;
+		size_t cubeBytes = 0, slabBytes = 0;
+		CUdeviceptr va[3] = { 0, 0, 0 };
+		CUmemGenericAllocationHandle local[3] = { 0, 0, 0 };
+		std::vector<CUmemGenericAllocationHandle> imported;
+		std::vector<CUdeviceptr> mapped; // every mapped slab (size slabBytes)
+	} cube;
 	VxbCounters lastCounters;
 	size_t validBytes = 0;
 
@@ -180,11 +192,17 @@ int buildTensorMap(vxb_context* ctx)
 size_t blocksAtLevel(uint32_t n, int level) { const size_t nb = (n / 16) >> level; return nb * nb * nb; }
 
 // dirty box of an incremental run, per level (GenerateBlockListForLevel :429-465)
+// (a sharded run uses the same mechanism for "the blocks of my z-slab": ranged, not incremental)
 struct Region
 {
 	int rangeMin[VXB_MAX_LEVELS][3], rangeMax[VXB_MAX_LEVELS][3]; // grid (x, y, z) block coordinates, [min, max)
 	unsigned idStart[VXB_MAX_LEVELS];
 	size_t count[VXB_MAX_LEVELS];
+	bool incremental = true;      // keep the caches of the last full run, continue its block ids
+	int phase = 0;                // 0 = whole pipeline; 1 = scan + classification of levels [0, splitLevel); 2 = the rest
+	int splitLevel = 0;           // first level whose blocks do not nest in a slab
+	int scanLayer0 = 0, scanLayer1 = 0; // level-0 block layers to scan [l0, l1)
+	uint64_t voxels = 0;          // voxels this run covers (capacity defaults)
 };
 
 struct KernelTimer
@@ -210,6 +228,177 @@ struct KernelTimer
 	}
 };
 }
+
+// ---- the cube of a sharded run: virtual memory management through driver entry points (no libcuda link) ----
+namespace
+{
+struct VmmApi
+{
+	decltype(&cuMemAddressReserve) addressReserve = nullptr;
+	decltype(&cuMemAddressFree) addressFree = nullptr;
+	decltype(&cuMemCreate) create = nullptr;
+	decltype(&cuMemRelease) release = nullptr;
+	decltype(&cuMemMap) map = nullptr;
+	decltype(&cuMemUnmap) unmap = nullptr;
+	decltype(&cuMemSetAccess) setAccess = nullptr;
+	decltype(&cuMemExportToShareableHandle) exportHandle = nullptr;
+	decltype(&cuMemImportFromShareableHandle) importHandle = nullptr;
+	decltype(&cuMemGetAllocationGranularity) granularity = nullptr;
+	bool ok = false;
+};
+
+const VmmApi& vmmApi()
+{
+	static VmmApi api;
+	static bool tried = false;
+	if (tried) return api;
+	tried = true;
+	struct Entry { const char* name; void** slot; };
+	const Entry entries[] = {
+		{ "cuMemAddressReserve", (void**)&api.addressReserve }, { "cuMemAddressFree", (void**)&api.addressFree },
+		{ "cuMemCreate", (void**)&api.create }, { "cuMemRelease", (void**)&api.release },
+		{ "cuMemMap", (void**)&api.map }, { "cuMemUnmap", (void**)&api.unmap }, { "cuMemSetAccess", (void**)&api.setAccess },
+		{ "cuMemExportToShareableHandle", (void**)&api.exportHandle }, { "cuMemImportFromShareableHandle", (void**)&api.importHandle },
+		{ "cuMemGetAllocationGranularity", (void**)&api.granularity },
+	};
+	bool all = true;
+	for (const Entry& e : entries)
+	{
+		cudaDriverEntryPointQueryResult q;
+		if (cudaGetDriverEntryPoint(e.name, e.slot, cudaEnableDefault, &q) != cudaSuccess || !*e.slot) all = false;
+	}
+	api.ok = all;
+	return api;
+}
+
+int failCu(vxb_context* ctx, const char* what, CUresult r)
+{
+	char buf[160]; snprintf(buf, sizeof(buf), "%s failed: CUresult %d", what, (int)r);
+	return fail(ctx, VXB_ERR_CUDA, buf);
+}
+#define VXB_CU(ctx, call) do { const CUresult r_ = (call); if (r_ != CUDA_SUCCESS) return failCu(ctx, #call, r_); } while (0)
+
+void releaseCube(vxb_context* ctx)
+{
+	vxb_context::Cube& c = ctx->cube;
+	if (!c.active) return;
+	const VmmApi& api = vmmApi();
+	for (CUdeviceptr p : c.mapped) api.unmap(p, c.slabBytes);
+	for (CUmemGenericAllocationHandle h : c.imported) api.release(h);
+	for (int k = 0; k < 3; ++k)
+	{
+		if (c.local[k]) api.release(c.local[k]);
+		if (c.va[k]) api.addressFree(c.va[k], c.cubeBytes);
+	}
+	c = vxb_context::Cube();
+}
+
+CUmemAllocationProp slabProp(int device)
+{
+	CUmemAllocationProp prop;
+	memset(&prop, 0, sizeof(prop));
+	prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+	prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+	prop.location.id = device;
+	prop.requestedHandleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+	return prop;
+}
+
+int mapSlab(vxb_context* ctx, int channel, uint32_t slab, CUmemGenericAllocationHandle handle)
+{
+	const VmmApi& api = vmmApi();
+	vxb_context::Cube& c = ctx->cube;
+	const CUdeviceptr at = c.va[channel] + (CUdeviceptr)slab * c.slabBytes;
+	VXB_CU(ctx, api.map(at, c.slabBytes, 0, handle, 0));
+	c.mapped.push_back(at);
+	CUmemAccessDesc access;
+	memset(&access, 0, sizeof(access));
+	access.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+	access.location.id = ctx->device;
+	access.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+	VXB_CU(ctx, api.setAccess(at, c.slabBytes, &access, 1));
+	return VXB_OK;
+}
+}
+
+extern "C"
+{
+
+int vxb_cube_create(vxb_context* ctx, uint32_t n, uint32_t rank, uint32_t world)
+{
+	if (!ctx) return VXB_ERR_ARGUMENT;
+	if (!validSize(n) || world == 0 || (world & (world - 1)) != 0 || rank >= world || n / world < 32)
+		return fail(ctx, VXB_ERR_ARGUMENT, "vxb_cube_create: n a power of two in [16, 4096], world a power of two with slabs of at least 32 planes, rank < world");
+	const VmmApi& api = vmmApi();
+	if (!api.ok) return fail(ctx, VXB_ERR_CUDA, "vxb_cube_create: the driver does not export the virtual memory management entry points");
+	cudaSetDevice(ctx->device);
+	cudaFree(nullptr); // make sure the primary context exists and is current for the driver calls
+	releaseCube(ctx);
+	vxb_context::Cube& c = ctx->cube;
+	c.rank = rank; c.world = world;
+	c.cubeBytes = (size_t)n * n * n;
+	c.slabBytes = c.cubeBytes / world;
+	const CUmemAllocationProp prop = slabProp(ctx->device);
+	size_t gran = 0;
+	VXB_CU(ctx, api.granularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_MINIMUM));
+	if (!gran || c.slabBytes % gran != 0)
+	{
+		char buf[160]; snprintf(buf, sizeof(buf), "vxb_cube_create: a slab (%zu bytes) must be a multiple of the allocation granularity (%zu bytes)", c.slabBytes, gran);
+		return fail(ctx, VXB_ERR_ARGUMENT, buf);
+	}
+	c.active = true;
+	for (int k = 0; k < 3; ++k)
+	{
+		VXB_CU(ctx, api.addressReserve(&c.va[k], c.cubeBytes, 0, 0, 0));
+		VXB_CU(ctx, api.create(&c.local[k], c.slabBytes, &prop, 0));
+		const int r = mapSlab(ctx, k, rank, c.local[k]);
+		if (r != VXB_OK) return r;
+	}
+	ctx->dDist = reinterpret_cast<const int8_t*>(c.va[0]);
+	ctx->dMat = reinterpret_cast<const uint8_t*>(c.va[1]);
+	ctx->dBlend = reinterpret_cast<const uint8_t*>(c.va[2]);
+	ctx->n = n; ctx->levels = levelsFor(n);
+	ctx->ownsGrid = false; ctx->haveGrid = true; ctx->haveResult = false; ctx->haveFullRun = false;
+	return buildTensorMap(ctx);
+}
+
+int vxb_cube_export(vxb_context* ctx, uint32_t channel, int* fd)
+{
+	if (!ctx || !fd) return VXB_ERR_ARGUMENT;
+	if (!ctx->cube.active || channel > 2) return fail(ctx, VXB_ERR_STATE, "vxb_cube_export: no cube, or channel > 2");
+	cudaSetDevice(ctx->device);
+	int out = -1;
+	VXB_CU(ctx, vmmApi().exportHandle(&out, ctx->cube.local[channel], CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0));
+	*fd = out;
+	return VXB_OK;
+}
+
+int vxb_cube_import(vxb_context* ctx, uint32_t peer, uint32_t channel, int fd)
+{
+	if (!ctx) return VXB_ERR_ARGUMENT;
+	vxb_context::Cube& c = ctx->cube;
+	if (!c.active || channel > 2 || peer >= c.world || peer == c.rank || fd < 0) return fail(ctx, VXB_ERR_ARGUMENT, "vxb_cube_import: no cube, or bad peer / channel / descriptor");
+	cudaSetDevice(ctx->device);
+	CUmemGenericAllocationHandle h = 0;
+	VXB_CU(ctx, vmmApi().importHandle(&h, (void*)(uintptr_t)fd, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR));
+	c.imported.push_back(h);
+	return mapSlab(ctx, (int)channel, peer, h);
+}
+
+int vxb_cube_slab(vxb_context* ctx, int8_t** dist, uint8_t** mat, uint8_t** blend, uint64_t* bytes)
+{
+	if (!ctx) return VXB_ERR_ARGUMENT;
+	const vxb_context::Cube& c = ctx->cube;
+	if (!c.active) return fail(ctx, VXB_ERR_STATE, "vxb_cube_slab: no cube");
+	const size_t off = (size_t)c.rank * c.slabBytes;
+	if (dist) *dist = reinterpret_cast<int8_t*>(c.va[0] + off);
+	if (mat) *mat = reinterpret_cast<uint8_t*>(c.va[1] + off);
+	if (blend) *blend = reinterpret_cast<uint8_t*>(c.va[2] + off);
+	if (bytes) *bytes = c.slabBytes;
+	return VXB_OK;
+}
+
+} // extern "C"
 
 extern "C"
 {
@@ -275,6 +464,8 @@ void vxb_destroy(vxb_context* ctx)
 	if (!ctx) return;
 	cudaSetDevice(ctx->device);
 	if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+	if (ctx->stream2) cudaStreamSynchronize(ctx->stream2);
+	releaseCube(ctx);
 	ctx->volDist.release(); ctx->volMat.release(); ctx->volBlend.release(); ctx->staging.release(); ctx->packOffsets.release(); ctx->updCoords.release(); ctx->lattice1.release();
 	ctx->scanFlags.release(); ctx->blockInfo.release(); ctx->consPages.release(); ctx->validFlags.release();
 	ctx->cachePages.release(); ctx->worklist.release(); ctx->emitList.release(); ctx->bigList.release(); ctx->transList.release(); ctx->ntScratch.release(); ctx->cellBlock.release(); ctx->vlist.release(); ctx->cellRecs.release(); ctx->blockRecs.release(); ctx->tvlist.release(); ctx->verts.release(); ctx->tverts.release();
@@ -518,6 +709,8 @@ int vxb_set_capacity(vxb_context* ctx, uint64_t v, uint64_t i, uint64_t tv, uint
 
 static int runPolygonize(vxb_context* ctx, uint32_t maxLevels, uint32_t flags, const Region* region)
 {
+	const bool incremental = region && region->incremental;
+	const int phase = region ? region->phase : 0;
 	if (!ctx) return VXB_ERR_ARGUMENT;
 	if (!ctx->haveGrid) return fail(ctx, VXB_ERR_STATE, "vxb_polygonize: no grid uploaded");
 	cudaSetDevice(ctx->device);
@@ -526,7 +719,7 @@ static int runPolygonize(vxb_context* ctx, uint32_t maxLevels, uint32_t flags, c
 	const int levels = ctx->levels;
 	const int computed = (maxLevels == 0 || (int)maxLevels > levels) ? levels : (int)maxLevels;
 	const size_t nb0 = n / 16, blocks0 = nb0 * nb0 * nb0;
-	const bool kernelTimes = (flags & VXB_FLAG_KERNEL_TIMES) != 0;
+	const bool kernelTimes = (flags & VXB_FLAG_KERNEL_TIMES) != 0 && phase == 0;
 
 	// ---- device state ----
 	VXB_CUDA(ctx, ctx->scanFlags.ensure(blocks0));
@@ -555,7 +748,7 @@ static int runPolygonize(vxb_context* ctx, uint32_t maxLevels, uint32_t flags, c
 	VXB_CUDA(ctx, ctx->blockRecs.ensure(totalBlocks));
 	VXB_CUDA(ctx, ctx->ntScratch.ensure(totalBlocks * 256));
 
-	const uint64_t vol = (uint64_t)n * n * n;
+	const uint64_t vol = (region && region->voxels) ? region->voxels : (uint64_t)n * n * n;
 	if (!ctx->capV) ctx->capV = std::max<uint64_t>(1u << 20, vol / 24);
 	if (!ctx->capI) ctx->capI = ctx->capV * 6;
 	if (!ctx->capTV) ctx->capTV = std::max<uint64_t>(1u << 18, ctx->capV / 8);
@@ -575,7 +768,8 @@ static int runPolygonize(vxb_context* ctx, uint32_t maxLevels, uint32_t flags, c
 	dev.emitList = ctx->emitList.p; dev.bigList = ctx->bigList.p; dev.transList = ctx->transList.p; dev.ntScratch = ctx->ntScratch.p;
 	dev.blockRecs = ctx->blockRecs.p;
 	dev.lattice1 = ctx->haveLattice1 ? ctx->lattice1.p : nullptr;
-	dev.incremental = region ? 1 : 0;
+	dev.incremental = incremental ? 1 : 0;
+	dev.ranged = region ? 1 : 0;
 	if (region)
 		for (int l = 0; l < levels; ++l)
 		{
@@ -605,18 +799,20 @@ static int runPolygonize(vxb_context* ctx, uint32_t maxLevels, uint32_t flags, c
 		KernelTimer timer{ ctx, kernelTimes };
 		uint32_t launches = 0;
 		for (int k = 0; k < 8; ++k) ctx->kindLaunches[k] = 0;
-		VXB_CUDA(ctx, cudaEventRecord(ctx->evBegin, ctx->stream));
-		VXB_CUDA(ctx, cudaMemsetAsync(ctx->counters.p, 0, sizeof(VxbCounters), ctx->stream));
-		if (!region) VXB_CUDA(ctx, cudaMemsetAsync(ctx->validFlags.p, 0, validBytes, ctx->stream)); // incremental runs keep the caches (:362-364)
-
+		if (phase != 2)
 		{
-			const dim3 grid((unsigned)((nb0 + 7) / 8), (unsigned)nb0, (unsigned)nb0);
+			VXB_CUDA(ctx, cudaEventRecord(ctx->evBegin, ctx->stream));
+			VXB_CUDA(ctx, cudaMemsetAsync(ctx->counters.p, 0, sizeof(VxbCounters), ctx->stream));
+			if (!incremental) VXB_CUDA(ctx, cudaMemsetAsync(ctx->validFlags.p, 0, validBytes, ctx->stream)); // incremental runs keep the caches (:362-364)
+			const size_t layer0 = (region && !incremental) ? (size_t)region->scanLayer0 : 0, layer1 = (region && !incremental) ? (size_t)region->scanLayer1 : nb0;
+			const dim3 grid((unsigned)((nb0 + 7) / 8), (unsigned)nb0, (unsigned)(layer1 - layer0));
 			timer.begin(0);
-			vxb_scan_kernel<<<grid, VXB_THREADS, 0, ctx->stream>>>(ctx->dDist, (int)n, ctx->scanFlags.p, ctx->haveLattice1 ? ctx->lattice1.p : nullptr);
+			vxb_scan_kernel<<<grid, VXB_THREADS, 0, ctx->stream>>>(ctx->dDist, (int)n, ctx->scanFlags.p, ctx->haveLattice1 ? ctx->lattice1.p : nullptr, (int)layer0);
 			timer.end(); ++launches; ++ctx->kindLaunches[0];
-			const unsigned g2 = (unsigned)std::min<size_t>((blocks0 + 255) / 256, (size_t)ctx->smCount * 8);
+			const size_t first = layer0 * nb0 * nb0, last = layer1 * nb0 * nb0;
+			const unsigned g2 = (unsigned)std::min<size_t>((last - first + 255) / 256, (size_t)ctx->smCount * 8);
 			timer.begin(1);
-			vxb_block_info_kernel<<<g2, 256, 0, ctx->stream>>>(ctx->dDist, (int)n, ctx->scanFlags.p, ctx->blockInfo.p);
+			vxb_block_info_kernel<<<g2, 256, 0, ctx->stream>>>(ctx->dDist, (int)n, ctx->scanFlags.p, ctx->blockInfo.p, first, last);
 			timer.end(); ++launches; ++ctx->kindLaunches[1];
 		}
 		const unsigned flatGrid = (unsigned)ctx->smCount * 8;
@@ -661,10 +857,21 @@ static int runPolygonize(vxb_context* ctx, uint32_t maxLevels, uint32_t flags, c
 		//   stream2: classify levels 1.. (a latency-bound chain of small launches) -> decide -> vertices -> triangles -> transitions
 		// and joins before vxb_finish_kernel.  Per-kernel timing (VXB_FLAG_KERNEL_TIMES) runs everything on one stream.
 		const bool fork = computed > 1 && !kernelTimes;
-		classifyLevel(0, ctx->stream);
+		if (phase != 2) classifyLevel(0, ctx->stream);
+		if (phase == 1)
+		{
+			// sharded run, first half: the levels whose blocks nest in this rank's slab.  Nothing is read back: the caller
+			// exchanges the material pages of level splitLevel-1 on this stream (vxb_shard_exchange_info) and calls phase 2.
+			for (int l = 1; l < region->splitLevel && l < computed; ++l) classifyLevel(l, ctx->stream);
+			VXB_CUDA(ctx, cudaGetLastError());
+			ctx->shardLaunches = launches;
+			return VXB_OK;
+		}
+		const int firstRest = (phase == 2) ? region->splitLevel : 1;
+		if (phase == 2) launches += ctx->shardLaunches;
 		if (!fork)
 		{
-			for (int l = 1; l < computed; ++l) classifyLevel(l, ctx->stream);
+			for (int l = firstRest; l < computed; ++l) classifyLevel(l, ctx->stream);
 			decideGroup(0, ctx->stream); // level 0 first: its blocks own the first directory slots / arena ranges
 			vxb_mark_split_kernel<<<1, 1, 0, ctx->stream>>>(dev); ++launches;
 			flatGroup(0, ctx->stream);
@@ -679,7 +886,7 @@ static int runPolygonize(vxb_context* ctx, uint32_t maxLevels, uint32_t flags, c
 		{
 			VXB_CUDA(ctx, cudaEventRecord(ctx->evFork, ctx->stream));
 			VXB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->evFork, 0));
-			for (int l = 1; l < computed; ++l) classifyLevel(l, ctx->stream2);
+			for (int l = firstRest; l < computed; ++l) classifyLevel(l, ctx->stream2);
 			decideGroup(0, ctx->stream);
 			vxb_mark_split_kernel<<<1, 1, 0, ctx->stream>>>(dev); ++launches;
 			VXB_CUDA(ctx, cudaEventRecord(ctx->evDecide0, ctx->stream));
@@ -712,6 +919,8 @@ static int runPolygonize(vxb_context* ctx, uint32_t maxLevels, uint32_t flags, c
 		if (hc.transVertices > ctx->capTV) ctx->capTV = (uint64_t)hc.transVertices + hc.transVertices / 8 + 1024;
 		if (hc.transIndices > ctx->capTI) ctx->capTI = (uint64_t)hc.transIndices + hc.transIndices / 8 + 1024;
 		if (hc.cells > ctx->capC) ctx->capC = (uint64_t)hc.cells + hc.cells / 8 + 1024;
+		// a sharded run cannot redo its first half here
+		if (phase == 2) return fail(ctx, VXB_ERR_CAPACITY, "vxb_polygonize_sharded: output arenas overflowed; capacities were grown, repeat both phases on every rank");
 	}
 
 	// the directory stays on the device (it is part of the result resident in HBM); vxb_result_download fetches and
@@ -744,6 +953,7 @@ static int runPolygonize(vxb_context* ctx, uint32_t maxLevels, uint32_t flags, c
 	for (int i = 0; i < 8; ++i) info.used_materials[i] = hc.usedMaterials[i];
 	ctx->haveResult = true;
 	if (!region) { ctx->haveFullRun = (computed == levels); ctx->nextId = (uint32_t)totalBlocks; }
+	else if (!incremental) ctx->haveFullRun = false;
 	return VXB_OK;
 }
 
@@ -791,6 +1001,81 @@ int vxb_polygonize_region(vxb_context* ctx, const float minCorner[3], const floa
 	const int r = runPolygonize(ctx, 0, flags, &region);
 	if (r == VXB_OK) ctx->nextId = id;
 	return r;
+}
+
+// ---- sharded runs: rank r of `world` owns the z-slab of n/world planes ----
+
+static int shardSplitLevel(uint32_t n, uint32_t world, int levels)
+{
+	int split = 0;
+	while (split < levels && (16u << split) <= n / world) ++split; // blocks of levels [0, split) nest in one slab
+	return split;
+}
+
+static int shardCheck(vxb_context* ctx, uint32_t rank, uint32_t world, const char* who)
+{
+	if (!ctx) return VXB_ERR_ARGUMENT;
+	if (!ctx->haveGrid) return fail(ctx, VXB_ERR_STATE, "sharded run: no grid");
+	if (world == 0 || (world & (world - 1)) != 0 || rank >= world || ctx->n / world < 32)
+	{
+		char buf[160]; snprintf(buf, sizeof(buf), "%s: world must be a power of two with slabs of at least 32 planes, rank < world", who);
+		return fail(ctx, VXB_ERR_ARGUMENT, buf);
+	}
+	return VXB_OK;
+}
+
+int vxb_polygonize_sharded(vxb_context* ctx, uint32_t rank, uint32_t world, uint32_t phase, uint32_t flags)
+{
+	int r = shardCheck(ctx, rank, world, "vxb_polygonize_sharded");
+	if (r != VXB_OK) return r;
+	if (phase > 1) return fail(ctx, VXB_ERR_ARGUMENT, "vxb_polygonize_sharded: phase is 0 (classify the nested levels) or 1 (finish)");
+	Region region;
+	region.incremental = false;
+	region.phase = (int)phase + 1;
+	region.splitLevel = shardSplitLevel(ctx->n, world, ctx->levels);
+	region.voxels = (uint64_t)ctx->n * ctx->n * (ctx->n / world);
+	const uint32_t nb0 = ctx->n / 16, slab0 = nb0 / world;
+	region.scanLayer0 = (int)(rank * slab0 ? rank * slab0 - 1 : 0);
+	region.scanLayer1 = (int)std::min(nb0, (rank + 1) * slab0 + 1);
+	for (int l = 0; l < ctx->levels; ++l)
+	{
+		const int nbl = (int)(nb0 >> l);
+		const bool nested = l < region.splitLevel;
+		const int z0 = nested ? (int)(rank * (slab0 >> l)) : 0, z1 = nested ? (int)((rank + 1) * (slab0 >> l)) : (rank == 0 ? nbl : 0);
+		const bool any = z1 > z0;
+		region.rangeMin[l][0] = 0; region.rangeMin[l][1] = 0; region.rangeMin[l][2] = z0;
+		region.rangeMax[l][0] = any ? nbl : 0; region.rangeMax[l][1] = any ? nbl : 0; region.rangeMax[l][2] = z1;
+		region.idStart[l] = 0; // ids are the full-run ids: idBase[level] + coordinate id (:395-401)
+		region.count[l] = any ? (size_t)nbl * nbl * (z1 - z0) : 0;
+	}
+	return runPolygonize(ctx, 0, flags, &region);
+}
+
+int vxb_shard_exchange_info(vxb_context* ctx, uint32_t rank, uint32_t world, vxb_shard_exchange* out)
+{
+	int r = shardCheck(ctx, rank, world, "vxb_shard_exchange_info");
+	if (r != VXB_OK) return r;
+	if (!out) return fail(ctx, VXB_ERR_ARGUMENT, "vxb_shard_exchange_info: out is null");
+	memset(out, 0, sizeof(*out));
+	const int split = shardSplitLevel(ctx->n, world, ctx->levels);
+	out->split_level = (uint32_t)split;
+	if (split >= ctx->levels) return VXB_OK; // world == 1: every level nests, nothing to exchange
+	const int l = split - 1; // >= 1 because slabs have at least 32 planes
+	size_t validOff = 0, cacheOff = 0;
+	for (int k = 0; k < l; ++k)
+	{
+		const size_t b = blocksAtLevel(ctx->n, k);
+		validOff += (b + 15) & ~(size_t)15;
+		if (k >= 1) cacheOff += b * 4096;
+	}
+	const size_t blocks = blocksAtLevel(ctx->n, l);
+	if (!ctx->cachePages.p || !ctx->validFlags.p) return fail(ctx, VXB_ERR_STATE, "vxb_shard_exchange_info: call phase 0 of vxb_polygonize_sharded first");
+	out->level = (uint32_t)l;
+	out->pages = ctx->cachePages.p + cacheOff;
+	out->pages_bytes = blocks * 4096 * sizeof(unsigned short);
+	out->valid = ctx->validFlags.p + validOff;
+	out->valid_bytes = blocks;
+	return VXB_OK;
 }
 
 int vxb_region_info_get(vxb_context* ctx, vxb_region_info* out)

@@ -83,6 +83,7 @@ struct VxbDev
 	// incremental runs (GenerateBlockListForLevel, modification branch :429-465): per level a box of blocks and the
 	// id of its first block; ids follow the z,y,x loop order of :456-464
 	int incremental;
+	int ranged; // block selection uses rangeMin/rangeMax (incremental runs and the slab of a sharded run)
 	int rangeMin[VXB_MAX_LEVELS][3], rangeMax[VXB_MAX_LEVELS][3];
 	unsigned int idStart[VXB_MAX_LEVELS];
 	VxbVertex* verts; unsigned int* idx; VxbVertex* tverts; unsigned int* tidx;
@@ -182,12 +183,13 @@ __device__ __forceinline__ unsigned vxb_zero_bytes(unsigned w) // 0x80 in every 
 }
 
 __global__ void __launch_bounds__(VXB_THREADS) vxb_scan_kernel(const signed char* __restrict__ dist, int n, unsigned int* __restrict__ scanFlags,
-	unsigned char* __restrict__ lattice1 /* (n/2)^3: the samples at even coordinates = the level-1 lattice, or null */)
+	unsigned char* __restrict__ lattice1 /* (n/2)^3: the samples at even coordinates = the level-1 lattice, or null */,
+	int zBlock0 /* first block layer (a rank of a sharded run scans its slab + one layer either side) */)
 {
 	__shared__ unsigned sFlags[8];
 	__shared__ unsigned sChanges[8];
 	const int nb = n >> 4;
-	const int bx0 = blockIdx.x * 8, by = blockIdx.y, bz = blockIdx.z;
+	const int bx0 = blockIdx.x * 8, by = blockIdx.y, bz = blockIdx.z + zBlock0;
 	const int tid = threadIdx.x;
 	const int j = tid & 7, rg = tid >> 3;
 	if (tid < 8) { sFlags[tid] = 0; sChanges[tid] = 0; }
@@ -257,11 +259,11 @@ __global__ void __launch_bounds__(VXB_THREADS) vxb_scan_kernel(const signed char
 }
 
 // K1b: raw flags -> blockInfo.  One thread per level-0 block.
-__global__ void vxb_block_info_kernel(const signed char* __restrict__ dist, int n, const unsigned int* __restrict__ scanFlags, unsigned char* __restrict__ blockInfo)
+__global__ void vxb_block_info_kernel(const signed char* __restrict__ dist, int n, const unsigned int* __restrict__ scanFlags, unsigned char* __restrict__ blockInfo,
+	size_t first, size_t total /* block range [first, total): whole layers, z-major */)
 {
 	const int nb = n >> 4;
-	const size_t total = (size_t)nb * nb * nb;
-	for (size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < total; b += (size_t)gridDim.x * blockDim.x)
+	for (size_t b = first + (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < total; b += (size_t)gridDim.x * blockDim.x)
 	{
 		const unsigned f = scanFlags[b];
 		const bool neg = f & 1, pos = f & 2, zero = f & 4;
@@ -375,9 +377,9 @@ __global__ void __launch_bounds__(VXB_THREADS) vxb_unpack_rle_kernel(const unsig
 __global__ void vxb_select_kernel(VxbDev d, int level)
 {
 	const int m = 1 << level, nb = d.n / 16 / m, nb0 = d.n / 16;
-	// full run: every block of the level; incremental run: the dirty box of the level
-	const int x0 = d.incremental ? d.rangeMin[level][0] : 0, y0 = d.incremental ? d.rangeMin[level][1] : 0, z0 = d.incremental ? d.rangeMin[level][2] : 0;
-	const int nx = d.incremental ? d.rangeMax[level][0] - x0 : nb, ny = d.incremental ? d.rangeMax[level][1] - y0 : nb, nz = d.incremental ? d.rangeMax[level][2] - z0 : nb;
+	// full run: every block of the level; incremental run: the dirty box of the level; sharded run: the rank's slab
+	const int x0 = d.ranged ? d.rangeMin[level][0] : 0, y0 = d.ranged ? d.rangeMin[level][1] : 0, z0 = d.ranged ? d.rangeMin[level][2] : 0;
+	const int nx = d.ranged ? d.rangeMax[level][0] - x0 : nb, ny = d.ranged ? d.rangeMax[level][1] - y0 : nb, nz = d.ranged ? d.rangeMax[level][2] - z0 : nb;
 	const unsigned total = (nx > 0 && ny > 0 && nz > 0) ? (unsigned)nx * ny * nz : 0u;
 	for (unsigned base = blockIdx.x * blockDim.x; base < total; base += gridDim.x * blockDim.x)
 	{

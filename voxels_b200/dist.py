@@ -1,9 +1,15 @@
 """torch.distributed plumbing for the multi-GPU runs (one process per GPU; NCCL on the B200 box, gloo in the CPU tests).
 
-The polygonizer shards spatially with NO data-path collective: every rank owns an independent n^3 tile of the terrain
-(`tile_origin`), so the only communication is the barrier around the timed region and the max-reduction of the per-rank
-device times (the contract of bench.py)."""
+Two ways to use N GPUs:
+  * independent tiles (bench.py's weak-scaling line): every rank owns its own n^3 tile of the terrain (`tile_origin`);
+    no data-path collective, only the barrier around the timed region and the max-reduction of the device times;
+  * ONE grid sharded into z-slabs (`ShardedGrid`, SURVEY.md section 8e / BASELINE configs[3]): the cube lives in one
+    virtual address range per rank whose slabs are the ranks' HBM, mapped into every peer over NVLink (file
+    descriptors travel over Unix sockets, `exchange_fds`); the data path has ONE all-gather (the material pages of the
+    last level that nests in a slab) and the directories are all-gathered at the end."""
 import os
+import socket
+import threading
 
 
 class Ranks:
@@ -57,3 +63,170 @@ def tile_origin(rank, n):
 def whole_job_throughput(n, world, ms_per_step):
     """Mvoxels/s of the whole job: every rank polygonizes its own n^3 tile per step."""
     return float(n) ** 3 * world / (ms_per_step * 1e-3) / 1e6
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# one grid, z-slabs across the ranks
+# ---------------------------------------------------------------------------------------------------------------------
+
+def slab_planes(n, rank, world):
+    """[z0, z1) of rank's slab."""
+    t = n // world
+    return rank * t, (rank + 1) * t
+
+
+def split_level(n, world):
+    """Levels [0, split) have blocks that nest in a slab of n/world planes (vxb_shard_exchange.split_level)."""
+    levels = (n // 16).bit_length()
+    s = 0
+    while s < levels and (16 << s) <= n // world:
+        s += 1
+    return s
+
+
+def exchange_fds(rank, world, fds, key):
+    """Every rank offers `fds` (a list of open file descriptors) to every peer; returns {peer: [fds...]} with this
+    process's duplicates of the peers' descriptors.  Unix sockets in the abstract namespace + SCM_RIGHTS; all ranks run
+    on one host (one process per GPU of a box)."""
+    if world == 1:
+        return {}
+    name = lambda r: "\0vxb200-%s-%d" % (key, r)  # noqa: E731
+    server = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+    server.bind(name(rank))
+    server.listen(world)
+
+    def serve():
+        for _ in range(world - 1):
+            conn, _addr = server.accept()
+            with conn:
+                conn.recv(1)
+                socket.send_fds(conn, [b"f"], list(fds))
+    t = threading.Thread(target=serve, daemon=True)
+    t.start()
+    got = {}
+    for peer in range(world):
+        if peer == rank:
+            continue
+        c = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+        for attempt in range(600):  # the peer may not be listening yet
+            try:
+                c.connect(name(peer))
+                break
+            except (ConnectionRefusedError, FileNotFoundError):
+                import time
+                time.sleep(0.05)
+        else:
+            raise RuntimeError("exchange_fds: rank %d never reached rank %d" % (rank, peer))
+        with c:
+            c.send(b"r")
+            _msg, received, _flags, _addr = socket.recv_fds(c, 1, len(fds))
+        if len(received) != len(fds):
+            raise RuntimeError("exchange_fds: expected %d descriptors from rank %d, got %d" % (len(fds), peer, len(received)))
+        got[peer] = list(received)
+    t.join()
+    server.close()
+    return got
+
+
+def gather_directories(ranks, records):
+    """All-gather of the per-rank block directories (numpy RECORD_DTYPE arrays): counts first, then the padded payload.
+    Returns (records of all ranks sorted by (level, coord_id), owner rank of each)."""
+    import numpy as np
+    import torch
+    if ranks.td is None:
+        order = np.lexsort((records["coord_id"], records["level"]))
+        return records[order], np.zeros(len(records), np.int32)
+    dev = ranks.device if ranks.device is not None else torch.device("cpu")
+    counts = torch.zeros(ranks.world, dtype=torch.int64, device=dev)
+    mine = torch.tensor([len(records)], dtype=torch.int64, device=dev)
+    ranks.td.all_gather_into_tensor(counts, mine)
+    counts = counts.cpu().numpy()
+    width = int(counts.max())
+    item = records.dtype.itemsize
+    payload = np.zeros(width * item, np.uint8)
+    payload[:len(records) * item] = records.view(np.uint8).reshape(-1)
+    out = torch.zeros(ranks.world * width * item, dtype=torch.uint8, device=dev)
+    ranks.td.all_gather_into_tensor(out, torch.from_numpy(payload).to(dev))
+    out = out.cpu().numpy().reshape(ranks.world, width * item)
+    parts, owners = [], []
+    for r in range(ranks.world):
+        parts.append(out[r, :int(counts[r]) * item].copy().view(records.dtype))
+        owners.append(np.full(int(counts[r]), r, np.int32))
+    allrec, owner = np.concatenate(parts), np.concatenate(owners)
+    order = np.lexsort((allrec["coord_id"], allrec["level"]))
+    return allrec[order], owner[order]
+
+
+class ShardedGrid:
+    """One n^3 grid polygonized by all ranks (one GPU each).  Usage:
+        sg = ShardedGrid(ranks, n)            # cube: local slab + peers' slabs mapped over NVLink
+        d, m, b = sg.slab_tensors()           # torch uint8/int8 views [n/world, n, n] of the LOCAL slab: fill them
+        sg.ready()                            # barrier: every slab is filled
+        info = sg.polygonize()                # two phases around the one all-gather; this rank's blocks
+        directory, owner = sg.directory()     # every rank's blocks (all-gather), reference order
+    """
+
+    def __init__(self, ranks, n, device_index=None, key=None):
+        import torch
+        from . import capi
+        self.ranks, self.n = ranks, n
+        self.rank, self.world = ranks.rank, ranks.world
+        self.device_index = ranks.local_rank if device_index is None else device_index
+        self.device = torch.device("cuda", self.device_index)
+        self.ctx = capi.Context(self.device_index)
+        self.ctx.cube_create(n, self.rank, self.world)
+        if self.world > 1:
+            fds = [self.ctx.cube_export(c) for c in range(3)]
+            key = key or os.environ.get("MASTER_PORT", "0")
+            got = exchange_fds(self.rank, self.world, fds, "%s-%d" % (key, n))
+            for peer, theirs in got.items():
+                for c, fd in enumerate(theirs):
+                    self.ctx.cube_import(peer, c, fd)
+                    os.close(fd)
+            for fd in fds:
+                os.close(fd)
+        self._stream = torch.cuda.ExternalStream(self.ctx.stream(), device=self.device)
+
+    def slab_tensors(self):
+        import torch
+        from . import capi
+        d, m, b, size = self.ctx.cube_slab()
+        shape = (self.n // self.world, self.n, self.n)
+        view = lambda p: torch.as_tensor(capi.DevicePointer(p, size), device=self.device).view(shape)  # noqa: E731
+        return view(d).view(torch.int8), view(m), view(b)
+
+    def ready(self):
+        import torch
+        torch.cuda.synchronize(self.device)
+        self.ranks.barrier()
+
+    def polygonize(self, flags=0, max_attempts=4):
+        import torch
+        from . import capi
+        for _ in range(max_attempts):
+            self.ctx.polygonize_sharded(self.rank, self.world, 0, flags)
+            x = self.ctx.shard_exchange_info(self.rank, self.world)
+            if self.world > 1 and x.pages_bytes:
+                # the ONE data-path collective: in-place all-gather of the last nested level's material pages + flags,
+                # stream-ordered after phase 0 on the context's stream
+                with torch.cuda.stream(self._stream):
+                    for ptr, nbytes in ((x.pages, x.pages_bytes), (x.valid, x.valid_bytes)):
+                        full = torch.as_tensor(capi.DevicePointer(ptr, nbytes), device=self.device)
+                        chunk = nbytes // self.world
+                        self.ranks.td.all_gather_into_tensor(full, full[self.rank * chunk:(self.rank + 1) * chunk])
+            rc = self.ctx.polygonize_sharded(self.rank, self.world, 1, flags)
+            # an overflow on any rank repeats the run on every rank (the exchange is collective)
+            if self.ranks.max_over_ranks(1.0 if rc != 0 else 0.0) == 0.0:
+                return self.ctx.info()
+        raise capi.VxbError("sharded run: output arenas kept overflowing")
+
+    def directory(self):
+        import numpy as np
+        from . import capi
+        info = self.ctx.info()
+        records = np.zeros(info.block_count, capi.RECORD_DTYPE)
+        self.ctx._check(self.ctx.L.vxb_result_download(self.ctx.h, capi._ptr(records), None, None, None, None), "vxb_result_download")
+        return gather_directories(self.ranks, records)
+
+    def close(self):
+        self.ctx.close()

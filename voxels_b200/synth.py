@@ -61,9 +61,11 @@ def quantise(d):
     return torch.clamp(torch.sign(d) * torch.ceil(torch.abs(d)), -4, 4).to(torch.int8)
 
 
-def terrain(n, device="cpu", seed=1234, origin=(0, 0), z_chunk=16):
+def terrain(n, device="cpu", seed=1234, origin=(0, 0), z_chunk=16, z_range=None, out=None):
     """(dist int8, mat uint8, blend uint8), each [n, n, n] indexed [z, y, x], on `device`.
-    origin shifts the (x, y) window so different ranks get different tiles of one endless terrain."""
+    origin shifts the (x, y) window so different ranks get different tiles of one endless terrain.
+    z_range=(z0, z1) produces only those planes of the same n^3 terrain ([z1-z0, n, n]: the slab of one rank of a
+    sharded run); out=(dist, mat, blend) writes into existing tensors of that shape."""
     dev = torch.device(device)
     pn = Perlin(seed, dev)
     xs = torch.arange(n, device=dev, dtype=torch.float32) + float(origin[0])
@@ -72,19 +74,24 @@ def terrain(n, device="cpu", seed=1234, origin=(0, 0), z_chunk=16):
     height = 0.5 * n + 0.18 * n * pn.fbm2(X2 / n * 4.0, Y2 / n * 4.0)                   # [Y, X]
     h1 = 0.45 * n + 0.03 * n * pn.noise2(X2 / 37.0, Y2 / 37.0)
     h2 = 0.60 * n + 0.03 * n * pn.noise2(X2 / 53.0 + 7.7, Y2 / 53.0 + 3.3)
-    dist = torch.empty((n, n, n), dtype=torch.int8, device=dev)
-    mat = torch.empty((n, n, n), dtype=torch.uint8, device=dev)
-    blend = torch.empty((n, n, n), dtype=torch.uint8, device=dev)
+    zlo, zhi = (0, n) if z_range is None else z_range
+    if out is None:
+        dist = torch.empty((zhi - zlo, n, n), dtype=torch.int8, device=dev)
+        mat = torch.empty((zhi - zlo, n, n), dtype=torch.uint8, device=dev)
+        blend = torch.empty((zhi - zlo, n, n), dtype=torch.uint8, device=dev)
+    else:
+        dist, mat, blend = out
     X3, Y3 = xs.reshape(1, 1, -1), ys.reshape(1, -1, 1)
-    for z0 in range(0, n, z_chunk):
-        zs = torch.arange(z0, min(n, z0 + z_chunk), device=dev, dtype=torch.float32).reshape(-1, 1, 1)
+    for z0 in range(zlo, zhi, z_chunk):
+        z1 = min(zhi, z0 + z_chunk)
+        zs = torch.arange(z0, z1, device=dev, dtype=torch.float32).reshape(-1, 1, 1)
         d = zs - height.unsqueeze(0) + 6.0 * pn.noise3(X3 / 24.0, Y3 / 24.0, zs / 24.0)
-        dist[z0:z0 + z_chunk] = quantise(torch.clamp(d, -100, 100))
+        dist[z0 - zlo:z1 - zlo] = quantise(torch.clamp(d, -100, 100))
         m = torch.where(zs < h1.unsqueeze(0), 0, torch.where(zs < h2.unsqueeze(0), 1, 2))
         ore = pn.noise3(X3 / 48.0 + 11.1, Y3 / 48.0 + 5.5, zs / 48.0 + 2.2) > 0.35
-        mat[z0:z0 + z_chunk] = torch.where(ore, 3, m).to(torch.uint8)
+        mat[z0 - zlo:z1 - zlo] = torch.where(ore, 3, m).to(torch.uint8)
         t = torch.clamp((zs - h1.unsqueeze(0)) / (h2 - h1).unsqueeze(0).clamp(min=1.0), 0, 1)
-        blend[z0:z0 + z_chunk] = (255.0 * (t * t * (3 - 2 * t))).to(torch.uint8)
+        blend[z0 - zlo:z1 - zlo] = (255.0 * (t * t * (3 - 2 * t))).to(torch.uint8)
     return dist, mat, blend
 
 
