@@ -152,8 +152,11 @@ int vxb_polygonize_region(vxb_context* ctx, const float min_corner[3], const flo
 int vxb_region_info_get(vxb_context* ctx, vxb_region_info* out);
 
 /* ---- Sharded runs: ONE grid polygonized by `world` ranks, one GPU each (BASELINE configs[3]) ----
- * Rank r owns the z-slab of n/world planes [r*n/world, (r+1)*n/world) and produces every block that nests in it
- * (levels with 16*2^l <= n/world); rank 0 also produces the few blocks of the coarser levels, which span slabs.
+ * Rank r owns the z-slab of planes [plane_begin[r], plane_begin[r+1]) - plane_begin has world+1 ascending entries from 0
+ * to n, multiples of 32; NULL means `world` equal slabs - and produces every block that nests in the slabs (the levels
+ * whose block edge 16*2^l divides every boundary); rank 0 also produces the few blocks of the coarser levels, which
+ * span slabs.  Unequal slabs are how a caller balances the ranks when the surface is not spread evenly over z (a
+ * terrain: z is up, TransVoxelImpl.cpp:1289-1291).
  * Blocks are a pure function of the level-0 volumes plus the material pages of their child level
  * (TransVoxelImpl.cpp:763-837), so the only data-path exchange is ONE all-gather of the material pages of the last
  * nested level, between the two phases; block ids are the reference's full-run ids (:395-401), so the directories of
@@ -164,13 +167,16 @@ int vxb_region_info_get(vxb_context* ctx, vxb_region_info* out);
  * reads outside its slab only the first planes of the next slab (far cell corners, normals) and - rank 0 - the sparse
  * samples of the coarse levels.
  *
- *   vxb_polygonize_sharded(ctx, r, w, 0, flags)   enqueue: scan of the slab (+1 block layer either side), classification
- *                                                 of the nested levels.  Does not synchronise.
- *   vxb_shard_exchange_info(ctx, r, w, &x)        the two device buffers to all-gather IN PLACE on vxb_stream(ctx):
- *                                                 rank r contributed bytes [r*bytes/w, (r+1)*bytes/w) of each
- *                                                 (ncclAllGather; torch.distributed.all_gather_into_tensor)
- *   vxb_polygonize_sharded(ctx, r, w, 1, flags)   the coarse levels (rank 0), vertices, triangles, transition cells,
- *                                                 directory.  Result = this rank's blocks (vxb_result_info_get / download).
+ *   vxb_polygonize_sharded(ctx, r, w, pb, 0, flags)  enqueue: scan of the slab (+1 block layer either side), classification
+ *                                                    of the nested levels.  Does not synchronise.
+ *   vxb_shard_exchange_info(ctx, r, w, pb, &x)       the two device buffers rank 0 needs complete before phase 1, to be
+ *                                                    exchanged IN PLACE on vxb_stream(ctx): rank r produced the blocks of
+ *                                                    layers [pb[r], pb[r+1]) / layer_planes, layer_blocks blocks each, i.e.
+ *                                                    that byte range of `valid` and 8192x that range of `pages`
+ *                                                    (equal slabs: ncclAllGather / all_gather_into_tensor; unequal: grouped
+ *                                                    ncclSend/ncclRecv to rank 0)
+ *   vxb_polygonize_sharded(ctx, r, w, pb, 1, flags)  the coarse levels (rank 0), vertices, triangles, transition cells,
+ *                                                    directory.  Result = this rank's blocks (vxb_result_info_get / download).
  * VXB_ERR_CAPACITY from phase 1 means the arenas were grown: every rank repeats both phases. */
 typedef struct vxb_shard_exchange
 {
@@ -180,22 +186,24 @@ typedef struct vxb_shard_exchange
 	uint64_t pages_bytes;
 	void* valid;            /* device: one byte per block of `level` */
 	uint64_t valid_bytes;
+	uint32_t layer_planes;  /* planes per block layer of `level` (16 << level) */
+	uint32_t layer_blocks;  /* blocks per z-layer of `level` */
 } vxb_shard_exchange;
-int vxb_polygonize_sharded(vxb_context* ctx, uint32_t rank, uint32_t world, uint32_t phase, uint32_t flags);
-int vxb_shard_exchange_info(vxb_context* ctx, uint32_t rank, uint32_t world, vxb_shard_exchange* out);
+int vxb_polygonize_sharded(vxb_context* ctx, uint32_t rank, uint32_t world, const uint32_t* plane_begin, uint32_t phase, uint32_t flags);
+int vxb_shard_exchange_info(vxb_context* ctx, uint32_t rank, uint32_t world, const uint32_t* plane_begin, vxb_shard_exchange* out);
 
 /* The cube of a sharded run in device memory: each of the three volumes is ONE contiguous n^3 virtual range
  * (cuMemAddressReserve); this rank's z-slab is backed by its own HBM (cuMemCreate + cuMemMap), the other slabs are the
  * peers' allocations imported through POSIX file descriptors and mapped over NVLink / NVSwitch.  Kernels and TMA
- * tensor maps address the cube exactly like a single-GPU grid.  n^2 * n/world bytes must be a multiple of the
- * allocation granularity (2 MiB).
+ * tensor maps address the cube exactly like a single-GPU grid.  Every slab (n^2 bytes per plane) must start and end on
+ * a multiple of the allocation granularity (2 MiB).
  *   vxb_cube_create   reserve + back + map the local slab; the context's grid becomes the cube
  *   vxb_cube_export   channel 0/1/2 = distance / material / blend: a file descriptor for the local slab (caller closes it
  *                     after sending it to the peers, e.g. over a Unix socket with SCM_RIGHTS)
  *   vxb_cube_import   map peer `peer`'s slab of `channel` from a received descriptor (the descriptor can be closed after)
  *   vxb_cube_slab     device pointers and byte size of the local slab (fill it with cudaMemcpy / a generator kernel)
  * All slabs must be mapped and filled (a barrier across the ranks) before vxb_polygonize_sharded. */
-int vxb_cube_create(vxb_context* ctx, uint32_t n, uint32_t rank, uint32_t world);
+int vxb_cube_create(vxb_context* ctx, uint32_t n, uint32_t rank, uint32_t world, const uint32_t* plane_begin);
 int vxb_cube_export(vxb_context* ctx, uint32_t channel, int* fd);
 int vxb_cube_import(vxb_context* ctx, uint32_t peer, uint32_t channel, int fd);
 int vxb_cube_slab(vxb_context* ctx, int8_t** dist, uint8_t** mat, uint8_t** blend, uint64_t* bytes_per_channel);

@@ -23,25 +23,30 @@ def _views(x, world):
             torch.as_tensor(capi.DevicePointer(x.valid, x.valid_bytes), device=dev))
 
 
-def run_virtual_ranks(contexts, world, flags=0):
+def run_virtual_ranks(contexts, world, flags=0, planes=None):
     """contexts[r] already sees the whole cube.  Returns the merged result."""
     import torch
     from voxels_b200 import capi
+    from voxels_b200.dist import uniform_planes
+    n = contexts[0].n
+    pb = uniform_planes(n, world) if planes is None else planes
     for attempt in range(4):
         for r, c in enumerate(contexts):
-            c.polygonize_sharded(r, world, 0, flags)
+            c.polygonize_sharded(r, world, 0, flags, planes)
         torch.cuda.synchronize()
-        xs = [c.shard_exchange_info(r, world) for r, c in enumerate(contexts)]
+        xs = [c.shard_exchange_info(r, world, planes) for r, c in enumerate(contexts)]
         if world > 1:
             views = [_views(x, world) for x in xs]
-            for kind in range(2):
-                chunk = views[0][kind].numel() // world
+            x = xs[0]
+            for kind, unit in ((0, 8192), (1, 1)):
                 for src in range(world):
+                    lo = pb[src] // x.layer_planes * x.layer_blocks * unit
+                    hi = pb[src + 1] // x.layer_planes * x.layer_blocks * unit
                     for dst in range(world):
                         if src != dst:
-                            views[dst][kind][src * chunk:(src + 1) * chunk].copy_(views[src][kind][src * chunk:(src + 1) * chunk])
+                            views[dst][kind][lo:hi].copy_(views[src][kind][lo:hi])
             torch.cuda.synchronize()
-        rcs = [c.polygonize_sharded(r, world, 1, flags) for r, c in enumerate(contexts)]
+        rcs = [c.polygonize_sharded(r, world, 1, flags, planes) for r, c in enumerate(contexts)]
         if not any(rcs):
             return capi.merge_results([c.download() for c in contexts])
     raise AssertionError("arenas kept overflowing")
@@ -56,8 +61,9 @@ def assert_same(a, b, levels):
     assert not problems, "\n".join(problems[:10])
 
 
-@pytest.mark.parametrize("name,world", [("hostile128", 2), ("hostile128", 4), ("sphere128", 2), ("noise64", 2), ("hostile64", 2)])
-def test_virtual_ranks_equal_single_run(gpu_context, name, world):
+@pytest.mark.parametrize("name,world,planes", [("hostile128", 2, None), ("hostile128", 4, None), ("sphere128", 2, None), ("noise64", 2, None),
+                                               ("hostile64", 2, None), ("hostile128", 3, [0, 32, 96, 128]), ("sphere128", 2, [0, 96, 128])])
+def test_virtual_ranks_equal_single_run(gpu_context, name, world, planes):
     import voxels_b200
     dist, mat, blend = (grids.MEDIUM.get(name) or grids.SMALL[name])()
     n = dist.shape[0]
@@ -70,7 +76,7 @@ def test_virtual_ranks_equal_single_run(gpu_context, name, world):
     try:
         for c in contexts:
             c.set_device_grid(n, d, m, b)
-        merged = run_virtual_ranks(contexts, world)
+        merged = run_virtual_ranks(contexts, world, planes=planes)
         assert_same(single, merged, info.levels_total)
         # every block exactly once, ids are the full-run ids
         assert np.array_equal(single.records["id"], merged.records["id"])
@@ -104,8 +110,8 @@ def test_sharded_against_reference(reference, gpu_context):
         reference.grid_destroy(g)
 
 
-@pytest.mark.parametrize("world", [1, 2, 4])
-def test_cube_of_mapped_slabs(gpu_context, world):
+@pytest.mark.parametrize("world,planes", [(1, None), (2, None), (4, None), (3, [0, 64, 192, 256])])
+def test_cube_of_mapped_slabs(gpu_context, world, planes):
     """The VMM cube: one virtual range per volume, every slab its own physical allocation, peers imported by descriptor."""
     import torch
     import voxels_b200
@@ -119,8 +125,10 @@ def test_cube_of_mapped_slabs(gpu_context, world):
     single = gpu_context.download()
     contexts = [voxels_b200.Context(0) for _ in range(world)]
     try:
+        from voxels_b200.dist import uniform_planes
+        pb = uniform_planes(n, world) if planes is None else planes
         for r, c in enumerate(contexts):
-            c.cube_create(n, r, world)
+            c.cube_create(n, r, world, planes)
         for r, c in enumerate(contexts):
             fds = [c.cube_export(ch) for ch in range(3)]
             for p, peer in enumerate(contexts):
@@ -129,14 +137,13 @@ def test_cube_of_mapped_slabs(gpu_context, world):
                         peer.cube_import(r, ch, fd)
             for fd in fds:
                 os.close(fd)
-        t = n // world
         for r, c in enumerate(contexts):
-            pd, pm, pb, size = c.cube_slab()
-            assert size == n * n * t
-            for ptr, src in ((pd, dist), (pm, mat), (pb, blend)):
-                torch.as_tensor(capi.DevicePointer(ptr, size), device=dev).copy_(src[r * t:(r + 1) * t].reshape(-1).view(torch.uint8))
+            pd, pm, pbl, size = c.cube_slab()
+            assert size == n * n * (pb[r + 1] - pb[r])
+            for ptr, src in ((pd, dist), (pm, mat), (pbl, blend)):
+                torch.as_tensor(capi.DevicePointer(ptr, size), device=dev).copy_(src[pb[r]:pb[r + 1]].reshape(-1).view(torch.uint8))
         torch.cuda.synchronize()
-        merged = run_virtual_ranks(contexts, world)
+        merged = run_virtual_ranks(contexts, world, planes=planes)
         assert_same(single, merged, info.levels_total)
     finally:
         for c in contexts:

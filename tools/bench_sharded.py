@@ -26,22 +26,39 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--verify", action="store_true")
+    ap.add_argument("--balance", type=int, default=0, metavar="PLANES",
+                    help="after a first run with equal slabs, re-shard with boundaries (multiples of PLANES) that even out the work it measured")
     args = ap.parse_args()
     import numpy as np
     import torch
     import voxels_b200
     from voxels_b200 import capi, synth
-    from voxels_b200.dist import Ranks, ShardedGrid, slab_planes
+    from voxels_b200.dist import Ranks, ShardedGrid, slab_planes, balanced_planes, layer_weights_from_directory
 
     local = int(os.environ.get("LOCAL_RANK", "0"))
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     ranks = Ranks("nccl", dev)
     n = args.size
-    sg = ShardedGrid(ranks, n)
-    z0, z1 = slab_planes(n, ranks.rank, ranks.world)
-    synth.terrain(n, dev, z_range=(z0, z1), out=sg.slab_tensors())
-    sg.ready()
+    def build(planes):
+        g = ShardedGrid(ranks, n, planes=planes)
+        z0, z1 = slab_planes(n, ranks.rank, ranks.world, planes)
+        synth.terrain(n, dev, z_range=(z0, z1), out=g.slab_tensors())
+        g.ready()
+        return g
+
+    sg = build(None)
+    planes = None
+    if args.balance and ranks.world > 1:
+        # z is up: a terrain's surface sits in a few z-layers.  One run with equal slabs tells where the work is; the
+        # slabs are then re-cut so that every rank gets the same share (what a client does from the previous frame).
+        sg.polygonize()
+        directory, _ = sg.directory()
+        planes = balanced_planes(layer_weights_from_directory(n, directory), ranks.world, args.balance // 16)
+        sg.close()
+        torch.cuda.synchronize(dev)
+        ranks.barrier()
+        sg = build(planes)
 
     stream = torch.cuda.ExternalStream(sg.ctx.stream(), device=dev)
     times = []
@@ -61,7 +78,8 @@ def main():
     out = {"metric": "Mvoxels/s polygonized (one grid sharded over the GPUs)", "value": float(n) ** 3 / (ms * 1e-3) / 1e6, "unit": "Mvoxels/s",
            "n_gpus": ranks.world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "scaling": "strong",
            "config": {"workload": "%d^3 seeded Perlin terrain, all LOD levels + transition cells, z-slabs of %d planes" % (n, n // ranks.world),
-                      "exchange": "one NCCL all-gather (material pages of the last nested level) + directory all-gather"},
+                      "slab_boundaries": planes if planes is not None else "equal",
+                      "exchange": "one NCCL exchange (material pages of the last nested level) + directory all-gather"},
            "blocks_total": int(len(directory)), "blocks_per_rank": [int((owner == r).sum()) for r in range(ranks.world)],
            "vertices_this_rank0": int(info.vertex_total)}
 

@@ -36,7 +36,7 @@ class RegionInfo(C.Structure):
 
 class ShardExchange(C.Structure):
     _fields_ = [("split_level", C.c_uint32), ("level", C.c_uint32), ("pages", C.c_void_p), ("pages_bytes", C.c_uint64),
-                ("valid", C.c_void_p), ("valid_bytes", C.c_uint64)]
+                ("valid", C.c_void_p), ("valid_bytes", C.c_uint64), ("layer_planes", C.c_uint32), ("layer_blocks", C.c_uint32)]
 
 
 ERR_CAPACITY = -4
@@ -91,9 +91,9 @@ def load_library():
         "vxb_grid_update_blocks": (C.c_int, [vp, u32, vp, vp, vp, vp]),
         "vxb_polygonize_region": (C.c_int, [vp, vp, vp, u32]),
         "vxb_region_info_get": (C.c_int, [vp, C.POINTER(RegionInfo)]),
-        "vxb_polygonize_sharded": (C.c_int, [vp, u32, u32, u32, u32]),
-        "vxb_shard_exchange_info": (C.c_int, [vp, u32, u32, C.POINTER(ShardExchange)]),
-        "vxb_cube_create": (C.c_int, [vp, u32, u32, u32]),
+        "vxb_polygonize_sharded": (C.c_int, [vp, u32, u32, vp, u32, u32]),
+        "vxb_shard_exchange_info": (C.c_int, [vp, u32, u32, vp, C.POINTER(ShardExchange)]),
+        "vxb_cube_create": (C.c_int, [vp, u32, u32, u32, vp]),
         "vxb_cube_export": (C.c_int, [vp, u32, C.POINTER(C.c_int)]),
         "vxb_cube_import": (C.c_int, [vp, u32, u32, C.c_int]),
         "vxb_cube_slab": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(u64)]),
@@ -282,21 +282,32 @@ class Context:
         return self.info()
 
     # ---- sharded runs (include/vxb200.h: vxb_polygonize_sharded, vxb_cube_*) ----
-    def polygonize_sharded(self, rank, world, phase, flags=0):
+    @staticmethod
+    def _planes(planes, world):
+        if planes is None:
+            return None, None
+        arr = np.ascontiguousarray(planes, np.uint32)
+        assert arr.size == world + 1, "plane_begin needs world + 1 entries"
+        return arr, _ptr(arr)
+
+    def polygonize_sharded(self, rank, world, phase, flags=0, planes=None):
         """Returns 0, or ERR_CAPACITY from phase 1 (arenas grown: every rank repeats both phases)."""
-        rc = self.L.vxb_polygonize_sharded(self.h, rank, world, phase, flags)
+        keep, pb = self._planes(planes, world)
+        rc = self.L.vxb_polygonize_sharded(self.h, rank, world, pb, phase, flags)
         if rc == ERR_CAPACITY and phase == 1:
             return rc
         self._check(rc, "vxb_polygonize_sharded")
         return 0
 
-    def shard_exchange_info(self, rank, world):
+    def shard_exchange_info(self, rank, world, planes=None):
         x = ShardExchange()
-        self._check(self.L.vxb_shard_exchange_info(self.h, rank, world, C.byref(x)), "vxb_shard_exchange_info")
+        keep, pb = self._planes(planes, world)
+        self._check(self.L.vxb_shard_exchange_info(self.h, rank, world, pb, C.byref(x)), "vxb_shard_exchange_info")
         return x
 
-    def cube_create(self, n, rank, world):
-        self._check(self.L.vxb_cube_create(self.h, n, rank, world), "vxb_cube_create")
+    def cube_create(self, n, rank, world, planes=None):
+        keep, pb = self._planes(planes, world)
+        self._check(self.L.vxb_cube_create(self.h, n, rank, world, pb), "vxb_cube_create")
         self.n = n
 
     def cube_export(self, channel):

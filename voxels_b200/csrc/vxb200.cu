@@ -105,11 +105,14 @@ struct vxb_context
 	{
 		bool active = false;
 		uint32_t rank = 0, world = 1;
-		size_t cubeBytes = 0, slabBytes = 0;
+		size_t cubeBytes = 0, planeBytes = 0;
+		std::vector<uint32_t> planes; // slab r = planes [planes[r], planes[r + 1])
 		CUdeviceptr va[3] = { 0, 0, 0 };
 		CUmemGenericAllocationHandle local[3] = { 0, 0, 0 };
 		std::vector<CUmemGenericAllocationHandle> imported;
-		std::vector<CUdeviceptr> mapped; // every mapped slab (size slabBytes)
+		std::vector<std::pair<CUdeviceptr, size_t> > mapped; // every mapped slab
+		size_t slabOffset(uint32_t r) const { return (size_t)planes[r] * planeBytes; }
+		size_t slabBytes(uint32_t r) const { return (size_t)(planes[r + 1] - planes[r]) * planeBytes; }
 	} cube;
 	VxbCounters lastCounters;
 	size_t validBytes = 0;
@@ -187,6 +190,39 @@ int buildTensorMap(vxb_context* ctx)
 	}
 	else ctx->tmap1 = ctx->tmap;
 	return r;
+}
+
+// Validates a slab layout (NULL = `world` equal slabs) and returns its boundaries and split level: levels [0, split)
+// have blocks that nest in every slab, i.e. every boundary is a multiple of 16 << (split - 1).
+int shardLayout(vxb_context* ctx, uint32_t n, int levels, uint32_t rank, uint32_t world, const uint32_t* planeBegin, const char* who,
+	std::vector<uint32_t>& planes, int& split)
+{
+	char buf[200];
+	if (world == 0 || world > 64 || rank >= world)
+	{
+		snprintf(buf, sizeof(buf), "%s: world in [1, 64], rank < world", who);
+		return fail(ctx, VXB_ERR_ARGUMENT, buf);
+	}
+	planes.resize(world + 1);
+	for (uint32_t r = 0; r <= world; ++r) planes[r] = planeBegin ? planeBegin[r] : (uint32_t)((uint64_t)n * r / world);
+	bool ok = planes[0] == 0 && planes[world] == n;
+	for (uint32_t r = 0; r < world && ok; ++r) ok = planes[r + 1] > planes[r] && planes[r + 1] % 32 == 0;
+	if (!ok)
+	{
+		snprintf(buf, sizeof(buf), "%s: slab boundaries must ascend from 0 to n in multiples of 32 planes (a uniform split needs n / world >= 32, world a power of two)", who);
+		return fail(ctx, VXB_ERR_ARGUMENT, buf);
+	}
+	split = 0;
+	for (;;)
+	{
+		if (split >= levels) break;
+		const uint32_t m = 16u << split;
+		bool nests = true;
+		for (uint32_t r = 1; r < world; ++r) if (planes[r] % m) nests = false;
+		if (!nests) break;
+		++split;
+	}
+	return VXB_OK;
 }
 
 size_t blocksAtLevel(uint32_t n, int level) { const size_t nb = (n / 16) >> level; return nb * nb * nb; }
@@ -283,7 +319,7 @@ void releaseCube(vxb_context* ctx)
 	vxb_context::Cube& c = ctx->cube;
 	if (!c.active) return;
 	const VmmApi& api = vmmApi();
-	for (CUdeviceptr p : c.mapped) api.unmap(p, c.slabBytes);
+	for (const auto& m : c.mapped) api.unmap(m.first, m.second);
 	for (CUmemGenericAllocationHandle h : c.imported) api.release(h);
 	for (int k = 0; k < 3; ++k)
 	{
@@ -308,15 +344,16 @@ int mapSlab(vxb_context* ctx, int channel, uint32_t slab, CUmemGenericAllocation
 {
 	const VmmApi& api = vmmApi();
 	vxb_context::Cube& c = ctx->cube;
-	const CUdeviceptr at = c.va[channel] + (CUdeviceptr)slab * c.slabBytes;
-	VXB_CU(ctx, api.map(at, c.slabBytes, 0, handle, 0));
-	c.mapped.push_back(at);
+	const CUdeviceptr at = c.va[channel] + (CUdeviceptr)c.slabOffset(slab);
+	const size_t bytes = c.slabBytes(slab);
+	VXB_CU(ctx, api.map(at, bytes, 0, handle, 0));
+	c.mapped.push_back(std::make_pair(at, bytes));
 	CUmemAccessDesc access;
 	memset(&access, 0, sizeof(access));
 	access.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
 	access.location.id = ctx->device;
 	access.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
-	VXB_CU(ctx, api.setAccess(at, c.slabBytes, &access, 1));
+	VXB_CU(ctx, api.setAccess(at, bytes, &access, 1));
 	return VXB_OK;
 }
 }
@@ -324,11 +361,14 @@ int mapSlab(vxb_context* ctx, int channel, uint32_t slab, CUmemGenericAllocation
 extern "C"
 {
 
-int vxb_cube_create(vxb_context* ctx, uint32_t n, uint32_t rank, uint32_t world)
+int vxb_cube_create(vxb_context* ctx, uint32_t n, uint32_t rank, uint32_t world, const uint32_t* planeBegin)
 {
 	if (!ctx) return VXB_ERR_ARGUMENT;
-	if (!validSize(n) || world == 0 || (world & (world - 1)) != 0 || rank >= world || n / world < 32)
-		return fail(ctx, VXB_ERR_ARGUMENT, "vxb_cube_create: n a power of two in [16, 4096], world a power of two with slabs of at least 32 planes, rank < world");
+	if (!validSize(n)) return fail(ctx, VXB_ERR_ARGUMENT, "vxb_cube_create: n must be a power of two in [16, 4096]");
+	std::vector<uint32_t> planes;
+	int split = 0;
+	const int lr = shardLayout(ctx, n, levelsFor(n), rank, world, planeBegin, "vxb_cube_create", planes, split);
+	if (lr != VXB_OK) return lr;
 	const VmmApi& api = vmmApi();
 	if (!api.ok) return fail(ctx, VXB_ERR_CUDA, "vxb_cube_create: the driver does not export the virtual memory management entry points");
 	cudaSetDevice(ctx->device);
@@ -337,20 +377,23 @@ int vxb_cube_create(vxb_context* ctx, uint32_t n, uint32_t rank, uint32_t world)
 	vxb_context::Cube& c = ctx->cube;
 	c.rank = rank; c.world = world;
 	c.cubeBytes = (size_t)n * n * n;
-	c.slabBytes = c.cubeBytes / world;
+	c.planeBytes = (size_t)n * n;
+	c.planes = planes;
 	const CUmemAllocationProp prop = slabProp(ctx->device);
 	size_t gran = 0;
 	VXB_CU(ctx, api.granularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_MINIMUM));
-	if (!gran || c.slabBytes % gran != 0)
-	{
-		char buf[160]; snprintf(buf, sizeof(buf), "vxb_cube_create: a slab (%zu bytes) must be a multiple of the allocation granularity (%zu bytes)", c.slabBytes, gran);
-		return fail(ctx, VXB_ERR_ARGUMENT, buf);
-	}
+	for (uint32_t r = 0; r < world; ++r)
+		if (!gran || c.slabOffset(r) % gran != 0 || c.slabBytes(r) % gran != 0)
+		{
+			char buf[200]; snprintf(buf, sizeof(buf), "vxb_cube_create: slab %u (%zu bytes at offset %zu) is not a multiple of the allocation granularity (%zu bytes)", r, c.slabBytes(r), c.slabOffset(r), gran);
+			c = vxb_context::Cube();
+			return fail(ctx, VXB_ERR_ARGUMENT, buf);
+		}
 	c.active = true;
 	for (int k = 0; k < 3; ++k)
 	{
 		VXB_CU(ctx, api.addressReserve(&c.va[k], c.cubeBytes, 0, 0, 0));
-		VXB_CU(ctx, api.create(&c.local[k], c.slabBytes, &prop, 0));
+		VXB_CU(ctx, api.create(&c.local[k], c.slabBytes(rank), &prop, 0));
 		const int r = mapSlab(ctx, k, rank, c.local[k]);
 		if (r != VXB_OK) return r;
 	}
@@ -390,11 +433,11 @@ int vxb_cube_slab(vxb_context* ctx, int8_t** dist, uint8_t** mat, uint8_t** blen
 	if (!ctx) return VXB_ERR_ARGUMENT;
 	const vxb_context::Cube& c = ctx->cube;
 	if (!c.active) return fail(ctx, VXB_ERR_STATE, "vxb_cube_slab: no cube");
-	const size_t off = (size_t)c.rank * c.slabBytes;
+	const size_t off = c.slabOffset(c.rank);
 	if (dist) *dist = reinterpret_cast<int8_t*>(c.va[0] + off);
 	if (mat) *mat = reinterpret_cast<uint8_t*>(c.va[1] + off);
 	if (blend) *blend = reinterpret_cast<uint8_t*>(c.va[2] + off);
-	if (bytes) *bytes = c.slabBytes;
+	if (bytes) *bytes = c.slabBytes(c.rank);
 	return VXB_OK;
 }
 
@@ -1003,64 +1046,51 @@ int vxb_polygonize_region(vxb_context* ctx, const float minCorner[3], const floa
 	return r;
 }
 
-// ---- sharded runs: rank r of `world` owns the z-slab of n/world planes ----
+// ---- sharded runs: rank r of `world` owns the z-slab [plane_begin[r], plane_begin[r+1]) ----
 
-static int shardSplitLevel(uint32_t n, uint32_t world, int levels)
-{
-	int split = 0;
-	while (split < levels && (16u << split) <= n / world) ++split; // blocks of levels [0, split) nest in one slab
-	return split;
-}
-
-static int shardCheck(vxb_context* ctx, uint32_t rank, uint32_t world, const char* who)
+int vxb_polygonize_sharded(vxb_context* ctx, uint32_t rank, uint32_t world, const uint32_t* planeBegin, uint32_t phase, uint32_t flags)
 {
 	if (!ctx) return VXB_ERR_ARGUMENT;
-	if (!ctx->haveGrid) return fail(ctx, VXB_ERR_STATE, "sharded run: no grid");
-	if (world == 0 || (world & (world - 1)) != 0 || rank >= world || ctx->n / world < 32)
-	{
-		char buf[160]; snprintf(buf, sizeof(buf), "%s: world must be a power of two with slabs of at least 32 planes, rank < world", who);
-		return fail(ctx, VXB_ERR_ARGUMENT, buf);
-	}
-	return VXB_OK;
-}
-
-int vxb_polygonize_sharded(vxb_context* ctx, uint32_t rank, uint32_t world, uint32_t phase, uint32_t flags)
-{
-	int r = shardCheck(ctx, rank, world, "vxb_polygonize_sharded");
-	if (r != VXB_OK) return r;
+	if (!ctx->haveGrid) return fail(ctx, VXB_ERR_STATE, "vxb_polygonize_sharded: no grid");
 	if (phase > 1) return fail(ctx, VXB_ERR_ARGUMENT, "vxb_polygonize_sharded: phase is 0 (classify the nested levels) or 1 (finish)");
+	std::vector<uint32_t> planes;
 	Region region;
+	int r = shardLayout(ctx, ctx->n, ctx->levels, rank, world, planeBegin, "vxb_polygonize_sharded", planes, region.splitLevel);
+	if (r != VXB_OK) return r;
 	region.incremental = false;
 	region.phase = (int)phase + 1;
-	region.splitLevel = shardSplitLevel(ctx->n, world, ctx->levels);
-	region.voxels = (uint64_t)ctx->n * ctx->n * (ctx->n / world);
-	const uint32_t nb0 = ctx->n / 16, slab0 = nb0 / world;
-	region.scanLayer0 = (int)(rank * slab0 ? rank * slab0 - 1 : 0);
-	region.scanLayer1 = (int)std::min(nb0, (rank + 1) * slab0 + 1);
+	const uint32_t z0 = planes[rank], z1 = planes[rank + 1];
+	region.voxels = (uint64_t)ctx->n * ctx->n * (z1 - z0);
+	const uint32_t nb0 = ctx->n / 16;
+	region.scanLayer0 = (int)(z0 ? z0 / 16 - 1 : 0);
+	region.scanLayer1 = (int)std::min(nb0, z1 / 16 + 1);
 	for (int l = 0; l < ctx->levels; ++l)
 	{
 		const int nbl = (int)(nb0 >> l);
 		const bool nested = l < region.splitLevel;
-		const int z0 = nested ? (int)(rank * (slab0 >> l)) : 0, z1 = nested ? (int)((rank + 1) * (slab0 >> l)) : (rank == 0 ? nbl : 0);
-		const bool any = z1 > z0;
-		region.rangeMin[l][0] = 0; region.rangeMin[l][1] = 0; region.rangeMin[l][2] = z0;
-		region.rangeMax[l][0] = any ? nbl : 0; region.rangeMax[l][1] = any ? nbl : 0; region.rangeMax[l][2] = z1;
+		const int b0 = nested ? (int)(z0 >> (4 + l)) : 0, b1 = nested ? (int)(z1 >> (4 + l)) : (rank == 0 ? nbl : 0);
+		const bool any = b1 > b0;
+		region.rangeMin[l][0] = 0; region.rangeMin[l][1] = 0; region.rangeMin[l][2] = b0;
+		region.rangeMax[l][0] = any ? nbl : 0; region.rangeMax[l][1] = any ? nbl : 0; region.rangeMax[l][2] = b1;
 		region.idStart[l] = 0; // ids are the full-run ids: idBase[level] + coordinate id (:395-401)
-		region.count[l] = any ? (size_t)nbl * nbl * (z1 - z0) : 0;
+		region.count[l] = any ? (size_t)nbl * nbl * (b1 - b0) : 0;
 	}
 	return runPolygonize(ctx, 0, flags, &region);
 }
 
-int vxb_shard_exchange_info(vxb_context* ctx, uint32_t rank, uint32_t world, vxb_shard_exchange* out)
+int vxb_shard_exchange_info(vxb_context* ctx, uint32_t rank, uint32_t world, const uint32_t* planeBegin, vxb_shard_exchange* out)
 {
-	int r = shardCheck(ctx, rank, world, "vxb_shard_exchange_info");
-	if (r != VXB_OK) return r;
+	if (!ctx) return VXB_ERR_ARGUMENT;
+	if (!ctx->haveGrid) return fail(ctx, VXB_ERR_STATE, "vxb_shard_exchange_info: no grid");
 	if (!out) return fail(ctx, VXB_ERR_ARGUMENT, "vxb_shard_exchange_info: out is null");
+	std::vector<uint32_t> planes;
+	int split = 0;
+	int r = shardLayout(ctx, ctx->n, ctx->levels, rank, world, planeBegin, "vxb_shard_exchange_info", planes, split);
+	if (r != VXB_OK) return r;
 	memset(out, 0, sizeof(*out));
-	const int split = shardSplitLevel(ctx->n, world, ctx->levels);
 	out->split_level = (uint32_t)split;
-	if (split >= ctx->levels) return VXB_OK; // world == 1: every level nests, nothing to exchange
-	const int l = split - 1; // >= 1 because slabs have at least 32 planes
+	if (split >= ctx->levels) return VXB_OK; // one rank: every level nests, nothing to exchange
+	const int l = split - 1; // >= 1: boundaries are multiples of 32 planes
 	size_t validOff = 0, cacheOff = 0;
 	for (int k = 0; k < l; ++k)
 	{
@@ -1068,13 +1098,15 @@ int vxb_shard_exchange_info(vxb_context* ctx, uint32_t rank, uint32_t world, vxb
 		validOff += (b + 15) & ~(size_t)15;
 		if (k >= 1) cacheOff += b * 4096;
 	}
-	const size_t blocks = blocksAtLevel(ctx->n, l);
+	const size_t nbl = (ctx->n / 16) >> l;
 	if (!ctx->cachePages.p || !ctx->validFlags.p) return fail(ctx, VXB_ERR_STATE, "vxb_shard_exchange_info: call phase 0 of vxb_polygonize_sharded first");
 	out->level = (uint32_t)l;
 	out->pages = ctx->cachePages.p + cacheOff;
-	out->pages_bytes = blocks * 4096 * sizeof(unsigned short);
+	out->pages_bytes = nbl * nbl * nbl * 4096 * sizeof(unsigned short);
 	out->valid = ctx->validFlags.p + validOff;
-	out->valid_bytes = blocks;
+	out->valid_bytes = nbl * nbl * nbl;
+	out->layer_planes = 16u << l;
+	out->layer_blocks = (uint32_t)(nbl * nbl);
 	return VXB_OK;
 }
 

@@ -69,19 +69,74 @@ def whole_job_throughput(n, world, ms_per_step):
 # one grid, z-slabs across the ranks
 # ---------------------------------------------------------------------------------------------------------------------
 
-def slab_planes(n, rank, world):
+def uniform_planes(n, world):
+    return [n * r // world for r in range(world + 1)]
+
+
+def slab_planes(n, rank, world, planes=None):
     """[z0, z1) of rank's slab."""
-    t = n // world
-    return rank * t, (rank + 1) * t
+    planes = uniform_planes(n, world) if planes is None else planes
+    return int(planes[rank]), int(planes[rank + 1])
 
 
-def split_level(n, world):
-    """Levels [0, split) have blocks that nest in a slab of n/world planes (vxb_shard_exchange.split_level)."""
+def split_level(n, world, planes=None):
+    """Levels [0, split) have blocks that nest in every slab (vxb_shard_exchange.split_level): the block edge 16 << l
+    divides every slab boundary."""
+    planes = uniform_planes(n, world) if planes is None else planes
     levels = (n // 16).bit_length()
     s = 0
-    while s < levels and (16 << s) <= n // world:
+    while s < levels and all(int(p) % (16 << s) == 0 for p in planes[1:-1]):
         s += 1
     return s
+
+
+def balanced_planes(layer_weights, world, align_layers):
+    """Slab boundaries that even out the work: layer_weights[i] = work in level-0 block layer i (16 planes), e.g. the
+    vertices + triangles the last run produced there.  Boundaries are multiples of align_layers layers (that decides
+    which levels still nest, see split_level); every slab gets at least one such unit.  Minimises the maximum slab
+    weight (dynamic programme over the <= n/16/align_layers cells)."""
+    import numpy as np
+    w = np.asarray(layer_weights, np.float64)
+    cells = len(w) // align_layers
+    assert cells >= world, "more ranks than alignment units"
+    cw = np.concatenate([[0.0], np.cumsum(w.reshape(cells, align_layers).sum(axis=1))])
+    inf = float("inf")
+    best = [[inf] * (cells + 1) for _ in range(world + 1)]
+    cut = [[0] * (cells + 1) for _ in range(world + 1)]
+    best[0][0] = 0.0
+    for r in range(1, world + 1):
+        for e in range(r, cells - (world - r) + 1):
+            for b in range(r - 1, e):
+                if best[r - 1][b] == inf:
+                    continue
+                # a tiny per-cell cost keeps empty regions spread over the ranks instead of piled on one
+                cost = max(best[r - 1][b], cw[e] - cw[b] + 1e-9 * (e - b))
+                if cost < best[r][e]:
+                    best[r][e], cut[r][e] = cost, b
+    bounds, e = [cells], cells
+    for r in range(world, 0, -1):
+        e = cut[r][e]
+        bounds.append(e)
+    return [b * align_layers * 16 for b in reversed(bounds)]
+
+
+def layer_weights_from_directory(n, records):
+    """Work per level-0 block layer from a block directory (numpy RECORD_DTYPE): a block's vertices + indices/3, spread
+    over the layers it covers."""
+    import numpy as np
+    nb0 = n // 16
+    w = np.zeros(nb0, np.float64)
+    level = records["level"].astype(np.int64)
+    nbl = nb0 >> level
+    z = records["coord_id"].astype(np.int64) // (nbl * nbl)
+    work = (records["vertex_count"].astype(np.float64) + records["index_count"] / 3.0
+            + records["trans_vertex_count"].sum(axis=1) + records["trans_index_count"].sum(axis=1) / 3.0)
+    for l in np.unique(level):
+        sel = level == l
+        span = 1 << int(l)
+        per_layer = np.bincount(z[sel], weights=work[sel] / span, minlength=nb0 >> int(l))
+        w += np.repeat(per_layer, span)
+    return w
 
 
 def exchange_fds(rank, world, fds, key):
@@ -166,15 +221,16 @@ class ShardedGrid:
         directory, owner = sg.directory()     # every rank's blocks (all-gather), reference order
     """
 
-    def __init__(self, ranks, n, device_index=None, key=None):
+    def __init__(self, ranks, n, device_index=None, key=None, planes=None):
         import torch
         from . import capi
         self.ranks, self.n = ranks, n
+        self.planes = None if planes is None else [int(p) for p in planes]  # None = equal slabs
         self.rank, self.world = ranks.rank, ranks.world
         self.device_index = ranks.local_rank if device_index is None else device_index
         self.device = torch.device("cuda", self.device_index)
         self.ctx = capi.Context(self.device_index)
-        self.ctx.cube_create(n, self.rank, self.world)
+        self.ctx.cube_create(n, self.rank, self.world, self.planes)
         if self.world > 1:
             fds = [self.ctx.cube_export(c) for c in range(3)]
             key = key or os.environ.get("MASTER_PORT", "0")
@@ -191,7 +247,8 @@ class ShardedGrid:
         import torch
         from . import capi
         d, m, b, size = self.ctx.cube_slab()
-        shape = (self.n // self.world, self.n, self.n)
+        z0, z1 = slab_planes(self.n, self.rank, self.world, self.planes)
+        shape = (z1 - z0, self.n, self.n)
         view = lambda p: torch.as_tensor(capi.DevicePointer(p, size), device=self.device).view(shape)  # noqa: E731
         return view(d).view(torch.int8), view(m), view(b)
 
@@ -203,18 +260,33 @@ class ShardedGrid:
     def polygonize(self, flags=0, max_attempts=4):
         import torch
         from . import capi
+        td = self.ranks.td
         for _ in range(max_attempts):
-            self.ctx.polygonize_sharded(self.rank, self.world, 0, flags)
-            x = self.ctx.shard_exchange_info(self.rank, self.world)
+            self.ctx.polygonize_sharded(self.rank, self.world, 0, flags, self.planes)
+            x = self.ctx.shard_exchange_info(self.rank, self.world, self.planes)
             if self.world > 1 and x.pages_bytes:
-                # the ONE data-path collective: in-place all-gather of the last nested level's material pages + flags,
-                # stream-ordered after phase 0 on the context's stream
+                # the ONE data-path exchange, stream-ordered after phase 0 on the context's stream and in place: the
+                # material pages + flags of the last nested level.  Equal slabs: all-gather; unequal: rank 0 (the only
+                # consumer, it builds the coarse levels) receives every other rank's range in one NCCL group.
                 with torch.cuda.stream(self._stream):
-                    for ptr, nbytes in ((x.pages, x.pages_bytes), (x.valid, x.valid_bytes)):
-                        full = torch.as_tensor(capi.DevicePointer(ptr, nbytes), device=self.device)
-                        chunk = nbytes // self.world
-                        self.ranks.td.all_gather_into_tensor(full, full[self.rank * chunk:(self.rank + 1) * chunk])
-            rc = self.ctx.polygonize_sharded(self.rank, self.world, 1, flags)
+                    pages = torch.as_tensor(capi.DevicePointer(x.pages, x.pages_bytes), device=self.device)
+                    valid = torch.as_tensor(capi.DevicePointer(x.valid, x.valid_bytes), device=self.device)
+                    if self.planes is None:
+                        for full in (pages, valid):
+                            chunk = full.numel() // self.world
+                            td.all_gather_into_tensor(full, full[self.rank * chunk:(self.rank + 1) * chunk])
+                    else:
+                        def rng(r, unit):
+                            return slice(self.planes[r] // x.layer_planes * x.layer_blocks * unit, self.planes[r + 1] // x.layer_planes * x.layer_blocks * unit)
+                        ops = []
+                        for full, unit in ((pages, 8192), (valid, 1)):
+                            if self.rank == 0:
+                                ops += [td.P2POp(td.irecv, full[rng(r, unit)], r) for r in range(1, self.world)]
+                            else:
+                                ops.append(td.P2POp(td.isend, full[rng(self.rank, unit)], 0))
+                        for req in td.batch_isend_irecv(ops):
+                            req.wait()
+            rc = self.ctx.polygonize_sharded(self.rank, self.world, 1, flags, self.planes)
             # an overflow on any rank repeats the run on every rank (the exchange is collective)
             if self.ranks.max_over_ranks(1.0 if rc != 0 else 0.0) == 0.0:
                 return self.ctx.info()
