@@ -90,6 +90,9 @@ void vxb_destroy(vxb_context* ctx);
 const char* vxb_last_error(const vxb_context* ctx);   /* ctx may be NULL: error of a failed vxb_create */
 /* cudaStream_t the context launches on (as void*), for callers that time with their own events */
 void* vxb_stream(vxb_context* ctx);
+/* cudaStream_t on which a sharded run's caller enqueues the exchange between the two phases (ordered after phase 0's
+ * classification; phase 1 makes only the coarse levels wait for it) */
+void* vxb_exchange_stream(vxb_context* ctx);
 
 /* ---- grid (input provider side: VoxelGrid accessors, src/VoxelGrid.h:49-55) ------------------ */
 /* n^3 dense volumes in HOST memory, index (z*n + y)*n + x.  mat/blend may be NULL (zeros). */
@@ -170,7 +173,7 @@ int vxb_region_info_get(vxb_context* ctx, vxb_region_info* out);
  *   vxb_polygonize_sharded(ctx, r, w, pb, 0, flags)  enqueue: scan of the slab (+1 block layer either side), classification
  *                                                    of the nested levels.  Does not synchronise.
  *   vxb_shard_exchange_info(ctx, r, w, pb, &x)       the two device buffers rank 0 needs complete before phase 1, to be
- *                                                    exchanged IN PLACE on vxb_stream(ctx): rank r produced the blocks of
+ *                                                    exchanged IN PLACE on vxb_exchange_stream(ctx): rank r produced the blocks of
  *                                                    layers [pb[r], pb[r+1]) / layer_planes, layer_blocks blocks each, i.e.
  *                                                    that byte range of `valid` and 8192x that range of `pages`
  *                                                    (equal slabs: ncclAllGather / all_gather_into_tensor; unequal: grouped

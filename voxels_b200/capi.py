@@ -78,6 +78,7 @@ def load_library():
         "vxb_destroy": (None, [vp]),
         "vxb_last_error": (C.c_char_p, [vp]),
         "vxb_stream": (vp, [vp]),
+        "vxb_exchange_stream": (vp, [vp]),
         "vxb_grid_upload_dense": (C.c_int, [vp, u32, vp, vp, vp]),
         "vxb_grid_upload_blocks": (C.c_int, [vp, u32, vp, vp, vp]),
         "vxb_grid_set_device": (C.c_int, [vp, u32, vp, vp, vp]),
@@ -111,7 +112,7 @@ def load_library():
     return L
 
 
-EXPORTED_SYMBOLS = ["vxb_create", "vxb_destroy", "vxb_last_error", "vxb_stream", "vxb_grid_upload_dense",
+EXPORTED_SYMBOLS = ["vxb_create", "vxb_destroy", "vxb_last_error", "vxb_stream", "vxb_exchange_stream", "vxb_grid_upload_dense",
                     "vxb_grid_upload_blocks", "vxb_grid_upload_packed", "vxb_pack_dense_bound", "vxb_pack_dense", "vxb_grid_set_device", "vxb_grid_device_pointers", "vxb_set_materials",
                     "vxb_polygonize", "vxb_polygonize_region", "vxb_region_info_get", "vxb_grid_update_blocks", "vxb_result_info_get", "vxb_result_download", "vxb_set_capacity", "vxb_kernel_ms",
                     "vxb_result_unmapped_materials", "vxb_host_alloc", "vxb_host_free", "vxb_polygonize_sharded", "vxb_shard_exchange_info",
@@ -331,6 +332,9 @@ class Context:
 
     def stream(self):
         return self.L.vxb_stream(self.h)
+
+    def exchange_stream(self):
+        return self.L.vxb_exchange_stream(self.h)
 
     def region_info(self):
         ri = RegionInfo()

@@ -528,6 +528,8 @@ const char* vxb_last_error(const vxb_context* ctx) { return ctx ? ctx->error.c_s
 
 void* vxb_stream(vxb_context* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 
+void* vxb_exchange_stream(vxb_context* ctx) { return ctx ? (void*)ctx->stream2 : nullptr; }
+
 int vxb_grid_upload_dense(vxb_context* ctx, uint32_t n, const int8_t* dist, const uint8_t* mat, const uint8_t* blend)
 {
 	if (!ctx) return VXB_ERR_ARGUMENT;
@@ -899,7 +901,7 @@ static int runPolygonize(vxb_context* ctx, uint32_t maxLevels, uint32_t flags, c
 		//   stream : level 0 -> decide -> vertices -> triangles
 		//   stream2: classify levels 1.. (a latency-bound chain of small launches) -> decide -> vertices -> triangles -> transitions
 		// and joins before vxb_finish_kernel.  Per-kernel timing (VXB_FLAG_KERNEL_TIMES) runs everything on one stream.
-		const bool fork = computed > 1 && !kernelTimes;
+		const bool fork = (computed > 1 && !kernelTimes) || phase == 2;
 		if (phase != 2) classifyLevel(0, ctx->stream);
 		if (phase == 1)
 		{
@@ -907,6 +909,10 @@ static int runPolygonize(vxb_context* ctx, uint32_t maxLevels, uint32_t flags, c
 			// exchanges the material pages of level splitLevel-1 on this stream (vxb_shard_exchange_info) and calls phase 2.
 			for (int l = 1; l < region->splitLevel && l < computed; ++l) classifyLevel(l, ctx->stream);
 			VXB_CUDA(ctx, cudaGetLastError());
+			// the exchange runs on the second stream (vxb_exchange_stream), ordered after this classification; in phase 2
+			// only the coarse levels wait for it, the vertices and triangles of the nested levels overlap it
+			VXB_CUDA(ctx, cudaEventRecord(ctx->evFork, ctx->stream));
+			VXB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->evFork, 0));
 			ctx->shardLaunches = launches;
 			return VXB_OK;
 		}
