@@ -61,7 +61,7 @@ def main():
         sg = build(planes)
 
     stream = torch.cuda.ExternalStream(sg.ctx.stream(), device=dev)
-    times = []
+    times, mine_ms, inner_ms = [], [], []
     for step in range(args.warmup + args.steps):
         ranks.barrier()
         torch.cuda.synchronize(dev)
@@ -73,14 +73,23 @@ def main():
         ms = ranks.max_over_ranks(e0.elapsed_time(e1))
         if step >= args.warmup:
             times.append(ms)
+            mine_ms.append(e0.elapsed_time(e1))
+            inner_ms.append(info.device_ms)
     directory, owner = sg.directory()
     ms = float(np.mean(times))
+    per_rank = torch.zeros(ranks.world * 2, dtype=torch.float64, device=dev)
+    if ranks.td is not None:
+        ranks.td.all_gather_into_tensor(per_rank, torch.tensor([float(np.mean(mine_ms)), float(np.mean(inner_ms))], dtype=torch.float64, device=dev))
+    else:
+        per_rank = torch.tensor([float(np.mean(mine_ms)), float(np.mean(inner_ms))])
+    per_rank = per_rank.cpu().numpy().reshape(-1, 2)
     out = {"metric": "Mvoxels/s polygonized (one grid sharded over the GPUs)", "value": float(n) ** 3 / (ms * 1e-3) / 1e6, "unit": "Mvoxels/s",
            "n_gpus": ranks.world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "scaling": "strong",
            "config": {"workload": "%d^3 seeded Perlin terrain, all LOD levels + transition cells, z-slabs of %d planes" % (n, n // ranks.world),
                       "slab_boundaries": planes if planes is not None else "equal",
                       "exchange": "one NCCL exchange (material pages of the last nested level) + directory all-gather"},
            "blocks_total": int(len(directory)), "blocks_per_rank": [int((owner == r).sum()) for r in range(ranks.world)],
+           "ms_per_rank": [round(float(v), 3) for v in per_rank[:, 0]], "device_ms_per_rank": [round(float(v), 3) for v in per_rank[:, 1]],
            "vertices_this_rank0": int(info.vertex_total)}
 
     if args.verify:
