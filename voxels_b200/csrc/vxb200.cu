@@ -90,6 +90,8 @@ struct vxb_context
 	uint64_t capV = 0, capI = 0, capTV = 0, capTI = 0;
 	CUtensorMap tmap, tmap1, tmapDist19, tmapMat, tmapBlend;
 	int gridVertexBlock = 0;
+	bool vbMatTiles = false;
+	size_t vbSmem = 0;
 	DevBuf<uint8_t> lattice1;
 	bool haveLattice1 = false;
 	int gridClassify = 0, gridDecideSmall = 0, gridDecideBig = 0, gridTransition = 0;
@@ -478,19 +480,21 @@ int vxb_create(int device, vxb_context** out)
 	if (e != cudaSuccess || !fn) { fail(nullptr, VXB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available", e); delete ctx; return VXB_ERR_CUDA; }
 	ctx->encodeTiled = reinterpret_cast<EncodeTiledFn>(fn);
 
-	struct KernelSetup { const void* fn; size_t smem; int* grid; const char* name; };
+	ctx->vbMatTiles = getenv("VXB200_VB_MAT_TILES") != nullptr;
+	ctx->vbSmem = ctx->vbMatTiles ? sizeof(VxbVertexBlockSmem) : offsetof(VxbVertexBlockSmem, mat);
+	struct KernelSetup { const void* fn; size_t smem; int* grid; const char* name; int threads; };
 	const KernelSetup setups[5] = {
-		{ (const void*)vxb_classify_kernel, sizeof(VxbClassifySmem), &ctx->gridClassify, "vxb_classify_kernel" },
-		{ (const void*)vxb_decide_kernel<1024, 0>, sizeof(VxbDecideSmemSmall), &ctx->gridDecideSmall, "vxb_decide_kernel<1024>" },
-		{ (const void*)vxb_decide_kernel<4096, 1>, sizeof(VxbDecideSmemBig), &ctx->gridDecideBig, "vxb_decide_kernel<4096>" },
-		{ (const void*)vxb_transition_kernel, sizeof(VxbTransSmem), &ctx->gridTransition, "vxb_transition_kernel" },
-		{ (const void*)vxb_vertex_block_kernel, sizeof(VxbVertexBlockSmem), &ctx->gridVertexBlock, "vxb_vertex_block_kernel" },
+		{ (const void*)vxb_classify_kernel, sizeof(VxbClassifySmem), &ctx->gridClassify, "vxb_classify_kernel", VXB_THREADS },
+		{ (const void*)vxb_decide_kernel<1024, 0>, sizeof(VxbDecideSmemSmall), &ctx->gridDecideSmall, "vxb_decide_kernel<1024>", VXB_THREADS },
+		{ (const void*)vxb_decide_kernel<4096, 1>, sizeof(VxbDecideSmemBig), &ctx->gridDecideBig, "vxb_decide_kernel<4096>", VXB_THREADS },
+		{ (const void*)vxb_transition_kernel, sizeof(VxbTransSmem), &ctx->gridTransition, "vxb_transition_kernel", VXB_THREADS },
+		{ ctx->vbMatTiles ? (const void*)vxb_vertex_block_kernel<true> : (const void*)vxb_vertex_block_kernel<false>, ctx->vbSmem, &ctx->gridVertexBlock, "vxb_vertex_block_kernel", VXB_VB_THREADS },
 	};
 	for (const KernelSetup& k : setups)
 	{
 		int occ = 0;
 		e = cudaFuncSetAttribute(k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k.smem);
-		if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k.fn, VXB_THREADS, k.smem);
+		if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k.fn, k.threads, k.smem);
 		if (e != cudaSuccess || occ < 1) { fail(nullptr, VXB_ERR_CUDA, k.name, e); delete ctx; return VXB_ERR_CUDA; }
 		*k.grid = occ * ctx->smCount;
 	}
@@ -880,7 +884,8 @@ static int runPolygonize(vxb_context* ctx, uint32_t maxLevels, uint32_t flags, c
 		};
 		auto flatGroup = [&](int part, cudaStream_t st) {
 			timer.begin(4);
-			if (part == 0) vxb_vertex_block_kernel<<<ctx->gridVertexBlock, VXB_THREADS, sizeof(VxbVertexBlockSmem), st>>>(ctx->tmapDist19, ctx->tmapMat, ctx->tmapBlend, dev);
+			if (part == 0 && ctx->vbMatTiles) vxb_vertex_block_kernel<true><<<ctx->gridVertexBlock, VXB_VB_THREADS, ctx->vbSmem, st>>>(ctx->tmapDist19, ctx->tmapMat, ctx->tmapBlend, dev);
+			else if (part == 0) vxb_vertex_block_kernel<false><<<ctx->gridVertexBlock, VXB_VB_THREADS, ctx->vbSmem, st>>>(ctx->tmapDist19, ctx->tmapMat, ctx->tmapBlend, dev);
 			else vxb_vertex_kernel<<<flatGrid, VXB_THREADS, 0, st>>>(dev, part);
 			timer.end(); ++launches; ++ctx->kindLaunches[4];
 			timer.begin(5);

@@ -13,7 +13,7 @@
 
 #if defined(__CUDACC__)
 #define VXB_FN __device__ __forceinline__
-#define VXB_FN_BIG __device__ __noinline__   // large helpers: one copy each, the kernels must stay I-cache friendly
+#define VXB_FN_BIG __device__ __forceinline__ // the per-vertex helpers: inlined, a call would pass the vertex through local memory
 #define VXB_SQRT(x) __fsqrt_rn(x)
 #define VXB_DIV(a, b) __fdiv_rn((a), (b))
 #else
@@ -80,6 +80,7 @@ struct VxbTileView
 	int ox, oy, oz;              // block origin (grid coordinates of its first voxel)
 	int sx, sy, sz;              // first coordinate held by the distance tile: (origin.x - 16, origin.y - 1, origin.z - 1)
 	                             // - TMA needs a 16-byte aligned innermost start -, or 0 on the low grid edge
+	int n;                       // != 0: material / blend are the global volumes (mat, blend = their bases), n = grid edge
 };
 
 // low edge: coordinate -1 clamps to 0 = the tile's first sample; the far edge is replicated when the tile is filled
@@ -88,8 +89,14 @@ VXB_FN int vxb_dist(const VxbTileView& g, int x, int y, int z)
 	const int xi = (x < g.sx ? g.sx : x) - g.sx, yi = (y < g.sy ? g.sy : y) - g.sy, zi = (z < g.sz ? g.sz : z) - g.sz;
 	return g.dist[(zi * 19 + yi) * 48 + xi];
 }
-VXB_FN unsigned vxb_mat(const VxbTileView& g, int x, int y, int z) { return g.mat[((z - g.oz) * 17 + (y - g.oy)) * 32 + (x - g.ox)]; }
-VXB_FN unsigned vxb_blend(const VxbTileView& g, int x, int y, int z) { return g.blend[((z - g.oz) * 17 + (y - g.oy)) * 32 + (x - g.ox)]; }
+VXB_FN size_t vxb_tile_mat_index(const VxbTileView& g, int x, int y, int z)
+{
+	if (!g.n) return (size_t)(((z - g.oz) * 17 + (y - g.oy)) * 32 + (x - g.ox));
+	const int m = g.n - 1; // the two material taps of a vertex (cell corners) are clamped like every grid read (:1242-1244)
+	return ((size_t)(z > m ? m : z) * g.n + (y > m ? m : y)) * g.n + (x > m ? m : x);
+}
+VXB_FN unsigned vxb_mat(const VxbTileView& g, int x, int y, int z) { return g.mat[vxb_tile_mat_index(g, x, y, z)]; }
+VXB_FN unsigned vxb_blend(const VxbTileView& g, int x, int y, int z) { return g.blend[vxb_tile_mat_index(g, x, y, z)]; }
 VXB_FN unsigned vxb_mat(const VxbGrid& g, int x, int y, int z) { return g.mat[vxb_index(g, x, y, z)]; }
 VXB_FN unsigned vxb_blend(const VxbGrid& g, int x, int y, int z) { return g.blend[vxb_index(g, x, y, z)]; }
 
@@ -272,10 +279,10 @@ VXB_FN_BIG void vxb_corner_vertex(const G& g, int level, const int base[3], cons
 {
 	const int m = 1 << level;
 	const int px = base[0] + ((corner & 1) ? m : 0), py = base[1] + ((corner & 2) ? m : 0), pz = base[2] + ((corner & 4) ? m : 0);
+	const unsigned myId = vxb_mat(g, px, py, pz), myBlend = vxb_blend(g, px, py, pz); // both taps in flight while the normal is computed
 	vxb_normal(g, px, py, pz, out.n);
-	const unsigned myId = vxb_mat(g, px, py, pz);
 	out.matId = cellMatId;
-	out.blend = (myId != cellMatId) ? cellMatBlend : vxb_blend(g, px, py, pz);
+	out.blend = (myId != cellMatId) ? cellMatBlend : myBlend;
 	out.p[0] = (float)px * 256.f; out.p[1] = (float)py * 256.f; out.p[2] = (float)pz * 256.f;
 	out.flags = vxb_corner_flags(level, local[0], local[1], local[2], corner);
 }
@@ -293,10 +300,12 @@ VXB_FN_BIG void vxb_edge_vertex(const G& g, int level, const int base[3], const 
 	const int u = 256 - t;
 	const float ft = (float)t, fu = (float)u;
 
+	// the four material / blend taps are issued before the normals so that their latency overlaps the arithmetic
+	const unsigned m0 = vxb_mat(g, p0[0], p0[1], p0[2]), m1 = vxb_mat(g, p1[0], p1[1], p1[2]);
+	const unsigned b0 = vxb_blend(g, p0[0], p0[1], p0[2]), b1 = vxb_blend(g, p1[0], p1[1], p1[2]);
 	float n0[3], n1[3];
 	vxb_normal(g, p0[0], p0[1], p0[2], n0);
 	vxb_normal(g, p1[0], p1[1], p1[2], n1);
-	const unsigned m0 = vxb_mat(g, p0[0], p0[1], p0[2]), m1 = vxb_mat(g, p1[0], p1[1], p1[2]);
 
 	out.p[0] = ft * (float)p0[0] + fu * (float)p1[0];
 	out.p[1] = ft * (float)p0[1] + fu * (float)p1[1];
@@ -305,7 +314,7 @@ VXB_FN_BIG void vxb_edge_vertex(const G& g, int level, const int base[3], const 
 
 	out.matId = cellMatId;
 	if (m0 == m1 && m0 == cellMatId)
-		out.blend = vxb_blend_u8((ft * (float)(int)vxb_blend(g, p0[0], p0[1], p0[2]) + fu * (float)(int)vxb_blend(g, p1[0], p1[1], p1[2])) / 256.f);
+		out.blend = vxb_blend_u8((ft * (float)(int)b0 + fu * (float)(int)b1) / 256.f);
 	else
 		out.blend = cellMatBlend;
 

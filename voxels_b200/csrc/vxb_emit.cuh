@@ -502,18 +502,22 @@ __global__ void __launch_bounds__(VXB_THREADS) vxb_vertex_kernel(const VxbDev d,
 // blend samples (17^3) are staged by three TMA loads, so the 16 one-byte taps of a vertex come from shared memory
 // instead of 16 separate 32-byte DRAM sectors.  Grid-edge clamping (:1198, :1242-1244) is baked into the tiles.
 #define VXB_DTILE_PITCH 48
+#define VXB_VB_CELLS 512   // blocks with more non-trivial cells read their records from global memory
+#define VXB_VB_THREADS 128 // a block has ~350 new vertices: 128-thread CTAs waste fewer lanes in the last round and more of them fit an SM
 #define VXB_DTILE_BYTES (19 * 19 * VXB_DTILE_PITCH)
 struct __align__(128) VxbVertexBlockSmem
 {
 	signed char dist[VXB_DTILE_BYTES + 80];
-	unsigned char mat[VXB_TILE_BYTES + 96];
-	unsigned char blend[VXB_TILE_BYTES + 96];
 	unsigned long long mbar;
 	unsigned int item;
 	unsigned int used[8];
+	uint4 cells[VXB_VB_CELLS]; // the block's cell records, staged while the TMA load is in flight
+	__align__(128) unsigned char mat[VXB_TILE_BYTES + 96]; // the material / blend tiles are optional (MAT_TILES)
+	unsigned char blend[VXB_TILE_BYTES + 96];
 };
 
-__global__ void __launch_bounds__(VXB_THREADS, 4) vxb_vertex_block_kernel(const __grid_constant__ CUtensorMap tmapDist19, const __grid_constant__ CUtensorMap tmapMat,
+template <bool MAT_TILES>
+__global__ void __launch_bounds__(VXB_VB_THREADS, 8) vxb_vertex_block_kernel(const __grid_constant__ CUtensorMap tmapDist19, const __grid_constant__ CUtensorMap tmapMat,
 	const __grid_constant__ CUtensorMap tmapBlend, const VxbDev d)
 {
 	extern __shared__ __align__(128) unsigned char smemRaw[];
@@ -534,18 +538,25 @@ __global__ void __launch_bounds__(VXB_THREADS, 4) vxb_vertex_block_kernel(const 
 		if (slot >= count) break;
 		const VxbBlockRec* br = &d.blockRecs[slot];
 		const unsigned coordId = br->packed & 0x0FFFFFFFu;
-		const unsigned voff = br->voff, nverts = br->nverts;
+		const unsigned voff = br->voff, nverts = br->nverts, cellBase = br->cellBase, ntc = br->ntc;
+		const bool staged = ntc <= VXB_VB_CELLS;
 		const int bx = coordId % nb, by = (coordId / nb) % nb, bz = coordId / (nb * nb);
 		// the distance tile starts one sample before the block, except on the low grid edge (all TMA coordinates stay >= 0)
 		const int sx = bx ? bx * 16 - 16 : 0, sy = by ? by * 16 - 1 : 0, sz = bz ? bz * 16 - 1 : 0; // x start 16-byte aligned
 		if (tid == 0)
 		{
 			vxb_fence_proxy_async();
-			vxb_mbar_expect_tx(&s.mbar, VXB_DTILE_BYTES + 2 * VXB_TILE_BYTES);
+			vxb_mbar_expect_tx(&s.mbar, VXB_DTILE_BYTES + (MAT_TILES ? 2 * VXB_TILE_BYTES : 0));
 			vxb_tma_load_3d(s.dist, &tmapDist19, sx, sy, sz, &s.mbar);
-			vxb_tma_load_3d(s.mat, &tmapMat, bx * 16, by * 16, bz * 16, &s.mbar);
-			vxb_tma_load_3d(s.blend, &tmapBlend, bx * 16, by * 16, bz * 16, &s.mbar);
+			if (MAT_TILES)
+			{
+				vxb_tma_load_3d(s.mat, &tmapMat, bx * 16, by * 16, bz * 16, &s.mbar);
+				vxb_tma_load_3d(s.blend, &tmapBlend, bx * 16, by * 16, bz * 16, &s.mbar);
+			}
 		}
+		if (staged)
+			for (unsigned i = tid; i < ntc; i += VXB_VB_THREADS) s.cells[i] = *reinterpret_cast<const uint4*>(&d.cellRecs[cellBase + i]);
+		unsigned e = (tid < nverts) ? d.vlist[voff + tid] : 0u;
 		vxb_mbar_wait(&s.mbar, phase);
 		phase ^= 1;
 		// far grid edge: TMA zero-fills outside the volume, the reference clamps the coordinate to n-1
@@ -553,23 +564,23 @@ __global__ void __launch_bounds__(VXB_THREADS, 4) vxb_vertex_block_kernel(const 
 		if (bx == nb - 1)
 		{
 			__syncthreads();
-			for (int i = tid; i < 19 * 19; i += VXB_THREADS)
+			for (int i = tid; i < 19 * 19; i += VXB_VB_THREADS)
 			{
 				signed char* r = s.dist + i * VXB_DTILE_PITCH;
 				r[lastX + 1] = r[lastX]; r[lastX + 2] = r[lastX];
 			}
-			for (int i = tid; i < 17 * 17; i += VXB_THREADS) { s.mat[i * VXB_TILE_PITCH + 16] = s.mat[i * VXB_TILE_PITCH + 15]; s.blend[i * VXB_TILE_PITCH + 16] = s.blend[i * VXB_TILE_PITCH + 15]; }
+			if (MAT_TILES) for (int i = tid; i < 17 * 17; i += VXB_VB_THREADS) { s.mat[i * VXB_TILE_PITCH + 16] = s.mat[i * VXB_TILE_PITCH + 15]; s.blend[i * VXB_TILE_PITCH + 16] = s.blend[i * VXB_TILE_PITCH + 15]; }
 		}
 		if (by == nb - 1)
 		{
 			__syncthreads();
-			for (int i = tid; i < 19 * VXB_DTILE_PITCH; i += VXB_THREADS)
+			for (int i = tid; i < 19 * VXB_DTILE_PITCH; i += VXB_VB_THREADS)
 			{
 				const int z = i / VXB_DTILE_PITCH, x = i % VXB_DTILE_PITCH;
 				signed char* p = s.dist + z * 19 * VXB_DTILE_PITCH + x;
 				for (int q = lastY + 1; q < 19; ++q) p[q * VXB_DTILE_PITCH] = p[lastY * VXB_DTILE_PITCH];
 			}
-			for (int i = tid; i < 17 * 17; i += VXB_THREADS)
+			if (MAT_TILES) for (int i = tid; i < 17 * 17; i += VXB_VB_THREADS)
 			{
 				const int z = i / 17, x = i % 17;
 				s.mat[(z * 17 + 16) * VXB_TILE_PITCH + x] = s.mat[(z * 17 + 15) * VXB_TILE_PITCH + x];
@@ -579,13 +590,13 @@ __global__ void __launch_bounds__(VXB_THREADS, 4) vxb_vertex_block_kernel(const 
 		if (bz == nb - 1)
 		{
 			__syncthreads();
-			for (int i = tid; i < 19 * VXB_DTILE_PITCH; i += VXB_THREADS)
+			for (int i = tid; i < 19 * VXB_DTILE_PITCH; i += VXB_VB_THREADS)
 			{
 				const int y = i / VXB_DTILE_PITCH, x = i % VXB_DTILE_PITCH;
 				signed char* p = s.dist + y * VXB_DTILE_PITCH + x;
 				for (int q = lastZ + 1; q < 19; ++q) p[q * 19 * VXB_DTILE_PITCH] = p[lastZ * 19 * VXB_DTILE_PITCH];
 			}
-			for (int i = tid; i < 17 * 17; i += VXB_THREADS)
+			if (MAT_TILES) for (int i = tid; i < 17 * 17; i += VXB_VB_THREADS)
 			{
 				const int y = i / 17, x = i % 17;
 				s.mat[(16 * 17 + y) * VXB_TILE_PITCH + x] = s.mat[(15 * 17 + y) * VXB_TILE_PITCH + x];
@@ -594,12 +605,14 @@ __global__ void __launch_bounds__(VXB_THREADS, 4) vxb_vertex_block_kernel(const 
 		}
 		__syncthreads();
 		VxbTileView g;
-		g.dist = s.dist; g.mat = s.mat; g.blend = s.blend; g.ox = bx * 16; g.oy = by * 16; g.oz = bz * 16; g.sx = sx; g.sy = sy; g.sz = sz;
-		for (unsigned j = tid; j < nverts; j += VXB_THREADS)
+		g.dist = s.dist; g.ox = bx * 16; g.oy = by * 16; g.oz = bz * 16; g.sx = sx; g.sy = sy; g.sz = sz;
+		if (MAT_TILES) { g.mat = s.mat; g.blend = s.blend; g.n = 0; }
+		else { g.mat = d.grid.mat; g.blend = d.grid.blend; g.n = d.n; }
+		for (unsigned j = tid; j < nverts; j += VXB_VB_THREADS)
 		{
-			const unsigned e = d.vlist[voff + j];
 			const unsigned ci = e >> 4; const int k = e & 15;
-			const uint4 crv = *reinterpret_cast<const uint4*>(&d.cellRecs[ci]);
+			if (j + VXB_VB_THREADS < nverts) e = d.vlist[voff + j + VXB_VB_THREADS]; // next round's entry, in flight during this one
+			const uint4 crv = staged ? s.cells[ci - cellBase] : *reinterpret_cast<const uint4*>(&d.cellRecs[ci]);
 			const int c = crv.x & 0xFFF;
 			const unsigned code = (crv.x >> 12) & 0xFF, zm = (crv.x >> 20) & 0xFF;
 			const int local[3] = { c & 15, (c >> 4) & 15, c >> 8 };
@@ -812,19 +825,31 @@ __global__ void __launch_bounds__(VXB_THREADS, 4) vxb_transition_kernel(const Vx
 		{
 			const int h = m >> 1, lim = d.n - 1;
 			const int origin[3] = { bx * 16 * m, by * 16 * m, bz * 16 * m };
-			for (int idx = tid; idx < 6 * 1089; idx += VXB_THREADS)
+			// four independent loads in flight per thread; faces without a neighbour block are staged too (clamped reads,
+			// never used: T1 skips them)
+			for (int idx0 = tid; idx0 < 6 * 1089; idx0 += 4 * VXB_THREADS)
 			{
-				const int face = idx / 1089, r = idx - face * 1089;
-				int axis, ua, va;
-				vxb_face_axes(face, axis, ua, va);
-				const int bc = (axis == 0) ? bx : (axis == 1 ? by : bz);
-				if (face < 3 ? (bc == 0) : (bc == nb - 1)) continue; // neighbour block outside the grid (:1829-1835)
-				const int j = r / 33, i = r - j * 33;
-				int p[3];
-				p[axis] = origin[axis] + ((face >= 3) ? 16 * m : 0);
-				p[ua] = origin[ua] + i * h;
-				p[va] = origin[va] + j * h;
-				s.face[face][r] = g.dist[((size_t)min(p[2], lim) * d.n + min(p[1], lim)) * d.n + min(p[0], lim)];
+				signed char v[4];
+#pragma unroll
+				for (int u = 0; u < 4; ++u)
+				{
+					const int idx = min(idx0 + u * VXB_THREADS, 6 * 1089 - 1);
+					const int face = idx / 1089, r = idx - face * 1089;
+					const int f3 = face >= 3 ? face - 3 : face;
+					const int j = r / 33, i = r - j * 33;
+					const int off = (face >= 3) ? 16 * m : 0, cu = i * h, cv = j * h;
+					// vxb_face_axes: f3 = 0: axis z, (u, v) = (x, y); 1: axis y, (x, z); 2: axis x, (y, z)
+					const int px = origin[0] + (f3 == 2 ? off : cu);
+					const int py = origin[1] + (f3 == 1 ? off : (f3 == 0 ? cv : cu));
+					const int pz = origin[2] + (f3 == 0 ? off : cv);
+					v[u] = g.dist[((size_t)min(pz, lim) * d.n + min(py, lim)) * d.n + min(px, lim)];
+				}
+#pragma unroll
+				for (int u = 0; u < 4; ++u)
+				{
+					const int idx = idx0 + u * VXB_THREADS;
+					if (idx < 6 * 1089) (&s.face[0][0])[(idx / 1089) * 1092 + (idx % 1089)] = v[u];
+				}
 			}
 		}
 		__syncthreads();
