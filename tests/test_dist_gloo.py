@@ -28,7 +28,7 @@ r.barrier()
 fake_ms = 10.0 + 5.0 * r.rank                      # rank 1 is "slower": the job time is the max over ranks
 ms = r.max_over_ranks(fake_ms)
 total_verts = r.sum_over_ranks(verts)
-print("RESULT rank=%d ms=%.1f tile_digest=%s verts=%d total=%d mvox=%.3f" % (r.rank, ms, digest[:12], verts, total_verts, whole_job_throughput(n, r.world, ms)))
+os.write(1, ("RESULT rank=%d ms=%.1f tile_digest=%s verts=%d total=%d mvox=%.3f\n" % (r.rank, ms, digest[:12], verts, total_verts, whole_job_throughput(n, r.world, ms))).encode())  # one atomic write per rank
 r.close()
 '''
 
@@ -91,7 +91,7 @@ assert len(allrec) == 7 and list(allrec["level"]) == sorted(allrec["level"])
 keys = list(zip(allrec["level"].tolist(), allrec["coord_id"].tolist()))
 assert keys == sorted(keys)
 assert owner.tolist() == [0, 0, 1, 1, 0, 1, 1], owner.tolist()
-print("RESULT rank=%d slab=%d-%d split=%d blocks=%d" % (r.rank, z0, z1, split_level(n, r.world), len(allrec)))
+os.write(1, ("RESULT rank=%d slab=%d-%d split=%d blocks=%d\n" % (r.rank, z0, z1, split_level(n, r.world), len(allrec))).encode())
 r.close()
 '''
 
