@@ -63,7 +63,7 @@ def build_tables(force=False):
 
 
 def build_cuda(force=False, verbose=False):
-    srcs = [os.path.join(CSRC, n) for n in ("vxb200.cu", "vxb_kernels.cuh", "vxb_cell.h")] + \
+    srcs = [os.path.join(CSRC, n) for n in os.listdir(CSRC) if n.endswith((".cu", ".cuh", ".h"))] + \
            [TABLES, os.path.join(REPO, "include", "vxb200.h")]
     if not force and _newer(LIBVXB, srcs):
         return

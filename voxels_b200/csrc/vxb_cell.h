@@ -469,14 +469,14 @@ struct VxbTransVertexDesc
 	bool endpoint;
 };
 
-VXB_FN VxbTransVertexDesc vxb_transition_vertex_desc(unsigned vd, const signed char v[13], const unsigned char* cornerData)
+// a, b = the samples at the vertex's edge endpoints v0 = (vd >> 4) & 15, v1 = vd & 15
+VXB_FN VxbTransVertexDesc vxb_transition_vertex_desc_ab(unsigned vd, int a, int b, const unsigned char* cornerData)
 {
 	VxbTransVertexDesc d;
 	d.v0 = (vd >> 4) & 0xF;
 	d.v1 = vd & 0xF;
 	d.dir = (vd >> 12) & 0xF;
 	d.slot = (vd >> 8) & 0xF;
-	const int a = v[d.v0], b = v[d.v1];
 	d.endpoint = (a == 0) || (b == 0); // t in {0, 256}, see vxb_zero_mask
 	if (d.endpoint)
 	{
@@ -487,6 +487,11 @@ VXB_FN VxbTransVertexDesc vxb_transition_vertex_desc(unsigned vd, const signed c
 	}
 	else d.t = vxb_fixed_t(a, b); // :1942
 	return d;
+}
+
+VXB_FN VxbTransVertexDesc vxb_transition_vertex_desc(unsigned vd, const signed char v[13], const unsigned char* cornerData)
+{
+	return vxb_transition_vertex_desc_ab(vd, v[(vd >> 4) & 0xF], v[vd & 0xF], cornerData);
 }
 
 // New transition vertex (:1980-2092).  local = low-res cell's local coords, base = its base.

@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(VXB_THREADS, 4) vxb_classify_kernel(const __gr
 	const int tid = threadIdx.x;
 	const int m = 1 << level, nb = d.n / 16 / m;
 	const bool midLevel = level > 0 && level != d.lastLevel;
-	unsigned phase[2] = { 0, 0 };
+	unsigned phaseBits = 0; // mbarrier phase of each tile buffer, bit = buffer
 	VxbVoteSource voteSrc;
 	if (level > 0) voteSrc = vxb_vote_source(d, level);
 	if (tid == 0) { vxb_mbar_init(&s.mbar[0], 1); vxb_mbar_init(&s.mbar[1], 1); }
@@ -101,7 +101,9 @@ __global__ void __launch_bounds__(VXB_THREADS, 4) vxb_classify_kernel(const __gr
 		const unsigned coordId = worklist[item];
 		const int bx = coordId % nb, by = (coordId / nb) % nb, bz = coordId / (nb * nb);
 		signed char* const tile = s.tiles[buf];
-		vxb_tile_complete(tile, &s.mbar[buf], phase[buf], d, level, bx, by, bz);
+		unsigned ph = (phaseBits >> buf) & 1u;
+		vxb_tile_complete(tile, &s.mbar[buf], ph, d, level, bx, by, bz);
+		phaseBits = (phaseBits & ~(1u << buf)) | (ph << buf);
 		__syncthreads();
 
 		vxb_classify_bits(tile, s.rowSign, s.nt32);
@@ -151,9 +153,8 @@ __global__ void __launch_bounds__(VXB_THREADS, 4) vxb_classify_kernel(const __gr
 				{
 					// material of every non-trivial cell (:1568): majority vote of its 8 children, stored in the level's page
 					const int base[3] = { (bx * 16 + (c & 15)) * m, (by * 16 + ((c >> 4) & 15)) * m, (bz * 16 + (c >> 8)) * m };
-					unsigned matId, matBlend;
-					if (vxb_vote_cell(voteSrc, base[0], base[1], base[2], matId, matBlend))
-						d.cachePages[level][(size_t)coordId * 4096 + c] = (unsigned short)(matId | (matBlend << 8));
+					const int vote = vxb_vote_cell(voteSrc, base[0], base[1], base[2]);
+					if (vote >= 0) d.cachePages[level][(size_t)coordId * 4096 + c] = (unsigned short)vote;
 				}
 			}
 			__syncthreads();
@@ -188,12 +189,12 @@ __global__ void __launch_bounds__(VXB_THREADS, 4) vxb_classify_kernel(const __gr
 					vxb_face_axes(face, axis, ua, va);
 					const int bc = (axis == 0) ? bx : (axis == 1 ? by : bz);
 					if (face < 3 ? (bc == 0) : (bc == nb - 1)) continue; // neighbour block outside the grid (:1829-1835)
-					int local[3];
-					local[axis] = (face >= 3) ? 15 : 0; local[ua] = col; local[va] = row;
+					// local[axis] = edge, local[ua] = col, local[va] = row, written with selects (an indexed array would be local memory)
+					const int edge = (face >= 3) ? 15 : 0;
+					const int local[3] = { axis == 0 ? edge : col, axis == 1 ? edge : (axis == 2 ? row : col), axis == 2 ? edge : row };
 					const int base[3] = { (bx * 16 + local[0]) * m, (by * 16 + local[1]) * m, (bz * 16 + local[2]) * m };
-					unsigned matId, matBlend;
-					if (vxb_vote_cell(voteSrc, base[0], base[1], base[2], matId, matBlend))
-						d.cachePages[level][(size_t)coordId * 4096 + local[2] * 256 + local[1] * 16 + local[0]] = (unsigned short)(matId | (matBlend << 8));
+					const int vote = vxb_vote_cell(voteSrc, base[0], base[1], base[2]);
+					if (vote >= 0) d.cachePages[level][(size_t)coordId * 4096 + local[2] * 256 + local[1] * 16 + local[0]] = (unsigned short)vote;
 				}
 			}
 		}
@@ -664,18 +665,34 @@ __global__ void __launch_bounds__(VXB_THREADS) vxb_triangle_kernel(const VxbDev 
 		const unsigned char* cd = &vxbGRegularCellData[cls * 16];
 		const unsigned geo = cd[0];
 		const unsigned myMat = crv.y & 0xFF, newMask = crv.z & 0xFFF;
-		unsigned vids[12];
+		// block-local vertex ids (< 49152) as 16-bit halves of six registers: a table-indexed array would live in local memory
+		unsigned w[6] = { 0u, 0u, 0u, 0u, 0u, 0u };
 		unsigned nextNew = crv.w & 0xFFFF;
-		for (int k = 0; k < (int)(geo >> 4); ++k)
+		const int nv = (int)(geo >> 4);
+#pragma unroll
+		for (int k = 0; k < 12; ++k)
 		{
-			if ((newMask >> k) & 1u) { vids[k] = nextNew++; continue; }
-			const VxbVertexDesc vd = vxb_regular_vertex_desc_lite(vxbGRegularVertexData[code * 12 + k], zm);
-			const int oc = c - (vd.dir & 1) - ((vd.dir >> 1) & 1) * 16 - ((vd.dir >> 2) & 1) * 256; // reused => the owner exists
-			const unsigned oi = vxb_rank_of(nt32, wpre, oc);
-			const uint4 orec = *reinterpret_cast<const uint4*>(&d.cellRecs[cellBase + oi]);
-			const unsigned ok = (orec.y >> (16 + 4 * vd.slot)) & 0xF;
-			vids[k] = (orec.w & 0xFFFF) + __popc(orec.z & 0xFFFu & ((1u << ok) - 1u));
+			if (k < nv) // (no break: the loop must unroll completely for w[] to stay in registers)
+			{
+				unsigned vid;
+				if ((newMask >> k) & 1u) vid = nextNew++;
+				else
+				{
+					const VxbVertexDesc vd = vxb_regular_vertex_desc_lite(vxbGRegularVertexData[code * 12 + k], zm);
+					const int oc = c - (vd.dir & 1) - ((vd.dir >> 1) & 1) * 16 - ((vd.dir >> 2) & 1) * 256; // reused => the owner exists
+					const unsigned oi = vxb_rank_of(nt32, wpre, oc);
+					const uint4 orec = *reinterpret_cast<const uint4*>(&d.cellRecs[cellBase + oi]);
+					const unsigned ok = (orec.y >> (16 + 4 * vd.slot)) & 0xF;
+					vid = (orec.w & 0xFFFF) + __popc(orec.z & 0xFFFu & ((1u << ok) - 1u));
+				}
+				w[k >> 1] |= vid << ((k & 1) * 16);
+			}
 		}
+		auto vidOf = [&](unsigned k) -> unsigned {
+			const unsigned i = k >> 1;
+			const unsigned pair = i == 0 ? w[0] : i == 1 ? w[1] : i == 2 ? w[2] : i == 3 ? w[3] : i == 4 ? w[4] : w[5];
+			return (k & 1u) ? (pair >> 16) : (pair & 0xFFFFu);
+		};
 		(void)mask; (void)myMat;
 		unsigned* out = d.idx + ioff + (crv.w >> 16) * 3;
 		unsigned removed = 0;
@@ -685,7 +702,7 @@ __global__ void __launch_bounds__(VXB_THREADS) vxb_triangle_kernel(const VxbDev 
 		const bool cannotDegenerate = (br->packed >> 28) == 0u && zm == 0u;
 		for (unsigned tr = 0; tr < (geo & 0xF); ++tr, out += 3)
 		{
-			const unsigned a = vids[cd[1 + tr * 3]], b = vids[cd[2 + tr * 3]], cc = vids[cd[3 + tr * 3]];
+			const unsigned a = vidOf(cd[1 + tr * 3]), b = vidOf(cd[2 + tr * 3]), cc = vidOf(cd[3 + tr * 3]);
 			bool kept = true;
 			if (!cannotDegenerate)
 			{
@@ -801,6 +818,19 @@ __device__ __forceinline__ void vxb_face_cell_samples(const signed char* lattice
 	v[9] = v[0]; v[10] = v[2]; v[11] = v[6]; v[12] = v[8];
 }
 
+// sample i (0..12) of a transition cell straight from the staged lattice (p = the cell's first sample): no per-thread
+// sample array, whose table-driven indexing would live in local memory
+__device__ __forceinline__ int vxb_lattice_sample(const signed char* p, int i)
+{
+	const int off = (i < 9) ? (i / 3) * 33 + (i % 3) : ((i - 9) & 1) * 2 + ((i - 9) >> 1) * 66;
+	return p[off];
+}
+
+__device__ __forceinline__ VxbTransVertexDesc vxb_lattice_vertex_desc(unsigned vd, const signed char* p)
+{
+	return vxb_transition_vertex_desc_ab(vd, vxb_lattice_sample(p, (vd >> 4) & 0xF), vxb_lattice_sample(p, vd & 0xF), vxbGTransitionCornerData);
+}
+
 __global__ void __launch_bounds__(VXB_THREADS, 4) vxb_transition_kernel(const VxbDev d)
 {
 	extern __shared__ __align__(128) unsigned char smemRaw[];
@@ -901,13 +931,12 @@ __global__ void __launch_bounds__(VXB_THREADS, 4) vxb_transition_kernel(const Vx
 				vxb_face_axes(face, axis, ua, va);
 				int local[3];
 				local[axis] = (face >= 3) ? 15 : 0; local[ua] = col; local[va] = row;
-				signed char v[13];
-				vxb_face_cell_samples(s.face[face], row, col, v);
+				const signed char* lat = s.face[face] + (2 * row) * 33 + 2 * col;
 				unsigned long long slots = ~0ull;
 				const int nv = vxbGTransitionCellData[(vxbGTransitionCellClass[code] & 0x7F) * 40] >> 4;
 				for (int k = 0; k < nv; ++k)
 				{
-					const VxbTransVertexDesc td = vxb_transition_vertex_desc(vxbGTransitionVertexData[code * 12 + k], v, vxbGTransitionCornerData);
+					const VxbTransVertexDesc td = vxb_lattice_vertex_desc(vxbGTransitionVertexData[code * 12 + k], lat);
 					if (td.dir == 8) slots = (slots & ~(0xFull << (4 * td.slot))) | ((unsigned long long)k << (4 * td.slot)); // stored only when no reuse was attempted (:2097)
 				}
 				s.slots[i] = slots;
@@ -919,8 +948,7 @@ __global__ void __launch_bounds__(VXB_THREADS, 4) vxb_transition_kernel(const Vx
 			{
 				const int ci = s.cell[i], face = ci >> 8, row = (ci >> 4) & 15, col = ci & 15;
 				const unsigned code = s.code[ci];
-				signed char v[13];
-				vxb_face_cell_samples(s.face[face], row, col, v);
+				const signed char* lat = s.face[face] + (2 * row) * 33 + 2 * col;
 				const unsigned geo = vxbGTransitionCellData[(vxbGTransitionCellClass[code] & 0x7F) * 40];
 				const unsigned rowBits = (s.nt[ci >> 5] >> (ci & 16)) & 0xFFFFu;
 				const int mask = ((row > 0) ? 2 : 0) | ((rowBits & ((1u << col) - 1u)) ? 1 : 0);
@@ -928,7 +956,7 @@ __global__ void __launch_bounds__(VXB_THREADS, 4) vxb_transition_kernel(const Vx
 				unsigned newMask = 0;
 				for (int k = 0; k < (int)(geo >> 4); ++k)
 				{
-					const VxbTransVertexDesc td = vxb_transition_vertex_desc(vxbGTransitionVertexData[code * 12 + k], v, vxbGTransitionCornerData);
+					const VxbTransVertexDesc td = vxb_lattice_vertex_desc(vxbGTransitionVertexData[code * 12 + k], lat);
 					bool isNew = true;
 					if ((td.dir & mask) == td.dir)
 					{
@@ -987,8 +1015,7 @@ __global__ void __launch_bounds__(VXB_THREADS, 4) vxb_transition_kernel(const Vx
 				const unsigned tvoff = s.tvoff[face], tioff = s.tioff[face];
 				if ((unsigned long long)tvoff + s.tvcount[face] > d.tvcap || (unsigned long long)tioff + s.ticount[face] > d.ticap) continue;
 				const unsigned code = s.code[ci];
-				signed char v[13];
-				vxb_face_cell_samples(s.face[face], row, col, v);
+				const signed char* lat = s.face[face] + (2 * row) * 33 + 2 * col;
 				const unsigned cls = vxbGTransitionCellClass[code];
 				const unsigned char* cd = &vxbGTransitionCellData[(cls & 0x7F) * 40];
 				const int nv = cd[0] >> 4, ntri = cd[0] & 0xF;
@@ -1001,12 +1028,12 @@ __global__ void __launch_bounds__(VXB_THREADS, 4) vxb_transition_kernel(const Vx
 					if ((newMask >> k) & 1u)
 					{
 						// the vertex itself is computed by vxb_transition_vertex_kernel, one thread per entry
-						d.tvlist[tvoff + nextNew] = make_uint2(slot, ((unsigned)face << 12) | ((unsigned)(ci & 255) << 4) | (unsigned)k);
+						d.tvlist[tvoff + nextNew] = make_uint2(slot, (code << 16) | ((unsigned)face << 12) | ((unsigned)(ci & 255) << 4) | (unsigned)k);
 						vids[k] = nextNew++;
 					}
 					else
 					{
-						const VxbTransVertexDesc td = vxb_transition_vertex_desc(vxbGTransitionVertexData[code * 12 + k], v, vxbGTransitionCornerData);
+						const VxbTransVertexDesc td = vxb_lattice_vertex_desc(vxbGTransitionVertexData[code * 12 + k], lat);
 						const int oc = ci - ((td.dir >> 1) & 1) * 16 - (td.dir & 1);
 						const unsigned oi = s.pre[oc >> 5] + __popc(s.nt[oc >> 5] & ((1u << (oc & 31)) - 1u));
 						const unsigned ok = (unsigned)((s.slots[oi] >> (4 * td.slot)) & 0xF);
@@ -1050,17 +1077,20 @@ __global__ void __launch_bounds__(VXB_THREADS) vxb_transition_vertex_kernel(cons
 			const unsigned coordId = packed & 0x0FFFFFFFu;
 			const int m = 1 << level, nb = d.n / 16 / m;
 			const int bx = coordId % nb, by = (coordId / nb) % nb, bz = coordId / (nb * nb);
-			const int face = (int)(e.y >> 12), cell = (int)((e.y >> 4) & 0xFF), k = (int)(e.y & 15);
+			const int face = (int)((e.y >> 12) & 7), cell = (int)((e.y >> 4) & 0xFF), k = (int)(e.y & 15);
+			const unsigned code = e.y >> 16; // the cell's 9-bit case code, known to vxb_transition_kernel
 			const int row = cell >> 4, col = cell & 15;
 			int axis, ua, va;
 			vxb_face_axes(face, axis, ua, va);
 			int local[3];
 			local[axis] = (face >= 3) ? 15 : 0; local[ua] = col; local[va] = row;
 			const int base[3] = { (bx * 16 + local[0]) * m, (by * 16 + local[1]) * m, (bz * 16 + local[2]) * m };
-			signed char v[13];
-			vxb_transition_samples(g, face, level, base, v);
-			const unsigned code = vxb_transition_case_code(v);
-			const VxbTransVertexDesc td = vxb_transition_vertex_desc(vxbGTransitionVertexData[code * 12 + k], v, vxbGTransitionCornerData);
+			// only the two samples at the ends of the vertex's edge are needed
+			const unsigned vd = vxbGTransitionVertexData[code * 12 + k];
+			int pa[3], pb[3];
+			vxb_transition_sample_pos(face, level, base, (vd >> 4) & 0xF, pa);
+			vxb_transition_sample_pos(face, level, base, vd & 0xF, pb);
+			const VxbTransVertexDesc td = vxb_transition_vertex_desc_ab(vd, vxb_dist(g, pa[0], pa[1], pa[2]), vxb_dist(g, pb[0], pb[1], pb[2]), vxbGTransitionCornerData);
 			const unsigned ent = d.cachePages[level][(size_t)coordId * 4096 + local[2] * 256 + local[1] * 16 + local[0]];
 			const unsigned matId = ent & 0xFF, matBlend = ent >> 8;
 			VxbRawVertex rv;

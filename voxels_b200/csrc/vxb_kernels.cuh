@@ -516,7 +516,9 @@ __device__ __forceinline__ VxbVoteSource vxb_vote_source(const VxbDev& d, int le
 	return v;
 }
 
-__device__ __noinline__ bool vxb_vote_cell(const VxbVoteSource d, const int bx0, const int by0, const int bz0, unsigned& id, unsigned& blend)
+// returns id | blend << 8, or -1 when no child carries a material (results in a register: a noinline callee would
+// write reference outputs through local memory)
+__device__ __noinline__ int vxb_vote_cell(const VxbVoteSource d, const int bx0, const int by0, const int bz0)
 {
 	const int level = d.level;
 	const int base[3] = { bx0, by0, bz0 };
@@ -527,12 +529,12 @@ __device__ __noinline__ bool vxb_vote_cell(const VxbVoteSource d, const int bx0,
 	unsigned cid[8], cbl[8]; // children, x fastest (:773-775); fully unrolled below so they live in registers
 	if (level == 1)
 	{
-		if (!d.valid[bid]) return false;
+		if (!d.valid[bid]) return -1;
 		const unsigned short* rows = reinterpret_cast<const unsigned short*>(static_cast<const unsigned int*>(d.pages) + bid * 128); // 16 bits per (z,y) row
 		const unsigned r00 = (rows[lz * 16 + ly] >> lx) & 3u, r01 = (rows[lz * 16 + ly + 1] >> lx) & 3u;
 		const unsigned r10 = (rows[(lz + 1) * 16 + ly] >> lx) & 3u, r11 = (rows[(lz + 1) * 16 + ly + 1] >> lx) & 3u;
 		const unsigned bits = r00 | (r01 << 2) | (r10 << 4) | (r11 << 6); // child q = x + 2y + 4z
-		if (!bits) return false;
+		if (!bits) return -1;
 #pragma unroll
 		for (int q = 0; q < 8; ++q)
 		{
@@ -546,11 +548,11 @@ __device__ __noinline__ bool vxb_vote_cell(const VxbVoteSource d, const int bx0,
 	}
 	else
 	{
-		if (!d.valid[bid]) return false;
+		if (!d.valid[bid]) return -1;
 		const unsigned int* page = reinterpret_cast<const unsigned int*>(static_cast<const unsigned short*>(d.pages) + bid * 4096); // 2 cells per word
 		const int o = (lz * 256 + ly * 16 + lx) >> 1;
 		const unsigned e0 = page[o], e1 = page[o + 8], e2 = page[o + 128], e3 = page[o + 136];
-		if ((e0 & e1 & e2 & e3 & 0x00FF00FFu) == 0x00FF00FFu) return false; // all eight children EMPTY_MATERIAL
+		if ((e0 & e1 & e2 & e3 & 0x00FF00FFu) == 0x00FF00FFu) return -1; // all eight children EMPTY_MATERIAL
 		cid[0] = e0 & 0xFF; cbl[0] = (e0 >> 8) & 0xFF; cid[1] = (e0 >> 16) & 0xFF; cbl[1] = e0 >> 24;
 		cid[2] = e1 & 0xFF; cbl[2] = (e1 >> 8) & 0xFF; cid[3] = (e1 >> 16) & 0xFF; cbl[3] = e1 >> 24;
 		cid[4] = e2 & 0xFF; cbl[4] = (e2 >> 8) & 0xFF; cid[5] = (e2 >> 16) & 0xFF; cbl[5] = e2 >> 24;
@@ -570,10 +572,8 @@ __device__ __noinline__ bool vxb_vote_cell(const VxbVoteSource d, const int bx0,
 		for (int p = q; p < 8; ++p) if (cid[p] == cid[q]) { ++cnt; bsum += cbl[p]; }
 		if (first && cnt > bestCount) { bestCount = cnt; bestId = cid[q]; bestBlend = bsum; }
 	}
-	if (!bestCount) return false;
-	id = bestId;
-	blend = (bestBlend / (unsigned)bestCount) & 0xFFu;
-	return true;
+	if (!bestCount) return -1;
+	return (int)(bestId | (((bestBlend / (unsigned)bestCount) & 0xFFu) << 8));
 }
 
 struct VxbDecision { bool isNew, quirkV0; unsigned ownerIdx; int ok; };
