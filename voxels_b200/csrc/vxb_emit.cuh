@@ -182,13 +182,26 @@ __global__ void __launch_bounds__(VXB_THREADS, 4) vxb_classify_kernel(const __gr
 					if (tid == 0) { d.cacheValid[level][coordId] = 1; s.pageReady = 1; }
 				}
 				const int row = tid >> 4, col = tid & 15;
-#pragma unroll 1
+				// most face cells have no child with a material: test all six faces first (independent loads, all in flight
+				// together), then run the vote only where it can succeed
+				unsigned candidates = 0;
+#pragma unroll
 				for (int face = 0; face < 6; ++face)
 				{
 					int axis, ua, va;
 					vxb_face_axes(face, axis, ua, va);
 					const int bc = (axis == 0) ? bx : (axis == 1 ? by : bz);
-					if (face < 3 ? (bc == 0) : (bc == nb - 1)) continue; // neighbour block outside the grid (:1829-1835)
+					const bool outside = face < 3 ? (bc == 0) : (bc == nb - 1); // neighbour block outside the grid (:1829-1835)
+					const int edge = (face >= 3) ? 15 : 0;
+					const int lx = axis == 0 ? edge : col, ly = axis == 1 ? edge : (axis == 2 ? row : col), lz = axis == 2 ? edge : row;
+					if (vxb_vote_candidate(voteSrc, (bx * 16 + lx) * m, (by * 16 + ly) * m, (bz * 16 + lz) * m) && !outside) candidates |= 1u << face;
+				}
+				while (candidates)
+				{
+					const int face = __ffs(candidates) - 1;
+					candidates &= candidates - 1;
+					int axis, ua, va;
+					vxb_face_axes(face, axis, ua, va);
 					// local[axis] = edge, local[ua] = col, local[va] = row, written with selects (an indexed array would be local memory)
 					const int edge = (face >= 3) ? 15 : 0;
 					const int local[3] = { axis == 0 ? edge : col, axis == 1 ? edge : (axis == 2 ? row : col), axis == 2 ? edge : row };

@@ -516,6 +516,28 @@ __device__ __forceinline__ VxbVoteSource vxb_vote_source(const VxbDev& d, int le
 	return v;
 }
 
+// Could the vote of this cell succeed?  The first tests of vxb_vote_cell as independent loads (no early exit, no call), so
+// that a caller can have the loads of several cells in flight at once.  Pages of blocks that were never written are
+// readable (the page space is reserved for every block) and are masked by the valid flag.
+__device__ __forceinline__ bool vxb_vote_candidate(const VxbVoteSource& d, const int bx0, const int by0, const int bz0)
+{
+	const int sh = d.level - 1, cnb = (d.n / 16) >> sh;
+	const int cx = bx0 >> sh, cy = by0 >> sh, cz = bz0 >> sh;
+	const size_t bid = ((size_t)(cz >> 4) * cnb + (cy >> 4)) * cnb + (cx >> 4);
+	const int lx = cx & 15, ly = cy & 15, lz = cz & 15;
+	const unsigned valid = d.valid[bid];
+	if (d.level == 1)
+	{
+		const unsigned short* rows = reinterpret_cast<const unsigned short*>(static_cast<const unsigned int*>(d.pages) + bid * 128);
+		const unsigned r = (unsigned)rows[lz * 16 + ly] | rows[lz * 16 + ly + 1] | rows[(lz + 1) * 16 + ly] | rows[(lz + 1) * 16 + ly + 1];
+		return valid != 0u && ((r >> lx) & 3u) != 0u;
+	}
+	const unsigned int* page = reinterpret_cast<const unsigned int*>(static_cast<const unsigned short*>(d.pages) + bid * 4096);
+	const int o = (lz * 256 + ly * 16 + lx) >> 1;
+	const unsigned all = page[o] & page[o + 8] & page[o + 128] & page[o + 136];
+	return valid != 0u && (all & 0x00FF00FFu) != 0x00FF00FFu;
+}
+
 // returns id | blend << 8, or -1 when no child carries a material (results in a register: a noinline callee would
 // write reference outputs through local memory)
 __device__ __noinline__ int vxb_vote_cell(const VxbVoteSource d, const int bx0, const int by0, const int bz0)
