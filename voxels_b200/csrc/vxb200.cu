@@ -102,6 +102,11 @@ struct vxb_context
 	DevBuf<unsigned int> updCoords;
 	bool directoryFetched = false;
 	uint32_t shardLaunches = 0;
+	// the launch sequence of a full run as a CUDA graph, re-instantiated when any kernel argument changes
+	cudaGraphExec_t graphExec = nullptr;
+	std::vector<unsigned char> graphKey;
+	uint32_t graphLaunches = 0;
+	bool graphDisabled = false;
 	// the cube of a sharded run (vxb_cube_*): one virtual range per volume, this rank's slab local, peers' slabs imported
 	struct Cube
 	{
@@ -481,6 +486,7 @@ int vxb_create(int device, vxb_context** out)
 	ctx->encodeTiled = reinterpret_cast<EncodeTiledFn>(fn);
 
 	ctx->vbMatTiles = getenv("VXB200_VB_MAT_TILES") != nullptr;
+	ctx->graphDisabled = getenv("VXB200_NO_GRAPH") != nullptr; // plain launches (debugging, A/B timing)
 	ctx->vbSmem = ctx->vbMatTiles ? sizeof(VxbVertexBlockSmem) : offsetof(VxbVertexBlockSmem, mat);
 	struct KernelSetup { const void* fn; size_t smem; int* grid; const char* name; int threads; };
 	const KernelSetup setups[5] = {
@@ -512,6 +518,7 @@ void vxb_destroy(vxb_context* ctx)
 	cudaSetDevice(ctx->device);
 	if (ctx->stream) cudaStreamSynchronize(ctx->stream);
 	if (ctx->stream2) cudaStreamSynchronize(ctx->stream2);
+	if (ctx->graphExec) cudaGraphExecDestroy(ctx->graphExec);
 	releaseCube(ctx);
 	ctx->volDist.release(); ctx->volMat.release(); ctx->volBlend.release(); ctx->staging.release(); ctx->packOffsets.release(); ctx->updCoords.release(); ctx->lattice1.release();
 	ctx->scanFlags.release(); ctx->blockInfo.release(); ctx->consPages.release(); ctx->validFlags.release();
@@ -848,113 +855,162 @@ static int runPolygonize(vxb_context* ctx, uint32_t maxLevels, uint32_t flags, c
 		KernelTimer timer{ ctx, kernelTimes };
 		uint32_t launches = 0;
 		for (int k = 0; k < 8; ++k) ctx->kindLaunches[k] = 0;
-		if (phase != 2)
+		if (phase != 2) VXB_CUDA(ctx, cudaEventRecord(ctx->evBegin, ctx->stream));
+		// everything between the two timing events: memsets, kernels, the fork/join of the two streams
+		auto enqueue = [&]() -> int
 		{
-			VXB_CUDA(ctx, cudaEventRecord(ctx->evBegin, ctx->stream));
-			VXB_CUDA(ctx, cudaMemsetAsync(ctx->counters.p, 0, sizeof(VxbCounters), ctx->stream));
-			if (!incremental) VXB_CUDA(ctx, cudaMemsetAsync(ctx->validFlags.p, 0, validBytes, ctx->stream)); // incremental runs keep the caches (:362-364)
-			const size_t layer0 = (region && !incremental) ? (size_t)region->scanLayer0 : 0, layer1 = (region && !incremental) ? (size_t)region->scanLayer1 : nb0;
-			const dim3 grid((unsigned)((nb0 + 7) / 8), (unsigned)nb0, (unsigned)(layer1 - layer0));
-			timer.begin(0);
-			vxb_scan_kernel<<<grid, VXB_THREADS, 0, ctx->stream>>>(ctx->dDist, (int)n, ctx->scanFlags.p, ctx->haveLattice1 ? ctx->lattice1.p : nullptr, (int)layer0);
-			timer.end(); ++launches; ++ctx->kindLaunches[0];
-			const size_t first = layer0 * nb0 * nb0, last = layer1 * nb0 * nb0;
-			const unsigned g2 = (unsigned)std::min<size_t>((last - first + 255) / 256, (size_t)ctx->smCount * 8);
-			timer.begin(1);
-			vxb_block_info_kernel<<<g2, 256, 0, ctx->stream>>>(ctx->dDist, (int)n, ctx->scanFlags.p, ctx->blockInfo.p, first, last);
-			timer.end(); ++launches; ++ctx->kindLaunches[1];
-		}
-		const unsigned flatGrid = (unsigned)ctx->smCount * 8;
-		auto classifyLevel = [&](int l, cudaStream_t st) {
-			const size_t b = region ? region->count[l] : blocksAtLevel(n, l);
-			if (!b) return;
-			const unsigned gs = (unsigned)std::min<size_t>((b + 255) / 256, (size_t)ctx->smCount * 8);
-			timer.begin(1);
-			vxb_select_kernel<<<gs, 256, 0, st>>>(dev, l);
-			timer.end(); ++launches; ++ctx->kindLaunches[1];
-			timer.begin(2);
-			vxb_classify_kernel<<<(unsigned)std::min<size_t>(b, ctx->gridClassify), VXB_THREADS, sizeof(VxbClassifySmem), st>>>(ctx->tmap, ctx->tmap1, dev, l);
-			timer.end(); ++launches; ++ctx->kindLaunches[2];
-		};
-		auto decideGroup = [&](int group, cudaStream_t st) {
-			timer.begin(3);
-			vxb_decide_kernel<1024, 0><<<ctx->gridDecideSmall, VXB_THREADS, sizeof(VxbDecideSmemSmall), st>>>(ctx->tmap, ctx->tmap1, dev, group);
-			vxb_decide_kernel<4096, 1><<<ctx->gridDecideBig, VXB_THREADS, sizeof(VxbDecideSmemBig), st>>>(ctx->tmap, ctx->tmap1, dev, group);
-			timer.end(); launches += 2; ctx->kindLaunches[3] += 2;
-		};
-		auto flatGroup = [&](int part, cudaStream_t st) {
-			timer.begin(4);
-			if (part == 0 && ctx->vbMatTiles) vxb_vertex_block_kernel<true><<<ctx->gridVertexBlock, VXB_VB_THREADS, ctx->vbSmem, st>>>(ctx->tmapDist19, ctx->tmapMat, ctx->tmapBlend, dev);
-			else if (part == 0) vxb_vertex_block_kernel<false><<<ctx->gridVertexBlock, VXB_VB_THREADS, ctx->vbSmem, st>>>(ctx->tmapDist19, ctx->tmapMat, ctx->tmapBlend, dev);
-			else vxb_vertex_kernel<<<flatGrid, VXB_THREADS, 0, st>>>(dev, part);
-			timer.end(); ++launches; ++ctx->kindLaunches[4];
-			timer.begin(5);
-			vxb_triangle_kernel<<<flatGrid, VXB_THREADS, 0, st>>>(dev, part);
-			timer.end(); ++launches; ++ctx->kindLaunches[5];
-		};
-		auto transitions = [&](cudaStream_t st) {
-			timer.begin(6);
-			if (dev.transitions)
+			if (phase != 2)
 			{
-				vxb_transition_kernel<<<ctx->gridTransition, VXB_THREADS, sizeof(VxbTransSmem), st>>>(dev);
-				vxb_transition_vertex_kernel<<<flatGrid, VXB_THREADS, 0, st>>>(dev);
-				launches += 2; ctx->kindLaunches[6] += 2;
+				VXB_CUDA(ctx, cudaMemsetAsync(ctx->counters.p, 0, sizeof(VxbCounters), ctx->stream));
+				if (!incremental) VXB_CUDA(ctx, cudaMemsetAsync(ctx->validFlags.p, 0, validBytes, ctx->stream)); // incremental runs keep the caches (:362-364)
+				const size_t layer0 = (region && !incremental) ? (size_t)region->scanLayer0 : 0, layer1 = (region && !incremental) ? (size_t)region->scanLayer1 : nb0;
+				const dim3 grid((unsigned)((nb0 + 7) / 8), (unsigned)nb0, (unsigned)(layer1 - layer0));
+				timer.begin(0);
+				vxb_scan_kernel<<<grid, VXB_THREADS, 0, ctx->stream>>>(ctx->dDist, (int)n, ctx->scanFlags.p, ctx->haveLattice1 ? ctx->lattice1.p : nullptr, (int)layer0);
+				timer.end(); ++launches; ++ctx->kindLaunches[0];
+				const size_t first = layer0 * nb0 * nb0, last = layer1 * nb0 * nb0;
+				const unsigned g2 = (unsigned)std::min<size_t>((last - first + 255) / 256, (size_t)ctx->smCount * 8);
+				timer.begin(1);
+				vxb_block_info_kernel<<<g2, 256, 0, ctx->stream>>>(ctx->dDist, (int)n, ctx->scanFlags.p, ctx->blockInfo.p, first, last);
+				timer.end(); ++launches; ++ctx->kindLaunches[1];
 			}
-			timer.end();
-		};
-		// Levels depend on each other only through vxb_classify_kernel, so with more than one level the work forks:
-		//   stream : level 0 -> decide -> vertices -> triangles
-		//   stream2: classify levels 1.. (a latency-bound chain of small launches) -> decide -> vertices -> triangles -> transitions
-		// and joins before vxb_finish_kernel.  Per-kernel timing (VXB_FLAG_KERNEL_TIMES) runs everything on one stream.
-		const bool fork = (computed > 1 && !kernelTimes) || phase == 2;
-		if (phase != 2) classifyLevel(0, ctx->stream);
-		if (phase == 1)
-		{
-			// sharded run, first half: the levels whose blocks nest in this rank's slab.  Nothing is read back: the caller
-			// exchanges the material pages of level splitLevel-1 on this stream (vxb_shard_exchange_info) and calls phase 2.
-			for (int l = 1; l < region->splitLevel && l < computed; ++l) classifyLevel(l, ctx->stream);
-			VXB_CUDA(ctx, cudaGetLastError());
-			// the exchange runs on the second stream (vxb_exchange_stream), ordered after this classification; in phase 2
-			// only the coarse levels wait for it, the vertices and triangles of the nested levels overlap it
-			VXB_CUDA(ctx, cudaEventRecord(ctx->evFork, ctx->stream));
-			VXB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->evFork, 0));
-			ctx->shardLaunches = launches;
+			const unsigned flatGrid = (unsigned)ctx->smCount * 8;
+			auto classifyLevel = [&](int l, cudaStream_t st) {
+				const size_t b = region ? region->count[l] : blocksAtLevel(n, l);
+				if (!b) return;
+				const unsigned gs = (unsigned)std::min<size_t>((b + 255) / 256, (size_t)ctx->smCount * 8);
+				timer.begin(1);
+				vxb_select_kernel<<<gs, 256, 0, st>>>(dev, l);
+				timer.end(); ++launches; ++ctx->kindLaunches[1];
+				timer.begin(2);
+				vxb_classify_kernel<<<(unsigned)std::min<size_t>(b, ctx->gridClassify), VXB_THREADS, sizeof(VxbClassifySmem), st>>>(ctx->tmap, ctx->tmap1, dev, l);
+				timer.end(); ++launches; ++ctx->kindLaunches[2];
+			};
+			auto decideGroup = [&](int group, cudaStream_t st) {
+				timer.begin(3);
+				vxb_decide_kernel<1024, 0><<<ctx->gridDecideSmall, VXB_THREADS, sizeof(VxbDecideSmemSmall), st>>>(ctx->tmap, ctx->tmap1, dev, group);
+				vxb_decide_kernel<4096, 1><<<ctx->gridDecideBig, VXB_THREADS, sizeof(VxbDecideSmemBig), st>>>(ctx->tmap, ctx->tmap1, dev, group);
+				timer.end(); launches += 2; ctx->kindLaunches[3] += 2;
+			};
+			auto flatGroup = [&](int part, cudaStream_t st) {
+				timer.begin(4);
+				if (part == 0 && ctx->vbMatTiles) vxb_vertex_block_kernel<true><<<ctx->gridVertexBlock, VXB_VB_THREADS, ctx->vbSmem, st>>>(ctx->tmapDist19, ctx->tmapMat, ctx->tmapBlend, dev);
+				else if (part == 0) vxb_vertex_block_kernel<false><<<ctx->gridVertexBlock, VXB_VB_THREADS, ctx->vbSmem, st>>>(ctx->tmapDist19, ctx->tmapMat, ctx->tmapBlend, dev);
+				else vxb_vertex_kernel<<<flatGrid, VXB_THREADS, 0, st>>>(dev, part);
+				timer.end(); ++launches; ++ctx->kindLaunches[4];
+				timer.begin(5);
+				vxb_triangle_kernel<<<flatGrid, VXB_THREADS, 0, st>>>(dev, part);
+				timer.end(); ++launches; ++ctx->kindLaunches[5];
+			};
+			auto transitions = [&](cudaStream_t st) {
+				timer.begin(6);
+				if (dev.transitions)
+				{
+					vxb_transition_kernel<<<ctx->gridTransition, VXB_THREADS, sizeof(VxbTransSmem), st>>>(dev);
+					vxb_transition_vertex_kernel<<<flatGrid, VXB_THREADS, 0, st>>>(dev);
+					launches += 2; ctx->kindLaunches[6] += 2;
+				}
+				timer.end();
+			};
+			// Levels depend on each other only through vxb_classify_kernel, so with more than one level the work forks:
+			//   stream : level 0 -> decide -> vertices -> triangles
+			//   stream2: classify levels 1.. (a latency-bound chain of small launches) -> decide -> vertices -> triangles -> transitions
+			// and joins before vxb_finish_kernel.  Per-kernel timing (VXB_FLAG_KERNEL_TIMES) runs everything on one stream.
+			const bool fork = (computed > 1 && !kernelTimes) || phase == 2;
+			if (phase != 2) classifyLevel(0, ctx->stream);
+			if (phase == 1)
+			{
+				// sharded run, first half: the levels whose blocks nest in this rank's slab.  Nothing is read back: the caller
+				// exchanges the material pages of level splitLevel-1 on this stream (vxb_shard_exchange_info) and calls phase 2.
+				for (int l = 1; l < region->splitLevel && l < computed; ++l) classifyLevel(l, ctx->stream);
+				VXB_CUDA(ctx, cudaGetLastError());
+				// the exchange runs on the second stream (vxb_exchange_stream), ordered after this classification; in phase 2
+				// only the coarse levels wait for it, the vertices and triangles of the nested levels overlap it
+				VXB_CUDA(ctx, cudaEventRecord(ctx->evFork, ctx->stream));
+				VXB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->evFork, 0));
+				ctx->shardLaunches = launches;
+				return 100; // first half enqueued
+			}
+			const int firstRest = (phase == 2) ? region->splitLevel : 1;
+			if (phase == 2) launches += ctx->shardLaunches;
+			if (!fork)
+			{
+				for (int l = firstRest; l < computed; ++l) classifyLevel(l, ctx->stream);
+				decideGroup(0, ctx->stream); // level 0 first: its blocks own the first directory slots / arena ranges
+				vxb_mark_split_kernel<<<1, 1, 0, ctx->stream>>>(dev); ++launches;
+				flatGroup(0, ctx->stream);
+				if (computed > 1)
+				{
+					decideGroup(1, ctx->stream);
+					flatGroup(1, ctx->stream);
+					transitions(ctx->stream);
+				}
+			}
+			else
+			{
+				VXB_CUDA(ctx, cudaEventRecord(ctx->evFork, ctx->stream));
+				VXB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->evFork, 0));
+				for (int l = firstRest; l < computed; ++l) classifyLevel(l, ctx->stream2);
+				decideGroup(0, ctx->stream);
+				vxb_mark_split_kernel<<<1, 1, 0, ctx->stream>>>(dev); ++launches;
+				VXB_CUDA(ctx, cudaEventRecord(ctx->evDecide0, ctx->stream));
+				flatGroup(0, ctx->stream);
+				VXB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->evDecide0, 0)); // arena cursors are shared: group 1 allocates after group 0
+				decideGroup(1, ctx->stream2);
+				flatGroup(1, ctx->stream2);
+				transitions(ctx->stream2);
+				VXB_CUDA(ctx, cudaEventRecord(ctx->evJoin, ctx->stream2));
+				VXB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->evJoin, 0));
+			}
+			timer.begin(7);
+			vxb_finish_kernel<<<(unsigned)ctx->smCount * 2, VXB_THREADS, 0, ctx->stream>>>(dev);
+			timer.end(); ++launches; ++ctx->kindLaunches[7];
 			return VXB_OK;
-		}
-		const int firstRest = (phase == 2) ? region->splitLevel : 1;
-		if (phase == 2) launches += ctx->shardLaunches;
-		if (!fork)
+		};
+		// A full run has no host decision inside the sequence, so it is captured once into a CUDA graph and replayed; the
+		// key is every kernel argument (a re-upload into other buffers, grown arenas, other flags => new capture).
+		bool replayed = false;
+		if (phase == 0 && !region && !kernelTimes && !ctx->graphDisabled)
 		{
-			for (int l = firstRest; l < computed; ++l) classifyLevel(l, ctx->stream);
-			decideGroup(0, ctx->stream); // level 0 first: its blocks own the first directory slots / arena ranges
-			vxb_mark_split_kernel<<<1, 1, 0, ctx->stream>>>(dev); ++launches;
-			flatGroup(0, ctx->stream);
-			if (computed > 1)
+			std::vector<unsigned char> key(sizeof(VxbDev) + 5 * sizeof(CUtensorMap) + 64, 0);
+			unsigned char* k = key.data();
+			memcpy(k, &dev, sizeof(VxbDev)); k += sizeof(VxbDev);
+			const CUtensorMap* maps[5] = { &ctx->tmap, &ctx->tmap1, &ctx->tmapDist19, &ctx->tmapMat, &ctx->tmapBlend };
+			for (const CUtensorMap* mp : maps) { memcpy(k, mp, sizeof(CUtensorMap)); k += sizeof(CUtensorMap); }
+			const void* ptrs[4] = { ctx->dDist, ctx->scanFlags.p, ctx->blockInfo.p, ctx->haveLattice1 ? ctx->lattice1.p : nullptr };
+			memcpy(k, ptrs, sizeof(ptrs)); k += sizeof(ptrs);
+			const int scalars[4] = { computed, (int)validBytes, (int)ctx->vbMatTiles, (int)n };
+			memcpy(k, scalars, sizeof(scalars));
+			if (!ctx->graphExec || key != ctx->graphKey)
 			{
-				decideGroup(1, ctx->stream);
-				flatGroup(1, ctx->stream);
-				transitions(ctx->stream);
+				if (ctx->graphExec) { cudaGraphExecDestroy(ctx->graphExec); ctx->graphExec = nullptr; }
+				cudaGraph_t graph = nullptr;
+				cudaError_t ce = cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal);
+				if (ce == cudaSuccess)
+				{
+					const int rc = enqueue();
+					ce = cudaStreamEndCapture(ctx->stream, &graph);
+					if (rc != VXB_OK && ce == cudaSuccess) ce = cudaErrorUnknown;
+				}
+				if (ce == cudaSuccess) ce = cudaGraphInstantiate(&ctx->graphExec, graph, 0);
+				if (graph) cudaGraphDestroy(graph);
+				if (ce != cudaSuccess) { ctx->graphExec = nullptr; ctx->graphDisabled = true; cudaGetLastError(); } // fall back to plain launches for good
+				else { ctx->graphKey = key; ctx->graphLaunches = launches; }
+				launches = 0;
+			}
+			if (ctx->graphExec)
+			{
+				VXB_CUDA(ctx, cudaGraphLaunch(ctx->graphExec, ctx->stream));
+				launches = ctx->graphLaunches;
+				replayed = true;
 			}
 		}
-		else
+		if (!replayed)
 		{
-			VXB_CUDA(ctx, cudaEventRecord(ctx->evFork, ctx->stream));
-			VXB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->evFork, 0));
-			for (int l = firstRest; l < computed; ++l) classifyLevel(l, ctx->stream2);
-			decideGroup(0, ctx->stream);
-			vxb_mark_split_kernel<<<1, 1, 0, ctx->stream>>>(dev); ++launches;
-			VXB_CUDA(ctx, cudaEventRecord(ctx->evDecide0, ctx->stream));
-			flatGroup(0, ctx->stream);
-			VXB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->evDecide0, 0)); // arena cursors are shared: group 1 allocates after group 0
-			decideGroup(1, ctx->stream2);
-			flatGroup(1, ctx->stream2);
-			transitions(ctx->stream2);
-			VXB_CUDA(ctx, cudaEventRecord(ctx->evJoin, ctx->stream2));
-			VXB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->evJoin, 0));
+			const int rc = enqueue();
+			if (rc == 100) return VXB_OK;
+			if (rc != VXB_OK) return rc;
 		}
-		timer.begin(7);
-		vxb_finish_kernel<<<(unsigned)ctx->smCount * 2, VXB_THREADS, 0, ctx->stream>>>(dev);
-		timer.end(); ++launches; ++ctx->kindLaunches[7];
 		VXB_CUDA(ctx, cudaGetLastError());
 		VXB_CUDA(ctx, cudaEventRecord(ctx->evEnd, ctx->stream));
 		VXB_CUDA(ctx, cudaMemcpyAsync(&hc, ctx->counters.p, sizeof(hc), cudaMemcpyDeviceToHost, ctx->stream));
