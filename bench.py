@@ -243,7 +243,7 @@ def main():
     traffic, traffic_src = None, None
     try:
         kind_keys = ["scan", "select", "classify", "decide", "vertex", "triangle", "transition", "finish"]
-        with open(os.path.join(REPO, "profiles", "r01b_traffic.json")) as f:
+        with open(os.path.join(REPO, "profiles", "r01d_traffic.json")) as f:
             tj = json.load(f)
         if n == 1024 and args.levels == 0 and not args.no_transitions:
             e = tj["per_kind"][kind_keys[dom]]

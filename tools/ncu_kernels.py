@@ -2,7 +2,7 @@
 """Summarises an `ncu --set full` report of one bench.py step: per launch a table row (markdown) and per kernel kind the
 DRAM traffic (json, read by bench.py for `roofline.traffic`).
 
-    ncu -i X.ncu-rep --page raw --csv > raw.csv ;  python tools/ncu_kernels.py raw.csv out_prefix "capture description"
+    ncu -i X.ncu-rep --page raw --csv > raw.csv ;  python tools/ncu_kernels.py raw.csv out_prefix "capture description" [first N launches]
 """
 import csv
 import json
@@ -21,14 +21,18 @@ def scale(value, unit, want):
     return v * f.get(unit, 1.0)
 
 
-def main(path, prefix, description):
+def main(path, prefix, description, limit=None):
     rows = list(csv.reader(open(path)))
+    if limit:
+        rows = rows[:2 + limit]
     hdr, units = rows[0], rows[1]
     idx = {k: hdr.index(v) for k, v in COLS.items()}
     name_i = hdr.index("Kernel Name")
     per_kind, lines = {}, ["| # | kernel | grid | us | DRAM read MB | DRAM write MB | regs | warps active % | IPC | warp-instr (M) |", "|---|---|---|---|---|---|---|---|---|---|"]
     for n, r in enumerate(rows[2:]):
         name = r[name_i].split("(")[0]
+        if name.startswith("void "):
+            name = name[5:]
         us = scale(r[idx["us"]], units[idx["us"]], "us")
         rd = scale(r[idx["rd"]], units[idx["rd"]], "byte")
         wr = scale(r[idx["wr"]], units[idx["wr"]], "byte")
@@ -45,4 +49,4 @@ def main(path, prefix, description):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1], sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else "")
+    main(sys.argv[1], sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else "", int(sys.argv[4]) if len(sys.argv) > 4 else None)
