@@ -5,6 +5,7 @@
 #include <cuda.h> // CUtensorMap types only; cuTensorMapEncodeTiled is resolved through the runtime (no libcuda link)
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -61,7 +62,7 @@ struct vxb_context
 	int device = 0;
 	int smCount = 0;
 	cudaStream_t stream = nullptr, stream2 = nullptr;
-	cudaEvent_t evBegin = nullptr, evEnd = nullptr, evFork = nullptr, evDecide0 = nullptr, evJoin = nullptr;
+	cudaEvent_t evBegin = nullptr, evEnd = nullptr, evFork = nullptr, evDecide0 = nullptr, evJoin = nullptr, evDir = nullptr;
 	std::vector<cudaEvent_t> kevents; // per-kernel timing (pairs)
 	std::string error;
 	EncodeTiledFn encodeTiled = nullptr;
@@ -72,7 +73,19 @@ struct vxb_context
 	const int8_t* dDist = nullptr; const uint8_t* dMat = nullptr; const uint8_t* dBlend = nullptr;
 	DevBuf<uint8_t> volDist, volMat, volBlend, staging;
 	DevBuf<unsigned long long> packOffsets;
-	std::vector<unsigned long long> hostOffsets;
+	struct PinnedBuf // page-locked host scratch (grows, never shrinks)
+	{
+		void* p = nullptr; size_t bytes = 0;
+		bool ensure(size_t want)
+		{
+			if (want <= bytes) return true;
+			if (p) cudaFreeHost(p);
+			p = nullptr; bytes = 0;
+			if (cudaHostAlloc(&p, want, cudaHostAllocDefault) != cudaSuccess) { p = nullptr; return false; }
+			bytes = want; return true;
+		}
+		void release() { if (p) cudaFreeHost(p); p = nullptr; bytes = 0; }
+	} hostOffsets, hostRecords;
 	DevBuf<unsigned int> scanFlags;
 	DevBuf<unsigned char> blockInfo;
 	DevBuf<unsigned int> consPages;
@@ -476,7 +489,8 @@ int vxb_create(int device, vxb_context** out)
 		(e = cudaEventCreate(&ctx->evBegin)) != cudaSuccess || (e = cudaEventCreate(&ctx->evEnd)) != cudaSuccess ||
 		(e = cudaEventCreateWithFlags(&ctx->evFork, cudaEventDisableTiming)) != cudaSuccess ||
 		(e = cudaEventCreateWithFlags(&ctx->evDecide0, cudaEventDisableTiming)) != cudaSuccess ||
-		(e = cudaEventCreateWithFlags(&ctx->evJoin, cudaEventDisableTiming)) != cudaSuccess)
+		(e = cudaEventCreateWithFlags(&ctx->evJoin, cudaEventDisableTiming)) != cudaSuccess ||
+		(e = cudaEventCreateWithFlags(&ctx->evDir, cudaEventDisableTiming)) != cudaSuccess)
 	{ fail(nullptr, VXB_ERR_CUDA, "stream/event creation", e); delete ctx; return VXB_ERR_CUDA; }
 
 	void* fn = nullptr;
@@ -519,6 +533,7 @@ void vxb_destroy(vxb_context* ctx)
 	if (ctx->stream) cudaStreamSynchronize(ctx->stream);
 	if (ctx->stream2) cudaStreamSynchronize(ctx->stream2);
 	if (ctx->graphExec) cudaGraphExecDestroy(ctx->graphExec);
+	ctx->hostOffsets.release(); ctx->hostRecords.release();
 	releaseCube(ctx);
 	ctx->volDist.release(); ctx->volMat.release(); ctx->volBlend.release(); ctx->staging.release(); ctx->packOffsets.release(); ctx->updCoords.release(); ctx->lattice1.release();
 	ctx->scanFlags.release(); ctx->blockInfo.release(); ctx->consPages.release(); ctx->validFlags.release();
@@ -530,6 +545,7 @@ void vxb_destroy(vxb_context* ctx)
 	if (ctx->evFork) cudaEventDestroy(ctx->evFork);
 	if (ctx->evDecide0) cudaEventDestroy(ctx->evDecide0);
 	if (ctx->evJoin) cudaEventDestroy(ctx->evJoin);
+	if (ctx->evDir) cudaEventDestroy(ctx->evDir);
 	if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
 	if (ctx->stream) cudaStreamDestroy(ctx->stream);
 	delete ctx;
@@ -594,33 +610,51 @@ int vxb_grid_upload_packed(vxb_context* ctx, const void* blob, size_t size)
 	const size_t nb = n / 16, blocks = nb * nb * nb;
 	const size_t tableBytes = blocks * 12;
 	if (size < 16 + tableBytes) return fail(ctx, VXB_ERR_ARGUMENT, "vxb_grid_upload_packed: truncated size table");
-	// per-block byte offsets (prefix sum of the size table); the data itself is only touched by the GPU
-	ctx->hostOffsets.resize(blocks);
-	{
-		const unsigned char* table = bytes + 16;
-		unsigned long long off = 16 + tableBytes;
-		for (size_t b = 0; b < blocks; ++b)
-		{
-			uint32_t sz[3];
-			memcpy(sz, table + b * 12, 12);
-			if (sz[0] > 4096 || sz[1] > 4096 || sz[2] > 4096) return fail(ctx, VXB_ERR_ARGUMENT, "vxb_grid_upload_packed: corrupt size table");
-			ctx->hostOffsets[b] = off;
-			off += 4ull + sz[0] + sz[1] + sz[2];
-		}
-		if (off > size) return fail(ctx, VXB_ERR_ARGUMENT, "vxb_grid_upload_packed: truncated block data");
-	}
 	cudaSetDevice(ctx->device);
 	int r = ensureGridStorage(ctx, n);
 	if (r != VXB_OK) return r;
 	VXB_CUDA(ctx, ctx->staging.ensure(size + 16));
 	VXB_CUDA(ctx, ctx->packOffsets.ensure(blocks));
+	const bool trace = getenv("VXB200_TRACE") != nullptr;
+	auto now = [] { return std::chrono::steady_clock::now(); };
+	auto msSince = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(now() - t).count(); };
+	const auto t0 = now();
+	// the copy starts first; the per-block byte offsets (prefix sum of the size table) are computed on the host while the
+	// DMA engine moves the data, which only the GPU touches
+	if (!ctx->hostOffsets.ensure(blocks * sizeof(unsigned long long))) return fail(ctx, VXB_ERR_CUDA, "vxb_grid_upload_packed: pinned scratch allocation failed");
+	unsigned long long* const hostOffsets = static_cast<unsigned long long*>(ctx->hostOffsets.p);
 	VXB_CUDA(ctx, cudaMemcpyAsync(ctx->staging.p, blob, size, cudaMemcpyHostToDevice, ctx->stream));
-	VXB_CUDA(ctx, cudaMemcpyAsync(ctx->packOffsets.p, ctx->hostOffsets.data(), blocks * sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream));
-	vxb_unpack_rle_kernel<<<(unsigned)blocks, VXB_THREADS, 0, ctx->stream>>>(ctx->staging.p, ctx->packOffsets.p,
+	bool corrupt = false;
+	unsigned long long off = 16 + tableBytes;
+	{
+		const unsigned char* table = bytes + 16;
+		for (size_t b = 0; b < blocks; ++b)
+		{
+			uint32_t sz[3];
+			memcpy(sz, table + b * 12, 12);
+			if (sz[0] > 4096 || sz[1] > 4096 || sz[2] > 4096) { corrupt = true; break; }
+			hostOffsets[b] = off;
+			off += 4ull + sz[0] + sz[1] + sz[2];
+		}
+	}
+	const double msTable = msSince(t0);
+	if (corrupt || off > size)
+	{
+		cudaStreamSynchronize(ctx->stream);
+		ctx->haveGrid = false;
+		return fail(ctx, VXB_ERR_ARGUMENT, corrupt ? "vxb_grid_upload_packed: corrupt size table" : "vxb_grid_upload_packed: truncated block data");
+	}
+	if (trace) cudaStreamSynchronize(ctx->stream);
+	const double msCopy = msSince(t0);
+	VXB_CUDA(ctx, cudaMemcpyAsync(ctx->packOffsets.p, hostOffsets, blocks * sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream));
+	vxb_unpack_rle_kernel<<<(unsigned)(((nb + 7) / 8) * nb * nb), VXB_THREADS, 0, ctx->stream>>>(ctx->staging.p, ctx->packOffsets.p,
 		reinterpret_cast<const unsigned int*>(ctx->staging.p + 16), ctx->volDist.p, ctx->volMat.p, ctx->volBlend.p, (int)n);
 	VXB_CUDA(ctx, cudaGetLastError());
 	VXB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-	return buildTensorMap(ctx);
+	const double msKernel = msSince(t0);
+	r = buildTensorMap(ctx);
+	if (trace) fprintf(stderr, "[vxb200] upload_packed: size table %.3f ms, copy done at %.3f ms, decode done at %.3f ms, maps at %.3f ms\n", msTable, msCopy, msKernel, msSince(t0));
+	return r;
 }
 
 size_t vxb_pack_dense_bound(uint32_t n)
@@ -1225,21 +1259,32 @@ int vxb_result_download(vxb_context* ctx, vxb_block_record* records, void* verti
 	if (!ctx->haveResult) return fail(ctx, VXB_ERR_STATE, "no result: call vxb_polygonize first");
 	cudaSetDevice(ctx->device);
 	const vxb_result_info& info = ctx->info;
-	if (!ctx->directoryFetched)
+	// directory first (small, into page-locked scratch), the arenas queued right behind it; the directory is sorted into the
+	// reference's block order (level, then z,y,x = coord id; :395-401, :1278) on the host while the arenas are in flight
+	const bool fetch = !ctx->directoryFetched;
+	if (fetch && info.block_count)
 	{
-		// directory: device -> host, sorted into the reference's block order (level, then z,y,x = coord id; :395-401, :1278)
+		if (!ctx->hostRecords.ensure(sizeof(vxb_block_record) * info.block_count)) return fail(ctx, VXB_ERR_CUDA, "vxb_result_download: pinned scratch allocation failed");
+		VXB_CUDA(ctx, cudaMemcpyAsync(ctx->hostRecords.p, ctx->records.p, sizeof(vxb_block_record) * info.block_count, cudaMemcpyDeviceToHost, ctx->stream));
+		VXB_CUDA(ctx, cudaEventRecord(ctx->evDir, ctx->stream));
+	}
+	if (vertices && info.vertex_span) VXB_CUDA(ctx, cudaMemcpyAsync(vertices, ctx->verts.p, info.vertex_span * sizeof(VxbVertex), cudaMemcpyDeviceToHost, ctx->stream));
+	if (indices && info.index_span) VXB_CUDA(ctx, cudaMemcpyAsync(indices, ctx->idx.p, info.index_span * 4, cudaMemcpyDeviceToHost, ctx->stream));
+	if (transVertices && info.trans_vertex_span) VXB_CUDA(ctx, cudaMemcpyAsync(transVertices, ctx->tverts.p, info.trans_vertex_span * sizeof(VxbVertex), cudaMemcpyDeviceToHost, ctx->stream));
+	if (transIndices && info.trans_index_span) VXB_CUDA(ctx, cudaMemcpyAsync(transIndices, ctx->tidx.p, info.trans_index_span * 4, cudaMemcpyDeviceToHost, ctx->stream));
+	if (fetch)
+	{
 		ctx->sortedRecords.resize(info.block_count);
 		if (info.block_count)
-			VXB_CUDA(ctx, cudaMemcpy(ctx->sortedRecords.data(), ctx->records.p, sizeof(vxb_block_record) * info.block_count, cudaMemcpyDeviceToHost));
+		{
+			VXB_CUDA(ctx, cudaEventSynchronize(ctx->evDir));
+			memcpy(ctx->sortedRecords.data(), ctx->hostRecords.p, sizeof(vxb_block_record) * info.block_count);
+		}
 		std::sort(ctx->sortedRecords.begin(), ctx->sortedRecords.end(), [](const vxb_block_record& a, const vxb_block_record& b) {
 			return a.level != b.level ? a.level < b.level : a.coord_id < b.coord_id; });
 		ctx->directoryFetched = true;
 	}
 	if (records && info.block_count) memcpy(records, ctx->sortedRecords.data(), sizeof(vxb_block_record) * info.block_count);
-	if (vertices && info.vertex_span) VXB_CUDA(ctx, cudaMemcpyAsync(vertices, ctx->verts.p, info.vertex_span * sizeof(VxbVertex), cudaMemcpyDeviceToHost, ctx->stream));
-	if (indices && info.index_span) VXB_CUDA(ctx, cudaMemcpyAsync(indices, ctx->idx.p, info.index_span * 4, cudaMemcpyDeviceToHost, ctx->stream));
-	if (transVertices && info.trans_vertex_span) VXB_CUDA(ctx, cudaMemcpyAsync(transVertices, ctx->tverts.p, info.trans_vertex_span * sizeof(VxbVertex), cudaMemcpyDeviceToHost, ctx->stream));
-	if (transIndices && info.trans_index_span) VXB_CUDA(ctx, cudaMemcpyAsync(transIndices, ctx->tidx.p, info.trans_index_span * 4, cudaMemcpyDeviceToHost, ctx->stream));
 	VXB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 
 	// vertices of unmapped materials carry a marker (vxb_finish_vertex); restore the reference's all-zero textures

@@ -317,57 +317,110 @@ __global__ void __launch_bounds__(VXB_THREADS) vxb_unpack_block_list_kernel(cons
 	*reinterpret_cast<uint4*>(dense + (((size_t)bz * 16 + z) * n + (size_t)by * 16 + y) * n + (size_t)bx * 16) = blocks[b * 256 + row];
 }
 
-// Upload helper: run-length decoding of one packed 16^3 block per CTA, all three channels
-// (VoxelGrid::DecompressBlock, VoxelGrid.cpp:674-694; block layout of PackForSave :304-312).
-// Thread t produces the 16 bytes of row t (x fastest): binary search of the run that covers its first byte.
+// Upload helper: run-length decoding of the packed 16^3 blocks (VoxelGrid::DecompressBlock, VoxelGrid.cpp:674-694; block
+// layout of PackForSave :304-312).  One CTA per 8 x-adjacent blocks: most channels of most blocks are a single value (17
+// runs of <= 255), those are written as full 128-byte lines (8 lanes x 16 bytes, the layout of vxb_scan_kernel's reads);
+// the others are decoded by the whole CTA, thread t producing row t by a binary search of the run covering its first byte.
+__device__ __forceinline__ void vxb_decode_channel(const unsigned char* src, unsigned size, bool raw, unsigned char* out, int n, int bx, int by, int bz,
+	unsigned short* start, unsigned char* value, unsigned* warpSums)
+{
+	const int tid = threadIdx.x, y = tid & 15, z = tid >> 4;
+	uint4 row;
+	unsigned char* rb = reinterpret_cast<unsigned char*>(&row);
+	if (raw) // BF_*Uncompressed (VoxelGrid.h:70-79): 4096 raw bytes
+	{
+		for (int i = 0; i < 16; ++i) rb[i] = src[tid * 16 + i];
+	}
+	else
+	{
+		const unsigned runs = min(size >> 1, 2048u);
+		const unsigned per = (runs + VXB_THREADS - 1) / VXB_THREADS;
+		const unsigned r0 = min(tid * per, runs), r1 = min(r0 + per, runs);
+		unsigned sum = 0;
+		for (unsigned r = r0; r < r1; ++r) sum += src[2 * r];
+		unsigned total;
+		unsigned base = vxb_block_scan(sum, warpSums, total);
+		for (unsigned r = r0; r < r1; ++r) { start[r] = (unsigned short)min(base, 4096u); value[r] = src[2 * r + 1]; base += src[2 * r]; }
+		if (tid == 0) start[runs] = 4096;
+		__syncthreads();
+		const unsigned p0 = tid * 16;
+		unsigned lo = 0, hi = runs; // last run with start <= p0
+		while (hi - lo > 1) { const unsigned mid = (lo + hi) >> 1; if (start[mid] <= p0) lo = mid; else hi = mid; }
+		unsigned r = lo;
+		for (int i = 0; i < 16; ++i)
+		{
+			while (r + 1 < runs && start[r + 1] <= p0 + i) ++r;
+			rb[i] = value[r];
+		}
+		__syncthreads();
+	}
+	*reinterpret_cast<uint4*>(out + (((size_t)bz * 16 + z) * n + (size_t)by * 16 + y) * n + (size_t)bx * 16) = row;
+}
+
 __global__ void __launch_bounds__(VXB_THREADS) vxb_unpack_rle_kernel(const unsigned char* __restrict__ blob, const unsigned long long* __restrict__ blockOffsets,
 	const unsigned int* __restrict__ sizes, unsigned char* __restrict__ dist, unsigned char* __restrict__ mat, unsigned char* __restrict__ blend, int n)
 {
 	__shared__ unsigned short start[2049];
 	__shared__ unsigned char value[2048];
 	__shared__ unsigned warpSums[8];
+	__shared__ unsigned long long sOff[8][3];  // byte offset of the channel's data in the blob
+	__shared__ unsigned sSize[8][3];
+	__shared__ int sKind[8][3];                // >= 0: every run has this value; -1: run-length coded; -2: raw
 	const int nb = n >> 4;
-	const size_t b = blockIdx.x;
-	const int bx = (int)(b % nb), by = (int)((b / nb) % nb), bz = (int)(b / ((size_t)nb * nb));
-	const int tid = threadIdx.x, y = tid & 15, z = tid >> 4;
-	const unsigned char* src = blob + blockOffsets[b];
-	const unsigned flags = src[0] | (src[1] << 8) | (src[2] << 16) | ((unsigned)src[3] << 24);
-	src += 4;
-	unsigned char* const outs[3] = { dist, mat, blend };
-	for (int ch = 0; ch < 3; ++ch)
+	const int groups = (nb + 7) >> 3;          // CTAs per row of blocks
+	const int bx0 = (int)(blockIdx.x % groups) * 8, by = (int)((blockIdx.x / groups) % nb), bz = (int)(blockIdx.x / ((size_t)groups * nb));
+	const int tid = threadIdx.x;
+	if (tid < 24)
 	{
-		const unsigned size = sizes[b * 3 + ch];
-		uint4 row;
-		unsigned char* rb = reinterpret_cast<unsigned char*>(&row);
-		if ((flags >> (1 + ch)) & 1u) // BF_*Uncompressed (VoxelGrid.h:70-79): 4096 raw bytes
+		const int j = tid / 3, ch = tid % 3;
+		int kind = -1;
+		if (bx0 + j < nb)
 		{
-			for (int i = 0; i < 16; ++i) rb[i] = src[tid * 16 + i];
-		}
-		else
-		{
-			const unsigned runs = min(size >> 1, 2048u);
-			const unsigned per = (runs + VXB_THREADS - 1) / VXB_THREADS;
-			const unsigned r0 = min(tid * per, runs), r1 = min(r0 + per, runs);
-			unsigned sum = 0;
-			for (unsigned r = r0; r < r1; ++r) sum += src[2 * r];
-			unsigned total;
-			unsigned base = vxb_block_scan(sum, warpSums, total);
-			for (unsigned r = r0; r < r1; ++r) { start[r] = (unsigned short)min(base, 4096u); value[r] = src[2 * r + 1]; base += src[2 * r]; }
-			if (tid == 0) start[runs] = 4096;
-			__syncthreads();
-			const unsigned p0 = tid * 16;
-			unsigned lo = 0, hi = runs; // last run with start <= p0
-			while (hi - lo > 1) { const unsigned mid = (lo + hi) >> 1; if (start[mid] <= p0) lo = mid; else hi = mid; }
-			unsigned r = lo;
-			for (int i = 0; i < 16; ++i)
+			const size_t b = ((size_t)bz * nb + by) * nb + bx0 + j;
+			const unsigned char* src = blob + blockOffsets[b];
+			const unsigned flags = src[0] | (src[1] << 8) | (src[2] << 16) | ((unsigned)src[3] << 24);
+			unsigned long long off = blockOffsets[b] + 4;
+			for (int c = 0; c < ch; ++c) off += sizes[b * 3 + c];
+			const unsigned size = sizes[b * 3 + ch];
+			sOff[j][ch] = off; sSize[j][ch] = size;
+			if ((flags >> (1 + ch)) & 1u) kind = -2;
+			else
 			{
-				while (r + 1 < runs && start[r + 1] <= p0 + i) ++r;
-				rb[i] = value[r];
+				const unsigned char* p = blob + off;
+				const unsigned runs = size >> 1;
+				bool same = runs >= 1 && runs <= 64;
+				for (unsigned r = 1; r < runs && same; ++r) same = p[2 * r + 1] == p[1];
+				if (same) kind = p[1];
 			}
-			__syncthreads();
 		}
-		*reinterpret_cast<uint4*>(outs[ch] + (((size_t)bz * 16 + z) * n + (size_t)by * 16 + y) * n + (size_t)bx * 16) = row;
-		src += size;
+		sKind[j][ch] = kind;
+	}
+	__syncthreads();
+	unsigned char* const outs[3] = { dist, mat, blend };
+	{
+		// single-valued channels: lane group j writes block j's 16 bytes of each row => full 128-byte lines
+		const int j = tid & 7, rg = tid >> 3;
+		if (bx0 + j < nb)
+#pragma unroll
+			for (int ch = 0; ch < 3; ++ch)
+			{
+				const int kind = sKind[j][ch];
+				if (kind < 0) continue;
+				const unsigned v4 = (unsigned)kind * 0x01010101u;
+				const uint4 row = make_uint4(v4, v4, v4, v4);
+#pragma unroll
+				for (int i = 0; i < 8; ++i)
+				{
+					const int r = i * 32 + rg, y = r & 15, z = r >> 4;
+					*reinterpret_cast<uint4*>(outs[ch] + (((size_t)bz * 16 + z) * n + (size_t)by * 16 + y) * n + (size_t)(bx0 + j) * 16) = row;
+				}
+			}
+	}
+	for (int e = 0; e < 24; ++e) // block-uniform loop over the channels that need real decoding
+	{
+		const int j = e / 3, ch = e % 3;
+		if (bx0 + j >= nb || sKind[j][ch] >= 0) continue;
+		vxb_decode_channel(blob + sOff[j][ch], sSize[j][ch], sKind[j][ch] == -2, outs[ch], n, bx0 + j, by, bz, start, value, warpSums);
 	}
 }
 
