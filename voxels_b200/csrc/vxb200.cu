@@ -63,6 +63,7 @@ struct vxb_context
 	int smCount = 0;
 	cudaStream_t stream = nullptr, stream2 = nullptr;
 	cudaEvent_t evBegin = nullptr, evEnd = nullptr, evFork = nullptr, evDecide0 = nullptr, evJoin = nullptr, evDir = nullptr;
+	cudaEvent_t evChunk[4] = { nullptr, nullptr, nullptr, nullptr };
 	std::vector<cudaEvent_t> kevents; // per-kernel timing (pairs)
 	std::string error;
 	EncodeTiledFn encodeTiled = nullptr;
@@ -490,7 +491,9 @@ int vxb_create(int device, vxb_context** out)
 		(e = cudaEventCreateWithFlags(&ctx->evFork, cudaEventDisableTiming)) != cudaSuccess ||
 		(e = cudaEventCreateWithFlags(&ctx->evDecide0, cudaEventDisableTiming)) != cudaSuccess ||
 		(e = cudaEventCreateWithFlags(&ctx->evJoin, cudaEventDisableTiming)) != cudaSuccess ||
-		(e = cudaEventCreateWithFlags(&ctx->evDir, cudaEventDisableTiming)) != cudaSuccess)
+		(e = cudaEventCreateWithFlags(&ctx->evDir, cudaEventDisableTiming)) != cudaSuccess ||
+		(e = cudaEventCreateWithFlags(&ctx->evChunk[0], cudaEventDisableTiming)) != cudaSuccess || (e = cudaEventCreateWithFlags(&ctx->evChunk[1], cudaEventDisableTiming)) != cudaSuccess ||
+		(e = cudaEventCreateWithFlags(&ctx->evChunk[2], cudaEventDisableTiming)) != cudaSuccess || (e = cudaEventCreateWithFlags(&ctx->evChunk[3], cudaEventDisableTiming)) != cudaSuccess)
 	{ fail(nullptr, VXB_ERR_CUDA, "stream/event creation", e); delete ctx; return VXB_ERR_CUDA; }
 
 	void* fn = nullptr;
@@ -546,6 +549,7 @@ void vxb_destroy(vxb_context* ctx)
 	if (ctx->evDecide0) cudaEventDestroy(ctx->evDecide0);
 	if (ctx->evJoin) cudaEventDestroy(ctx->evJoin);
 	if (ctx->evDir) cudaEventDestroy(ctx->evDir);
+	for (cudaEvent_t e : ctx->evChunk) if (e) cudaEventDestroy(e);
 	if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
 	if (ctx->stream) cudaStreamDestroy(ctx->stream);
 	delete ctx;
@@ -619,13 +623,15 @@ int vxb_grid_upload_packed(vxb_context* ctx, const void* blob, size_t size)
 	auto now = [] { return std::chrono::steady_clock::now(); };
 	auto msSince = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(now() - t).count(); };
 	const auto t0 = now();
-	// the copy starts first; the per-block byte offsets (prefix sum of the size table) are computed on the host while the
-	// DMA engine moves the data, which only the GPU touches
+	// Pipeline: header + size table first; while that moves, the per-block byte offsets (prefix sum of the size table) are
+	// computed on the host; then the block data in z-chunks on the copy stream, each chunk decoded on the second stream
+	// as soon as it has landed, so that only the last chunk's decode is exposed.
+	const size_t head = 16 + tableBytes;
 	if (!ctx->hostOffsets.ensure(blocks * sizeof(unsigned long long))) return fail(ctx, VXB_ERR_CUDA, "vxb_grid_upload_packed: pinned scratch allocation failed");
 	unsigned long long* const hostOffsets = static_cast<unsigned long long*>(ctx->hostOffsets.p);
-	VXB_CUDA(ctx, cudaMemcpyAsync(ctx->staging.p, blob, size, cudaMemcpyHostToDevice, ctx->stream));
+	VXB_CUDA(ctx, cudaMemcpyAsync(ctx->staging.p, blob, head, cudaMemcpyHostToDevice, ctx->stream));
 	bool corrupt = false;
-	unsigned long long off = 16 + tableBytes;
+	unsigned long long off = head;
 	{
 		const unsigned char* table = bytes + 16;
 		for (size_t b = 0; b < blocks; ++b)
@@ -644,16 +650,26 @@ int vxb_grid_upload_packed(vxb_context* ctx, const void* blob, size_t size)
 		ctx->haveGrid = false;
 		return fail(ctx, VXB_ERR_ARGUMENT, corrupt ? "vxb_grid_upload_packed: corrupt size table" : "vxb_grid_upload_packed: truncated block data");
 	}
-	if (trace) cudaStreamSynchronize(ctx->stream);
-	const double msCopy = msSince(t0);
 	VXB_CUDA(ctx, cudaMemcpyAsync(ctx->packOffsets.p, hostOffsets, blocks * sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream));
-	vxb_unpack_rle_kernel<<<(unsigned)(((nb + 7) / 8) * nb * nb), VXB_THREADS, 0, ctx->stream>>>(ctx->staging.p, ctx->packOffsets.p,
-		reinterpret_cast<const unsigned int*>(ctx->staging.p + 16), ctx->volDist.p, ctx->volMat.p, ctx->volBlend.p, (int)n);
+	const int chunks = nb >= 16 ? 4 : 1;
+	const size_t groupsPerLayer = ((nb + 7) / 8) * nb;
+	for (int c = 0; c < chunks; ++c)
+	{
+		const size_t layer0 = nb * c / chunks, layer1 = nb * (c + 1) / chunks;
+		const unsigned long long byte0 = hostOffsets[layer0 * nb * nb], byte1 = (layer1 == nb) ? off : hostOffsets[layer1 * nb * nb];
+		VXB_CUDA(ctx, cudaMemcpyAsync(ctx->staging.p + byte0, bytes + byte0, (size_t)(byte1 - byte0), cudaMemcpyHostToDevice, ctx->stream));
+		VXB_CUDA(ctx, cudaEventRecord(ctx->evChunk[c], ctx->stream));
+		VXB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->evChunk[c], 0));
+		vxb_unpack_rle_kernel<<<(unsigned)(groupsPerLayer * (layer1 - layer0)), VXB_THREADS, 0, ctx->stream2>>>(ctx->staging.p, ctx->packOffsets.p,
+			reinterpret_cast<const unsigned int*>(ctx->staging.p + 16), ctx->volDist.p, ctx->volMat.p, ctx->volBlend.p, (int)n, (int)layer0);
+	}
 	VXB_CUDA(ctx, cudaGetLastError());
+	VXB_CUDA(ctx, cudaEventRecord(ctx->evJoin, ctx->stream2));
+	VXB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->evJoin, 0));
 	VXB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	const double msKernel = msSince(t0);
 	r = buildTensorMap(ctx);
-	if (trace) fprintf(stderr, "[vxb200] upload_packed: size table %.3f ms, copy done at %.3f ms, decode done at %.3f ms, maps at %.3f ms\n", msTable, msCopy, msKernel, msSince(t0));
+	if (trace) fprintf(stderr, "[vxb200] upload_packed: offsets ready at %.3f ms, copy + decode done at %.3f ms, maps at %.3f ms\n", msTable, msKernel, msSince(t0));
 	return r;
 }
 

@@ -358,7 +358,8 @@ __device__ __forceinline__ void vxb_decode_channel(const unsigned char* src, uns
 }
 
 __global__ void __launch_bounds__(VXB_THREADS) vxb_unpack_rle_kernel(const unsigned char* __restrict__ blob, const unsigned long long* __restrict__ blockOffsets,
-	const unsigned int* __restrict__ sizes, unsigned char* __restrict__ dist, unsigned char* __restrict__ mat, unsigned char* __restrict__ blend, int n)
+	const unsigned int* __restrict__ sizes, unsigned char* __restrict__ dist, unsigned char* __restrict__ mat, unsigned char* __restrict__ blend, int n,
+	int zLayer0 /* first block layer of this launch: the blob is decoded in z-chunks while the rest is still being copied */)
 {
 	__shared__ unsigned short start[2049];
 	__shared__ unsigned char value[2048];
@@ -368,7 +369,7 @@ __global__ void __launch_bounds__(VXB_THREADS) vxb_unpack_rle_kernel(const unsig
 	__shared__ int sKind[8][3];                // >= 0: every run has this value; -1: run-length coded; -2: raw
 	const int nb = n >> 4;
 	const int groups = (nb + 7) >> 3;          // CTAs per row of blocks
-	const int bx0 = (int)(blockIdx.x % groups) * 8, by = (int)((blockIdx.x / groups) % nb), bz = (int)(blockIdx.x / ((size_t)groups * nb));
+	const int bx0 = (int)(blockIdx.x % groups) * 8, by = (int)((blockIdx.x / groups) % nb), bz = (int)(blockIdx.x / ((size_t)groups * nb)) + zLayer0;
 	const int tid = threadIdx.x;
 	if (tid < 24)
 	{
