@@ -914,10 +914,12 @@ static int runPolygonize(vxb_context* ctx, uint32_t maxLevels, uint32_t flags, c
 				VXB_CUDA(ctx, cudaMemsetAsync(ctx->counters.p, 0, sizeof(VxbCounters), ctx->stream));
 				if (!incremental) VXB_CUDA(ctx, cudaMemsetAsync(ctx->validFlags.p, 0, validBytes, ctx->stream)); // incremental runs keep the caches (:362-364)
 				const size_t layer0 = (region && !incremental) ? (size_t)region->scanLayer0 : 0, layer1 = (region && !incremental) ? (size_t)region->scanLayer1 : nb0;
-				const dim3 grid((unsigned)((nb0 + 7) / 8), (unsigned)nb0, (unsigned)(layer1 - layer0));
-				timer.begin(0);
-				vxb_scan_kernel<<<grid, VXB_THREADS, 0, ctx->stream>>>(ctx->dDist, (int)n, ctx->scanFlags.p, ctx->haveLattice1 ? ctx->lattice1.p : nullptr, (int)layer0);
-				timer.end(); ++launches; ++ctx->kindLaunches[0];
+				const int perCta = nb0 >= 32 ? 32 : 8;
+			const dim3 grid((unsigned)((nb0 + perCta - 1) / perCta), (unsigned)nb0, (unsigned)(layer1 - layer0));
+			timer.begin(0);
+			if (perCta == 32) vxb_scan_kernel<32><<<grid, VXB_THREADS, 0, ctx->stream>>>(ctx->dDist, (int)n, ctx->scanFlags.p, ctx->haveLattice1 ? ctx->lattice1.p : nullptr, (int)layer0);
+			else vxb_scan_kernel<8><<<grid, VXB_THREADS, 0, ctx->stream>>>(ctx->dDist, (int)n, ctx->scanFlags.p, ctx->haveLattice1 ? ctx->lattice1.p : nullptr, (int)layer0);
+			timer.end(); ++launches; ++ctx->kindLaunches[0];
 				const size_t first = layer0 * nb0 * nb0, last = layer1 * nb0 * nb0;
 				const unsigned g2 = (unsigned)std::min<size_t>((last - first + 255) / 256, (size_t)ctx->smCount * 8);
 				timer.begin(1);

@@ -182,79 +182,89 @@ __device__ __forceinline__ unsigned vxb_zero_bytes(unsigned w) // 0x80 in every 
 	return ~(((w & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | w) & 0x80808080u;
 }
 
-__global__ void __launch_bounds__(VXB_THREADS) vxb_scan_kernel(const signed char* __restrict__ dist, int n, unsigned int* __restrict__ scanFlags,
+// J = x-adjacent blocks per CTA = lanes per row: a load instruction of a warp covers (32 / (32/J))... J * 16 contiguous
+// bytes.  J = 32 (grids of >= 32 blocks per row): every warp-wide load is 512 contiguous bytes, which keeps DRAM pages open
+// longer than the 128-byte pieces of J = 8 (small grids).
+template <int J>
+__global__ void __launch_bounds__(VXB_THREADS, (J == 32 ? 3 : 4)) vxb_scan_kernel(const signed char* __restrict__ dist, int n, unsigned int* __restrict__ scanFlags,
 	unsigned char* __restrict__ lattice1 /* (n/2)^3: the samples at even coordinates = the level-1 lattice, or null */,
 	int zBlock0 /* first block layer (a rank of a sharded run scans its slab + one layer either side) */)
 {
-	__shared__ unsigned sFlags[8];
-	__shared__ unsigned sChanges[8];
+	constexpr int RG = VXB_THREADS / J; // row groups: thread (j, rg) reads rows rg, rg + RG, ... of block j
+	__shared__ unsigned sFlags[J];
+	__shared__ unsigned sChanges[J];
 	const int nb = n >> 4;
-	const int bx0 = blockIdx.x * 8, by = blockIdx.y, bz = blockIdx.z + zBlock0;
+	const int bx0 = blockIdx.x * J, by = blockIdx.y, bz = blockIdx.z + zBlock0;
 	const int tid = threadIdx.x;
-	const int j = tid & 7, rg = tid >> 3;
-	if (tid < 8) { sFlags[tid] = 0; sChanges[tid] = 0; }
+	const int j = tid % J, rg = tid / J;
+	if (tid < J) { sFlags[tid] = 0; sChanges[tid] = 0; }
 	__syncthreads();
 
 	unsigned neg = 0, pos = 0, zero = 0, negE = 0, nonnegE = 0, changes = 0;
 	if (bx0 + j < nb)
 	{
 		const uint4* src = reinterpret_cast<const uint4*>(dist + (((size_t)bz * 16) * n + (size_t)by * 16) * n + (size_t)(bx0 + j) * 16);
-		uint4 rows[8];
-#pragma unroll
-		for (int i = 0; i < 8; ++i)
+		const size_t ys = (size_t)n >> 4, zs = ys * n; // strides of y and z in 16-byte units
+		// row q * RG + rg of the block: RG = 32: (y, z) = (rg & 15, 2q + (rg >> 4));  RG = 8: (y, z) = ((q & 1) * 8 + rg, q >> 1)
+		const int y0 = (RG == 32) ? (rg & 15) : rg, z0 = (RG == 32) ? (rg >> 4) : 0;
+		const uint4* p = src + (size_t)z0 * zs + (size_t)y0 * ys;
+#pragma unroll 1
+		for (int batch = 0; batch < J / 8; ++batch, p += (RG == 32 ? 16 : 4) * zs)
 		{
-			const int row = i * 32 + rg, y = row & 15, z = row >> 4;
-			rows[i] = __ldg(src + (((size_t)z * n + y) * n >> 4));
-		}
+			uint4 rows[8];
 #pragma unroll
-		for (int i = 0; i < 8; ++i)
-		{
-			const int row = i * 32 + rg, y = row & 15, z = row >> 4;
-			const unsigned w[4] = { rows[i].x, rows[i].y, rows[i].z, rows[i].w };
-			const bool even = !((y | z) & 1);
-			// a row of 16 equal bytes (the common case away from the surface) has no value change inside it
-			const unsigned splat = (w[0] & 0xFFu) * 0x01010101u;
-			const bool flat = (w[0] == splat) & (w[1] == splat) & (w[2] == splat) & (w[3] == splat);
-			if (even && lattice1)
-			{
-				// by-product: the even-x bytes of the even rows, so that level 1 can stage its tiles with TMA too
-				const int h = n >> 1;
-				uint2 e;
-				e.x = __byte_perm(w[0], w[1], 0x6420);
-				e.y = __byte_perm(w[2], w[3], 0x6420);
-				*reinterpret_cast<uint2*>(lattice1 + (((size_t)(bz * 8 + (z >> 1))) * h + (by * 8 + (y >> 1))) * h + (size_t)(bx0 + j) * 8) = e;
-			}
+			for (int i = 0; i < 8; ++i)
+				rows[i] = __ldg(p + ((RG == 32) ? (size_t)(2 * i) * zs : (size_t)(i >> 1) * zs + (size_t)((i & 1) * 8) * ys));
 #pragma unroll
-			for (int q = 0; q < 4; ++q)
+			for (int i = 0; i < 8; ++i)
 			{
-				const unsigned zb = vxb_zero_bytes(w[q]);
-				neg |= w[q] & 0x80808080u;
-				zero |= zb;
-				pos |= ~w[q] & 0x80808080u & ~zb;
-				if (even) { negE |= w[q] & 0x00800080u; nonnegE |= ~w[q] & 0x00800080u; }
-			}
-			if (!flat)
-			{
+				const int y = (RG == 32) ? y0 : ((i & 1) * 8 + y0), z = (RG == 32) ? (z0 + 2 * i + batch * 16) : ((i >> 1) + batch * 4);
+				const unsigned w[4] = { rows[i].x, rows[i].y, rows[i].z, rows[i].w };
+				const bool even = !((y | z) & 1);
+				// a row of 16 equal bytes (the common case away from the surface) has no value change inside it
+				const unsigned splat = (w[0] & 0xFFu) * 0x01010101u;
+				const bool flat = (w[0] == splat) & (w[1] == splat) & (w[2] == splat) & (w[3] == splat);
+				if (even && lattice1)
+				{
+					// by-product: the even-x bytes of the even rows, so that level 1 can stage its tiles with TMA too
+					const int h = n >> 1;
+					uint2 e;
+					e.x = __byte_perm(w[0], w[1], 0x6420);
+					e.y = __byte_perm(w[2], w[3], 0x6420);
+					*reinterpret_cast<uint2*>(lattice1 + (((size_t)(bz * 8 + (z >> 1))) * h + (by * 8 + (y >> 1))) * h + (size_t)(bx0 + j) * 8) = e;
+				}
 #pragma unroll
 				for (int q = 0; q < 4; ++q)
 				{
-					// adjacent-byte changes inside the 16-byte row: compare byte k with byte k+1
-					const unsigned nxt = (q < 3) ? w[q + 1] : (w[3] >> 24);
-					const unsigned shifted = (w[q] >> 8) | (nxt << 24);
-					const unsigned x = w[q] ^ shifted;
-					unsigned diff = ((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x; // bit 7 of each byte set iff byte != 0
-					diff &= (q < 3) ? 0x80808080u : 0x00808080u;               // byte 15 has no right neighbour in the row
-					changes += __popc(diff);
+					const unsigned zb = vxb_zero_bytes(w[q]);
+					neg |= w[q] & 0x80808080u;
+					zero |= zb;
+					pos |= ~w[q] & 0x80808080u & ~zb;
+					if (even) { negE |= w[q] & 0x00800080u; nonnegE |= ~w[q] & 0x00800080u; }
+				}
+				if (!flat)
+				{
+#pragma unroll
+					for (int q = 0; q < 4; ++q)
+					{
+						// adjacent-byte changes inside the 16-byte row: compare byte k with byte k+1
+						const unsigned nxt = (q < 3) ? w[q + 1] : (w[3] >> 24);
+						const unsigned shifted = (w[q] >> 8) | (nxt << 24);
+						const unsigned x = w[q] ^ shifted;
+						unsigned diff = ((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x; // bit 7 of each byte set iff byte != 0
+						diff &= (q < 3) ? 0x80808080u : 0x00808080u;               // byte 15 has no right neighbour in the row
+						changes += __popc(diff);
+					}
 				}
 			}
 		}
 	}
 	unsigned f = (neg ? 1u : 0u) | (pos ? 2u : 0u) | (zero ? 4u : 0u) | (negE ? 8u : 0u) | (nonnegE ? 16u : 0u);
-	f |= __shfl_xor_sync(0xFFFFFFFFu, f, 8); f |= __shfl_xor_sync(0xFFFFFFFFu, f, 16);
-	changes += __shfl_xor_sync(0xFFFFFFFFu, changes, 8); changes += __shfl_xor_sync(0xFFFFFFFFu, changes, 16);
-	if ((tid & 31) < 8) { atomicOr(&sFlags[j], f); atomicAdd(&sChanges[j], changes); }
+#pragma unroll
+	for (int o = J; o < 32; o <<= 1) { f |= __shfl_xor_sync(0xFFFFFFFFu, f, o); changes += __shfl_xor_sync(0xFFFFFFFFu, changes, o); } // lanes of the same block
+	if ((tid & 31) < J) { atomicOr(&sFlags[j], f); atomicAdd(&sChanges[j], changes); }
 	__syncthreads();
-	if (tid < 8 && bx0 + tid < nb)
+	if (tid < J && bx0 + tid < nb)
 		scanFlags[((size_t)bz * nb + by) * nb + bx0 + tid] = sFlags[tid] | (sChanges[tid] << 8);
 }
 
