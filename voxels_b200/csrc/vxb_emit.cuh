@@ -18,6 +18,15 @@
 //
 // Bit-exactness notes are in vxb_kernels.cuh / vxb_cell.h; the formulation is identical, only the schedule differs.
 #pragma once
+#ifndef VXB_OCC
+#define VXB_OCC 5 // resident CTAs per SM the per-block kernels are compiled for (register cap 65536 / (256 * VXB_OCC))
+#endif
+#ifndef VXB_FLAT_OCC
+#define VXB_FLAT_OCC 4 // same for the flat per-vertex kernels
+#endif
+#ifndef VXB_VB_OCC
+#define VXB_VB_OCC 8 // and for the 128-thread level-0 vertex kernel
+#endif
 
 struct __align__(128) VxbClassifySmem
 {
@@ -70,7 +79,7 @@ __device__ __forceinline__ void vxb_init_cache_page(const VxbDev& d, int level, 
 	for (int i = threadIdx.x; i < 2048; i += VXB_THREADS) page[i] = 0x00FF00FFu; // {EMPTY_MATERIAL, 0} x 2  (:424)
 }
 
-__global__ void __launch_bounds__(VXB_THREADS, 4) vxb_classify_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap1, const VxbDev d, const int level)
+__global__ void __launch_bounds__(VXB_THREADS, VXB_OCC) vxb_classify_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap1, const VxbDev d, const int level)
 {
 	extern __shared__ __align__(128) unsigned char smemRaw[];
 	VxbClassifySmem& s = *reinterpret_cast<VxbClassifySmem*>(smemRaw);
@@ -254,7 +263,7 @@ __device__ __forceinline__ unsigned vxb_rank_of(const unsigned int* nt32, const 
 // TIER 1: items come from bigList (CAP_C = 4096 = every possible block).
 // group 0 = level 0 only, group 1 = levels >= 1, group 2 = all levels (single-stream runs)
 template <int CAP_C, int TIER>
-__global__ void __launch_bounds__(VXB_THREADS, (CAP_C <= 1024 ? 4 : 2)) vxb_decide_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap1, const VxbDev d, const int group)
+__global__ void __launch_bounds__(VXB_THREADS, (CAP_C <= 1024 ? VXB_OCC : 2)) vxb_decide_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap1, const VxbDev d, const int group)
 {
 	const int levelLo = (group == 1) ? 1 : 0, levelHi = (group == 0) ? 0 : d.levels - 1, g2 = group & 1;
 	const int levelCount = levelHi - levelLo + 1;
@@ -460,7 +469,7 @@ __global__ void vxb_mark_split_kernel(const VxbDev d)
 	d.counters->splitRecords = d.counters->records;
 }
 
-__global__ void __launch_bounds__(VXB_THREADS) vxb_vertex_kernel(const VxbDev d, const int part)
+__global__ void __launch_bounds__(VXB_THREADS, VXB_FLAT_OCC) vxb_vertex_kernel(const VxbDev d, const int part)
 {
 	__shared__ unsigned sUsed[8];
 	if (threadIdx.x < 8) sUsed[threadIdx.x] = 0;
@@ -531,7 +540,7 @@ struct __align__(128) VxbVertexBlockSmem
 };
 
 template <bool MAT_TILES>
-__global__ void __launch_bounds__(VXB_VB_THREADS, 8) vxb_vertex_block_kernel(const __grid_constant__ CUtensorMap tmapDist19, const __grid_constant__ CUtensorMap tmapMat,
+__global__ void __launch_bounds__(VXB_VB_THREADS, VXB_VB_OCC) vxb_vertex_block_kernel(const __grid_constant__ CUtensorMap tmapDist19, const __grid_constant__ CUtensorMap tmapMat,
 	const __grid_constant__ CUtensorMap tmapBlend, const VxbDev d)
 {
 	extern __shared__ __align__(128) unsigned char smemRaw[];
@@ -844,7 +853,7 @@ __device__ __forceinline__ VxbTransVertexDesc vxb_lattice_vertex_desc(unsigned v
 	return vxb_transition_vertex_desc_ab(vd, vxb_lattice_sample(p, (vd >> 4) & 0xF), vxb_lattice_sample(p, vd & 0xF), vxbGTransitionCornerData);
 }
 
-__global__ void __launch_bounds__(VXB_THREADS, 4) vxb_transition_kernel(const VxbDev d)
+__global__ void __launch_bounds__(VXB_THREADS, VXB_OCC) vxb_transition_kernel(const VxbDev d)
 {
 	extern __shared__ __align__(128) unsigned char smemRaw[];
 	VxbTransSmem& s = *reinterpret_cast<VxbTransSmem*>(smemRaw);
@@ -1073,7 +1082,7 @@ __global__ void __launch_bounds__(VXB_THREADS, 4) vxb_transition_kernel(const Vx
 }
 
 // flat: one thread per new transition vertex (:1980-2092)
-__global__ void __launch_bounds__(VXB_THREADS) vxb_transition_vertex_kernel(const VxbDev d)
+__global__ void __launch_bounds__(VXB_THREADS, VXB_FLAT_OCC) vxb_transition_vertex_kernel(const VxbDev d)
 {
 	__shared__ unsigned sUsed[8];
 	if (threadIdx.x < 8) sUsed[threadIdx.x] = 0;
