@@ -31,6 +31,37 @@ def test_library_exports_every_declared_symbol():
 def test_struct_mirrors_match_header_sizes():
     assert capi.RECORD_DTYPE.itemsize == 128 and capi.VERTEX_DTYPE.itemsize == 48
     assert C.sizeof(capi.ResultInfo) == 4 * 4 + 8 * 8 + 20 * 4 + 8 * 4 + 4 + 4
+    assert C.sizeof(capi.RegionInfo) == 8 + 2 * 12 * 3 * 4 + 2 * 12 * 4
+    assert C.sizeof(capi.ShardExchange) == 4 + 4 + 8 + 8 + 8 + 8 + 4 + 4          # vxb_shard_exchange
+
+
+def test_merge_results_rebases_offsets_and_sorts():
+    """capi.merge_results (sharded runs): arenas concatenated in rank order, directory in the reference's block order."""
+    import numpy as np
+
+    def fake(level_coord_pairs, nv, ni):
+        r = capi.Result.__new__(capi.Result)
+        r.n, r.info = 64, None
+        r.records = np.zeros(len(level_coord_pairs), capi.RECORD_DTYPE)
+        voff = ioff = 0
+        for k, (l, c) in enumerate(level_coord_pairs):
+            r.records[k]["level"], r.records[k]["coord_id"] = l, c
+            r.records[k]["vertex_count"], r.records[k]["index_count"] = nv, ni
+            r.records[k]["vertex_offset"], r.records[k]["index_offset"] = voff, ioff
+            voff += nv; ioff += ni
+        r.verts = np.zeros(voff, capi.VERTEX_DTYPE); r.verts["pos"][:, 0] = np.arange(voff) + 1000 * level_coord_pairs[0][1]
+        r.idx = np.arange(ioff, dtype=np.uint32)
+        r.tverts = np.zeros(0, capi.VERTEX_DTYPE); r.tidx = np.zeros(0, np.uint32)
+        r.stats = np.arange(20, dtype=np.uint32)
+        return r
+
+    a, b = fake([(0, 5), (1, 0)], 3, 6), fake([(0, 2), (0, 9)], 2, 3)
+    m = capi.merge_results([a, b])
+    assert [(int(r["level"]), int(r["coord_id"])) for r in m.records] == [(0, 2), (0, 5), (0, 9), (1, 0)]
+    assert len(m.verts) == 10 and len(m.idx) == 18 and np.array_equal(m.stats, 2 * np.arange(20))
+    first_b = m.records[0]                                   # rank 1's first block: offsets moved behind rank 0's arenas
+    assert first_b["vertex_offset"] == 6 and first_b["index_offset"] == 12
+    assert m.verts["pos"][first_b["vertex_offset"], 0] == 2000.0
 
 
 def test_no_cpu_fallback_without_a_device():

@@ -115,3 +115,27 @@ def test_split_level_matches_the_reference_block_sizes():
     assert split_level(1024, 8) == 4
     assert split_level(1024, 1) == 7      # one rank: every level nests, nothing to exchange
     assert split_level(64, 2) == 2
+
+
+def test_balanced_planes_even_out_the_work():
+    sys.path.insert(0, REPO)
+    import numpy as np
+    from voxels_b200.dist import balanced_planes, layer_weights_from_directory, split_level
+    from voxels_b200 import capi
+    # a terrain: all the work in a few middle layers (z is up)
+    w = np.zeros(128)
+    w[50:70] = 100.0
+    planes = balanced_planes(w, 4, 2)                       # boundaries on multiples of 2 layers = 32 planes
+    assert planes[0] == 0 and planes[-1] == 2048 and all(p % 32 == 0 for p in planes) and planes == sorted(planes)
+    loads = [w[a // 16:b // 16].sum() for a, b in zip(planes[:-1], planes[1:])]
+    assert max(loads) <= 600.0                               # 2000 units over 4 ranks, cells of 200: the optimum is 600
+    assert all(b > a for a, b in zip(planes[:-1], planes[1:]))   # no empty slab
+    assert split_level(2048, 4, planes) == 2                 # 32-plane alignment: levels 0 and 1 nest
+    assert split_level(2048, 4, [0, 512, 1024, 1536, 2048]) == 6
+    # weights from a directory: a level-1 block spreads over the two level-0 layers it covers, plus the scan's volume term
+    recs = np.zeros(2, capi.RECORD_DTYPE)
+    recs["level"] = [0, 1]
+    recs["coord_id"] = [3 * 16 * 16, 1 * 8 * 8]              # n = 256: level-0 block layer 3, level-1 block layer 1 (= level-0 layers 2, 3)
+    recs["vertex_count"] = [100, 60]
+    lw = layer_weights_from_directory(256, recs, scan_units_per_byte=0.0)
+    assert lw.tolist() == [0.0, 0.0, 30.0, 130.0] + [0.0] * 12

@@ -102,10 +102,8 @@ struct vxb_context
 	DevBuf<VxbCounters> counters;
 	DevBuf<VxbMaterialLut> lut;
 	uint64_t capV = 0, capI = 0, capTV = 0, capTI = 0;
-	CUtensorMap tmap, tmap1, tmapDist19, tmapMat, tmapBlend;
+	CUtensorMap tmap, tmap1, tmapDist19;
 	int gridVertexBlock = 0;
-	bool vbMatTiles = false;
-	size_t vbSmem = 0;
 	DevBuf<uint8_t> lattice1;
 	bool haveLattice1 = false;
 	int gridClassify = 0, gridDecideSmall = 0, gridDecideBig = 0, gridTransition = 0;
@@ -198,8 +196,6 @@ int buildTensorMap(vxb_context* ctx)
 {
 	int r = encodeTileMap(ctx, &ctx->tmap, ctx->dDist, ctx->n);
 	if (r == VXB_OK) r = encodeTileMap(ctx, &ctx->tmapDist19, ctx->dDist, ctx->n, 19, VXB_DTILE_PITCH);
-	if (r == VXB_OK) r = encodeTileMap(ctx, &ctx->tmapMat, ctx->dMat, ctx->n);
-	if (r == VXB_OK) r = encodeTileMap(ctx, &ctx->tmapBlend, ctx->dBlend, ctx->n);
 	if (r != VXB_OK) return r;
 	// even-lattice copy for level 1 (written by vxb_scan_kernel each run); needs at least one 16-sample row
 	ctx->haveLattice1 = ctx->n >= 64;
@@ -502,16 +498,14 @@ int vxb_create(int device, vxb_context** out)
 	if (e != cudaSuccess || !fn) { fail(nullptr, VXB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available", e); delete ctx; return VXB_ERR_CUDA; }
 	ctx->encodeTiled = reinterpret_cast<EncodeTiledFn>(fn);
 
-	ctx->vbMatTiles = getenv("VXB200_VB_MAT_TILES") != nullptr;
 	ctx->graphDisabled = getenv("VXB200_NO_GRAPH") != nullptr; // plain launches (debugging, A/B timing)
-	ctx->vbSmem = ctx->vbMatTiles ? sizeof(VxbVertexBlockSmem) : offsetof(VxbVertexBlockSmem, mat);
 	struct KernelSetup { const void* fn; size_t smem; int* grid; const char* name; int threads; };
 	const KernelSetup setups[5] = {
 		{ (const void*)vxb_classify_kernel, sizeof(VxbClassifySmem), &ctx->gridClassify, "vxb_classify_kernel", VXB_THREADS },
 		{ (const void*)vxb_decide_kernel<1024, 0>, sizeof(VxbDecideSmemSmall), &ctx->gridDecideSmall, "vxb_decide_kernel<1024>", VXB_THREADS },
 		{ (const void*)vxb_decide_kernel<4096, 1>, sizeof(VxbDecideSmemBig), &ctx->gridDecideBig, "vxb_decide_kernel<4096>", VXB_THREADS },
 		{ (const void*)vxb_transition_kernel, sizeof(VxbTransSmem), &ctx->gridTransition, "vxb_transition_kernel", VXB_THREADS },
-		{ ctx->vbMatTiles ? (const void*)vxb_vertex_block_kernel<true> : (const void*)vxb_vertex_block_kernel<false>, ctx->vbSmem, &ctx->gridVertexBlock, "vxb_vertex_block_kernel", VXB_VB_THREADS },
+		{ (const void*)vxb_vertex_block_kernel, sizeof(VxbVertexBlockSmem), &ctx->gridVertexBlock, "vxb_vertex_block_kernel", VXB_VB_THREADS },
 	};
 	for (const KernelSetup& k : setups)
 	{
@@ -946,8 +940,7 @@ static int runPolygonize(vxb_context* ctx, uint32_t maxLevels, uint32_t flags, c
 			};
 			auto flatGroup = [&](int part, cudaStream_t st) {
 				timer.begin(4);
-				if (part == 0 && ctx->vbMatTiles) vxb_vertex_block_kernel<true><<<ctx->gridVertexBlock, VXB_VB_THREADS, ctx->vbSmem, st>>>(ctx->tmapDist19, ctx->tmapMat, ctx->tmapBlend, dev);
-				else if (part == 0) vxb_vertex_block_kernel<false><<<ctx->gridVertexBlock, VXB_VB_THREADS, ctx->vbSmem, st>>>(ctx->tmapDist19, ctx->tmapMat, ctx->tmapBlend, dev);
+				if (part == 0) vxb_vertex_block_kernel<<<ctx->gridVertexBlock, VXB_VB_THREADS, sizeof(VxbVertexBlockSmem), st>>>(ctx->tmapDist19, dev);
 				else vxb_vertex_kernel<<<flatGrid, VXB_THREADS, 0, st>>>(dev, part);
 				timer.end(); ++launches; ++ctx->kindLaunches[4];
 				timer.begin(5);
@@ -1024,14 +1017,14 @@ static int runPolygonize(vxb_context* ctx, uint32_t maxLevels, uint32_t flags, c
 		bool replayed = false;
 		if (phase == 0 && !region && !kernelTimes && !ctx->graphDisabled)
 		{
-			std::vector<unsigned char> key(sizeof(VxbDev) + 5 * sizeof(CUtensorMap) + 64, 0);
+			std::vector<unsigned char> key(sizeof(VxbDev) + 3 * sizeof(CUtensorMap) + 64, 0);
 			unsigned char* k = key.data();
 			memcpy(k, &dev, sizeof(VxbDev)); k += sizeof(VxbDev);
-			const CUtensorMap* maps[5] = { &ctx->tmap, &ctx->tmap1, &ctx->tmapDist19, &ctx->tmapMat, &ctx->tmapBlend };
+			const CUtensorMap* maps[3] = { &ctx->tmap, &ctx->tmap1, &ctx->tmapDist19 };
 			for (const CUtensorMap* mp : maps) { memcpy(k, mp, sizeof(CUtensorMap)); k += sizeof(CUtensorMap); }
 			const void* ptrs[4] = { ctx->dDist, ctx->scanFlags.p, ctx->blockInfo.p, ctx->haveLattice1 ? ctx->lattice1.p : nullptr };
 			memcpy(k, ptrs, sizeof(ptrs)); k += sizeof(ptrs);
-			const int scalars[4] = { computed, (int)validBytes, (int)ctx->vbMatTiles, (int)n };
+			const int scalars[4] = { computed, (int)validBytes, (int)nb0, (int)n };
 			memcpy(k, scalars, sizeof(scalars));
 			if (!ctx->graphExec || key != ctx->graphKey)
 			{

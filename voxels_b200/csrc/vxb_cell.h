@@ -70,17 +70,16 @@ VXB_FN size_t vxb_index(const VxbGrid& g, int x, int y, int z)
 VXB_FN int vxb_dist(const VxbGrid& g, int x, int y, int z) { return g.dist[vxb_index(g, x, y, z)]; }
 
 // Level-0 block neighbourhood staged in shared memory (device only): distance samples for coordinates
-// [origin-1, origin+17] per axis (19^3, rows of 32 bytes), material / blend for [origin, origin+16] (17^3).
-// Clamping at the grid edges is baked in when the tile is filled, so reads need no clamp.
+// [origin-1, origin+17] per axis (19^3).  Clamping at the grid edges is baked in when the tile is filled.
 struct VxbTileView
 {
 	const signed char* dist;     // 19 x 19 rows of 48 bytes, first sample = (sx, sy, sz)
-	const unsigned char* mat;    // index ((z - oz) * 17 + (y - oy)) * 32 + (x - ox)
+	const unsigned char* mat;    // the global material / blend volumes (two taps per vertex: not worth a tile)
 	const unsigned char* blend;
 	int ox, oy, oz;              // block origin (grid coordinates of its first voxel)
 	int sx, sy, sz;              // first coordinate held by the distance tile: (origin.x - 16, origin.y - 1, origin.z - 1)
 	                             // - TMA needs a 16-byte aligned innermost start -, or 0 on the low grid edge
-	int n;                       // != 0: material / blend are the global volumes (mat, blend = their bases), n = grid edge
+	int n;                       // grid edge
 };
 
 // low edge: coordinate -1 clamps to 0 = the tile's first sample; the far edge is replicated when the tile is filled
@@ -91,7 +90,6 @@ VXB_FN int vxb_dist(const VxbTileView& g, int x, int y, int z)
 }
 VXB_FN size_t vxb_tile_mat_index(const VxbTileView& g, int x, int y, int z)
 {
-	if (!g.n) return (size_t)(((z - g.oz) * 17 + (y - g.oy)) * 32 + (x - g.ox));
 	const int m = g.n - 1; // the two material taps of a vertex (cell corners) are clamped like every grid read (:1242-1244)
 	return ((size_t)(z > m ? m : z) * g.n + (y > m ? m : y)) * g.n + (x > m ? m : x);
 }

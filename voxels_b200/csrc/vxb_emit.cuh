@@ -521,9 +521,10 @@ __global__ void __launch_bounds__(VXB_THREADS, VXB_FLAT_OCC) vxb_vertex_kernel(c
 	if (threadIdx.x < 8 && sUsed[threadIdx.x]) atomicOr(&d.counters->usedMaterials[threadIdx.x], sUsed[threadIdx.x]);
 }
 
-// Level-0 vertices, one emitted block per CTA iteration: the block's distance neighbourhood (19^3) and its material /
-// blend samples (17^3) are staged by three TMA loads, so the 16 one-byte taps of a vertex come from shared memory
-// instead of 16 separate 32-byte DRAM sectors.  Grid-edge clamping (:1198, :1242-1244) is baked into the tiles.
+// Level-0 vertices, one emitted block per CTA iteration: the block's distance neighbourhood (19^3) is staged by one TMA
+// load, so the twelve distance taps of a vertex come from shared memory instead of separate 32-byte DRAM sectors.
+// Grid-edge clamping (:1198) is baked into the tile.  (Staging the material / blend samples too was slower: the extra
+// 18 KB per CTA halve the occupancy.)
 #define VXB_DTILE_PITCH 48
 #define VXB_VB_CELLS 512   // blocks with more non-trivial cells read their records from global memory
 #define VXB_VB_THREADS 128 // a block has ~350 new vertices: 128-thread CTAs waste fewer lanes in the last round and more of them fit an SM
@@ -535,13 +536,9 @@ struct __align__(128) VxbVertexBlockSmem
 	unsigned int item;
 	unsigned int used[8];
 	uint4 cells[VXB_VB_CELLS]; // the block's cell records, staged while the TMA load is in flight
-	__align__(128) unsigned char mat[VXB_TILE_BYTES + 96]; // the material / blend tiles are optional (MAT_TILES)
-	unsigned char blend[VXB_TILE_BYTES + 96];
 };
 
-template <bool MAT_TILES>
-__global__ void __launch_bounds__(VXB_VB_THREADS, VXB_VB_OCC) vxb_vertex_block_kernel(const __grid_constant__ CUtensorMap tmapDist19, const __grid_constant__ CUtensorMap tmapMat,
-	const __grid_constant__ CUtensorMap tmapBlend, const VxbDev d)
+__global__ void __launch_bounds__(VXB_VB_THREADS, VXB_VB_OCC) vxb_vertex_block_kernel(const __grid_constant__ CUtensorMap tmapDist19, const VxbDev d)
 {
 	extern __shared__ __align__(128) unsigned char smemRaw[];
 	VxbVertexBlockSmem& s = *reinterpret_cast<VxbVertexBlockSmem*>(smemRaw);
@@ -569,13 +566,8 @@ __global__ void __launch_bounds__(VXB_VB_THREADS, VXB_VB_OCC) vxb_vertex_block_k
 		if (tid == 0)
 		{
 			vxb_fence_proxy_async();
-			vxb_mbar_expect_tx(&s.mbar, VXB_DTILE_BYTES + (MAT_TILES ? 2 * VXB_TILE_BYTES : 0));
+			vxb_mbar_expect_tx(&s.mbar, VXB_DTILE_BYTES);
 			vxb_tma_load_3d(s.dist, &tmapDist19, sx, sy, sz, &s.mbar);
-			if (MAT_TILES)
-			{
-				vxb_tma_load_3d(s.mat, &tmapMat, bx * 16, by * 16, bz * 16, &s.mbar);
-				vxb_tma_load_3d(s.blend, &tmapBlend, bx * 16, by * 16, bz * 16, &s.mbar);
-			}
 		}
 		if (staged)
 			for (unsigned i = tid; i < ntc; i += VXB_VB_THREADS) s.cells[i] = *reinterpret_cast<const uint4*>(&d.cellRecs[cellBase + i]);
@@ -592,7 +584,6 @@ __global__ void __launch_bounds__(VXB_VB_THREADS, VXB_VB_OCC) vxb_vertex_block_k
 				signed char* r = s.dist + i * VXB_DTILE_PITCH;
 				r[lastX + 1] = r[lastX]; r[lastX + 2] = r[lastX];
 			}
-			if (MAT_TILES) for (int i = tid; i < 17 * 17; i += VXB_VB_THREADS) { s.mat[i * VXB_TILE_PITCH + 16] = s.mat[i * VXB_TILE_PITCH + 15]; s.blend[i * VXB_TILE_PITCH + 16] = s.blend[i * VXB_TILE_PITCH + 15]; }
 		}
 		if (by == nb - 1)
 		{
@@ -602,12 +593,6 @@ __global__ void __launch_bounds__(VXB_VB_THREADS, VXB_VB_OCC) vxb_vertex_block_k
 				const int z = i / VXB_DTILE_PITCH, x = i % VXB_DTILE_PITCH;
 				signed char* p = s.dist + z * 19 * VXB_DTILE_PITCH + x;
 				for (int q = lastY + 1; q < 19; ++q) p[q * VXB_DTILE_PITCH] = p[lastY * VXB_DTILE_PITCH];
-			}
-			if (MAT_TILES) for (int i = tid; i < 17 * 17; i += VXB_VB_THREADS)
-			{
-				const int z = i / 17, x = i % 17;
-				s.mat[(z * 17 + 16) * VXB_TILE_PITCH + x] = s.mat[(z * 17 + 15) * VXB_TILE_PITCH + x];
-				s.blend[(z * 17 + 16) * VXB_TILE_PITCH + x] = s.blend[(z * 17 + 15) * VXB_TILE_PITCH + x];
 			}
 		}
 		if (bz == nb - 1)
@@ -619,18 +604,11 @@ __global__ void __launch_bounds__(VXB_VB_THREADS, VXB_VB_OCC) vxb_vertex_block_k
 				signed char* p = s.dist + y * VXB_DTILE_PITCH + x;
 				for (int q = lastZ + 1; q < 19; ++q) p[q * 19 * VXB_DTILE_PITCH] = p[lastZ * 19 * VXB_DTILE_PITCH];
 			}
-			if (MAT_TILES) for (int i = tid; i < 17 * 17; i += VXB_VB_THREADS)
-			{
-				const int y = i / 17, x = i % 17;
-				s.mat[(16 * 17 + y) * VXB_TILE_PITCH + x] = s.mat[(15 * 17 + y) * VXB_TILE_PITCH + x];
-				s.blend[(16 * 17 + y) * VXB_TILE_PITCH + x] = s.blend[(15 * 17 + y) * VXB_TILE_PITCH + x];
-			}
 		}
 		__syncthreads();
 		VxbTileView g;
 		g.dist = s.dist; g.ox = bx * 16; g.oy = by * 16; g.oz = bz * 16; g.sx = sx; g.sy = sy; g.sz = sz;
-		if (MAT_TILES) { g.mat = s.mat; g.blend = s.blend; g.n = 0; }
-		else { g.mat = d.grid.mat; g.blend = d.grid.blend; g.n = d.n; }
+		g.mat = d.grid.mat; g.blend = d.grid.blend; g.n = d.n; // the two material / blend taps of a vertex stay global loads
 		for (unsigned j = tid; j < nverts; j += VXB_VB_THREADS)
 		{
 			const unsigned ci = e >> 4; const int k = e & 15;
