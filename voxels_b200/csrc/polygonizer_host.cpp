@@ -104,6 +104,31 @@ void releaseContext(vxb_context* c)
 	if (g_ContextPool.size() < 2) g_ContextPool.push_back(c); else vxb_destroy(c);
 }
 
+// The page-locked staging of a full upload (3 n^3 bytes) costs tens of milliseconds to allocate, and clients create a
+// Polygonizer per call: the buffers live in a process-wide pool like the contexts (never freed at exit on purpose: the
+// CUDA runtime may already be gone when static destructors run).
+struct Staging
+{
+	HostBuffer Dist, Mat, Blend;
+};
+std::vector<Staging*> g_StagingPool;
+
+Staging* acquireStaging()
+{
+	{
+		std::lock_guard<std::mutex> guard(g_PoolLock);
+		if (!g_StagingPool.empty()) { Staging* s = g_StagingPool.back(); g_StagingPool.pop_back(); return s; }
+	}
+	return new Staging;
+}
+
+void releaseStaging(Staging* s)
+{
+	if (!s) return;
+	std::lock_guard<std::mutex> guard(g_PoolLock);
+	if (g_StagingPool.size() < 2) g_StagingPool.push_back(s); else delete s;
+}
+
 // host copy of the output of ONE device run
 struct Arena
 {
@@ -160,7 +185,10 @@ public:
 
 private:
 	PolygonSurface* ExecuteIncremental(const Grid& grid, SurfaceImpl* surface, ModificationImpl* modification);
-	HostBuffer StageDist, StageMat, StageBlend;
+	Staging* m_Staging = nullptr;
+
+public:
+	~TransVoxelImpl() { releaseStaging(m_Staging); }
 };
 
 namespace
@@ -274,11 +302,12 @@ PolygonSurface* TransVoxelImpl::Execute(const Grid& grid, const MaterialMap* mat
 	// ---- grid -> device: every block through the public accessors, decompressed in parallel into pinned staging ----
 	const unsigned nb = n / 16;
 	const size_t volume = size_t(n) * n * n;
-	if (!StageDist.ensure(volume) || !StageMat.ensure(volume) || !StageBlend.ensure(volume)) return fail("pinned staging allocation failed");
+	if (!m_Staging) m_Staging = acquireStaging();
+	if (!m_Staging->Dist.ensure(volume) || !m_Staging->Mat.ensure(volume) || !m_Staging->Blend.ensure(volume)) return fail("pinned staging allocation failed");
 	{
-		char* sd = static_cast<char*>(StageDist.p);
-		unsigned char* sm = static_cast<unsigned char*>(StageMat.p);
-		unsigned char* sb = static_cast<unsigned char*>(StageBlend.p);
+		char* sd = static_cast<char*>(m_Staging->Dist.p);
+		unsigned char* sm = static_cast<unsigned char*>(m_Staging->Mat.p);
+		unsigned char* sb = static_cast<unsigned char*>(m_Staging->Blend.p);
 		const long total = long(nb) * nb * nb;
 		#pragma omp parallel for schedule(static)
 		for (long b = 0; b < total; ++b)
@@ -288,8 +317,8 @@ PolygonSurface* TransVoxelImpl::Execute(const Grid& grid, const MaterialMap* mat
 			grid.GetBlockMaterialData(coords, sm + size_t(b) * 4096, sb + size_t(b) * 4096);
 		}
 	}
-	if (vxb_grid_upload_blocks(ctx, n, static_cast<const int8_t*>(StageDist.p), static_cast<const uint8_t*>(StageMat.p),
-		static_cast<const uint8_t*>(StageBlend.p)) != VXB_OK) return fail("grid upload failed");
+	if (vxb_grid_upload_blocks(ctx, n, static_cast<const int8_t*>(m_Staging->Dist.p), static_cast<const uint8_t*>(m_Staging->Mat.p),
+		static_cast<const uint8_t*>(m_Staging->Blend.p)) != VXB_OK) return fail("grid upload failed");
 
 	// ---- polygonize on the device ----
 	if (vxb_polygonize(ctx, 0, 0) != VXB_OK) return fail("polygonization failed");
@@ -361,7 +390,8 @@ PolygonSurface* TransVoxelImpl::ExecuteIncremental(const Grid& grid, SurfaceImpl
 		if (b1[a] < b0[a]) b1[a] = b0[a];
 	}
 	const size_t count = size_t(b1[0] - b0[0] + 1) * (b1[1] - b0[1] + 1) * (b1[2] - b0[2] + 1);
-	if (!StageDist.ensure(count * 4096) || !StageMat.ensure(count * 4096) || !StageBlend.ensure(count * 4096)) return fail("pinned staging allocation failed");
+	if (!m_Staging) m_Staging = acquireStaging();
+	if (!m_Staging->Dist.ensure(count * 4096) || !m_Staging->Mat.ensure(count * 4096) || !m_Staging->Blend.ensure(count * 4096)) return fail("pinned staging allocation failed");
 	std::vector<uint32_t> coords(count * 3);
 	{
 		size_t i = 0;
@@ -369,13 +399,13 @@ PolygonSurface* TransVoxelImpl::ExecuteIncremental(const Grid& grid, SurfaceImpl
 		{
 			coords[i * 3] = x; coords[i * 3 + 1] = y; coords[i * 3 + 2] = z;
 			const float3 c = float3(float(x), float(y), float(z));
-			grid.GetBlockDistanceData(c, static_cast<char*>(StageDist.p) + i * 4096);
-			grid.GetBlockMaterialData(c, static_cast<unsigned char*>(StageMat.p) + i * 4096, static_cast<unsigned char*>(StageBlend.p) + i * 4096);
+			grid.GetBlockDistanceData(c, static_cast<char*>(m_Staging->Dist.p) + i * 4096);
+			grid.GetBlockMaterialData(c, static_cast<unsigned char*>(m_Staging->Mat.p) + i * 4096, static_cast<unsigned char*>(m_Staging->Blend.p) + i * 4096);
 		}
 	}
 	g_Trace.mark(0);
-	if (vxb_grid_update_blocks(ctx, uint32_t(count), coords.data(), static_cast<const int8_t*>(StageDist.p), static_cast<const uint8_t*>(StageMat.p),
-		static_cast<const uint8_t*>(StageBlend.p)) != VXB_OK) return fail("grid update failed");
+	if (vxb_grid_update_blocks(ctx, uint32_t(count), coords.data(), static_cast<const int8_t*>(m_Staging->Dist.p), static_cast<const uint8_t*>(m_Staging->Mat.p),
+		static_cast<const uint8_t*>(m_Staging->Blend.p)) != VXB_OK) return fail("grid update failed");
 
 	g_Trace.mark(1);
 	// ---- re-polygonize the dirty boxes of all levels ----
