@@ -104,7 +104,8 @@ def reference_run(n, steps, warmup, origin_x, torch, device_for_gen):
     dist, mat, blend = synth.terrain(n, device_for_gen, origin=(origin_x, 0))
     dist, mat, blend = dist.cpu().numpy(), mat.cpu().numpy(), blend.cpu().numpy()
     grid = ref.grid_from_dense(dist, mat, blend)
-    threads = ref.L.vxh_max_threads()
+    # every host core this process may use (torchrun exports OMP_NUM_THREADS=1, which is not what the reference would run with)
+    threads = max(ref.L.vxh_max_threads(), len(os.sched_getaffinity(0)))
     times = []
     for i in range(warmup + steps):
         s, sec = ref.polygonize(grid, threads=threads)
