@@ -94,25 +94,35 @@ class ClockSampler:
         return {"sm_mhz": clocks[len(clocks) // 2] if clocks else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(clocks)}
 
 
-def reference_run(n, steps, warmup, origin_x, torch, device_for_gen):
-    """Times the reference's own Polygonizer::Execute (all host threads) on the terrain tile; returns (Mvoxels/s, info)."""
+def reference_run(n, steps, warmup, origin_x, torch, device_for_gen, budget_s=200.0):
+    """Times the reference's own Polygonizer::Execute (all host threads) on the terrain tile; returns (Mvoxels/s, info).
+    The sample is the full n^3 tile when warmup + steps executions fit the time budget, else the (n/2)^3 tile of the
+    same terrain (bounded sample: the run must end within a few minutes whatever K is)."""
     import harness
     from voxels_b200 import synth
     if not os.path.exists(harness.REF_LIB):
         return None, {"unavailable": "oracle/_ref/libvxh_ref.so not built (make -C oracle ref needs the reference checkout)"}
     ref = harness.reference()
-    dist, mat, blend = synth.terrain(n, device_for_gen, origin=(origin_x, 0))
-    dist, mat, blend = dist.cpu().numpy(), mat.cpu().numpy(), blend.cpu().numpy()
-    grid = ref.grid_from_dense(dist, mat, blend)
     # every host core this process may use (torchrun exports OMP_NUM_THREADS=1, which is not what the reference would run with)
     threads = max(ref.L.vxh_max_threads(), len(os.sched_getaffinity(0)))
-    times = []
-    for i in range(warmup + steps):
-        s, sec = ref.polygonize(grid, threads=threads)
-        ref.surface_destroy(s)
-        if i >= warmup:
-            times.append(sec)
-    ref.grid_destroy(grid)
+    while True:
+        dist, mat, blend = synth.terrain(n, device_for_gen, origin=(origin_x, 0))
+        dist, mat, blend = dist.cpu().numpy(), mat.cpu().numpy(), blend.cpu().numpy()
+        grid = ref.grid_from_dense(dist, mat, blend)
+        times = []
+        shrink = False
+        for i in range(warmup + steps):
+            s, sec = ref.polygonize(grid, threads=threads)
+            ref.surface_destroy(s)
+            if i == 0 and n > 256 and sec * (warmup + steps) > budget_s:
+                shrink = True
+                break
+            if i >= warmup:
+                times.append(sec)
+        ref.grid_destroy(grid)
+        if not shrink:
+            break
+        n //= 2
     per_step = sum(times) / len(times)
     return n ** 3 / per_step / 1e6, {"cores": threads, "seconds_per_execute": per_step, "best_seconds": min(times), "n": n}
 
@@ -141,10 +151,11 @@ def main():
             "impl": "reference", "metric": "Mvoxels/s polygonized", "value": value, "unit": "Mvoxels/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": info["seconds_per_execute"] * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int8 samples / fp32 vertices", "data": "synthetic",
-            "config": {"workload": "%d^3 seeded Perlin terrain, all LOD levels + transition cells (reference Polygonizer::Execute)" % sample_n,
+            "config": {"workload": "%d^3 seeded Perlin terrain, all LOD levels + transition cells (reference Polygonizer::Execute)" % info["n"],
                        "impl": "unmodified reference sources, g++ -O2 -fopenmp -msse2, OMP threads = %d" % info["cores"]},
             "cpu_baseline": {"value": value, "unit": "Mvoxels/s", "cores": info["cores"], "kind": "reference",
-                             "sample": "full %d^3 grid, Polygonizer::Execute only (grid build excluded), mean of %d runs" % (sample_n, args.steps)},
+                             "sample": "%s %d^3 grid, Polygonizer::Execute only (grid build excluded), mean of %d runs"
+                                       % ("full" if info["n"] == sample_n else "bounded sample (time budget):", info["n"], args.steps)},
             "e2e": {"value": value, "unit": "Mvoxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": time.time() - t0,
         }
@@ -371,8 +382,8 @@ def main():
         v, ci = reference_run(sample_n, 2, 0, 0, torch, dev)
         if v is not None:
             cpu = {"value": v, "unit": "Mvoxels/s", "cores": ci["cores"], "kind": "reference",
-                   "sample": "full %d^3 terrain tile (same bytes as the GPU step when sizes match), Polygonizer::Execute only, mean of 2 runs, %.1f s wall incl. grid build"
-                             % (sample_n, time.time() - t0)}
+                   "sample": "%s %d^3 terrain tile (same bytes as the GPU step when sizes match), Polygonizer::Execute only, mean of 2 runs, %.1f s wall incl. grid build"
+                             % ("full" if ci["n"] == sample_n else "bounded sample:", ci["n"], time.time() - t0)}
         else:
             cpu = {"value": None, "unit": "Mvoxels/s", "cores": 0, "kind": "reference", "sample": ci["unavailable"]}
 
