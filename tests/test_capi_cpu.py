@@ -107,3 +107,17 @@ def test_pack_dense_matches_reference_bytes(reference):
         blob = reference.grid_pack(g)
         reference.grid_destroy(g)
         assert np.array_equal(blob, voxels_b200.pack_dense(dist, mat, blend)), name
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/vxb200.h is the FFI boundary: it must compile as C99 on its own (no C++/torch types)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if not gcc:
+        pytest.skip("no gcc")
+    src = tmp_path / "t.c"
+    src.write_text('#include "vxb200.h"\nint main(void) { vxb_result_info i; vxb_block_record r; vxb_shard_exchange x; (void)i; (void)r; (void)x; return 0; }\n')
+    out = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(REPO, "include"), "-fsyntax-only", str(src)],
+                         capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
