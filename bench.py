@@ -346,29 +346,41 @@ def main():
             out3 = {k: torch.empty_like(v).pin_memory() for k, v in out.items()}
             into3 = {k: v.data_ptr() for k, v in out3.items()}
             psteps = max(4, esteps * 2)
-            gate = threading.Barrier(3)
+            gate = threading.Barrier(3, timeout=300)
+            failures = []
 
             def worker(c, buffers):
-                for i in range(psteps + 1):
-                    if i == 1:
-                        gate.wait()  # first step = warm-up
-                    c.upload_packed(h_blob.data_ptr(), blob_bytes)
-                    c.polygonize(args.levels, flags)
-                    c.download(into=buffers)
-                gate.wait()
+                try:
+                    for i in range(psteps + 1):
+                        if i == 1:
+                            gate.wait()  # first step = warm-up
+                        c.upload_packed(h_blob.data_ptr(), blob_bytes)
+                        c.polygonize(args.levels, flags)
+                        c.download(into=buffers)
+                    gate.wait()
+                except Exception as exc:  # never leave the other parties waiting
+                    failures.append(repr(exc))
+                    gate.abort()
 
             threads = [threading.Thread(target=worker, args=(ctx2, into)), threading.Thread(target=worker, args=(ctx3, into3))]
             for t in threads:
                 t.start()
-            gate.wait()
-            t0 = time.perf_counter()
-            gate.wait()
-            wall_ms = 1e3 * (time.perf_counter() - t0)
+            try:
+                gate.wait()
+                t0 = time.perf_counter()
+                gate.wait()
+                wall_ms = 1e3 * (time.perf_counter() - t0)
+            except threading.BrokenBarrierError:
+                wall_ms = None
             for t in threads:
                 t.join()
-            ms_pipe = max_over_ranks(wall_ms / (2 * psteps))
-            e2e["two_in_flight"] = {"value": whole_job_throughput(n, world, ms_pipe), "unit": "Mvoxels/s", "ms_per_step": ms_pipe, "steps": 2 * psteps,
-                                    "timing": "host clock over all steps; two host threads, one context each, same calls as e2e"}
+            if wall_ms is not None and not failures:
+                ms_pipe = max_over_ranks(wall_ms / (2 * psteps))
+                e2e["two_in_flight"] = {"value": whole_job_throughput(n, world, ms_pipe), "unit": "Mvoxels/s", "ms_per_step": ms_pipe, "steps": 2 * psteps,
+                                        "timing": "host clock over all steps; two host threads, one context each, same calls as e2e"}
+            else:
+                max_over_ranks(0.0)  # keep the ranks' collectives aligned
+                e2e["two_in_flight"] = {"value": None, "error": "; ".join(failures) or "barrier timeout"}
             ctx3.close()
             del out3
         ctx2.close()
