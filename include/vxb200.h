@@ -90,8 +90,7 @@ void vxb_destroy(vxb_context* ctx);
 const char* vxb_last_error(const vxb_context* ctx);   /* ctx may be NULL: error of a failed vxb_create */
 /* cudaStream_t the context launches on (as void*), for callers that time with their own events */
 void* vxb_stream(vxb_context* ctx);
-/* cudaStream_t on which a sharded run's caller enqueues the exchange between the two phases (ordered after phase 0's
- * classification; phase 1 makes only the coarse levels wait for it) */
+/* the context's second cudaStream_t (transition cells run on it next to the flat vertex / triangle kernels) */
 void* vxb_exchange_stream(vxb_context* ctx);
 
 /* ---- grid (input provider side: VoxelGrid accessors, src/VoxelGrid.h:49-55) ------------------ */
@@ -155,61 +154,68 @@ int vxb_polygonize_region(vxb_context* ctx, const float min_corner[3], const flo
 int vxb_region_info_get(vxb_context* ctx, vxb_region_info* out);
 
 /* ---- Sharded runs: ONE grid polygonized by `world` ranks, one GPU each (BASELINE configs[3]) ----
- * Rank r owns the z-slab of planes [plane_begin[r], plane_begin[r+1]) - plane_begin has world+1 ascending entries from 0
- * to n, multiples of 32; NULL means `world` equal slabs - and produces every block that nests in the slabs (the levels
- * whose block edge 16*2^l divides every boundary); rank 0 also produces the few blocks of the coarser levels, which
- * span slabs.  Unequal slabs are how a caller balances the ranks when the surface is not spread evenly over z (a
- * terrain: z is up, TransVoxelImpl.cpp:1289-1291).
- * Blocks are a pure function of the level-0 volumes plus the material pages of their child level
- * (TransVoxelImpl.cpp:763-837), so the only data-path exchange is ONE all-gather of the material pages of the last
- * nested level, between the two phases; block ids are the reference's full-run ids (:395-401), so the directories of
- * the ranks concatenate and sort into exactly the single-GPU directory.
+ * The reference balances its OpenMP block loop by blocks (TransVoxelImpl.cpp:500-503); so does this: WORK is dealt by
+ * blocks, independently of where the DATA lives.
  *
- * Every rank's context must see the whole cube through its grid pointers (vxb_cube_create below maps the peers'
- * slabs over NVLink; a single-process caller can simply share one dense upload through vxb_grid_set_device).  A rank
- * reads outside its slab only the first planes of the next slab (far cell corners, normals) and - rank 0 - the sparse
- * samples of the coarse levels.
+ * Data.  The cube (vxb_cube_*): each volume is ONE contiguous n^3 virtual range on every rank; the z-axis is cut into
+ * pieces of `group_planes` planes, piece p backed by the HBM of rank p % world (cyclic, so that a terrain's surface - a
+ * few z-layers - is spread over all ranks' memories) and mapped into every peer over NVLink.  Kernels and TMA tensor maps
+ * address the cube exactly like a single-GPU grid.  A fourth channel holds the even-lattice copy the level-1 tiles read.
  *
- *   vxb_polygonize_sharded(ctx, r, w, pb, 0, flags)  enqueue: scan of the slab (+1 block layer either side), classification
- *                                                    of the nested levels.  Does not synchronise.
- *   vxb_shard_exchange_info(ctx, r, w, pb, &x)       the two device buffers rank 0 needs complete before phase 1, to be
- *                                                    exchanged IN PLACE on vxb_exchange_stream(ctx): rank r produced the blocks of
- *                                                    layers [pb[r], pb[r+1]) / layer_planes, layer_blocks blocks each, i.e.
- *                                                    that byte range of `valid` and 8192x that range of `pages`
- *                                                    (equal slabs: ncclAllGather / all_gather_into_tensor; unequal: grouped
- *                                                    ncclSend/ncclRecv to rank 0)
- *   vxb_polygonize_sharded(ctx, r, w, pb, 1, flags)  the coarse levels (rank 0), vertices, triangles, transition cells,
- *                                                    directory.  Result = this rank's blocks (vxb_result_info_get / download).
- * VXB_ERR_CAPACITY from phase 1 means the arenas were grown: every rank repeats both phases. */
-typedef struct vxb_shard_exchange
+ * Work.  Every rank streams its OWN pieces once (vxb_scan_kernel: flags per 16^3 block); ONE ncclAllGather makes the
+ * 1-byte-per-block info complete everywhere (exchange 0).  From it every rank derives the same work split: the
+ * "super-blocks" (blocks of the last level with more than 4096 blocks) in coordinate order, cut where the running count of
+ * surface-crossing level-0 blocks passes total * r / world.  A rank polygonizes every level up to the super-block
+ * level inside its super-blocks - the material votes of a cell only read its own children (:763-837), so this chain is
+ * rank-local - and stores the pages of its super-blocks into every peer's page buffer (peer stores, exchange 1, ordered by a
+ * second tiny all-gather).  The few coarse levels above are classified by every rank (identical votes), and block b of
+ * level l is emitted by rank (b + l) % world.  Block ids are the reference's full-run ids (:395-401), so the directories
+ * of the ranks concatenate and sort into exactly the single-GPU directory; statistics are the sum over the ranks.
+ *
+ *   vxb_cube_create(ctx, n, rank, world, group_planes)      reserve the ranges, back + map the local pieces (0 = n / world)
+ *   vxb_cube_export / vxb_cube_import                        one POSIX file descriptor per (channel, piece), sent to the peers
+ *   vxb_shard_configure(ctx, rank, world, group_planes)     work-split state + the page buffer (needs a grid: the cube, or for
+ *                                                            virtual ranks of one process a shared vxb_grid_set_device)
+ *   vxb_shard_export / vxb_shard_import                      the page buffer, likewise (or vxb_shard_set_peer with raw pointers)
+ *   vxb_shard_nccl_unique_id / vxb_shard_nccl_init           the communicator of the two all-gathers (libnccl.so.2 via dlopen; the
+ *                                                            id travels by the caller's own means, e.g. torch.distributed)
+ *   vxb_polygonize_sharded(ctx, 3, flags)                    the whole step, one stream-ordered sequence (replayed as a CUDA graph)
+ *   vxb_polygonize_sharded(ctx, 0 | 1 | 2, flags)            the three pieces around the two exchanges, for callers that do
+ *                                                            the exchanges themselves (tests: device copies between virtual ranks):
+ *                                                            after 0 gather block_info (rank r's chunk = bytes [r, r+1) * chunk_bytes),
+ *                                                            after 1 synchronise all ranks; 2 blocks and delivers the result.
+ * VXB_ERR_CAPACITY means the arenas were grown: every rank repeats the run. */
+typedef struct vxb_nccl_id { char internal[128]; } vxb_nccl_id;   /* = ncclUniqueId */
+typedef struct vxb_shard_buffers
 {
-	uint32_t split_level;   /* levels [0, split_level) nest in a slab; == levels when world == 1 (nothing to exchange) */
-	uint32_t level;         /* the level whose pages are exchanged (split_level - 1) */
-	void* pages;            /* device: {material id, blend} of every cell of every block of `level`, block-major (z,y,x) */
+	void* block_info;             /* device: one byte per level-0 block, rank-major (the layout of the all-gather) */
+	uint64_t block_info_bytes;
+	uint64_t chunk_bytes;         /* block_info_bytes / world */
+	void* pages;                  /* device: {material id, blend} of every cell of every super-block, block-major (z,y,x) */
 	uint64_t pages_bytes;
-	void* valid;            /* device: one byte per block of `level` */
+	void* valid;                  /* device: one byte per super-block */
 	uint64_t valid_bytes;
-	uint32_t layer_planes;  /* planes per block layer of `level` (16 << level) */
-	uint32_t layer_blocks;  /* blocks per z-layer of `level` */
-} vxb_shard_exchange;
-int vxb_polygonize_sharded(vxb_context* ctx, uint32_t rank, uint32_t world, const uint32_t* plane_begin, uint32_t phase, uint32_t flags);
-int vxb_shard_exchange_info(vxb_context* ctx, uint32_t rank, uint32_t world, const uint32_t* plane_begin, vxb_shard_exchange* out);
+	uint32_t super_level;
+	uint32_t pad;
+} vxb_shard_buffers;
+int vxb_shard_configure(vxb_context* ctx, uint32_t rank, uint32_t world, uint32_t group_planes);
+int vxb_shard_buffers_get(vxb_context* ctx, vxb_shard_buffers* out);
+int vxb_shard_set_peer(vxb_context* ctx, uint32_t peer, void* pages, void* valid);
+int vxb_shard_export(vxb_context* ctx, int* fd);
+int vxb_shard_import(vxb_context* ctx, uint32_t peer, int fd);
+int vxb_shard_nccl_unique_id(vxb_nccl_id* id);
+int vxb_shard_nccl_init(vxb_context* ctx, const vxb_nccl_id* id, uint32_t rank, uint32_t world);
+int vxb_polygonize_sharded(vxb_context* ctx, uint32_t phase, uint32_t flags);
 
-/* The cube of a sharded run in device memory: each of the three volumes is ONE contiguous n^3 virtual range
- * (cuMemAddressReserve); this rank's z-slab is backed by its own HBM (cuMemCreate + cuMemMap), the other slabs are the
- * peers' allocations imported through POSIX file descriptors and mapped over NVLink / NVSwitch.  Kernels and TMA
- * tensor maps address the cube exactly like a single-GPU grid.  Every slab (n^2 bytes per plane) must start and end on
- * a multiple of the allocation granularity (2 MiB).
- *   vxb_cube_create   reserve + back + map the local slab; the context's grid becomes the cube
- *   vxb_cube_export   channel 0/1/2 = distance / material / blend: a file descriptor for the local slab (caller closes it
- *                     after sending it to the peers, e.g. over a Unix socket with SCM_RIGHTS)
- *   vxb_cube_import   map peer `peer`'s slab of `channel` from a received descriptor (the descriptor can be closed after)
- *   vxb_cube_slab     device pointers and byte size of the local slab (fill it with cudaMemcpy / a generator kernel)
- * All slabs must be mapped and filled (a barrier across the ranks) before vxb_polygonize_sharded. */
-int vxb_cube_create(vxb_context* ctx, uint32_t n, uint32_t rank, uint32_t world, const uint32_t* plane_begin);
-int vxb_cube_export(vxb_context* ctx, uint32_t channel, int* fd);
-int vxb_cube_import(vxb_context* ctx, uint32_t peer, uint32_t channel, int fd);
-int vxb_cube_slab(vxb_context* ctx, int8_t** dist, uint8_t** mat, uint8_t** blend, uint64_t* bytes_per_channel);
+/* The cube: see above.  Every piece (group_planes * n^2 bytes; the lattice channel an eighth of that) must be a multiple of
+ * the allocation granularity (2 MiB); when only the lattice pieces are not, the cube has three channels and level 1 gathers
+ * its tiles.  vxb_cube_info: number of pieces, channels and bytes per piece of each channel (uint64_t[4]).
+ * vxb_cube_piece: device pointers of piece `piece` (any rank's: the whole cube is addressable) and its size in bytes. */
+int vxb_cube_create(vxb_context* ctx, uint32_t n, uint32_t rank, uint32_t world, uint32_t group_planes);
+int vxb_cube_info(vxb_context* ctx, uint32_t* pieces, uint32_t* channels, uint64_t* piece_bytes);
+int vxb_cube_export(vxb_context* ctx, uint32_t channel, uint32_t piece, int* fd);
+int vxb_cube_import(vxb_context* ctx, uint32_t channel, uint32_t piece, int fd);
+int vxb_cube_piece(vxb_context* ctx, uint32_t piece, int8_t** dist, uint8_t** mat, uint8_t** blend, uint64_t* bytes_per_channel);
 /* Copies the directory (sorted by level, then coord_id = the reference's block order) and the
  * arenas to HOST memory sized from vxb_result_info spans.  Vertices are 48-byte
  * Voxels::PolygonVertex (include/Polygonizer.h:14-48).  Any pointer may be NULL to skip it. */
@@ -231,9 +237,10 @@ void vxb_host_free(void* p);
 int vxb_set_capacity(vxb_context* ctx, uint64_t vertices, uint64_t indices, uint64_t trans_vertices, uint64_t trans_indices);
 
 /* Per-kernel device time of the last vxb_polygonize run with VXB_FLAG_KERNEL_TIMES, for bench.py's roofline line:
- * which = 0: vxb_scan_kernel (streams the level-0 distance volume once), 1: block info + selection kernels,
- * 2: vxb_classify_kernel (one launch per level), 3: vxb_decide_kernel (two capacity tiers), 4: vxb_vertex_kernel,
- * 5: vxb_triangle_kernel, 6: vxb_transition_kernel, 7: vxb_finish_kernel.  Milliseconds, summed per kind. */
+ * which = 0: vxb_scan_kernel (streams the level-0 distance volume once), 1: block info, sign-mix pyramid + selection kernels,
+ * 2: vxb_block_kernel<1>/<2> (levels >= 1: classification, votes, decisions) + vxb_decide_kernel<4096>, 3: vxb_block_kernel<0>
+ * (level 0: classification, decisions, vertices and triangles in one pass), 4: vxb_vertex_kernel (levels >= 1),
+ * 5: vxb_triangle_kernel (levels >= 1), 6: vxb_transition_kernel + vertices, 7: vxb_finish_kernel.  Milliseconds, summed per kind. */
 int vxb_kernel_ms(vxb_context* ctx, int which, float* ms, uint32_t* launches);
 
 #ifdef __cplusplus

@@ -32,7 +32,8 @@ def test_struct_mirrors_match_header_sizes():
     assert capi.RECORD_DTYPE.itemsize == 128 and capi.VERTEX_DTYPE.itemsize == 48
     assert C.sizeof(capi.ResultInfo) == 4 * 4 + 8 * 8 + 20 * 4 + 8 * 4 + 4 + 4
     assert C.sizeof(capi.RegionInfo) == 8 + 2 * 12 * 3 * 4 + 2 * 12 * 4
-    assert C.sizeof(capi.ShardExchange) == 4 + 4 + 8 + 8 + 8 + 8 + 4 + 4          # vxb_shard_exchange
+    assert C.sizeof(capi.ShardBuffers) == 8 * 7 + 4 + 4                                 # vxb_shard_buffers
+    assert C.sizeof(capi.NcclId) == 128                                                  # vxb_nccl_id = ncclUniqueId
 
 
 def test_merge_results_rebases_offsets_and_sorts():
@@ -117,7 +118,7 @@ def test_header_is_plain_c(tmp_path):
     if not gcc:
         pytest.skip("no gcc")
     src = tmp_path / "t.c"
-    src.write_text('#include "vxb200.h"\nint main(void) { vxb_result_info i; vxb_block_record r; vxb_shard_exchange x; (void)i; (void)r; (void)x; return 0; }\n')
+    src.write_text('#include "vxb200.h"\nint main(void) { vxb_result_info i; vxb_block_record r; vxb_shard_buffers x; vxb_nccl_id y; (void)y; (void)i; (void)r; (void)x; return 0; }\n')
     out = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(REPO, "include"), "-fsyntax-only", str(src)],
                          capture_output=True, text=True)
     assert out.returncode == 0, out.stderr

@@ -63,7 +63,7 @@ import os, sys, tempfile
 sys.path.insert(0, os.environ["VXB_REPO"])
 import numpy as np, torch
 from voxels_b200 import capi
-from voxels_b200.dist import Ranks, exchange_fds, gather_directories, slab_planes, split_level
+from voxels_b200.dist import Ranks, exchange_fds, gather_directories, owned_pieces, default_group_planes
 r = Ranks("gloo", torch.device("cpu"))
 assert r.world == 2
 # 1. descriptors travel between the ranks (what carries the cuMemExportToShareableHandle handles of the slabs)
@@ -80,8 +80,9 @@ for c, fd in enumerate(got[peer]):
         f.seek(0); texts.append(f.read().decode())
 assert texts == ["rank%d-channel%d" % (peer, c) for c in range(3)], texts
 # 2. directory all-gather: counts, then padded payload; reference order = (level, coord_id)
-n = 256
-z0, z1 = slab_planes(n, r.rank, r.world)
+n = 1024
+g = default_group_planes(n, r.world)
+mine_pieces = owned_pieces(n, r.rank, r.world, g)
 recs = np.zeros(3 + r.rank, capi.RECORD_DTYPE)
 recs["level"] = [0, 0, 1] + [2] * r.rank
 recs["coord_id"] = [10 + 100 * r.rank, 5 + 100 * r.rank, 7 + r.rank] + [0] * r.rank
@@ -91,7 +92,11 @@ assert len(allrec) == 7 and list(allrec["level"]) == sorted(allrec["level"])
 keys = list(zip(allrec["level"].tolist(), allrec["coord_id"].tolist()))
 assert keys == sorted(keys)
 assert owner.tolist() == [0, 0, 1, 1, 0, 1, 1], owner.tolist()
-os.write(1, ("RESULT rank=%d slab=%d-%d split=%d blocks=%d\n" % (r.rank, z0, z1, split_level(n, r.world), len(allrec))).encode())
+# 3. the NCCL id of the in-step all-gathers travels as a python object
+ids = [b"x" * 128 if r.rank == 0 else None]
+r.td.broadcast_object_list(ids, src=0)
+assert ids[0] == b"x" * 128
+os.write(1, ("RESULT rank=%d group=%d pieces=%d first=%d-%d blocks=%d\n" % (r.rank, g, len(mine_pieces), mine_pieces[0][1], mine_pieces[0][2], len(allrec))).encode())
 r.close()
 '''
 
@@ -105,37 +110,21 @@ def test_sharded_plumbing_two_ranks_gloo(tmp_path):
     out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
     lines = sorted(l for l in out.stdout.splitlines() if l.startswith("RESULT"))
-    assert lines == ["RESULT rank=0 slab=0-128 split=4 blocks=7", "RESULT rank=1 slab=128-256 split=4 blocks=7"], out.stdout + out.stderr
+    assert lines == ["RESULT rank=0 group=32 pieces=16 first=0-32 blocks=7", "RESULT rank=1 group=32 pieces=16 first=32-64 blocks=7"], out.stdout + out.stderr
 
 
-def test_split_level_matches_the_reference_block_sizes():
+def test_cyclic_pieces_cover_the_grid_once():
     sys.path.insert(0, REPO)
-    from voxels_b200.dist import split_level
-    assert split_level(2048, 8) == 5      # 16,32,64,128,256-voxel blocks nest in 256-plane slabs
-    assert split_level(1024, 8) == 4
-    assert split_level(1024, 1) == 7      # one rank: every level nests, nothing to exchange
-    assert split_level(64, 2) == 2
-
-
-def test_balanced_planes_even_out_the_work():
-    sys.path.insert(0, REPO)
-    import numpy as np
-    from voxels_b200.dist import balanced_planes, layer_weights_from_directory, split_level
-    from voxels_b200 import capi
-    # a terrain: all the work in a few middle layers (z is up)
-    w = np.zeros(128)
-    w[50:70] = 100.0
-    planes = balanced_planes(w, 4, 2)                       # boundaries on multiples of 2 layers = 32 planes
-    assert planes[0] == 0 and planes[-1] == 2048 and all(p % 32 == 0 for p in planes) and planes == sorted(planes)
-    loads = [w[a // 16:b // 16].sum() for a, b in zip(planes[:-1], planes[1:])]
-    assert max(loads) <= 600.0                               # 2000 units over 4 ranks, cells of 200: the optimum is 600
-    assert all(b > a for a, b in zip(planes[:-1], planes[1:]))   # no empty slab
-    assert split_level(2048, 4, planes) == 2                 # 32-plane alignment: levels 0 and 1 nest
-    assert split_level(2048, 4, [0, 512, 1024, 1536, 2048]) == 6
-    # weights from a directory: a level-1 block spreads over the two level-0 layers it covers, plus the scan's volume term
-    recs = np.zeros(2, capi.RECORD_DTYPE)
-    recs["level"] = [0, 1]
-    recs["coord_id"] = [3 * 16 * 16, 1 * 8 * 8]              # n = 256: level-0 block layer 3, level-1 block layer 1 (= level-0 layers 2, 3)
-    recs["vertex_count"] = [100, 60]
-    lw = layer_weights_from_directory(256, recs, scan_units_per_byte=0.0)
-    assert lw.tolist() == [0.0, 0.0, 30.0, 130.0] + [0.0] * 12
+    from voxels_b200.dist import default_group_planes, owned_pieces
+    for n, world in ((1024, 1), (1024, 2), (1024, 4), (1024, 8), (2048, 8), (512, 4), (256, 2)):
+        g = default_group_planes(n, world)
+        assert g % 32 == 0 and n % g == 0 and (n // g) % world == 0
+        assert (g * n * n) % (2 << 20) == 0                        # allocation granularity of the volume pieces
+        seen = []
+        for r in range(world):
+            mine = owned_pieces(n, r, world, g)
+            assert all(p % world == r and z1 - z0 == g and z0 == p * g for p, z0, z1 in mine)
+            seen += [p for p, _, _ in mine]
+        assert sorted(seen) == list(range(n // g))                 # every piece exactly one owner
+    # a terrain's surface (a few z-layers) is spread over all ranks' memories: 8 ranks, 1024^3 => 32-plane pieces
+    assert default_group_planes(1024, 8) == 32 and default_group_planes(2048, 8) == 32

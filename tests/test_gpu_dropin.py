@@ -116,3 +116,39 @@ def test_incremental_edits_match_reference(reference, dropin, name, n, count):
         assert np.array_equal(ma, mb), "edit %d ModifiedBlocks differ" % step
     for lib, g, s, mod in state:
         lib.modification_destroy(mod); lib.surface_destroy(s); lib.grid_destroy(g)
+
+
+def test_config5_terrain_512_1000_edits(reference, dropin):
+    """BASELINE configs[4] as written: 512^3 terrain, 1000 seeded sphere add/subtract edits near the surface, incremental
+    re-polygonization after each; the two surfaces (all levels, statistics, ModifiedBlocks) are compared every 100 edits."""
+    import sys
+    import torch
+    from voxels_b200 import synth
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import bench_edits
+    n = 512
+    dist, mat, blend = (t.cpu().numpy() for t in synth.terrain(n, "cuda:0" if torch.cuda.is_available() else "cpu"))
+    edits = bench_edits.edit_sequence(n, 1000, dist)
+    state = []
+    for lib in (reference, dropin):
+        g = lib.grid_from_dense(dist, mat, blend)
+        s, _ = lib.polygonize(g)
+        state.append([lib, g, s, lib.modification_create()])
+    for step, (pos, radius, extent, kind) in enumerate(edits):
+        boxes = []
+        for lib, g, s, mod in state:
+            box = lib.grid_inject_sphere(g, pos, radius, extent, kind)
+            s2, _ = lib.polygonize(g, modification=mod, surface=s, box=box)
+            assert s2 == s
+            boxes.append(box)
+        assert np.array_equal(boxes[0], boxes[1])
+        if (step + 1) % 100 == 0:
+            (la, ga, sa, ma), (lb, gb, sb, mb) = state
+            problems = []
+            for l in range(la.surface_levels(sa)):
+                problems += compare.level_diff(la.surface_level(sa, l), lb.surface_level(sb, l), "edit %d L%d" % (step, l))
+            assert not problems, "\n".join(problems[:10])
+            assert np.array_equal(la.surface_stats(sa), lb.surface_stats(sb))
+            assert np.array_equal(la.modification_blocks(ma), lb.modification_blocks(mb))
+    for lib, g, s, mod in state:
+        lib.modification_destroy(mod); lib.surface_destroy(s); lib.grid_destroy(g)

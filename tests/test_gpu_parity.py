@@ -217,3 +217,43 @@ def test_full_size_properties_1024(gpu_context):
     gpu_context.polygonize(1, voxels_b200.FLAG_NO_TRANSITIONS)
     res3 = gpu_context.download()
     assert golden_hash.level_digests(res.level(0)) == golden_hash.level_digests(res3.level(0))
+
+
+# ---- BASELINE sizes against the unmodified reference (oracle/_ref), end to end (TransVoxelImpl.cpp:468-538) ------
+def _terrain_numpy(n):
+    import torch
+    from voxels_b200 import synth
+    dist, mat, blend = synth.terrain(n, "cuda:0")
+    torch.cuda.synchronize()
+    return tuple(t.cpu().numpy() for t in (dist, mat, blend))
+
+
+def test_config2_terrain_512_level0_regular_cells_against_reference(reference, gpu_context):
+    """BASELINE configs[1]: 512^3 Perlin terrain, single LOD, regular cells only - level 0 bit-exact vs the reference."""
+    import voxels_b200
+    dist, mat, blend = _terrain_numpy(512)
+    problems, res = run_both(reference, gpu_context, dist, mat, blend, max_levels=1, flags=voxels_b200.FLAG_NO_TRANSITIONS)
+    assert not problems, "\n".join(problems[:10])
+    assert len(res.records) > 1000
+
+
+def test_config2_terrain_512_all_levels_against_reference(reference, gpu_context):
+    dist, mat, blend = _terrain_numpy(512)
+    problems, res = run_both(reference, gpu_context, dist, mat, blend)
+    assert not problems, "\n".join(problems[:10])
+
+
+def test_config3_terrain_1024_levels_0_to_3_with_transitions_against_reference(reference, gpu_context):
+    """BASELINE configs[2]: 1024^3 terrain, 4 LOD levels + transition cells.  The reference always computes all 7
+    levels; levels 0-3 (level-3 transitions included: 3 is not the last level) are compared bit-exactly."""
+    dist, mat, blend = _terrain_numpy(1024)
+    problems, res = run_both(reference, gpu_context, dist, mat, blend, max_levels=4)
+    assert not problems, "\n".join(problems[:10])
+    assert res.info.levels_computed == 4 and res.info.trans_vertex_total > 0
+
+
+def test_config3_terrain_1024_all_levels_against_reference(reference, gpu_context):
+    """The bench workload itself (1024^3, all 7 levels + transitions): every block, vertex, index and the statistics."""
+    dist, mat, blend = _terrain_numpy(1024)
+    problems, res = run_both(reference, gpu_context, dist, mat, blend)
+    assert not problems, "\n".join(problems[:10])

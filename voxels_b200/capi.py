@@ -34,9 +34,14 @@ class RegionInfo(C.Structure):
                 ("id_start", C.c_uint32 * 12), ("block_count", C.c_uint32 * 12)]
 
 
-class ShardExchange(C.Structure):
-    _fields_ = [("split_level", C.c_uint32), ("level", C.c_uint32), ("pages", C.c_void_p), ("pages_bytes", C.c_uint64),
-                ("valid", C.c_void_p), ("valid_bytes", C.c_uint64), ("layer_planes", C.c_uint32), ("layer_blocks", C.c_uint32)]
+class ShardBuffers(C.Structure):
+    _fields_ = [("block_info", C.c_void_p), ("block_info_bytes", C.c_uint64), ("chunk_bytes", C.c_uint64), ("pages", C.c_void_p),
+                ("pages_bytes", C.c_uint64), ("valid", C.c_void_p), ("valid_bytes", C.c_uint64), ("super_level", C.c_uint32),
+                ("pad", C.c_uint32)]
+
+
+class NcclId(C.Structure):
+    _fields_ = [("internal", C.c_char * 128)]
 
 
 ERR_CAPACITY = -4
@@ -92,12 +97,19 @@ def load_library():
         "vxb_grid_update_blocks": (C.c_int, [vp, u32, vp, vp, vp, vp]),
         "vxb_polygonize_region": (C.c_int, [vp, vp, vp, u32]),
         "vxb_region_info_get": (C.c_int, [vp, C.POINTER(RegionInfo)]),
-        "vxb_polygonize_sharded": (C.c_int, [vp, u32, u32, vp, u32, u32]),
-        "vxb_shard_exchange_info": (C.c_int, [vp, u32, u32, vp, C.POINTER(ShardExchange)]),
-        "vxb_cube_create": (C.c_int, [vp, u32, u32, u32, vp]),
-        "vxb_cube_export": (C.c_int, [vp, u32, C.POINTER(C.c_int)]),
+        "vxb_polygonize_sharded": (C.c_int, [vp, u32, u32]),
+        "vxb_shard_configure": (C.c_int, [vp, u32, u32, u32]),
+        "vxb_shard_buffers_get": (C.c_int, [vp, C.POINTER(ShardBuffers)]),
+        "vxb_shard_set_peer": (C.c_int, [vp, u32, vp, vp]),
+        "vxb_shard_export": (C.c_int, [vp, C.POINTER(C.c_int)]),
+        "vxb_shard_import": (C.c_int, [vp, u32, C.c_int]),
+        "vxb_shard_nccl_unique_id": (C.c_int, [C.POINTER(NcclId)]),
+        "vxb_shard_nccl_init": (C.c_int, [vp, C.POINTER(NcclId), u32, u32]),
+        "vxb_cube_create": (C.c_int, [vp, u32, u32, u32, u32]),
+        "vxb_cube_info": (C.c_int, [vp, C.POINTER(u32), C.POINTER(u32), C.POINTER(u64 * 4)]),
+        "vxb_cube_export": (C.c_int, [vp, u32, u32, C.POINTER(C.c_int)]),
         "vxb_cube_import": (C.c_int, [vp, u32, u32, C.c_int]),
-        "vxb_cube_slab": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(u64)]),
+        "vxb_cube_piece": (C.c_int, [vp, u32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(u64)]),
         "vxb_result_download": (C.c_int, [vp, vp, vp, vp, vp, vp]),
         "vxb_set_capacity": (C.c_int, [vp, u64, u64, u64, u64]),
         "vxb_kernel_ms": (C.c_int, [vp, C.c_int, C.POINTER(C.c_float), C.POINTER(u32)]),
@@ -115,8 +127,19 @@ def load_library():
 EXPORTED_SYMBOLS = ["vxb_create", "vxb_destroy", "vxb_last_error", "vxb_stream", "vxb_exchange_stream", "vxb_grid_upload_dense",
                     "vxb_grid_upload_blocks", "vxb_grid_upload_packed", "vxb_pack_dense_bound", "vxb_pack_dense", "vxb_grid_set_device", "vxb_grid_device_pointers", "vxb_set_materials",
                     "vxb_polygonize", "vxb_polygonize_region", "vxb_region_info_get", "vxb_grid_update_blocks", "vxb_result_info_get", "vxb_result_download", "vxb_set_capacity", "vxb_kernel_ms",
-                    "vxb_result_unmapped_materials", "vxb_host_alloc", "vxb_host_free", "vxb_polygonize_sharded", "vxb_shard_exchange_info",
-                    "vxb_cube_create", "vxb_cube_export", "vxb_cube_import", "vxb_cube_slab"]
+                    "vxb_result_unmapped_materials", "vxb_host_alloc", "vxb_host_free", "vxb_polygonize_sharded", "vxb_shard_configure",
+                    "vxb_shard_buffers_get", "vxb_shard_set_peer", "vxb_shard_export", "vxb_shard_import", "vxb_shard_nccl_unique_id",
+                    "vxb_shard_nccl_init", "vxb_cube_create", "vxb_cube_info", "vxb_cube_export", "vxb_cube_import", "vxb_cube_piece"]
+
+
+def nccl_unique_id():
+    """128 bytes from ncclGetUniqueId (through libvxb200.so's dlopen of libnccl.so.2)."""
+    L = load_library()
+    nid = NcclId()
+    rc = L.vxb_shard_nccl_unique_id(C.byref(nid))
+    if rc != 0:
+        raise VxbError("vxb_shard_nccl_unique_id failed (%d): %s" % (rc, L.vxb_last_error(None).decode()))
+    return bytes(C.string_at(C.byref(nid), 128))
 
 
 def _ptr(a):
@@ -282,47 +305,62 @@ class Context:
         self._check(self.L.vxb_polygonize_region(self.h, _ptr(lo), _ptr(hi), flags), "vxb_polygonize_region")
         return self.info()
 
-    # ---- sharded runs (include/vxb200.h: vxb_polygonize_sharded, vxb_cube_*) ----
-    @staticmethod
-    def _planes(planes, world):
-        if planes is None:
-            return None, None
-        arr = np.ascontiguousarray(planes, np.uint32)
-        assert arr.size == world + 1, "plane_begin needs world + 1 entries"
-        return arr, _ptr(arr)
+    # ---- sharded runs (include/vxb200.h: vxb_polygonize_sharded, vxb_shard_*, vxb_cube_*) ----
+    def shard_configure(self, rank, world, group_planes=0):
+        self._check(self.L.vxb_shard_configure(self.h, rank, world, group_planes), "vxb_shard_configure")
 
-    def polygonize_sharded(self, rank, world, phase, flags=0, planes=None):
-        """Returns 0, or ERR_CAPACITY from phase 1 (arenas grown: every rank repeats both phases)."""
-        keep, pb = self._planes(planes, world)
-        rc = self.L.vxb_polygonize_sharded(self.h, rank, world, pb, phase, flags)
-        if rc == ERR_CAPACITY and phase == 1:
+    def shard_buffers(self):
+        x = ShardBuffers()
+        self._check(self.L.vxb_shard_buffers_get(self.h, C.byref(x)), "vxb_shard_buffers_get")
+        return x
+
+    def shard_set_peer(self, peer, pages, valid):
+        self._check(self.L.vxb_shard_set_peer(self.h, peer, C.c_void_p(pages), C.c_void_p(valid)), "vxb_shard_set_peer")
+
+    def shard_export(self):
+        fd = C.c_int(-1)
+        self._check(self.L.vxb_shard_export(self.h, C.byref(fd)), "vxb_shard_export")
+        return fd.value
+
+    def shard_import(self, peer, fd):
+        self._check(self.L.vxb_shard_import(self.h, peer, fd), "vxb_shard_import")
+
+    def shard_nccl_init(self, id_bytes, rank, world):
+        nid = NcclId()
+        C.memmove(C.byref(nid), bytes(id_bytes), 128)
+        self._check(self.L.vxb_shard_nccl_init(self.h, C.byref(nid), rank, world), "vxb_shard_nccl_init")
+
+    def polygonize_sharded(self, phase, flags=0):
+        """phase 0 / 1 / 2: the pieces around the two exchanges; 3: the whole step (NCCL inside).  Returns 0, or
+        ERR_CAPACITY from phase 2 / 3 (arenas grown: every rank repeats the run)."""
+        rc = self.L.vxb_polygonize_sharded(self.h, phase, flags)
+        if rc == ERR_CAPACITY and phase >= 2:
             return rc
         self._check(rc, "vxb_polygonize_sharded")
         return 0
 
-    def shard_exchange_info(self, rank, world, planes=None):
-        x = ShardExchange()
-        keep, pb = self._planes(planes, world)
-        self._check(self.L.vxb_shard_exchange_info(self.h, rank, world, pb, C.byref(x)), "vxb_shard_exchange_info")
-        return x
-
-    def cube_create(self, n, rank, world, planes=None):
-        keep, pb = self._planes(planes, world)
-        self._check(self.L.vxb_cube_create(self.h, n, rank, world, pb), "vxb_cube_create")
+    def cube_create(self, n, rank, world, group_planes=0):
+        self._check(self.L.vxb_cube_create(self.h, n, rank, world, group_planes), "vxb_cube_create")
         self.n = n
 
-    def cube_export(self, channel):
+    def cube_info(self):
+        """(pieces, channels, bytes per piece of each channel)."""
+        pieces, channels, sizes = C.c_uint32(0), C.c_uint32(0), (C.c_uint64 * 4)()
+        self._check(self.L.vxb_cube_info(self.h, C.byref(pieces), C.byref(channels), C.byref(sizes)), "vxb_cube_info")
+        return pieces.value, channels.value, list(sizes)
+
+    def cube_export(self, channel, piece):
         fd = C.c_int(-1)
-        self._check(self.L.vxb_cube_export(self.h, channel, C.byref(fd)), "vxb_cube_export")
+        self._check(self.L.vxb_cube_export(self.h, channel, piece, C.byref(fd)), "vxb_cube_export")
         return fd.value
 
-    def cube_import(self, peer, channel, fd):
-        self._check(self.L.vxb_cube_import(self.h, peer, channel, fd), "vxb_cube_import")
+    def cube_import(self, channel, piece, fd):
+        self._check(self.L.vxb_cube_import(self.h, channel, piece, fd), "vxb_cube_import")
 
-    def cube_slab(self):
-        """(dist, mat, blend) device addresses of the local slab and its size in bytes per channel."""
+    def cube_piece(self, piece):
+        """(dist, mat, blend) device addresses of a piece and its size in bytes per channel."""
         d, m, b, size = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_uint64(0)
-        self._check(self.L.vxb_cube_slab(self.h, C.byref(d), C.byref(m), C.byref(b), C.byref(size)), "vxb_cube_slab")
+        self._check(self.L.vxb_cube_piece(self.h, piece, C.byref(d), C.byref(m), C.byref(b), C.byref(size)), "vxb_cube_piece")
         return d.value, m.value, b.value, size.value
 
     def device_pointers(self):

@@ -62,9 +62,12 @@ struct HostBuffer
 	~HostBuffer() { release(); }
 };
 
+struct Arena;
+
 struct BlockView : public BlockPolygons
 {
 	unsigned Id;
+	Arena* Owner; // the host arena this block's arrays live in
 	const PolygonVertex* Vertices; unsigned VertexCount;
 	const unsigned* Indices; unsigned IndexCount;
 	const PolygonVertex* TransVertices[6]; unsigned TransVertexCount[6];
@@ -129,10 +132,13 @@ void releaseStaging(Staging* s)
 	if (g_StagingPool.size() < 2) g_StagingPool.push_back(s); else delete s;
 }
 
-// host copy of the output of ONE device run
+// host copy of the output of ONE device run.  Live = block views still pointing into it: an incremental Execute erases
+// the blocks of the dirty boxes (:443-450), and an arena whose last block is gone is freed (the reference frees the
+// erased blocks' vectors the same way).
 struct Arena
 {
 	HostBuffer Verts, Idx, TransVerts, TransIdx;
+	size_t Live = 0;
 };
 
 // The polygonized surface: block views over host arenas (one per run: the full run + one small one per edit).
@@ -193,8 +199,15 @@ public:
 
 namespace
 {
-// appends the blocks of the context's current result to the surface (views over a new arena)
-bool appendResult(vxb_context* ctx, SurfaceImpl* surface, unsigned n, const vxb_result_info& info)
+// Downloads the context's current result into a new arena and builds the block views over it, per level, in the order
+// PushBlocksToResult appends them (level, then z,y,x: :1274-1293).  Nothing of the surface is touched: a failure leaves it intact.
+struct Downloaded
+{
+	std::unique_ptr<Arena> Storage;
+	std::vector<std::vector<BlockView>> Levels;
+};
+
+bool downloadResult(vxb_context* ctx, unsigned n, const vxb_result_info& info, Downloaded& out)
 {
 	std::unique_ptr<Arena> arena(new Arena);
 	if (!arena->Verts.ensure(size_t(info.vertex_span) * sizeof(PolygonVertex) + 16) || !arena->Idx.ensure(size_t(info.index_span) * 4 + 16)
@@ -208,10 +221,12 @@ bool appendResult(vxb_context* ctx, SurfaceImpl* surface, unsigned n, const vxb_
 	const unsigned* idx = static_cast<const unsigned*>(arena->Idx.p);
 	const PolygonVertex* tverts = static_cast<const PolygonVertex*>(arena->TransVerts.p);
 	const unsigned* tidx = static_cast<const unsigned*>(arena->TransIdx.p);
-	for (const vxb_block_record& r : records) // sorted: level, then z,y,x = the order PushBlocksToResult appends in (:1274-1293)
+	out.Levels.assign(info.levels_total, std::vector<BlockView>());
+	for (const vxb_block_record& r : records)
 	{
 		BlockView b;
 		b.Id = r.id;
+		b.Owner = arena.get();
 		b.Vertices = verts + r.vertex_offset; b.VertexCount = r.vertex_count;
 		b.Indices = idx + r.index_offset; b.IndexCount = r.index_count;
 		for (int f = 0; f < 6; ++f)
@@ -223,15 +238,26 @@ bool appendResult(vxb_context* ctx, SurfaceImpl* surface, unsigned n, const vxb_
 		const unsigned bx = r.coord_id % nbl, by = (r.coord_id / nbl) % nbl, bz = r.coord_id / (nbl * nbl);
 		b.MinimalCorner = float3(float(bx * m), float(bz * m), float(by * m)); // y/z swapped on output (:1289-1291)
 		b.MaximalCorner = float3(float(bx * m + m), float(bz * m + m), float(by * m + m));
-		surface->Levels[r.level].push_back(b);
+		out.Levels[r.level].push_back(b);
 	}
-	surface->Arenas.push_back(std::move(arena));
+	arena->Live = records.size();
+	out.Storage = std::move(arena);
+	return true;
+}
+
+// appends the downloaded blocks to the surface; arenas no block points into any more are freed
+void commitResult(SurfaceImpl* surface, Downloaded& dl, const vxb_result_info& info)
+{
+	for (size_t l = 0; l < dl.Levels.size() && l < surface->Levels.size(); ++l)
+		surface->Levels[l].insert(surface->Levels[l].end(), dl.Levels[l].begin(), dl.Levels[l].end());
+	if (dl.Storage->Live) surface->Arenas.push_back(std::move(dl.Storage));
+	surface->Arenas.erase(std::remove_if(surface->Arenas.begin(), surface->Arenas.end(),
+		[](const std::unique_ptr<Arena>& a) { return a->Live == 0; }), surface->Arenas.end());
 	surface->Stats.BlocksCalculated = info.stats[0];
 	surface->Stats.TrivialCells = info.stats[1];
 	surface->Stats.NonTrivialCells = info.stats[2];
 	surface->Stats.DegenerateTrianglesRemoved = info.stats[3];
 	for (unsigned i = 0; i < PolygonizationStatistics::CASES_COUNT; ++i) surface->Stats.PerCaseCellsCount[i] = info.stats[4 + i];
-	return true;
 }
 
 // one LS_Error per vertex whose material has no mapping, as the reference logs them (:1364-1368)
@@ -328,7 +354,11 @@ PolygonSurface* TransVoxelImpl::Execute(const Grid& grid, const MaterialMap* mat
 	SurfaceImpl* surface = new SurfaceImpl;
 	surface->Extents = float3(float(n), float(n), float(n)); // (W, H, D) :481
 	surface->Levels.resize(info.levels_total);
-	if (!appendResult(ctx, surface, n, info)) { delete surface; return fail("result download failed"); }
+	{
+		Downloaded dl;
+		if (!downloadResult(ctx, n, info, dl)) { delete surface; return fail("result download failed"); }
+		commitResult(surface, dl, info);
+	}
 	surface->Context = ctx; // from here on the surface owns the device state
 	{
 		// PolygonMap::GetCacheSizeBytes (:196-220): consistency bits of every level-0 block + {id, blend} of every coarser cell
@@ -416,6 +446,10 @@ PolygonSurface* TransVoxelImpl::ExecuteIncremental(const Grid& grid, SurfaceImpl
 	if (vxb_result_info_get(ctx, &info) != VXB_OK || vxb_region_info_get(ctx, &region) != VXB_OK) return fail("no result");
 
 	g_Trace.mark(2);
+	// the new blocks come to the host first: a failed download leaves the surface as it was
+	Downloaded dl;
+	if (!downloadResult(ctx, n, info, dl)) return fail("result download failed");
+	g_Trace.mark(4);
 	// ---- splice: drop the old blocks of each level's dirty box (:443-450), append the new ones (:1293) ----
 	for (unsigned l = 0; l < region.levels && l < surface->Levels.size(); ++l)
 	{
@@ -423,14 +457,15 @@ PolygonSurface* TransVoxelImpl::ExecuteIncremental(const Grid& grid, SurfaceImpl
 		auto& blocks = surface->Levels[l];
 		blocks.erase(std::remove_if(blocks.begin(), blocks.end(), [&](const BlockView& b) {
 			const float3& c = b.MinimalCorner;
-			return c.x >= mn[0] && c.y >= mn[1] && c.z >= mn[2] && c.x < mx[0] && c.y < mx[1] && c.z < mx[2];
+			const bool dirty = c.x >= mn[0] && c.y >= mn[1] && c.z >= mn[2] && c.x < mx[0] && c.y < mx[1] && c.z < mx[2];
+			if (dirty) --b.Owner->Live;
+			return dirty;
 		}), blocks.end());
 		for (uint32_t i = 0; i < region.block_count[l]; ++i) modification->ModifiedBlocks.push_back(region.id_start[l] + i); // :463
 	}
-	g_Trace.mark(3);
-	if (!appendResult(ctx, surface, n, info)) return fail("result download failed");
+	commitResult(surface, dl, info);
 	logUnmapped(ctx);
-	g_Trace.mark(4);
+	g_Trace.mark(3);
 	++g_Trace.runs;
 	return surface;
 }

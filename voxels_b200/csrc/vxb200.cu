@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <cuda.h> // CUtensorMap types only; cuTensorMapEncodeTiled is resolved through the runtime (no libcuda link)
 
+#include <dlfcn.h>
+
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
@@ -26,7 +28,6 @@
 #include "vxb_kernels.cuh"
 #include "vxb_emit.cuh"
 
-typedef VxbDecideSmem<1024> VxbDecideSmemSmall;
 typedef VxbDecideSmem<4096> VxbDecideSmemBig;
 
 static_assert(sizeof(VxbVertex) == 48, "PolygonVertex layout");
@@ -62,7 +63,7 @@ struct vxb_context
 	int device = 0;
 	int smCount = 0;
 	cudaStream_t stream = nullptr, stream2 = nullptr;
-	cudaEvent_t evBegin = nullptr, evEnd = nullptr, evFork = nullptr, evDecide0 = nullptr, evJoin = nullptr, evDir = nullptr;
+	cudaEvent_t evBegin = nullptr, evEnd = nullptr, evFork = nullptr, evDecide0 = nullptr, evJoin = nullptr, evDir = nullptr, evVerts = nullptr;
 	cudaEvent_t evChunk[4] = { nullptr, nullptr, nullptr, nullptr };
 	std::vector<cudaEvent_t> kevents; // per-kernel timing (pairs)
 	std::string error;
@@ -105,8 +106,10 @@ struct vxb_context
 	CUtensorMap tmap, tmap1, tmapDist19;
 	int gridVertexBlock = 0;
 	DevBuf<uint8_t> lattice1;
-	bool haveLattice1 = false;
-	int gridClassify = 0, gridDecideSmall = 0, gridDecideBig = 0, gridTransition = 0;
+	uint8_t* latticePtr = nullptr;  // lattice1.p, or the cube's fourth channel
+	bool haveLattice1 = false, latticeOff = false;
+	int gridBlock[3] = { 0, 0, 0 }, gridDecideBig = 0, gridTransition = 0;
+	DevBuf<unsigned char> mixInfo, coarseDone;
 	uint64_t capC = 0;
 	bool haveFullRun = false;      // device caches (consistency / material pages) describe the current grid
 	uint32_t nextId = 0;           // PolygonMap::GetNextBlockId (TransVoxelImpl.cpp:149-152)
@@ -114,6 +117,27 @@ struct vxb_context
 	DevBuf<unsigned int> updCoords;
 	bool directoryFetched = false;
 	uint32_t shardLaunches = 0;
+	// sharded runs (vxb_shard_*)
+	struct Shard
+	{
+		bool on = false;
+		uint32_t rank = 0, world = 1, groupLayers = 0; // groups of groupLayers level-0 block layers, dealt cyclically
+		int sbLevel = 0;                               // super-block level = coarseLo - 1
+		DevBuf<unsigned char> sbMine;
+		DevBuf<unsigned int> sbWeight;
+		// level-sbLevel pages + valid flags in ONE buffer the peers can map: VMM allocation (real ranks) or cudaMalloc (virtual ranks)
+		unsigned char* pagesBuf = nullptr; size_t pagesBytes = 0, validBytes = 0, bufBytes = 0;
+		bool pagesVmm = false;
+		CUdeviceptr pagesVa = 0; CUmemGenericAllocationHandle pagesHandle = 0;
+		unsigned short* peerPages[8] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
+		unsigned char* peerValid[8] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
+		bool peerSet[8] = { false, false, false, false, false, false, false, false };
+		std::vector<std::pair<CUdeviceptr, size_t> > peerMapped;
+		std::vector<CUmemGenericAllocationHandle> peerHandles;
+		void* comm = nullptr;                          // ncclComm_t
+		DevBuf<unsigned long long> barrierBuf;         // the tiny all-gather that orders the page exchange
+		uint32_t phaseLaunches = 0;
+	} shard;
 	// the launch sequence of a full run as a CUDA graph, re-instantiated when any kernel argument changes
 	cudaGraphExec_t graphExec = nullptr;
 	std::vector<unsigned char> graphKey;
@@ -122,16 +146,15 @@ struct vxb_context
 	// the cube of a sharded run (vxb_cube_*): one virtual range per volume, this rank's slab local, peers' slabs imported
 	struct Cube
 	{
-		bool active = false;
-		uint32_t rank = 0, world = 1;
-		size_t cubeBytes = 0, planeBytes = 0;
-		std::vector<uint32_t> planes; // slab r = planes [planes[r], planes[r + 1])
-		CUdeviceptr va[3] = { 0, 0, 0 };
-		CUmemGenericAllocationHandle local[3] = { 0, 0, 0 };
+		bool active = false, lattice = false;
+		uint32_t rank = 0, world = 1, n = 0;
+		uint32_t groupPlanes = 0, pieces = 0;          // piece p = planes [p * groupPlanes, (p + 1) * groupPlanes), owner p % world
+		CUdeviceptr va[4] = { 0, 0, 0, 0 };            // distance, material, blend, even lattice ((n/2)^3)
+		size_t vaBytes[4] = { 0, 0, 0, 0 };
+		std::vector<CUmemGenericAllocationHandle> local[4]; // this rank's pieces, in order of local index (piece = rank + k * world)
 		std::vector<CUmemGenericAllocationHandle> imported;
-		std::vector<std::pair<CUdeviceptr, size_t> > mapped; // every mapped slab
-		size_t slabOffset(uint32_t r) const { return (size_t)planes[r] * planeBytes; }
-		size_t slabBytes(uint32_t r) const { return (size_t)(planes[r + 1] - planes[r]) * planeBytes; }
+		std::vector<std::pair<CUdeviceptr, size_t> > mapped; // every mapped piece
+		size_t pieceBytes(int channel) const { return channel < 3 ? (size_t)groupPlanes * n * n : (size_t)(groupPlanes / 2) * (n / 2) * (n / 2); }
 	} cube;
 	VxbCounters lastCounters;
 	size_t validBytes = 0;
@@ -172,9 +195,11 @@ int ensureGridStorage(vxb_context* ctx, uint32_t n)
 	ctx->dDist = reinterpret_cast<const int8_t*>(ctx->volDist.p);
 	ctx->dMat = ctx->volMat.p; ctx->dBlend = ctx->volBlend.p;
 	ctx->n = n; ctx->levels = levelsFor(n);
-	ctx->ownsGrid = true; ctx->haveGrid = true; ctx->haveResult = false; ctx->haveFullRun = false;
+	// haveGrid becomes true only when an upload has completed (a failed upload leaves no half-filled grid behind)
+	ctx->ownsGrid = true; ctx->haveGrid = false; ctx->haveResult = false; ctx->haveFullRun = false;
 	return VXB_OK;
 }
+
 
 int encodeTileMap(vxb_context* ctx, CUtensorMap* map, const void* base, uint32_t n, uint32_t rows = 17, uint32_t pitch = VXB_TILE_PITCH)
 {
@@ -197,65 +222,39 @@ int buildTensorMap(vxb_context* ctx)
 	int r = encodeTileMap(ctx, &ctx->tmap, ctx->dDist, ctx->n);
 	if (r == VXB_OK) r = encodeTileMap(ctx, &ctx->tmapDist19, ctx->dDist, ctx->n, 19, VXB_DTILE_PITCH);
 	if (r != VXB_OK) return r;
-	// even-lattice copy for level 1 (written by vxb_scan_kernel each run); needs at least one 16-sample row
-	ctx->haveLattice1 = ctx->n >= 64;
+	// even-lattice copy for level 1 (written by vxb_scan_kernel each run); needs at least one 16-sample row.  In a sharded
+	// run every rank writes the part of its own layers, so the copy must be shared like the volumes (the cube's fourth
+	// channel); without that level 1 gathers its tiles from the distance volume.
+	const bool cubeLattice = ctx->cube.active && ctx->cube.lattice;
+	ctx->haveLattice1 = ctx->n >= 64 && !ctx->latticeOff && (!ctx->cube.active || cubeLattice);
+	ctx->latticePtr = nullptr;
 	if (ctx->haveLattice1)
 	{
 		const size_t h = ctx->n / 2;
-		VXB_CUDA(ctx, ctx->lattice1.ensure(h * h * h));
-		r = encodeTileMap(ctx, &ctx->tmap1, ctx->lattice1.p, (uint32_t)h);
+		if (cubeLattice) ctx->latticePtr = reinterpret_cast<uint8_t*>(ctx->cube.va[3]);
+		else { VXB_CUDA(ctx, ctx->lattice1.ensure(h * h * h)); ctx->latticePtr = ctx->lattice1.p; }
+		r = encodeTileMap(ctx, &ctx->tmap1, ctx->latticePtr, (uint32_t)h);
 	}
 	else ctx->tmap1 = ctx->tmap;
 	return r;
 }
 
-// Validates a slab layout (NULL = `world` equal slabs) and returns its boundaries and split level: levels [0, split)
-// have blocks that nest in every slab, i.e. every boundary is a multiple of 16 << (split - 1).
-int shardLayout(vxb_context* ctx, uint32_t n, int levels, uint32_t rank, uint32_t world, const uint32_t* planeBegin, const char* who,
-	std::vector<uint32_t>& planes, int& split)
+int finishUpload(vxb_context* ctx)
 {
-	char buf[200];
-	if (world == 0 || world > 64 || rank >= world)
-	{
-		snprintf(buf, sizeof(buf), "%s: world in [1, 64], rank < world", who);
-		return fail(ctx, VXB_ERR_ARGUMENT, buf);
-	}
-	planes.resize(world + 1);
-	for (uint32_t r = 0; r <= world; ++r) planes[r] = planeBegin ? planeBegin[r] : (uint32_t)((uint64_t)n * r / world);
-	bool ok = planes[0] == 0 && planes[world] == n;
-	for (uint32_t r = 0; r < world && ok; ++r) ok = planes[r + 1] > planes[r] && planes[r + 1] % 32 == 0;
-	if (!ok)
-	{
-		snprintf(buf, sizeof(buf), "%s: slab boundaries must ascend from 0 to n in multiples of 32 planes (a uniform split needs n / world >= 32, world a power of two)", who);
-		return fail(ctx, VXB_ERR_ARGUMENT, buf);
-	}
-	split = 0;
-	for (;;)
-	{
-		if (split >= levels) break;
-		const uint32_t m = 16u << split;
-		bool nests = true;
-		for (uint32_t r = 1; r < world; ++r) if (planes[r] % m) nests = false;
-		if (!nests) break;
-		++split;
-	}
-	return VXB_OK;
+	const int r = buildTensorMap(ctx);
+	if (r == VXB_OK) ctx->haveGrid = true;
+	return r;
 }
 
 size_t blocksAtLevel(uint32_t n, int level) { const size_t nb = (n / 16) >> level; return nb * nb * nb; }
 
-// dirty box of an incremental run, per level (GenerateBlockListForLevel :429-465)
-// (a sharded run uses the same mechanism for "the blocks of my z-slab": ranged, not incremental)
+// dirty box of an incremental run, per level (GenerateBlockListForLevel :429-465): the run keeps the caches of the last
+// full run and continues its block ids
 struct Region
 {
 	int rangeMin[VXB_MAX_LEVELS][3], rangeMax[VXB_MAX_LEVELS][3]; // grid (x, y, z) block coordinates, [min, max)
 	unsigned idStart[VXB_MAX_LEVELS];
 	size_t count[VXB_MAX_LEVELS];
-	bool incremental = true;      // keep the caches of the last full run, continue its block ids
-	int phase = 0;                // 0 = whole pipeline; 1 = scan + classification of levels [0, splitLevel); 2 = the rest
-	int splitLevel = 0;           // first level whose blocks do not nest in a slab
-	int scanLayer0 = 0, scanLayer1 = 0; // level-0 block layers to scan [l0, l1)
-	uint64_t voxels = 0;          // voxels this run covers (capacity defaults)
 };
 
 struct KernelTimer
@@ -338,12 +337,30 @@ void releaseCube(vxb_context* ctx)
 	const VmmApi& api = vmmApi();
 	for (const auto& m : c.mapped) api.unmap(m.first, m.second);
 	for (CUmemGenericAllocationHandle h : c.imported) api.release(h);
-	for (int k = 0; k < 3; ++k)
+	for (int k = 0; k < 4; ++k)
 	{
-		if (c.local[k]) api.release(c.local[k]);
-		if (c.va[k]) api.addressFree(c.va[k], c.cubeBytes);
+		for (CUmemGenericAllocationHandle h : c.local[k]) api.release(h);
+		if (c.va[k]) api.addressFree(c.va[k], c.vaBytes[k]);
 	}
 	c = vxb_context::Cube();
+}
+
+void releaseShard(vxb_context* ctx)
+{
+	vxb_context::Shard& sh = ctx->shard;
+	const VmmApi& api = vmmApi();
+	for (const auto& m : sh.peerMapped) { api.unmap(m.first, m.second); api.addressFree(m.first, m.second); }
+	for (CUmemGenericAllocationHandle h : sh.peerHandles) api.release(h);
+	if (sh.pagesVmm)
+	{
+		if (sh.pagesVa) { api.unmap(sh.pagesVa, sh.bufBytes); api.addressFree(sh.pagesVa, sh.bufBytes); }
+		if (sh.pagesHandle) api.release(sh.pagesHandle);
+	}
+	else if (sh.pagesBuf) cudaFree(sh.pagesBuf);
+	sh.sbMine.release(); sh.sbWeight.release(); sh.barrierBuf.release();
+	void* comm = sh.comm;
+	sh = vxb_context::Shard();
+	sh.comm = comm; // the communicator outlives a re-configuration (vxb_destroy ends it)
 }
 
 CUmemAllocationProp slabProp(int device)
@@ -357,14 +374,11 @@ CUmemAllocationProp slabProp(int device)
 	return prop;
 }
 
-int mapSlab(vxb_context* ctx, int channel, uint32_t slab, CUmemGenericAllocationHandle handle)
+int mapRange(vxb_context* ctx, CUdeviceptr at, size_t bytes, CUmemGenericAllocationHandle handle, std::vector<std::pair<CUdeviceptr, size_t> >& mapped)
 {
 	const VmmApi& api = vmmApi();
-	vxb_context::Cube& c = ctx->cube;
-	const CUdeviceptr at = c.va[channel] + (CUdeviceptr)c.slabOffset(slab);
-	const size_t bytes = c.slabBytes(slab);
 	VXB_CU(ctx, api.map(at, bytes, 0, handle, 0));
-	c.mapped.push_back(std::make_pair(at, bytes));
+	mapped.push_back(std::make_pair(at, bytes));
 	CUmemAccessDesc access;
 	memset(&access, 0, sizeof(access));
 	access.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
@@ -373,46 +387,90 @@ int mapSlab(vxb_context* ctx, int channel, uint32_t slab, CUmemGenericAllocation
 	VXB_CU(ctx, api.setAccess(at, bytes, &access, 1));
 	return VXB_OK;
 }
+
+// ---- NCCL through dlopen (the library torch.distributed already loaded, or the system one): the data path of a
+// sharded run calls ncclAllGather itself so that a whole step is ONE stream-ordered sequence (and one CUDA graph) ----
+struct NcclApi
+{
+	int (*getUniqueId)(void*) = nullptr;
+	int (*commInitRank)(void**, int, vxb_nccl_id, int) = nullptr;
+	int (*allGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+	int (*commDestroy)(void*) = nullptr;
+	const char* (*getErrorString)(int) = nullptr;
+	bool ok = false;
+};
+
+const NcclApi& ncclApi()
+{
+	static NcclApi api;
+	static bool tried = false;
+	if (tried) return api;
+	tried = true;
+	void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+	if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+	if (!lib) return api;
+	api.getUniqueId = (int (*)(void*))dlsym(lib, "ncclGetUniqueId");
+	api.commInitRank = (int (*)(void**, int, vxb_nccl_id, int))dlsym(lib, "ncclCommInitRank");
+	api.allGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(lib, "ncclAllGather");
+	api.commDestroy = (int (*)(void*))dlsym(lib, "ncclCommDestroy");
+	api.getErrorString = (const char* (*)(int))dlsym(lib, "ncclGetErrorString");
+	api.ok = api.getUniqueId && api.commInitRank && api.allGather && api.commDestroy;
+	return api;
+}
+
+int failNccl(vxb_context* ctx, const char* what, int r)
+{
+	char buf[200];
+	const NcclApi& api = ncclApi();
+	snprintf(buf, sizeof(buf), "%s failed: ncclResult %d (%s)", what, r, api.getErrorString ? api.getErrorString(r) : "?");
+	return fail(ctx, VXB_ERR_CUDA, buf);
+}
 }
 
 extern "C"
 {
 
-int vxb_cube_create(vxb_context* ctx, uint32_t n, uint32_t rank, uint32_t world, const uint32_t* planeBegin)
+// The cube of a sharded run: pieces of `group_planes` planes, piece p owned by rank p % world.
+int vxb_cube_create(vxb_context* ctx, uint32_t n, uint32_t rank, uint32_t world, uint32_t groupPlanes)
 {
 	if (!ctx) return VXB_ERR_ARGUMENT;
 	if (!validSize(n)) return fail(ctx, VXB_ERR_ARGUMENT, "vxb_cube_create: n must be a power of two in [16, 4096]");
-	std::vector<uint32_t> planes;
-	int split = 0;
-	const int lr = shardLayout(ctx, n, levelsFor(n), rank, world, planeBegin, "vxb_cube_create", planes, split);
-	if (lr != VXB_OK) return lr;
+	if (world == 0 || world > 8 || rank >= world) return fail(ctx, VXB_ERR_ARGUMENT, "vxb_cube_create: world in [1, 8], rank < world");
+	if (groupPlanes == 0) groupPlanes = n / world;
+	if (groupPlanes % 32 != 0 || n % groupPlanes != 0 || (n / groupPlanes) % world != 0)
+		return fail(ctx, VXB_ERR_ARGUMENT, "vxb_cube_create: group_planes must be a multiple of 32 planes that divides n into a multiple of `world` pieces");
 	const VmmApi& api = vmmApi();
 	if (!api.ok) return fail(ctx, VXB_ERR_CUDA, "vxb_cube_create: the driver does not export the virtual memory management entry points");
 	cudaSetDevice(ctx->device);
 	cudaFree(nullptr); // make sure the primary context exists and is current for the driver calls
 	releaseCube(ctx);
 	vxb_context::Cube& c = ctx->cube;
-	c.rank = rank; c.world = world;
-	c.cubeBytes = (size_t)n * n * n;
-	c.planeBytes = (size_t)n * n;
-	c.planes = planes;
+	c.rank = rank; c.world = world; c.n = n;
+	c.groupPlanes = groupPlanes; c.pieces = n / groupPlanes;
 	const CUmemAllocationProp prop = slabProp(ctx->device);
 	size_t gran = 0;
 	VXB_CU(ctx, api.granularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_MINIMUM));
-	for (uint32_t r = 0; r < world; ++r)
-		if (!gran || c.slabOffset(r) % gran != 0 || c.slabBytes(r) % gran != 0)
-		{
-			char buf[200]; snprintf(buf, sizeof(buf), "vxb_cube_create: slab %u (%zu bytes at offset %zu) is not a multiple of the allocation granularity (%zu bytes)", r, c.slabBytes(r), c.slabOffset(r), gran);
-			c = vxb_context::Cube();
-			return fail(ctx, VXB_ERR_ARGUMENT, buf);
-		}
-	c.active = true;
-	for (int k = 0; k < 3; ++k)
+	if (!gran || c.pieceBytes(0) % gran != 0)
 	{
-		VXB_CU(ctx, api.addressReserve(&c.va[k], c.cubeBytes, 0, 0, 0));
-		VXB_CU(ctx, api.create(&c.local[k], c.slabBytes(rank), &prop, 0));
-		const int r = mapSlab(ctx, k, rank, c.local[k]);
-		if (r != VXB_OK) return r;
+		char buf[200]; snprintf(buf, sizeof(buf), "vxb_cube_create: a piece (%zu bytes) is not a multiple of the allocation granularity (%zu bytes)", c.pieceBytes(0), gran);
+		c = vxb_context::Cube();
+		return fail(ctx, VXB_ERR_ARGUMENT, buf);
+	}
+	c.lattice = n >= 64 && c.pieceBytes(3) % gran == 0; // else level-1 tiles are gathered from the distance volume
+	c.active = true;
+	const int channels = c.lattice ? 4 : 3;
+	for (int k = 0; k < channels; ++k)
+	{
+		c.vaBytes[k] = c.pieceBytes(k) * c.pieces;
+		VXB_CU(ctx, api.addressReserve(&c.va[k], c.vaBytes[k], 0, 0, 0));
+		for (uint32_t p = rank; p < c.pieces; p += world)
+		{
+			CUmemGenericAllocationHandle h = 0;
+			VXB_CU(ctx, api.create(&h, c.pieceBytes(k), &prop, 0));
+			c.local[k].push_back(h);
+			const int r = mapRange(ctx, c.va[k] + (CUdeviceptr)(c.pieceBytes(k) * p), c.pieceBytes(k), h, c.mapped);
+			if (r != VXB_OK) return r;
+		}
 	}
 	ctx->dDist = reinterpret_cast<const int8_t*>(c.va[0]);
 	ctx->dMat = reinterpret_cast<const uint8_t*>(c.va[1]);
@@ -422,39 +480,53 @@ int vxb_cube_create(vxb_context* ctx, uint32_t n, uint32_t rank, uint32_t world,
 	return buildTensorMap(ctx);
 }
 
-int vxb_cube_export(vxb_context* ctx, uint32_t channel, int* fd)
+int vxb_cube_info(vxb_context* ctx, uint32_t* pieces, uint32_t* channels, uint64_t* pieceBytes)
+{
+	if (!ctx) return VXB_ERR_ARGUMENT;
+	const vxb_context::Cube& c = ctx->cube;
+	if (!c.active) return fail(ctx, VXB_ERR_STATE, "vxb_cube_info: no cube");
+	if (pieces) *pieces = c.pieces;
+	if (channels) *channels = c.lattice ? 4u : 3u;
+	if (pieceBytes) for (int k = 0; k < 4; ++k) pieceBytes[k] = (k < 3 || c.lattice) ? c.pieceBytes(k) : 0;
+	return VXB_OK;
+}
+
+int vxb_cube_export(vxb_context* ctx, uint32_t channel, uint32_t piece, int* fd)
 {
 	if (!ctx || !fd) return VXB_ERR_ARGUMENT;
-	if (!ctx->cube.active || channel > 2) return fail(ctx, VXB_ERR_STATE, "vxb_cube_export: no cube, or channel > 2");
+	const vxb_context::Cube& c = ctx->cube;
+	if (!c.active || channel >= (c.lattice ? 4u : 3u) || piece >= c.pieces || piece % c.world != c.rank)
+		return fail(ctx, VXB_ERR_ARGUMENT, "vxb_cube_export: no cube, bad channel, or a piece this rank does not own");
 	cudaSetDevice(ctx->device);
 	int out = -1;
-	VXB_CU(ctx, vmmApi().exportHandle(&out, ctx->cube.local[channel], CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0));
+	VXB_CU(ctx, vmmApi().exportHandle(&out, c.local[channel][piece / c.world], CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0));
 	*fd = out;
 	return VXB_OK;
 }
 
-int vxb_cube_import(vxb_context* ctx, uint32_t peer, uint32_t channel, int fd)
+int vxb_cube_import(vxb_context* ctx, uint32_t channel, uint32_t piece, int fd)
 {
 	if (!ctx) return VXB_ERR_ARGUMENT;
 	vxb_context::Cube& c = ctx->cube;
-	if (!c.active || channel > 2 || peer >= c.world || peer == c.rank || fd < 0) return fail(ctx, VXB_ERR_ARGUMENT, "vxb_cube_import: no cube, or bad peer / channel / descriptor");
+	if (!c.active || channel >= (c.lattice ? 4u : 3u) || piece >= c.pieces || piece % c.world == c.rank || fd < 0)
+		return fail(ctx, VXB_ERR_ARGUMENT, "vxb_cube_import: no cube, or bad channel / piece / descriptor");
 	cudaSetDevice(ctx->device);
 	CUmemGenericAllocationHandle h = 0;
 	VXB_CU(ctx, vmmApi().importHandle(&h, (void*)(uintptr_t)fd, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR));
 	c.imported.push_back(h);
-	return mapSlab(ctx, (int)channel, peer, h);
+	return mapRange(ctx, c.va[channel] + (CUdeviceptr)(c.pieceBytes(channel) * piece), c.pieceBytes(channel), h, c.mapped);
 }
 
-int vxb_cube_slab(vxb_context* ctx, int8_t** dist, uint8_t** mat, uint8_t** blend, uint64_t* bytes)
+int vxb_cube_piece(vxb_context* ctx, uint32_t piece, int8_t** dist, uint8_t** mat, uint8_t** blend, uint64_t* bytes)
 {
 	if (!ctx) return VXB_ERR_ARGUMENT;
 	const vxb_context::Cube& c = ctx->cube;
-	if (!c.active) return fail(ctx, VXB_ERR_STATE, "vxb_cube_slab: no cube");
-	const size_t off = c.slabOffset(c.rank);
+	if (!c.active || piece >= c.pieces) return fail(ctx, VXB_ERR_STATE, "vxb_cube_piece: no cube, or bad piece");
+	const size_t off = c.pieceBytes(0) * piece;
 	if (dist) *dist = reinterpret_cast<int8_t*>(c.va[0] + off);
 	if (mat) *mat = reinterpret_cast<uint8_t*>(c.va[1] + off);
 	if (blend) *blend = reinterpret_cast<uint8_t*>(c.va[2] + off);
-	if (bytes) *bytes = c.slabBytes(c.rank);
+	if (bytes) *bytes = c.pieceBytes(0);
 	return VXB_OK;
 }
 
@@ -488,35 +560,36 @@ int vxb_create(int device, vxb_context** out)
 		(e = cudaEventCreateWithFlags(&ctx->evDecide0, cudaEventDisableTiming)) != cudaSuccess ||
 		(e = cudaEventCreateWithFlags(&ctx->evJoin, cudaEventDisableTiming)) != cudaSuccess ||
 		(e = cudaEventCreateWithFlags(&ctx->evDir, cudaEventDisableTiming)) != cudaSuccess ||
+		(e = cudaEventCreateWithFlags(&ctx->evVerts, cudaEventDisableTiming)) != cudaSuccess ||
 		(e = cudaEventCreateWithFlags(&ctx->evChunk[0], cudaEventDisableTiming)) != cudaSuccess || (e = cudaEventCreateWithFlags(&ctx->evChunk[1], cudaEventDisableTiming)) != cudaSuccess ||
 		(e = cudaEventCreateWithFlags(&ctx->evChunk[2], cudaEventDisableTiming)) != cudaSuccess || (e = cudaEventCreateWithFlags(&ctx->evChunk[3], cudaEventDisableTiming)) != cudaSuccess)
-	{ fail(nullptr, VXB_ERR_CUDA, "stream/event creation", e); delete ctx; return VXB_ERR_CUDA; }
+	{ fail(nullptr, VXB_ERR_CUDA, "stream/event creation", e); vxb_destroy(ctx); return VXB_ERR_CUDA; }
 
 	void* fn = nullptr;
 	cudaDriverEntryPointQueryResult qres;
 	e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
-	if (e != cudaSuccess || !fn) { fail(nullptr, VXB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available", e); delete ctx; return VXB_ERR_CUDA; }
+	if (e != cudaSuccess || !fn) { fail(nullptr, VXB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available", e); vxb_destroy(ctx); return VXB_ERR_CUDA; }
 	ctx->encodeTiled = reinterpret_cast<EncodeTiledFn>(fn);
 
 	ctx->graphDisabled = getenv("VXB200_NO_GRAPH") != nullptr; // plain launches (debugging, A/B timing)
 	struct KernelSetup { const void* fn; size_t smem; int* grid; const char* name; int threads; };
 	const KernelSetup setups[5] = {
-		{ (const void*)vxb_classify_kernel, sizeof(VxbClassifySmem), &ctx->gridClassify, "vxb_classify_kernel", VXB_THREADS },
-		{ (const void*)vxb_decide_kernel<1024, 0>, sizeof(VxbDecideSmemSmall), &ctx->gridDecideSmall, "vxb_decide_kernel<1024>", VXB_THREADS },
+		{ (const void*)vxb_block_kernel<0>, sizeof(VxbBlockSmem<0>), &ctx->gridBlock[0], "vxb_block_kernel<0>", VXB_THREADS },
+		{ (const void*)vxb_block_kernel<1>, sizeof(VxbBlockSmem<1>), &ctx->gridBlock[1], "vxb_block_kernel<1>", VXB_THREADS },
+		{ (const void*)vxb_block_kernel<2>, sizeof(VxbBlockSmem<2>), &ctx->gridBlock[2], "vxb_block_kernel<2>", VXB_THREADS },
 		{ (const void*)vxb_decide_kernel<4096, 1>, sizeof(VxbDecideSmemBig), &ctx->gridDecideBig, "vxb_decide_kernel<4096>", VXB_THREADS },
 		{ (const void*)vxb_transition_kernel, sizeof(VxbTransSmem), &ctx->gridTransition, "vxb_transition_kernel", VXB_THREADS },
-		{ (const void*)vxb_vertex_block_kernel, sizeof(VxbVertexBlockSmem), &ctx->gridVertexBlock, "vxb_vertex_block_kernel", VXB_VB_THREADS },
 	};
 	for (const KernelSetup& k : setups)
 	{
 		int occ = 0;
 		e = cudaFuncSetAttribute(k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k.smem);
 		if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k.fn, k.threads, k.smem);
-		if (e != cudaSuccess || occ < 1) { fail(nullptr, VXB_ERR_CUDA, k.name, e); delete ctx; return VXB_ERR_CUDA; }
+		if (e != cudaSuccess || occ < 1) { fail(nullptr, VXB_ERR_CUDA, k.name, e); vxb_destroy(ctx); return VXB_ERR_CUDA; }
 		*k.grid = occ * ctx->smCount;
 	}
 
-	if (ctx->counters.ensure(1) != cudaSuccess || ctx->lut.ensure(1) != cudaSuccess) { fail(nullptr, VXB_ERR_CUDA, "cudaMalloc"); delete ctx; return VXB_ERR_CUDA; }
+	if (ctx->counters.ensure(1) != cudaSuccess || ctx->lut.ensure(1) != cudaSuccess) { fail(nullptr, VXB_ERR_CUDA, "cudaMalloc"); vxb_destroy(ctx); return VXB_ERR_CUDA; }
 	*out = ctx;
 	const int r = vxb_set_materials(ctx, nullptr, nullptr);
 	if (r != VXB_OK) { g_createError = ctx->error; vxb_destroy(ctx); *out = nullptr; return r; }
@@ -531,7 +604,10 @@ void vxb_destroy(vxb_context* ctx)
 	if (ctx->stream2) cudaStreamSynchronize(ctx->stream2);
 	if (ctx->graphExec) cudaGraphExecDestroy(ctx->graphExec);
 	ctx->hostOffsets.release(); ctx->hostRecords.release();
+	releaseShard(ctx);
+	if (ctx->shard.comm && ncclApi().ok) { ncclApi().commDestroy(ctx->shard.comm); ctx->shard.comm = nullptr; }
 	releaseCube(ctx);
+	ctx->mixInfo.release(); ctx->coarseDone.release();
 	ctx->volDist.release(); ctx->volMat.release(); ctx->volBlend.release(); ctx->staging.release(); ctx->packOffsets.release(); ctx->updCoords.release(); ctx->lattice1.release();
 	ctx->scanFlags.release(); ctx->blockInfo.release(); ctx->consPages.release(); ctx->validFlags.release();
 	ctx->cachePages.release(); ctx->worklist.release(); ctx->emitList.release(); ctx->bigList.release(); ctx->transList.release(); ctx->ntScratch.release(); ctx->cellBlock.release(); ctx->vlist.release(); ctx->cellRecs.release(); ctx->blockRecs.release(); ctx->tvlist.release(); ctx->verts.release(); ctx->tverts.release();
@@ -543,6 +619,7 @@ void vxb_destroy(vxb_context* ctx)
 	if (ctx->evDecide0) cudaEventDestroy(ctx->evDecide0);
 	if (ctx->evJoin) cudaEventDestroy(ctx->evJoin);
 	if (ctx->evDir) cudaEventDestroy(ctx->evDir);
+	if (ctx->evVerts) cudaEventDestroy(ctx->evVerts);
 	for (cudaEvent_t e : ctx->evChunk) if (e) cudaEventDestroy(e);
 	if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
 	if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -569,7 +646,7 @@ int vxb_grid_upload_dense(vxb_context* ctx, uint32_t n, const int8_t* dist, cons
 	if (blend) VXB_CUDA(ctx, cudaMemcpyAsync(ctx->volBlend.p, blend, vol, cudaMemcpyHostToDevice, ctx->stream));
 	else VXB_CUDA(ctx, cudaMemsetAsync(ctx->volBlend.p, 0, vol, ctx->stream));
 	VXB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-	return buildTensorMap(ctx);
+	return finishUpload(ctx);
 }
 
 int vxb_grid_upload_blocks(vxb_context* ctx, uint32_t n, const int8_t* distBlocks, const uint8_t* matBlocks, const uint8_t* blendBlocks)
@@ -592,7 +669,7 @@ int vxb_grid_upload_blocks(vxb_context* ctx, uint32_t n, const int8_t* distBlock
 		VXB_CUDA(ctx, cudaGetLastError());
 	}
 	VXB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-	return buildTensorMap(ctx);
+	return finishUpload(ctx);
 }
 
 int vxb_grid_upload_packed(vxb_context* ctx, const void* blob, size_t size)
@@ -624,7 +701,7 @@ int vxb_grid_upload_packed(vxb_context* ctx, const void* blob, size_t size)
 	if (!ctx->hostOffsets.ensure(blocks * sizeof(unsigned long long))) return fail(ctx, VXB_ERR_CUDA, "vxb_grid_upload_packed: pinned scratch allocation failed");
 	unsigned long long* const hostOffsets = static_cast<unsigned long long*>(ctx->hostOffsets.p);
 	VXB_CUDA(ctx, cudaMemcpyAsync(ctx->staging.p, blob, head, cudaMemcpyHostToDevice, ctx->stream));
-	bool corrupt = false;
+	bool corrupt = false, truncated = false;
 	unsigned long long off = head;
 	{
 		const unsigned char* table = bytes + 16;
@@ -634,15 +711,25 @@ int vxb_grid_upload_packed(vxb_context* ctx, const void* blob, size_t size)
 			memcpy(sz, table + b * 12, 12);
 			if (sz[0] > 4096 || sz[1] > 4096 || sz[2] > 4096) { corrupt = true; break; }
 			hostOffsets[b] = off;
+			if (off + 4 > size) { truncated = true; break; }
+			// the block's flags word: a raw channel holds exactly 4096 bytes, a run-length coded one whole (length, value) pairs
+			uint32_t bflags;
+			memcpy(&bflags, bytes + off, 4);
+			for (int ch = 0; ch < 3; ++ch)
+			{
+				const bool raw = (bflags >> (1 + ch)) & 1u;
+				if (raw ? (sz[ch] != 4096) : (sz[ch] == 0 || (sz[ch] & 1u))) corrupt = true;
+			}
+			if (corrupt) break;
 			off += 4ull + sz[0] + sz[1] + sz[2];
 		}
 	}
 	const double msTable = msSince(t0);
-	if (corrupt || off > size)
+	if (corrupt || truncated || off > size)
 	{
 		cudaStreamSynchronize(ctx->stream);
 		ctx->haveGrid = false;
-		return fail(ctx, VXB_ERR_ARGUMENT, corrupt ? "vxb_grid_upload_packed: corrupt size table" : "vxb_grid_upload_packed: truncated block data");
+		return fail(ctx, VXB_ERR_ARGUMENT, corrupt ? "vxb_grid_upload_packed: corrupt size table or block flags" : "vxb_grid_upload_packed: truncated block data");
 	}
 	VXB_CUDA(ctx, cudaMemcpyAsync(ctx->packOffsets.p, hostOffsets, blocks * sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream));
 	const int chunks = nb >= 16 ? 4 : 1;
@@ -662,7 +749,7 @@ int vxb_grid_upload_packed(vxb_context* ctx, const void* blob, size_t size)
 	VXB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->evJoin, 0));
 	VXB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	const double msKernel = msSince(t0);
-	r = buildTensorMap(ctx);
+	r = finishUpload(ctx);
 	if (trace) fprintf(stderr, "[vxb200] upload_packed: offsets ready at %.3f ms, copy + decode done at %.3f ms, maps at %.3f ms\n", msTable, msKernel, msSince(t0));
 	return r;
 }
@@ -807,10 +894,12 @@ int vxb_set_capacity(vxb_context* ctx, uint64_t v, uint64_t i, uint64_t tv, uint
 	return VXB_OK;
 }
 
-static int runPolygonize(vxb_context* ctx, uint32_t maxLevels, uint32_t flags, const Region* region)
+// shardPhase: -1 = not a sharded run; 0 = scan + block info (no sync); 1 = plan + the levels below the coarse ones + page
+// publication (no sync); 2 = coarse levels, emission, directory (syncs, result); 3 = everything, the two exchanges by
+// ncclAllGather on the context's stream (needs vxb_shard_nccl_init)
+static int runPolygonize(vxb_context* ctx, uint32_t maxLevels, uint32_t flags, const Region* region, int shardPhase = -1)
 {
-	const bool incremental = region && region->incremental;
-	const int phase = region ? region->phase : 0;
+	const bool incremental = region != nullptr;
 	if (!ctx) return VXB_ERR_ARGUMENT;
 	if (!ctx->haveGrid) return fail(ctx, VXB_ERR_STATE, "vxb_polygonize: no grid uploaded");
 	cudaSetDevice(ctx->device);
@@ -819,16 +908,22 @@ static int runPolygonize(vxb_context* ctx, uint32_t maxLevels, uint32_t flags, c
 	const int levels = ctx->levels;
 	const int computed = (maxLevels == 0 || (int)maxLevels > levels) ? levels : (int)maxLevels;
 	const size_t nb0 = n / 16, blocks0 = nb0 * nb0 * nb0;
-	const bool kernelTimes = (flags & VXB_FLAG_KERNEL_TIMES) != 0 && phase == 0;
+	const bool sharded = shardPhase >= 0;
+	vxb_context::Shard& sh = ctx->shard;
+	const bool kernelTimes = (flags & VXB_FLAG_KERNEL_TIMES) != 0 && !sharded;
 
 	// ---- device state ----
 	VXB_CUDA(ctx, ctx->scanFlags.ensure(blocks0));
 	VXB_CUDA(ctx, ctx->blockInfo.ensure(blocks0));
 	VXB_CUDA(ctx, ctx->consPages.ensure(blocks0 * 128));
-	size_t totalBlocks = 0, validBytes = 0, cacheEntries = 0;
-	size_t validOff[VXB_MAX_LEVELS], cacheOff[VXB_MAX_LEVELS];
+	size_t totalBlocks = 0, validBytes = 0, cacheEntries = 0, mixBytes = 0;
+	size_t validOff[VXB_MAX_LEVELS], cacheOff[VXB_MAX_LEVELS], mixOff[VXB_MAX_LEVELS];
 	VxbDev dev;
 	memset(&dev, 0, sizeof(dev));
+	// coarse levels: from the first level with <= 4096 blocks (but not below 2) everything runs in one launch
+	int coarseLo = 2;
+	while (coarseLo < levels && blocksAtLevel(n, coarseLo) > 4096) ++coarseLo;
+	size_t coarseBlocks = 0;
 	for (int l = 0; l < levels; ++l)
 	{
 		const size_t b = blocksAtLevel(n, l);
@@ -837,9 +932,13 @@ static int runPolygonize(vxb_context* ctx, uint32_t maxLevels, uint32_t flags, c
 		totalBlocks += b;
 		validOff[l] = validBytes; validBytes += (b + 15) & ~(size_t)15;
 		cacheOff[l] = cacheEntries; if (l >= 1) cacheEntries += b * 4096;
+		mixOff[l] = mixBytes; if (l >= 1) mixBytes += (b + 15) & ~(size_t)15;
+		dev.coarseBase[l] = (unsigned)coarseBlocks; if (l >= coarseLo) coarseBlocks += b;
 	}
 	VXB_CUDA(ctx, ctx->validFlags.ensure(validBytes));
 	VXB_CUDA(ctx, ctx->cachePages.ensure(cacheEntries ? cacheEntries : 1));
+	VXB_CUDA(ctx, ctx->mixInfo.ensure(mixBytes ? mixBytes : 16));
+	VXB_CUDA(ctx, ctx->coarseDone.ensure(coarseBlocks ? coarseBlocks : 16));
 	VXB_CUDA(ctx, ctx->worklist.ensure(totalBlocks));
 	VXB_CUDA(ctx, ctx->records.ensure(totalBlocks));
 	VXB_CUDA(ctx, ctx->emitList.ensure(totalBlocks));
@@ -848,7 +947,7 @@ static int runPolygonize(vxb_context* ctx, uint32_t maxLevels, uint32_t flags, c
 	VXB_CUDA(ctx, ctx->blockRecs.ensure(totalBlocks));
 	VXB_CUDA(ctx, ctx->ntScratch.ensure(totalBlocks * 256));
 
-	const uint64_t vol = (region && region->voxels) ? region->voxels : (uint64_t)n * n * n;
+	const uint64_t vol = sharded ? (uint64_t)n * n * n / sh.world * 2 : (uint64_t)n * n * n;
 	if (!ctx->capV) ctx->capV = std::max<uint64_t>(1u << 20, vol / 24);
 	if (!ctx->capI) ctx->capI = ctx->capV * 6;
 	if (!ctx->capTV) ctx->capTV = std::max<uint64_t>(1u << 18, ctx->capV / 8);
@@ -856,18 +955,23 @@ static int runPolygonize(vxb_context* ctx, uint32_t maxLevels, uint32_t flags, c
 	if (!ctx->capC) ctx->capC = ctx->capV + ctx->capV / 4;
 
 	dev.grid.dist = ctx->dDist; dev.grid.mat = ctx->dMat; dev.grid.blend = ctx->dBlend; dev.grid.n = (int)n;
-	dev.n = (int)n; dev.levels = levels; dev.lastLevel = levels - 1;
+	dev.n = (int)n; dev.levels = levels; dev.lastLevel = levels - 1; dev.computed = computed;
 	dev.scanFlags = ctx->scanFlags.p; dev.blockInfo = ctx->blockInfo.p;
 	dev.consPages = ctx->consPages.p;
 	dev.consValid = ctx->validFlags.p + validOff[0];
-	for (int l = 1; l < levels; ++l) { dev.cachePages[l] = ctx->cachePages.p + cacheOff[l]; dev.cacheValid[l] = ctx->validFlags.p + validOff[l]; }
+	for (int l = 1; l < levels; ++l)
+	{
+		dev.cachePages[l] = ctx->cachePages.p + cacheOff[l]; dev.cacheValid[l] = ctx->validFlags.p + validOff[l];
+		dev.mixInfo[l] = ctx->mixInfo.p + mixOff[l];
+	}
+	dev.coarseLo = coarseLo; dev.coarseDone = ctx->coarseDone.p;
 	dev.worklist = ctx->worklist.p;
 	dev.records = ctx->records.p; dev.rcap = (unsigned)totalBlocks;
 	dev.counters = ctx->counters.p; dev.lut = ctx->lut.p;
 	dev.transitions = (flags & VXB_FLAG_NO_TRANSITIONS) ? 0 : 1;
 	dev.emitList = ctx->emitList.p; dev.bigList = ctx->bigList.p; dev.transList = ctx->transList.p; dev.ntScratch = ctx->ntScratch.p;
 	dev.blockRecs = ctx->blockRecs.p;
-	dev.lattice1 = ctx->haveLattice1 ? ctx->lattice1.p : nullptr;
+	dev.lattice1 = ctx->haveLattice1 ? ctx->latticePtr : nullptr;
 	dev.incremental = incremental ? 1 : 0;
 	dev.ranged = region ? 1 : 0;
 	if (region)
@@ -876,6 +980,26 @@ static int runPolygonize(vxb_context* ctx, uint32_t maxLevels, uint32_t flags, c
 			for (int a = 0; a < 3; ++a) { dev.rangeMin[l][a] = region->rangeMin[l][a]; dev.rangeMax[l][a] = region->rangeMax[l][a]; }
 			dev.idStart[l] = region->idStart[l];
 		}
+	VxbPeers peers;
+	memset(&peers, 0, sizeof(peers));
+	if (sharded)
+	{
+		if (!sh.on) return fail(ctx, VXB_ERR_STATE, "vxb_polygonize_sharded: call vxb_shard_configure first");
+		if (sh.sbLevel != coarseLo - 1 || coarseLo >= levels) return fail(ctx, VXB_ERR_STATE, "vxb_polygonize_sharded: the grid changed since vxb_shard_configure");
+		dev.shardWorld = (int)sh.world; dev.shardRank = (int)sh.rank; dev.shardLayers = (int)sh.groupLayers;
+		dev.sbLevel = sh.sbLevel; dev.sbMine = sh.sbMine.p; dev.sbWeight = sh.sbWeight.p;
+		// the pages of the super-block level live in the buffer the peers write into
+		dev.cachePages[sh.sbLevel] = reinterpret_cast<unsigned short*>(sh.pagesBuf);
+		dev.cacheValid[sh.sbLevel] = sh.pagesBuf + sh.pagesBytes;
+		for (uint32_t p = 0; p < sh.world; ++p)
+		{
+			if (p == sh.rank) continue;
+			if (!sh.peerSet[p]) return fail(ctx, VXB_ERR_STATE, "vxb_polygonize_sharded: a peer's page buffer is not set (vxb_shard_set_peer / vxb_shard_import)");
+			peers.pages[peers.count] = sh.peerPages[p]; peers.valid[peers.count] = sh.peerValid[p]; ++peers.count;
+		}
+		if (shardPhase == 3 && (!sh.comm || !ncclApi().ok)) return fail(ctx, VXB_ERR_STATE, "vxb_polygonize_sharded: phase 3 needs vxb_shard_nccl_init");
+	}
+	const int scanWorld = sharded ? (int)sh.world : 1, scanRank = sharded ? (int)sh.rank : 0, scanGroup = sharded ? (int)sh.groupLayers : (int)nb0;
 
 	VxbCounters hc;
 	for (int attempt = 0; attempt < 6; ++attempt)
@@ -899,142 +1023,182 @@ static int runPolygonize(vxb_context* ctx, uint32_t maxLevels, uint32_t flags, c
 		KernelTimer timer{ ctx, kernelTimes };
 		uint32_t launches = 0;
 		for (int k = 0; k < 8; ++k) ctx->kindLaunches[k] = 0;
-		if (phase != 2) VXB_CUDA(ctx, cudaEventRecord(ctx->evBegin, ctx->stream));
-		// everything between the two timing events: memsets, kernels, the fork/join of the two streams
-		auto enqueue = [&]() -> int
+		const unsigned flatGrid = (unsigned)ctx->smCount * 8;
+		cudaStream_t st = ctx->stream;
+
+		// ---- the pieces of a run; a full run is all of them in order, a sharded run has an exchange after the first two ----
+		auto scanPart = [&]() -> int
 		{
-			if (phase != 2)
-			{
-				VXB_CUDA(ctx, cudaMemsetAsync(ctx->counters.p, 0, sizeof(VxbCounters), ctx->stream));
-				if (!incremental) VXB_CUDA(ctx, cudaMemsetAsync(ctx->validFlags.p, 0, validBytes, ctx->stream)); // incremental runs keep the caches (:362-364)
-				const size_t layer0 = (region && !incremental) ? (size_t)region->scanLayer0 : 0, layer1 = (region && !incremental) ? (size_t)region->scanLayer1 : nb0;
-				const int perCta = nb0 >= 32 ? 32 : 8;
-			const dim3 grid((unsigned)((nb0 + perCta - 1) / perCta), (unsigned)nb0, (unsigned)(layer1 - layer0));
+			VXB_CUDA(ctx, cudaMemsetAsync(ctx->counters.p, 0, sizeof(VxbCounters), st));
+			if (!incremental) VXB_CUDA(ctx, cudaMemsetAsync(ctx->validFlags.p, 0, validBytes, st)); // incremental runs keep the caches (:362-364)
+			if (sharded) VXB_CUDA(ctx, cudaMemsetAsync(sh.pagesBuf + sh.pagesBytes, 0, sh.validBytes, st));
+			if (coarseBlocks) VXB_CUDA(ctx, cudaMemsetAsync(ctx->coarseDone.p, 0, coarseBlocks, st));
+			const size_t myLayers = nb0 / scanWorld;
+			const int perCta = nb0 >= 32 ? 32 : 8;
+			const dim3 grid((unsigned)((nb0 + perCta - 1) / perCta), (unsigned)nb0, (unsigned)myLayers);
 			timer.begin(0);
-			if (perCta == 32) vxb_scan_kernel<32><<<grid, VXB_THREADS, 0, ctx->stream>>>(ctx->dDist, (int)n, ctx->scanFlags.p, ctx->haveLattice1 ? ctx->lattice1.p : nullptr, (int)layer0);
-			else vxb_scan_kernel<8><<<grid, VXB_THREADS, 0, ctx->stream>>>(ctx->dDist, (int)n, ctx->scanFlags.p, ctx->haveLattice1 ? ctx->lattice1.p : nullptr, (int)layer0);
+			if (perCta == 32) vxb_scan_kernel<32><<<grid, VXB_THREADS, 0, st>>>(ctx->dDist, (int)n, ctx->scanFlags.p, ctx->haveLattice1 ? ctx->latticePtr : nullptr, scanGroup, scanWorld, scanRank);
+			else vxb_scan_kernel<8><<<grid, VXB_THREADS, 0, st>>>(ctx->dDist, (int)n, ctx->scanFlags.p, ctx->haveLattice1 ? ctx->latticePtr : nullptr, scanGroup, scanWorld, scanRank);
 			timer.end(); ++launches; ++ctx->kindLaunches[0];
-				const size_t first = layer0 * nb0 * nb0, last = layer1 * nb0 * nb0;
-				const unsigned g2 = (unsigned)std::min<size_t>((last - first + 255) / 256, (size_t)ctx->smCount * 8);
+			const size_t mine = myLayers * nb0 * nb0;
+			const unsigned g2 = (unsigned)std::min<size_t>((mine + 255) / 256, (size_t)ctx->smCount * 8);
+			timer.begin(1);
+			vxb_block_info_kernel<<<g2, 256, 0, st>>>(ctx->dDist, (int)n, ctx->scanFlags.p, ctx->blockInfo.p, mine, scanGroup, scanWorld, scanRank);
+			timer.end(); ++launches; ++ctx->kindLaunches[1];
+			return VXB_OK;
+		};
+		auto selectLevel = [&](int l) {
+			const size_t b = region ? region->count[l] : blocksAtLevel(n, l);
+			const unsigned gs = (unsigned)std::min<size_t>((b + 255) / 256, (size_t)ctx->smCount * 8);
+			timer.begin(1);
+			vxb_select_kernel<<<gs, 256, 0, st>>>(dev, l);
+			timer.end(); ++launches; ++ctx->kindLaunches[1];
+			return b;
+		};
+		auto levelPart = [&]() -> int
+		{
+			if (levels > 1)
+			{
+				// sign-mix pyramid: the block walk of levels >= 2 and (sharded runs) the weights of the super-blocks
+				size_t threadsA = 0, ctasB = 0;
+				for (int l = 1; l < levels; ++l) { if (l <= 2) threadsA += blocksAtLevel(n, l); else ctasB += blocksAtLevel(n, l); }
+				const unsigned ctasA = (unsigned)((threadsA + 255) / 256);
 				timer.begin(1);
-				vxb_block_info_kernel<<<g2, 256, 0, ctx->stream>>>(ctx->dDist, (int)n, ctx->scanFlags.p, ctx->blockInfo.p, first, last);
+				vxb_pyramid_kernel<<<ctasA + (unsigned)ctasB, 256, 0, st>>>(dev, ctasA);
 				timer.end(); ++launches; ++ctx->kindLaunches[1];
 			}
-			const unsigned flatGrid = (unsigned)ctx->smCount * 8;
-			auto classifyLevel = [&](int l, cudaStream_t st) {
-				const size_t b = region ? region->count[l] : blocksAtLevel(n, l);
-				if (!b) return;
-				const unsigned gs = (unsigned)std::min<size_t>((b + 255) / 256, (size_t)ctx->smCount * 8);
-				timer.begin(1);
-				vxb_select_kernel<<<gs, 256, 0, st>>>(dev, l);
-				timer.end(); ++launches; ++ctx->kindLaunches[1];
-				timer.begin(2);
-				vxb_classify_kernel<<<(unsigned)std::min<size_t>(b, ctx->gridClassify), VXB_THREADS, sizeof(VxbClassifySmem), st>>>(ctx->tmap, ctx->tmap1, dev, l);
-				timer.end(); ++launches; ++ctx->kindLaunches[2];
-			};
-			auto decideGroup = [&](int group, cudaStream_t st) {
+			if (sharded) { vxb_plan_kernel<<<1, 1024, 0, st>>>(dev); ++launches; }
+			if (selectLevel(0))
+			{
 				timer.begin(3);
-				vxb_decide_kernel<1024, 0><<<ctx->gridDecideSmall, VXB_THREADS, sizeof(VxbDecideSmemSmall), st>>>(ctx->tmap, ctx->tmap1, dev, group);
-				vxb_decide_kernel<4096, 1><<<ctx->gridDecideBig, VXB_THREADS, sizeof(VxbDecideSmemBig), st>>>(ctx->tmap, ctx->tmap1, dev, group);
-				timer.end(); launches += 2; ctx->kindLaunches[3] += 2;
-			};
-			auto flatGroup = [&](int part, cudaStream_t st) {
-				timer.begin(4);
-				if (part == 0) vxb_vertex_block_kernel<<<ctx->gridVertexBlock, VXB_VB_THREADS, sizeof(VxbVertexBlockSmem), st>>>(ctx->tmapDist19, dev);
-				else vxb_vertex_kernel<<<flatGrid, VXB_THREADS, 0, st>>>(dev, part);
-				timer.end(); ++launches; ++ctx->kindLaunches[4];
-				timer.begin(5);
-				vxb_triangle_kernel<<<flatGrid, VXB_THREADS, 0, st>>>(dev, part);
-				timer.end(); ++launches; ++ctx->kindLaunches[5];
-			};
-			auto transitions = [&](cudaStream_t st) {
-				timer.begin(6);
-				if (dev.transitions)
-				{
-					vxb_transition_kernel<<<ctx->gridTransition, VXB_THREADS, sizeof(VxbTransSmem), st>>>(dev);
-					vxb_transition_vertex_kernel<<<flatGrid, VXB_THREADS, 0, st>>>(dev);
-					launches += 2; ctx->kindLaunches[6] += 2;
-				}
-				timer.end();
-			};
-			// Levels depend on each other only through vxb_classify_kernel, so with more than one level the work forks:
-			//   stream : level 0 -> decide -> vertices -> triangles
-			//   stream2: classify levels 1.. (a latency-bound chain of small launches) -> decide -> vertices -> triangles -> transitions
-			// and joins before vxb_finish_kernel.  Per-kernel timing (VXB_FLAG_KERNEL_TIMES) runs everything on one stream.
-			const bool fork = (computed > 1 && !kernelTimes) || phase == 2;
-			if (phase != 2) classifyLevel(0, ctx->stream);
-			if (phase == 1)
-			{
-				// sharded run, first half: the levels whose blocks nest in this rank's slab.  Nothing is read back: the caller
-				// exchanges the material pages of level splitLevel-1 on this stream (vxb_shard_exchange_info) and calls phase 2.
-				for (int l = 1; l < region->splitLevel && l < computed; ++l) classifyLevel(l, ctx->stream);
-				VXB_CUDA(ctx, cudaGetLastError());
-				// the exchange runs on the second stream (vxb_exchange_stream), ordered after this classification; in phase 2
-				// only the coarse levels wait for it, the vertices and triangles of the nested levels overlap it
-				VXB_CUDA(ctx, cudaEventRecord(ctx->evFork, ctx->stream));
-				VXB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->evFork, 0));
-				ctx->shardLaunches = launches;
-				return 100; // first half enqueued
+				vxb_block_kernel<0><<<ctx->gridBlock[0], VXB_THREADS, sizeof(VxbBlockSmem<0>), st>>>(ctx->tmapDist19, ctx->tmapDist19, dev, 0);
+				timer.end(); ++launches; ++ctx->kindLaunches[3];
 			}
-			const int firstRest = (phase == 2) ? region->splitLevel : 1;
-			if (phase == 2) launches += ctx->shardLaunches;
-			if (!fork)
+			vxb_mark_split_kernel<<<1, 1, 0, st>>>(dev); ++launches; // level 0 is complete: the flat kernels work on [split, end)
+			for (int l = 1; l < coarseLo && l < computed; ++l)
 			{
-				for (int l = firstRest; l < computed; ++l) classifyLevel(l, ctx->stream);
-				decideGroup(0, ctx->stream); // level 0 first: its blocks own the first directory slots / arena ranges
-				vxb_mark_split_kernel<<<1, 1, 0, ctx->stream>>>(dev); ++launches;
-				flatGroup(0, ctx->stream);
-				if (computed > 1)
+				if (!selectLevel(l)) continue;
+				timer.begin(2);
+				vxb_block_kernel<1><<<ctx->gridBlock[1], VXB_THREADS, sizeof(VxbBlockSmem<1>), st>>>(ctx->tmap, ctx->tmap1, dev, l);
+				timer.end(); ++launches; ++ctx->kindLaunches[2];
+			}
+			if (sharded && peers.count) { vxb_publish_kernel<<<(unsigned)ctx->smCount * 4, VXB_THREADS, 0, st>>>(dev, peers); ++launches; }
+			VXB_CUDA(ctx, cudaGetLastError());
+			return VXB_OK;
+		};
+		auto tailPart = [&]() -> int
+		{
+			if (computed > coarseLo)
+			{
+				timer.begin(2);
+				vxb_block_kernel<2><<<ctx->gridBlock[2], VXB_THREADS, sizeof(VxbBlockSmem<2>), st>>>(ctx->tmap, ctx->tmap1, dev, coarseLo);
+				timer.end(); ++launches; ++ctx->kindLaunches[2];
+			}
+			// blocks too large for the shared-memory path of vxb_block_kernel (> 1024 non-trivial cells / > 2048 level-0 vertices)
+			timer.begin(2);
+			vxb_decide_kernel<4096, 1><<<ctx->gridDecideBig, VXB_THREADS, sizeof(VxbDecideSmemBig), st>>>(ctx->tmap, ctx->tmap1, dev, 2);
+			timer.end(); ++launches; ++ctx->kindLaunches[2];
+			// vertices + triangles of everything but the level-0 blocks done inside vxb_block_kernel<0>, next to the transition
+			// cells (which need the block records and the material pages only)
+			const bool fork = dev.transitions && computed > 1 && !kernelTimes;
+			if (fork)
+			{
+				VXB_CUDA(ctx, cudaEventRecord(ctx->evFork, st));
+				VXB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->evFork, 0));
+			}
+			timer.begin(4);
+			vxb_vertex_kernel<<<flatGrid, VXB_THREADS, 0, st>>>(dev, 1);
+			timer.end(); ++launches; ++ctx->kindLaunches[4];
+			timer.begin(5);
+			vxb_triangle_kernel<<<flatGrid, VXB_THREADS, 0, st>>>(dev, 1);
+			timer.end(); ++launches; ++ctx->kindLaunches[5];
+			if (dev.transitions && computed > 1)
+			{
+				cudaStream_t ts = fork ? ctx->stream2 : st;
+				timer.begin(6);
+				vxb_transition_kernel<<<ctx->gridTransition, VXB_THREADS, sizeof(VxbTransSmem), ts>>>(dev);
+				vxb_transition_vertex_kernel<<<flatGrid, VXB_THREADS, 0, ts>>>(dev);
+				timer.end(); launches += 2; ctx->kindLaunches[6] += 2;
+				if (fork)
 				{
-					decideGroup(1, ctx->stream);
-					flatGroup(1, ctx->stream);
-					transitions(ctx->stream);
+					VXB_CUDA(ctx, cudaEventRecord(ctx->evJoin, ctx->stream2));
+					VXB_CUDA(ctx, cudaStreamWaitEvent(st, ctx->evJoin, 0));
 				}
+			}
+			timer.begin(7);
+			vxb_finish_kernel<<<(unsigned)ctx->smCount * 2, VXB_THREADS, 0, st>>>(dev);
+			timer.end(); ++launches; ++ctx->kindLaunches[7];
+			VXB_CUDA(ctx, cudaGetLastError());
+			return VXB_OK;
+		};
+		auto exchange = [&](int which) -> int
+		{
+			const NcclApi& nccl = ncclApi();
+			if (which == 0)
+			{
+				// all-gather of the block info: every rank's layers are one contiguous chunk (rank-major layout)
+				const size_t chunk = blocks0 / sh.world;
+				const int r = nccl.allGather(ctx->blockInfo.p + chunk * sh.rank, ctx->blockInfo.p, chunk, /*ncclUint8*/ 1, sh.comm, st);
+				if (r != 0) return failNccl(ctx, "ncclAllGather (block info)", r);
 			}
 			else
 			{
-				VXB_CUDA(ctx, cudaEventRecord(ctx->evFork, ctx->stream));
-				VXB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->evFork, 0));
-				for (int l = firstRest; l < computed; ++l) classifyLevel(l, ctx->stream2);
-				decideGroup(0, ctx->stream);
-				vxb_mark_split_kernel<<<1, 1, 0, ctx->stream>>>(dev); ++launches;
-				VXB_CUDA(ctx, cudaEventRecord(ctx->evDecide0, ctx->stream));
-				flatGroup(0, ctx->stream);
-				VXB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->evDecide0, 0)); // arena cursors are shared: group 1 allocates after group 0
-				decideGroup(1, ctx->stream2);
-				flatGroup(1, ctx->stream2);
-				transitions(ctx->stream2);
-				VXB_CUDA(ctx, cudaEventRecord(ctx->evJoin, ctx->stream2));
-				VXB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->evJoin, 0));
+				// the pages were written straight into the peers' buffers by vxb_publish_kernel; this all-gather (one word per
+				// rank) only orders every rank's coarse levels after every rank's publication
+				const int r = nccl.allGather(sh.barrierBuf.p + sh.rank, sh.barrierBuf.p, 8, /*ncclUint8*/ 1, sh.comm, st);
+				if (r != 0) return failNccl(ctx, "ncclAllGather (page exchange barrier)", r);
 			}
-			timer.begin(7);
-			vxb_finish_kernel<<<(unsigned)ctx->smCount * 2, VXB_THREADS, 0, ctx->stream>>>(dev);
-			timer.end(); ++launches; ++ctx->kindLaunches[7];
 			return VXB_OK;
 		};
-		// A full run has no host decision inside the sequence, so it is captured once into a CUDA graph and replayed; the
-		// key is every kernel argument (a re-upload into other buffers, grown arenas, other flags => new capture).
-		bool replayed = false;
-		if (phase == 0 && !region && !kernelTimes && !ctx->graphDisabled)
+		auto enqueueAll = [&]() -> int
 		{
-			std::vector<unsigned char> key(sizeof(VxbDev) + 3 * sizeof(CUtensorMap) + 64, 0);
+			int r = scanPart();
+			if (r == VXB_OK && shardPhase == 3) r = exchange(0);
+			if (r == VXB_OK) r = levelPart();
+			if (r == VXB_OK && shardPhase == 3) r = exchange(1);
+			if (r == VXB_OK) r = tailPart();
+			return r;
+		};
+
+		if (shardPhase == 0)
+		{
+			VXB_CUDA(ctx, cudaEventRecord(ctx->evBegin, st));
+			const int r = scanPart();
+			VXB_CUDA(ctx, cudaGetLastError());
+			sh.phaseLaunches = launches;
+			return r;
+		}
+		if (shardPhase == 1)
+		{
+			const int r = levelPart();
+			sh.phaseLaunches += launches;
+			return r;
+		}
+		if (shardPhase != 2) VXB_CUDA(ctx, cudaEventRecord(ctx->evBegin, st));
+		// A run has no host decision inside the sequence, so it is captured once into a CUDA graph and replayed; the key is
+		// every kernel argument (a re-upload into other buffers, grown arenas, other flags => new capture).
+		bool replayed = false;
+		if ((shardPhase == -1 || shardPhase == 3) && !incremental && !kernelTimes && !ctx->graphDisabled)
+		{
+			std::vector<unsigned char> key(sizeof(VxbDev) + sizeof(VxbPeers) + 3 * sizeof(CUtensorMap) + 64, 0);
 			unsigned char* k = key.data();
 			memcpy(k, &dev, sizeof(VxbDev)); k += sizeof(VxbDev);
+			memcpy(k, &peers, sizeof(VxbPeers)); k += sizeof(VxbPeers);
 			const CUtensorMap* maps[3] = { &ctx->tmap, &ctx->tmap1, &ctx->tmapDist19 };
 			for (const CUtensorMap* mp : maps) { memcpy(k, mp, sizeof(CUtensorMap)); k += sizeof(CUtensorMap); }
-			const void* ptrs[4] = { ctx->dDist, ctx->scanFlags.p, ctx->blockInfo.p, ctx->haveLattice1 ? ctx->lattice1.p : nullptr };
+			const void* ptrs[4] = { ctx->dDist, ctx->scanFlags.p, ctx->blockInfo.p, ctx->haveLattice1 ? ctx->latticePtr : nullptr };
 			memcpy(k, ptrs, sizeof(ptrs)); k += sizeof(ptrs);
-			const int scalars[4] = { computed, (int)validBytes, (int)nb0, (int)n };
+			const int scalars[6] = { computed, (int)validBytes, (int)nb0, (int)n, shardPhase, (int)flags };
 			memcpy(k, scalars, sizeof(scalars));
 			if (!ctx->graphExec || key != ctx->graphKey)
 			{
 				if (ctx->graphExec) { cudaGraphExecDestroy(ctx->graphExec); ctx->graphExec = nullptr; }
 				cudaGraph_t graph = nullptr;
-				cudaError_t ce = cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal);
+				cudaError_t ce = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
 				if (ce == cudaSuccess)
 				{
-					const int rc = enqueue();
-					ce = cudaStreamEndCapture(ctx->stream, &graph);
+					const int rc = enqueueAll();
+					ce = cudaStreamEndCapture(st, &graph);
 					if (rc != VXB_OK && ce == cudaSuccess) ce = cudaErrorUnknown;
 				}
 				if (ce == cudaSuccess) ce = cudaGraphInstantiate(&ctx->graphExec, graph, 0);
@@ -1045,21 +1209,21 @@ static int runPolygonize(vxb_context* ctx, uint32_t maxLevels, uint32_t flags, c
 			}
 			if (ctx->graphExec)
 			{
-				VXB_CUDA(ctx, cudaGraphLaunch(ctx->graphExec, ctx->stream));
+				VXB_CUDA(ctx, cudaGraphLaunch(ctx->graphExec, st));
 				launches = ctx->graphLaunches;
 				replayed = true;
 			}
 		}
 		if (!replayed)
 		{
-			const int rc = enqueue();
-			if (rc == 100) return VXB_OK;
+			const int rc = (shardPhase == 2) ? tailPart() : enqueueAll();
 			if (rc != VXB_OK) return rc;
+			if (shardPhase == 2) launches += sh.phaseLaunches;
 		}
 		VXB_CUDA(ctx, cudaGetLastError());
-		VXB_CUDA(ctx, cudaEventRecord(ctx->evEnd, ctx->stream));
-		VXB_CUDA(ctx, cudaMemcpyAsync(&hc, ctx->counters.p, sizeof(hc), cudaMemcpyDeviceToHost, ctx->stream));
-		VXB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		VXB_CUDA(ctx, cudaEventRecord(ctx->evEnd, st));
+		VXB_CUDA(ctx, cudaMemcpyAsync(&hc, ctx->counters.p, sizeof(hc), cudaMemcpyDeviceToHost, st));
+		VXB_CUDA(ctx, cudaStreamSynchronize(st));
 		float ms = 0.f;
 		VXB_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->evBegin, ctx->evEnd));
 		timer.collect();
@@ -1074,8 +1238,8 @@ static int runPolygonize(vxb_context* ctx, uint32_t maxLevels, uint32_t flags, c
 		if (hc.transVertices > ctx->capTV) ctx->capTV = (uint64_t)hc.transVertices + hc.transVertices / 8 + 1024;
 		if (hc.transIndices > ctx->capTI) ctx->capTI = (uint64_t)hc.transIndices + hc.transIndices / 8 + 1024;
 		if (hc.cells > ctx->capC) ctx->capC = (uint64_t)hc.cells + hc.cells / 8 + 1024;
-		// a sharded run cannot redo its first half here
-		if (phase == 2) return fail(ctx, VXB_ERR_CAPACITY, "vxb_polygonize_sharded: output arenas overflowed; capacities were grown, repeat both phases on every rank");
+		// a sharded run is collective: the caller repeats it on every rank
+		if (sharded) return fail(ctx, VXB_ERR_CAPACITY, "vxb_polygonize_sharded: output arenas overflowed; capacities were grown, repeat the run on every rank");
 	}
 
 	// the directory stays on the device (it is part of the result resident in HBM); vxb_result_download fetches and
@@ -1092,11 +1256,13 @@ static int runPolygonize(vxb_context* ctx, uint32_t maxLevels, uint32_t flags, c
 	info.vertex_total = hc.vertices; info.index_total = (uint64_t)hc.indices - 3ull * hc.degenerate;
 	info.trans_vertex_total = hc.transVertices; info.trans_index_total = hc.transIndices;
 	// statistics (TransVoxelImpl.cpp:528-531): BlocksCalculated counts every block of every computed level;
-	// TrivialCells only those of processed (not skipped) blocks
+	// TrivialCells only those of processed (not skipped) blocks.  The statistics of a sharded run are the SUM over the
+	// ranks (modulo 2^32): rank 0 carries the terms that do not depend on the work split.
 	uint64_t blocksCalculated = 0, processedCells = (uint64_t)hc.nonSkippedLevel0 * 4096ull;
 	for (int l = 0; l < computed; ++l)
 	{
 		const size_t b = region ? region->count[l] : blocksAtLevel(n, l);
+		if (sharded && sh.rank != 0) continue;
 		blocksCalculated += b;
 		if (l) processedCells += b * 4096ull;
 	}
@@ -1107,8 +1273,8 @@ static int runPolygonize(vxb_context* ctx, uint32_t maxLevels, uint32_t flags, c
 	for (int i = 0; i < 16; ++i) info.stats[4 + i] = hc.perCase[i];
 	for (int i = 0; i < 8; ++i) info.used_materials[i] = hc.usedMaterials[i];
 	ctx->haveResult = true;
-	if (!region) { ctx->haveFullRun = (computed == levels); ctx->nextId = (uint32_t)totalBlocks; }
-	else if (!incremental) ctx->haveFullRun = false;
+	if (!region && !sharded) { ctx->haveFullRun = (computed == levels); ctx->nextId = (uint32_t)totalBlocks; }
+	else if (sharded) ctx->haveFullRun = false;
 	return VXB_OK;
 }
 
@@ -1158,68 +1324,152 @@ int vxb_polygonize_region(vxb_context* ctx, const float minCorner[3], const floa
 	return r;
 }
 
-// ---- sharded runs: rank r of `world` owns the z-slab [plane_begin[r], plane_begin[r+1]) ----
+// ---- sharded runs: one grid, `world` ranks, one GPU each ----
 
-int vxb_polygonize_sharded(vxb_context* ctx, uint32_t rank, uint32_t world, const uint32_t* planeBegin, uint32_t phase, uint32_t flags)
+int vxb_shard_configure(vxb_context* ctx, uint32_t rank, uint32_t world, uint32_t groupPlanes)
 {
 	if (!ctx) return VXB_ERR_ARGUMENT;
-	if (!ctx->haveGrid) return fail(ctx, VXB_ERR_STATE, "vxb_polygonize_sharded: no grid");
-	if (phase > 1) return fail(ctx, VXB_ERR_ARGUMENT, "vxb_polygonize_sharded: phase is 0 (classify the nested levels) or 1 (finish)");
-	std::vector<uint32_t> planes;
-	Region region;
-	int r = shardLayout(ctx, ctx->n, ctx->levels, rank, world, planeBegin, "vxb_polygonize_sharded", planes, region.splitLevel);
-	if (r != VXB_OK) return r;
-	region.incremental = false;
-	region.phase = (int)phase + 1;
-	const uint32_t z0 = planes[rank], z1 = planes[rank + 1];
-	region.voxels = (uint64_t)ctx->n * ctx->n * (z1 - z0);
-	const uint32_t nb0 = ctx->n / 16;
-	region.scanLayer0 = (int)(z0 ? z0 / 16 - 1 : 0);
-	region.scanLayer1 = (int)std::min(nb0, z1 / 16 + 1);
-	for (int l = 0; l < ctx->levels; ++l)
+	if (!ctx->haveGrid) return fail(ctx, VXB_ERR_STATE, "vxb_shard_configure: no grid (vxb_cube_create or vxb_grid_set_device first)");
+	const uint32_t n = ctx->n;
+	if (world == 0 || world > 8 || rank >= world) return fail(ctx, VXB_ERR_ARGUMENT, "vxb_shard_configure: world in [1, 8], rank < world");
+	if (groupPlanes == 0) groupPlanes = n / world;
+	if (groupPlanes % 32 != 0 || n % groupPlanes != 0 || (n / groupPlanes) % world != 0)
+		return fail(ctx, VXB_ERR_ARGUMENT, "vxb_shard_configure: group_planes must be a multiple of 32 planes that divides n into a multiple of `world` pieces");
+	if (ctx->cube.active && (ctx->cube.groupPlanes != groupPlanes || ctx->cube.world != world || ctx->cube.rank != rank))
+		return fail(ctx, VXB_ERR_ARGUMENT, "vxb_shard_configure: rank / world / group_planes differ from the cube's");
+	int coarseLo = 2;
+	while (coarseLo < ctx->levels && blocksAtLevel(n, coarseLo) > 4096) ++coarseLo;
+	if (coarseLo >= ctx->levels) return fail(ctx, VXB_ERR_ARGUMENT, "vxb_shard_configure: the grid is too small to shard (n >= 64)");
+	cudaSetDevice(ctx->device);
+	releaseShard(ctx);
+	vxb_context::Shard& sh = ctx->shard;
+	sh.rank = rank; sh.world = world; sh.groupLayers = groupPlanes / 16; sh.sbLevel = coarseLo - 1;
+	const size_t sb = blocksAtLevel(n, sh.sbLevel);
+	VXB_CUDA(ctx, sh.sbMine.ensure(sb));
+	VXB_CUDA(ctx, sh.sbWeight.ensure(sb));
+	VXB_CUDA(ctx, sh.barrierBuf.ensure(8));
+	VXB_CUDA(ctx, cudaMemset(sh.barrierBuf.p, 0, 64));
+	sh.pagesBytes = sb * 4096 * sizeof(unsigned short);
+	sh.validBytes = (sb + 255) & ~(size_t)255;
+	sh.bufBytes = sh.pagesBytes + sh.validBytes;
+	const VmmApi& api = vmmApi();
+	if (ctx->cube.active && api.ok)
 	{
-		const int nbl = (int)(nb0 >> l);
-		const bool nested = l < region.splitLevel;
-		const int b0 = nested ? (int)(z0 >> (4 + l)) : 0, b1 = nested ? (int)(z1 >> (4 + l)) : (rank == 0 ? nbl : 0);
-		const bool any = b1 > b0;
-		region.rangeMin[l][0] = 0; region.rangeMin[l][1] = 0; region.rangeMin[l][2] = b0;
-		region.rangeMax[l][0] = any ? nbl : 0; region.rangeMax[l][1] = any ? nbl : 0; region.rangeMax[l][2] = b1;
-		region.idStart[l] = 0; // ids are the full-run ids: idBase[level] + coordinate id (:395-401)
-		region.count[l] = any ? (size_t)nbl * nbl * (b1 - b0) : 0;
+		// exportable (the peers map it and store their pages into it)
+		const CUmemAllocationProp prop = slabProp(ctx->device);
+		size_t gran = 0;
+		VXB_CU(ctx, api.granularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_MINIMUM));
+		sh.bufBytes = (sh.bufBytes + gran - 1) / gran * gran;
+		VXB_CU(ctx, api.addressReserve(&sh.pagesVa, sh.bufBytes, 0, 0, 0));
+		VXB_CU(ctx, api.create(&sh.pagesHandle, sh.bufBytes, &prop, 0));
+		std::vector<std::pair<CUdeviceptr, size_t> > scratch;
+		const int r = mapRange(ctx, sh.pagesVa, sh.bufBytes, sh.pagesHandle, scratch);
+		if (r != VXB_OK) return r;
+		sh.pagesVmm = true;
+		sh.pagesBuf = reinterpret_cast<unsigned char*>(sh.pagesVa);
 	}
-	return runPolygonize(ctx, 0, flags, &region);
+	else
+	{
+		VXB_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&sh.pagesBuf), sh.bufBytes));
+	}
+	sh.on = true;
+	if (!ctx->cube.active && !ctx->latticeOff)
+	{
+		// virtual ranks over one shared upload: no shared even-lattice copy => level 1 gathers its tiles
+		ctx->latticeOff = true;
+		const int r = buildTensorMap(ctx);
+		if (r != VXB_OK) return r;
+	}
+	if (ctx->graphExec) { cudaGraphExecDestroy(ctx->graphExec); ctx->graphExec = nullptr; }
+	ctx->graphKey.clear();
+	return VXB_OK;
 }
 
-int vxb_shard_exchange_info(vxb_context* ctx, uint32_t rank, uint32_t world, const uint32_t* planeBegin, vxb_shard_exchange* out)
+int vxb_shard_buffers_get(vxb_context* ctx, vxb_shard_buffers* out)
+{
+	if (!ctx || !out) return VXB_ERR_ARGUMENT;
+	const vxb_context::Shard& sh = ctx->shard;
+	if (!sh.on) return fail(ctx, VXB_ERR_STATE, "vxb_shard_buffers_get: call vxb_shard_configure first");
+	const size_t nb0 = ctx->n / 16, blocks0 = nb0 * nb0 * nb0;
+	cudaSetDevice(ctx->device);
+	VXB_CUDA(ctx, ctx->blockInfo.ensure(blocks0));
+	memset(out, 0, sizeof(*out));
+	out->block_info = ctx->blockInfo.p;
+	out->block_info_bytes = blocks0;
+	out->chunk_bytes = blocks0 / sh.world;
+	out->pages = sh.pagesBuf;
+	out->pages_bytes = sh.pagesBytes;
+	out->valid = sh.pagesBuf + sh.pagesBytes;
+	out->valid_bytes = sh.validBytes;
+	out->super_level = (uint32_t)sh.sbLevel;
+	return VXB_OK;
+}
+
+int vxb_shard_set_peer(vxb_context* ctx, uint32_t peer, void* pages, void* valid)
 {
 	if (!ctx) return VXB_ERR_ARGUMENT;
-	if (!ctx->haveGrid) return fail(ctx, VXB_ERR_STATE, "vxb_shard_exchange_info: no grid");
-	if (!out) return fail(ctx, VXB_ERR_ARGUMENT, "vxb_shard_exchange_info: out is null");
-	std::vector<uint32_t> planes;
-	int split = 0;
-	int r = shardLayout(ctx, ctx->n, ctx->levels, rank, world, planeBegin, "vxb_shard_exchange_info", planes, split);
-	if (r != VXB_OK) return r;
-	memset(out, 0, sizeof(*out));
-	out->split_level = (uint32_t)split;
-	if (split >= ctx->levels) return VXB_OK; // one rank: every level nests, nothing to exchange
-	const int l = split - 1; // >= 1: boundaries are multiples of 32 planes
-	size_t validOff = 0, cacheOff = 0;
-	for (int k = 0; k < l; ++k)
-	{
-		const size_t b = blocksAtLevel(ctx->n, k);
-		validOff += (b + 15) & ~(size_t)15;
-		if (k >= 1) cacheOff += b * 4096;
-	}
-	const size_t nbl = (ctx->n / 16) >> l;
-	if (!ctx->cachePages.p || !ctx->validFlags.p) return fail(ctx, VXB_ERR_STATE, "vxb_shard_exchange_info: call phase 0 of vxb_polygonize_sharded first");
-	out->level = (uint32_t)l;
-	out->pages = ctx->cachePages.p + cacheOff;
-	out->pages_bytes = nbl * nbl * nbl * 4096 * sizeof(unsigned short);
-	out->valid = ctx->validFlags.p + validOff;
-	out->valid_bytes = nbl * nbl * nbl;
-	out->layer_planes = 16u << l;
-	out->layer_blocks = (uint32_t)(nbl * nbl);
+	vxb_context::Shard& sh = ctx->shard;
+	if (!sh.on || peer >= sh.world || peer == sh.rank || !pages || !valid) return fail(ctx, VXB_ERR_ARGUMENT, "vxb_shard_set_peer: not configured, or bad peer / pointer");
+	sh.peerPages[peer] = static_cast<unsigned short*>(pages);
+	sh.peerValid[peer] = static_cast<unsigned char*>(valid);
+	sh.peerSet[peer] = true;
 	return VXB_OK;
+}
+
+int vxb_shard_export(vxb_context* ctx, int* fd)
+{
+	if (!ctx || !fd) return VXB_ERR_ARGUMENT;
+	const vxb_context::Shard& sh = ctx->shard;
+	if (!sh.on || !sh.pagesVmm) return fail(ctx, VXB_ERR_STATE, "vxb_shard_export: needs vxb_shard_configure on a context with a cube");
+	cudaSetDevice(ctx->device);
+	int out = -1;
+	VXB_CU(ctx, vmmApi().exportHandle(&out, sh.pagesHandle, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0));
+	*fd = out;
+	return VXB_OK;
+}
+
+int vxb_shard_import(vxb_context* ctx, uint32_t peer, int fd)
+{
+	if (!ctx) return VXB_ERR_ARGUMENT;
+	vxb_context::Shard& sh = ctx->shard;
+	if (!sh.on || !sh.pagesVmm || peer >= sh.world || peer == sh.rank || fd < 0) return fail(ctx, VXB_ERR_ARGUMENT, "vxb_shard_import: not configured, or bad peer / descriptor");
+	cudaSetDevice(ctx->device);
+	const VmmApi& api = vmmApi();
+	CUmemGenericAllocationHandle h = 0;
+	VXB_CU(ctx, api.importHandle(&h, (void*)(uintptr_t)fd, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR));
+	sh.peerHandles.push_back(h);
+	CUdeviceptr va = 0;
+	VXB_CU(ctx, api.addressReserve(&va, sh.bufBytes, 0, 0, 0));
+	const int r = mapRange(ctx, va, sh.bufBytes, h, sh.peerMapped);
+	if (r != VXB_OK) return r;
+	return vxb_shard_set_peer(ctx, peer, reinterpret_cast<void*>(va), reinterpret_cast<unsigned char*>(va) + sh.pagesBytes);
+}
+
+int vxb_shard_nccl_unique_id(vxb_nccl_id* id)
+{
+	if (!id) return VXB_ERR_ARGUMENT;
+	const NcclApi& api = ncclApi();
+	if (!api.ok) return fail(nullptr, VXB_ERR_CUDA, "vxb_shard_nccl_unique_id: libnccl.so.2 could not be loaded");
+	const int r = api.getUniqueId(id);
+	return r == 0 ? VXB_OK : failNccl(nullptr, "ncclGetUniqueId", r);
+}
+
+int vxb_shard_nccl_init(vxb_context* ctx, const vxb_nccl_id* id, uint32_t rank, uint32_t world)
+{
+	if (!ctx || !id) return VXB_ERR_ARGUMENT;
+	const NcclApi& api = ncclApi();
+	if (!api.ok) return fail(ctx, VXB_ERR_CUDA, "vxb_shard_nccl_init: libnccl.so.2 could not be loaded");
+	cudaSetDevice(ctx->device);
+	if (ctx->shard.comm) { api.commDestroy(ctx->shard.comm); ctx->shard.comm = nullptr; }
+	const int r = api.commInitRank(&ctx->shard.comm, (int)world, *id, (int)rank);
+	return r == 0 ? VXB_OK : failNccl(ctx, "ncclCommInitRank", r);
+}
+
+int vxb_polygonize_sharded(vxb_context* ctx, uint32_t phase, uint32_t flags)
+{
+	if (!ctx) return VXB_ERR_ARGUMENT;
+	if (phase > 3) return fail(ctx, VXB_ERR_ARGUMENT, "vxb_polygonize_sharded: phase is 0, 1, 2 (the pieces around the two exchanges) or 3 (everything, NCCL inside)");
+	return runPolygonize(ctx, 0, flags, nullptr, (int)phase);
 }
 
 int vxb_region_info_get(vxb_context* ctx, vxb_region_info* out)

@@ -28,27 +28,16 @@
 #define VXB_VB_OCC 8 // and for the 128-thread level-0 vertex kernel
 #endif
 
-struct __align__(128) VxbClassifySmem
-{
-	signed char tiles[2][VXB_TILE_BYTES + 96]; // double buffered: the next block's tile lands while this one is classified
-	unsigned int rowSign[17 * 17 + 3]; // bit x = sample (x, y, z) of the tile is negative
-	unsigned int nt32[128];
-	unsigned int wpre[132];
-	unsigned short list[4096];
-	unsigned int warpSums[8];
-	unsigned int hist[16];
-	unsigned long long mbar[2];
-	unsigned int item, hasChild, pageReady, emitIdx;
-};
-
 // Non-trivial bits of all 4096 cells from the tile, 16 cells per thread-step instead of one:
 // a cell is non-trivial iff its 8 corner signs are neither all 0 nor all 1 (Cell::CalcCaseCode :741-750, :1560).
+// `tile` points at sample (0,0,0) of the block; rows are PITCH bytes apart, z-slices ROWS rows.
+template <int PITCH, int ROWS>
 __device__ __forceinline__ void vxb_classify_bits(const signed char* tile, unsigned int* rowSign, unsigned int* nt32)
 {
 	const int tid = threadIdx.x;
 	for (int r = tid; r < 17 * 17; r += VXB_THREADS)
 	{
-		const unsigned int* w = reinterpret_cast<const unsigned int*>(tile + r * VXB_TILE_PITCH);
+		const unsigned int* w = reinterpret_cast<const unsigned int*>(tile + ((r / 17) * ROWS + (r % 17)) * PITCH);
 		unsigned m = 0;
 #pragma unroll
 		for (int q = 0; q < 4; ++q) m |= ((((w[q] >> 7) & 0x01010101u) * 0x01020408u) >> 24 & 0xFu) << (4 * q);
@@ -64,13 +53,14 @@ __device__ __forceinline__ void vxb_classify_bits(const signed char* tile, unsig
 	}
 }
 
+template <int PITCH, int ROWS>
 __device__ __forceinline__ void vxb_tile_samples(const signed char* tile, int c, signed char v[8])
 {
 	const int lx = c & 15, ly = (c >> 4) & 15, lz = c >> 8;
-	const signed char* p = tile + (lz * 17 + ly) * VXB_TILE_PITCH + lx;
-	v[0] = p[0]; v[1] = p[1]; v[2] = p[VXB_TILE_PITCH]; v[3] = p[VXB_TILE_PITCH + 1];
-	p += 17 * VXB_TILE_PITCH;
-	v[4] = p[0]; v[5] = p[1]; v[6] = p[VXB_TILE_PITCH]; v[7] = p[VXB_TILE_PITCH + 1];
+	const signed char* p = tile + (lz * ROWS + ly) * PITCH + lx;
+	v[0] = p[0]; v[1] = p[1]; v[2] = p[PITCH]; v[3] = p[PITCH + 1];
+	p += ROWS * PITCH;
+	v[4] = p[0]; v[5] = p[1]; v[6] = p[PITCH]; v[7] = p[PITCH + 1];
 }
 
 __device__ __forceinline__ void vxb_init_cache_page(const VxbDev& d, int level, unsigned coordId)
@@ -79,43 +69,248 @@ __device__ __forceinline__ void vxb_init_cache_page(const VxbDev& d, int level, 
 	for (int i = threadIdx.x; i < 2048; i += VXB_THREADS) page[i] = 0x00FF00FFu; // {EMPTY_MATERIAL, 0} x 2  (:424)
 }
 
-__global__ void __launch_bounds__(VXB_THREADS, VXB_OCC) vxb_classify_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap1, const VxbDev d, const int level)
+__device__ __forceinline__ unsigned vxb_rank_of(const unsigned int* nt32, const unsigned int* wpre, int c)
 {
+	return wpre[c >> 5] + __popc(nt32[c >> 5] & ((1u << (c & 31)) - 1u));
+}
+
+// Level-0 halo tile (vxb_block_kernel<0>): the block's distance neighbourhood, coordinates [origin - 1, origin + 17] per
+// axis, as 19 x 19 rows of 48 bytes (the TMA box starts on a 16-byte boundary one 16-byte group before the block).
+#define VXB_DTILE_PITCH 48
+#define VXB_DTILE_BYTES (19 * 19 * VXB_DTILE_PITCH)
+#define VXB_CAP_C 1024   // non-trivial cells of a block handled in shared memory; larger blocks go to vxb_decide_kernel<4096, 1>
+#define VXB_VL_CAP 2048  // new vertices of a level-0 block generated inside the CTA; more => the flat kernels
+
+// ------------------------------------------------------------------------------------------------
+// vxb_block_kernel<MODE>: everything that needs the block as a unit, in ONE pass over its sample tile
+//   tile -> case codes -> non-trivial bits; consistency page (level 0) or majority votes of the non-trivial cells and of
+//   every transition-face cell into the level's material page (CalculateMaterialForCellCache :753-838, called from :1568
+//   and :1859) - the only cross-level dependency; statistics; then, for blocks with non-trivial cells: ordered compaction,
+//   materials, owned reuse slots, new-vs-reuse decisions, block scans -> vertex / triangle bases, arena reservation.
+//   MODE 0  level 0 from its work list: halo tile by one TMA load (double buffered); the new vertices and the triangles
+//           are produced right here from shared memory (no per-cell records in global memory).
+//   MODE 1  one level from its work list (17^3 tile: TMA for level 0 / the even lattice of level 1, strided gather else);
+//           writes 16-byte cell records + the vertex work list for the flat per-vertex / per-cell kernels.
+//   MODE 2  all coarse levels [coarseLo, computed) in ONE launch: items = blocks in level order; a block first waits for
+//           the done flags of its eight children (they were taken earlier from the same cursor, so they are running or
+//           done: no deadlock), applies the block-walk test itself, then works like MODE 1.
+// ------------------------------------------------------------------------------------------------
+template <int MODE>
+struct __align__(128) VxbBlockSmem
+{
+	signed char tiles[2][MODE == 0 ? (VXB_DTILE_BYTES + 80) : (VXB_TILE_BYTES + 96)]; // double buffered: the next block's tile lands while this one is worked on
+	unsigned int rowSign[17 * 17 + 3]; // bit x = sample (x, y, z) of the tile is negative
+	unsigned int nt32[128];
+	unsigned int wpre[132];
+	unsigned char tabClass[256];
+	unsigned char tabCell[256];
+	unsigned short tabVert[3072];
+	unsigned int warpSums[8];
+	unsigned int hist[16];
+	unsigned int used[8];
+	unsigned long long mbar[2];
+	unsigned int item, hasChild, pageReady, emitIdx, voff, ioff, cellBase, slot, take, removed;
+	unsigned int levelEnd[VXB_MAX_LEVELS + 1];
+	unsigned int recA[VXB_CAP_C];     // matId | matBlend<<8 | slotK<<16
+	unsigned int recB[VXB_CAP_C];     // newMask | quirkMask<<12 | reuse mask << 24
+	unsigned short list[VXB_CAP_C];   // compact index -> cell id
+	unsigned short cz[VXB_CAP_C];     // case code | zero mask << 8
+	unsigned short vbase[VXB_CAP_C];  // exclusive scan of new-vertex counts
+	unsigned short tbase[VXB_CAP_C];  // exclusive scan of triangle counts
+	unsigned short vl[MODE == 0 ? VXB_VL_CAP : 8]; // MODE 0: block-local vertex -> compact cell index << 4 | table vertex
+};
+
+// true when an arena overflowed: the host grows the arenas and repeats the run, the later kernels do nothing
+__device__ __forceinline__ bool vxb_overflowed(const VxbDev& d)
+{
+	const VxbCounters* c = d.counters;
+	return c->vertices > d.vcap || c->indices > d.icap || c->cells > d.ccap || c->records > d.rcap;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(VXB_THREADS, (MODE == 0 ? 3 : (MODE == 2 ? 3 : VXB_OCC))) vxb_block_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB, const VxbDev d, const int levelArg)
+{
+	constexpr int PITCH = (MODE == 0) ? VXB_DTILE_PITCH : VXB_TILE_PITCH;
+	constexpr int ROWS = (MODE == 0) ? 19 : 17;
+	typedef VxbBlockSmem<MODE> Smem;
 	extern __shared__ __align__(128) unsigned char smemRaw[];
-	VxbClassifySmem& s = *reinterpret_cast<VxbClassifySmem*>(smemRaw);
+	Smem& s = *reinterpret_cast<Smem*>(smemRaw);
 	const int tid = threadIdx.x;
-	const int m = 1 << level, nb = d.n / 16 / m;
-	const bool midLevel = level > 0 && level != d.lastLevel;
+	const VxbGrid g = d.grid;
 	unsigned phaseBits = 0; // mbarrier phase of each tile buffer, bit = buffer
-	VxbVoteSource voteSrc;
-	if (level > 0) voteSrc = vxb_vote_source(d, level);
 	if (tid == 0) { vxb_mbar_init(&s.mbar[0], 1); vxb_mbar_init(&s.mbar[1], 1); }
 	if (tid < 16) s.hist[tid] = 0;
+	if (tid < 8) s.used[tid] = 0;
+	for (int i = tid; i < 256; i += VXB_THREADS) { s.tabClass[i] = vxbGRegularCellClass[i]; s.tabCell[i] = vxbGRegularCellData[i]; }
+	for (int i = tid; i < 3072; i += VXB_THREADS) s.tabVert[i] = vxbGRegularVertexData[i];
 	unsigned statNonTrivial = 0;
-	const unsigned workCount = d.counters->workCount[level];
-	const unsigned* worklist = d.worklist + d.workBase[level];
-	if (tid == 0) s.item = atomicAdd(&d.counters->workCursor[level], 1u);
+
+	// ---- work source ----
+	unsigned workCount;
+	const unsigned* worklist = nullptr;
+	unsigned* cursor;
+	if (MODE == 2)
+	{
+		if (tid == 0)
+		{
+			unsigned acc = 0;
+			for (int l = d.coarseLo; l < d.computed; ++l)
+			{
+				const int nbl = (d.n >> 4) >> l;
+				const int nx = d.ranged ? d.rangeMax[l][0] - d.rangeMin[l][0] : nbl, ny = d.ranged ? d.rangeMax[l][1] - d.rangeMin[l][1] : nbl, nz = d.ranged ? d.rangeMax[l][2] - d.rangeMin[l][2] : nbl;
+				acc += (nx > 0 && ny > 0 && nz > 0) ? (unsigned)nx * ny * nz : 0u;
+				s.levelEnd[l - d.coarseLo] = acc;
+			}
+		}
+		__syncthreads();
+		workCount = (d.computed > d.coarseLo) ? s.levelEnd[d.computed - d.coarseLo - 1] : 0u;
+		cursor = &d.counters->coarseCursor;
+	}
+	else
+	{
+		workCount = d.counters->workCount[levelArg];
+		worklist = d.worklist + d.workBase[levelArg];
+		cursor = &d.counters->workCursor[levelArg];
+	}
+
+	// block coordinates of a work item (MODE 2: also its level)
+	auto decode = [&](unsigned item, int& level, int& bx, int& by, int& bz) {
+		if (MODE == 2)
+		{
+			int q = 0;
+			while (item >= s.levelEnd[q]) ++q;
+			level = d.coarseLo + q;
+			unsigned r = item - (q ? s.levelEnd[q - 1] : 0u);
+			const int nbl = (d.n >> 4) >> level;
+			const int x0 = d.ranged ? d.rangeMin[level][0] : 0, y0 = d.ranged ? d.rangeMin[level][1] : 0, z0 = d.ranged ? d.rangeMin[level][2] : 0;
+			const int nx = d.ranged ? d.rangeMax[level][0] - x0 : nbl, ny = d.ranged ? d.rangeMax[level][1] - y0 : nbl;
+			bx = x0 + (int)(r % nx); by = y0 + (int)((r / nx) % ny); bz = z0 + (int)(r / ((unsigned)nx * ny));
+		}
+		else
+		{
+			level = levelArg;
+			const int nbl = (d.n >> 4) >> level;
+			const unsigned c = worklist[item];
+			bx = c % nbl; by = (c / nbl) % nbl; bz = c / (nbl * nbl);
+		}
+	};
+	// tile of the block: issue (thread 0; asynchronous when TMA applies) ...
+	auto issue = [&](int buf, int level, int bx, int by, int bz) {
+		if (MODE == 0)
+		{
+			if (tid == 0)
+			{
+				// the tile starts one sample before the block, except on the low grid edge (all TMA coordinates stay >= 0)
+				const int sx = bx ? bx * 16 - 16 : 0, sy = by ? by * 16 - 1 : 0, sz = bz ? bz * 16 - 1 : 0; // x start 16-byte aligned
+				vxb_fence_proxy_async();
+				vxb_mbar_expect_tx(&s.mbar[buf], VXB_DTILE_BYTES);
+				vxb_tma_load_3d(s.tiles[buf], &tmapA, sx, sy, sz, &s.mbar[buf]);
+			}
+		}
+		else if (MODE == 1) vxb_tile_issue(s.tiles[buf], &s.mbar[buf], &tmapA, &tmapB, d, level, bx, by, bz);
+	};
+
+	if (tid == 0) s.item = atomicAdd(cursor, 1u);
 	__syncthreads();
 	unsigned item = s.item;
 	int buf = 0;
-	if (item < workCount) { const unsigned c0 = worklist[item]; vxb_tile_issue(s.tiles[0], &s.mbar[0], &tmap, &tmap1, d, level, c0 % nb, (c0 / nb) % nb, c0 / (nb * nb)); }
+	if (item < workCount) { int l, x, y, z; decode(item, l, x, y, z); issue(0, l, x, y, z); }
 	__syncthreads();
 
 	while (item < workCount)
 	{
-		if (tid == 0) { s.item = atomicAdd(&d.counters->workCursor[level], 1u); s.hasChild = 0; s.pageReady = 0; }
+		if (tid == 0) { s.item = atomicAdd(cursor, 1u); s.hasChild = 0; s.pageReady = 0; s.take = 1; s.removed = 0; }
 		__syncthreads();
 		const unsigned nextItem = s.item;
-		if (nextItem < workCount) { const unsigned c1 = worklist[nextItem]; vxb_tile_issue(s.tiles[buf ^ 1], &s.mbar[buf ^ 1], &tmap, &tmap1, d, level, c1 % nb, (c1 / nb) % nb, c1 / (nb * nb)); }
-		const unsigned coordId = worklist[item];
-		const int bx = coordId % nb, by = (coordId / nb) % nb, bz = coordId / (nb * nb);
-		signed char* const tile = s.tiles[buf];
-		unsigned ph = (phaseBits >> buf) & 1u;
-		vxb_tile_complete(tile, &s.mbar[buf], ph, d, level, bx, by, bz);
-		phaseBits = (phaseBits & ~(1u << buf)) | (ph << buf);
+		if (nextItem < workCount && MODE != 2) { int l, x, y, z; decode(nextItem, l, x, y, z); issue(buf ^ 1, l, x, y, z); }
+		int level, bx, by, bz;
+		decode(item, level, bx, by, bz);
+		const int m = 1 << level, nb = d.n / 16 / m;
+		const unsigned coordId = ((unsigned)bz * nb + by) * nb + bx;
+		const bool midLevel = level > 0 && level != d.lastLevel;
+		signed char* const tileRaw = s.tiles[MODE == 2 ? 0 : buf];
+
+		if (MODE == 2)
+		{
+			// wait for the children of this run (blocks of the previous coarse level inside the run's range), then the block walk test
+			if (tid == 0)
+			{
+				if (level > d.coarseLo)
+				{
+					const int cnb = nb * 2, cl = level - 1;
+					for (int q = 0; q < 8; ++q)
+					{
+						const int cx = bx * 2 + (q & 1), cy = by * 2 + ((q >> 1) & 1), cz = bz * 2 + (q >> 2);
+						if (d.ranged && (cx < d.rangeMin[cl][0] || cx >= d.rangeMax[cl][0] || cy < d.rangeMin[cl][1] || cy >= d.rangeMax[cl][1] || cz < d.rangeMin[cl][2] || cz >= d.rangeMax[cl][2])) continue;
+						const volatile unsigned char* flag = d.coarseDone + d.coarseBase[cl] + ((size_t)cz * cnb + cy) * cnb + cx;
+						unsigned spins = 0;
+						while (!*flag) { __nanosleep(64); if (++spins > (1u << 24)) __trap(); }
+					}
+					__threadfence();
+				}
+				s.take = vxb_coarse_block_needed(d, level, bx, by, bz) ? 1u : 0u;
+			}
+			__syncthreads();
+			if (!s.take)
+			{
+				if (tid == 0) { __threadfence(); *(volatile unsigned char*)(d.coarseDone + d.coarseBase[level] + coordId) = 1; }
+				__syncthreads();
+				item = nextItem;
+				continue;
+			}
+		}
+
+		// ---- tile ----
+		const signed char* tile; // sample (0, 0, 0) of the block
+		int hsx = 0, hsy = 0, hsz = 0; // MODE 0: first coordinate held by the halo tile
+		if (MODE == 0)
+		{
+			hsx = bx ? bx * 16 - 16 : 0; hsy = by ? by * 16 - 1 : 0; hsz = bz ? bz * 16 - 1 : 0;
+			vxb_mbar_wait(&s.mbar[buf], (phaseBits >> buf) & 1u);
+			phaseBits ^= 1u << buf;
+			// far grid edge: TMA zero-fills outside the volume, the reference clamps the coordinate to n-1 (:1037-1047, :1198)
+			const int lastX = d.n - 1 - hsx, lastY = d.n - 1 - hsy, lastZ = d.n - 1 - hsz; // tile index of coordinate n-1
+			if (bx == nb - 1)
+			{
+				__syncthreads();
+				for (int i = tid; i < 19 * 19; i += VXB_THREADS)
+				{
+					signed char* r = tileRaw + i * VXB_DTILE_PITCH;
+					r[lastX + 1] = r[lastX]; r[lastX + 2] = r[lastX];
+				}
+			}
+			if (by == nb - 1)
+			{
+				__syncthreads();
+				for (int i = tid; i < 19 * VXB_DTILE_PITCH; i += VXB_THREADS)
+				{
+					const int z = i / VXB_DTILE_PITCH, x = i % VXB_DTILE_PITCH;
+					signed char* p = tileRaw + z * 19 * VXB_DTILE_PITCH + x;
+					for (int q = lastY + 1; q < 19; ++q) p[q * VXB_DTILE_PITCH] = p[lastY * VXB_DTILE_PITCH];
+				}
+			}
+			if (bz == nb - 1)
+			{
+				__syncthreads();
+				for (int i = tid; i < 19 * VXB_DTILE_PITCH; i += VXB_THREADS)
+				{
+					const int y = i / VXB_DTILE_PITCH, x = i % VXB_DTILE_PITCH;
+					signed char* p = tileRaw + y * VXB_DTILE_PITCH + x;
+					for (int q = lastZ + 1; q < 19; ++q) p[q * 19 * VXB_DTILE_PITCH] = p[lastZ * 19 * VXB_DTILE_PITCH];
+				}
+			}
+			tile = tileRaw + ((bz * 16 - hsz) * 19 + (by * 16 - hsy)) * VXB_DTILE_PITCH + (bx * 16 - hsx);
+		}
+		else
+		{
+			unsigned ph = (phaseBits >> buf) & 1u;
+			vxb_tile_complete(tileRaw, &s.mbar[buf], ph, d, level, bx, by, bz);
+			phaseBits = (phaseBits & ~(1u << buf)) | (ph << buf);
+			tile = tileRaw;
+		}
 		__syncthreads();
 
-		vxb_classify_bits(tile, s.rowSign, s.nt32);
+		vxb_classify_bits<PITCH, ROWS>(tile, s.rowSign, s.nt32);
 		__syncthreads();
 		unsigned ntc;
 		{
@@ -124,6 +319,9 @@ __global__ void __launch_bounds__(VXB_THREADS, VXB_OCC) vxb_classify_kernel(cons
 			if (tid < 128) s.wpre[tid] = ex;
 		}
 		__syncthreads();
+		const bool inCap = ntc <= (unsigned)VXB_CAP_C;
+		// sharded runs: every rank classifies the coarse levels (the votes feed the next level), one of them emits the block
+		const bool emitMine = MODE != 2 || vxb_coarse_emit_is_mine(d, level, coordId);
 
 		if (ntc > 0)
 		{
@@ -136,6 +334,7 @@ __global__ void __launch_bounds__(VXB_THREADS, VXB_OCC) vxb_classify_kernel(cons
 				}
 			}
 			else if (!d.cacheValid[level][coordId]) vxb_init_cache_page(d, level, coordId);
+			if (inCap)
 			{
 				// ordered compact list: thread = cell row (z, y), 16 bits each
 				unsigned bits = reinterpret_cast<const unsigned short*>(s.nt32)[tid];
@@ -147,37 +346,46 @@ __global__ void __launch_bounds__(VXB_THREADS, VXB_OCC) vxb_classify_kernel(cons
 			{
 				if (level == 0) d.consValid[coordId] = 1; else d.cacheValid[level][coordId] = 1;
 				s.pageReady = 1;
-				const unsigned idx = d.workBase[level] + atomicAdd(&d.counters->emitCount[level], 1u);
-				d.emitList[idx] = ((unsigned)level << 28) | coordId;
-				s.emitIdx = idx;
-				statNonTrivial += ntc;
-			}
-			for (unsigned i = tid; i < ntc; i += VXB_THREADS)
-			{
-				const int c = s.list[i];
-				signed char v[8];
-				vxb_tile_samples(tile, c, v);
-				atomicAdd(&s.hist[vxbGRegularCellClass[vxb_case_code(v)]], 1u); // PerCaseCellsCount (:1574)
-				if (level > 0)
+				if (emitMine)
 				{
-					// material of every non-trivial cell (:1568): majority vote of its 8 children, stored in the level's page
-					const int base[3] = { (bx * 16 + (c & 15)) * m, (by * 16 + ((c >> 4) & 15)) * m, (bz * 16 + (c >> 8)) * m };
-					const int vote = vxb_vote_cell(voteSrc, base[0], base[1], base[2]);
-					if (vote >= 0) d.cachePages[level][(size_t)coordId * 4096 + c] = (unsigned short)vote;
+					const unsigned idx = d.workBase[level] + atomicAdd(&d.counters->emitCount[level], 1u);
+					d.emitList[idx] = ((unsigned)level << 28) | coordId;
+					s.emitIdx = idx;
+					statNonTrivial += ntc;
 				}
 			}
+			// statistics (PerCaseCellsCount :1574) and, above level 0, the material of every non-trivial cell (:1568):
+			// majority vote of its 8 children, stored in the level's page
+			auto cellWork = [&](int c) {
+				signed char v[8];
+				vxb_tile_samples<PITCH, ROWS>(tile, c, v);
+				if (emitMine) atomicAdd(&s.hist[s.tabClass[vxb_case_code(v)]], 1u);
+				if (level > 0)
+				{
+					const VxbVoteSource voteSrc = vxb_vote_source(d, level);
+					const int vote = vxb_vote_cell(voteSrc, (bx * 16 + (c & 15)) * m, (by * 16 + ((c >> 4) & 15)) * m, (bz * 16 + (c >> 8)) * m);
+					if (vote >= 0) d.cachePages[level][(size_t)coordId * 4096 + c] = (unsigned short)vote;
+				}
+			};
+			if (inCap) { for (unsigned i = tid; i < ntc; i += VXB_THREADS) cellWork(s.list[i]); }
+			else
+			{
+				unsigned bits = reinterpret_cast<const unsigned short*>(s.nt32)[tid];
+				while (bits) { const int x = __ffs(bits) - 1; bits &= bits - 1; cellWork(tid * 16 + x); }
+			}
 			__syncthreads();
-			if (tid < 128) { d.ntScratch[(size_t)s.emitIdx * 256 + tid] = s.nt32[tid]; d.ntScratch[(size_t)s.emitIdx * 256 + 128 + tid] = s.wpre[tid]; }
+			if (!inCap && emitMine && tid < 128) { d.ntScratch[(size_t)s.emitIdx * 256 + tid] = s.nt32[tid]; d.ntScratch[(size_t)s.emitIdx * 256 + 128 + tid] = s.wpre[tid]; }
 		}
 
 		// every cell of every transition face votes too, trivial ones included (:1859) - observable at the next level
-		if (midLevel)
+		if (MODE != 0 && midLevel)
 		{
+			const VxbVoteSource voteSrc = vxb_vote_source(d, level);
 			if (tid < 8)
 			{
 				const int cnb = nb * 2;
 				const size_t cb = ((size_t)(bz * 2 + (tid >> 2)) * cnb + (by * 2 + ((tid >> 1) & 1))) * cnb + (bx * 2 + (tid & 1));
-				const bool valid = (level == 1) ? d.consValid[cb] : d.cacheValid[level - 1][cb];
+				const bool valid = (level == 1) ? __ldcg(d.consValid + cb) : __ldcg(d.cacheValid[level - 1] + cb);
 				if (valid) atomicOr(&s.hasChild, 1u);
 			}
 			__syncthreads();
@@ -214,19 +422,263 @@ __global__ void __launch_bounds__(VXB_THREADS, VXB_OCC) vxb_classify_kernel(cons
 					// local[axis] = edge, local[ua] = col, local[va] = row, written with selects (an indexed array would be local memory)
 					const int edge = (face >= 3) ? 15 : 0;
 					const int local[3] = { axis == 0 ? edge : col, axis == 1 ? edge : (axis == 2 ? row : col), axis == 2 ? edge : row };
-					const int base[3] = { (bx * 16 + local[0]) * m, (by * 16 + local[1]) * m, (bz * 16 + local[2]) * m };
-					const int vote = vxb_vote_cell(voteSrc, base[0], base[1], base[2]);
+					const int vote = vxb_vote_cell(voteSrc, (bx * 16 + local[0]) * m, (by * 16 + local[1]) * m, (bz * 16 + local[2]) * m);
 					if (vote >= 0) d.cachePages[level][(size_t)coordId * 4096 + local[2] * 256 + local[1] * 16 + local[0]] = (unsigned short)vote;
 				}
 			}
 		}
+		__syncthreads(); // the votes of this block are visible to the CTA (pass A reads the page back)
+
+		if (ntc > 0 && !inCap)
+		{
+			if (tid == 0 && emitMine) d.bigList[atomicAdd(&d.counters->bigCount[0], 1u)] = s.emitIdx;
+		}
+		else if (ntc > 0 && emitMine)
+		{
+			// ---- pass A: material, case code, zero mask, owned slots ----
+			for (unsigned i = tid; i < ntc; i += VXB_THREADS)
+			{
+				const int c = s.list[i];
+				signed char v[8];
+				vxb_tile_samples<PITCH, ROWS>(tile, c, v);
+				const unsigned code = vxb_case_code(v);
+				const unsigned zm = vxb_zero_mask(v);
+				unsigned matId, matBlend;
+				if (level == 0)
+				{
+					const size_t gi = ((size_t)((bz * 16 + (c >> 8))) * d.n + (by * 16 + ((c >> 4) & 15))) * d.n + (bx * 16 + (c & 15));
+					matId = g.mat[gi]; matBlend = g.blend[gi];
+				}
+				else
+				{
+					const unsigned e = d.cachePages[level][(size_t)coordId * 4096 + c]; // voted above
+					matId = e & 0xFF; matBlend = e >> 8;
+				}
+				unsigned slotK = 0xFFFFu;
+				const int nv = s.tabCell[s.tabClass[code] * 16] >> 4;
+				for (int k = 0; k < nv; ++k)
+				{
+					const VxbVertexDesc vd = vxb_regular_vertex_desc_lite(s.tabVert[code * 12 + k], zm);
+					const int sl = vxb_regular_owned_slot(vd);
+					if (sl >= 0) slotK = (slotK & ~(0xFu << (4 * sl))) | ((unsigned)k << (4 * sl));
+				}
+				s.cz[i] = (unsigned short)(code | (zm << 8));
+				s.recA[i] = matId | (matBlend << 8) | (slotK << 16);
+			}
+			__syncthreads();
+
+			// ---- pass B: new-vs-reuse decisions ----
+			for (unsigned i = tid; i < ntc; i += VXB_THREADS)
+			{
+				const int c = s.list[i];
+				const unsigned code = s.cz[i] & 0xFF, zm = s.cz[i] >> 8;
+				const unsigned geo = s.tabCell[s.tabClass[code] * 16];
+				const unsigned rowStart = vxb_rank_of(s.nt32, s.wpre, c & ~15), sliceStart = s.wpre[(c >> 8) * 8];
+				const int mask = (i > rowStart ? 1 : 0) | (rowStart > sliceStart ? 2 : 0) | (sliceStart > 0 ? 4 : 0);
+				const unsigned myMat = s.recA[i] & 0xFF;
+				unsigned newMask = 0, quirkMask = 0;
+				for (int k = 0; k < (int)(geo >> 4); ++k)
+				{
+					// new-vs-reuse decision (:1610-1644) from the owner cell's record
+					const VxbVertexDesc vd = vxb_regular_vertex_desc_lite(s.tabVert[code * 12 + k], zm);
+					bool isNew = true;
+					if (!vd.atC7 && (vd.dir & mask) == vd.dir) // dir == 8 never passes: mask < 8
+					{
+						const int oc = c - (vd.dir & 1) - ((vd.dir >> 1) & 1) * 16 - ((vd.dir >> 2) & 1) * 256;
+						int ok = VXB_NO_SLOT; unsigned oa = 0;
+						if ((s.nt32[oc >> 5] >> (oc & 31)) & 1u)
+						{
+							oa = s.recA[vxb_rank_of(s.nt32, s.wpre, oc)];
+							ok = (oa >> (16 + 4 * vd.slot)) & 0xF;
+						}
+						if (ok != VXB_NO_SLOT) { if ((oa & 0xFF) == myMat) isNew = false; } // else: material split, new at its natural place
+						else if (vd.endpoint) quirkMask |= 1u << k;                            // :1633-1640 creates the vertex at v0
+					}
+					if (isNew) newMask |= 1u << k;
+				}
+				s.recB[i] = newMask | (quirkMask << 12) | ((unsigned)mask << 24);
+				s.vbase[i] = (unsigned short)__popc(newMask);
+				s.tbase[i] = (unsigned short)(geo & 0xF);
+			}
+			__syncthreads();
+
+			// ---- exclusive scans in serial cell order (contiguous chunk per thread) ----
+			unsigned nverts, ntris;
+			{
+				const unsigned per = (ntc + VXB_THREADS - 1) / VXB_THREADS;
+				const unsigned i0 = min(tid * per, ntc), i1 = min(i0 + per, ntc);
+				unsigned sv = 0, st = 0;
+				for (unsigned i = i0; i < i1; ++i) { sv += s.vbase[i]; st += s.tbase[i]; }
+				unsigned total;
+				const unsigned base = vxb_block_scan(sv | (st << 16), s.warpSums, total);
+				nverts = total & 0xFFFF; ntris = total >> 16;
+				unsigned bv = base & 0xFFFF, bt = base >> 16;
+				for (unsigned i = i0; i < i1; ++i)
+				{
+					const unsigned cv = s.vbase[i], ct = s.tbase[i];
+					s.vbase[i] = (unsigned short)bv; s.tbase[i] = (unsigned short)bt;
+					bv += cv; bt += ct;
+				}
+			}
+			const bool inCta = MODE == 0 && nverts <= (unsigned)VXB_VL_CAP;
+			if (MODE == 0 && !inCta)
+			{
+				// too many vertices for the in-CTA path: hand the block to vxb_decide_kernel<4096, 1> + the flat kernels
+				__syncthreads();
+				if (tid < 128) { d.ntScratch[(size_t)s.emitIdx * 256 + tid] = s.nt32[tid]; d.ntScratch[(size_t)s.emitIdx * 256 + 128 + tid] = s.wpre[tid]; }
+				if (tid == 0) d.bigList[atomicAdd(&d.counters->bigCount[0], 1u)] = s.emitIdx;
+			}
+			else
+			{
+				if (tid == 0)
+				{
+					s.voff = atomicAdd(&d.counters->vertices, nverts);
+					s.ioff = atomicAdd(&d.counters->indices, ntris * 3);
+					s.cellBase = (MODE == 0) ? 0u : atomicAdd(&d.counters->cells, ntc);
+					s.slot = atomicAdd(&d.counters->records, 1u);
+				}
+				__syncthreads();
+				const unsigned voff = s.voff, ioff = s.ioff, cellBase = s.cellBase, slot = s.slot;
+				const bool fits = (unsigned long long)voff + nverts <= d.vcap && (unsigned long long)ioff + ntris * 3ull <= d.icap
+					&& (unsigned long long)cellBase + ntc <= d.ccap && slot < d.rcap;
+				if (fits && MODE != 0)
+				{
+					for (unsigned i = tid; i < ntc; i += VXB_THREADS)
+					{
+						const unsigned rb = s.recB[i];
+						VxbCellRec cr;
+						cr.a = (unsigned)s.list[i] | ((unsigned)s.cz[i] << 12) | ((rb >> 24) << 28);
+						cr.b = s.recA[i];
+						cr.c = rb & 0x00FFFFFFu;
+						cr.d = (unsigned)s.vbase[i] | ((unsigned)s.tbase[i] << 16);
+						*reinterpret_cast<uint4*>(&d.cellRecs[cellBase + i]) = *reinterpret_cast<const uint4*>(&cr);
+						d.cellBlock[cellBase + i] = slot;
+						unsigned nm = rb & 0xFFFu, j = voff + s.vbase[i];
+						while (nm) { const int k = __ffs(nm) - 1; nm &= nm - 1; d.vlist[j++] = ((cellBase + i) << 4) | (unsigned)k; }
+					}
+					if (tid < 128) { d.ntScratch[(size_t)s.emitIdx * 256 + tid] = s.nt32[tid]; d.ntScratch[(size_t)s.emitIdx * 256 + 128 + tid] = s.wpre[tid]; }
+				}
+				if (fits && MODE == 0)
+				{
+					// ---- the block's new vertices, one thread each (:1576-1726), from the halo tile ----
+					for (unsigned i = tid; i < ntc; i += VXB_THREADS)
+					{
+						unsigned nm = s.recB[i] & 0xFFFu, j = s.vbase[i];
+						while (nm) { const int k = __ffs(nm) - 1; nm &= nm - 1; s.vl[j++] = (unsigned short)((i << 4) | (unsigned)k); }
+					}
+					__syncthreads();
+					VxbTileView tv;
+					tv.dist = tileRaw; tv.ox = bx * 16; tv.oy = by * 16; tv.oz = bz * 16; tv.sx = hsx; tv.sy = hsy; tv.sz = hsz;
+					tv.mat = g.mat; tv.blend = g.blend; tv.n = d.n; // the two material / blend taps of a vertex stay global loads
+					for (unsigned j = tid; j < nverts; j += VXB_THREADS)
+					{
+						const unsigned e = s.vl[j];
+						const unsigned i = e >> 4; const int k = e & 15;
+						const int c = s.list[i];
+						const unsigned code = s.cz[i] & 0xFF, zm = s.cz[i] >> 8;
+						const int local[3] = { c & 15, (c >> 4) & 15, c >> 8 };
+						const int base[3] = { bx * 16 + local[0], by * 16 + local[1], bz * 16 + local[2] };
+						const unsigned ra = s.recA[i];
+						const unsigned matId = ra & 0xFF, matBlend = (ra >> 8) & 0xFF;
+						VxbVertexDesc vd = vxb_regular_vertex_desc_lite(s.tabVert[code * 12 + k], zm);
+						VxbRawVertex rv;
+						if (vd.endpoint)
+						{
+							const bool quirk = (s.recB[i] >> (12 + k)) & 1u;
+							vxb_corner_vertex(tv, 0, base, local, quirk ? vd.v0 : ((vd.t == 0) ? vd.v1 : vd.v0), matId, matBlend, rv);
+						}
+						else
+						{
+							const int a = vxb_dist(tv, base[0] + (vd.v0 & 1), base[1] + ((vd.v0 >> 1) & 1), base[2] + (vd.v0 >> 2));
+							const int b = vxb_dist(tv, base[0] + (vd.v1 & 1), base[1] + ((vd.v1 >> 1) & 1), base[2] + (vd.v1 >> 2));
+							vd.t = vxb_fixed_t(a, b); // :1591
+							vxb_edge_vertex(tv, 0, base, local, vd, matId, matBlend, rv);
+						}
+						vxb_regular_secondary(0, rv);
+						VxbVertex ov;
+						vxb_finish_vertex(rv, *d.lut, ov);
+						vxb_store_vertex(d.verts + voff + j, ov);
+						atomicOr(&s.used[matId >> 5], 1u << (matId & 31));
+					}
+					__syncthreads(); // the positions are read back by the degenerate test below
+					// ---- triangles, one thread per non-trivial cell (:1714-1726 + the degenerate filter of :1300-1321) ----
+					unsigned removed = 0;
+					for (unsigned i = tid; i < ntc; i += VXB_THREADS)
+					{
+						const int c = s.list[i];
+						const unsigned code = s.cz[i] & 0xFF, zm = s.cz[i] >> 8;
+						const unsigned char* cd = &s.tabCell[s.tabClass[code] * 16];
+						const unsigned geo = cd[0];
+						const unsigned newMask = s.recB[i] & 0xFFFu;
+						unsigned w[6] = { 0u, 0u, 0u, 0u, 0u, 0u }; // block-local vertex ids as 16-bit halves (an indexed array would be local memory)
+						unsigned nextNew = s.vbase[i];
+						const int nv = (int)(geo >> 4);
+#pragma unroll
+						for (int k = 0; k < 12; ++k)
+						{
+							if (k < nv)
+							{
+								unsigned vid;
+								if ((newMask >> k) & 1u) vid = nextNew++;
+								else
+								{
+									const VxbVertexDesc vd = vxb_regular_vertex_desc_lite(s.tabVert[code * 12 + k], zm);
+									const int oc = c - (vd.dir & 1) - ((vd.dir >> 1) & 1) * 16 - ((vd.dir >> 2) & 1) * 256; // reused => the owner exists
+									const unsigned oi = vxb_rank_of(s.nt32, s.wpre, oc);
+									const unsigned ok = (s.recA[oi] >> (16 + 4 * vd.slot)) & 0xF;
+									vid = (unsigned)s.vbase[oi] + __popc(s.recB[oi] & 0xFFFu & ((1u << ok) - 1u));
+								}
+								w[k >> 1] |= vid << ((k & 1) * 16);
+							}
+						}
+						auto vidOf = [&](unsigned k) -> unsigned {
+							const unsigned q = k >> 1;
+							const unsigned pair = q == 0 ? w[0] : q == 1 ? w[1] : q == 2 ? w[2] : q == 3 ? w[3] : q == 4 ? w[4] : w[5];
+							return (k & 1u) ? (pair >> 16) : (pair & 0xFFFFu);
+						};
+						unsigned* out = d.idx + ioff + (unsigned)s.tbase[i] * 3;
+						// a level-0 cell without a zero sample cannot produce a degenerate triangle (see vxb_triangle_kernel)
+						const bool cannotDegenerate = zm == 0u;
+						for (unsigned tr = 0; tr < (geo & 0xF); ++tr, out += 3)
+						{
+							const unsigned a = vidOf(cd[1 + tr * 3]), b = vidOf(cd[2 + tr * 3]), cc = vidOf(cd[3 + tr * 3]);
+							bool kept = true;
+							if (!cannotDegenerate)
+							{
+								const float* fa = d.verts[voff + a].pos; const float* fb = d.verts[voff + b].pos; const float* fc = d.verts[voff + cc].pos;
+								const float pa[3] = { fa[0] * 256.f, fa[2] * 256.f, fa[1] * 256.f };
+								const float pb[3] = { fb[0] * 256.f, fb[2] * 256.f, fb[1] * 256.f };
+								const float pc[3] = { fc[0] * 256.f, fc[2] * 256.f, fc[1] * 256.f };
+								kept = vxb_triangle_kept(pa, pb, pc);
+							}
+							if (kept) { out[0] = a; out[1] = b; out[2] = cc; }
+							else { out[0] = 0xFFFFFFFFu; out[1] = 0xFFFFFFFFu; out[2] = 0xFFFFFFFFu; ++removed; }
+						}
+					}
+					if (removed) atomicAdd(&s.removed, removed);
+					__syncthreads();
+				}
+				if (fits && tid == 0)
+				{
+					VxbBlockRec br;
+					br.packed = ((unsigned)level << 28) | coordId; br.emitIdx = s.emitIdx; br.voff = voff; br.ioff = ioff; br.cellBase = cellBase;
+					br.ntc = ntc; br.nverts = nverts; br.ntris = ntris; br.removed = (MODE == 0) ? s.removed : 0u;
+					for (int f = 0; f < 6; ++f) { br.tvoff[f] = 0; br.tioff[f] = 0; br.tvcount[f] = 0; br.ticount[f] = 0; }
+					br.pad[0] = br.pad[1] = br.pad[2] = 0;
+					d.blockRecs[slot] = br;
+					if (level > 0 && level != d.lastLevel && d.transitions) d.transList[atomicAdd(&d.counters->transBlocks, 1u)] = slot;
+				}
+			}
+		}
 		__syncthreads();
+		if (MODE == 2 && tid == 0) { __threadfence(); *(volatile unsigned char*)(d.coarseDone + d.coarseBase[level] + coordId) = 1; }
 		item = nextItem;
 		buf ^= 1;
 	}
 
 	__syncthreads();
 	if (tid < 16 && s.hist[tid]) atomicAdd(&d.counters->perCase[tid], s.hist[tid]);
+	if (tid < 8 && s.used[tid]) atomicOr(&d.counters->usedMaterials[tid], s.used[tid]);
 	if (tid == 0 && statNonTrivial) atomicAdd(&d.counters->nonTrivial, statNonTrivial);
 }
 
@@ -253,11 +705,6 @@ struct __align__(128) VxbDecideSmem
 	unsigned short vbase[CAP_C];  // exclusive scan of new-vertex counts
 	unsigned short tbase[CAP_C];  // exclusive scan of triangle counts
 };
-
-__device__ __forceinline__ unsigned vxb_rank_of(const unsigned int* nt32, const unsigned int* wpre, int c)
-{
-	return wpre[c >> 5] + __popc(nt32[c >> 5] & ((1u << (c & 31)) - 1u));
-}
 
 // TIER 0: items come from the emit list (all levels, top level first); blocks with > CAP_C cells go to bigList.
 // TIER 1: items come from bigList (CAP_C = 4096 = every possible block).
@@ -331,7 +778,7 @@ __global__ void __launch_bounds__(VXB_THREADS, (CAP_C <= 1024 ? VXB_OCC : 2)) vx
 		{
 			const int c = s.list[i];
 			signed char v[8];
-			vxb_tile_samples(s.tile, c, v);
+			vxb_tile_samples<VXB_TILE_PITCH, 17>(s.tile, c, v);
 			const unsigned code = vxb_case_code(v);
 			const unsigned zm = vxb_zero_mask(v);
 			unsigned matId, matBlend;
@@ -452,13 +899,6 @@ __global__ void __launch_bounds__(VXB_THREADS, (CAP_C <= 1024 ? VXB_OCC : 2)) vx
 	}
 }
 
-// true when an arena overflowed: the host grows the arenas and repeats the run, the later kernels do nothing
-__device__ __forceinline__ bool vxb_overflowed(const VxbDev& d)
-{
-	const VxbCounters* c = d.counters;
-	return c->vertices > d.vcap || c->indices > d.icap || c->cells > d.ccap || c->records > d.rcap;
-}
-
 // ------------------------------------------------------------------------------------------------
 // flat kernels.  part 0 = [0, split) (group 0), part 1 = [split, total) (group 1), part 2 = everything
 // ------------------------------------------------------------------------------------------------
@@ -525,10 +965,8 @@ __global__ void __launch_bounds__(VXB_THREADS, VXB_FLAT_OCC) vxb_vertex_kernel(c
 // load, so the twelve distance taps of a vertex come from shared memory instead of separate 32-byte DRAM sectors.
 // Grid-edge clamping (:1198) is baked into the tile.  (Staging the material / blend samples too was slower: the extra
 // 18 KB per CTA halve the occupancy.)
-#define VXB_DTILE_PITCH 48
 #define VXB_VB_CELLS 512   // blocks with more non-trivial cells read their records from global memory
 #define VXB_VB_THREADS 128 // a block has ~350 new vertices: 128-thread CTAs waste fewer lanes in the last round and more of them fit an SM
-#define VXB_DTILE_BYTES (19 * 19 * VXB_DTILE_PITCH)
 struct __align__(128) VxbVertexBlockSmem
 {
 	signed char dist[VXB_DTILE_BYTES + 80];

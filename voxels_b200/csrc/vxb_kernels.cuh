@@ -46,6 +46,7 @@ struct VxbCounters
 	unsigned int vertexBlockCursor;
 	unsigned int transBlocks, transCursor;  // emitted mid-level blocks (vxb_transition_kernel work list)
 	unsigned int finishCursor;
+	unsigned int coarseCursor;              // item cursor of the single launch that handles the coarse levels
 };
 
 // One non-trivial cell of an emitted block (written by vxb_decide_kernel, read by the flat kernels)
@@ -101,7 +102,50 @@ struct VxbDev
 	uint2* tvlist;            // transition vertex (arena index) -> {block slot, face << 12 | cell << 4 | table vertex}
 	VxbBlockRec* blockRecs;
 	const unsigned char* lattice1; // (n/2)^3 even-lattice copy of the distance volume (level-1 samples), or null
+	int computed;                  // levels [0, computed) are polygonized
+	// sign-mix pyramid (vxb_pyramid_kernel): per block of level l >= 1, bit 0 = some covered level-0 block holds a negative
+	// sample, bit 1 = a non-negative one.  Lets the block walk of levels >= 2 skip blocks that cannot have a non-trivial cell.
+	unsigned char* mixInfo[VXB_MAX_LEVELS];
+	// coarse levels (one launch, vxb_block_kernel<2>): levels [coarseLo, computed); a block waits for the done flags of its children
+	int coarseLo;
+	unsigned char* coarseDone;                 // [coarseBase[l] + coordId], zeroed per run
+	unsigned int coarseBase[VXB_MAX_LEVELS];
+	// sharded runs (vxb_shard_*): the z-axis is cut into groups of shardLayers level-0 block layers, dealt cyclically to
+	// shardWorld ranks; blockInfo is stored rank-major (every rank's layers contiguous: the layout of the all-gather)
+	int shardWorld, shardRank, shardLayers;
+	// work ownership of a sharded run: blocks of levels <= sbLevel belong to the rank that owns their level-sbLevel ancestor
+	// ("super-block"; sbMine[coordId at sbLevel] != 0 = mine, written by vxb_plan_kernel from the weights the pyramid kernel
+	// counts); the coarse levels above are classified by every rank and emitted by rank (coordId + level) % world
+	int sbLevel;
+	unsigned char* sbMine;
+	unsigned int* sbWeight;
 };
+
+__device__ __forceinline__ bool vxb_block_is_mine(const VxbDev& d, int level, int bx, int by, int bz)
+{
+	if (!d.shardWorld) return true;
+	const int sh = d.sbLevel - level, nbs = (d.n >> 4) >> d.sbLevel;
+	return d.sbMine[((size_t)(bz >> sh) * nbs + (by >> sh)) * nbs + (bx >> sh)] != 0;
+}
+
+__device__ __forceinline__ bool vxb_coarse_emit_is_mine(const VxbDev& d, int level, unsigned coordId)
+{
+	return !d.shardWorld || (int)((coordId + (unsigned)level) % (unsigned)d.shardWorld) == d.shardRank;
+}
+
+// layer z of the level-0 block grid -> its slot in blockInfo (identity unless the run is sharded)
+__device__ __forceinline__ int vxb_layer_slot(const VxbDev& d, int z)
+{
+	if (!d.shardWorld) return z;
+	const int g = z / d.shardLayers, owner = g % d.shardWorld, perRank = (d.n >> 4) / d.shardWorld;
+	return owner * perRank + (g / d.shardWorld) * d.shardLayers + z % d.shardLayers;
+}
+
+__device__ __forceinline__ const unsigned char* vxb_binfo_row(const VxbDev& d, int y, int z)
+{
+	const int nb0 = d.n >> 4;
+	return d.blockInfo + ((size_t)vxb_layer_slot(d, z) * nb0 + y) * nb0;
+}
 
 // ------------------------------------------------------------------------------------------------
 // small PTX wrappers (mbarrier + TMA), sm_90+/sm_100a
@@ -188,13 +232,15 @@ __device__ __forceinline__ unsigned vxb_zero_bytes(unsigned w) // 0x80 in every 
 template <int J>
 __global__ void __launch_bounds__(VXB_THREADS, (J == 32 ? 3 : 4)) vxb_scan_kernel(const signed char* __restrict__ dist, int n, unsigned int* __restrict__ scanFlags,
 	unsigned char* __restrict__ lattice1 /* (n/2)^3: the samples at even coordinates = the level-1 lattice, or null */,
-	int zBlock0 /* first block layer (a rank of a sharded run scans its slab + one layer either side) */)
+	int groupLayers, int world, int rank /* sharded runs: blockIdx.z counts this rank's layers (groups of groupLayers block layers,
+	                                        dealt cyclically to the ranks); unsharded: world = 1 */)
 {
 	constexpr int RG = VXB_THREADS / J; // row groups: thread (j, rg) reads rows rg, rg + RG, ... of block j
 	__shared__ unsigned sFlags[J];
 	__shared__ unsigned sChanges[J];
 	const int nb = n >> 4;
-	const int bx0 = blockIdx.x * J, by = blockIdx.y, bz = blockIdx.z + zBlock0;
+	const int bx0 = blockIdx.x * J, by = blockIdx.y;
+	const int bz = ((int)(blockIdx.z / groupLayers) * world + rank) * groupLayers + (int)(blockIdx.z % groupLayers);
 	const int tid = threadIdx.x;
 	const int j = tid % J, rg = tid / J;
 	if (tid < J) { sFlags[tid] = 0; sChanges[tid] = 0; }
@@ -270,11 +316,16 @@ __global__ void __launch_bounds__(VXB_THREADS, (J == 32 ? 3 : 4)) vxb_scan_kerne
 
 // K1b: raw flags -> blockInfo.  One thread per level-0 block.
 __global__ void vxb_block_info_kernel(const signed char* __restrict__ dist, int n, const unsigned int* __restrict__ scanFlags, unsigned char* __restrict__ blockInfo,
-	size_t first, size_t total /* block range [first, total): whole layers, z-major */)
+	size_t total /* blocks of this rank: whole layers, z-major */, int groupLayers, int world, int rank /* as vxb_scan_kernel */)
 {
 	const int nb = n >> 4;
-	for (size_t b = first + (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < total; b += (size_t)gridDim.x * blockDim.x)
+	const size_t layerBlocks = (size_t)nb * nb;
+	for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (size_t)gridDim.x * blockDim.x)
 	{
+		// q = rank-local index (layer-major); b = the block's coordinate id; the result goes to the rank-major slot
+		const int lz = (int)(q / layerBlocks);
+		const int tz = ((lz / groupLayers) * world + rank) * groupLayers + lz % groupLayers;
+		const size_t b = (size_t)tz * layerBlocks + q % layerBlocks;
 		const unsigned f = scanFlags[b];
 		const bool neg = f & 1, pos = f & 2, zero = f & 4;
 		const unsigned changes = f >> 8; // value changes inside 16-byte rows (lower bound of run ends)
@@ -301,8 +352,69 @@ __global__ void vxb_block_info_kernel(const signed char* __restrict__ dist, int 
 				}
 			}
 		}
-		blockInfo[b] = (unsigned char)((neg ? VXB_BI_NEG : 0) | ((pos || zero) ? VXB_BI_NONNEG : 0) | (empty ? VXB_BI_EMPTY : 0)
+		blockInfo[(size_t)rank * (total) + q] = (unsigned char)((neg ? VXB_BI_NEG : 0) | ((pos || zero) ? VXB_BI_NONNEG : 0) | (empty ? VXB_BI_EMPTY : 0)
 			| ((f & 8) ? VXB_BI_NEG_E : 0) | ((f & 16) ? VXB_BI_NONNEG_E : 0));
+	}
+}
+
+// K1c: sign-mix pyramid over the level-0 blockInfo: mixInfo[l][b] = OR of (NEG, NONNEG) over the (2^l)^3 level-0 blocks that
+// block b of level l covers.  CTAs [0, ctasA): one thread per block of levels 1 and 2; then one CTA per block of levels >= 3.
+__global__ void __launch_bounds__(256) vxb_pyramid_kernel(const VxbDev d, const unsigned ctasA)
+{
+	const int nb0 = d.n >> 4;
+	if (blockIdx.x < ctasA)
+	{
+		unsigned q = blockIdx.x * 256u + threadIdx.x;
+		int level = 0;
+		for (int l = 1; l <= 2 && l < d.levels; ++l)
+		{
+			const unsigned cnt = (unsigned)(nb0 >> l) * (nb0 >> l) * (nb0 >> l);
+			if (q < cnt) { level = l; break; }
+			q -= cnt;
+		}
+		if (!level) return;
+		const int nb = nb0 >> level, span = 1 << level;
+		const int bx = q % nb, by = (q / nb) % nb, bz = q / (nb * nb);
+		unsigned u = 0, mixed = 0;
+		for (int z = 0; z < span; ++z) for (int y = 0; y < span; ++y)
+		{
+			const unsigned char* row = vxb_binfo_row(d, by * span + y, bz * span + z) + bx * span;
+			for (int x = 0; x < span; ++x) { u |= row[x]; mixed += (row[x] & 3u) == 3u; }
+		}
+		d.mixInfo[level][q] = (unsigned char)(u & 3u);
+		if (d.sbWeight && level == d.sbLevel) d.sbWeight[q] = mixed;
+		return;
+	}
+	unsigned q = blockIdx.x - ctasA;
+	int level = 3;
+	for (; level < d.levels; ++level)
+	{
+		const unsigned cnt = (unsigned)(nb0 >> level) * (nb0 >> level) * (nb0 >> level);
+		if (q < cnt) break;
+		q -= cnt;
+	}
+	if (level >= d.levels) return;
+	const int nb = nb0 >> level, span = 1 << level; // span >= 8: rows of whole 8-byte words
+	const int bx = q % nb, by = (q / nb) % nb, bz = q / (nb * nb);
+	unsigned u = 0, mixed = 0;
+	for (int r = threadIdx.x; r < span * span; r += 256)
+	{
+		const uint2* row = reinterpret_cast<const uint2*>(vxb_binfo_row(d, by * span + r % span, bz * span + r / span) + bx * span);
+		for (int x = 0; x < span / 8; ++x)
+		{
+			const uint2 w = row[x];
+			u |= w.x | w.y;
+			mixed += __popc(w.x & (w.x >> 1) & 0x01010101u) + __popc(w.y & (w.y >> 1) & 0x01010101u);
+		}
+	}
+	u |= u >> 16; u |= u >> 8;
+	const int neg = __syncthreads_or(u & 1u), nonneg = __syncthreads_or(u & 2u);
+	if (threadIdx.x == 0) d.mixInfo[level][q] = (unsigned char)((neg ? 1u : 0u) | (nonneg ? 2u : 0u));
+	if (d.sbWeight && level == d.sbLevel)
+	{
+		if (threadIdx.x == 0) d.sbWeight[q] = 0;
+		__syncthreads();
+		if (mixed) atomicAdd(&d.sbWeight[q], mixed);
 	}
 }
 
@@ -438,6 +550,26 @@ __global__ void __launch_bounds__(VXB_THREADS) vxb_unpack_rle_kernel(const unsig
 // ------------------------------------------------------------------------------------------------
 // K2: block selection for one level
 // ------------------------------------------------------------------------------------------------
+// Levels >= 2: can block (bx, by, bz) have a non-trivial cell or a vote to cast?  Its cells sample the closed box
+// [origin, origin + 16 m], i.e. the level-(l-1) blocks 2b .. 2b+2 per axis (superset: the whole +2 block instead of its first
+// plane); without a sign mix there no cell is non-trivial, and without a child page no vote can succeed (:763-837), so the
+// block leaves no trace in the result, the caches or the statistics (BlocksCalculated / TrivialCells count every block).
+__device__ __forceinline__ bool vxb_coarse_block_needed(const VxbDev& d, int level, int bx, int by, int bz)
+{
+	const int cnb = (d.n >> 4) >> (level - 1);
+	const unsigned char* mix = d.mixInfo[level - 1];
+	const unsigned char* valid = d.cacheValid[level - 1];
+	unsigned u = 0, anyChild = 0;
+	for (int z = 0; z < 3; ++z) for (int y = 0; y < 3; ++y) for (int x = 0; x < 3; ++x)
+	{
+		const int cx = min(2 * bx + x, cnb - 1), cy = min(2 * by + y, cnb - 1), cz = min(2 * bz + z, cnb - 1);
+		const size_t cb = ((size_t)cz * cnb + cy) * cnb + cx;
+		u |= mix[cb];
+		if (x < 2 && y < 2 && z < 2) anyChild |= __ldcg(valid + cb);
+	}
+	return u == 3u || anyChild != 0u;
+}
+
 __global__ void vxb_select_kernel(VxbDev d, int level)
 {
 	const int m = 1 << level, nb = d.n / 16 / m, nb0 = d.n / 16;
@@ -454,14 +586,15 @@ __global__ void vxb_select_kernel(VxbDev d, int level)
 		{
 			const int bx = x0 + (int)(q % nx), by = y0 + (int)((q / nx) % ny), bz = z0 + (int)(q / ((unsigned)nx * ny));
 			b = ((unsigned)bz * nb + by) * nb + bx;
-			if (level == 0)
+			if (!vxb_block_is_mine(d, level, bx, by, bz)) { /* another rank's block */ }
+			else if (level == 0)
 			{
 				// AreBlockAndNeighborsEmpty :1511-1527
 				bool skip = true;
 				for (int z = -1; z < 2 && skip; ++z) for (int y = -1; y < 2 && skip; ++y) for (int x = -1; x < 2; ++x)
 				{
 					const int cx = min(max(bx + x, 0), nb - 1), cy = min(max(by + y, 0), nb - 1), cz = min(max(bz + z, 0), nb - 1);
-					if (!(d.blockInfo[((size_t)cz * nb + cy) * nb + cx] & VXB_BI_EMPTY)) { skip = false; break; }
+					if (!(vxb_binfo_row(d, cy, cz)[cx] & VXB_BI_EMPTY)) { skip = false; break; }
 				}
 				if (!skip)
 				{
@@ -471,7 +604,7 @@ __global__ void vxb_select_kernel(VxbDev d, int level)
 					for (int z = 0; z < 2; ++z) for (int y = 0; y < 2; ++y) for (int x = 0; x < 2; ++x)
 					{
 						const int cx = min(bx + x, nb - 1), cy = min(by + y, nb - 1), cz = min(bz + z, nb - 1);
-						u |= d.blockInfo[((size_t)cz * nb + cy) * nb + cx];
+						u |= vxb_binfo_row(d, cy, cz)[cx];
 					}
 					take = (u & VXB_BI_NEG) && (u & VXB_BI_NONNEG);
 				}
@@ -486,14 +619,14 @@ __global__ void vxb_select_kernel(VxbDev d, int level)
 				{
 					const int cx = min(2 * bx + x, nb0 - 1), cy = min(2 * by + y, nb0 - 1), cz = min(2 * bz + z, nb0 - 1);
 					const size_t cb = ((size_t)cz * nb0 + cy) * nb0 + cx;
-					const unsigned bi = d.blockInfo[cb];
+					const unsigned bi = vxb_binfo_row(d, cy, cz)[cx];
 					u |= (bi >> 3) & 3u;
 					if (edge) u |= bi & 3u;
 					if (x < 2 && y < 2 && z < 2 && d.consValid[cb]) anyChild = true;
 				}
 				take = (u == 3u) || anyChild;
 			}
-			else take = true;
+			else take = vxb_coarse_block_needed(d, level, bx, by, bz);
 		}
 		const unsigned ballot = __ballot_sync(0xFFFFFFFFu, take);
 		const unsigned cballot = __ballot_sync(0xFFFFFFFFu, counted);
@@ -506,6 +639,68 @@ __global__ void vxb_select_kernel(VxbDev d, int level)
 		}
 		off = __shfl_sync(0xFFFFFFFFu, off, 0);
 		if (take) d.worklist[d.workBase[level] + off + __popc(ballot & ((1u << lane) - 1u))] = b;
+	}
+}
+
+// Sharded runs: which super-blocks are mine.  Every rank runs this on the same (all-gathered) blockInfo, so all ranks
+// agree: super-blocks in coordinate order, cut where the running weight (level-0 blocks with a sign mix) crosses
+// total * r / world.  One CTA of 1024 threads; <= 32768 super-blocks.
+__global__ void __launch_bounds__(1024) vxb_plan_kernel(const VxbDev d)
+{
+	__shared__ unsigned long long sums[32];
+	__shared__ unsigned long long sTotal;
+	const int nbs = (d.n >> 4) >> d.sbLevel;
+	const unsigned count = (unsigned)nbs * nbs * nbs;
+	const unsigned per = (count + 1023u) / 1024u;
+	const unsigned i0 = min(threadIdx.x * per, count), i1 = min(i0 + per, count);
+	unsigned long long mine = 0;
+	for (unsigned i = i0; i < i1; ++i) mine += (unsigned long long)d.sbWeight[i] * 1024ull + 1ull; // + 1: a super-block without a mixed block still costs a look (about 1/1000 of a block)
+	unsigned long long inc = mine;
+	const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	for (int o = 1; o < 32; o <<= 1) { const unsigned long long t = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= (unsigned)o) inc += t; }
+	if (lane == 31) sums[warp] = inc;
+	__syncthreads();
+	if (threadIdx.x == 0)
+	{
+		unsigned long long acc = 0;
+		for (int w = 0; w < 32; ++w) { const unsigned long long v = sums[w]; sums[w] = acc; acc += v; }
+		sTotal = acc;
+	}
+	__syncthreads();
+	unsigned long long run = sums[warp] + inc - mine; // exclusive prefix of this thread's chunk
+	const unsigned long long total = sTotal;
+	for (unsigned i = i0; i < i1; ++i)
+	{
+		const unsigned owner = (unsigned)min((unsigned long long)(d.shardWorld - 1), run * (unsigned long long)d.shardWorld / total);
+		d.sbMine[i] = owner == (unsigned)d.shardRank;
+		run += (unsigned long long)d.sbWeight[i] * 1024ull + 1ull;
+	}
+}
+
+// Sharded runs: the material pages of level sbLevel that this rank produced go to every peer (plain 16-byte stores
+// through the peers' mapped buffers: NVLink), so that every rank can classify the coarse levels above.
+struct VxbPeers
+{
+	unsigned short* pages[8];
+	unsigned char* valid[8];
+	int count;
+};
+
+__global__ void __launch_bounds__(VXB_THREADS) vxb_publish_kernel(const VxbDev d, const VxbPeers peers)
+{
+	const int nbs = (d.n >> 4) >> d.sbLevel;
+	const unsigned count = (unsigned)nbs * nbs * nbs;
+	for (unsigned b = blockIdx.x; b < count; b += gridDim.x)
+	{
+		if (!d.sbMine[b] || !d.cacheValid[d.sbLevel][b]) continue;
+		const uint4* src = reinterpret_cast<const uint4*>(d.cachePages[d.sbLevel] + (size_t)b * 4096);
+		const uint4 v0 = src[threadIdx.x], v1 = src[threadIdx.x + VXB_THREADS];
+		for (int p = 0; p < peers.count; ++p)
+		{
+			uint4* dst = reinterpret_cast<uint4*>(peers.pages[p] + (size_t)b * 4096);
+			dst[threadIdx.x] = v0; dst[threadIdx.x + VXB_THREADS] = v1;
+			if (threadIdx.x == 0) peers.valid[p][b] = 1;
+		}
 	}
 }
 
@@ -589,7 +784,7 @@ __device__ __forceinline__ bool vxb_vote_candidate(const VxbVoteSource& d, const
 	const int cx = bx0 >> sh, cy = by0 >> sh, cz = bz0 >> sh;
 	const size_t bid = ((size_t)(cz >> 4) * cnb + (cy >> 4)) * cnb + (cx >> 4);
 	const int lx = cx & 15, ly = cy & 15, lz = cz & 15;
-	const unsigned valid = d.valid[bid];
+	const unsigned valid = __ldcg(d.valid + bid); // L2: a flag byte shares its line with blocks other CTAs of this launch finish (coarse levels)
 	if (d.level == 1)
 	{
 		const unsigned short* rows = reinterpret_cast<const unsigned short*>(static_cast<const unsigned int*>(d.pages) + bid * 128);
@@ -615,7 +810,7 @@ __device__ __noinline__ int vxb_vote_cell(const VxbVoteSource d, const int bx0, 
 	unsigned cid[8], cbl[8]; // children, x fastest (:773-775); fully unrolled below so they live in registers
 	if (level == 1)
 	{
-		if (!d.valid[bid]) return -1;
+		if (!__ldcg(d.valid + bid)) return -1;
 		const unsigned short* rows = reinterpret_cast<const unsigned short*>(static_cast<const unsigned int*>(d.pages) + bid * 128); // 16 bits per (z,y) row
 		const unsigned r00 = (rows[lz * 16 + ly] >> lx) & 3u, r01 = (rows[lz * 16 + ly + 1] >> lx) & 3u;
 		const unsigned r10 = (rows[(lz + 1) * 16 + ly] >> lx) & 3u, r11 = (rows[(lz + 1) * 16 + ly + 1] >> lx) & 3u;
@@ -634,7 +829,7 @@ __device__ __noinline__ int vxb_vote_cell(const VxbVoteSource d, const int bx0, 
 	}
 	else
 	{
-		if (!d.valid[bid]) return -1;
+		if (!__ldcg(d.valid + bid)) return -1;
 		const unsigned int* page = reinterpret_cast<const unsigned int*>(static_cast<const unsigned short*>(d.pages) + bid * 4096); // 2 cells per word
 		const int o = (lz * 256 + ly * 16 + lx) >> 1;
 		const unsigned e0 = page[o], e1 = page[o + 8], e2 = page[o + 128], e3 = page[o + 136];

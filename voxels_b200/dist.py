@@ -1,12 +1,13 @@
 """torch.distributed plumbing for the multi-GPU runs (one process per GPU; NCCL on the B200 box, gloo in the CPU tests).
 
-Two ways to use N GPUs:
-  * independent tiles (bench.py's weak-scaling line): every rank owns its own n^3 tile of the terrain (`tile_origin`);
-    no data-path collective, only the barrier around the timed region and the max-reduction of the device times;
-  * ONE grid sharded into z-slabs (`ShardedGrid`, SURVEY.md section 8e / BASELINE configs[3]): the cube lives in one
-    virtual address range per rank whose slabs are the ranks' HBM, mapped into every peer over NVLink (file
-    descriptors travel over Unix sockets, `exchange_fds`); the data path has ONE all-gather (the material pages of the
-    last level that nests in a slab) and the directories are all-gathered at the end."""
+ONE grid polygonized by all ranks (`ShardedGrid`, SURVEY.md section 8e / BASELINE configs[3], include/vxb200.h "Sharded
+runs"): the cube lives in one virtual address range per rank whose z-pieces are the ranks' HBM (dealt cyclically), mapped
+into every peer over NVLink (file descriptors travel over Unix sockets, `exchange_fds`); work is dealt by blocks; the
+data path has two exchanges (an ncclAllGather of the per-block info, peer stores of the material pages ordered by a
+second tiny all-gather), both issued by libvxb200.so itself on the context's stream, so a step is one CUDA graph.
+torch.distributed carries the rendezvous: the NCCL id broadcast, barriers, the max-reduction of device times and the
+all-gather of the block directories.  `tile_origin` / `whole_job_throughput`: the independent-tiles weak-scaling mode
+kept as a secondary bench line."""
 import os
 import socket
 import threading
@@ -66,79 +67,23 @@ def whole_job_throughput(n, world, ms_per_step):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-# one grid, z-slabs across the ranks
+# one grid, all ranks
 # ---------------------------------------------------------------------------------------------------------------------
 
-def uniform_planes(n, world):
-    return [n * r // world for r in range(world + 1)]
+def default_group_planes(n, world):
+    """Planes per piece: 32 (the finest the block walk allows) when the pieces still meet the 2 MiB allocation granularity
+    for the volumes AND the even-lattice channel (an eighth of a volume piece), else the smallest multiple that does;
+    never more than n / world."""
+    g = 32
+    while g * n * n // 8 % (2 << 20) != 0 and g < n // world:
+        g *= 2
+    return min(g, n // world)
 
 
-def slab_planes(n, rank, world, planes=None):
-    """[z0, z1) of rank's slab."""
-    planes = uniform_planes(n, world) if planes is None else planes
-    return int(planes[rank]), int(planes[rank + 1])
-
-
-def split_level(n, world, planes=None):
-    """Levels [0, split) have blocks that nest in every slab (vxb_shard_exchange.split_level): the block edge 16 << l
-    divides every slab boundary."""
-    planes = uniform_planes(n, world) if planes is None else planes
-    levels = (n // 16).bit_length()
-    s = 0
-    while s < levels and all(int(p) % (16 << s) == 0 for p in planes[1:-1]):
-        s += 1
-    return s
-
-
-def balanced_planes(layer_weights, world, align_layers):
-    """Slab boundaries that even out the work: layer_weights[i] = work in level-0 block layer i (16 planes), e.g. the
-    vertices + triangles the last run produced there.  Boundaries are multiples of align_layers layers (that decides
-    which levels still nest, see split_level); every slab gets at least one such unit.  Minimises the maximum slab
-    weight (dynamic programme over the <= n/16/align_layers cells)."""
-    import numpy as np
-    w = np.asarray(layer_weights, np.float64)
-    cells = len(w) // align_layers
-    assert cells >= world, "more ranks than alignment units"
-    cw = np.concatenate([[0.0], np.cumsum(w.reshape(cells, align_layers).sum(axis=1))])
-    inf = float("inf")
-    best = [[inf] * (cells + 1) for _ in range(world + 1)]
-    cut = [[0] * (cells + 1) for _ in range(world + 1)]
-    best[0][0] = 0.0
-    for r in range(1, world + 1):
-        for e in range(r, cells - (world - r) + 1):
-            for b in range(r - 1, e):
-                if best[r - 1][b] == inf:
-                    continue
-                # a tiny per-cell cost keeps empty regions spread over the ranks instead of piled on one
-                cost = max(best[r - 1][b], cw[e] - cw[b] + 1e-9 * (e - b))
-                if cost < best[r][e]:
-                    best[r][e], cut[r][e] = cost, b
-    bounds, e = [cells], cells
-    for r in range(world, 0, -1):
-        e = cut[r][e]
-        bounds.append(e)
-    return [b * align_layers * 16 for b in reversed(bounds)]
-
-
-def layer_weights_from_directory(n, records, scan_units_per_byte=1.0 / 512):
-    """Work per level-0 block layer from a block directory (numpy RECORD_DTYPE): a block's vertices + indices/3, spread
-    over the layers it covers, plus the volume term - every layer is streamed once by the scan kernel whether or not
-    the surface crosses it (measured on a B200: ~0.1 ns per vertex/triangle unit, scan at ~5.3 TB/s => ~1/512 unit per
-    byte of the layer's 16 n^2 distance samples)."""
-    import numpy as np
-    nb0 = n // 16
-    w = np.full(nb0, scan_units_per_byte * 16.0 * n * n, np.float64)
-    level = records["level"].astype(np.int64)
-    nbl = nb0 >> level
-    z = records["coord_id"].astype(np.int64) // (nbl * nbl)
-    work = (records["vertex_count"].astype(np.float64) + records["index_count"] / 3.0
-            + records["trans_vertex_count"].sum(axis=1) + records["trans_index_count"].sum(axis=1) / 3.0)
-    for l in np.unique(level):
-        sel = level == l
-        span = 1 << int(l)
-        per_layer = np.bincount(z[sel], weights=work[sel] / span, minlength=nb0 >> int(l))
-        w += np.repeat(per_layer, span)
-    return w
+def owned_pieces(n, rank, world, group_planes):
+    """[(piece, z0, z1)] of the pieces rank backs with its own HBM (cyclic deal)."""
+    pieces = n // group_planes
+    return [(p, p * group_planes, (p + 1) * group_planes) for p in range(rank, pieces, world)]
 
 
 def exchange_fds(rank, world, fds, key):
@@ -216,43 +161,60 @@ def gather_directories(ranks, records):
 
 class ShardedGrid:
     """One n^3 grid polygonized by all ranks (one GPU each).  Usage:
-        sg = ShardedGrid(ranks, n)            # cube: local slab + peers' slabs mapped over NVLink
-        d, m, b = sg.slab_tensors()           # torch uint8/int8 views [n/world, n, n] of the LOCAL slab: fill them
-        sg.ready()                            # barrier: every slab is filled
-        info = sg.polygonize()                # two phases around the one all-gather; this rank's blocks
+        sg = ShardedGrid(ranks, n)            # cube: local pieces + peers' pieces mapped over NVLink, page buffers, NCCL
+        for z0, z1, (d, m, b) in sg.piece_tensors():   # torch views [z1-z0, n, n] of the LOCAL pieces: fill them
+            ...
+        sg.ready()                            # barrier: every piece is filled
+        info = sg.polygonize()                # one stream-ordered step (two exchanges inside); this rank's blocks
         directory, owner = sg.directory()     # every rank's blocks (all-gather), reference order
     """
 
-    def __init__(self, ranks, n, device_index=None, key=None, planes=None):
+    def __init__(self, ranks, n, device_index=None, key=None, group_planes=None):
         import torch
         from . import capi
         self.ranks, self.n = ranks, n
-        self.planes = None if planes is None else [int(p) for p in planes]  # None = equal slabs
         self.rank, self.world = ranks.rank, ranks.world
+        self.group_planes = default_group_planes(n, self.world) if group_planes is None else int(group_planes)
         self.device_index = ranks.local_rank if device_index is None else device_index
         self.device = torch.device("cuda", self.device_index)
         self.ctx = capi.Context(self.device_index)
-        self.ctx.cube_create(n, self.rank, self.world, self.planes)
+        self.ctx.cube_create(n, self.rank, self.world, self.group_planes)
+        self.pieces, self.channels, _ = self.ctx.cube_info()
+        self.ctx.shard_configure(self.rank, self.world, self.group_planes)
         if self.world > 1:
-            fds = [self.ctx.cube_export(c) for c in range(3)]
+            mine = [p for p, _, _ in owned_pieces(n, self.rank, self.world, self.group_planes)]
+            fds = [self.ctx.cube_export(c, p) for p in mine for c in range(self.channels)] + [self.ctx.shard_export()]
             key = key or os.environ.get("MASTER_PORT", "0")
             got = exchange_fds(self.rank, self.world, fds, "%s-%d" % (key, n))
             for peer, theirs in got.items():
-                for c, fd in enumerate(theirs):
-                    self.ctx.cube_import(peer, c, fd)
-                    os.close(fd)
+                it = iter(theirs)
+                for p, _, _ in owned_pieces(n, peer, self.world, self.group_planes):
+                    for c in range(self.channels):
+                        fd = next(it)
+                        self.ctx.cube_import(c, p, fd)
+                        os.close(fd)
+                fd = next(it)
+                self.ctx.shard_import(peer, fd)
+                os.close(fd)
             for fd in fds:
                 os.close(fd)
-        self._stream = torch.cuda.ExternalStream(self.ctx.exchange_stream(), device=self.device)
+            # the communicator of the two in-step all-gathers: id from rank 0, carried by torch.distributed
+            ids = [capi.nccl_unique_id() if self.rank == 0 else None]
+            ranks.td.broadcast_object_list(ids, src=0)
+            self.ctx.shard_nccl_init(ids[0], self.rank, self.world)
+        self.last_attempts = 0
 
-    def slab_tensors(self):
+    def piece_tensors(self):
+        """[(z0, z1, (dist, mat, blend))]: torch views of this rank's pieces."""
         import torch
         from . import capi
-        d, m, b, size = self.ctx.cube_slab()
-        z0, z1 = slab_planes(self.n, self.rank, self.world, self.planes)
-        shape = (z1 - z0, self.n, self.n)
-        view = lambda p: torch.as_tensor(capi.DevicePointer(p, size), device=self.device).view(shape)  # noqa: E731
-        return view(d).view(torch.int8), view(m), view(b)
+        out = []
+        for p, z0, z1 in owned_pieces(self.n, self.rank, self.world, self.group_planes):
+            d, m, b, size = self.ctx.cube_piece(p)
+            shape = (z1 - z0, self.n, self.n)
+            view = lambda ptr: torch.as_tensor(capi.DevicePointer(ptr, size), device=self.device).view(shape)  # noqa: E731
+            out.append((z0, z1, (view(d).view(torch.int8), view(m), view(b))))
+        return out
 
     def ready(self):
         import torch
@@ -260,39 +222,20 @@ class ShardedGrid:
         self.ranks.barrier()
 
     def polygonize(self, flags=0, max_attempts=4):
-        import torch
         from . import capi
-        td = self.ranks.td
-        for _ in range(max_attempts):
-            self.ctx.polygonize_sharded(self.rank, self.world, 0, flags, self.planes)
-            x = self.ctx.shard_exchange_info(self.rank, self.world, self.planes)
-            if self.world > 1 and x.pages_bytes:
-                # the ONE data-path exchange, stream-ordered after phase 0 on the context's exchange stream, in place: the
-                # material pages + flags of the last nested level.  Equal slabs: all-gather; unequal: rank 0 (the only
-                # consumer, it builds the coarse levels) receives every other rank's range in one NCCL group.
-                with torch.cuda.stream(self._stream):
-                    pages = torch.as_tensor(capi.DevicePointer(x.pages, x.pages_bytes), device=self.device)
-                    valid = torch.as_tensor(capi.DevicePointer(x.valid, x.valid_bytes), device=self.device)
-                    if self.planes is None:
-                        for full in (pages, valid):
-                            chunk = full.numel() // self.world
-                            td.all_gather_into_tensor(full, full[self.rank * chunk:(self.rank + 1) * chunk])
-                    else:
-                        def rng(r, unit):
-                            return slice(self.planes[r] // x.layer_planes * x.layer_blocks * unit, self.planes[r + 1] // x.layer_planes * x.layer_blocks * unit)
-                        ops = []
-                        for full, unit in ((pages, 8192), (valid, 1)):
-                            if self.rank == 0:
-                                ops += [td.P2POp(td.irecv, full[rng(r, unit)], r) for r in range(1, self.world)]
-                            else:
-                                ops.append(td.P2POp(td.isend, full[rng(self.rank, unit)], 0))
-                        for req in td.batch_isend_irecv(ops):
-                            req.wait()
-            rc = self.ctx.polygonize_sharded(self.rank, self.world, 1, flags, self.planes)
-            # an overflow on any rank repeats the run on every rank (the exchange is collective)
+        for attempt in range(max_attempts):
+            rc = self.ctx.polygonize_sharded(3, flags) if self.world > 1 else self._single(flags)
+            # an overflow on any rank repeats the run on every rank (the exchanges are collective)
             if self.ranks.max_over_ranks(1.0 if rc != 0 else 0.0) == 0.0:
+                self.last_attempts = attempt + 1
                 return self.ctx.info()
         raise capi.VxbError("sharded run: output arenas kept overflowing")
+
+    def _single(self, flags):
+        # world == 1: no peers, no communicator - the three pieces back to back
+        self.ctx.polygonize_sharded(0, flags)
+        self.ctx.polygonize_sharded(1, flags)
+        return self.ctx.polygonize_sharded(2, flags)
 
     def directory(self):
         import numpy as np
