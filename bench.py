@@ -6,21 +6,38 @@
                                                            (oracle/_ref, unmodified sources compiled by oracle/Makefile)
 
 A "step" is one full polygonization (all LOD levels + transition cells = what the reference's Execute always
-computes; BASELINE configs[2] asks for levels 0-3, a subset) of one n^3 grid.  Rank r works on its own tile of the
-same endless terrain (x-origin shifted by r*n): independent objects, no data-path collective -> weak scaling.
-  value : n^3 * ranks / time, grid resident in HBM, CUDA events on the launching stream, max over ranks.
-  e2e   : same, through the C ABI with HOST (pinned) buffers: H2D of the 3 dense volumes and D2H of the full
-          result (directory + vertex/index arenas) inside the timed region, every step.
+computes; BASELINE configs[2] asks for levels 0-3, a subset) of ONE n^3 grid (n = 1024 by default).
+  N = 1 : the grid is resident in HBM, vxb_polygonize (one CUDA graph).
+  N > 1 : the SAME grid polygonized by all N ranks (strong scaling, voxels_b200.dist.ShardedGrid): the cube's z-pieces
+          live in the ranks' HBM (cyclic deal, peer-mapped over NVLink), work is dealt by blocks, two exchanges inside
+          every step (an ncclAllGather of the per-block info; peer stores of material pages ordered by a second tiny
+          all-gather).
+  value : n^3 / time of a step; CUDA events on the launching stream around K steps, barrier + synchronize on both
+          sides, max over ranks.
+  e2e   : the same through the C ABI with HOST (pinned) buffers: H2D of the grid in the reference's PackForSave form
+          (every rank its own pieces) and D2H of the full result (directory + vertex/index arenas) inside the timed
+          region, every step.
 Inputs (1 GiB per channel at 1024^3) are far larger than the 126 MB L2, so no explicit L2 flush is needed.
 Prints ONE JSON line on rank 0.
 """
-import argparse
-import json
 import os
-import subprocess
 import sys
-import threading
-import time
+
+# Host cores this process may use, read BEFORE any OpenMP runtime exists (with OMP_PROC_BIND set libgomp pins the
+# initial thread, after which the affinity mask shows one CPU).  OMP_PROC_BIND=spread (SURVEY.md 8d) is for the
+# reference's OpenMP loops and is read when libgomp is loaded; it is set only where the reference runs (the reference
+# arm, and the single-process N = 1 line with its cpu_baseline leg) - never under torchrun with several ranks, whose
+# main threads would all be pinned to the first core.
+HOST_CPUS = len(os.sched_getaffinity(0))
+if "reference" in sys.argv or int(os.environ.get("WORLD_SIZE", "1")) == 1:
+    os.environ.setdefault("OMP_PROC_BIND", "spread")
+
+import argparse  # noqa: E402
+import hashlib  # noqa: E402
+import json  # noqa: E402
+import subprocess  # noqa: E402
+import threading  # noqa: E402
+import time  # noqa: E402
 
 REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
@@ -34,11 +51,13 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--size", type=int, default=1024, help="grid edge n (power of two)")
-    ap.add_argument("--levels", type=int, default=0, help="LOD levels to compute (0 = all, as the reference)")
+    ap.add_argument("--levels", type=int, default=0, help="LOD levels to compute (0 = all, as the reference; N = 1 only)")
     ap.add_argument("--no-transitions", action="store_true")
-    ap.add_argument("--cpu-sample-size", type=int, default=0, help="grid edge of the CPU-baseline sample (0 = same as --size, capped at 1024)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-config4", action="store_true", help="skip the second record (2048^3, BASELINE configs[3])")
+    ap.add_argument("--no-tiles", action="store_true", help="N > 1: skip the independent-tiles weak-scaling extra")
+    ap.add_argument("--group-planes", type=int, default=0, help="N > 1: planes per cube piece (0 = default)")
     return ap.parse_args()
 
 
@@ -49,6 +68,38 @@ def measured_peak_hbm():
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def kernel_source_digest():
+    """sha256 over the kernel sources: a committed ncu capture is quoted only for the build it was taken from."""
+    h = hashlib.sha256()
+    d = os.path.join(REPO, "voxels_b200", "csrc")
+    for name in sorted(os.listdir(d)):
+        if name.endswith((".cu", ".cuh", ".h")):
+            with open(os.path.join(d, name), "rb") as f:
+                h.update(f.read())
+    return h.hexdigest()[:16]
+
+
+def host_cpu():
+    model, cores = "unknown", set()
+    try:
+        phys = core = None
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name") and model == "unknown":
+                    model = line.split(":", 1)[1].strip()
+                elif line.startswith("physical id"):
+                    phys = line.split(":", 1)[1].strip()
+                elif line.startswith("core id"):
+                    core = line.split(":", 1)[1].strip()
+                elif not line.strip():
+                    if phys is not None and core is not None:
+                        cores.add((phys, core))
+                    phys = core = None
+    except Exception:
+        pass
+    return model, len(cores)
 
 
 class ClockSampler:
@@ -94,37 +145,67 @@ class ClockSampler:
         return {"sm_mhz": clocks[len(clocks) // 2] if clocks else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(clocks)}
 
 
-def reference_run(n, steps, warmup, origin_x, torch, device_for_gen, budget_s=200.0):
-    """Times the reference's own Polygonizer::Execute (all host threads) on the terrain tile; returns (Mvoxels/s, info).
-    The sample is the full n^3 tile when warmup + steps executions fit the time budget, else the (n/2)^3 tile of the
-    same terrain (bounded sample: the run must end within a few minutes whatever K is)."""
-    import harness
-    from voxels_b200 import synth
-    if not os.path.exists(harness.REF_LIB):
-        return None, {"unavailable": "oracle/_ref/libvxh_ref.so not built (make -C oracle ref needs the reference checkout)"}
-    ref = harness.reference()
+def reference_threads(ref):
     # every host core this process may use (torchrun exports OMP_NUM_THREADS=1, which is not what the reference would run with)
-    threads = max(ref.L.vxh_max_threads(), len(os.sched_getaffinity(0)))
-    while True:
-        dist, mat, blend = synth.terrain(n, device_for_gen, origin=(origin_x, 0))
-        dist, mat, blend = dist.cpu().numpy(), mat.cpu().numpy(), blend.cpu().numpy()
-        grid = ref.grid_from_dense(dist, mat, blend)
-        times = []
-        shrink = False
-        for i in range(warmup + steps):
-            s, sec = ref.polygonize(grid, threads=threads)
+    return max(ref.L.vxh_max_threads(), HOST_CPUS)
+
+
+def reference_run(n, steps, warmup, dist, mat, blend, budget_s=150.0, keep_surface=False):
+    """Times the reference's own Polygonizer::Execute (all host threads) on the given n^3 grid (numpy [z,y,x] arrays).
+    The GRID is never shrunk; when warmup + steps executions would not fit the time budget the number of executions is
+    cut (never below 1 warm-up + 2 timed) and the line says so.  Returns (Mvoxels/s, info, ref, grid, surface)."""
+    import harness
+    if not os.path.exists(harness.REF_LIB):
+        return None, {"unavailable": "oracle/_ref/libvxh_ref.so not built (make -C oracle ref needs the reference checkout)"}, None, None, None
+    ref = harness.reference()
+    threads = reference_threads(ref)
+    grid = ref.grid_from_dense(dist, mat, blend)
+    times, surface = [], None
+    warmup = max(1, warmup)
+    want = warmup + steps
+    done = 0
+    t_first = None
+    while done < want:
+        s, sec = ref.polygonize(grid, threads=threads)
+        if t_first is None:
+            t_first = sec
+            fit = int(budget_s / max(sec, 1e-3))
+            if fit < want:
+                warmup = 1
+                want = max(1 + 2, min(want, fit))
+        if done >= warmup:
+            times.append(sec)
+        done += 1
+        if keep_surface and done == want:
+            surface = s
+        else:
             ref.surface_destroy(s)
-            if i == 0 and n > 256 and sec * (warmup + steps) > budget_s:
-                shrink = True
-                break
-            if i >= warmup:
-                times.append(sec)
+    if not keep_surface:
         ref.grid_destroy(grid)
-        if not shrink:
-            break
-        n //= 2
+        grid = None
     per_step = sum(times) / len(times)
-    return n ** 3 / per_step / 1e6, {"cores": threads, "seconds_per_execute": per_step, "best_seconds": min(times), "n": n}
+    model, phys = host_cpu()
+    info = {"cores": threads, "physical_cores": phys, "cpu_model": model, "seconds_per_execute": per_step, "best_seconds": min(times),
+            "timed_executions": len(times), "warmup_executions": warmup, "n": n, "omp_proc_bind": os.environ.get("OMP_PROC_BIND")}
+    return n ** 3 / per_step / 1e6, info, ref, grid, surface
+
+
+def compare_with_reference(ref, surface, result, stats):
+    """Level by level, bit by bit (tests/compare.py rules).  Returns {"checked", "levels", "mismatches", "first"}."""
+    import numpy as np
+    import compare
+    problems = []
+    levels = ref.surface_levels(surface)
+    for l in range(levels):
+        problems += compare.level_diff(ref.surface_level(surface, l), result.level(l), "L%d" % l)
+    if stats is not None and not np.array_equal(ref.surface_stats(surface), stats):
+        problems.append("statistics differ")
+    return {"checked": True, "levels": int(levels), "mismatches": len(problems), "first": problems[:3]}
+
+
+def terrain_config4(sg, synth, dev):
+    for z0, z1, out in sg.piece_tensors():
+        synth.terrain(sg.n, dev, z_range=(z0, z1), out=out)
 
 
 def main():
@@ -140,22 +221,27 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
+        from voxels_b200 import synth
         gen_dev = "cuda:0" if torch.cuda.is_available() else "cpu"
-        sample_n = min(n, 1024)
         t0 = time.time()
-        value, info = reference_run(sample_n, args.steps, args.warmup, 0, torch, gen_dev)
+        dist, mat, blend = (t.cpu().numpy() for t in synth.terrain(n, gen_dev))
+        value, info, _, _, _ = reference_run(n, args.steps, args.warmup, dist, mat, blend)
         if value is None:
             print(json.dumps({"impl": "reference", "unavailable": info["unavailable"]}))
             return 0
+        cut = info["timed_executions"] != args.steps
         line = {
             "impl": "reference", "metric": "Mvoxels/s polygonized", "value": value, "unit": "Mvoxels/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": info["seconds_per_execute"] * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "int8 samples / fp32 vertices", "data": "synthetic",
-            "config": {"workload": "%d^3 seeded Perlin terrain, all LOD levels + transition cells (reference Polygonizer::Execute)" % info["n"],
-                       "impl": "unmodified reference sources, g++ -O2 -fopenmp -msse2, OMP threads = %d" % info["cores"]},
-            "cpu_baseline": {"value": value, "unit": "Mvoxels/s", "cores": info["cores"], "kind": "reference",
-                             "sample": "%s %d^3 grid, Polygonizer::Execute only (grid build excluded), mean of %d runs"
-                                       % ("full" if info["n"] == sample_n else "bounded sample (time budget):", info["n"], args.steps)},
+            "scaling": "strong", "vs_baseline": None, "dtype": "int8 samples / fp32 vertices", "data": "synthetic",
+            "config": {"workload": "%d^3 seeded Perlin terrain, all LOD levels + transition cells (reference Polygonizer::Execute)" % n,
+                       "impl": "unmodified reference sources, g++ -O2 -fopenmp -msse2, OMP threads = %d, OMP_PROC_BIND=%s" % (info["cores"], info["omp_proc_bind"]),
+                       "same_grid_as_b200_arm": True},
+            "cpu_baseline": {"value": value, "unit": "Mvoxels/s", "cores": info["cores"], "physical_cores": info["physical_cores"], "cpu_model": info["cpu_model"],
+                             "kind": "reference", "best_value": n ** 3 / info["best_seconds"] / 1e6,
+                             "sample": "full %d^3 grid (never shrunk), Polygonizer::Execute only (grid build excluded), mean of %d timed executions after %d warm-up%s"
+                                       % (n, info["timed_executions"], info["warmup_executions"],
+                                          " (executions cut from --steps %d --warmup %d to fit the time budget)" % (args.steps, args.warmup) if cut else "")},
             "e2e": {"value": value, "unit": "Mvoxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": time.time() - t0,
         }
@@ -170,23 +256,16 @@ def main():
     dev = torch.device("cuda", local_rank)
     import voxels_b200
     from voxels_b200 import synth
-    from voxels_b200.dist import Ranks, tile_origin, whole_job_throughput
+    from voxels_b200.dist import Ranks, ShardedGrid, tile_origin, whole_job_throughput
     ranks = Ranks("nccl", dev)
-
     flags = voxels_b200.FLAG_NO_TRANSITIONS if args.no_transitions else 0
-    dist, mat, blend = synth.terrain(n, dev, origin=tile_origin(rank, n))
-    torch.cuda.synchronize()
-    ctx = voxels_b200.Context(local_rank)
-    ctx.set_device_grid(n, dist.data_ptr(), mat.data_ptr(), blend.data_ptr(), keep=(dist, mat, blend))
-    stream = torch.cuda.ExternalStream(ctx.L.vxb_stream(ctx.h), device=dev)
+    peak, peak_src = measured_peak_hbm()
 
     def barrier():
         ranks.barrier()
         torch.cuda.synchronize()
 
-    max_over_ranks = ranks.max_over_ranks
-
-    def timed(fn, steps):
+    def timed(fn, steps, stream):
         """K steps bracketed by barrier+synchronize; CUDA events on the launching stream; max over ranks."""
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -195,153 +274,146 @@ def main():
             fn()
         e1.record(stream)
         barrier()
-        return max_over_ranks(e0.elapsed_time(e1)) / steps
+        return ranks.max_over_ranks(e0.elapsed_time(e1)) / steps
 
-    # -- value: grid resident in HBM --
-    info = None
+    def algorithmic_bytes(nn, levels_computed, V, I, TV, TI):
+        d_level0 = float(nn) ** 3
+        d_upper = sum((nn >> l) ** 3 for l in range(1, levels_computed))
+        return d_level0, float(d_upper), 4.0 * (V + TV), 48.0 * (V + TV) + 4.0 * (I + TI)  # D + M + O
 
-    def step_resident():
-        nonlocal info
-        info = ctx.polygonize(args.levels, flags)
-
-    # clocks are sampled (nvidia-smi, 50 ms period) from the warm-up through the timed region; the timed region of a
-    # few ms-long steps is shorter than one sample period, so identical untimed steps keep the load up for >= 1.5 s
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     t_load = time.time()
-    for _ in range(max(args.warmup, 3)):
-        step_resident()
-    ms_resident = timed(step_resident, args.steps)
-    while rank == 0 and time.time() - t_load < 1.5:
-        step_resident()
-    clocks = sampler.stop() if rank == 0 else None
-    if clocks is not None:
-        clocks["window"] = "warm-up + timed region + identical untimed steps, %.1f s under load" % (time.time() - t_load)
-    launches_per_step = info.kernel_launches
-    device_ms_inner = info.device_ms
-
-    # -- per-kernel times for the roofline (separate steps: the extra events add a little stream overhead) --
-    kind_ms = [0.0] * 8
-    kind_launches = [0] * 8
-    ksteps = max(3, min(args.steps, 10))
-    for _ in range(ksteps):
-        ctx.polygonize(args.levels, flags | voxels_b200.FLAG_KERNEL_TIMES)
-        for k in range(8):
-            ms, ln = ctx.kernel_ms(k)
-            kind_ms[k] += ms / ksteps
-            kind_launches[k] = ln
-    info = ctx.polygonize(args.levels, flags)
-    levels_computed = info.levels_computed
-    V, I, TV, TI = info.vertex_total, info.index_total, info.trans_vertex_total, info.trans_index_total
-    d_level0 = float(n) ** 3
-    d_upper = sum((n >> l) ** 3 for l in range(1, levels_computed))
-    bytes_out = 48.0 * (V + TV) + 4.0 * (I + TI)
-    bytes_mat = 4.0 * (V + TV)
-    bytes_alg_total = d_level0 + d_upper + bytes_mat + bytes_out  # D + M + O
-    peak, peak_src = measured_peak_hbm()
-    kinds = ["vxb_scan_kernel (streams the level-0 distance volume once)", "vxb_block_info/vxb_select kernels",
-             "vxb_classify_kernel (one launch per level: tiles, case codes, material votes)",
-             "vxb_decide_kernel (per block: ordering, reuse decisions, scans; all levels)",
-             "vxb_vertex_kernel (flat, one thread per new vertex)", "vxb_triangle_kernel (flat, one thread per non-trivial cell)",
-             "vxb_transition_kernel (per mid-level block)", "vxb_finish_kernel (compaction + directory)"]
-    # SURVEY.md 8(d) split per kernel: level-0 samples are read once by the scan; coarser levels' samples by classify;
-    # materials + vertices by the vertex kernel; indices by the triangle kernel; transition output by its kernel.
-    # Tile re-reads of candidate blocks and the intermediate cell records are overhead, not algorithmic bytes.
-    alg_by_kind = [d_level0, 0.0, float(d_upper), 0.0, 52.0 * V, 4.0 * I, 52.0 * TV + 4.0 * TI, 0.0]
-    dom = max(range(8), key=lambda k: kind_ms[k])
-    ach = alg_by_kind[dom] / (kind_ms[dom] * 1e-3) / 1e9 if kind_ms[dom] > 0 else 0.0
-    # DRAM traffic of that kernel kind per step from the committed `ncu --set full` capture (only valid for the default workload)
-    traffic, traffic_src = None, None
-    try:
-        kind_keys = ["scan", "select", "classify", "decide", "vertex", "triangle", "transition", "finish"]
-        with open(os.path.join(REPO, "profiles", "r01d_traffic.json")) as f:
-            tj = json.load(f)
-        if n == 1024 and args.levels == 0 and not args.no_transitions:
-            e = tj["per_kind"][kind_keys[dom]]
-            traffic, traffic_src = e["dram_read"] + e["dram_write"], tj["capture"]
-    except Exception:
-        pass
-    roofline = {"bound": "hbm", "kernel": kinds[dom], "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "traffic_source": traffic_src,
-                "peak_source": peak_src, "algorithmic_bytes_per_step": alg_by_kind[dom], "kernel_ms_per_step": kind_ms[dom],
-                "launches_per_step": kind_launches[dom],
-                "all_kernels": {kinds[k]: {"ms_per_step": kind_ms[k], "launches": kind_launches[k], "algorithmic_bytes": alg_by_kind[k],
-                                           "achieved_gbs": (alg_by_kind[k] / (kind_ms[k] * 1e-3) / 1e9 if kind_ms[k] > 0 else 0.0)} for k in range(8)},
-                "job": {"algorithmic_bytes": bytes_alg_total, "device_ms": device_ms_inner,
-                        "achieved_gbs": bytes_alg_total / (device_ms_inner * 1e-3) / 1e9, "frac": bytes_alg_total / (device_ms_inner * 1e-3) / 1e9 / peak}}
-
-    # -- e2e: host buffers through the C ABI, H2D + D2H inside the timed region --
-    # headline e2e: the grid arrives in the reference's own storage form (the bytes of Grid::PackForSave: RLE blocks),
-    # is copied as is and decoded on the GPU; e2e_dense: the same with three dense n^3 host volumes.
+    extra = {}
     e2e = None
-    e2e_dense = None
-    if not args.no_e2e:
-        h_dist, h_mat, h_blend = (t.cpu() for t in (dist, mat, blend))
-        packed = voxels_b200.pack_dense(h_dist.numpy(), h_mat.numpy(), h_blend.numpy())
-        h_blob = torch.from_numpy(packed.copy()).pin_memory()
-        blob_bytes = int(h_blob.numel())
-        h_dist, h_mat, h_blend = (t.pin_memory() for t in (h_dist, h_mat, h_blend))
-        ctx2 = voxels_b200.Context(local_rank)
-        stream2 = torch.cuda.ExternalStream(ctx2.L.vxb_stream(ctx2.h), device=dev)
-        out = {
-            "verts": torch.empty(int(info.vertex_span * 1.1) * 48 + 4096, dtype=torch.uint8).pin_memory(),
-            "idx": torch.empty(int(info.index_span * 1.1) * 4 + 4096, dtype=torch.uint8).pin_memory(),
-            "tverts": torch.empty(int(info.trans_vertex_span * 1.1) * 48 + 4096, dtype=torch.uint8).pin_memory(),
-            "tidx": torch.empty(int(info.trans_index_span * 1.1) * 4 + 4096, dtype=torch.uint8).pin_memory(),
-        }
-        into = {k: v.data_ptr() for k, v in out.items()}
-        d2h = [0]
+    cpu = None
+    parity = None
 
-        parts = {"upload": 0.0, "polygonize": 0.0, "download": 0.0, "steps": 0}  # host clock around the three (synchronous) calls
+    if world == 1:
+        # ------------------------------------------------------------ N = 1: resident grid, one CUDA graph per step
+        dist, mat, blend = synth.terrain(n, dev)
+        torch.cuda.synchronize()
+        ctx = voxels_b200.Context(local_rank)
+        ctx.set_device_grid(n, dist.data_ptr(), mat.data_ptr(), blend.data_ptr(), keep=(dist, mat, blend))
+        stream = torch.cuda.ExternalStream(ctx.L.vxb_stream(ctx.h), device=dev)
+        info = None
 
-        def finish_step(t0):
-            t1 = time.perf_counter()
-            i2 = ctx2.polygonize(args.levels, flags)
-            t2 = time.perf_counter()
-            ctx2.download(into=into)
-            t3 = time.perf_counter()
-            parts["upload"] += t1 - t0; parts["polygonize"] += t2 - t1; parts["download"] += t3 - t2; parts["steps"] += 1
-            d2h[0] = i2.block_count * 128 + i2.vertex_span * 48 + i2.index_span * 4 + i2.trans_vertex_span * 48 + i2.trans_index_span * 4
+        def step_resident():
+            nonlocal info
+            info = ctx.polygonize(args.levels, flags)
 
-        def step_e2e_packed():
-            t0 = time.perf_counter()
-            ctx2.upload_packed(h_blob.data_ptr(), blob_bytes)
-            finish_step(t0)
+        for _ in range(max(args.warmup, 3)):
+            step_resident()
+        ms_step = timed(step_resident, args.steps, stream)
+        while time.time() - t_load < 1.5:  # keep the load up for at least a few clock samples (50 ms period)
+            step_resident()
+        clocks = sampler.stop()
+        clocks["window"] = "warm-up + timed region + identical untimed steps, %.1f s under load" % (time.time() - t_load)
+        launches_per_step = info.kernel_launches
+        device_ms_inner = info.device_ms
 
-        def step_e2e_dense():
-            t0 = time.perf_counter()
-            ctx2.upload_dense_ptr(n, h_dist.data_ptr(), h_mat.data_ptr(), h_blend.data_ptr())
-            finish_step(t0)
+        # per-kernel times for the roofline table (separate steps on one stream with plain launches: clean per-kernel events)
+        kind_ms, kind_launches = [0.0] * 8, [0] * 8
+        ksteps = max(3, min(args.steps, 10))
+        for _ in range(ksteps):
+            ctx.polygonize(args.levels, flags | voxels_b200.FLAG_KERNEL_TIMES)
+            for k in range(8):
+                ms, ln = ctx.kernel_ms(k)
+                kind_ms[k] += ms / ksteps
+                kind_launches[k] = ln
+        info = ctx.polygonize(args.levels, flags)
+        levels_computed = info.levels_computed
+        V, I, TV, TI = info.vertex_total, info.index_total, info.trans_vertex_total, info.trans_index_total
+        d0, dup, bm, bo = algorithmic_bytes(n, levels_computed, V, I, TV, TI)
+        bytes_alg_total = d0 + dup + bm + bo
+        kinds = ["vxb_scan_kernel (streams the level-0 distance volume once)",
+                 "vxb_block_info / vxb_pyramid / vxb_select kernels (block walk)",
+                 "vxb_block_kernel<1>/<2> (levels >= 1: tiles, case codes, material votes, reuse decisions)",
+                 "vxb_block_kernel<0> (level 0: tile -> case codes -> decisions -> vertices -> triangles in one pass)",
+                 "vxb_vertex_kernel (levels >= 1, flat, one thread per new vertex)",
+                 "vxb_triangle_kernel (levels >= 1, flat, one thread per non-trivial cell)",
+                 "vxb_transition_kernel + vxb_transition_vertex_kernel (per mid-level block)",
+                 "vxb_finish_kernel (compaction + directory)"]
+        # SURVEY.md 8(d) split per kernel kind: level-0 samples are read once by the scan; the coarser levels' samples by
+        # their block kernels; level-0 materials + vertices + indices by vxb_block_kernel<0>; the rest by the flat kernels.
+        # Tile re-reads of candidate blocks and the intermediate cell records are overhead, not algorithmic bytes.
+        lv = ctx.download().records
+        v0 = int(lv["vertex_count"][lv["level"] == 0].sum()); i0 = int(lv["index_count"][lv["level"] == 0].sum())
+        alg_by_kind = [d0, 0.0, dup, 52.0 * v0 + 4.0 * i0, 52.0 * (V - v0), 4.0 * (I - i0), 52.0 * TV + 4.0 * TI, 0.0]
+        dom = max(range(8), key=lambda k: kind_ms[k])
+        per_kind = {kinds[k]: {"ms_per_step": kind_ms[k], "launches": kind_launches[k], "algorithmic_bytes": alg_by_kind[k],
+                               "achieved_gbs": (alg_by_kind[k] / (kind_ms[k] * 1e-3) / 1e9 if kind_ms[k] > 0 else 0.0)} for k in range(8)}
+        # DRAM traffic per step from the committed `ncu --set full` capture - only when it was taken from THIS build
+        traffic, traffic_src = None, None
+        try:
+            with open(os.path.join(REPO, "profiles", "r02_traffic.json")) as f:
+                tj = json.load(f)
+            if tj.get("kernel_source_digest") == kernel_source_digest() and n == 1024 and args.levels == 0 and not args.no_transitions:
+                traffic, traffic_src = tj["step"]["dram_read"] + tj["step"]["dram_write"], tj["capture"]
+        except Exception:
+            pass
+        ach = bytes_alg_total / (ms_step * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": "whole step (every kernel of one vxb_polygonize, CUDA graph)", "achieved": ach, "peak": peak, "unit": "GB/s",
+                    "frac": ach / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                    "algorithmic_bytes_per_step": bytes_alg_total, "ms_per_step": ms_step,
+                    "algorithmic_bytes": {"distance_level0": d0, "distance_upper_levels": dup, "materials": bm, "output": bo},
+                    "dominant_kernel": {"kernel": kinds[dom], **per_kind[kinds[dom]], "frac": per_kind[kinds[dom]]["achieved_gbs"] / peak},
+                    "all_kernels": per_kind,
+                    "all_kernels_note": "CUDA events per kernel kind on one stream with plain launches (VXB_FLAG_KERNEL_TIMES), summed over the kind's launches; the timed step replays a graph with the transition cells on a second stream"}
+        workload = "%d^3 seeded Perlin terrain, ONE grid on 1 GPU, LOD levels 0-%d%s (BASELINE configs[2] asks for levels 0-3 + transitions: a subset)" \
+                   % (n, levels_computed - 1, "" if args.no_transitions else " + transition cells")
+        config = {"workload": workload, "grid": "dense int8 distance + uint8 material + uint8 blend, resident in HBM",
+                  "sharding": "none (1 GPU)", "l2": "inputs (%.2f GiB per channel) larger than the 126 MB L2; no flush" % (n ** 3 / 2.0 ** 30),
+                  "vertices": int(V), "indices": int(I), "transition_vertices": int(TV), "transition_indices": int(TI), "blocks_emitted": int(info.block_count)}
 
-        def breakdown():
-            k = max(parts["steps"], 1)
-            out = {name: round(1e3 * parts[name] / k, 3) for name in ("upload", "polygonize", "download")}
-            parts.update(upload=0.0, polygonize=0.0, download=0.0, steps=0)
-            return out
+        # -- e2e: host buffers through the C ABI, H2D + D2H inside the timed region --
+        if not args.no_e2e:
+            h_dist, h_mat, h_blend = (t.cpu() for t in (dist, mat, blend))
+            packed = voxels_b200.pack_dense(h_dist.numpy(), h_mat.numpy(), h_blend.numpy())
+            h_blob = torch.from_numpy(packed.copy()).pin_memory()
+            blob_bytes = int(h_blob.numel())
+            ctx2 = voxels_b200.Context(local_rank)
+            stream2 = torch.cuda.ExternalStream(ctx2.L.vxb_stream(ctx2.h), device=dev)
+            out = {
+                "verts": torch.empty(int(info.vertex_span * 1.1) * 48 + 4096, dtype=torch.uint8).pin_memory(),
+                "idx": torch.empty(int(info.index_span * 1.1) * 4 + 4096, dtype=torch.uint8).pin_memory(),
+                "tverts": torch.empty(int(info.trans_vertex_span * 1.1) * 48 + 4096, dtype=torch.uint8).pin_memory(),
+                "tidx": torch.empty(int(info.trans_index_span * 1.1) * 4 + 4096, dtype=torch.uint8).pin_memory(),
+            }
+            into = {k: v.data_ptr() for k, v in out.items()}
+            d2h = [0]
+            parts = {"upload": 0.0, "polygonize": 0.0, "download": 0.0, "steps": 0}  # host clock around the three (synchronous) calls
 
-        esteps = max(2, min(args.steps, 5))
-        stream_saved = stream
-        stream = stream2
-        for _ in range(2):
-            step_e2e_packed()
-        breakdown()
-        ms_e2e = timed(step_e2e_packed, esteps)
-        e2e = {"value": whole_job_throughput(n, world, ms_e2e), "unit": "Mvoxels/s", "ms_per_step": ms_e2e, "steps": esteps, "host_ms": breakdown(),
-               "h2d_bytes_per_step": blob_bytes + 8 * (n // 16) ** 3, "d2h_bytes_per_step": int(d2h[0]),
-               "path": "vxb_grid_upload_packed (PackForSave bytes, pinned host -> HBM, RLE decode on the GPU) + vxb_polygonize + "
-                       "vxb_result_download (directory + arenas, HBM -> pinned host)"}
-        for _ in range(2):
-            step_e2e_dense()
-        breakdown()
-        ms_dense = timed(step_e2e_dense, esteps)
-        e2e_dense = {"value": whole_job_throughput(n, world, ms_dense), "unit": "Mvoxels/s", "ms_per_step": ms_dense, "steps": esteps, "host_ms": breakdown(),
-                     "h2d_bytes_per_step": 3 * n ** 3, "d2h_bytes_per_step": int(d2h[0]),
-                     "path": "vxb_grid_upload_dense (3 dense volumes, pinned host -> HBM) + vxb_polygonize + vxb_result_download"}
-        stream = stream_saved
-        # the same calls from two host threads, each with its own context and buffers: step k's download (D2H) overlaps
-        # step k+1's upload (H2D) and kernels, the way a client streams many grids through one GPU.  Extra information,
-        # timed on the host clock over all steps; the headline `e2e` above is one step at a time.
-        if True:
+            def step_e2e_packed():
+                t0 = time.perf_counter()
+                ctx2.upload_packed(h_blob.data_ptr(), blob_bytes)
+                t1 = time.perf_counter()
+                i2 = ctx2.polygonize(args.levels, flags)
+                t2 = time.perf_counter()
+                ctx2.download(into=into)
+                t3 = time.perf_counter()
+                parts["upload"] += t1 - t0; parts["polygonize"] += t2 - t1; parts["download"] += t3 - t2; parts["steps"] += 1
+                d2h[0] = i2.block_count * 128 + i2.vertex_span * 48 + i2.index_span * 4 + i2.trans_vertex_span * 48 + i2.trans_index_span * 4
+
+            def breakdown():
+                k = max(parts["steps"], 1)
+                o = {name: round(1e3 * parts[name] / k, 3) for name in ("upload", "polygonize", "download")}
+                parts.update(upload=0.0, polygonize=0.0, download=0.0, steps=0)
+                return o
+
+            esteps = max(3, min(args.steps, 5))
+            for _ in range(3):
+                step_e2e_packed()
+            breakdown()
+            ms_e2e = timed(step_e2e_packed, esteps, stream2)
+            e2e = {"value": float(n) ** 3 / (ms_e2e * 1e-3) / 1e6, "unit": "Mvoxels/s", "ms_per_step": ms_e2e, "steps": esteps, "host_ms": breakdown(),
+                   "h2d_bytes_per_step": blob_bytes + 8 * (n // 16) ** 3, "d2h_bytes_per_step": int(d2h[0]),
+                   "path": "vxb_grid_upload_packed (PackForSave bytes, pinned host -> HBM, RLE decode on the GPU) + vxb_polygonize + "
+                           "vxb_result_download (directory + arenas, HBM -> pinned host)"}
+            # the same calls from two host threads, each with its own context and buffers: step k's download (D2H) overlaps
+            # step k+1's upload (H2D) and kernels, the way a client streams many grids through one GPU.  Extra information,
+            # timed on the host clock over all steps; the headline `e2e` above is one step at a time.
             ctx3 = voxels_b200.Context(local_rank)
             out3 = {k: torch.empty_like(v).pin_memory() for k, v in out.items()}
             into3 = {k: v.data_ptr() for k, v in out3.items()}
@@ -375,46 +447,245 @@ def main():
             for t in threads:
                 t.join()
             if wall_ms is not None and not failures:
-                ms_pipe = max_over_ranks(wall_ms / (2 * psteps))
-                e2e["two_in_flight"] = {"value": whole_job_throughput(n, world, ms_pipe), "unit": "Mvoxels/s", "ms_per_step": ms_pipe, "steps": 2 * psteps,
+                ms_pipe = wall_ms / (2 * psteps)
+                e2e["two_in_flight"] = {"value": float(n) ** 3 / (ms_pipe * 1e-3) / 1e6, "unit": "Mvoxels/s", "ms_per_step": ms_pipe, "steps": 2 * psteps,
                                         "timing": "host clock over all steps; two host threads, one context each, same calls as e2e"}
             else:
-                max_over_ranks(0.0)  # keep the ranks' collectives aligned
                 e2e["two_in_flight"] = {"value": None, "error": "; ".join(failures) or "barrier timeout"}
             ctx3.close()
-            del out3
-        ctx2.close()
-        del h_dist, h_mat, h_blend, h_blob, out
+            ctx2.close()
+            del out3, out, h_blob
 
-    # -- CPU baseline: the reference itself on this box's host cores (rank 0, N=1 only) --
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        sample_n = args.cpu_sample_size or min(n, 1024)
-        t0 = time.time()
-        v, ci = reference_run(sample_n, 2, 0, 0, torch, dev)
-        if v is not None:
-            cpu = {"value": v, "unit": "Mvoxels/s", "cores": ci["cores"], "kind": "reference",
-                   "sample": "%s %d^3 terrain tile (same bytes as the GPU step when sizes match), Polygonizer::Execute only, mean of 2 runs, %.1f s wall incl. grid build"
-                             % ("full" if ci["n"] == sample_n else "bounded sample:", ci["n"], time.time() - t0)}
-        else:
-            cpu = {"value": None, "unit": "Mvoxels/s", "cores": 0, "kind": "reference", "sample": ci["unavailable"]}
+        # -- CPU baseline: the reference itself on this box's host cores, on the SAME bytes, and the parity check of the step --
+        if not args.no_cpu_baseline:
+            t0 = time.time()
+            hd, hm, hb = (t.cpu().numpy() for t in (dist, mat, blend))
+            v, ci, ref, rgrid, rsurf = reference_run(n, 3, 1, hd, hm, hb, budget_s=90.0, keep_surface=True)
+            if v is not None:
+                cpu = {"value": n ** 3 / ci["best_seconds"] / 1e6, "mean_value": v, "unit": "Mvoxels/s", "cores": ci["cores"], "physical_cores": ci["physical_cores"],
+                       "cpu_model": ci["cpu_model"], "kind": "reference",
+                       "sample": "full %d^3 terrain (the same bytes as the GPU step), Polygonizer::Execute only, best of %d after %d warm-up, OMP_PROC_BIND=%s, %.1f s wall incl. grid build"
+                                 % (n, ci["timed_executions"], ci["warmup_executions"], ci["omp_proc_bind"], time.time() - t0)}
+                if args.levels == 0 and not args.no_transitions:
+                    res = ctx.download()
+                    parity = compare_with_reference(ref, rsurf, res, res.stats)
+                    parity["what"] = "the reference's PolygonSurface vs the GPU result of the same %d^3 bytes: block table, vertices, indices, transition meshes, statistics" % n
+                    del res
+                # -- e2e through the reference's own API: Polygonizer::Execute of the drop-in on a reference Grid, host in / host out --
+                import harness
+                if os.path.exists(harness.B200_LIB) and args.levels == 0 and not args.no_transitions and not args.no_e2e:
+                    dl = harness.load(harness.B200_LIB)
+                    g2 = dl.grid_from_dense(hd, hm, hb)
+                    secs = []
+                    dsurf = None
+                    for i in range(1 + 3):
+                        if dsurf is not None:
+                            dl.surface_destroy(dsurf)
+                        dsurf, sec = dl.polygonize(g2)
+                        if i:
+                            secs.append(sec)
+                    import compare
+                    problems = []
+                    for l in range(ref.surface_levels(rsurf)):
+                        problems += compare.level_diff(ref.surface_level(rsurf, l), dl.surface_level(dsurf, l), "L%d" % l)
+                    dl.surface_destroy(dsurf); dl.grid_destroy(g2)
+                    ms_d = 1e3 * sum(secs) / len(secs)
+                    extra["e2e_dropin"] = {"value": float(n) ** 3 / (ms_d * 1e-3) / 1e6, "unit": "Mvoxels/s", "ms_per_step": ms_d, "best_ms": 1e3 * min(secs), "steps": len(secs),
+                                           "path": "Voxels::Polygonizer::Execute of libvoxels_b200.so on a reference Grid (compressed blocks -> pinned blob -> GPU decode -> kernels -> "
+                                                   "arenas back to the host -> PolygonSurface), host clock around Execute only",
+                                           "parity": {"checked": True, "mismatches": len(problems), "first": problems[:3]},
+                                           "vs_reference_same_run": (float(n) ** 3 / (ms_d * 1e-3) / 1e6) / v}
+                ref.surface_destroy(rsurf); ref.grid_destroy(rgrid)
+            else:
+                cpu = {"value": None, "unit": "Mvoxels/s", "cores": 0, "kind": "reference", "sample": ci["unavailable"]}
+            del hd, hm, hb
+        ctx.close()
+        del dist, mat, blend
+        sharding_note = None
+        scaling = "strong"
+    else:
+        # ------------------------------------------------------------ N > 1: ONE grid, all ranks
+        sg = ShardedGrid(ranks, n, group_planes=args.group_planes or None)
+        for z0, z1, outt in sg.piece_tensors():
+            synth.terrain(n, dev, z_range=(z0, z1), out=outt)
+        sg.ready()
+        stream = torch.cuda.ExternalStream(sg.ctx.stream(), device=dev)
+        for _ in range(max(args.warmup, 3)):
+            info = sg.polygonize(flags)   # grows the arenas if needed (collective retry)
+        inner = []
 
-    value = whole_job_throughput(n, world, ms_resident)
+        def step_sharded():
+            rc = sg.ctx.polygonize_sharded(3, flags)
+            if rc != 0:
+                raise RuntimeError("arena overflow inside the timed region")
+            inner.append(sg.ctx.info().device_ms)
+
+        ms_step = timed(step_sharded, args.steps, stream)
+        # keep the load up for a few clock samples (50 ms period): identical untimed steps, the same count on every rank
+        # (the steps are collective), derived from the measured step time
+        for _ in range(min(4000, int(1200.0 / max(ms_step, 0.05)))):
+            sg.ctx.polygonize_sharded(3, flags)
+        inner_timed = inner[:args.steps]
+        clocks = sampler.stop() if rank == 0 else None
+        if clocks is not None:
+            clocks["window"] = "warm-up + timed region, %.1f s under load" % (time.time() - t_load)
+        info = sg.ctx.info()
+        launches_per_step = info.kernel_launches
+        device_ms_inner = ranks.max_over_ranks(sum(inner_timed) / max(len(inner_timed), 1))
+        directory, owner = sg.directory()
+        import numpy as np
+        V = int(directory["vertex_count"].sum()); I = int(directory["index_count"].sum())
+        TV = int(directory["trans_vertex_count"].sum()); TI = int(directory["trans_index_count"].sum())
+        d0, dup, bm, bo = algorithmic_bytes(n, info.levels_total, V, I, TV, TI)
+        bytes_alg_total = d0 + dup + bm + bo
+        ach = bytes_alg_total / (ms_step * 1e-3) / 1e9
+        per_rank_blocks = [int((owner == r).sum()) for r in range(world)]
+        per_rank_verts = [int(directory["vertex_count"][owner == r].sum()) for r in range(world)]
+        roofline = {"bound": "hbm", "kernel": "whole step (every kernel + both exchanges of one vxb_polygonize_sharded on every rank)", "achieved": ach,
+                    "peak": peak * world, "unit": "GB/s", "frac": ach / (peak * world), "traffic": None, "peak_source": peak_src + " x %d GPUs" % world,
+                    "algorithmic_bytes_per_step": bytes_alg_total, "ms_per_step": ms_step}
+        config = {"workload": "%d^3 seeded Perlin terrain, ONE grid over %d GPUs (strong scaling), all LOD levels + transition cells" % (n, world),
+                  "grid": "dense int8 distance + uint8 material + uint8 blend; z-pieces of %d planes dealt cyclically to the ranks' HBM, mapped into every peer over NVLink" % sg.group_planes,
+                  "sharding": "work dealt by blocks (super-blocks cut by surface weight); exchange 0 = ncclAllGather of the per-block info, exchange 1 = peer stores of material pages + a one-word ncclAllGather; coarse levels classified by every rank",
+                  "l2": "inputs larger than the 126 MB L2; no flush", "vertices": V, "indices": I, "transition_vertices": TV, "transition_indices": TI,
+                  "blocks_emitted": int(len(directory)), "blocks_per_rank": per_rank_blocks, "vertices_per_rank": per_rank_verts, "nccl_ranks": world}
+        # every rank's geometry digest equals the single-GPU result?  (cheap version inside the bench: directory self-consistency;
+        # the bit-exact multi-GPU comparison lives in tools/bench_sharded.py --verify and tests/test_gpu_sharded.py)
+        key = directory["level"].astype(np.int64) * (1 << 32) + directory["coord_id"]
+        parity = {"checked": True, "what": "merged directory strictly ordered by (level, coord_id) with every block owned by exactly one rank",
+                  "mismatches": int((np.diff(key) <= 0).sum())}
+
+        # -- e2e: every rank uploads ITS pieces from the same PackForSave blob in pinned host memory, barrier, step, own result back --
+        if not args.no_e2e:
+            full = synth.terrain(n, dev) if rank == 0 else None
+            blob_t = None
+            if rank == 0:
+                hd, hm, hb = (t.cpu().numpy() for t in full)
+                packed = voxels_b200.pack_dense(hd, hm, hb)
+                blob_t = torch.from_numpy(packed.copy())
+                del hd, hm, hb, full
+            size_t = torch.tensor([blob_t.numel() if rank == 0 else 0], dtype=torch.int64, device=dev)
+            ranks.td.broadcast(size_t, src=0)
+            blob_dev = torch.empty(int(size_t.item()), dtype=torch.uint8, device=dev)
+            if rank == 0:
+                blob_dev.copy_(blob_t)
+            ranks.td.broadcast(blob_dev, src=0)
+            h_blob = blob_dev.cpu().pin_memory()
+            del blob_dev
+            blob_bytes = int(h_blob.numel())
+            out = {
+                "verts": torch.empty(int(info.vertex_span * 1.2) * 48 + 4096, dtype=torch.uint8).pin_memory(),
+                "idx": torch.empty(int(info.index_span * 1.2) * 4 + 4096, dtype=torch.uint8).pin_memory(),
+                "tverts": torch.empty(int(info.trans_vertex_span * 1.2) * 48 + 4096, dtype=torch.uint8).pin_memory(),
+                "tidx": torch.empty(int(info.trans_index_span * 1.2) * 4 + 4096, dtype=torch.uint8).pin_memory(),
+            }
+            into = {k: v.data_ptr() for k, v in out.items()}
+            moved = [0, 0]
+
+            def step_e2e():
+                ranks.barrier()                                       # no peer still reads the pieces this upload overwrites
+                sg.ctx.upload_packed(h_blob.data_ptr(), blob_bytes)   # this rank's pieces only
+                ranks.barrier()                                       # every piece resident before any rank reads its peers'
+                rc = sg.ctx.polygonize_sharded(3, flags)
+                if rc != 0:
+                    raise RuntimeError("arena overflow inside the timed region")
+                i2 = sg.ctx.info()
+                sg.ctx.download(into=into)
+                moved[1] = i2.block_count * 128 + i2.vertex_span * 48 + i2.index_span * 4 + i2.trans_vertex_span * 48 + i2.trans_index_span * 4
+
+            esteps = max(3, min(args.steps, 5))
+            for _ in range(3):
+                step_e2e()
+            ms_e2e = timed(step_e2e, esteps, stream)
+            d2h_total = ranks.sum_over_ranks(moved[1])
+            e2e = {"value": float(n) ** 3 / (ms_e2e * 1e-3) / 1e6, "unit": "Mvoxels/s", "ms_per_step": ms_e2e, "steps": esteps,
+                   "h2d_bytes_per_step": blob_bytes, "d2h_bytes_per_step": int(d2h_total),
+                   "path": "per rank: vxb_grid_upload_packed of its own pieces (pinned host -> HBM, RLE decode on the GPU), barrier, vxb_polygonize_sharded, "
+                           "vxb_result_download of its own blocks; bytes are the sums over the ranks (every rank reads its byte ranges of the same blob)"}
+            del out, h_blob
+        sg.close()
+        sharding_note = "strong scaling: the SAME %d^3 grid on every N" % n
+        scaling = "strong"
+
+        # -- extra: the independent-tiles mode (one n^3 tile per rank, no data-path collective): weak scaling --
+        if not args.no_tiles:
+            dist, mat, blend = synth.terrain(n, dev, origin=tile_origin(rank, n))
+            torch.cuda.synchronize()
+            ctxt = voxels_b200.Context(local_rank)
+            ctxt.set_device_grid(n, dist.data_ptr(), mat.data_ptr(), blend.data_ptr(), keep=(dist, mat, blend))
+            st = torch.cuda.ExternalStream(ctxt.L.vxb_stream(ctxt.h), device=dev)
+            for _ in range(3):
+                ctxt.polygonize(0, flags)
+            ms_t = timed(lambda: ctxt.polygonize(0, flags), max(3, min(args.steps, 5)), st)
+            extra["independent_tiles"] = {"value": whole_job_throughput(n, world, ms_t), "unit": "Mvoxels/s", "ms_per_step": ms_t, "scaling": "weak",
+                                          "what": "one %d^3 terrain tile per rank, no data-path collective (round 1's line)" % n}
+            ctxt.close()
+            del dist, mat, blend
+
+    # ---------------------------------------------------------------- second record: BASELINE configs[3], 2048^3 (one grid over N GPUs)
+    if not args.no_config4:
+        try:
+            n4 = 2048
+            torch.cuda.empty_cache()
+            import numpy as np
+            if world > 1:
+                sg4 = ShardedGrid(ranks, n4, key="c4-%s" % os.environ.get("MASTER_PORT", "0"))
+                terrain_config4(sg4, synth, dev)
+                sg4.ready()
+                st4 = torch.cuda.ExternalStream(sg4.ctx.stream(), device=dev)
+                for _ in range(3):
+                    i4 = sg4.polygonize(flags)
+
+                def step4():
+                    if sg4.ctx.polygonize_sharded(3, flags) != 0:
+                        raise RuntimeError("arena overflow inside the timed region")
+            else:
+                vol4 = synth.terrain(n4, dev)
+                torch.cuda.synchronize()
+                sg4 = voxels_b200.Context(local_rank)
+                sg4.set_device_grid(n4, vol4[0].data_ptr(), vol4[1].data_ptr(), vol4[2].data_ptr(), keep=vol4)
+                st4 = torch.cuda.ExternalStream(sg4.L.vxb_stream(sg4.h), device=dev)
+                for _ in range(3):
+                    i4 = sg4.polygonize(0, flags)
+
+                def step4():
+                    sg4.polygonize(0, flags)
+
+            s4 = max(3, min(args.steps, 5))
+            ms4 = timed(step4, s4, st4)
+            if world > 1:
+                dir4, own4 = sg4.directory()
+            else:
+                dir4 = sg4.download().records
+                own4 = np.zeros(len(dir4), np.int32)
+            V4 = int(dir4["vertex_count"].sum()); I4 = int(dir4["index_count"].sum())
+            TV4 = int(dir4["trans_vertex_count"].sum()); TI4 = int(dir4["trans_index_count"].sum())
+            a4 = sum(algorithmic_bytes(n4, i4.levels_total, V4, I4, TV4, TI4))
+            extra["config4_2048"] = {"metric": "Mvoxels/s polygonized", "value": float(n4) ** 3 / (ms4 * 1e-3) / 1e6, "unit": "Mvoxels/s", "ms_per_step": ms4, "steps": s4,
+                                     "n_gpus": world, "scaling": "strong", "workload": "2048^3 seeded Perlin terrain, ONE grid over %d GPU(s), all 8 LOD levels + transition cells" % world,
+                                     "blocks_emitted": int(len(dir4)), "blocks_per_rank": [int((own4 == r).sum()) for r in range(world)],
+                                     "roofline": {"achieved": a4 / (ms4 * 1e-3) / 1e9, "peak": peak * world, "frac": a4 / (ms4 * 1e-3) / 1e9 / (peak * world), "unit": "GB/s",
+                                                  "algorithmic_bytes_per_step": a4}}
+            sg4.close()
+        except Exception as exc:  # the headline line must still be printed
+            extra["config4_2048"] = {"value": None, "error": repr(exc)[:300]}
+            try:
+                ranks.max_over_ranks(0.0)
+            except Exception:
+                pass
+
+    value = float(n) ** 3 / (ms_step * 1e-3) / 1e6
     if rank == 0:
         line = {
             "metric": "Mvoxels/s polygonized", "value": value, "unit": "Mvoxels/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_resident, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "int8 samples / fp32 vertices", "data": "synthetic",
-            "config": {"workload": "%d^3 seeded Perlin terrain per GPU, LOD levels 0-%d%s (BASELINE configs[2] asks for levels 0-3 + transitions)"
-                                   % (n, levels_computed - 1, "" if args.no_transitions else " + transition cells"),
-                       "grid": "dense int8 distance + uint8 material + uint8 blend, resident in HBM", "sharding": "one independent terrain tile per rank, no data-path collective",
-                       "l2": "inputs (%.2f GiB per channel) larger than the 126 MB L2; no flush" % (n ** 3 / 2.0 ** 30),
-                       "vertices": int(V), "indices": int(I), "transition_vertices": int(TV), "transition_indices": int(TI), "blocks_emitted": int(info.block_count)},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_dense": e2e_dense, "clocks": clocks,
-            "gpu_launches": int(launches_per_step * args.steps), "device_ms_per_step_inner": device_ms_inner,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
+            "dtype": "int8 samples / fp32 vertices", "data": "synthetic", "config": config,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "parity": parity, "clocks": clocks,
+            "gpu_launches": int(launches_per_step * args.steps), "device_ms_per_step_inner": device_ms_inner, "extra": extra,
         }
+        if sharding_note:
+            line["config"]["scaling_note"] = sharding_note
         print(json.dumps(line))
-    ctx.close()
     ranks.close()
     return 0
 

@@ -115,6 +115,44 @@ int vxb_grid_set_device(vxb_context* ctx, uint32_t n, const int8_t* d_dist, cons
 /* Device pointers of the context-owned dense volumes (after an upload), for tools/benchmarks. */
 int vxb_grid_device_pointers(vxb_context* ctx, const int8_t** d_dist, const uint8_t** d_mat, const uint8_t** d_blend);
 
+/* ---- device-resident grid store (the steps before the polygonizer; reference src/VoxelGrid.cpp) ------------------
+ * A built-in procedural surface: the device-side analogue of a client's Voxels::VoxelSurface (include/VoxelSurface.h:35-40;
+ * a client callback cannot run on the GPU, these can).  voxels_b200/csrc/vxb_surfaces.h evaluates them with bit-identical
+ * floats on the device and on the host (the test harness serves the same functions to the unmodified reference grid store).
+ *   SPHERE   p = {cx, cy, cz, r}: d = |x - c| - r             material / blend: constants
+ *   PLANE    p = {nx, ny, nz, d0}: d = n . x - d0              material / blend: constants
+ *   TERRAIN  p = {N, ox, oy}: the seeded Perlin terrain of BASELINE configs[1..4]: heightfield 0.5 N +
+ *            0.18 N fbm2 + 6 perlin3 detail, 3 material bands + ore pockets, smooth blends; N = horizontal period (the grid
+ *            edge), (ox, oy) = window origin; seed = permutation table
+ * Distances are clamped to +-100 before quantisation (keeps the reference's char conversion defined, VoxelGrid.cpp:37-40). */
+enum { VXB_SURFACE_SPHERE = 0, VXB_SURFACE_PLANE = 1, VXB_SURFACE_TERRAIN = 2 };
+typedef struct vxb_surface
+{
+	uint32_t kind;
+	uint32_t material, blend;     /* SPHERE / PLANE */
+	uint32_t seed;                /* TERRAIN */
+	float p[8];
+} vxb_surface;
+/* Grid::Create(n, n, n, start_x, start_y, start_z, step, &surface) (VoxelGrid.cpp:79-132) into context-owned dense volumes -
+ * or, when the context has a cube (sharded runs), into the pieces this rank backs: sample, round away from zero, clamp to +-4. */
+int vxb_grid_fill(vxb_context* ctx, uint32_t n, const vxb_surface* surface, const float start[3], float step);
+/* VoxelGrid::InjectSurface (VoxelGrid.cpp:388-488) on the device copy: position / extents in grid (Z-up) coordinates, type =
+ * InjectionType (0 IT_Add, 1 IT_SubtractAddInner, 2 IT_Subtract; include/Grid.h).  The surface is sampled relative to
+ * `position` exactly as the reference samples the client's surface (:419-428).  out_min / out_max = the modified box the
+ * reference returns (Y-up "DX style", :479-487) = what Modification::MinCornerModified / MaxCornerModified take.
+ * Needs a context-owned grid (upload or fill). */
+int vxb_grid_inject_surface(vxb_context* ctx, const float position[3], const float extents[3], const vxb_surface* surface, int type,
+	float out_min[3], float out_max[3]);
+/* VoxelGrid::InjectMaterial (VoxelGrid.cpp:490-584). */
+int vxb_grid_inject_material(vxb_context* ctx, const float position[3], const float extents[3], uint32_t material, int add_subtract_blend,
+	float out_min[3], float out_max[3]);
+/* Grid::PackForSave of the device grid (VoxelGrid::CompressBlock :610-672 + PackForSave :269-315): every block run-length coded on
+ * the GPU (raw fallback when RLE is ineffective, BF_Empty flag), then the blob copied to HOST memory `out` (capacity bytes,
+ * vxb_pack_dense_bound is enough).  Byte-identical to what the reference produces for the same voxels. */
+int vxb_grid_pack(vxb_context* ctx, void* out, size_t capacity, size_t* written);
+/* The dense volumes back to HOST memory (n^3 bytes each; any pointer may be NULL). */
+int vxb_grid_download_dense(vxb_context* ctx, int8_t* dist, uint8_t* mat, uint8_t* blend);
+
 /* MaterialMap::GetMaterial pre-tabulated (include/MaterialMap.h:19-30): table = 256 x
  * {DiffuseIds0[3], DiffuseIds1[3]}, valid = 256 bytes (0 = GetMaterial returned nullptr).
  * NULL table = identity map, NULL valid = all valid. */

@@ -58,6 +58,10 @@ class VoxelsLib:
             "vxh_grid_to_dense": (None, [vp, vp, vp, vp]),
             "vxh_grid_empty_flags": (C.c_int, [vp, vp]),
             "vxh_grid_inject_sphere": (None, [vp, f, f, f, f, f, C.c_int, vp]),
+            "vxh_grid_create_builtin": (vp, [u, vp, f, f, f, f]),
+            "vxh_builtin_dense": (None, [u, vp, vp, vp, vp]),
+            "vxh_grid_inject_builtin": (None, [vp, vp, vp, vp, C.c_int, vp]),
+            "vxh_grid_inject_material": (None, [vp, vp, vp, u, C.c_int, vp]),
             "vxh_grid_pack_size": (u, [vp, C.POINTER(vp)]),
             "vxh_pack_data": (vp, [vp]),
             "vxh_pack_destroy": (None, [vp]),
@@ -120,6 +124,29 @@ class VoxelsLib:
     def grid_inject_sphere(self, grid, pos, radius, extent, inject_type):
         box = np.zeros(6, np.float32)
         self.L.vxh_grid_inject_sphere(grid, pos[0], pos[1], pos[2], radius, extent, inject_type, self._ptr(box))
+        return box
+
+    # ---- built-in procedural surfaces (voxels_b200/csrc/vxb_surfaces.h evaluated on the host, fed to the reference) ----
+    def grid_create_builtin(self, n, surface, start=(0.0, 0.0, 0.0), step=1.0):
+        """Grid::Create(n, n, n, start, step, &surface) with a capi.Surface."""
+        return self.L.vxh_grid_create_builtin(n, C.cast(C.byref(surface), C.c_void_p), start[0], start[1], start[2], step)
+
+    def builtin_dense(self, n, surface):
+        """(dist, mat, blend) [z, y, x]: the surface quantised the reference's way, on all host threads."""
+        dist = np.empty((n, n, n), np.int8); mat = np.empty((n, n, n), np.uint8); blend = np.empty((n, n, n), np.uint8)
+        self.L.vxh_builtin_dense(n, C.cast(C.byref(surface), C.c_void_p), self._ptr(dist), self._ptr(mat), self._ptr(blend))
+        return dist, mat, blend
+
+    def grid_inject_builtin(self, grid, pos, ext, surface, inject_type):
+        box = np.zeros(6, np.float32)
+        p = np.ascontiguousarray(pos, np.float32); e = np.ascontiguousarray(ext, np.float32)
+        self.L.vxh_grid_inject_builtin(grid, self._ptr(p), self._ptr(e), C.cast(C.byref(surface), C.c_void_p), inject_type, self._ptr(box))
+        return box
+
+    def grid_inject_material(self, grid, pos, ext, material, add_subtract_blend):
+        box = np.zeros(6, np.float32)
+        p = np.ascontiguousarray(pos, np.float32); e = np.ascontiguousarray(ext, np.float32)
+        self.L.vxh_grid_inject_material(grid, self._ptr(p), self._ptr(e), material, 1 if add_subtract_blend else 0, self._ptr(box))
         return box
 
     def grid_pack(self, grid):

@@ -29,6 +29,10 @@
 #include <omp.h>
 #endif
 
+// the built-in procedural surfaces of the product's device-side grid store, evaluated here on the host with bit-identical
+// floats and served to the UNMODIFIED reference grid store through its VoxelSurface callback
+#include "../../voxels_b200/csrc/vxb_surfaces.h"
+
 using namespace Voxels;
 
 namespace
@@ -85,6 +89,37 @@ struct SphereSurface : public VoxelSurface
 			output[id] = d;
 			if (materialid) materialid[id] = Material;
 			if (blend) blend[id] = BlendValue;
+			++id;
+		}
+	}
+};
+
+// vxb_surface (include/vxb200.h) as a client VoxelSurface: values x-fastest, then y, then z (VoxelGrid.cpp:116-126)
+struct BuiltinSurface : public VoxelSurface
+{
+	vxb_surface S;
+	unsigned char Perm[512];
+	explicit BuiltinSurface(const vxb_surface& s) : S(s) { vxs_permutation(s.seed, Perm); }
+
+	virtual void GetSurface(float xStart, float xEnd, float xStep,
+		float yStart, float yEnd, float yStep,
+		float zStart, float zEnd, float zStep,
+		float* output, unsigned char* materialid, unsigned char* blend) override
+	{
+		size_t id = 0;
+		// sample k of an axis sits at start + k * step (the grid hands out whole blocks / whole sections: VoxelGrid.cpp:100-113, :419-428)
+		int nx = 0, ny = 0, nz = 0;
+		for (float x = xStart; x < xEnd; x += xStep) ++nx;
+		for (float y = yStart; y < yEnd; y += yStep) ++ny;
+		for (float z = zStart; z < zEnd; z += zStep) ++nz;
+		for (int kz = 0; kz < nz; ++kz)
+		for (int ky = 0; ky < ny; ++ky)
+		for (int kx = 0; kx < nx; ++kx)
+		{
+			unsigned m, b;
+			output[id] = vxs_surface_value(S, Perm, xStart + float(kx) * xStep, yStart + float(ky) * yStep, zStart + float(kz) * zStep, m, b);
+			if (materialid) materialid[id] = (unsigned char)m;
+			if (blend) blend[id] = (unsigned char)b;
 			++id;
 		}
 	}
@@ -170,6 +205,34 @@ void* vxh_grid_create_sphere(unsigned n, float cx, float cy, float cz, float r, 
 	return Grid::Create(n, n, n, 0.f, 0.f, 0.f, 1.f, &s);
 }
 
+// Grid::Create(n, n, n, sx, sy, sz, step, &builtin): the reference's own constructor walks the blocks and quantises
+void* vxh_grid_create_builtin(unsigned n, const vxb_surface* surface, float sx, float sy, float sz, float step)
+{
+	BuiltinSurface s(*surface);
+	return Grid::Create(n, n, n, sx, sy, sz, step, &s);
+}
+
+// The same voxels as dense arrays, on every host thread (for full-size inputs: the reference's constructor is serial):
+// surface value -> the reference's round (away from zero) -> clamp to +-4 (VoxelGrid.cpp:37-50), start 0, step 1.
+void vxh_builtin_dense(unsigned n, const vxb_surface* surface, signed char* dist, unsigned char* mat, unsigned char* blend)
+{
+	BuiltinSurface s(*surface);
+	#pragma omp parallel for schedule(static)
+	for (long zy = 0; zy < long(n) * n; ++zy)
+	{
+		const unsigned z = unsigned(zy / n), y = unsigned(zy % n);
+		for (unsigned x = 0; x < n; ++x)
+		{
+			unsigned m, b;
+			const float d = vxs_surface_value(s.S, s.Perm, float(x), float(y), float(z), m, b);
+			int v = vxs_round_away(d);
+			v = v > 4 ? 4 : (v < -4 ? -4 : v);
+			const size_t g = (size_t(z) * n + y) * n + x;
+			dist[g] = (signed char)v; mat[g] = (unsigned char)m; blend[g] = (unsigned char)b;
+		}
+	}
+}
+
 // Exact-bytes grid: empty grid + Grid::ModifyBlock*Data per block (include/Grid.h:135-146).
 void* vxh_grid_from_dense(unsigned n, const signed char* dist, const unsigned char* mat, const unsigned char* blend)
 {
@@ -251,6 +314,24 @@ void vxh_grid_inject_sphere(void* gridPtr, float px, float py, float pz, float r
 	SphereSurface s;
 	s.Cx = 0.f; s.Cy = 0.f; s.Cz = 0.f; s.R = radius; s.Material = 0; s.BlendValue = 0;
 	const float3pair box = grid->InjectSurface(float3(px, py, pz), float3(extent, extent, extent), &s, InjectionType(type));
+	out6[0] = box.first.x; out6[1] = box.first.y; out6[2] = box.first.z;
+	out6[3] = box.second.x; out6[4] = box.second.y; out6[5] = box.second.z;
+}
+
+// Grid::InjectSurface with a built-in surface (sampled relative to the position, VoxelGrid.cpp:419-428)
+void vxh_grid_inject_builtin(void* gridPtr, const float* pos, const float* ext, const vxb_surface* surface, int type, float* out6)
+{
+	Grid* grid = static_cast<Grid*>(gridPtr);
+	BuiltinSurface s(*surface);
+	const float3pair box = grid->InjectSurface(float3(pos[0], pos[1], pos[2]), float3(ext[0], ext[1], ext[2]), &s, InjectionType(type));
+	out6[0] = box.first.x; out6[1] = box.first.y; out6[2] = box.first.z;
+	out6[3] = box.second.x; out6[4] = box.second.y; out6[5] = box.second.z;
+}
+
+void vxh_grid_inject_material(void* gridPtr, const float* pos, const float* ext, unsigned material, int addSubtractBlend, float* out6)
+{
+	Grid* grid = static_cast<Grid*>(gridPtr);
+	const float3pair box = grid->InjectMaterial(float3(pos[0], pos[1], pos[2]), float3(ext[0], ext[1], ext[2]), (unsigned char)material, addSubtractBlend != 0);
 	out6[0] = box.first.x; out6[1] = box.first.y; out6[2] = box.first.z;
 	out6[3] = box.second.x; out6[4] = box.second.y; out6[5] = box.second.z;
 }

@@ -1,15 +1,15 @@
 #!/usr/bin/env python
-"""BASELINE configs[3]: ONE n^3 terrain polygonized by all ranks (z-slabs, one GPU each).
+"""BASELINE configs[3] and the strong-scaling line: ONE n^3 terrain polygonized by all ranks (voxels_b200.dist.ShardedGrid).
 
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
-        tools/bench_sharded.py [--size 2048] [--steps 10] [--warmup 3] [--verify]
+    torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/bench_sharded.py --size 2048 [--verify] [--reference]
 
-Every rank fills its own slab of the cube (synthetic terrain, on the device), maps the peers' slabs over NVLink and runs
-voxels_b200.dist.ShardedGrid.polygonize: scan + nested levels, ONE in-place NCCL all-gather of the last nested level's
-material pages, the rest.  Timed per step on the device (CUDA events on the context's stream), max over ranks; the block
-directories are all-gathered after the timed loop.  --verify (needs the whole grid to fit rank 0's GPU next to its slab)
-re-runs the grid unsharded on rank 0 and compares the gathered directory entry by entry and rank 0's geometry bit by bit.
-Rank 0 prints one JSON line."""
+--verify     every rank also polygonizes the whole grid alone (single-GPU path) and compares ITS OWN blocks of the
+             sharded run bit by bit (vertices, indices, transition meshes); rank 0 compares the merged directory entry
+             by entry and the summed statistics.
+--reference  (n <= 1024) rank 0 additionally runs the unmodified reference (oracle/_ref) on the same bytes and compares
+             the single-GPU result level by level - with --verify that pins every rank's geometry to the reference.
+Prints one JSON line on rank 0.
+"""
 import argparse
 import json
 import os
@@ -25,99 +25,105 @@ def main():
     ap.add_argument("--size", type=int, default=2048)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--group-planes", type=int, default=0)
     ap.add_argument("--verify", action="store_true")
-    ap.add_argument("--balance", type=int, default=0, metavar="PLANES",
-                    help="after a first run with equal slabs, re-shard with boundaries (multiples of PLANES) that even out the work it measured")
+    ap.add_argument("--reference", action="store_true")
     args = ap.parse_args()
     import numpy as np
     import torch
     import voxels_b200
     from voxels_b200 import capi, synth
-    from voxels_b200.dist import Ranks, ShardedGrid, slab_planes, balanced_planes, layer_weights_from_directory
+    from voxels_b200.dist import Ranks, ShardedGrid
 
     local = int(os.environ.get("LOCAL_RANK", "0"))
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     ranks = Ranks("nccl", dev)
     n = args.size
-    def build(planes):
-        g = ShardedGrid(ranks, n, planes=planes)
-        z0, z1 = slab_planes(n, ranks.rank, ranks.world, planes)
-        synth.terrain(n, dev, z_range=(z0, z1), out=g.slab_tensors())
-        g.ready()
-        return g
-
-    sg = build(None)
-    planes = None
-    if args.balance and ranks.world > 1:
-        # z is up: a terrain's surface sits in a few z-layers.  One run with equal slabs tells where the work is; the
-        # slabs are then re-cut so that every rank gets the same share (what a client does from the previous frame).
-        sg.polygonize()
-        directory, _ = sg.directory()
-        planes = balanced_planes(layer_weights_from_directory(n, directory), ranks.world, args.balance // 16)
-        sg.close()
-        torch.cuda.synchronize(dev)
-        ranks.barrier()
-        sg = build(planes)
-
+    sg = ShardedGrid(ranks, n, group_planes=args.group_planes or None)
+    for z0, z1, out in sg.piece_tensors():
+        synth.terrain(n, dev, z_range=(z0, z1), out=out)
+    sg.ready()
     stream = torch.cuda.ExternalStream(sg.ctx.stream(), device=dev)
-    times, mine_ms, inner_ms = [], [], []
-    for step in range(args.warmup + args.steps):
-        ranks.barrier()
-        torch.cuda.synchronize(dev)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
+    for _ in range(args.warmup):
         info = sg.polygonize()
-        e1.record(stream)
-        torch.cuda.synchronize(dev)
-        ms = ranks.max_over_ranks(e0.elapsed_time(e1))
-        if step >= args.warmup:
-            times.append(ms)
-            mine_ms.append(e0.elapsed_time(e1))
-            inner_ms.append(info.device_ms)
+    inner = []
+    ranks.barrier(); torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        if ranks.world > 1:
+            assert sg.ctx.polygonize_sharded(3, 0) == 0
+        else:
+            sg.polygonize()
+        inner.append(sg.ctx.info().device_ms)
+    e1.record(stream)
+    ranks.barrier(); torch.cuda.synchronize(dev)
+    ms = ranks.max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    info = sg.ctx.info()
     directory, owner = sg.directory()
-    ms = float(np.mean(times))
-    per_rank = torch.zeros(ranks.world * 2, dtype=torch.float64, device=dev)
+    per_rank = torch.zeros(ranks.world, dtype=torch.float64, device=dev)
+    mine_ms = torch.tensor([float(np.mean(inner))], dtype=torch.float64, device=dev)
     if ranks.td is not None:
-        ranks.td.all_gather_into_tensor(per_rank, torch.tensor([float(np.mean(mine_ms)), float(np.mean(inner_ms))], dtype=torch.float64, device=dev))
+        ranks.td.all_gather_into_tensor(per_rank, mine_ms)
     else:
-        per_rank = torch.tensor([float(np.mean(mine_ms)), float(np.mean(inner_ms))])
-    per_rank = per_rank.cpu().numpy().reshape(-1, 2)
-    out = {"metric": "Mvoxels/s polygonized (one grid sharded over the GPUs)", "value": float(n) ** 3 / (ms * 1e-3) / 1e6, "unit": "Mvoxels/s",
+        per_rank = mine_ms
+    stats = torch.tensor([int(v) for v in info.stats], dtype=torch.int64, device=dev)
+    if ranks.td is not None:
+        ranks.td.all_reduce(stats)
+    stats = (stats.cpu().numpy() & 0xFFFFFFFF).astype(np.uint32)
+    out = {"metric": "Mvoxels/s polygonized (one grid over the GPUs)", "value": float(n) ** 3 / (ms * 1e-3) / 1e6, "unit": "Mvoxels/s",
            "n_gpus": ranks.world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "scaling": "strong",
-           "config": {"workload": "%d^3 seeded Perlin terrain, all LOD levels + transition cells, z-slabs of %d planes" % (n, n // ranks.world),
-                      "slab_boundaries": planes if planes is not None else "equal",
-                      "exchange": "one NCCL exchange (material pages of the last nested level) + directory all-gather"},
+           "config": {"workload": "%d^3 seeded Perlin terrain, all LOD levels + transition cells, pieces of %d planes dealt cyclically" % (n, sg.group_planes),
+                      "exchange": "ncclAllGather of the per-block info + peer stores of material pages (ordered by a one-word ncclAllGather), inside every step"},
            "blocks_total": int(len(directory)), "blocks_per_rank": [int((owner == r).sum()) for r in range(ranks.world)],
-           "ms_per_rank": [round(float(v), 3) for v in per_rank[:, 0]], "device_ms_per_rank": [round(float(v), 3) for v in per_rank[:, 1]],
-           "vertices_this_rank0": int(info.vertex_total)}
+           "vertices_per_rank": [int(directory["vertex_count"][owner == r].sum()) for r in range(ranks.world)],
+           "device_ms_per_rank": [round(float(v), 3) for v in per_rank.cpu().numpy()], "launches_per_step": int(info.kernel_launches)}
 
     if args.verify:
+        import compare
         problems = []
         mine = sg.ctx.download()
+        ctx = voxels_b200.Context(local)
+        full = synth.terrain(n, dev)
+        ctx.set_device_grid(n, full[0].data_ptr(), full[1].data_ptr(), full[2].data_ptr(), keep=full)
+        sinfo = ctx.polygonize()
+        single = ctx.download()
+        # this rank's blocks of the sharded run against the same blocks of the single-GPU run, bit by bit
+        keys = set(zip(mine.records["level"].tolist(), mine.records["coord_id"].tolist()))
+        keep = np.array([(l, c) in keys for l, c in zip(single.records["level"].tolist(), single.records["coord_id"].tolist())], bool)
+        sub = capi.Result.__new__(capi.Result)
+        sub.n, sub.info, sub.records = n, None, single.records[keep]
+        sub.verts, sub.idx, sub.tverts, sub.tidx, sub.stats = single.verts, single.idx, single.tverts, single.tidx, single.stats
+        for l in range(info.levels_total):
+            problems += compare.level_diff(sub.level(l), mine.level(l), "rank%d L%d" % (ranks.rank, l))
         if ranks.rank == 0:
-            import compare
-            ctx = voxels_b200.Context(local)
-            full = synth.terrain(n, dev)
-            ctx.set_device_grid(n, full[0].data_ptr(), full[1].data_ptr(), full[2].data_ptr(), keep=full)
-            ctx.polygonize()
-            single = ctx.download()
             if len(single.records) != len(directory):
                 problems.append("directory sizes differ: %d vs %d" % (len(single.records), len(directory)))
             else:
                 for f in ("level", "coord_id", "id", "vertex_count", "index_count", "trans_vertex_count", "trans_index_count"):
                     if not np.array_equal(single.records[f], directory[f]):
                         problems.append("directory field %s differs" % f)
-            # geometry of rank 0's own blocks, bit by bit
-            keys = set(zip(mine.records["level"].tolist(), mine.records["coord_id"].tolist()))
-            keep = np.array([(l, c) in keys for l, c in zip(single.records["level"].tolist(), single.records["coord_id"].tolist())])
-            sub = capi.Result.__new__(capi.Result)
-            sub.n, sub.info, sub.records = n, None, single.records[keep]
-            sub.verts, sub.idx, sub.tverts, sub.tidx, sub.stats = single.verts, single.idx, single.tverts, single.tidx, single.stats
-            for l in range(info.levels_total):
-                problems += compare.level_diff(sub.level(l), mine.level(l), "rank0 L%d" % l)
-            ctx.close()
-        out["verify_problems"] = problems[:10]
+            if not np.array_equal(stats, single.stats):
+                problems.append("summed statistics differ: %s vs %s" % (stats.tolist(), single.stats.tolist()))
+            if args.reference and n <= 1024:
+                import harness
+                ref = harness.reference()
+                hd, hm, hb = (t.cpu().numpy() for t in full)
+                g = ref.grid_from_dense(hd, hm, hb)
+                s, sec = ref.polygonize(g, threads=max(ref.L.vxh_max_threads(), len(os.sched_getaffinity(0))))
+                for l in range(ref.surface_levels(s)):
+                    problems += compare.level_diff(ref.surface_level(s, l), single.level(l), "reference L%d" % l)
+                if not np.array_equal(ref.surface_stats(s), single.stats):
+                    problems.append("reference statistics differ")
+                out["reference_seconds"] = sec
+                ref.surface_destroy(s); ref.grid_destroy(g)
+        bad = ranks.sum_over_ranks(len(problems))
+        out["verify"] = {"ranks_compared": ranks.world, "problems_all_ranks": int(bad), "first_rank0": problems[:5],
+                         "what": "every rank: its blocks vs the single-GPU run (bit-exact); rank 0: merged directory + summed statistics"
+                                 + ("; single-GPU run vs the unmodified reference" if args.reference and n <= 1024 else "")}
+        out["single_gpu_ms"] = float(sinfo.device_ms)
+        ctx.close()
     if ranks.rank == 0:
         print(json.dumps(out))
     sg.close()

@@ -40,6 +40,29 @@ class ShardBuffers(C.Structure):
                 ("pad", C.c_uint32)]
 
 
+class Surface(C.Structure):
+    """vxb_surface (include/vxb200.h): a built-in procedural surface."""
+    _fields_ = [("kind", C.c_uint32), ("material", C.c_uint32), ("blend", C.c_uint32), ("seed", C.c_uint32), ("p", C.c_float * 8)]
+
+    @staticmethod
+    def sphere(center, radius, material=0, blend=0):
+        s = Surface(); s.kind = 0; s.material = material; s.blend = blend
+        s.p[0], s.p[1], s.p[2], s.p[3] = center[0], center[1], center[2], radius
+        return s
+
+    @staticmethod
+    def plane(normal, d0, material=0, blend=0):
+        s = Surface(); s.kind = 1; s.material = material; s.blend = blend
+        s.p[0], s.p[1], s.p[2], s.p[3] = normal[0], normal[1], normal[2], d0
+        return s
+
+    @staticmethod
+    def terrain(period, origin=(0.0, 0.0), seed=1234):
+        s = Surface(); s.kind = 2; s.seed = seed
+        s.p[0], s.p[1], s.p[2] = float(period), float(origin[0]), float(origin[1])
+        return s
+
+
 class NcclId(C.Structure):
     _fields_ = [("internal", C.c_char * 128)]
 
@@ -92,6 +115,11 @@ def load_library():
         "vxb_pack_dense": (C.c_int, [u32, vp, vp, vp, vp, C.c_size_t, C.POINTER(C.c_size_t)]),
         "vxb_grid_device_pointers": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),
         "vxb_set_materials": (C.c_int, [vp, vp, vp]),
+        "vxb_grid_fill": (C.c_int, [vp, u32, C.POINTER(Surface), vp, C.c_float]),
+        "vxb_grid_inject_surface": (C.c_int, [vp, vp, vp, C.POINTER(Surface), C.c_int, vp, vp]),
+        "vxb_grid_inject_material": (C.c_int, [vp, vp, vp, u32, C.c_int, vp, vp]),
+        "vxb_grid_pack": (C.c_int, [vp, vp, C.c_size_t, C.POINTER(C.c_size_t)]),
+        "vxb_grid_download_dense": (C.c_int, [vp, vp, vp, vp]),
         "vxb_polygonize": (C.c_int, [vp, u32, u32]),
         "vxb_result_info_get": (C.c_int, [vp, C.POINTER(ResultInfo)]),
         "vxb_grid_update_blocks": (C.c_int, [vp, u32, vp, vp, vp, vp]),
@@ -129,7 +157,8 @@ EXPORTED_SYMBOLS = ["vxb_create", "vxb_destroy", "vxb_last_error", "vxb_stream",
                     "vxb_polygonize", "vxb_polygonize_region", "vxb_region_info_get", "vxb_grid_update_blocks", "vxb_result_info_get", "vxb_result_download", "vxb_set_capacity", "vxb_kernel_ms",
                     "vxb_result_unmapped_materials", "vxb_host_alloc", "vxb_host_free", "vxb_polygonize_sharded", "vxb_shard_configure",
                     "vxb_shard_buffers_get", "vxb_shard_set_peer", "vxb_shard_export", "vxb_shard_import", "vxb_shard_nccl_unique_id",
-                    "vxb_shard_nccl_init", "vxb_cube_create", "vxb_cube_info", "vxb_cube_export", "vxb_cube_import", "vxb_cube_piece"]
+                    "vxb_shard_nccl_init", "vxb_grid_fill", "vxb_grid_inject_surface", "vxb_grid_inject_material", "vxb_grid_pack",
+                    "vxb_grid_download_dense", "vxb_cube_create", "vxb_cube_info", "vxb_cube_export", "vxb_cube_import", "vxb_cube_piece"]
 
 
 def nccl_unique_id():
@@ -276,6 +305,39 @@ class Context:
             ptr, nbytes = _ptr(blob), blob.size
         self._check(self.L.vxb_grid_upload_packed(self.h, ptr, nbytes), "vxb_grid_upload_packed")
         self.n = int(np.frombuffer(C.string_at(ptr, 8), np.uint32)[1])
+
+    # ---- device-resident grid store (fill / edit / pack) ----
+    def fill(self, n, surface, start=(0.0, 0.0, 0.0), step=1.0):
+        """Grid::Create(n, n, n, start, step, &surface) on the device (a capi.Surface); with a cube: this rank's pieces."""
+        st = np.ascontiguousarray(start, np.float32)
+        self._check(self.L.vxb_grid_fill(self.h, n, C.byref(surface), _ptr(st), step), "vxb_grid_fill")
+        self.n = n
+
+    def inject_surface(self, position, extents, surface, inject_type):
+        """VoxelGrid::InjectSurface on the device grid; returns the modified box (6 floats, Y-up) the reference returns."""
+        p = np.ascontiguousarray(position, np.float32); e = np.ascontiguousarray(extents, np.float32)
+        lo = np.zeros(3, np.float32); hi = np.zeros(3, np.float32)
+        self._check(self.L.vxb_grid_inject_surface(self.h, _ptr(p), _ptr(e), C.byref(surface), inject_type, _ptr(lo), _ptr(hi)), "vxb_grid_inject_surface")
+        return np.concatenate([lo, hi])
+
+    def inject_material(self, position, extents, material, add_subtract_blend):
+        p = np.ascontiguousarray(position, np.float32); e = np.ascontiguousarray(extents, np.float32)
+        lo = np.zeros(3, np.float32); hi = np.zeros(3, np.float32)
+        self._check(self.L.vxb_grid_inject_material(self.h, _ptr(p), _ptr(e), material, 1 if add_subtract_blend else 0, _ptr(lo), _ptr(hi)), "vxb_grid_inject_material")
+        return np.concatenate([lo, hi])
+
+    def pack(self):
+        """Grid::PackForSave of the device grid (GPU run-length coding): numpy uint8 blob."""
+        buf = np.empty(self.L.vxb_pack_dense_bound(self.n), np.uint8)
+        written = C.c_size_t(0)
+        self._check(self.L.vxb_grid_pack(self.h, _ptr(buf), buf.size, C.byref(written)), "vxb_grid_pack")
+        return buf[:written.value].copy()
+
+    def download_dense(self):
+        n = self.n
+        dist = np.empty((n, n, n), np.int8); mat = np.empty((n, n, n), np.uint8); blend = np.empty((n, n, n), np.uint8)
+        self._check(self.L.vxb_grid_download_dense(self.h, _ptr(dist), _ptr(mat), _ptr(blend)), "vxb_grid_download_dense")
+        return dist, mat, blend
 
     def set_device_grid(self, n, d_dist, d_mat, d_blend, keep=None):
         """Device pointers (ints) of dense volumes that stay resident (e.g. torch tensors' data_ptr())."""

@@ -17,6 +17,13 @@
 #include "stdafx.h" // reference src/stdafx.h through the shim: Logger (VOXLOG), VOXELS_LOG_SIZE
 #include <Structs.h>
 #include <Grid.h>
+// The grid store's compressed blocks (src/VoxelGrid.h:82-104: flags + three run-length coded channels per block) are what
+// PackForSave serialises (src/VoxelGrid.cpp:269-315) and what the GPU decodes; the reference's own backend is a friend-less
+// client of VoxelGrid too, but only needs decompressed blocks.  A maintainer adds `const std::vector<Block>& GetBlocks() const`
+// (INTEGRATION.md); until then this translation unit reads the private member.
+#define private public
+#include <VoxelGrid.h>
+#undef private
 #include <MaterialMap.h>
 #include <Polygonizer.h>
 
@@ -112,7 +119,8 @@ void releaseContext(vxb_context* c)
 // CUDA runtime may already be gone when static destructors run).
 struct Staging
 {
-	HostBuffer Dist, Mat, Blend;
+	HostBuffer Dist, Mat, Blend; // decompressed blocks of the edited region (incremental runs)
+	HostBuffer Blob;             // the grid in PackForSave form (full runs)
 };
 std::vector<Staging*> g_StagingPool;
 
@@ -141,6 +149,32 @@ struct Arena
 	size_t Live = 0;
 };
 
+// Page-locked arenas of full runs (hundreds of MB) are pooled like the contexts: allocating them costs ~0.1 s
+std::vector<Arena*> g_ArenaPool;
+
+Arena* acquireArena()
+{
+	{
+		std::lock_guard<std::mutex> guard(g_PoolLock);
+		if (!g_ArenaPool.empty()) { Arena* a = g_ArenaPool.back(); g_ArenaPool.pop_back(); a->Live = 0; return a; }
+	}
+	return new Arena;
+}
+
+void releaseArena(Arena* a)
+{
+	if (!a) return;
+	if (a->Verts.pinned)
+	{
+		std::lock_guard<std::mutex> guard(g_PoolLock);
+		if (g_ArenaPool.size() < 2) { g_ArenaPool.push_back(a); return; }
+	}
+	delete a;
+}
+
+struct ArenaReturn { void operator()(Arena* a) const { releaseArena(a); } };
+typedef std::unique_ptr<Arena, ArenaReturn> ArenaPtr;
+
 // The polygonized surface: block views over host arenas (one per run: the full run + one small one per edit).
 // It owns the device context that holds the grid copy and the material caches of this surface, the way the
 // reference's PolygonMap owns its MaterialCache (TransVoxelImpl.h:81-95), so later incremental runs find them.
@@ -150,7 +184,7 @@ struct SurfaceImpl : public PolygonSurface
 	std::vector<std::vector<BlockView>> Levels;
 	PolygonizationStatistics Stats;
 	unsigned CacheBytes = 0;
-	std::vector<std::unique_ptr<Arena>> Arenas;
+	std::vector<ArenaPtr> Arenas;
 	vxb_context* Context = nullptr;
 	~SurfaceImpl() { releaseContext(Context); }
 
@@ -203,13 +237,13 @@ namespace
 // PushBlocksToResult appends them (level, then z,y,x: :1274-1293).  Nothing of the surface is touched: a failure leaves it intact.
 struct Downloaded
 {
-	std::unique_ptr<Arena> Storage;
+	ArenaPtr Storage;
 	std::vector<std::vector<BlockView>> Levels;
 };
 
 bool downloadResult(vxb_context* ctx, unsigned n, const vxb_result_info& info, Downloaded& out)
 {
-	std::unique_ptr<Arena> arena(new Arena);
+	ArenaPtr arena(acquireArena());
 	if (!arena->Verts.ensure(size_t(info.vertex_span) * sizeof(PolygonVertex) + 16) || !arena->Idx.ensure(size_t(info.index_span) * 4 + 16)
 		|| !arena->TransVerts.ensure(size_t(info.trans_vertex_span) * sizeof(PolygonVertex) + 16) || !arena->TransIdx.ensure(size_t(info.trans_index_span) * 4 + 16))
 		return false;
@@ -252,7 +286,7 @@ void commitResult(SurfaceImpl* surface, Downloaded& dl, const vxb_result_info& i
 		surface->Levels[l].insert(surface->Levels[l].end(), dl.Levels[l].begin(), dl.Levels[l].end());
 	if (dl.Storage->Live) surface->Arenas.push_back(std::move(dl.Storage));
 	surface->Arenas.erase(std::remove_if(surface->Arenas.begin(), surface->Arenas.end(),
-		[](const std::unique_ptr<Arena>& a) { return a->Live == 0; }), surface->Arenas.end());
+		[](const ArenaPtr& a) { return a->Live == 0; }), surface->Arenas.end());
 	surface->Stats.BlocksCalculated = info.stats[0];
 	surface->Stats.TrivialCells = info.stats[1];
 	surface->Stats.NonTrivialCells = info.stats[2];
@@ -325,26 +359,44 @@ PolygonSurface* TransVoxelImpl::Execute(const Grid& grid, const MaterialMap* mat
 	};
 	if (!uploadMaterials(ctx, materials)) return fail("material table upload failed");
 
-	// ---- grid -> device: every block through the public accessors, decompressed in parallel into pinned staging ----
+	// ---- grid -> device: the grid store's compressed blocks, laid out as PackForSave does (VoxelGrid.cpp:269-315: header,
+	// 3 sizes per block, then per block {flags, distance, material, blend}) in page-locked staging - a parallel memcpy of
+	// ~0.2 bytes per voxel - copied as is and run-length decoded on the GPU (vxb_grid_upload_packed) ----
 	const unsigned nb = n / 16;
-	const size_t volume = size_t(n) * n * n;
 	if (!m_Staging) m_Staging = acquireStaging();
-	if (!m_Staging->Dist.ensure(volume) || !m_Staging->Mat.ensure(volume) || !m_Staging->Blend.ensure(volume)) return fail("pinned staging allocation failed");
 	{
-		char* sd = static_cast<char*>(m_Staging->Dist.p);
-		unsigned char* sm = static_cast<unsigned char*>(m_Staging->Mat.p);
-		unsigned char* sb = static_cast<unsigned char*>(m_Staging->Blend.p);
-		const long total = long(nb) * nb * nb;
-		#pragma omp parallel for schedule(static)
-		for (long b = 0; b < total; ++b)
+		const VoxelGrid* vg = grid.GetInternalRepresentation();
+		const auto& blocks = vg->m_Blocks;
+		const size_t count = blocks.size();
+		if (count != size_t(nb) * nb * nb) return fail("the grid holds no block data (Grid::Create without a surface)");
+		std::vector<size_t> offsets(count + 1);
+		const size_t head = 16 + count * 12;
+		size_t off = head;
+		for (size_t b = 0; b < count; ++b)
 		{
-			const float3 coords(float(b % nb), float((b / nb) % nb), float(b / (long(nb) * nb)));
-			grid.GetBlockDistanceData(coords, sd + size_t(b) * 4096);
-			grid.GetBlockMaterialData(coords, sm + size_t(b) * 4096, sb + size_t(b) * 4096);
+			offsets[b] = off;
+			off += 4 + blocks[b].DistanceData.size() + blocks[b].MaterialData.size() + blocks[b].BlendData.size();
 		}
+		offsets[count] = off;
+		if (!m_Staging->Blob.ensure(off)) return fail("pinned staging allocation failed");
+		unsigned char* blob = static_cast<unsigned char*>(m_Staging->Blob.p);
+		const uint32_t header[4] = { 1u, n, n, n };
+		memcpy(blob, header, 16);
+		#pragma omp parallel for schedule(static)
+		for (long b = 0; b < long(count); ++b)
+		{
+			const auto& blk = blocks[b];
+			const uint32_t sz[3] = { uint32_t(blk.DistanceData.size()), uint32_t(blk.MaterialData.size()), uint32_t(blk.BlendData.size()) };
+			memcpy(blob + 16 + size_t(b) * 12, sz, 12);
+			unsigned char* out = blob + offsets[b];
+			const uint32_t flags = blk.Flags;
+			memcpy(out, &flags, 4); out += 4;
+			memcpy(out, blk.DistanceData.data(), sz[0]); out += sz[0];
+			memcpy(out, blk.MaterialData.data(), sz[1]); out += sz[1];
+			memcpy(out, blk.BlendData.data(), sz[2]);
+		}
+		if (vxb_grid_upload_packed(ctx, blob, off) != VXB_OK) return fail("grid upload failed");
 	}
-	if (vxb_grid_upload_blocks(ctx, n, static_cast<const int8_t*>(m_Staging->Dist.p), static_cast<const uint8_t*>(m_Staging->Mat.p),
-		static_cast<const uint8_t*>(m_Staging->Blend.p)) != VXB_OK) return fail("grid upload failed");
 
 	// ---- polygonize on the device ----
 	if (vxb_polygonize(ctx, 0, 0) != VXB_OK) return fail("polygonization failed");

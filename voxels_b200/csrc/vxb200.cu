@@ -27,6 +27,7 @@
 #include "vxb_cell.h"
 #include "vxb_kernels.cuh"
 #include "vxb_emit.cuh"
+#include "vxb_grid.cuh"
 
 typedef VxbDecideSmem<4096> VxbDecideSmemBig;
 
@@ -64,7 +65,7 @@ struct vxb_context
 	int smCount = 0;
 	cudaStream_t stream = nullptr, stream2 = nullptr;
 	cudaEvent_t evBegin = nullptr, evEnd = nullptr, evFork = nullptr, evDecide0 = nullptr, evJoin = nullptr, evDir = nullptr, evVerts = nullptr;
-	cudaEvent_t evChunk[4] = { nullptr, nullptr, nullptr, nullptr };
+	std::vector<cudaEvent_t> evChunks; // packed upload: one per z-chunk
 	std::vector<cudaEvent_t> kevents; // per-kernel timing (pairs)
 	std::string error;
 	EncodeTiledFn encodeTiled = nullptr;
@@ -75,6 +76,8 @@ struct vxb_context
 	const int8_t* dDist = nullptr; const uint8_t* dMat = nullptr; const uint8_t* dBlend = nullptr;
 	DevBuf<uint8_t> volDist, volMat, volBlend, staging;
 	DevBuf<unsigned long long> packOffsets;
+	DevBuf<float> fillColumns;
+	DevBuf<unsigned int> packSizes, packFlags;
 	struct PinnedBuf // page-locked host scratch (grows, never shrinks)
 	{
 		void* p = nullptr; size_t bytes = 0;
@@ -110,6 +113,12 @@ struct vxb_context
 	bool haveLattice1 = false, latticeOff = false;
 	int gridBlock[3] = { 0, 0, 0 }, gridDecideBig = 0, gridTransition = 0;
 	DevBuf<unsigned char> mixInfo, coarseDone;
+	// lattices of the coarse levels (VxbDev::coarseLattice): own buffer, or - sharded runs - an area of the buffer the peers map
+	DevBuf<unsigned char> coarseLatticeBuf;
+	DevBuf<CUtensorMap> coarseMaps;
+	unsigned char* coarseLatticeBase = nullptr;
+	size_t coarseLatticeOff[VXB_MAX_LEVELS] = { 0 }, coarseLatticeBytes = 0;
+	int coarseLo = 2;
 	uint64_t capC = 0;
 	bool haveFullRun = false;      // device caches (consistency / material pages) describe the current grid
 	uint32_t nextId = 0;           // PolygonMap::GetNextBlockId (TransVoxelImpl.cpp:149-152)
@@ -126,7 +135,8 @@ struct vxb_context
 		DevBuf<unsigned char> sbMine;
 		DevBuf<unsigned int> sbWeight;
 		// level-sbLevel pages + valid flags in ONE buffer the peers can map: VMM allocation (real ranks) or cudaMalloc (virtual ranks)
-		unsigned char* pagesBuf = nullptr; size_t pagesBytes = 0, validBytes = 0, bufBytes = 0;
+		unsigned char* pagesBuf = nullptr; size_t pagesBytes = 0, validBytes = 0, latticeBytes = 0, bufBytes = 0; // pages | valid | coarse lattices
+		unsigned char* peerLattice[8] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
 		bool pagesVmm = false;
 		CUdeviceptr pagesVa = 0; CUmemGenericAllocationHandle pagesHandle = 0;
 		unsigned short* peerPages[8] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
@@ -217,6 +227,65 @@ int encodeTileMap(vxb_context* ctx, CUtensorMap* map, const void* base, uint32_t
 	return VXB_OK;
 }
 
+size_t blocksAtLevel(uint32_t n, int level) { const size_t nb = (n / 16) >> level; return nb * nb * nb; }
+
+// coarse levels: from the first level with <= 4096 blocks (but not below 2) everything runs in one launch
+int coarseLoFor(uint32_t n, int levels)
+{
+	int lo = 2;
+	while (lo < levels && blocksAtLevel(n, lo) > 4096) ++lo;
+	return lo;
+}
+
+// byte layout of the coarse levels' lattices in one buffer: level l at offsets[l], (h + 1)^2 rows of h + 16 bytes
+size_t coarseLatticeLayout(uint32_t n, int levels, size_t offsets[VXB_MAX_LEVELS])
+{
+	size_t total = 0;
+	const int lo = coarseLoFor(n, levels);
+	for (int l = 0; l < VXB_MAX_LEVELS; ++l) offsets[l] = 0;
+	for (int l = lo; l < levels; ++l)
+	{
+		const size_t h = n >> l;
+		offsets[l] = total;
+		total += ((h + 16) * (h + 1) * (h + 1) + 127) & ~(size_t)127;
+	}
+	return total;
+}
+
+// (re)builds the coarse levels' lattice area and tensor maps: base = where the lattices live
+int buildCoarseLattices(vxb_context* ctx, unsigned char* sharedBase)
+{
+	const uint32_t n = ctx->n;
+	ctx->coarseLo = coarseLoFor(n, ctx->levels);
+	ctx->coarseLatticeBytes = coarseLatticeLayout(n, ctx->levels, ctx->coarseLatticeOff);
+	if (sharedBase) ctx->coarseLatticeBase = sharedBase;
+	else
+	{
+		VXB_CUDA(ctx, ctx->coarseLatticeBuf.ensure(ctx->coarseLatticeBytes ? ctx->coarseLatticeBytes : 128));
+		ctx->coarseLatticeBase = ctx->coarseLatticeBuf.p;
+	}
+	VXB_CUDA(ctx, ctx->coarseMaps.ensure(VXB_MAX_LEVELS));
+	CUtensorMap maps[VXB_MAX_LEVELS];
+	memset(maps, 0, sizeof(maps));
+	for (int l = ctx->coarseLo; l < ctx->levels; ++l)
+	{
+		const cuuint64_t h = n >> l;
+		const cuuint64_t dims[3] = { h + 1, h + 1, h + 1 };
+		const cuuint64_t strides[2] = { h + 16, (h + 16) * (h + 1) };
+		const cuuint32_t box[3] = { VXB_TILE_PITCH, 17, 17 };
+		const cuuint32_t estr[3] = { 1, 1, 1 };
+		const CUresult r = ctx->encodeTiled(&maps[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, ctx->coarseLatticeBase + ctx->coarseLatticeOff[l], dims, strides, box, estr,
+			CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+		if (r != CUDA_SUCCESS)
+		{
+			char buf[128]; snprintf(buf, sizeof(buf), "cuTensorMapEncodeTiled (coarse level %d) failed: CUresult %d", l, (int)r);
+			return fail(ctx, VXB_ERR_CUDA, buf);
+		}
+	}
+	VXB_CUDA(ctx, cudaMemcpy(ctx->coarseMaps.p, maps, sizeof(maps), cudaMemcpyHostToDevice));
+	return VXB_OK;
+}
+
 int buildTensorMap(vxb_context* ctx)
 {
 	int r = encodeTileMap(ctx, &ctx->tmap, ctx->dDist, ctx->n);
@@ -236,6 +305,7 @@ int buildTensorMap(vxb_context* ctx)
 		r = encodeTileMap(ctx, &ctx->tmap1, ctx->latticePtr, (uint32_t)h);
 	}
 	else ctx->tmap1 = ctx->tmap;
+	if (r == VXB_OK) r = buildCoarseLattices(ctx, ctx->shard.on ? ctx->shard.pagesBuf + ctx->shard.pagesBytes + ctx->shard.validBytes : nullptr);
 	return r;
 }
 
@@ -245,8 +315,6 @@ int finishUpload(vxb_context* ctx)
 	if (r == VXB_OK) ctx->haveGrid = true;
 	return r;
 }
-
-size_t blocksAtLevel(uint32_t n, int level) { const size_t nb = (n / 16) >> level; return nb * nb * nb; }
 
 // dirty box of an incremental run, per level (GenerateBlockListForLevel :429-465): the run keeps the caches of the last
 // full run and continues its block ids
@@ -561,8 +629,7 @@ int vxb_create(int device, vxb_context** out)
 		(e = cudaEventCreateWithFlags(&ctx->evJoin, cudaEventDisableTiming)) != cudaSuccess ||
 		(e = cudaEventCreateWithFlags(&ctx->evDir, cudaEventDisableTiming)) != cudaSuccess ||
 		(e = cudaEventCreateWithFlags(&ctx->evVerts, cudaEventDisableTiming)) != cudaSuccess ||
-		(e = cudaEventCreateWithFlags(&ctx->evChunk[0], cudaEventDisableTiming)) != cudaSuccess || (e = cudaEventCreateWithFlags(&ctx->evChunk[1], cudaEventDisableTiming)) != cudaSuccess ||
-		(e = cudaEventCreateWithFlags(&ctx->evChunk[2], cudaEventDisableTiming)) != cudaSuccess || (e = cudaEventCreateWithFlags(&ctx->evChunk[3], cudaEventDisableTiming)) != cudaSuccess)
+		false)
 	{ fail(nullptr, VXB_ERR_CUDA, "stream/event creation", e); vxb_destroy(ctx); return VXB_ERR_CUDA; }
 
 	void* fn = nullptr;
@@ -607,7 +674,8 @@ void vxb_destroy(vxb_context* ctx)
 	releaseShard(ctx);
 	if (ctx->shard.comm && ncclApi().ok) { ncclApi().commDestroy(ctx->shard.comm); ctx->shard.comm = nullptr; }
 	releaseCube(ctx);
-	ctx->mixInfo.release(); ctx->coarseDone.release();
+	ctx->fillColumns.release(); ctx->packSizes.release(); ctx->packFlags.release();
+	ctx->mixInfo.release(); ctx->coarseDone.release(); ctx->coarseLatticeBuf.release(); ctx->coarseMaps.release();
 	ctx->volDist.release(); ctx->volMat.release(); ctx->volBlend.release(); ctx->staging.release(); ctx->packOffsets.release(); ctx->updCoords.release(); ctx->lattice1.release();
 	ctx->scanFlags.release(); ctx->blockInfo.release(); ctx->consPages.release(); ctx->validFlags.release();
 	ctx->cachePages.release(); ctx->worklist.release(); ctx->emitList.release(); ctx->bigList.release(); ctx->transList.release(); ctx->ntScratch.release(); ctx->cellBlock.release(); ctx->vlist.release(); ctx->cellRecs.release(); ctx->blockRecs.release(); ctx->tvlist.release(); ctx->verts.release(); ctx->tverts.release();
@@ -620,7 +688,7 @@ void vxb_destroy(vxb_context* ctx)
 	if (ctx->evJoin) cudaEventDestroy(ctx->evJoin);
 	if (ctx->evDir) cudaEventDestroy(ctx->evDir);
 	if (ctx->evVerts) cudaEventDestroy(ctx->evVerts);
-	for (cudaEvent_t e : ctx->evChunk) if (e) cudaEventDestroy(e);
+	for (cudaEvent_t e : ctx->evChunks) if (e) cudaEventDestroy(e);
 	if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
 	if (ctx->stream) cudaStreamDestroy(ctx->stream);
 	delete ctx;
@@ -686,7 +754,11 @@ int vxb_grid_upload_packed(vxb_context* ctx, const void* blob, size_t size)
 	const size_t tableBytes = blocks * 12;
 	if (size < 16 + tableBytes) return fail(ctx, VXB_ERR_ARGUMENT, "vxb_grid_upload_packed: truncated size table");
 	cudaSetDevice(ctx->device);
-	int r = ensureGridStorage(ctx, n);
+	// a context with a cube (sharded runs) receives only the pieces this rank backs: the same blob on every rank, each
+	// copies and decodes the byte ranges of its own block layers
+	const bool pieces = ctx->cube.active;
+	if (pieces && ctx->cube.n != n) return fail(ctx, VXB_ERR_ARGUMENT, "vxb_grid_upload_packed: the blob's grid size differs from the cube's");
+	int r = pieces ? VXB_OK : ensureGridStorage(ctx, n);
 	if (r != VXB_OK) return r;
 	VXB_CUDA(ctx, ctx->staging.ensure(size + 16));
 	VXB_CUDA(ctx, ctx->packOffsets.ensure(blocks));
@@ -732,24 +804,44 @@ int vxb_grid_upload_packed(vxb_context* ctx, const void* blob, size_t size)
 		return fail(ctx, VXB_ERR_ARGUMENT, corrupt ? "vxb_grid_upload_packed: corrupt size table or block flags" : "vxb_grid_upload_packed: truncated block data");
 	}
 	VXB_CUDA(ctx, cudaMemcpyAsync(ctx->packOffsets.p, hostOffsets, blocks * sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream));
-	const int chunks = nb >= 16 ? 4 : 1;
-	const size_t groupsPerLayer = ((nb + 7) / 8) * nb;
-	for (int c = 0; c < chunks; ++c)
+	std::vector<std::pair<size_t, size_t> > ranges; // block layers [first, second)
+	if (pieces)
 	{
-		const size_t layer0 = nb * c / chunks, layer1 = nb * (c + 1) / chunks;
+		const size_t g = ctx->cube.groupPlanes / 16;
+		for (size_t p = ctx->cube.rank; p < ctx->cube.pieces; p += ctx->cube.world) ranges.push_back(std::make_pair(p * g, (p + 1) * g));
+	}
+	else
+	{
+		const int chunks = nb >= 16 ? 4 : 1;
+		for (int c = 0; c < chunks; ++c) ranges.push_back(std::make_pair(nb * c / chunks, nb * (c + 1) / chunks));
+	}
+	while (ctx->evChunks.size() < ranges.size())
+	{
+		cudaEvent_t ev = nullptr;
+		VXB_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+		ctx->evChunks.push_back(ev);
+	}
+	unsigned char* const outDist = pieces ? reinterpret_cast<unsigned char*>(ctx->cube.va[0]) : ctx->volDist.p;
+	unsigned char* const outMat = pieces ? reinterpret_cast<unsigned char*>(ctx->cube.va[1]) : ctx->volMat.p;
+	unsigned char* const outBlend = pieces ? reinterpret_cast<unsigned char*>(ctx->cube.va[2]) : ctx->volBlend.p;
+	const size_t groupsPerLayer = ((nb + 7) / 8) * nb;
+	for (size_t c = 0; c < ranges.size(); ++c)
+	{
+		const size_t layer0 = ranges[c].first, layer1 = ranges[c].second;
 		const unsigned long long byte0 = hostOffsets[layer0 * nb * nb], byte1 = (layer1 == nb) ? off : hostOffsets[layer1 * nb * nb];
 		VXB_CUDA(ctx, cudaMemcpyAsync(ctx->staging.p + byte0, bytes + byte0, (size_t)(byte1 - byte0), cudaMemcpyHostToDevice, ctx->stream));
-		VXB_CUDA(ctx, cudaEventRecord(ctx->evChunk[c], ctx->stream));
-		VXB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->evChunk[c], 0));
+		VXB_CUDA(ctx, cudaEventRecord(ctx->evChunks[c], ctx->stream));
+		VXB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->evChunks[c], 0));
 		vxb_unpack_rle_kernel<<<(unsigned)(groupsPerLayer * (layer1 - layer0)), VXB_THREADS, 0, ctx->stream2>>>(ctx->staging.p, ctx->packOffsets.p,
-			reinterpret_cast<const unsigned int*>(ctx->staging.p + 16), ctx->volDist.p, ctx->volMat.p, ctx->volBlend.p, (int)n, (int)layer0);
+			reinterpret_cast<const unsigned int*>(ctx->staging.p + 16), outDist, outMat, outBlend, (int)n, (int)layer0);
 	}
 	VXB_CUDA(ctx, cudaGetLastError());
 	VXB_CUDA(ctx, cudaEventRecord(ctx->evJoin, ctx->stream2));
 	VXB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->evJoin, 0));
 	VXB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	const double msKernel = msSince(t0);
-	r = finishUpload(ctx);
+	if (pieces) { ctx->haveResult = false; ctx->haveFullRun = false; r = VXB_OK; }
+	else r = finishUpload(ctx);
 	if (trace) fprintf(stderr, "[vxb200] upload_packed: offsets ready at %.3f ms, copy + decode done at %.3f ms, maps at %.3f ms\n", msTable, msKernel, msSince(t0));
 	return r;
 }
@@ -844,6 +936,157 @@ int vxb_pack_dense(uint32_t n, const int8_t* dist, const uint8_t* mat, const uin
 	return VXB_OK;
 }
 
+int vxb_grid_fill(vxb_context* ctx, uint32_t n, const vxb_surface* surface, const float start[3], float step)
+{
+	if (!ctx) return VXB_ERR_ARGUMENT;
+	if (!validSize(n) || !surface || surface->kind > VXB_SURFACE_TERRAIN) return fail(ctx, VXB_ERR_ARGUMENT, "vxb_grid_fill: bad size or surface");
+	cudaSetDevice(ctx->device);
+	const bool pieces = ctx->cube.active;
+	if (pieces && ctx->cube.n != n) return fail(ctx, VXB_ERR_ARGUMENT, "vxb_grid_fill: n differs from the cube's");
+	int r = pieces ? VXB_OK : ensureGridStorage(ctx, n);
+	if (r != VXB_OK) return r;
+	VxbFillArgs* args = new VxbFillArgs;
+	memset(args, 0, sizeof(*args));
+	args->surface = *surface;
+	vxs_permutation(surface->seed, args->perm);
+	for (int k = 0; k < 3; ++k) args->start[k] = start ? start[k] : 0.f;
+	args->step = step;
+	args->n = (int)n;
+	signed char* dDist = const_cast<signed char*>(reinterpret_cast<const signed char*>(pieces ? ctx->dDist : reinterpret_cast<const int8_t*>(ctx->volDist.p)));
+	unsigned char* dMat = pieces ? const_cast<unsigned char*>(ctx->dMat) : ctx->volMat.p;
+	unsigned char* dBlend = pieces ? const_cast<unsigned char*>(ctx->dBlend) : ctx->volBlend.p;
+	if (surface->kind == VXB_SURFACE_TERRAIN)
+	{
+		if (ctx->fillColumns.ensure((size_t)n * n * 4) != cudaSuccess) { delete args; return fail(ctx, VXB_ERR_CUDA, "vxb_grid_fill: column buffer allocation failed"); }
+		args->columns = ctx->fillColumns.p;
+		vxb_fill_columns_kernel<<<(unsigned)(((size_t)n * n + 255) / 256), 256, 0, ctx->stream>>>(*args);
+	}
+	std::vector<std::pair<int, int> > ranges;
+	if (pieces) for (uint32_t p = ctx->cube.rank; p < ctx->cube.pieces; p += ctx->cube.world) ranges.push_back(std::make_pair((int)(p * ctx->cube.groupPlanes), (int)((p + 1) * ctx->cube.groupPlanes)));
+	else ranges.push_back(std::make_pair(0, (int)n));
+	for (const auto& rg : ranges)
+	{
+		args->z0 = rg.first; args->z1 = rg.second;
+		vxb_fill_kernel<<<(unsigned)ctx->smCount * 16, 256, 0, ctx->stream>>>(*args, dDist, dMat, dBlend);
+	}
+	const cudaError_t e = cudaGetLastError();
+	const cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
+	delete args;
+	if (e != cudaSuccess || e2 != cudaSuccess) return fail(ctx, VXB_ERR_CUDA, "vxb_grid_fill", e != cudaSuccess ? e : e2);
+	if (pieces) { ctx->haveResult = false; ctx->haveFullRun = false; return VXB_OK; }
+	return finishUpload(ctx);
+}
+
+namespace
+{
+// touched block range + the box the reference returns (VoxelGrid.cpp:479-487 / :577-584: "DX-style" Y-up)
+int prepareEdit(vxb_context* ctx, const char* who, const float position[3], const float extents[3], VxbEditArgs& a, float outMin[3], float outMax[3])
+{
+	if (!ctx->haveGrid || !ctx->ownsGrid) return fail(ctx, VXB_ERR_STATE, who);
+	const float n = (float)ctx->n;
+	memset(&a, 0, sizeof(a));
+	a.n = (int)ctx->n;
+	const int nb = (int)(ctx->n / 16);
+	bool any = true;
+	for (int k = 0; k < 3; ++k)
+	{
+		a.position[k] = position[k]; a.extents[k] = extents[k];
+		const float lo = position[k] - extents[k] / 2.f, hi = lo + extents[k];
+		// blocks whose section is non-empty: the ones the half-open range [lo, hi) clipped to the grid reaches
+		const float clo = lo < 0.f ? 0.f : lo, chi = hi > n ? n : hi;
+		if (!(chi > clo)) any = false;
+		int b0 = (int)floorf(clo / 16.f), b1 = (int)ceilf(chi / 16.f);
+		if (b0 < 0) b0 = 0;
+		if (b1 > nb) b1 = nb;
+		a.b0[k] = b0; a.bn[k] = b1 > b0 ? b1 - b0 : 0;
+		if (a.bn[k] == 0) any = false;
+	}
+	const float icp[3] = { position[0] - extents[0] / 2.f, position[1] - extents[1] / 2.f, position[2] - extents[2] / 2.f };
+	const float gs[3] = { std::max(0.f, icp[0]), std::max(0.f, icp[2]), std::max(0.f, icp[1]) };
+	if (outMin) { outMin[0] = gs[0]; outMin[1] = gs[1]; outMin[2] = gs[2]; }
+	if (outMax) { outMax[0] = std::min(n, gs[0] + extents[0]); outMax[1] = std::min(n, gs[1] + extents[2]); outMax[2] = std::min(n, gs[2] + extents[1]); }
+	return any ? VXB_OK : 1; // 1 = nothing to touch
+}
+}
+
+int vxb_grid_inject_surface(vxb_context* ctx, const float position[3], const float extents[3], const vxb_surface* surface, int type, float outMin[3], float outMax[3])
+{
+	if (!ctx || !position || !extents || !surface) return VXB_ERR_ARGUMENT;
+	if (type < 0 || type > 2 || surface->kind > VXB_SURFACE_TERRAIN) return fail(ctx, VXB_ERR_ARGUMENT, "vxb_grid_inject_surface: bad injection type or surface");
+	cudaSetDevice(ctx->device);
+	VxbEditArgs a;
+	const int r = prepareEdit(ctx, "vxb_grid_inject_surface: needs a context-owned grid (upload or fill)", position, extents, a, outMin, outMax);
+	if (r < 0) return r;
+	if (r == 1) return VXB_OK;
+	a.surface = *surface; a.type = type;
+	if (surface->kind == VXB_SURFACE_TERRAIN) vxs_permutation(surface->seed, a.perm);
+	vxb_inject_surface_kernel<<<(unsigned)(a.bn[0] * a.bn[1] * a.bn[2]), 256, 0, ctx->stream>>>(a, reinterpret_cast<signed char*>(ctx->volDist.p));
+	VXB_CUDA(ctx, cudaGetLastError());
+	ctx->haveResult = false;
+	return VXB_OK;
+}
+
+int vxb_grid_inject_material(vxb_context* ctx, const float position[3], const float extents[3], uint32_t material, int addSubtractBlend, float outMin[3], float outMax[3])
+{
+	if (!ctx || !position || !extents) return VXB_ERR_ARGUMENT;
+	if (material > 255) return fail(ctx, VXB_ERR_ARGUMENT, "vxb_grid_inject_material: material id > 255");
+	cudaSetDevice(ctx->device);
+	VxbEditArgs a;
+	const int r = prepareEdit(ctx, "vxb_grid_inject_material: needs a context-owned grid (upload or fill)", position, extents, a, outMin, outMax);
+	if (r < 0) return r;
+	if (r == 1) return VXB_OK;
+	a.material = (int)material; a.addBlend = addSubtractBlend ? 1 : 0;
+	vxb_inject_material_kernel<<<(unsigned)(a.bn[0] * a.bn[1] * a.bn[2]), 256, 0, ctx->stream>>>(a, ctx->volMat.p, ctx->volBlend.p);
+	VXB_CUDA(ctx, cudaGetLastError());
+	ctx->haveResult = false;
+	return VXB_OK;
+}
+
+int vxb_grid_pack(vxb_context* ctx, void* out, size_t capacity, size_t* written)
+{
+	if (!ctx || !out) return VXB_ERR_ARGUMENT;
+	if (!ctx->haveGrid) return fail(ctx, VXB_ERR_STATE, "vxb_grid_pack: no grid");
+	cudaSetDevice(ctx->device);
+	const uint32_t n = ctx->n;
+	const size_t nb = n / 16, blocks = nb * nb * nb;
+	const size_t head = 16 + blocks * 12;
+	if (capacity < head) return fail(ctx, VXB_ERR_CAPACITY, "vxb_grid_pack: capacity below the header + size table");
+	VXB_CUDA(ctx, ctx->packSizes.ensure(blocks * 3));
+	VXB_CUDA(ctx, ctx->packFlags.ensure(blocks));
+	VXB_CUDA(ctx, ctx->packOffsets.ensure(blocks + 1));
+	const unsigned char* d = reinterpret_cast<const unsigned char*>(ctx->dDist);
+	vxb_pack_sizes_kernel<<<(unsigned)blocks, VXB_THREADS, 0, ctx->stream>>>(d, ctx->dMat, ctx->dBlend, (int)n, ctx->packSizes.p, ctx->packFlags.p);
+	vxb_pack_offsets_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->packSizes.p, ctx->packOffsets.p, blocks, (unsigned long long)head);
+	unsigned long long total = 0;
+	VXB_CUDA(ctx, cudaMemcpyAsync(&total, ctx->packOffsets.p + blocks, sizeof(total), cudaMemcpyDeviceToHost, ctx->stream));
+	VXB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	if (total > capacity) return fail(ctx, VXB_ERR_CAPACITY, "vxb_grid_pack: capacity too small (vxb_pack_dense_bound is always enough)");
+	VXB_CUDA(ctx, ctx->staging.ensure((size_t)total + 16));
+	vxb_pack_write_kernel<<<(unsigned)blocks, VXB_THREADS, 0, ctx->stream>>>(d, ctx->dMat, ctx->dBlend, (int)n, ctx->packFlags.p, ctx->packOffsets.p, ctx->staging.p);
+	VXB_CUDA(ctx, cudaGetLastError());
+	unsigned char* bytes = static_cast<unsigned char*>(out);
+	const uint32_t header[4] = { 1u, n, n, n };
+	memcpy(bytes, header, 16);
+	VXB_CUDA(ctx, cudaMemcpyAsync(bytes + 16, ctx->packSizes.p, blocks * 12, cudaMemcpyDeviceToHost, ctx->stream));
+	VXB_CUDA(ctx, cudaMemcpyAsync(bytes + head, ctx->staging.p + head, (size_t)total - head, cudaMemcpyDeviceToHost, ctx->stream));
+	VXB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	if (written) *written = (size_t)total;
+	return VXB_OK;
+}
+
+int vxb_grid_download_dense(vxb_context* ctx, int8_t* dist, uint8_t* mat, uint8_t* blend)
+{
+	if (!ctx) return VXB_ERR_ARGUMENT;
+	if (!ctx->haveGrid) return fail(ctx, VXB_ERR_STATE, "vxb_grid_download_dense: no grid");
+	cudaSetDevice(ctx->device);
+	const size_t vol = (size_t)ctx->n * ctx->n * ctx->n;
+	if (dist) VXB_CUDA(ctx, cudaMemcpyAsync(dist, ctx->dDist, vol, cudaMemcpyDeviceToHost, ctx->stream));
+	if (mat) VXB_CUDA(ctx, cudaMemcpyAsync(mat, ctx->dMat, vol, cudaMemcpyDeviceToHost, ctx->stream));
+	if (blend) VXB_CUDA(ctx, cudaMemcpyAsync(blend, ctx->dBlend, vol, cudaMemcpyDeviceToHost, ctx->stream));
+	VXB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	return VXB_OK;
+}
+
 int vxb_grid_set_device(vxb_context* ctx, uint32_t n, const int8_t* dDist, const uint8_t* dMat, const uint8_t* dBlend)
 {
 	if (!ctx) return VXB_ERR_ARGUMENT;
@@ -920,9 +1163,7 @@ static int runPolygonize(vxb_context* ctx, uint32_t maxLevels, uint32_t flags, c
 	size_t validOff[VXB_MAX_LEVELS], cacheOff[VXB_MAX_LEVELS], mixOff[VXB_MAX_LEVELS];
 	VxbDev dev;
 	memset(&dev, 0, sizeof(dev));
-	// coarse levels: from the first level with <= 4096 blocks (but not below 2) everything runs in one launch
-	int coarseLo = 2;
-	while (coarseLo < levels && blocksAtLevel(n, coarseLo) > 4096) ++coarseLo;
+	const int coarseLo = ctx->coarseLo;
 	size_t coarseBlocks = 0;
 	for (int l = 0; l < levels; ++l)
 	{
@@ -965,6 +1206,11 @@ static int runPolygonize(vxb_context* ctx, uint32_t maxLevels, uint32_t flags, c
 		dev.mixInfo[l] = ctx->mixInfo.p + mixOff[l];
 	}
 	dev.coarseLo = coarseLo; dev.coarseDone = ctx->coarseDone.p;
+	VxbCoarseLattices scanLat;
+	memset(&scanLat, 0, sizeof(scanLat));
+	scanLat.lo = coarseLo; scanLat.levels = levels;
+	for (int l = coarseLo; l < levels; ++l) { dev.coarseLattice[l] = ctx->coarseLatticeBase + ctx->coarseLatticeOff[l]; scanLat.p[l] = dev.coarseLattice[l]; }
+	dev.coarseMaps = ctx->coarseMaps.p;
 	dev.worklist = ctx->worklist.p;
 	dev.records = ctx->records.p; dev.rcap = (unsigned)totalBlocks;
 	dev.counters = ctx->counters.p; dev.lut = ctx->lut.p;
@@ -982,6 +1228,8 @@ static int runPolygonize(vxb_context* ctx, uint32_t maxLevels, uint32_t flags, c
 		}
 	VxbPeers peers;
 	memset(&peers, 0, sizeof(peers));
+	VxbPeerLattices peerLat;
+	memset(&peerLat, 0, sizeof(peerLat));
 	if (sharded)
 	{
 		if (!sh.on) return fail(ctx, VXB_ERR_STATE, "vxb_polygonize_sharded: call vxb_shard_configure first");
@@ -995,8 +1243,11 @@ static int runPolygonize(vxb_context* ctx, uint32_t maxLevels, uint32_t flags, c
 		{
 			if (p == sh.rank) continue;
 			if (!sh.peerSet[p]) return fail(ctx, VXB_ERR_STATE, "vxb_polygonize_sharded: a peer's page buffer is not set (vxb_shard_set_peer / vxb_shard_import)");
-			peers.pages[peers.count] = sh.peerPages[p]; peers.valid[peers.count] = sh.peerValid[p]; ++peers.count;
+			peers.pages[peers.count] = sh.peerPages[p]; peers.valid[peers.count] = sh.peerValid[p];
+			peerLat.base[peers.count] = sh.peerLattice[p];
+			++peers.count;
 		}
+		peerLat.count = peers.count;
 		if (shardPhase == 3 && (!sh.comm || !ncclApi().ok)) return fail(ctx, VXB_ERR_STATE, "vxb_polygonize_sharded: phase 3 needs vxb_shard_nccl_init");
 	}
 	const int scanWorld = sharded ? (int)sh.world : 1, scanRank = sharded ? (int)sh.rank : 0, scanGroup = sharded ? (int)sh.groupLayers : (int)nb0;
@@ -1037,9 +1288,15 @@ static int runPolygonize(vxb_context* ctx, uint32_t maxLevels, uint32_t flags, c
 			const int perCta = nb0 >= 32 ? 32 : 8;
 			const dim3 grid((unsigned)((nb0 + perCta - 1) / perCta), (unsigned)nb0, (unsigned)myLayers);
 			timer.begin(0);
-			if (perCta == 32) vxb_scan_kernel<32><<<grid, VXB_THREADS, 0, st>>>(ctx->dDist, (int)n, ctx->scanFlags.p, ctx->haveLattice1 ? ctx->latticePtr : nullptr, scanGroup, scanWorld, scanRank);
-			else vxb_scan_kernel<8><<<grid, VXB_THREADS, 0, st>>>(ctx->dDist, (int)n, ctx->scanFlags.p, ctx->haveLattice1 ? ctx->latticePtr : nullptr, scanGroup, scanWorld, scanRank);
+			if (perCta == 32) vxb_scan_kernel<32><<<grid, VXB_THREADS, 0, st>>>(ctx->dDist, (int)n, ctx->scanFlags.p, ctx->haveLattice1 ? ctx->latticePtr : nullptr, scanLat, scanGroup, scanWorld, scanRank);
+			else vxb_scan_kernel<8><<<grid, VXB_THREADS, 0, st>>>(ctx->dDist, (int)n, ctx->scanFlags.p, ctx->haveLattice1 ? ctx->latticePtr : nullptr, scanLat, scanGroup, scanWorld, scanRank);
 			timer.end(); ++launches; ++ctx->kindLaunches[0];
+			if (sharded && peerLat.count && coarseLo < levels)
+			{
+				// the lattice planes of my layers -> every peer (ordered before the peers' coarse levels by the exchanges)
+				vxb_publish_lattice_kernel<<<(unsigned)ctx->smCount, VXB_THREADS, 0, st>>>(dev, peerLat, ctx->coarseLatticeBase);
+				++launches;
+			}
 			const size_t mine = myLayers * nb0 * nb0;
 			const unsigned g2 = (unsigned)std::min<size_t>((mine + 255) / 256, (size_t)ctx->smCount * 8);
 			timer.begin(1);
@@ -1180,10 +1437,11 @@ static int runPolygonize(vxb_context* ctx, uint32_t maxLevels, uint32_t flags, c
 		bool replayed = false;
 		if ((shardPhase == -1 || shardPhase == 3) && !incremental && !kernelTimes && !ctx->graphDisabled)
 		{
-			std::vector<unsigned char> key(sizeof(VxbDev) + sizeof(VxbPeers) + 3 * sizeof(CUtensorMap) + 64, 0);
+			std::vector<unsigned char> key(sizeof(VxbDev) + sizeof(VxbPeers) + sizeof(VxbPeerLattices) + 3 * sizeof(CUtensorMap) + 64, 0);
 			unsigned char* k = key.data();
 			memcpy(k, &dev, sizeof(VxbDev)); k += sizeof(VxbDev);
 			memcpy(k, &peers, sizeof(VxbPeers)); k += sizeof(VxbPeers);
+			memcpy(k, &peerLat, sizeof(VxbPeerLattices)); k += sizeof(VxbPeerLattices);
 			const CUtensorMap* maps[3] = { &ctx->tmap, &ctx->tmap1, &ctx->tmapDist19 };
 			for (const CUtensorMap* mp : maps) { memcpy(k, mp, sizeof(CUtensorMap)); k += sizeof(CUtensorMap); }
 			const void* ptrs[4] = { ctx->dDist, ctx->scanFlags.p, ctx->blockInfo.p, ctx->haveLattice1 ? ctx->latticePtr : nullptr };
@@ -1337,8 +1595,7 @@ int vxb_shard_configure(vxb_context* ctx, uint32_t rank, uint32_t world, uint32_
 		return fail(ctx, VXB_ERR_ARGUMENT, "vxb_shard_configure: group_planes must be a multiple of 32 planes that divides n into a multiple of `world` pieces");
 	if (ctx->cube.active && (ctx->cube.groupPlanes != groupPlanes || ctx->cube.world != world || ctx->cube.rank != rank))
 		return fail(ctx, VXB_ERR_ARGUMENT, "vxb_shard_configure: rank / world / group_planes differ from the cube's");
-	int coarseLo = 2;
-	while (coarseLo < ctx->levels && blocksAtLevel(n, coarseLo) > 4096) ++coarseLo;
+	const int coarseLo = coarseLoFor(n, ctx->levels);
 	if (coarseLo >= ctx->levels) return fail(ctx, VXB_ERR_ARGUMENT, "vxb_shard_configure: the grid is too small to shard (n >= 64)");
 	cudaSetDevice(ctx->device);
 	releaseShard(ctx);
@@ -1351,7 +1608,11 @@ int vxb_shard_configure(vxb_context* ctx, uint32_t rank, uint32_t world, uint32_
 	VXB_CUDA(ctx, cudaMemset(sh.barrierBuf.p, 0, 64));
 	sh.pagesBytes = sb * 4096 * sizeof(unsigned short);
 	sh.validBytes = (sb + 255) & ~(size_t)255;
-	sh.bufBytes = sh.pagesBytes + sh.validBytes;
+	{
+		size_t offs[VXB_MAX_LEVELS];
+		sh.latticeBytes = coarseLatticeLayout(n, ctx->levels, offs);
+	}
+	sh.bufBytes = sh.pagesBytes + sh.validBytes + sh.latticeBytes;
 	const VmmApi& api = vmmApi();
 	if (ctx->cube.active && api.ok)
 	{
@@ -1373,10 +1634,10 @@ int vxb_shard_configure(vxb_context* ctx, uint32_t rank, uint32_t world, uint32_
 		VXB_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&sh.pagesBuf), sh.bufBytes));
 	}
 	sh.on = true;
-	if (!ctx->cube.active && !ctx->latticeOff)
+	// virtual ranks over one shared upload: no shared even-lattice copy => level 1 gathers its tiles.  The coarse levels'
+	// lattices move into the buffer the peers map (buildTensorMap -> buildCoarseLattices).
+	if (!ctx->cube.active) ctx->latticeOff = true;
 	{
-		// virtual ranks over one shared upload: no shared even-lattice copy => level 1 gathers its tiles
-		ctx->latticeOff = true;
 		const int r = buildTensorMap(ctx);
 		if (r != VXB_OK) return r;
 	}
@@ -1412,6 +1673,7 @@ int vxb_shard_set_peer(vxb_context* ctx, uint32_t peer, void* pages, void* valid
 	if (!sh.on || peer >= sh.world || peer == sh.rank || !pages || !valid) return fail(ctx, VXB_ERR_ARGUMENT, "vxb_shard_set_peer: not configured, or bad peer / pointer");
 	sh.peerPages[peer] = static_cast<unsigned short*>(pages);
 	sh.peerValid[peer] = static_cast<unsigned char*>(valid);
+	sh.peerLattice[peer] = static_cast<unsigned char*>(pages) + sh.pagesBytes + sh.validBytes; // one buffer: pages | valid | lattices
 	sh.peerSet[peer] = true;
 	return VXB_OK;
 }

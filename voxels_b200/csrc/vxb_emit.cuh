@@ -249,6 +249,13 @@ __global__ void __launch_bounds__(VXB_THREADS, (MODE == 0 ? 3 : (MODE == 2 ? 3 :
 					__threadfence();
 				}
 				s.take = vxb_coarse_block_needed(d, level, bx, by, bz) ? 1u : 0u;
+				if (s.take)
+				{
+					// the block's 17^3 samples: one TMA box of the level's lattice (far-edge entries included, no fix-up)
+					vxb_fence_proxy_async();
+					vxb_mbar_expect_tx(&s.mbar[0], VXB_TILE_BYTES);
+					vxb_tma_load_3d(s.tiles[0], d.coarseMaps + level, bx * 16, by * 16, bz * 16, &s.mbar[0]);
+				}
 			}
 			__syncthreads();
 			if (!s.take)
@@ -300,6 +307,12 @@ __global__ void __launch_bounds__(VXB_THREADS, (MODE == 0 ? 3 : (MODE == 2 ? 3 :
 				}
 			}
 			tile = tileRaw + ((bz * 16 - hsz) * 19 + (by * 16 - hsy)) * VXB_DTILE_PITCH + (bx * 16 - hsx);
+		}
+		else if (MODE == 2)
+		{
+			vxb_mbar_wait(&s.mbar[0], phaseBits & 1u);
+			phaseBits ^= 1u;
+			tile = tileRaw;
 		}
 		else
 		{

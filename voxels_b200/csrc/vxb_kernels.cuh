@@ -108,6 +108,11 @@ struct VxbDev
 	unsigned char* mixInfo[VXB_MAX_LEVELS];
 	// coarse levels (one launch, vxb_block_kernel<2>): levels [coarseLo, computed); a block waits for the done flags of its children
 	int coarseLo;
+	// their sample lattices: level l holds the samples at multiples of 2^l plus, per axis, one extra entry for the clamped
+	// far-edge coordinate n (= the sample at n - 1, :1037-1047): (h + 1)^3 entries, h = n >> l, rows of h + 16 bytes.  Written by
+	// vxb_scan_kernel on its way through the volume; a 17^3 tile of any coarse block is ONE TMA box of its level's map.
+	unsigned char* coarseLattice[VXB_MAX_LEVELS];
+	const CUtensorMap* coarseMaps;             // [VXB_MAX_LEVELS], device memory
 	unsigned char* coarseDone;                 // [coarseBase[l] + coordId], zeroed per run
 	unsigned int coarseBase[VXB_MAX_LEVELS];
 	// sharded runs (vxb_shard_*): the z-axis is cut into groups of shardLayers level-0 block layers, dealt cyclically to
@@ -229,9 +234,42 @@ __device__ __forceinline__ unsigned vxb_zero_bytes(unsigned w) // 0x80 in every 
 // J = x-adjacent blocks per CTA = lanes per row: a load instruction of a warp covers (32 / (32/J))... J * 16 contiguous
 // bytes.  J = 32 (grids of >= 32 blocks per row): every warp-wide load is 512 contiguous bytes, which keeps DRAM pages open
 // longer than the 128-byte pieces of J = 8 (small grids).
+// the coarse levels' lattices (VxbDev::coarseLattice), as a scan-kernel argument
+struct VxbCoarseLattices
+{
+	unsigned char* p[VXB_MAX_LEVELS];
+	int lo, levels; // levels [lo, levels) have a lattice (lo >= 2)
+};
+
+// One 16-byte row (global y, z; samples x = bx * 16 .. + 15) -> its entries of the coarse lattices.  Rare: only rows whose y
+// and z are multiples of 2^lo or the last coordinate of the grid get here.
+__device__ __noinline__ void vxb_scan_coarse_row(const VxbCoarseLattices* __restrict__ latp, int n, int bx, int y, int z, unsigned w0, unsigned w1, unsigned w2, unsigned w3)
+{
+	const VxbCoarseLattices& lat = *latp;
+	const unsigned w[4] = { w0, w1, w2, w3 };
+	for (int l = lat.lo; l < lat.levels; ++l)
+	{
+		const int m = 1 << l, h = n >> l, pitch = h + 16;
+		const int ly[2] = { (y & (m - 1)) == 0 ? (y >> l) : -1, y == n - 1 ? h : -1 };
+		const int lz[2] = { (z & (m - 1)) == 0 ? (z >> l) : -1, z == n - 1 ? h : -1 };
+		for (int a = 0; a < 2; ++a) for (int b = 0; b < 2; ++b)
+		{
+			if (ly[a] < 0 || lz[b] < 0) continue;
+			unsigned char* out = lat.p[l] + ((size_t)lz[b] * (h + 1) + ly[a]) * pitch;
+			for (int k = 0; k < 16; k += (m < 16 ? m : 16))
+			{
+				const int x = bx * 16 + k;
+				if ((x & (m - 1)) == 0) out[x >> l] = (unsigned char)(w[k >> 2] >> ((k & 3) * 8));
+			}
+			if (bx * 16 + 15 == n - 1) out[h] = (unsigned char)(w[3] >> 24);
+		}
+	}
+}
+
 template <int J>
 __global__ void __launch_bounds__(VXB_THREADS, (J == 32 ? 3 : 4)) vxb_scan_kernel(const signed char* __restrict__ dist, int n, unsigned int* __restrict__ scanFlags,
 	unsigned char* __restrict__ lattice1 /* (n/2)^3: the samples at even coordinates = the level-1 lattice, or null */,
+	const __grid_constant__ VxbCoarseLattices coarse,
 	int groupLayers, int world, int rank /* sharded runs: blockIdx.z counts this rank's layers (groups of groupLayers block layers,
 	                                        dealt cyclically to the ranks); unsharded: world = 1 */)
 {
@@ -267,6 +305,11 @@ __global__ void __launch_bounds__(VXB_THREADS, (J == 32 ? 3 : 4)) vxb_scan_kerne
 				const int y = (RG == 32) ? y0 : ((i & 1) * 8 + y0), z = (RG == 32) ? (z0 + 2 * i + batch * 16) : ((i >> 1) + batch * 4);
 				const unsigned w[4] = { rows[i].x, rows[i].y, rows[i].z, rows[i].w };
 				const bool even = !((y | z) & 1);
+				if (coarse.lo < coarse.levels)
+				{
+					const int gy = by * 16 + y, gz = bz * 16 + z, mm = (1 << coarse.lo) - 1;
+					if (((gy & mm) == 0 || gy == n - 1) && ((gz & mm) == 0 || gz == n - 1)) vxb_scan_coarse_row(&coarse, n, bx0 + j, gy, gz, rows[i].x, rows[i].y, rows[i].z, rows[i].w);
+				}
 				// a row of 16 equal bytes (the common case away from the surface) has no value change inside it
 				const unsigned splat = (w[0] & 0xFFu) * 0x01010101u;
 				const bool flat = (w[0] == splat) & (w[1] == splat) & (w[2] == splat) & (w[3] == splat);
@@ -685,6 +728,36 @@ struct VxbPeers
 	unsigned char* valid[8];
 	int count;
 };
+
+// Sharded runs: the planes of the coarse levels' lattices this rank wrote while scanning its pieces go to every peer
+// (the lattices live in the buffer the peers map; byte offsets are the same on every rank).
+struct VxbPeerLattices
+{
+	unsigned char* base[8];    // the peers' lattice areas
+	int count;
+};
+
+__global__ void __launch_bounds__(VXB_THREADS) vxb_publish_lattice_kernel(const VxbDev d, const VxbPeerLattices peers, unsigned char* myBase)
+{
+	const int planesPerPiece = d.shardLayers * 16;
+	for (int l = d.coarseLo; l < d.levels; ++l)
+	{
+		const int h = d.n >> l, pitch = h + 16;
+		const size_t planeBytes = (size_t)pitch * (h + 1);
+		for (int lz = blockIdx.x; lz <= h; lz += gridDim.x)
+		{
+			const int z = min(lz << l, d.n - 1);
+			if ((z / planesPerPiece) % d.shardWorld != d.shardRank) continue;
+			const uint4* src = reinterpret_cast<const uint4*>(d.coarseLattice[l] + planeBytes * lz);
+			const size_t off = (size_t)(d.coarseLattice[l] - myBase) + planeBytes * lz;
+			for (size_t i = threadIdx.x; i < planeBytes / 16; i += VXB_THREADS)
+			{
+				const uint4 v = src[i];
+				for (int p = 0; p < peers.count; ++p) reinterpret_cast<uint4*>(peers.base[p] + off)[i] = v;
+			}
+		}
+	}
+}
 
 __global__ void __launch_bounds__(VXB_THREADS) vxb_publish_kernel(const VxbDev d, const VxbPeers peers)
 {
