@@ -203,11 +203,6 @@ def compare_with_reference(ref, surface, result, stats):
     return {"checked": True, "levels": int(levels), "mismatches": len(problems), "first": problems[:3]}
 
 
-def terrain_config4(sg, synth, dev):
-    for z0, z1, out in sg.piece_tensors():
-        synth.terrain(sg.n, dev, z_range=(z0, z1), out=out)
-
-
 def main():
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -221,10 +216,14 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        from voxels_b200 import synth
-        gen_dev = "cuda:0" if torch.cuda.is_available() else "cpu"
+        import harness
+        from voxels_b200 import capi
         t0 = time.time()
-        dist, mat, blend = (t.cpu().numpy() for t in synth.terrain(n, gen_dev))
+        if not os.path.exists(harness.REF_LIB):
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libvxh_ref.so not built (make -C oracle ref needs the reference checkout)"}))
+            return 0
+        # the same bytes the b200 arm fills on the device: the built-in terrain evaluated on the host (all threads)
+        dist, mat, blend = harness.reference().builtin_dense(n, capi.Surface.terrain(n))
         value, info, _, _, _ = reference_run(n, args.steps, args.warmup, dist, mat, blend)
         if value is None:
             print(json.dumps({"impl": "reference", "unavailable": info["unavailable"]}))
@@ -255,7 +254,7 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     import voxels_b200
-    from voxels_b200 import synth
+    from voxels_b200 import capi
     from voxels_b200.dist import Ranks, ShardedGrid, tile_origin, whole_job_throughput
     ranks = Ranks("nccl", dev)
     flags = voxels_b200.FLAG_NO_TRANSITIONS if args.no_transitions else 0
@@ -292,10 +291,10 @@ def main():
 
     if world == 1:
         # ------------------------------------------------------------ N = 1: resident grid, one CUDA graph per step
-        dist, mat, blend = synth.terrain(n, dev)
-        torch.cuda.synchronize()
         ctx = voxels_b200.Context(local_rank)
-        ctx.set_device_grid(n, dist.data_ptr(), mat.data_ptr(), blend.data_ptr(), keep=(dist, mat, blend))
+        t_fill = time.perf_counter()
+        ctx.fill(n, capi.Surface.terrain(n))   # Grid::Create(n, n, n, 0, 0, 0, 1, &terrain) on the device
+        extra["grid_fill_ms"] = 1e3 * (time.perf_counter() - t_fill)
         stream = torch.cuda.ExternalStream(ctx.L.vxb_stream(ctx.h), device=dev)
         info = None
 
@@ -369,9 +368,10 @@ def main():
 
         # -- e2e: host buffers through the C ABI, H2D + D2H inside the timed region --
         if not args.no_e2e:
-            h_dist, h_mat, h_blend = (t.cpu() for t in (dist, mat, blend))
-            packed = voxels_b200.pack_dense(h_dist.numpy(), h_mat.numpy(), h_blend.numpy())
-            h_blob = torch.from_numpy(packed.copy()).pin_memory()
+            t_pack = time.perf_counter()
+            packed = ctx.pack()   # Grid::PackForSave of the device grid: run-length coding on the GPU
+            extra["grid_pack_ms"] = 1e3 * (time.perf_counter() - t_pack)
+            h_blob = torch.from_numpy(packed).pin_memory()
             blob_bytes = int(h_blob.numel())
             ctx2 = voxels_b200.Context(local_rank)
             stream2 = torch.cuda.ExternalStream(ctx2.L.vxb_stream(ctx2.h), device=dev)
@@ -459,7 +459,7 @@ def main():
         # -- CPU baseline: the reference itself on this box's host cores, on the SAME bytes, and the parity check of the step --
         if not args.no_cpu_baseline:
             t0 = time.time()
-            hd, hm, hb = (t.cpu().numpy() for t in (dist, mat, blend))
+            hd, hm, hb = ctx.download_dense()
             v, ci, ref, rgrid, rsurf = reference_run(n, 3, 1, hd, hm, hb, budget_s=90.0, keep_surface=True)
             if v is not None:
                 cpu = {"value": n ** 3 / ci["best_seconds"] / 1e6, "mean_value": v, "unit": "Mvoxels/s", "cores": ci["cores"], "physical_cores": ci["physical_cores"],
@@ -500,14 +500,12 @@ def main():
                 cpu = {"value": None, "unit": "Mvoxels/s", "cores": 0, "kind": "reference", "sample": ci["unavailable"]}
             del hd, hm, hb
         ctx.close()
-        del dist, mat, blend
         sharding_note = None
         scaling = "strong"
     else:
         # ------------------------------------------------------------ N > 1: ONE grid, all ranks
         sg = ShardedGrid(ranks, n, group_planes=args.group_planes or None)
-        for z0, z1, outt in sg.piece_tensors():
-            synth.terrain(n, dev, z_range=(z0, z1), out=outt)
+        sg.ctx.fill(n, capi.Surface.terrain(n))   # every rank fills the pieces it backs
         sg.ready()
         stream = torch.cuda.ExternalStream(sg.ctx.stream(), device=dev)
         for _ in range(max(args.warmup, 3)):
@@ -557,13 +555,12 @@ def main():
 
         # -- e2e: every rank uploads ITS pieces from the same PackForSave blob in pinned host memory, barrier, step, own result back --
         if not args.no_e2e:
-            full = synth.terrain(n, dev) if rank == 0 else None
             blob_t = None
             if rank == 0:
-                hd, hm, hb = (t.cpu().numpy() for t in full)
-                packed = voxels_b200.pack_dense(hd, hm, hb)
-                blob_t = torch.from_numpy(packed.copy())
-                del hd, hm, hb, full
+                ctxp = voxels_b200.Context(local_rank)
+                ctxp.fill(n, capi.Surface.terrain(n))
+                blob_t = torch.from_numpy(ctxp.pack())
+                ctxp.close()
             size_t = torch.tensor([blob_t.numel() if rank == 0 else 0], dtype=torch.int64, device=dev)
             ranks.td.broadcast(size_t, src=0)
             blob_dev = torch.empty(int(size_t.item()), dtype=torch.uint8, device=dev)
@@ -609,10 +606,8 @@ def main():
 
         # -- extra: the independent-tiles mode (one n^3 tile per rank, no data-path collective): weak scaling --
         if not args.no_tiles:
-            dist, mat, blend = synth.terrain(n, dev, origin=tile_origin(rank, n))
-            torch.cuda.synchronize()
             ctxt = voxels_b200.Context(local_rank)
-            ctxt.set_device_grid(n, dist.data_ptr(), mat.data_ptr(), blend.data_ptr(), keep=(dist, mat, blend))
+            ctxt.fill(n, capi.Surface.terrain(n, origin=tile_origin(rank, n)))
             st = torch.cuda.ExternalStream(ctxt.L.vxb_stream(ctxt.h), device=dev)
             for _ in range(3):
                 ctxt.polygonize(0, flags)
@@ -620,7 +615,6 @@ def main():
             extra["independent_tiles"] = {"value": whole_job_throughput(n, world, ms_t), "unit": "Mvoxels/s", "ms_per_step": ms_t, "scaling": "weak",
                                           "what": "one %d^3 terrain tile per rank, no data-path collective (round 1's line)" % n}
             ctxt.close()
-            del dist, mat, blend
 
     # ---------------------------------------------------------------- second record: BASELINE configs[3], 2048^3 (one grid over N GPUs)
     if not args.no_config4:
@@ -630,7 +624,7 @@ def main():
             import numpy as np
             if world > 1:
                 sg4 = ShardedGrid(ranks, n4, key="c4-%s" % os.environ.get("MASTER_PORT", "0"))
-                terrain_config4(sg4, synth, dev)
+                sg4.ctx.fill(n4, capi.Surface.terrain(n4))
                 sg4.ready()
                 st4 = torch.cuda.ExternalStream(sg4.ctx.stream(), device=dev)
                 for _ in range(3):
@@ -640,10 +634,8 @@ def main():
                     if sg4.ctx.polygonize_sharded(3, flags) != 0:
                         raise RuntimeError("arena overflow inside the timed region")
             else:
-                vol4 = synth.terrain(n4, dev)
-                torch.cuda.synchronize()
                 sg4 = voxels_b200.Context(local_rank)
-                sg4.set_device_grid(n4, vol4[0].data_ptr(), vol4[1].data_ptr(), vol4[2].data_ptr(), keep=vol4)
+                sg4.fill(n4, capi.Surface.terrain(n4))
                 st4 = torch.cuda.ExternalStream(sg4.L.vxb_stream(sg4.h), device=dev)
                 for _ in range(3):
                     i4 = sg4.polygonize(0, flags)

@@ -260,6 +260,29 @@ int vxb_cube_piece(vxb_context* ctx, uint32_t piece, int8_t** dist, uint8_t** ma
 int vxb_result_download(vxb_context* ctx, vxb_block_record* records, void* vertices, uint32_t* indices,
 	void* trans_vertices, uint32_t* trans_indices);
 
+/* ---- consumer side: the result as indirect draws, without leaving HBM (doc_source/Rendering.md:18-58) ------------------
+ * The arenas are merged vertex / index buffers: a block is drawn with {index_count, first_index, base_vertex} (indices are
+ * block-local).  vxb_result_device_arenas hands the device pointers to the renderer (CUDA-graphics interop / external
+ * memory).  vxb_result_select_lod runs, per frame, the cut through the LOD octree on the GPU: node of level l around the
+ * camera is refined while the camera is closer than base_distance * 2^l to its centre; for every drawn block of level > 0
+ * `block_adj` has bit f set when the neighbour across face f (BlockPolygons::TransitionFaceId order) is drawn finer - then
+ * the block's transition mesh f is drawn too and the vertex shader selects the secondary position of the vertices whose
+ * mask (SecondaryPosition.w) is covered by block_adj (Rendering.md:44-52).  Both lists are VkDrawIndexedIndirectCommand /
+ * D3D12_DRAW_INDEXED_ARGUMENTS arrays with first_instance = the draw's index into the info array. */
+typedef struct vxb_draw_command { uint32_t index_count, instance_count, first_index; int32_t base_vertex; uint32_t first_instance; } vxb_draw_command;
+typedef struct vxb_draw_info { uint32_t block_id, level, block_adj, face; /* face = 0xFFFFFFFF: the regular mesh */ } vxb_draw_info;
+typedef struct vxb_draw_lists
+{
+	uint32_t regular_count, transition_count;   /* also resident on the device: counts[0], counts[1] (for *IndirectCount draws) */
+	const uint32_t* counts;                     /* device */
+	const vxb_draw_command* regular; const vxb_draw_info* regular_info;          /* device, regular_count entries */
+	const vxb_draw_command* transition; const vxb_draw_info* transition_info;    /* device, transition_count entries */
+} vxb_draw_lists;
+int vxb_result_device_arenas(vxb_context* ctx, const void** vertices, const uint32_t** indices, const void** trans_vertices, const uint32_t** trans_indices);
+int vxb_result_select_lod(vxb_context* ctx, const float camera[3], float base_distance, vxb_draw_lists* out);
+/* the two lists copied to HOST memory (tests, debugging); capacities in entries, any pointer may be NULL */
+int vxb_result_download_draws(vxb_context* ctx, vxb_draw_command* regular, vxb_draw_info* regular_info, vxb_draw_command* transition, vxb_draw_info* transition_info);
+
 /* GetMaterial(id) == nullptr handling (TransVoxelImpl.cpp:1364-1368: textures stay zero, one LS_Error log per
  * vertex): after vxb_result_download the material ids of those vertices, in the reference's logging order
  * (level, block, regular vertices, then transition faces), can be read here.  Returns the count; copies at

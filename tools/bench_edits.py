@@ -8,6 +8,11 @@ drop-in backend (build/libvxh_b200.so).  Timed per edit: Execute only (the Injec
 host code on both sides and is reported separately).  The drop-in's Execute includes reading the touched blocks from the
 Grid, the H2D update, all kernels, the D2H of the re-created blocks and the splice into the surface.
 
+A third column, "device": the same edits WITHOUT the host grid - vxb_grid_inject_surface (the edit kernel on the
+device-resident grid) + vxb_polygonize_region + vxb_result_download through the C ABI; timed per edit as
+one unit (edit + re-polygonization + the re-created blocks back on the host) and compared with the reference's
+re-created blocks at every check point.
+
     python tools/bench_edits.py [--size 512] [--edits 1000] [--check-every 100]
 """
 import argparse
@@ -52,6 +57,13 @@ def main():
     edits = edit_sequence(n, args.edits, dist)
     libs = [("reference", harness.reference()), ("b200", harness.load(harness.B200_LIB))]
     state = {}
+    # the device column: grid resident in HBM, edited there
+    import voxels_b200
+    from voxels_b200 import capi
+    dctx = voxels_b200.Context(0)
+    dctx.upload_dense(dist, mat, blend)
+    dctx.polygonize()
+    dev = {"seconds": 0.0, "blocks": 0, "mismatches": 0}
     for name, lib in libs:
         g = lib.grid_from_dense(dist, mat, blend)
         t0 = time.time()
@@ -69,6 +81,23 @@ def main():
             s2, sec = lib.polygonize(st["grid"], modification=st["mod"], surface=st["surface"], box=box)
             st["inject_s"] += t1 - t0
             st["exec_s"] += sec
+        t0 = time.perf_counter()
+        dbox = dctx.inject_surface(np.array(pos, np.float32), np.full(3, extent, np.float32), capi.Surface.sphere((0, 0, 0), radius), kind)
+        dctx.polygonize_region(dbox[:3], dbox[3:])
+        part = dctx.download()
+        dev["seconds"] += time.perf_counter() - t0
+        dev["blocks"] += len(part.records)
+        if args.check_every and (i + 1) % args.check_every == 0:
+            # the blocks this edit re-created = the tail of every level of the reference's surface (erase + append)
+            a = state["reference"]
+            for l in range(a["lib"].surface_levels(a["surface"])):
+                want, got = a["lib"].surface_level(a["surface"], l), part.level(l)
+                k = len(got.rows); cut = len(want.rows) - k
+                r = want.rows
+                tail = harness.LevelDump(r[cut:], want.verts[int(r["nv"][:cut].sum()):], want.idx[int(r["ni"][:cut].sum()):],
+                                         want.tverts[int(r["tnv"][:cut].sum()):], want.tidx[int(r["tni"][:cut].sum()):])
+                if cut < 0 or compare.level_diff(tail, got, "device edit %d L%d" % (i, l)):
+                    dev["mismatches"] += 1
         if args.check_every and (i + 1) % args.check_every == 0:
             a, b = state["reference"], state["b200"]
             for l in range(a["lib"].surface_levels(a["surface"])):
@@ -83,6 +112,12 @@ def main():
                      "inject_ms_per_edit": 1e3 * st["inject_s"] / len(edits), "blocks_recreated_per_edit": blocks / len(edits),
                      "threads": lib.L.vxh_max_threads() if name == "reference" else None}
     out["speedup_execute"] = out["b200"]["edits_per_s"] / out["reference"]["edits_per_s"]
+    out["device"] = {"edits_per_s": len(edits) / dev["seconds"], "ms_per_edit": 1e3 * dev["seconds"] / len(edits), "blocks_recreated_per_edit": dev["blocks"] / len(edits),
+                     "parity_checks_failed": dev["mismatches"],
+                     "what": "vxb_grid_inject_surface (edit kernel on the device grid) + vxb_polygonize_region + vxb_result_download, host clock per edit; "
+                             "compare with reference inject_ms_per_edit + ms_per_edit"}
+    out["speedup_device_vs_reference_inject_plus_execute"] = (out["reference"]["ms_per_edit"] + out["reference"]["inject_ms_per_edit"]) / out["device"]["ms_per_edit"]
+    dctx.close()
     print(json.dumps(out))
 
 

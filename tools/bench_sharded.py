@@ -32,7 +32,7 @@ def main():
     import numpy as np
     import torch
     import voxels_b200
-    from voxels_b200 import capi, synth
+    from voxels_b200 import capi
     from voxels_b200.dist import Ranks, ShardedGrid
 
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -41,8 +41,8 @@ def main():
     ranks = Ranks("nccl", dev)
     n = args.size
     sg = ShardedGrid(ranks, n, group_planes=args.group_planes or None)
-    for z0, z1, out in sg.piece_tensors():
-        synth.terrain(n, dev, z_range=(z0, z1), out=out)
+    terrain = capi.Surface.terrain(n)
+    sg.ctx.fill(n, terrain)   # every rank fills the pieces it backs (Grid::Create on the device)
     sg.ready()
     stream = torch.cuda.ExternalStream(sg.ctx.stream(), device=dev)
     for _ in range(args.warmup):
@@ -85,8 +85,7 @@ def main():
         problems = []
         mine = sg.ctx.download()
         ctx = voxels_b200.Context(local)
-        full = synth.terrain(n, dev)
-        ctx.set_device_grid(n, full[0].data_ptr(), full[1].data_ptr(), full[2].data_ptr(), keep=full)
+        ctx.fill(n, terrain)
         sinfo = ctx.polygonize()
         single = ctx.download()
         # this rank's blocks of the sharded run against the same blocks of the single-GPU run, bit by bit
@@ -109,7 +108,7 @@ def main():
             if args.reference and n <= 1024:
                 import harness
                 ref = harness.reference()
-                hd, hm, hb = (t.cpu().numpy() for t in full)
+                hd, hm, hb = ctx.download_dense()
                 g = ref.grid_from_dense(hd, hm, hb)
                 s, sec = ref.polygonize(g, threads=max(ref.L.vxh_max_threads(), len(os.sched_getaffinity(0))))
                 for l in range(ref.surface_levels(s)):

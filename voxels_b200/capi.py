@@ -63,6 +63,15 @@ class Surface(C.Structure):
         return s
 
 
+class DrawLists(C.Structure):
+    _fields_ = [("regular_count", C.c_uint32), ("transition_count", C.c_uint32), ("counts", C.c_void_p), ("regular", C.c_void_p),
+                ("regular_info", C.c_void_p), ("transition", C.c_void_p), ("transition_info", C.c_void_p)]
+
+
+DRAW_COMMAND_DTYPE = np.dtype([("index_count", "<u4"), ("instance_count", "<u4"), ("first_index", "<u4"), ("base_vertex", "<i4"), ("first_instance", "<u4")])
+DRAW_INFO_DTYPE = np.dtype([("block_id", "<u4"), ("level", "<u4"), ("block_adj", "<u4"), ("face", "<u4")])
+
+
 class NcclId(C.Structure):
     _fields_ = [("internal", C.c_char * 128)]
 
@@ -120,6 +129,9 @@ def load_library():
         "vxb_grid_inject_material": (C.c_int, [vp, vp, vp, u32, C.c_int, vp, vp]),
         "vxb_grid_pack": (C.c_int, [vp, vp, C.c_size_t, C.POINTER(C.c_size_t)]),
         "vxb_grid_download_dense": (C.c_int, [vp, vp, vp, vp]),
+        "vxb_result_device_arenas": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),
+        "vxb_result_select_lod": (C.c_int, [vp, vp, C.c_float, C.POINTER(DrawLists)]),
+        "vxb_result_download_draws": (C.c_int, [vp, vp, vp, vp, vp]),
         "vxb_polygonize": (C.c_int, [vp, u32, u32]),
         "vxb_result_info_get": (C.c_int, [vp, C.POINTER(ResultInfo)]),
         "vxb_grid_update_blocks": (C.c_int, [vp, u32, vp, vp, vp, vp]),
@@ -158,7 +170,7 @@ EXPORTED_SYMBOLS = ["vxb_create", "vxb_destroy", "vxb_last_error", "vxb_stream",
                     "vxb_result_unmapped_materials", "vxb_host_alloc", "vxb_host_free", "vxb_polygonize_sharded", "vxb_shard_configure",
                     "vxb_shard_buffers_get", "vxb_shard_set_peer", "vxb_shard_export", "vxb_shard_import", "vxb_shard_nccl_unique_id",
                     "vxb_shard_nccl_init", "vxb_grid_fill", "vxb_grid_inject_surface", "vxb_grid_inject_material", "vxb_grid_pack",
-                    "vxb_grid_download_dense", "vxb_cube_create", "vxb_cube_info", "vxb_cube_export", "vxb_cube_import", "vxb_cube_piece"]
+                    "vxb_grid_download_dense", "vxb_result_device_arenas", "vxb_result_select_lod", "vxb_result_download_draws", "vxb_cube_create", "vxb_cube_info", "vxb_cube_export", "vxb_cube_import", "vxb_cube_piece"]
 
 
 def nccl_unique_id():
@@ -338,6 +350,23 @@ class Context:
         dist = np.empty((n, n, n), np.int8); mat = np.empty((n, n, n), np.uint8); blend = np.empty((n, n, n), np.uint8)
         self._check(self.L.vxb_grid_download_dense(self.h, _ptr(dist), _ptr(mat), _ptr(blend)), "vxb_grid_download_dense")
         return dist, mat, blend
+
+    # ---- consumer side: LOD cut + indirect draw lists on the device ----
+    def select_lod(self, camera, base_distance):
+        """(regular commands, regular infos, transition commands, transition infos) as numpy record arrays (copied back for
+        inspection; a renderer consumes the device-resident lists of vxb_draw_lists directly)."""
+        cam = np.ascontiguousarray(camera, np.float32)
+        lists = DrawLists()
+        self._check(self.L.vxb_result_select_lod(self.h, _ptr(cam), base_distance, C.byref(lists)), "vxb_result_select_lod")
+        rc = np.zeros(lists.regular_count, DRAW_COMMAND_DTYPE); ri = np.zeros(lists.regular_count, DRAW_INFO_DTYPE)
+        tc = np.zeros(lists.transition_count, DRAW_COMMAND_DTYPE); ti = np.zeros(lists.transition_count, DRAW_INFO_DTYPE)
+        self._check(self.L.vxb_result_download_draws(self.h, _ptr(rc), _ptr(ri), _ptr(tc), _ptr(ti)), "vxb_result_download_draws")
+        return rc, ri, tc, ti
+
+    def device_arenas(self):
+        v, i, tv, ti = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self._check(self.L.vxb_result_device_arenas(self.h, C.byref(v), C.byref(i), C.byref(tv), C.byref(ti)), "vxb_result_device_arenas")
+        return v.value, i.value, tv.value, ti.value
 
     def set_device_grid(self, n, d_dist, d_mat, d_blend, keep=None):
         """Device pointers (ints) of dense volumes that stay resident (e.g. torch tensors' data_ptr())."""

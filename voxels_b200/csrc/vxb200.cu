@@ -28,6 +28,7 @@
 #include "vxb_kernels.cuh"
 #include "vxb_emit.cuh"
 #include "vxb_grid.cuh"
+#include "vxb_draw.cuh"
 
 typedef VxbDecideSmem<4096> VxbDecideSmemBig;
 
@@ -77,6 +78,11 @@ struct vxb_context
 	DevBuf<uint8_t> volDist, volMat, volBlend, staging;
 	DevBuf<unsigned long long> packOffsets;
 	DevBuf<float> fillColumns;
+	DevBuf<vxb_draw_command> drawCmd, drawTCmd;
+	DevBuf<vxb_draw_info> drawInfo, drawTInfo;
+	DevBuf<unsigned int> drawCounts;
+	vxb_draw_lists drawLists;
+	VxbDev lastDev; // kernel-side view of the last run (records, arenas), for the consumer-side kernels
 	DevBuf<unsigned int> packSizes, packFlags;
 	struct PinnedBuf // page-locked host scratch (grows, never shrinks)
 	{
@@ -621,6 +627,8 @@ int vxb_create(int device, vxb_context** out)
 	vxb_context* ctx = new vxb_context;
 	ctx->device = device; ctx->smCount = prop.multiProcessorCount;
 	memset(&ctx->info, 0, sizeof(ctx->info));
+	memset(&ctx->drawLists, 0, sizeof(ctx->drawLists));
+	memset(&ctx->lastDev, 0, sizeof(ctx->lastDev));
 	if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
 		(e = cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking)) != cudaSuccess ||
 		(e = cudaEventCreate(&ctx->evBegin)) != cudaSuccess || (e = cudaEventCreate(&ctx->evEnd)) != cudaSuccess ||
@@ -675,6 +683,7 @@ void vxb_destroy(vxb_context* ctx)
 	if (ctx->shard.comm && ncclApi().ok) { ncclApi().commDestroy(ctx->shard.comm); ctx->shard.comm = nullptr; }
 	releaseCube(ctx);
 	ctx->fillColumns.release(); ctx->packSizes.release(); ctx->packFlags.release();
+	ctx->drawCmd.release(); ctx->drawTCmd.release(); ctx->drawInfo.release(); ctx->drawTInfo.release(); ctx->drawCounts.release();
 	ctx->mixInfo.release(); ctx->coarseDone.release(); ctx->coarseLatticeBuf.release(); ctx->coarseMaps.release();
 	ctx->volDist.release(); ctx->volMat.release(); ctx->volBlend.release(); ctx->staging.release(); ctx->packOffsets.release(); ctx->updCoords.release(); ctx->lattice1.release();
 	ctx->scanFlags.release(); ctx->blockInfo.release(); ctx->consPages.release(); ctx->validFlags.release();
@@ -1284,12 +1293,15 @@ static int runPolygonize(vxb_context* ctx, uint32_t maxLevels, uint32_t flags, c
 			if (!incremental) VXB_CUDA(ctx, cudaMemsetAsync(ctx->validFlags.p, 0, validBytes, st)); // incremental runs keep the caches (:362-364)
 			if (sharded) VXB_CUDA(ctx, cudaMemsetAsync(sh.pagesBuf + sh.pagesBytes, 0, sh.validBytes, st));
 			if (coarseBlocks) VXB_CUDA(ctx, cudaMemsetAsync(ctx->coarseDone.p, 0, coarseBlocks, st));
-			const size_t myLayers = nb0 / scanWorld;
+			// incremental runs: only the block layers of the level-0 dirty box changed since the last run
+			const int zBase = incremental ? std::max(0, region->rangeMin[0][2]) : 0;
+			const size_t myLayers = incremental ? (size_t)std::max(0, std::min((int)nb0, region->rangeMax[0][2]) - zBase) : nb0 / scanWorld;
+			if (!myLayers) return VXB_OK;
 			const int perCta = nb0 >= 32 ? 32 : 8;
 			const dim3 grid((unsigned)((nb0 + perCta - 1) / perCta), (unsigned)nb0, (unsigned)myLayers);
 			timer.begin(0);
-			if (perCta == 32) vxb_scan_kernel<32><<<grid, VXB_THREADS, 0, st>>>(ctx->dDist, (int)n, ctx->scanFlags.p, ctx->haveLattice1 ? ctx->latticePtr : nullptr, scanLat, scanGroup, scanWorld, scanRank);
-			else vxb_scan_kernel<8><<<grid, VXB_THREADS, 0, st>>>(ctx->dDist, (int)n, ctx->scanFlags.p, ctx->haveLattice1 ? ctx->latticePtr : nullptr, scanLat, scanGroup, scanWorld, scanRank);
+			if (perCta == 32) vxb_scan_kernel<32><<<grid, VXB_THREADS, 0, st>>>(ctx->dDist, (int)n, ctx->scanFlags.p, ctx->haveLattice1 ? ctx->latticePtr : nullptr, scanLat, scanGroup, scanWorld, scanRank, zBase);
+			else vxb_scan_kernel<8><<<grid, VXB_THREADS, 0, st>>>(ctx->dDist, (int)n, ctx->scanFlags.p, ctx->haveLattice1 ? ctx->latticePtr : nullptr, scanLat, scanGroup, scanWorld, scanRank, zBase);
 			timer.end(); ++launches; ++ctx->kindLaunches[0];
 			if (sharded && peerLat.count && coarseLo < levels)
 			{
@@ -1300,7 +1312,7 @@ static int runPolygonize(vxb_context* ctx, uint32_t maxLevels, uint32_t flags, c
 			const size_t mine = myLayers * nb0 * nb0;
 			const unsigned g2 = (unsigned)std::min<size_t>((mine + 255) / 256, (size_t)ctx->smCount * 8);
 			timer.begin(1);
-			vxb_block_info_kernel<<<g2, 256, 0, st>>>(ctx->dDist, (int)n, ctx->scanFlags.p, ctx->blockInfo.p, mine, scanGroup, scanWorld, scanRank);
+			vxb_block_info_kernel<<<g2, 256, 0, st>>>(ctx->dDist, (int)n, ctx->scanFlags.p, ctx->blockInfo.p, mine, scanGroup, scanWorld, scanRank, zBase);
 			timer.end(); ++launches; ++ctx->kindLaunches[1];
 			return VXB_OK;
 		};
@@ -1503,6 +1515,7 @@ static int runPolygonize(vxb_context* ctx, uint32_t maxLevels, uint32_t flags, c
 	// the directory stays on the device (it is part of the result resident in HBM); vxb_result_download fetches and
 	// sorts it into the reference's block order on demand
 	ctx->lastCounters = hc;
+	ctx->lastDev = dev;
 	ctx->directoryFetched = false;
 	ctx->sortedRecords.clear();
 
@@ -1828,6 +1841,59 @@ int vxb_result_download(vxb_context* ctx, vxb_block_record* records, void* verti
 			for (int f = 0; f < 6; ++f) fix(transVertices, r.trans_vertex_offset[f], r.trans_vertex_count[f]);
 		}
 	}
+	return VXB_OK;
+}
+
+int vxb_result_device_arenas(vxb_context* ctx, const void** vertices, const uint32_t** indices, const void** transVertices, const uint32_t** transIndices)
+{
+	if (!ctx) return VXB_ERR_ARGUMENT;
+	if (!ctx->haveResult) return fail(ctx, VXB_ERR_STATE, "no result: call vxb_polygonize first");
+	if (vertices) *vertices = ctx->verts.p;
+	if (indices) *indices = ctx->idx.p;
+	if (transVertices) *transVertices = ctx->tverts.p;
+	if (transIndices) *transIndices = ctx->tidx.p;
+	return VXB_OK;
+}
+
+int vxb_result_select_lod(vxb_context* ctx, const float camera[3], float baseDistance, vxb_draw_lists* out)
+{
+	if (!ctx || !camera) return VXB_ERR_ARGUMENT;
+	if (!ctx->haveResult) return fail(ctx, VXB_ERR_STATE, "no result: call vxb_polygonize first");
+	cudaSetDevice(ctx->device);
+	const uint32_t blocks = ctx->info.block_count;
+	const size_t cap = blocks ? blocks : 1;
+	VXB_CUDA(ctx, ctx->drawCmd.ensure(cap)); VXB_CUDA(ctx, ctx->drawInfo.ensure(cap));
+	VXB_CUDA(ctx, ctx->drawTCmd.ensure(cap * 6)); VXB_CUDA(ctx, ctx->drawTInfo.ensure(cap * 6));
+	VXB_CUDA(ctx, ctx->drawCounts.ensure(2));
+	VXB_CUDA(ctx, cudaMemsetAsync(ctx->drawCounts.p, 0, 8, ctx->stream));
+	VxbLodArgs a;
+	for (int k = 0; k < 3; ++k) a.camera[k] = camera[k];
+	a.baseDistance = baseDistance;
+	a.counts = ctx->drawCounts.p;
+	a.regular = ctx->drawCmd.p; a.regularInfo = ctx->drawInfo.p; a.transition = ctx->drawTCmd.p; a.transitionInfo = ctx->drawTInfo.p;
+	a.capacity = (unsigned)(cap * 6);
+	if (blocks) vxb_lod_select_kernel<<<(blocks + 255) / 256, 256, 0, ctx->stream>>>(ctx->lastDev, a, blocks);
+	unsigned counts[2] = { 0, 0 };
+	VXB_CUDA(ctx, cudaMemcpyAsync(counts, ctx->drawCounts.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+	VXB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	VXB_CUDA(ctx, cudaGetLastError());
+	vxb_draw_lists& l = ctx->drawLists;
+	l.regular_count = counts[0]; l.transition_count = counts[1];
+	l.counts = ctx->drawCounts.p;
+	l.regular = ctx->drawCmd.p; l.regular_info = ctx->drawInfo.p; l.transition = ctx->drawTCmd.p; l.transition_info = ctx->drawTInfo.p;
+	if (out) *out = l;
+	return VXB_OK;
+}
+
+int vxb_result_download_draws(vxb_context* ctx, vxb_draw_command* regular, vxb_draw_info* regularInfo, vxb_draw_command* transition, vxb_draw_info* transitionInfo)
+{
+	if (!ctx) return VXB_ERR_ARGUMENT;
+	cudaSetDevice(ctx->device);
+	const vxb_draw_lists& l = ctx->drawLists;
+	if (regular && l.regular_count) VXB_CUDA(ctx, cudaMemcpy(regular, l.regular, sizeof(vxb_draw_command) * l.regular_count, cudaMemcpyDeviceToHost));
+	if (regularInfo && l.regular_count) VXB_CUDA(ctx, cudaMemcpy(regularInfo, l.regular_info, sizeof(vxb_draw_info) * l.regular_count, cudaMemcpyDeviceToHost));
+	if (transition && l.transition_count) VXB_CUDA(ctx, cudaMemcpy(transition, l.transition, sizeof(vxb_draw_command) * l.transition_count, cudaMemcpyDeviceToHost));
+	if (transitionInfo && l.transition_count) VXB_CUDA(ctx, cudaMemcpy(transitionInfo, l.transition_info, sizeof(vxb_draw_info) * l.transition_count, cudaMemcpyDeviceToHost));
 	return VXB_OK;
 }
 

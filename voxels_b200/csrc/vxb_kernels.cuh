@@ -271,14 +271,15 @@ __global__ void __launch_bounds__(VXB_THREADS, (J == 32 ? 3 : 4)) vxb_scan_kerne
 	unsigned char* __restrict__ lattice1 /* (n/2)^3: the samples at even coordinates = the level-1 lattice, or null */,
 	const __grid_constant__ VxbCoarseLattices coarse,
 	int groupLayers, int world, int rank /* sharded runs: blockIdx.z counts this rank's layers (groups of groupLayers block layers,
-	                                        dealt cyclically to the ranks); unsharded: world = 1 */)
+	                                        dealt cyclically to the ranks); unsharded: world = 1 */,
+	int zBase /* first block layer (incremental runs rescan only the layers of the level-0 dirty box) */)
 {
 	constexpr int RG = VXB_THREADS / J; // row groups: thread (j, rg) reads rows rg, rg + RG, ... of block j
 	__shared__ unsigned sFlags[J];
 	__shared__ unsigned sChanges[J];
 	const int nb = n >> 4;
 	const int bx0 = blockIdx.x * J, by = blockIdx.y;
-	const int bz = ((int)(blockIdx.z / groupLayers) * world + rank) * groupLayers + (int)(blockIdx.z % groupLayers);
+	const int bz = zBase + ((int)(blockIdx.z / groupLayers) * world + rank) * groupLayers + (int)(blockIdx.z % groupLayers);
 	const int tid = threadIdx.x;
 	const int j = tid % J, rg = tid / J;
 	if (tid < J) { sFlags[tid] = 0; sChanges[tid] = 0; }
@@ -359,7 +360,7 @@ __global__ void __launch_bounds__(VXB_THREADS, (J == 32 ? 3 : 4)) vxb_scan_kerne
 
 // K1b: raw flags -> blockInfo.  One thread per level-0 block.
 __global__ void vxb_block_info_kernel(const signed char* __restrict__ dist, int n, const unsigned int* __restrict__ scanFlags, unsigned char* __restrict__ blockInfo,
-	size_t total /* blocks of this rank: whole layers, z-major */, int groupLayers, int world, int rank /* as vxb_scan_kernel */)
+	size_t total /* blocks of this rank: whole layers, z-major */, int groupLayers, int world, int rank, int zBase /* as vxb_scan_kernel */)
 {
 	const int nb = n >> 4;
 	const size_t layerBlocks = (size_t)nb * nb;
@@ -367,7 +368,7 @@ __global__ void vxb_block_info_kernel(const signed char* __restrict__ dist, int 
 	{
 		// q = rank-local index (layer-major); b = the block's coordinate id; the result goes to the rank-major slot
 		const int lz = (int)(q / layerBlocks);
-		const int tz = ((lz / groupLayers) * world + rank) * groupLayers + lz % groupLayers;
+		const int tz = zBase + ((lz / groupLayers) * world + rank) * groupLayers + lz % groupLayers;
 		const size_t b = (size_t)tz * layerBlocks + q % layerBlocks;
 		const unsigned f = scanFlags[b];
 		const bool neg = f & 1, pos = f & 2, zero = f & 4;
@@ -395,7 +396,7 @@ __global__ void vxb_block_info_kernel(const signed char* __restrict__ dist, int 
 				}
 			}
 		}
-		blockInfo[(size_t)rank * (total) + q] = (unsigned char)((neg ? VXB_BI_NEG : 0) | ((pos || zero) ? VXB_BI_NONNEG : 0) | (empty ? VXB_BI_EMPTY : 0)
+		blockInfo[world == 1 ? b : (size_t)rank * total + q] = (unsigned char)((neg ? VXB_BI_NEG : 0) | ((pos || zero) ? VXB_BI_NONNEG : 0) | (empty ? VXB_BI_EMPTY : 0)
 			| ((f & 8) ? VXB_BI_NEG_E : 0) | ((f & 16) ? VXB_BI_NONNEG_E : 0));
 	}
 }
