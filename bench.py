@@ -255,7 +255,8 @@ def main():
     dev = torch.device("cuda", local_rank)
     import voxels_b200
     from voxels_b200 import capi
-    from voxels_b200.dist import Ranks, ShardedGrid, tile_origin, whole_job_throughput
+    from voxels_b200.dist import Ranks, ShardedGrid, bind_to_gpu_numa_node, tile_origin, whole_job_throughput
+    numa_node = bind_to_gpu_numa_node(local_rank) if world > 1 else None   # N ranks: each next to its GPU's memory controllers
     ranks = Ranks("nccl", dev)
     flags = voxels_b200.FLAG_NO_TRANSITIONS if args.no_transitions else 0
     peak, peak_src = measured_peak_hbm()
@@ -546,7 +547,8 @@ def main():
                   "grid": "dense int8 distance + uint8 material + uint8 blend; z-pieces of %d planes dealt cyclically to the ranks' HBM, mapped into every peer over NVLink" % sg.group_planes,
                   "sharding": "work dealt by blocks (super-blocks cut by surface weight); exchange 0 = ncclAllGather of the per-block info, exchange 1 = peer stores of material pages + a one-word ncclAllGather; coarse levels classified by every rank",
                   "l2": "inputs larger than the 126 MB L2; no flush", "vertices": V, "indices": I, "transition_vertices": TV, "transition_indices": TI,
-                  "blocks_emitted": int(len(directory)), "blocks_per_rank": per_rank_blocks, "vertices_per_rank": per_rank_verts, "nccl_ranks": world}
+                  "blocks_emitted": int(len(directory)), "blocks_per_rank": per_rank_blocks, "vertices_per_rank": per_rank_verts, "nccl_ranks": world,
+                  "host_binding": "every rank pinned to the CPUs of its GPU's NUMA node (rank 0: node %s)" % numa_node}
         # every rank's geometry digest equals the single-GPU result?  (cheap version inside the bench: directory self-consistency;
         # the bit-exact multi-GPU comparison lives in tools/bench_sharded.py --verify and tests/test_gpu_sharded.py)
         key = directory["level"].astype(np.int64) * (1 << 32) + directory["coord_id"]

@@ -128,3 +128,10 @@ def test_cyclic_pieces_cover_the_grid_once():
         assert sorted(seen) == list(range(n // g))                 # every piece exactly one owner
     # a terrain's surface (a few z-layers) is spread over all ranks' memories: 8 ranks, 1024^3 => 32-plane pieces
     assert default_group_planes(1024, 8) == 32 and default_group_planes(2048, 8) == 32
+
+
+def test_parse_cpulist():
+    sys.path.insert(0, REPO)
+    from voxels_b200.dist import parse_cpulist
+    assert parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
+    assert parse_cpulist("5") == [5] and parse_cpulist("") == []

@@ -8,8 +8,10 @@ import csv
 import json
 import sys
 
-KINDS = [("vxb_scan", "scan"), ("vxb_block_info", "select"), ("vxb_select", "select"), ("vxb_classify", "classify"), ("vxb_decide", "decide"),
-         ("vxb_mark_split", "decide"), ("vxb_vertex", "vertex"), ("vxb_triangle", "triangle"), ("vxb_transition", "transition"), ("vxb_finish", "finish")]
+KINDS = [("vxb_scan", "scan"), ("vxb_block_info", "select"), ("vxb_pyramid", "select"), ("vxb_select", "select"), ("vxb_plan", "select"),
+         ("vxb_block_kernel<0", "block_level0"), ("vxb_block_kernel<1", "block_levels1plus"), ("vxb_block_kernel<2", "block_levels1plus"),
+         ("vxb_classify", "classify"), ("vxb_decide", "block_levels1plus"), ("vxb_mark_split", "select"), ("vxb_vertex", "vertex"),
+         ("vxb_triangle", "triangle"), ("vxb_transition", "transition"), ("vxb_finish", "finish"), ("vxb_publish", "exchange")]
 COLS = {"us": "gpu__time_duration.sum", "rd": "dram__bytes_read.sum", "wr": "dram__bytes_write.sum", "regs": "launch__registers_per_thread",
         "warps": "sm__warps_active.avg.pct_of_peak_sustained_active", "inst": "smsp__inst_executed.sum", "grid": "launch__grid_size",
         "ipc": "sm__inst_executed.avg.per_cycle_elapsed"}
@@ -19,6 +21,16 @@ def scale(value, unit, want):
     f = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us": 1.0, "ms": 1e3, "usecond": 1.0, "nsecond": 1e-3, "msecond": 1e3}
     v = float(value.replace(",", "")) if value else 0.0
     return v * f.get(unit, 1.0)
+
+
+def kernel_source_digest():
+    import hashlib, os
+    h = hashlib.sha256()
+    d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "voxels_b200", "csrc")
+    for name in sorted(os.listdir(d)):
+        if name.endswith((".cu", ".cuh", ".h")):
+            h.update(open(os.path.join(d, name), "rb").read())
+    return h.hexdigest()[:16]
 
 
 def main(path, prefix, description, limit=None):
@@ -33,6 +45,7 @@ def main(path, prefix, description, limit=None):
         name = r[name_i].split("(")[0]
         if name.startswith("void "):
             name = name[5:]
+        name = name.replace(", ", ",")
         us = scale(r[idx["us"]], units[idx["us"]], "us")
         rd = scale(r[idx["rd"]], units[idx["rd"]], "byte")
         wr = scale(r[idx["wr"]], units[idx["wr"]], "byte")
@@ -43,7 +56,8 @@ def main(path, prefix, description, limit=None):
             e = per_kind.setdefault(kind, {"us": 0.0, "dram_read": 0.0, "dram_write": 0.0, "launches": 0})
             e["us"] += us; e["dram_read"] += rd; e["dram_write"] += wr; e["launches"] += 1
     open(prefix + "_kernels.md", "w").write("\n".join(lines) + "\n")
-    json.dump({"capture": description, "per_kind": per_kind}, open(prefix + "_traffic.json", "w"), indent=1)
+    step = {k: sum(e[k] for e in per_kind.values()) for k in ("us", "dram_read", "dram_write", "launches")}
+    json.dump({"capture": description, "kernel_source_digest": kernel_source_digest(), "step": step, "per_kind": per_kind}, open(prefix + "_traffic.json", "w"), indent=1)
     total = sum(e["us"] for e in per_kind.values())
     print("serialised sum %.1f us; shares: %s" % (total, ", ".join("%s %.1f%%" % (k, 100 * e["us"] / total) for k, e in per_kind.items())))
 

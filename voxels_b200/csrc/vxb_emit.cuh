@@ -34,8 +34,8 @@
 template <int PITCH, int ROWS>
 __device__ __forceinline__ void vxb_classify_bits(const signed char* tile, unsigned int* rowSign, unsigned int* nt32)
 {
-	const int tid = threadIdx.x;
-	for (int r = tid; r < 17 * 17; r += VXB_THREADS)
+	const int tid = threadIdx.x, nthreads = (int)blockDim.x;
+	for (int r = tid; r < 17 * 17; r += nthreads)
 	{
 		const unsigned int* w = reinterpret_cast<const unsigned int*>(tile + ((r / 17) * ROWS + (r % 17)) * PITCH);
 		unsigned m = 0;
@@ -45,11 +45,12 @@ __device__ __forceinline__ void vxb_classify_bits(const signed char* tile, unsig
 		rowSign[r] = m;
 	}
 	__syncthreads();
+	for (int t = tid; t < 256; t += nthreads)
 	{
-		const int z = tid >> 4, y = tid & 15;
+		const int z = t >> 4, y = t & 15;
 		const unsigned a = rowSign[z * 17 + y], b = rowSign[z * 17 + y + 1], c = rowSign[(z + 1) * 17 + y], e = rowSign[(z + 1) * 17 + y + 1];
 		const unsigned any = a | b | c | e, all = a & b & c & e;
-		reinterpret_cast<unsigned short*>(nt32)[tid] = (unsigned short)((any | (any >> 1)) & ~(all & (all >> 1)) & 0xFFFFu);
+		reinterpret_cast<unsigned short*>(nt32)[t] = (unsigned short)((any | (any >> 1)) & ~(all & (all >> 1)) & 0xFFFFu);
 	}
 }
 
@@ -66,7 +67,7 @@ __device__ __forceinline__ void vxb_tile_samples(const signed char* tile, int c,
 __device__ __forceinline__ void vxb_init_cache_page(const VxbDev& d, int level, unsigned coordId)
 {
 	unsigned int* page = reinterpret_cast<unsigned int*>(d.cachePages[level] + (size_t)coordId * 4096);
-	for (int i = threadIdx.x; i < 2048; i += VXB_THREADS) page[i] = 0x00FF00FFu; // {EMPTY_MATERIAL, 0} x 2  (:424)
+	for (int i = threadIdx.x; i < 2048; i += (int)blockDim.x) page[i] = 0x00FF00FFu; // {EMPTY_MATERIAL, 0} x 2  (:424)
 }
 
 __device__ __forceinline__ unsigned vxb_rank_of(const unsigned int* nt32, const unsigned int* wpre, int c)
@@ -78,8 +79,11 @@ __device__ __forceinline__ unsigned vxb_rank_of(const unsigned int* nt32, const 
 // axis, as 19 x 19 rows of 48 bytes (the TMA box starts on a 16-byte boundary one 16-byte group before the block).
 #define VXB_DTILE_PITCH 48
 #define VXB_DTILE_BYTES (19 * 19 * VXB_DTILE_PITCH)
-#define VXB_CAP_C 1024   // non-trivial cells of a block handled in shared memory; larger blocks go to vxb_decide_kernel<4096, 1>
-#define VXB_VL_CAP 2048  // new vertices of a level-0 block generated inside the CTA; more => the flat kernels
+// Capacities of the shared-memory path of vxb_block_kernel<MODE, T>: non-trivial cells of a block (larger blocks go to
+// vxb_decide_kernel<4096, 1>) and new vertices of a level-0 block generated inside the CTA (more => the flat kernels).
+// The 128-thread level-0 variant trades capacity and the second tile buffer for twice as many resident CTAs.
+template <int MODE, int T> struct VxbBlockCaps { static constexpr int CAP = 1024, VL = (MODE == 0 ? 2048 : 8), NBUF = 2; };
+template <> struct VxbBlockCaps<0, 128> { static constexpr int CAP = 512, VL = 1024, NBUF = 1; };
 
 // ------------------------------------------------------------------------------------------------
 // vxb_block_kernel<MODE>: everything that needs the block as a unit, in ONE pass over its sample tile
@@ -95,10 +99,11 @@ __device__ __forceinline__ unsigned vxb_rank_of(const unsigned int* nt32, const 
 //           the done flags of its eight children (they were taken earlier from the same cursor, so they are running or
 //           done: no deadlock), applies the block-walk test itself, then works like MODE 1.
 // ------------------------------------------------------------------------------------------------
-template <int MODE>
+template <int MODE, int T>
 struct __align__(128) VxbBlockSmem
 {
-	signed char tiles[2][MODE == 0 ? (VXB_DTILE_BYTES + 80) : (VXB_TILE_BYTES + 96)]; // double buffered: the next block's tile lands while this one is worked on
+	typedef VxbBlockCaps<MODE, T> Caps;
+	signed char tiles[Caps::NBUF][MODE == 0 ? (VXB_DTILE_BYTES + 80) : (VXB_TILE_BYTES + 96)]; // NBUF = 2: the next block's tile lands while this one is worked on
 	unsigned int rowSign[17 * 17 + 3]; // bit x = sample (x, y, z) of the tile is negative
 	unsigned int nt32[128];
 	unsigned int wpre[132];
@@ -111,13 +116,13 @@ struct __align__(128) VxbBlockSmem
 	unsigned long long mbar[2];
 	unsigned int item, hasChild, pageReady, emitIdx, voff, ioff, cellBase, slot, take, removed;
 	unsigned int levelEnd[VXB_MAX_LEVELS + 1];
-	unsigned int recA[VXB_CAP_C];     // matId | matBlend<<8 | slotK<<16
-	unsigned int recB[VXB_CAP_C];     // newMask | quirkMask<<12 | reuse mask << 24
-	unsigned short list[VXB_CAP_C];   // compact index -> cell id
-	unsigned short cz[VXB_CAP_C];     // case code | zero mask << 8
-	unsigned short vbase[VXB_CAP_C];  // exclusive scan of new-vertex counts
-	unsigned short tbase[VXB_CAP_C];  // exclusive scan of triangle counts
-	unsigned short vl[MODE == 0 ? VXB_VL_CAP : 8]; // MODE 0: block-local vertex -> compact cell index << 4 | table vertex
+	unsigned int recA[Caps::CAP];     // matId | matBlend<<8 | slotK<<16
+	unsigned int recB[Caps::CAP];     // newMask | quirkMask<<12 | reuse mask << 24
+	unsigned short list[Caps::CAP];   // compact index -> cell id
+	unsigned short cz[Caps::CAP];     // case code | zero mask << 8
+	unsigned short vbase[Caps::CAP];  // exclusive scan of new-vertex counts
+	unsigned short tbase[Caps::CAP];  // exclusive scan of triangle counts
+	unsigned short vl[Caps::VL];      // MODE 0: block-local vertex -> compact cell index << 4 | table vertex
 };
 
 // true when an arena overflowed: the host grows the arenas and repeats the run, the later kernels do nothing
@@ -127,12 +132,14 @@ __device__ __forceinline__ bool vxb_overflowed(const VxbDev& d)
 	return c->vertices > d.vcap || c->indices > d.icap || c->cells > d.ccap || c->records > d.rcap;
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(VXB_THREADS, (MODE == 0 ? 3 : (MODE == 2 ? 3 : VXB_OCC))) vxb_block_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB, const VxbDev d, const int levelArg)
+template <int MODE, int T>
+__global__ void __launch_bounds__(T, (MODE == 0 ? (T == 128 ? 5 : 3) : (MODE == 2 ? 3 : VXB_OCC))) vxb_block_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB, const VxbDev d, const int levelArg)
 {
 	constexpr int PITCH = (MODE == 0) ? VXB_DTILE_PITCH : VXB_TILE_PITCH;
 	constexpr int ROWS = (MODE == 0) ? 19 : 17;
-	typedef VxbBlockSmem<MODE> Smem;
+	typedef VxbBlockSmem<MODE, T> Smem;
+	constexpr int CAP_C = Smem::Caps::CAP, VL_CAP = Smem::Caps::VL, NBUF = Smem::Caps::NBUF;
+	static_assert(T == 128 || T == 256, "the per-word steps assume 128 or 256 threads");
 	extern __shared__ __align__(128) unsigned char smemRaw[];
 	Smem& s = *reinterpret_cast<Smem*>(smemRaw);
 	const int tid = threadIdx.x;
@@ -141,8 +148,8 @@ __global__ void __launch_bounds__(VXB_THREADS, (MODE == 0 ? 3 : (MODE == 2 ? 3 :
 	if (tid == 0) { vxb_mbar_init(&s.mbar[0], 1); vxb_mbar_init(&s.mbar[1], 1); }
 	if (tid < 16) s.hist[tid] = 0;
 	if (tid < 8) s.used[tid] = 0;
-	for (int i = tid; i < 256; i += VXB_THREADS) { s.tabClass[i] = vxbGRegularCellClass[i]; s.tabCell[i] = vxbGRegularCellData[i]; }
-	for (int i = tid; i < 3072; i += VXB_THREADS) s.tabVert[i] = vxbGRegularVertexData[i];
+	for (int i = tid; i < 256; i += T) { s.tabClass[i] = vxbGRegularCellClass[i]; s.tabCell[i] = vxbGRegularCellData[i]; }
+	for (int i = tid; i < 3072; i += T) s.tabVert[i] = vxbGRegularVertexData[i];
 	unsigned statNonTrivial = 0;
 
 	// ---- work source ----
@@ -222,13 +229,14 @@ __global__ void __launch_bounds__(VXB_THREADS, (MODE == 0 ? 3 : (MODE == 2 ? 3 :
 		if (tid == 0) { s.item = atomicAdd(cursor, 1u); s.hasChild = 0; s.pageReady = 0; s.take = 1; s.removed = 0; }
 		__syncthreads();
 		const unsigned nextItem = s.item;
-		if (nextItem < workCount && MODE != 2) { int l, x, y, z; decode(nextItem, l, x, y, z); issue(buf ^ 1, l, x, y, z); }
+		bool nextIssued = false; // NBUF == 1: the next tile is requested as soon as this one is not read any more
+		if (nextItem < workCount && MODE != 2 && NBUF == 2) { int l, x, y, z; decode(nextItem, l, x, y, z); issue(buf ^ 1, l, x, y, z); nextIssued = true; }
 		int level, bx, by, bz;
 		decode(item, level, bx, by, bz);
 		const int m = 1 << level, nb = d.n / 16 / m;
 		const unsigned coordId = ((unsigned)bz * nb + by) * nb + bx;
 		const bool midLevel = level > 0 && level != d.lastLevel;
-		signed char* const tileRaw = s.tiles[MODE == 2 ? 0 : buf];
+		signed char* const tileRaw = s.tiles[(MODE == 2 || NBUF == 1) ? 0 : buf];
 
 		if (MODE == 2)
 		{
@@ -280,7 +288,7 @@ __global__ void __launch_bounds__(VXB_THREADS, (MODE == 0 ? 3 : (MODE == 2 ? 3 :
 			if (bx == nb - 1)
 			{
 				__syncthreads();
-				for (int i = tid; i < 19 * 19; i += VXB_THREADS)
+				for (int i = tid; i < 19 * 19; i += T)
 				{
 					signed char* r = tileRaw + i * VXB_DTILE_PITCH;
 					r[lastX + 1] = r[lastX]; r[lastX + 2] = r[lastX];
@@ -289,7 +297,7 @@ __global__ void __launch_bounds__(VXB_THREADS, (MODE == 0 ? 3 : (MODE == 2 ? 3 :
 			if (by == nb - 1)
 			{
 				__syncthreads();
-				for (int i = tid; i < 19 * VXB_DTILE_PITCH; i += VXB_THREADS)
+				for (int i = tid; i < 19 * VXB_DTILE_PITCH; i += T)
 				{
 					const int z = i / VXB_DTILE_PITCH, x = i % VXB_DTILE_PITCH;
 					signed char* p = tileRaw + z * 19 * VXB_DTILE_PITCH + x;
@@ -299,7 +307,7 @@ __global__ void __launch_bounds__(VXB_THREADS, (MODE == 0 ? 3 : (MODE == 2 ? 3 :
 			if (bz == nb - 1)
 			{
 				__syncthreads();
-				for (int i = tid; i < 19 * VXB_DTILE_PITCH; i += VXB_THREADS)
+				for (int i = tid; i < 19 * VXB_DTILE_PITCH; i += T)
 				{
 					const int y = i / VXB_DTILE_PITCH, x = i % VXB_DTILE_PITCH;
 					signed char* p = tileRaw + y * VXB_DTILE_PITCH + x;
@@ -327,12 +335,12 @@ __global__ void __launch_bounds__(VXB_THREADS, (MODE == 0 ? 3 : (MODE == 2 ? 3 :
 		__syncthreads();
 		unsigned ntc;
 		{
-			const unsigned cnt = (tid < 128) ? __popc(s.nt32[tid]) : 0u;
+			const unsigned cnt = (tid < 128) ? __popc(s.nt32[tid]) : 0u; // T >= 128: one word per thread
 			const unsigned ex = vxb_block_scan(cnt, s.warpSums, ntc);
 			if (tid < 128) s.wpre[tid] = ex;
 		}
 		__syncthreads();
-		const bool inCap = ntc <= (unsigned)VXB_CAP_C;
+		const bool inCap = ntc <= (unsigned)CAP_C;
 		// sharded runs: every rank classifies the coarse levels (the votes feed the next level), one of them emits the block
 		const bool emitMine = MODE != 2 || vxb_coarse_emit_is_mine(d, level, coordId);
 
@@ -349,10 +357,13 @@ __global__ void __launch_bounds__(VXB_THREADS, (MODE == 0 ? 3 : (MODE == 2 ? 3 :
 			else if (!d.cacheValid[level][coordId]) vxb_init_cache_page(d, level, coordId);
 			if (inCap)
 			{
-				// ordered compact list: thread = cell row (z, y), 16 bits each
-				unsigned bits = reinterpret_cast<const unsigned short*>(s.nt32)[tid];
-				unsigned pos = s.wpre[tid >> 1] + ((tid & 1) ? __popc(s.nt32[tid >> 1] & 0xFFFFu) : 0u);
-				while (bits) { const int x = __ffs(bits) - 1; bits &= bits - 1; s.list[pos++] = (unsigned short)(tid * 16 + x); }
+				// ordered compact list: one cell row (z, y) = 16 bits at a time
+				for (int r = tid; r < 256; r += T)
+				{
+					unsigned bits = reinterpret_cast<const unsigned short*>(s.nt32)[r];
+					unsigned pos = s.wpre[r >> 1] + ((r & 1) ? __popc(s.nt32[r >> 1] & 0xFFFFu) : 0u);
+					while (bits) { const int x = __ffs(bits) - 1; bits &= bits - 1; s.list[pos++] = (unsigned short)(r * 16 + x); }
+				}
 			}
 			__syncthreads();
 			if (tid == 0)
@@ -380,11 +391,14 @@ __global__ void __launch_bounds__(VXB_THREADS, (MODE == 0 ? 3 : (MODE == 2 ? 3 :
 					if (vote >= 0) d.cachePages[level][(size_t)coordId * 4096 + c] = (unsigned short)vote;
 				}
 			};
-			if (inCap) { for (unsigned i = tid; i < ntc; i += VXB_THREADS) cellWork(s.list[i]); }
+			if (inCap) { if (level > 0) for (unsigned i = tid; i < ntc; i += T) cellWork(s.list[i]); } // level 0: the histogram is taken in pass A
 			else
 			{
-				unsigned bits = reinterpret_cast<const unsigned short*>(s.nt32)[tid];
-				while (bits) { const int x = __ffs(bits) - 1; bits &= bits - 1; cellWork(tid * 16 + x); }
+				for (int r = tid; r < 256; r += T)
+				{
+					unsigned bits = reinterpret_cast<const unsigned short*>(s.nt32)[r];
+					while (bits) { const int x = __ffs(bits) - 1; bits &= bits - 1; cellWork(r * 16 + x); }
+				}
 			}
 			__syncthreads();
 			if (!inCap && emitMine && tid < 128) { d.ntScratch[(size_t)s.emitIdx * 256 + tid] = s.nt32[tid]; d.ntScratch[(size_t)s.emitIdx * 256 + 128 + tid] = s.wpre[tid]; }
@@ -411,7 +425,9 @@ __global__ void __launch_bounds__(VXB_THREADS, (MODE == 0 ? 3 : (MODE == 2 ? 3 :
 					__syncthreads();
 					if (tid == 0) { d.cacheValid[level][coordId] = 1; s.pageReady = 1; }
 				}
-				const int row = tid >> 4, col = tid & 15;
+				for (int fc = tid; fc < 256; fc += T)
+				{
+				const int row = fc >> 4, col = fc & 15;
 				// most face cells have no child with a material: test all six faces first (independent loads, all in flight
 				// together), then run the vote only where it can succeed
 				unsigned candidates = 0;
@@ -438,6 +454,7 @@ __global__ void __launch_bounds__(VXB_THREADS, (MODE == 0 ? 3 : (MODE == 2 ? 3 :
 					const int vote = vxb_vote_cell(voteSrc, (bx * 16 + local[0]) * m, (by * 16 + local[1]) * m, (bz * 16 + local[2]) * m);
 					if (vote >= 0) d.cachePages[level][(size_t)coordId * 4096 + local[2] * 256 + local[1] * 16 + local[0]] = (unsigned short)vote;
 				}
+				}
 			}
 		}
 		__syncthreads(); // the votes of this block are visible to the CTA (pass A reads the page back)
@@ -449,7 +466,7 @@ __global__ void __launch_bounds__(VXB_THREADS, (MODE == 0 ? 3 : (MODE == 2 ? 3 :
 		else if (ntc > 0 && emitMine)
 		{
 			// ---- pass A: material, case code, zero mask, owned slots ----
-			for (unsigned i = tid; i < ntc; i += VXB_THREADS)
+			for (unsigned i = tid; i < ntc; i += T)
 			{
 				const int c = s.list[i];
 				signed char v[8];
@@ -459,6 +476,7 @@ __global__ void __launch_bounds__(VXB_THREADS, (MODE == 0 ? 3 : (MODE == 2 ? 3 :
 				unsigned matId, matBlend;
 				if (level == 0)
 				{
+					atomicAdd(&s.hist[s.tabClass[code]], 1u); // PerCaseCellsCount (:1574)
 					const size_t gi = ((size_t)((bz * 16 + (c >> 8))) * d.n + (by * 16 + ((c >> 4) & 15))) * d.n + (bx * 16 + (c & 15));
 					matId = g.mat[gi]; matBlend = g.blend[gi];
 				}
@@ -481,7 +499,7 @@ __global__ void __launch_bounds__(VXB_THREADS, (MODE == 0 ? 3 : (MODE == 2 ? 3 :
 			__syncthreads();
 
 			// ---- pass B: new-vs-reuse decisions ----
-			for (unsigned i = tid; i < ntc; i += VXB_THREADS)
+			for (unsigned i = tid; i < ntc; i += T)
 			{
 				const int c = s.list[i];
 				const unsigned code = s.cz[i] & 0xFF, zm = s.cz[i] >> 8;
@@ -518,7 +536,7 @@ __global__ void __launch_bounds__(VXB_THREADS, (MODE == 0 ? 3 : (MODE == 2 ? 3 :
 			// ---- exclusive scans in serial cell order (contiguous chunk per thread) ----
 			unsigned nverts, ntris;
 			{
-				const unsigned per = (ntc + VXB_THREADS - 1) / VXB_THREADS;
+				const unsigned per = (ntc + T - 1) / T;
 				const unsigned i0 = min(tid * per, ntc), i1 = min(i0 + per, ntc);
 				unsigned sv = 0, st = 0;
 				for (unsigned i = i0; i < i1; ++i) { sv += s.vbase[i]; st += s.tbase[i]; }
@@ -533,7 +551,7 @@ __global__ void __launch_bounds__(VXB_THREADS, (MODE == 0 ? 3 : (MODE == 2 ? 3 :
 					bv += cv; bt += ct;
 				}
 			}
-			const bool inCta = MODE == 0 && nverts <= (unsigned)VXB_VL_CAP;
+			const bool inCta = MODE == 0 && nverts <= (unsigned)VL_CAP;
 			if (MODE == 0 && !inCta)
 			{
 				// too many vertices for the in-CTA path: hand the block to vxb_decide_kernel<4096, 1> + the flat kernels
@@ -543,20 +561,18 @@ __global__ void __launch_bounds__(VXB_THREADS, (MODE == 0 ? 3 : (MODE == 2 ? 3 :
 			}
 			else
 			{
-				if (tid == 0)
-				{
-					s.voff = atomicAdd(&d.counters->vertices, nverts);
-					s.ioff = atomicAdd(&d.counters->indices, ntris * 3);
-					s.cellBase = (MODE == 0) ? 0u : atomicAdd(&d.counters->cells, ntc);
-					s.slot = atomicAdd(&d.counters->records, 1u);
-				}
+				// four independent atomics from four warps: one round trip instead of four in a row
+				if (tid == 0) s.voff = atomicAdd(&d.counters->vertices, nverts);
+				if (tid == 32) s.ioff = atomicAdd(&d.counters->indices, ntris * 3);
+				if (tid == 64) s.cellBase = (MODE == 0) ? 0u : atomicAdd(&d.counters->cells, ntc);
+				if (tid == 96) s.slot = atomicAdd(&d.counters->records, 1u);
 				__syncthreads();
 				const unsigned voff = s.voff, ioff = s.ioff, cellBase = s.cellBase, slot = s.slot;
 				const bool fits = (unsigned long long)voff + nverts <= d.vcap && (unsigned long long)ioff + ntris * 3ull <= d.icap
 					&& (unsigned long long)cellBase + ntc <= d.ccap && slot < d.rcap;
 				if (fits && MODE != 0)
 				{
-					for (unsigned i = tid; i < ntc; i += VXB_THREADS)
+					for (unsigned i = tid; i < ntc; i += T)
 					{
 						const unsigned rb = s.recB[i];
 						VxbCellRec cr;
@@ -574,7 +590,7 @@ __global__ void __launch_bounds__(VXB_THREADS, (MODE == 0 ? 3 : (MODE == 2 ? 3 :
 				if (fits && MODE == 0)
 				{
 					// ---- the block's new vertices, one thread each (:1576-1726), from the halo tile ----
-					for (unsigned i = tid; i < ntc; i += VXB_THREADS)
+					for (unsigned i = tid; i < ntc; i += T)
 					{
 						unsigned nm = s.recB[i] & 0xFFFu, j = s.vbase[i];
 						while (nm) { const int k = __ffs(nm) - 1; nm &= nm - 1; s.vl[j++] = (unsigned short)((i << 4) | (unsigned)k); }
@@ -583,7 +599,7 @@ __global__ void __launch_bounds__(VXB_THREADS, (MODE == 0 ? 3 : (MODE == 2 ? 3 :
 					VxbTileView tv;
 					tv.dist = tileRaw; tv.ox = bx * 16; tv.oy = by * 16; tv.oz = bz * 16; tv.sx = hsx; tv.sy = hsy; tv.sz = hsz;
 					tv.mat = g.mat; tv.blend = g.blend; tv.n = d.n; // the two material / blend taps of a vertex stay global loads
-					for (unsigned j = tid; j < nverts; j += VXB_THREADS)
+					for (unsigned j = tid; j < nverts; j += T)
 					{
 						const unsigned e = s.vl[j];
 						const unsigned i = e >> 4; const int k = e & 15;
@@ -614,9 +630,10 @@ __global__ void __launch_bounds__(VXB_THREADS, (MODE == 0 ? 3 : (MODE == 2 ? 3 :
 						atomicOr(&s.used[matId >> 5], 1u << (matId & 31));
 					}
 					__syncthreads(); // the positions are read back by the degenerate test below
+					if (NBUF == 1 && nextItem < workCount) { int l2, x2, y2, z2; decode(nextItem, l2, x2, y2, z2); issue(0, l2, x2, y2, z2); nextIssued = true; } // the tile is not read any more
 					// ---- triangles, one thread per non-trivial cell (:1714-1726 + the degenerate filter of :1300-1321) ----
 					unsigned removed = 0;
-					for (unsigned i = tid; i < ntc; i += VXB_THREADS)
+					for (unsigned i = tid; i < ntc; i += T)
 					{
 						const int c = s.list[i];
 						const unsigned code = s.cz[i] & 0xFF, zm = s.cz[i] >> 8;
@@ -685,8 +702,9 @@ __global__ void __launch_bounds__(VXB_THREADS, (MODE == 0 ? 3 : (MODE == 2 ? 3 :
 		}
 		__syncthreads();
 		if (MODE == 2 && tid == 0) { __threadfence(); *(volatile unsigned char*)(d.coarseDone + d.coarseBase[level] + coordId) = 1; }
+		if (NBUF == 1 && MODE != 2 && !nextIssued && nextItem < workCount) { int l2, x2, y2, z2; decode(nextItem, l2, x2, y2, z2); issue(0, l2, x2, y2, z2); }
 		item = nextItem;
-		buf ^= 1;
+		if (NBUF == 2) buf ^= 1;
 	}
 
 	__syncthreads();
@@ -1302,34 +1320,78 @@ __global__ void __launch_bounds__(VXB_THREADS, VXB_OCC) vxb_transition_kernel(co
 		const int m = 1 << level, nb = d.n / 16 / m;
 		const int bx = coordId % nb, by = (coordId / nb) % nb, bz = coordId / (nb * nb);
 
-		// T0: stage the half-stride lattices of the faces that have a neighbour block (independent clamped loads)
+		// T0: stage the half-stride lattices of the six face planes (clamped reads; faces without a neighbour block are staged
+		// too and never used: T1 skips them)
 		{
 			const int h = m >> 1, lim = d.n - 1;
 			const int origin[3] = { bx * 16 * m, by * 16 * m, bz * 16 * m };
-			// four independent loads in flight per thread; faces without a neighbour block are staged too (clamped reads,
-			// never used: T1 skips them)
-			for (int idx0 = tid; idx0 < 6 * 1089; idx0 += 4 * VXB_THREADS)
+			if (level == 1)
 			{
-				signed char v[4];
-#pragma unroll
-				for (int u = 0; u < 4; ++u)
+				// level 1: the lattice is the level-0 volume itself, so a row of the four faces normal to z or y is 33 CONTIGUOUS
+				// bytes starting on a 32-byte boundary: two 16-byte loads + one byte instead of 33 sector-sized byte loads
+				for (int q = tid; q < 4 * 33 * 3; q += VXB_THREADS)
 				{
-					const int idx = min(idx0 + u * VXB_THREADS, 6 * 1089 - 1);
-					const int face = idx / 1089, r = idx - face * 1089;
-					const int f3 = face >= 3 ? face - 3 : face;
-					const int j = r / 33, i = r - j * 33;
-					const int off = (face >= 3) ? 16 * m : 0, cu = i * h, cv = j * h;
-					// vxb_face_axes: f3 = 0: axis z, (u, v) = (x, y); 1: axis y, (x, z); 2: axis x, (y, z)
-					const int px = origin[0] + (f3 == 2 ? off : cu);
-					const int py = origin[1] + (f3 == 1 ? off : (f3 == 0 ? cv : cu));
-					const int pz = origin[2] + (f3 == 0 ? off : cv);
-					v[u] = g.dist[((size_t)min(pz, lim) * d.n + min(py, lim)) * d.n + min(px, lim)];
+					const int fi = q / 99, r = q - fi * 99, j = r / 3, part = r - j * 3; // fi: 0 = z-, 1 = y-, 2 = z+, 3 = y+
+					const int face = (fi & 1) + (fi >> 1) * 3;                               // internal face ids 0 (z-), 1 (y-), 3 (z+), 4 (y+)
+					const int off = (face >= 3) ? 32 : 0;
+					const int py = origin[1] + ((face % 3) == 1 ? off : j), pz = origin[2] + ((face % 3) == 0 ? off : j);
+					const signed char* row = g.dist + ((size_t)min(pz, lim) * d.n + min(py, lim)) * d.n + origin[0];
+					signed char* dst = &s.face[face][j * 33];
+					if (part < 2)
+					{
+						const uint4 v = *reinterpret_cast<const uint4*>(row + part * 16);
+						const unsigned w[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+						for (int k = 0; k < 16; ++k) dst[part * 16 + k] = (signed char)(w[k >> 2] >> ((k & 3) * 8));
+					}
+					else dst[32] = row[min(32, lim - origin[0])];
 				}
-#pragma unroll
-				for (int u = 0; u < 4; ++u)
+				// the two faces normal to x: one sample per row of the volume
+				for (int idx0 = tid; idx0 < 2 * 1089; idx0 += 4 * VXB_THREADS)
 				{
-					const int idx = idx0 + u * VXB_THREADS;
-					if (idx < 6 * 1089) (&s.face[0][0])[(idx / 1089) * 1092 + (idx % 1089)] = v[u];
+					signed char v[4];
+#pragma unroll
+					for (int u = 0; u < 4; ++u)
+					{
+						const int idx = min(idx0 + u * VXB_THREADS, 2 * 1089 - 1);
+						const int hi = idx / 1089, r = idx - hi * 1089, j = r / 33, i = r - j * 33;
+						const int px = origin[0] + (hi ? 32 : 0), py = origin[1] + i, pz = origin[2] + j;
+						v[u] = g.dist[((size_t)min(pz, lim) * d.n + min(py, lim)) * d.n + min(px, lim)];
+					}
+#pragma unroll
+					for (int u = 0; u < 4; ++u)
+					{
+						const int idx = idx0 + u * VXB_THREADS;
+						if (idx < 2 * 1089) s.face[idx < 1089 ? 2 : 5][idx % 1089] = v[u];
+					}
+				}
+			}
+			else
+			{
+				// four independent loads in flight per thread
+				for (int idx0 = tid; idx0 < 6 * 1089; idx0 += 4 * VXB_THREADS)
+				{
+					signed char v[4];
+#pragma unroll
+					for (int u = 0; u < 4; ++u)
+					{
+						const int idx = min(idx0 + u * VXB_THREADS, 6 * 1089 - 1);
+						const int face = idx / 1089, r = idx - face * 1089;
+						const int f3 = face >= 3 ? face - 3 : face;
+						const int j = r / 33, i = r - j * 33;
+						const int off = (face >= 3) ? 16 * m : 0, cu = i * h, cv = j * h;
+						// vxb_face_axes: f3 = 0: axis z, (u, v) = (x, y); 1: axis y, (x, z); 2: axis x, (y, z)
+						const int px = origin[0] + (f3 == 2 ? off : cu);
+						const int py = origin[1] + (f3 == 1 ? off : (f3 == 0 ? cv : cu));
+						const int pz = origin[2] + (f3 == 0 ? off : cv);
+						v[u] = g.dist[((size_t)min(pz, lim) * d.n + min(py, lim)) * d.n + min(px, lim)];
+					}
+#pragma unroll
+					for (int u = 0; u < 4; ++u)
+					{
+						const int idx = idx0 + u * VXB_THREADS;
+						if (idx < 6 * 1089) (&s.face[0][0])[(idx / 1089) * 1092 + (idx % 1089)] = v[u];
+					}
 				}
 			}
 		}

@@ -197,9 +197,10 @@ __device__ __forceinline__ void vxb_fence_proxy_async()
 	asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
-// exclusive scan over the 256 threads of the CTA; every thread gets the grand total too
+// exclusive scan over the threads of the CTA (<= 256); every thread gets the grand total too
 __device__ __forceinline__ unsigned vxb_block_scan(unsigned v, unsigned* warpSums /*[8]*/, unsigned& total)
 {
+	const int nwarps = (int)(blockDim.x >> 5);
 	const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	unsigned inc = v;
 #pragma unroll
@@ -215,6 +216,7 @@ __device__ __forceinline__ unsigned vxb_block_scan(unsigned v, unsigned* warpSum
 #pragma unroll
 	for (int w = 0; w < VXB_THREADS / 32; ++w)
 	{
+		if (w >= nwarps) break;
 		const unsigned s = warpSums[w];
 		if ((unsigned)w < warp) base += s;
 		tot += s;
@@ -814,15 +816,15 @@ __device__ __forceinline__ void vxb_tile_complete(signed char* tile, unsigned lo
 		vxb_mbar_wait(mbar, phase);
 		phase ^= 1;
 		// level 0, far grid edge: the +1 plane is outside the volume (TMA zero-fills); the reference clamps (:1037-1047)
-		if (bx == nb - 1) { __syncthreads(); for (int i = tid; i < 17 * 17; i += VXB_THREADS) tile[i * VXB_TILE_PITCH + 16] = tile[i * VXB_TILE_PITCH + 15]; }
-		if (by == nb - 1) { __syncthreads(); for (int i = tid; i < 17 * 17; i += VXB_THREADS) { const int z = i / 17, x = i % 17; tile[(z * 17 + 16) * VXB_TILE_PITCH + x] = tile[(z * 17 + 15) * VXB_TILE_PITCH + x]; } }
-		if (bz == nb - 1) { __syncthreads(); for (int i = tid; i < 17 * 17; i += VXB_THREADS) { const int y = i / 17, x = i % 17; tile[(16 * 17 + y) * VXB_TILE_PITCH + x] = tile[(15 * 17 + y) * VXB_TILE_PITCH + x]; } }
+		if (bx == nb - 1) { __syncthreads(); for (int i = tid; i < 17 * 17; i += (int)blockDim.x) tile[i * VXB_TILE_PITCH + 16] = tile[i * VXB_TILE_PITCH + 15]; }
+		if (by == nb - 1) { __syncthreads(); for (int i = tid; i < 17 * 17; i += (int)blockDim.x) { const int z = i / 17, x = i % 17; tile[(z * 17 + 16) * VXB_TILE_PITCH + x] = tile[(z * 17 + 15) * VXB_TILE_PITCH + x]; } }
+		if (bz == nb - 1) { __syncthreads(); for (int i = tid; i < 17 * 17; i += (int)blockDim.x) { const int y = i / 17, x = i % 17; tile[(16 * 17 + y) * VXB_TILE_PITCH + x] = tile[(15 * 17 + y) * VXB_TILE_PITCH + x]; } }
 	}
 	else
 	{
 		const int lim = n - 1;
 		const signed char* dist = d.grid.dist;
-		for (int i = tid; i < 17 * 17 * 17; i += VXB_THREADS)
+		for (int i = tid; i < 17 * 17 * 17; i += (int)blockDim.x)
 		{
 			const int x = i % 17, y = (i / 17) % 17, z = i / 289;
 			const int gx = min((bx * 16 + x) * m, lim), gy = min((by * 16 + y) * m, lim), gz = min((bz * 16 + z) * m, lim);

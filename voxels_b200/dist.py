@@ -56,6 +56,43 @@ class Ranks:
             self.td.destroy_process_group()
 
 
+def bind_to_gpu_numa_node(device_index):
+    """Pins this process (its threads, and through first-touch its page-locked buffers) to the CPUs of the NUMA node the GPU
+    hangs off, so that N ranks do not fight over one socket's memory controllers during their host<->device copies.
+    Returns the node number, or None when the topology cannot be read (then nothing is changed)."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(device_index)
+        bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/numa_node" % bdf) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            cpus = parse_cpulist(f.read())
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
+
+
+def parse_cpulist(text):
+    """'0-3,8,10-11' -> [0, 1, 2, 3, 8, 10, 11] (the format of /sys/devices/system/node/node*/cpulist)."""
+    out = []
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        if "-" in part:
+            a, b = part.split("-")
+            out += list(range(int(a), int(b) + 1))
+        else:
+            out.append(int(part))
+    return out
+
+
 def tile_origin(rank, n):
     """(x, y) origin of rank's tile in the endless terrain: tiles are laid out along x, n voxels apart."""
     return (rank * n, 0)
