@@ -57,7 +57,9 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-config4", action="store_true", help="skip the second record (2048^3, BASELINE configs[3])")
     ap.add_argument("--no-tiles", action="store_true", help="N > 1: skip the independent-tiles weak-scaling extra")
-    ap.add_argument("--group-planes", type=int, default=0, help="N > 1: planes per cube piece (0 = default)")
+    ap.add_argument("--group-planes", type=int, default=0, help="N > 1: planes per scan group / cube piece (0 = default)")
+    ap.add_argument("--shard-mode", default="replicated", choices=["replicated", "cube"],
+                    help="N > 1: volumes replicated in every rank's HBM (work sharded; default) or sharded as a peer-mapped cube")
     return ap.parse_args()
 
 
@@ -489,10 +491,19 @@ def main():
                     problems = []
                     for l in range(ref.surface_levels(rsurf)):
                         problems += compare.level_diff(ref.surface_level(rsurf, l), dl.surface_level(dsurf, l), "L%d" % l)
+                    stages = None
+                    try:
+                        import ctypes
+                        lib = ctypes.CDLL(os.path.join(REPO, "voxels_b200", "lib", "libvoxels_b200.so"))
+                        st6 = (ctypes.c_double * 6)()
+                        lib.voxels_b200_last_execute_stages(st6)
+                        stages = dict(zip(("materials", "block_offsets", "pack_blob", "upload_decode", "kernels", "download_views"), (round(v, 3) for v in st6)))
+                    except Exception:
+                        pass
                     dl.surface_destroy(dsurf); dl.grid_destroy(g2)
                     ms_d = 1e3 * sum(secs) / len(secs)
                     extra["e2e_dropin"] = {"value": float(n) ** 3 / (ms_d * 1e-3) / 1e6, "unit": "Mvoxels/s", "ms_per_step": ms_d, "best_ms": 1e3 * min(secs), "steps": len(secs),
-                                           "path": "Voxels::Polygonizer::Execute of libvoxels_b200.so on a reference Grid (compressed blocks -> pinned blob -> GPU decode -> kernels -> "
+                                           "host_ms_last": stages, "path": "Voxels::Polygonizer::Execute of libvoxels_b200.so on a reference Grid (compressed blocks -> pinned blob -> GPU decode -> kernels -> "
                                                    "arenas back to the host -> PolygonSurface), host clock around Execute only",
                                            "parity": {"checked": True, "mismatches": len(problems), "first": problems[:3]},
                                            "vs_reference_same_run": (float(n) ** 3 / (ms_d * 1e-3) / 1e6) / v}
@@ -505,8 +516,8 @@ def main():
         scaling = "strong"
     else:
         # ------------------------------------------------------------ N > 1: ONE grid, all ranks
-        sg = ShardedGrid(ranks, n, group_planes=args.group_planes or None)
-        sg.ctx.fill(n, capi.Surface.terrain(n))   # every rank fills the pieces it backs
+        sg = ShardedGrid(ranks, n, group_planes=args.group_planes or None, mode=args.shard_mode)
+        sg.fill(capi.Surface.terrain(n))   # replicated: every rank the whole (read-only) grid; cube: the pieces it backs
         sg.ready()
         stream = torch.cuda.ExternalStream(sg.ctx.stream(), device=dev)
         for _ in range(max(args.warmup, 3)):
@@ -544,8 +555,9 @@ def main():
                     "peak": peak * world, "unit": "GB/s", "frac": ach / (peak * world), "traffic": None, "peak_source": peak_src + " x %d GPUs" % world,
                     "algorithmic_bytes_per_step": bytes_alg_total, "ms_per_step": ms_step}
         config = {"workload": "%d^3 seeded Perlin terrain, ONE grid over %d GPUs (strong scaling), all LOD levels + transition cells" % (n, world),
-                  "grid": "dense int8 distance + uint8 material + uint8 blend; z-pieces of %d planes dealt cyclically to the ranks' HBM, mapped into every peer over NVLink" % sg.group_planes,
-                  "sharding": "work dealt by blocks (super-blocks cut by surface weight); exchange 0 = ncclAllGather of the per-block info, exchange 1 = peer stores of material pages + a one-word ncclAllGather; coarse levels classified by every rank",
+                  "grid": ("dense int8 distance + uint8 material + uint8 blend, read-only, resident in EVERY rank's HBM (3 GiB at 1024^3): every kernel load is local" if args.shard_mode == "replicated"
+                           else "dense int8 distance + uint8 material + uint8 blend; z-pieces of %d planes dealt cyclically to the ranks' HBM, mapped into every peer over NVLink" % sg.group_planes),
+                  "sharding": "work dealt by blocks: every rank scans 1/N of the layers; exchange 0 = ncclAllGather of the per-block info; super-blocks cut by surface weight; exchange 1 = peer stores of material pages + a one-word ncclAllGather; coarse levels classified by every rank; output stays on the rank",
                   "l2": "inputs larger than the 126 MB L2; no flush", "vertices": V, "indices": I, "transition_vertices": TV, "transition_indices": TI,
                   "blocks_emitted": int(len(directory)), "blocks_per_rank": per_rank_blocks, "vertices_per_rank": per_rank_verts, "nccl_ranks": world,
                   "host_binding": "every rank pinned to the CPUs of its GPU's NUMA node (rank 0: node %s)" % numa_node}
@@ -582,9 +594,11 @@ def main():
             moved = [0, 0]
 
             def step_e2e():
-                ranks.barrier()                                       # no peer still reads the pieces this upload overwrites
-                sg.ctx.upload_packed(h_blob.data_ptr(), blob_bytes)   # this rank's pieces only
-                ranks.barrier()                                       # every piece resident before any rank reads its peers'
+                if args.shard_mode == "cube":
+                    ranks.barrier()                                   # no peer still reads the pieces this upload overwrites
+                sg.upload_packed(h_blob.data_ptr(), blob_bytes)       # replicated: the whole grid; cube: this rank's pieces only
+                if args.shard_mode == "cube":
+                    ranks.barrier()                                   # every piece resident before any rank reads its peers'
                 rc = sg.ctx.polygonize_sharded(3, flags)
                 if rc != 0:
                     raise RuntimeError("arena overflow inside the timed region")
@@ -598,9 +612,9 @@ def main():
             ms_e2e = timed(step_e2e, esteps, stream)
             d2h_total = ranks.sum_over_ranks(moved[1])
             e2e = {"value": float(n) ** 3 / (ms_e2e * 1e-3) / 1e6, "unit": "Mvoxels/s", "ms_per_step": ms_e2e, "steps": esteps,
-                   "h2d_bytes_per_step": blob_bytes, "d2h_bytes_per_step": int(d2h_total),
-                   "path": "per rank: vxb_grid_upload_packed of its own pieces (pinned host -> HBM, RLE decode on the GPU), barrier, vxb_polygonize_sharded, "
-                           "vxb_result_download of its own blocks; bytes are the sums over the ranks (every rank reads its byte ranges of the same blob)"}
+                   "h2d_bytes_per_step": blob_bytes * (world if args.shard_mode == "replicated" else 1), "d2h_bytes_per_step": int(d2h_total),
+                   "path": "per rank: vxb_grid_upload_packed (pinned host -> HBM, RLE decode on the GPU; replicated: the whole grid over the rank's own PCIe link, cube: its pieces), "
+                           "vxb_polygonize_sharded, vxb_result_download of its own blocks; bytes are the sums over the ranks"}
             del out, h_blob
         sg.close()
         sharding_note = "strong scaling: the SAME %d^3 grid on every N" % n
@@ -625,8 +639,8 @@ def main():
             torch.cuda.empty_cache()
             import numpy as np
             if world > 1:
-                sg4 = ShardedGrid(ranks, n4, key="c4-%s" % os.environ.get("MASTER_PORT", "0"))
-                sg4.ctx.fill(n4, capi.Surface.terrain(n4))
+                sg4 = ShardedGrid(ranks, n4, key="c4-%s" % os.environ.get("MASTER_PORT", "0"), mode=args.shard_mode)
+                sg4.fill(capi.Surface.terrain(n4))
                 sg4.ready()
                 st4 = torch.cuda.ExternalStream(sg4.ctx.stream(), device=dev)
                 for _ in range(3):

@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--group-planes", type=int, default=0)
+    ap.add_argument("--mode", default="replicated", choices=["replicated", "cube"])
     ap.add_argument("--verify", action="store_true")
     ap.add_argument("--reference", action="store_true")
     args = ap.parse_args()
@@ -40,9 +41,9 @@ def main():
     torch.cuda.set_device(dev)
     ranks = Ranks("nccl", dev)
     n = args.size
-    sg = ShardedGrid(ranks, n, group_planes=args.group_planes or None)
+    sg = ShardedGrid(ranks, n, group_planes=args.group_planes or None, mode=args.mode)
     terrain = capi.Surface.terrain(n)
-    sg.ctx.fill(n, terrain)   # every rank fills the pieces it backs (Grid::Create on the device)
+    sg.fill(terrain)   # Grid::Create on the device: the whole grid on every rank (replicated) or the pieces it backs (cube)
     sg.ready()
     stream = torch.cuda.ExternalStream(sg.ctx.stream(), device=dev)
     for _ in range(args.warmup):
@@ -52,10 +53,7 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(args.steps):
-        if ranks.world > 1:
-            assert sg.ctx.polygonize_sharded(3, 0) == 0
-        else:
-            sg.polygonize()
+        assert sg.ctx.polygonize_sharded(3, 0) == 0
         inner.append(sg.ctx.info().device_ms)
     e1.record(stream)
     ranks.barrier(); torch.cuda.synchronize(dev)
@@ -74,12 +72,26 @@ def main():
     stats = (stats.cpu().numpy() & 0xFFFFFFFF).astype(np.uint32)
     out = {"metric": "Mvoxels/s polygonized (one grid over the GPUs)", "value": float(n) ** 3 / (ms * 1e-3) / 1e6, "unit": "Mvoxels/s",
            "n_gpus": ranks.world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "scaling": "strong",
-           "config": {"workload": "%d^3 seeded Perlin terrain, all LOD levels + transition cells, pieces of %d planes dealt cyclically" % (n, sg.group_planes),
+           "config": {"workload": "%d^3 seeded Perlin terrain, all LOD levels + transition cells, volumes %s, scan groups / pieces of %d planes dealt cyclically" % (n, args.mode, sg.group_planes),
                       "exchange": "ncclAllGather of the per-block info + peer stores of material pages (ordered by a one-word ncclAllGather), inside every step"},
            "blocks_total": int(len(directory)), "blocks_per_rank": [int((owner == r).sum()) for r in range(ranks.world)],
            "vertices_per_rank": [int(directory["vertex_count"][owner == r].sum()) for r in range(ranks.world)],
            "device_ms_per_rank": [round(float(v), 3) for v in per_rank.cpu().numpy()], "launches_per_step": int(info.kernel_launches)}
 
+    # where the step goes, per rank: one extra step with per-kernel events (plain launches, one stream)
+    kinds = ["scan+coarse lattice", "block walk (info, pyramid, plan, select)", "block kernels levels>=1 + coarse", "block kernel level 0", "vertices levels>=1",
+             "triangles levels>=1", "transitions", "finish", "exchange 0 (lattice publish + all-gather)", "exchange 1 (page publish + all-gather)"]
+    ranks.barrier()
+    sg.ctx.polygonize_sharded(3, voxels_b200.FLAG_KERNEL_TIMES)
+    if True:
+        mine_k = torch.tensor([sg.ctx.kernel_ms(k)[0] for k in range(10)], dtype=torch.float64, device=dev)
+        all_k = torch.zeros(ranks.world * 10, dtype=torch.float64, device=dev)
+        if ranks.td is not None:
+            ranks.td.all_gather_into_tensor(all_k, mine_k)
+        else:
+            all_k = mine_k
+        all_k = all_k.cpu().numpy().reshape(ranks.world, 10)
+        out["kernel_ms_per_rank"] = {kinds[k]: [round(float(v), 3) for v in all_k[:, k]] for k in range(10)}
     if args.verify:
         import compare
         problems = []

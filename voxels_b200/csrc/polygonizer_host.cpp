@@ -323,6 +323,25 @@ bool uploadMaterials(vxb_context* ctx, const MaterialMap* materials)
 }
 }
 
+namespace
+{
+// host-side stage times of the last full Execute (milliseconds): materials, block offsets, blob packing, upload + decode,
+// kernels, download + block views - read by bench.py through voxels_b200_last_execute_stages
+double g_LastStages[6] = { 0, 0, 0, 0, 0, 0 };
+struct StageClock
+{
+	std::chrono::steady_clock::time_point last = std::chrono::steady_clock::now();
+	void mark(int stage)
+	{
+		const auto now = std::chrono::steady_clock::now();
+		g_LastStages[stage] = std::chrono::duration<double, std::milli>(now - last).count();
+		last = now;
+	}
+};
+}
+
+extern "C" void voxels_b200_last_execute_stages(double* out6) { for (int i = 0; i < 6; ++i) out6[i] = g_LastStages[i]; }
+
 PolygonSurface* TransVoxelImpl::Execute(const Grid& grid, const MaterialMap* materials, Modification* modification)
 {
 	char buffer[VOXELS_LOG_SIZE];
@@ -357,7 +376,9 @@ PolygonSurface* TransVoxelImpl::Execute(const Grid& grid, const MaterialMap* mat
 		releaseContext(ctx);
 		return nullptr;
 	};
+	StageClock clock;
 	if (!uploadMaterials(ctx, materials)) return fail("material table upload failed");
+	clock.mark(0);
 
 	// ---- grid -> device: the grid store's compressed blocks, laid out as PackForSave does (VoxelGrid.cpp:269-315: header,
 	// 3 sizes per block, then per block {flags, distance, material, blend}) in page-locked staging - a parallel memcpy of
@@ -379,6 +400,7 @@ PolygonSurface* TransVoxelImpl::Execute(const Grid& grid, const MaterialMap* mat
 		}
 		offsets[count] = off;
 		if (!m_Staging->Blob.ensure(off)) return fail("pinned staging allocation failed");
+		clock.mark(1);
 		unsigned char* blob = static_cast<unsigned char*>(m_Staging->Blob.p);
 		const uint32_t header[4] = { 1u, n, n, n };
 		memcpy(blob, header, 16);
@@ -395,13 +417,16 @@ PolygonSurface* TransVoxelImpl::Execute(const Grid& grid, const MaterialMap* mat
 			memcpy(out, blk.MaterialData.data(), sz[1]); out += sz[1];
 			memcpy(out, blk.BlendData.data(), sz[2]);
 		}
+		clock.mark(2);
 		if (vxb_grid_upload_packed(ctx, blob, off) != VXB_OK) return fail("grid upload failed");
+		clock.mark(3);
 	}
 
 	// ---- polygonize on the device ----
 	if (vxb_polygonize(ctx, 0, 0) != VXB_OK) return fail("polygonization failed");
 	vxb_result_info info;
 	if (vxb_result_info_get(ctx, &info) != VXB_OK) return fail("no result");
+	clock.mark(4);
 
 	SurfaceImpl* surface = new SurfaceImpl;
 	surface->Extents = float3(float(n), float(n), float(n)); // (W, H, D) :481
@@ -419,6 +444,7 @@ PolygonSurface* TransVoxelImpl::Execute(const Grid& grid, const MaterialMap* mat
 		surface->CacheBytes = unsigned(total);
 	}
 	logUnmapped(ctx);
+	clock.mark(5);
 	if (modification) modification->Map = surface; // (the reference would have dereferenced the null Map, :443)
 	return surface;
 }

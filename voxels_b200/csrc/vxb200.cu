@@ -117,7 +117,7 @@ struct vxb_context
 	DevBuf<uint8_t> lattice1;
 	uint8_t* latticePtr = nullptr;  // lattice1.p, or the cube's fourth channel
 	bool haveLattice1 = false, latticeOff = false;
-	int gridBlock[3] = { 0, 0, 0 }, gridBlock0Small = 0, level0Threads = 128, gridDecideBig = 0, gridTransition = 0;
+	int gridBlock[3] = { 0, 0, 0 }, gridBlock0Small = 0, level0Threads = 256, gridDecideBig = 0, gridTransition = 0;
 	DevBuf<unsigned char> mixInfo, coarseDone;
 	// lattices of the coarse levels (VxbDev::coarseLattice): own buffer, or - sharded runs - an area of the buffer the peers map
 	DevBuf<unsigned char> coarseLatticeBuf;
@@ -180,8 +180,8 @@ struct vxb_context
 	std::vector<vxb_block_record> sortedRecords;
 	uint8_t lutValid[256];
 	std::vector<uint8_t> unmapped; // material ids of vertices whose material had no mapping, in logging order
-	float kindMs[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
-	uint32_t kindLaunches[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+	float kindMs[10] = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 };        // 8, 9: the two exchanges of a sharded run
+	uint32_t kindLaunches[10] = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 };
 };
 
 namespace
@@ -235,21 +235,22 @@ int encodeTileMap(vxb_context* ctx, CUtensorMap* map, const void* base, uint32_t
 
 size_t blocksAtLevel(uint32_t n, int level) { const size_t nb = (n / 16) >> level; return nb * nb * nb; }
 
-// coarse levels: from the first level with <= 4096 blocks (but not below 2) everything runs in one launch
+// coarse levels: from the first level with <= 512 blocks (but not below 2) everything runs in one launch
 int coarseLoFor(uint32_t n, int levels)
 {
 	int lo = 2;
-	while (lo < levels && blocksAtLevel(n, lo) > 4096) ++lo;
+	while (lo < levels && blocksAtLevel(n, lo) > 512) ++lo;
 	return lo;
 }
+
+#define VXB_LATTICE_LO 2 // levels >= 2 have their own sample lattice (VxbDev::coarseLattice)
 
 // byte layout of the coarse levels' lattices in one buffer: level l at offsets[l], (h + 1)^2 rows of h + 16 bytes
 size_t coarseLatticeLayout(uint32_t n, int levels, size_t offsets[VXB_MAX_LEVELS])
 {
 	size_t total = 0;
-	const int lo = coarseLoFor(n, levels);
 	for (int l = 0; l < VXB_MAX_LEVELS; ++l) offsets[l] = 0;
-	for (int l = lo; l < levels; ++l)
+	for (int l = VXB_LATTICE_LO; l < levels; ++l)
 	{
 		const size_t h = n >> l;
 		offsets[l] = total;
@@ -273,7 +274,7 @@ int buildCoarseLattices(vxb_context* ctx, unsigned char* sharedBase)
 	VXB_CUDA(ctx, ctx->coarseMaps.ensure(VXB_MAX_LEVELS));
 	CUtensorMap maps[VXB_MAX_LEVELS];
 	memset(maps, 0, sizeof(maps));
-	for (int l = ctx->coarseLo; l < ctx->levels; ++l)
+	for (int l = VXB_LATTICE_LO; l < ctx->levels; ++l)
 	{
 		const cuuint64_t h = n >> l;
 		const cuuint64_t dims[3] = { h + 1, h + 1, h + 1 };
@@ -344,7 +345,7 @@ struct KernelTimer
 	void end() { if (!on) return; cudaEventRecord(ctx->kevents[used + 1], ctx->stream); used += 2; }
 	void collect()
 	{
-		for (int k = 0; k < 8; ++k) ctx->kindMs[k] = 0.f;
+		for (int k = 0; k < 10; ++k) ctx->kindMs[k] = 0.f;
 		if (!on) return;
 		for (size_t i = 0; i < kinds.size(); ++i)
 		{
@@ -648,7 +649,7 @@ int vxb_create(int device, vxb_context** out)
 
 	ctx->graphDisabled = getenv("VXB200_NO_GRAPH") != nullptr; // plain launches (debugging, A/B timing)
 	struct KernelSetup { const void* fn; size_t smem; int* grid; const char* name; int threads; };
-	ctx->level0Threads = getenv("VXB200_L0_THREADS") ? atoi(getenv("VXB200_L0_THREADS")) : 128; // A/B switch: 128 (default) or 256
+	ctx->level0Threads = getenv("VXB200_L0_THREADS") ? atoi(getenv("VXB200_L0_THREADS")) : 256; // A/B switch: 256 (default: measured faster) or 128
 	const KernelSetup setups[6] = {
 		{ (const void*)vxb_block_kernel<0, 256>, sizeof(VxbBlockSmem<0, 256>), &ctx->gridBlock[0], "vxb_block_kernel<0, 256>", 256 },
 		{ (const void*)vxb_block_kernel<0, 128>, sizeof(VxbBlockSmem<0, 128>), &ctx->gridBlock0Small, "vxb_block_kernel<0, 128>", 128 },
@@ -787,24 +788,59 @@ int vxb_grid_upload_packed(vxb_context* ctx, const void* blob, size_t size)
 	bool corrupt = false, truncated = false;
 	unsigned long long off = head;
 	{
+		// per-block byte offsets = prefix sum of the size table, and a check of every block's flags word, on all host threads:
+		// chunk sums from the table, a short serial prefix over the chunks, then offsets + checks per chunk
 		const unsigned char* table = bytes + 16;
-		for (size_t b = 0; b < blocks; ++b)
+		const int chunks = 256;
+		const size_t per = (blocks + chunks - 1) / chunks;
+		unsigned long long chunkBytes[chunks + 1];
+		int bad = 0;
+		#pragma omp parallel for schedule(static) reduction(|:bad)
+		for (int c = 0; c < chunks; ++c)
 		{
-			uint32_t sz[3];
-			memcpy(sz, table + b * 12, 12);
-			if (sz[0] > 4096 || sz[1] > 4096 || sz[2] > 4096) { corrupt = true; break; }
-			hostOffsets[b] = off;
-			if (off + 4 > size) { truncated = true; break; }
-			// the block's flags word: a raw channel holds exactly 4096 bytes, a run-length coded one whole (length, value) pairs
-			uint32_t bflags;
-			memcpy(&bflags, bytes + off, 4);
-			for (int ch = 0; ch < 3; ++ch)
+			unsigned long long sum = 0;
+			const size_t b0 = std::min(blocks, per * c), b1 = std::min(blocks, b0 + per);
+			for (size_t b = b0; b < b1; ++b)
 			{
-				const bool raw = (bflags >> (1 + ch)) & 1u;
-				if (raw ? (sz[ch] != 4096) : (sz[ch] == 0 || (sz[ch] & 1u))) corrupt = true;
+				uint32_t sz[3];
+				memcpy(sz, table + b * 12, 12);
+				if (sz[0] > 4096 || sz[1] > 4096 || sz[2] > 4096) bad |= 1;
+				sum += 4ull + sz[0] + sz[1] + sz[2];
 			}
-			if (corrupt) break;
-			off += 4ull + sz[0] + sz[1] + sz[2];
+			chunkBytes[c] = sum;
+		}
+		if (bad) corrupt = true;
+		if (!corrupt)
+		{
+			unsigned long long run = head;
+			for (int c = 0; c < chunks; ++c) { const unsigned long long v = chunkBytes[c]; chunkBytes[c] = run; run += v; }
+			off = run;
+			if (off > size) truncated = true;
+		}
+		if (!corrupt && !truncated)
+		{
+			#pragma omp parallel for schedule(static) reduction(|:bad)
+			for (int c = 0; c < chunks; ++c)
+			{
+				unsigned long long o = chunkBytes[c];
+				const size_t b0 = std::min(blocks, per * c), b1 = std::min(blocks, b0 + per);
+				for (size_t b = b0; b < b1; ++b)
+				{
+					uint32_t sz[3];
+					memcpy(sz, table + b * 12, 12);
+					hostOffsets[b] = o;
+					// the block's flags word: a raw channel holds exactly 4096 bytes, a run-length coded one whole (length, value) pairs
+					uint32_t bflags;
+					memcpy(&bflags, bytes + o, 4);
+					for (int ch = 0; ch < 3; ++ch)
+					{
+						const bool raw = (bflags >> (1 + ch)) & 1u;
+						if (raw ? (sz[ch] != 4096) : (sz[ch] == 0 || (sz[ch] & 1u))) bad |= 1;
+					}
+					o += 4ull + sz[0] + sz[1] + sz[2];
+				}
+			}
+			if (bad) corrupt = true;
 		}
 	}
 	const double msTable = msSince(t0);
@@ -1164,7 +1200,7 @@ static int runPolygonize(vxb_context* ctx, uint32_t maxLevels, uint32_t flags, c
 	const size_t nb0 = n / 16, blocks0 = nb0 * nb0 * nb0;
 	const bool sharded = shardPhase >= 0;
 	vxb_context::Shard& sh = ctx->shard;
-	const bool kernelTimes = (flags & VXB_FLAG_KERNEL_TIMES) != 0 && !sharded;
+	const bool kernelTimes = (flags & VXB_FLAG_KERNEL_TIMES) != 0 && (!sharded || shardPhase == 3);
 
 	// ---- device state ----
 	VXB_CUDA(ctx, ctx->scanFlags.ensure(blocks0));
@@ -1219,9 +1255,10 @@ static int runPolygonize(vxb_context* ctx, uint32_t maxLevels, uint32_t flags, c
 	dev.coarseLo = coarseLo; dev.coarseDone = ctx->coarseDone.p;
 	VxbCoarseLattices scanLat;
 	memset(&scanLat, 0, sizeof(scanLat));
-	scanLat.lo = coarseLo; scanLat.levels = levels;
-	for (int l = coarseLo; l < levels; ++l) { dev.coarseLattice[l] = ctx->coarseLatticeBase + ctx->coarseLatticeOff[l]; scanLat.p[l] = dev.coarseLattice[l]; }
+	scanLat.lo = VXB_LATTICE_LO; scanLat.levels = levels;
+	for (int l = VXB_LATTICE_LO; l < levels; ++l) { dev.coarseLattice[l] = ctx->coarseLatticeBase + ctx->coarseLatticeOff[l]; scanLat.p[l] = dev.coarseLattice[l]; }
 	dev.coarseMaps = ctx->coarseMaps.p;
+	dev.latticeLo = VXB_LATTICE_LO;
 	dev.worklist = ctx->worklist.p;
 	dev.records = ctx->records.p; dev.rcap = (unsigned)totalBlocks;
 	dev.counters = ctx->counters.p; dev.lut = ctx->lut.p;
@@ -1259,7 +1296,7 @@ static int runPolygonize(vxb_context* ctx, uint32_t maxLevels, uint32_t flags, c
 			++peers.count;
 		}
 		peerLat.count = peers.count;
-		if (shardPhase == 3 && (!sh.comm || !ncclApi().ok)) return fail(ctx, VXB_ERR_STATE, "vxb_polygonize_sharded: phase 3 needs vxb_shard_nccl_init");
+		if (shardPhase == 3 && sh.world > 1 && (!sh.comm || !ncclApi().ok)) return fail(ctx, VXB_ERR_STATE, "vxb_polygonize_sharded: phase 3 needs vxb_shard_nccl_init");
 	}
 	const int scanWorld = sharded ? (int)sh.world : 1, scanRank = sharded ? (int)sh.rank : 0, scanGroup = sharded ? (int)sh.groupLayers : (int)nb0;
 
@@ -1284,10 +1321,12 @@ static int runPolygonize(vxb_context* ctx, uint32_t maxLevels, uint32_t flags, c
 
 		KernelTimer timer{ ctx, kernelTimes };
 		uint32_t launches = 0;
-		for (int k = 0; k < 8; ++k) ctx->kindLaunches[k] = 0;
+		for (int k = 0; k < 10; ++k) ctx->kindLaunches[k] = 0;
 		const unsigned flatGrid = (unsigned)ctx->smCount * 8;
 		cudaStream_t st = ctx->stream;
 
+		bool latticeForked = false;
+		auto joinLattice = [&]() { if (latticeForked) { cudaStreamWaitEvent(st, ctx->evVerts, 0); latticeForked = false; } };
 		// ---- the pieces of a run; a full run is all of them in order, a sharded run has an exchange after the first two ----
 		auto scanPart = [&]() -> int
 		{
@@ -1302,14 +1341,32 @@ static int runPolygonize(vxb_context* ctx, uint32_t maxLevels, uint32_t flags, c
 			const int perCta = nb0 >= 32 ? 32 : 8;
 			const dim3 grid((unsigned)((nb0 + perCta - 1) / perCta), (unsigned)nb0, (unsigned)myLayers);
 			timer.begin(0);
-			if (perCta == 32) vxb_scan_kernel<32><<<grid, VXB_THREADS, 0, st>>>(ctx->dDist, (int)n, ctx->scanFlags.p, ctx->haveLattice1 ? ctx->latticePtr : nullptr, scanLat, scanGroup, scanWorld, scanRank, zBase);
-			else vxb_scan_kernel<8><<<grid, VXB_THREADS, 0, st>>>(ctx->dDist, (int)n, ctx->scanFlags.p, ctx->haveLattice1 ? ctx->latticePtr : nullptr, scanLat, scanGroup, scanWorld, scanRank, zBase);
+			if (perCta == 32) vxb_scan_kernel<32><<<grid, VXB_THREADS, 0, st>>>(ctx->dDist, (int)n, ctx->scanFlags.p, ctx->haveLattice1 ? ctx->latticePtr : nullptr, scanGroup, scanWorld, scanRank, zBase);
+			else vxb_scan_kernel<8><<<grid, VXB_THREADS, 0, st>>>(ctx->dDist, (int)n, ctx->scanFlags.p, ctx->haveLattice1 ? ctx->latticePtr : nullptr, scanGroup, scanWorld, scanRank, zBase);
 			timer.end(); ++launches; ++ctx->kindLaunches[0];
-			if (sharded && peerLat.count && coarseLo < levels)
+			if (VXB_LATTICE_LO < computed)
+			{
+				// the sample lattices of levels >= 2: needed only by vxb_block_kernel<2>, so a single-GPU run computes them on the
+				// second stream next to the block walk and the level-0 kernel; a sharded rank does the rows of its own planes here
+				const bool cubeRows = sharded && ctx->cube.active; // the volumes are split over the ranks: own rows here, then published
+				cudaStream_t ls = (cubeRows || kernelTimes || shardPhase == 0) ? st : ctx->stream2;
+				if (ls != st)
+				{
+					VXB_CUDA(ctx, cudaEventRecord(ctx->evDecide0, st));
+					VXB_CUDA(ctx, cudaStreamWaitEvent(ls, ctx->evDecide0, 0));
+				}
+				timer.begin(1);
+				vxb_coarse_lattice_kernel<<<(unsigned)ctx->smCount * 4, 256, 0, ls>>>(reinterpret_cast<const signed char*>(ctx->dDist), (int)n, scanLat,
+					cubeRows ? (int)sh.groupLayers * 16 : 1, cubeRows ? (int)sh.world : 0, cubeRows ? (int)sh.rank : 0);
+				timer.end(); ++launches; ++ctx->kindLaunches[1];
+				if (ls != st) { VXB_CUDA(ctx, cudaEventRecord(ctx->evVerts, ls)); latticeForked = true; } // joined before the first kernel that reads a lattice
+			}
+			if (sharded && ctx->cube.active && peerLat.count && VXB_LATTICE_LO < levels)
 			{
 				// the lattice planes of my layers -> every peer (ordered before the peers' coarse levels by the exchanges)
+				timer.begin(8);
 				vxb_publish_lattice_kernel<<<(unsigned)ctx->smCount, VXB_THREADS, 0, st>>>(dev, peerLat, ctx->coarseLatticeBase);
-				++launches;
+				timer.end(); ++launches; ++ctx->kindLaunches[8];
 			}
 			const size_t mine = myLayers * nb0 * nb0;
 			const unsigned g2 = (unsigned)std::min<size_t>((mine + 255) / 256, (size_t)ctx->smCount * 8);
@@ -1338,7 +1395,7 @@ static int runPolygonize(vxb_context* ctx, uint32_t maxLevels, uint32_t flags, c
 				vxb_pyramid_kernel<<<ctasA + (unsigned)ctasB, 256, 0, st>>>(dev, ctasA);
 				timer.end(); ++launches; ++ctx->kindLaunches[1];
 			}
-			if (sharded) { vxb_plan_kernel<<<1, 1024, 0, st>>>(dev); ++launches; }
+			if (sharded) { timer.begin(1); vxb_plan_kernel<<<1, 1024, 0, st>>>(dev); timer.end(); ++launches; ++ctx->kindLaunches[1]; }
 			if (selectLevel(0))
 			{
 				timer.begin(3);
@@ -1350,11 +1407,12 @@ static int runPolygonize(vxb_context* ctx, uint32_t maxLevels, uint32_t flags, c
 			for (int l = 1; l < coarseLo && l < computed; ++l)
 			{
 				if (!selectLevel(l)) continue;
+				if (l >= VXB_LATTICE_LO) joinLattice();
 				timer.begin(2);
 				vxb_block_kernel<1, 256><<<ctx->gridBlock[1], VXB_THREADS, sizeof(VxbBlockSmem<1, 256>), st>>>(ctx->tmap, ctx->tmap1, dev, l);
 				timer.end(); ++launches; ++ctx->kindLaunches[2];
 			}
-			if (sharded && peers.count) { vxb_publish_kernel<<<(unsigned)ctx->smCount * 4, VXB_THREADS, 0, st>>>(dev, peers); ++launches; }
+			if (sharded && peers.count) { timer.begin(9); vxb_publish_kernel<<<(unsigned)ctx->smCount * 4, VXB_THREADS, 0, st>>>(dev, peers); timer.end(); ++launches; ++ctx->kindLaunches[9]; }
 			VXB_CUDA(ctx, cudaGetLastError());
 			return VXB_OK;
 		};
@@ -1362,6 +1420,7 @@ static int runPolygonize(vxb_context* ctx, uint32_t maxLevels, uint32_t flags, c
 		{
 			if (computed > coarseLo)
 			{
+				joinLattice(); // the lattices are complete
 				timer.begin(2);
 				vxb_block_kernel<2, 256><<<ctx->gridBlock[2], VXB_THREADS, sizeof(VxbBlockSmem<2, 256>), st>>>(ctx->tmap, ctx->tmap1, dev, coarseLo);
 				timer.end(); ++launches; ++ctx->kindLaunches[2];
@@ -1397,6 +1456,7 @@ static int runPolygonize(vxb_context* ctx, uint32_t maxLevels, uint32_t flags, c
 					VXB_CUDA(ctx, cudaStreamWaitEvent(st, ctx->evJoin, 0));
 				}
 			}
+			joinLattice();
 			timer.begin(7);
 			vxb_finish_kernel<<<(unsigned)ctx->smCount * 2, VXB_THREADS, 0, st>>>(dev);
 			timer.end(); ++launches; ++ctx->kindLaunches[7];
@@ -1405,7 +1465,10 @@ static int runPolygonize(vxb_context* ctx, uint32_t maxLevels, uint32_t flags, c
 		};
 		auto exchange = [&](int which) -> int
 		{
+			if (sh.world == 1) return VXB_OK; // one rank: nothing to exchange
 			const NcclApi& nccl = ncclApi();
+			timer.begin(8 + which);
+			++ctx->kindLaunches[8 + which];
 			if (which == 0)
 			{
 				// all-gather of the block info: every rank's layers are one contiguous chunk (rank-major layout)
@@ -1420,6 +1483,7 @@ static int runPolygonize(vxb_context* ctx, uint32_t maxLevels, uint32_t flags, c
 				const int r = nccl.allGather(sh.barrierBuf.p + sh.rank, sh.barrierBuf.p, 8, /*ncclUint8*/ 1, sh.comm, st);
 				if (r != 0) return failNccl(ctx, "ncclAllGather (page exchange barrier)", r);
 			}
+			timer.end();
 			return VXB_OK;
 		};
 		auto enqueueAll = [&]() -> int
@@ -1630,7 +1694,7 @@ int vxb_shard_configure(vxb_context* ctx, uint32_t rank, uint32_t world, uint32_
 	}
 	sh.bufBytes = sh.pagesBytes + sh.validBytes + sh.latticeBytes;
 	const VmmApi& api = vmmApi();
-	if (ctx->cube.active && api.ok)
+	if (api.ok)
 	{
 		// exportable (the peers map it and store their pages into it)
 		const CUmemAllocationProp prop = slabProp(ctx->device);
@@ -1698,7 +1762,7 @@ int vxb_shard_export(vxb_context* ctx, int* fd)
 {
 	if (!ctx || !fd) return VXB_ERR_ARGUMENT;
 	const vxb_context::Shard& sh = ctx->shard;
-	if (!sh.on || !sh.pagesVmm) return fail(ctx, VXB_ERR_STATE, "vxb_shard_export: needs vxb_shard_configure on a context with a cube");
+	if (!sh.on || !sh.pagesVmm) return fail(ctx, VXB_ERR_STATE, "vxb_shard_export: needs vxb_shard_configure (and a driver with the virtual memory management API)");
 	cudaSetDevice(ctx->device);
 	int out = -1;
 	VXB_CU(ctx, vmmApi().exportHandle(&out, sh.pagesHandle, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0));
@@ -1919,7 +1983,7 @@ void vxb_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 int vxb_kernel_ms(vxb_context* ctx, int which, float* ms, uint32_t* launches)
 {
-	if (!ctx || which < 0 || which > 7) return VXB_ERR_ARGUMENT;
+	if (!ctx || which < 0 || which > 9) return VXB_ERR_ARGUMENT;
 	if (ms) *ms = ctx->kindMs[which];
 	if (launches) *launches = ctx->kindLaunches[which];
 	return VXB_OK;

@@ -240,29 +240,45 @@ __global__ void __launch_bounds__(T, (MODE == 0 ? (T == 128 ? 5 : 3) : (MODE == 
 
 		if (MODE == 2)
 		{
-			// wait for the children of this run (blocks of the previous coarse level inside the run's range), then the block walk test
-			if (tid == 0)
+			// warp 0: wait for the children of this run (blocks of the previous coarse level inside the run's range), one lane
+			// each, then the block walk test (vxb_coarse_block_needed) with one lane per child-level neighbour
+			if (tid < 32)
 			{
-				if (level > d.coarseLo)
+				const int cnb = nb * 2, cl = level - 1;
+				if (level > d.coarseLo && tid < 8)
 				{
-					const int cnb = nb * 2, cl = level - 1;
-					for (int q = 0; q < 8; ++q)
+					const int cx = bx * 2 + (tid & 1), cy = by * 2 + ((tid >> 1) & 1), cz = bz * 2 + (tid >> 2);
+					const bool inRun = !(d.ranged && (cx < d.rangeMin[cl][0] || cx >= d.rangeMax[cl][0] || cy < d.rangeMin[cl][1] || cy >= d.rangeMax[cl][1] || cz < d.rangeMin[cl][2] || cz >= d.rangeMax[cl][2]));
+					if (inRun)
 					{
-						const int cx = bx * 2 + (q & 1), cy = by * 2 + ((q >> 1) & 1), cz = bz * 2 + (q >> 2);
-						if (d.ranged && (cx < d.rangeMin[cl][0] || cx >= d.rangeMax[cl][0] || cy < d.rangeMin[cl][1] || cy >= d.rangeMax[cl][1] || cz < d.rangeMin[cl][2] || cz >= d.rangeMax[cl][2])) continue;
 						const volatile unsigned char* flag = d.coarseDone + d.coarseBase[cl] + ((size_t)cz * cnb + cy) * cnb + cx;
 						unsigned spins = 0;
-						while (!*flag) { __nanosleep(64); if (++spins > (1u << 24)) __trap(); }
+						while (!*flag) { __nanosleep(32); if (++spins > (1u << 24)) __trap(); }
 					}
 					__threadfence();
 				}
-				s.take = vxb_coarse_block_needed(d, level, bx, by, bz) ? 1u : 0u;
-				if (s.take)
+				__syncwarp();
+				unsigned u = 0, anyChild = 0;
+				if (tid < 27)
 				{
-					// the block's 17^3 samples: one TMA box of the level's lattice (far-edge entries included, no fix-up)
-					vxb_fence_proxy_async();
-					vxb_mbar_expect_tx(&s.mbar[0], VXB_TILE_BYTES);
-					vxb_tma_load_3d(s.tiles[0], d.coarseMaps + level, bx * 16, by * 16, bz * 16, &s.mbar[0]);
+					const int x = tid % 3, y = (tid / 3) % 3, z = tid / 9;
+					const int cx = min(2 * bx + x, cnb - 1), cy = min(2 * by + y, cnb - 1), cz = min(2 * bz + z, cnb - 1);
+					const size_t cb = ((size_t)cz * cnb + cy) * cnb + cx;
+					u = d.mixInfo[cl][cb];
+					if (x < 2 && y < 2 && z < 2) anyChild = __ldcg(d.cacheValid[cl] + cb);
+				}
+				u = __reduce_or_sync(0xFFFFFFFFu, u);
+				anyChild = __reduce_or_sync(0xFFFFFFFFu, anyChild);
+				if (tid == 0)
+				{
+					s.take = (u == 3u || anyChild != 0u) ? 1u : 0u;
+					if (s.take)
+					{
+						// the block's 17^3 samples: one TMA box of the level's lattice (far-edge entries included, no fix-up)
+						vxb_fence_proxy_async();
+						vxb_mbar_expect_tx(&s.mbar[0], VXB_TILE_BYTES);
+						vxb_tma_load_3d(s.tiles[0], d.coarseMaps + level, bx * 16, by * 16, bz * 16, &s.mbar[0]);
+					}
 				}
 			}
 			__syncthreads();
@@ -458,6 +474,8 @@ __global__ void __launch_bounds__(T, (MODE == 0 ? (T == 128 ? 5 : 3) : (MODE == 
 			}
 		}
 		__syncthreads(); // the votes of this block are visible to the CTA (pass A reads the page back)
+		// coarse levels: the parent only needs this block's page, so it is released before the block's own emission work
+		if (MODE == 2 && tid == 0) { __threadfence(); *(volatile unsigned char*)(d.coarseDone + d.coarseBase[level] + coordId) = 1; }
 
 		if (ntc > 0 && !inCap)
 		{
@@ -701,7 +719,6 @@ __global__ void __launch_bounds__(T, (MODE == 0 ? (T == 128 ? 5 : 3) : (MODE == 
 			}
 		}
 		__syncthreads();
-		if (MODE == 2 && tid == 0) { __threadfence(); *(volatile unsigned char*)(d.coarseDone + d.coarseBase[level] + coordId) = 1; }
 		if (NBUF == 1 && MODE != 2 && !nextIssued && nextItem < workCount) { int l2, x2, y2, z2; decode(nextItem, l2, x2, y2, z2); issue(0, l2, x2, y2, z2); }
 		item = nextItem;
 		if (NBUF == 2) buf ^= 1;

@@ -177,6 +177,18 @@ __device__ __forceinline__ unsigned vxb_rle_channel(const unsigned char* __restr
 	*reinterpret_cast<uint4*>(rowBytes) = row;
 	sPrev[t] = rowBytes[15];
 	__syncthreads();
+	{
+		// most channels of most blocks hold one value: 4096 = 16 runs of 255 + one of 16, no scans needed
+		const unsigned splat = (unsigned)sPrev[0] * 0x01010101u;
+		const int uniform = __syncthreads_and(row.x == splat && row.y == splat && row.z == splat && row.w == splat);
+		if (uniform)
+		{
+			if (t <= 17) starts[t] = (unsigned short)(t < 17 ? t * 255 : 4096);
+			raw = false;
+			__syncthreads();
+			return 34u;
+		}
+	}
 	const int prev = t ? sPrev[t - 1] : -1;
 	// last value change at or before each of my bytes: first within the row, then the incoming one from earlier rows
 	unsigned changeMask = 0;

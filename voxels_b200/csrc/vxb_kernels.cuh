@@ -110,9 +110,10 @@ struct VxbDev
 	int coarseLo;
 	// their sample lattices: level l holds the samples at multiples of 2^l plus, per axis, one extra entry for the clamped
 	// far-edge coordinate n (= the sample at n - 1, :1037-1047): (h + 1)^3 entries, h = n >> l, rows of h + 16 bytes.  Written by
-	// vxb_scan_kernel on its way through the volume; a 17^3 tile of any coarse block is ONE TMA box of its level's map.
+	// vxb_coarse_lattice_kernel; a 17^3 tile of any coarse block is ONE TMA box of its level's map.
 	unsigned char* coarseLattice[VXB_MAX_LEVELS];
 	const CUtensorMap* coarseMaps;             // [VXB_MAX_LEVELS], device memory
+	int latticeLo;                             // levels >= latticeLo have such a lattice (2; levels <= 1 read the volume / the even lattice)
 	unsigned char* coarseDone;                 // [coarseBase[l] + coordId], zeroed per run
 	unsigned int coarseBase[VXB_MAX_LEVELS];
 	// sharded runs (vxb_shard_*): the z-axis is cut into groups of shardLayers level-0 block layers, dealt cyclically to
@@ -243,35 +244,36 @@ struct VxbCoarseLattices
 	int lo, levels; // levels [lo, levels) have a lattice (lo >= 2)
 };
 
-// One 16-byte row (global y, z; samples x = bx * 16 .. + 15) -> its entries of the coarse lattices.  Rare: only rows whose y
-// and z are multiples of 2^lo or the last coordinate of the grid get here.
-__device__ __noinline__ void vxb_scan_coarse_row(const VxbCoarseLattices* __restrict__ latp, int n, int bx, int y, int z, unsigned w0, unsigned w1, unsigned w2, unsigned w3)
+// The coarse levels' lattices from the distance volume: one warp per lattice row (level, lz, ly) reads the source row
+// (y = min(ly 2^l, n-1), z likewise) once, coalesced, and keeps every 2^l-th sample plus the clamped far-edge entry.
+// Off the critical path of a single-GPU run (second stream, needed only by vxb_block_kernel<2>); sharded runs: every rank
+// does the rows of its own planes (zOwnerWorld > 0) before publishing them.
+__global__ void __launch_bounds__(256) vxb_coarse_lattice_kernel(const signed char* __restrict__ dist, int n, const __grid_constant__ VxbCoarseLattices lat,
+	int planesPerPiece, int zOwnerWorld, int zOwnerRank)
 {
-	const VxbCoarseLattices& lat = *latp;
-	const unsigned w[4] = { w0, w1, w2, w3 };
+	const int lane = threadIdx.x & 31;
+	const unsigned warpsPerGrid = gridDim.x * (blockDim.x >> 5);
+	unsigned w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
 	for (int l = lat.lo; l < lat.levels; ++l)
 	{
-		const int m = 1 << l, h = n >> l, pitch = h + 16;
-		const int ly[2] = { (y & (m - 1)) == 0 ? (y >> l) : -1, y == n - 1 ? h : -1 };
-		const int lz[2] = { (z & (m - 1)) == 0 ? (z >> l) : -1, z == n - 1 ? h : -1 };
-		for (int a = 0; a < 2; ++a) for (int b = 0; b < 2; ++b)
+		const int h = n >> l, pitch = h + 16, m = 1 << l;
+		const unsigned rows = (unsigned)(h + 1) * (h + 1);
+		for (; w < rows; w += warpsPerGrid)
 		{
-			if (ly[a] < 0 || lz[b] < 0) continue;
-			unsigned char* out = lat.p[l] + ((size_t)lz[b] * (h + 1) + ly[a]) * pitch;
-			for (int k = 0; k < 16; k += (m < 16 ? m : 16))
-			{
-				const int x = bx * 16 + k;
-				if ((x & (m - 1)) == 0) out[x >> l] = (unsigned char)(w[k >> 2] >> ((k & 3) * 8));
-			}
-			if (bx * 16 + 15 == n - 1) out[h] = (unsigned char)(w[3] >> 24);
+			const int lz = (int)(w / (h + 1)), ly = (int)(w % (h + 1));
+			const int z = min(lz << l, n - 1), y = min(ly << l, n - 1);
+			if (zOwnerWorld && (z / planesPerPiece) % zOwnerWorld != zOwnerRank) continue;
+			const signed char* src = dist + ((size_t)z * n + y) * n;
+			unsigned char* out = lat.p[l] + ((size_t)lz * (h + 1) + ly) * pitch;
+			for (int lx = lane; lx <= h; lx += 32) out[lx] = (unsigned char)src[min(lx * m, n - 1)];
 		}
+		w -= rows; // continue with the next level's rows
 	}
 }
 
 template <int J>
 __global__ void __launch_bounds__(VXB_THREADS, (J == 32 ? 3 : 4)) vxb_scan_kernel(const signed char* __restrict__ dist, int n, unsigned int* __restrict__ scanFlags,
 	unsigned char* __restrict__ lattice1 /* (n/2)^3: the samples at even coordinates = the level-1 lattice, or null */,
-	const __grid_constant__ VxbCoarseLattices coarse,
 	int groupLayers, int world, int rank /* sharded runs: blockIdx.z counts this rank's layers (groups of groupLayers block layers,
 	                                        dealt cyclically to the ranks); unsharded: world = 1 */,
 	int zBase /* first block layer (incremental runs rescan only the layers of the level-0 dirty box) */)
@@ -308,11 +310,6 @@ __global__ void __launch_bounds__(VXB_THREADS, (J == 32 ? 3 : 4)) vxb_scan_kerne
 				const int y = (RG == 32) ? y0 : ((i & 1) * 8 + y0), z = (RG == 32) ? (z0 + 2 * i + batch * 16) : ((i >> 1) + batch * 4);
 				const unsigned w[4] = { rows[i].x, rows[i].y, rows[i].z, rows[i].w };
 				const bool even = !((y | z) & 1);
-				if (coarse.lo < coarse.levels)
-				{
-					const int gy = by * 16 + y, gz = bz * 16 + z, mm = (1 << coarse.lo) - 1;
-					if (((gy & mm) == 0 || gy == n - 1) && ((gz & mm) == 0 || gz == n - 1)) vxb_scan_coarse_row(&coarse, n, bx0 + j, gy, gz, rows[i].x, rows[i].y, rows[i].z, rows[i].w);
-				}
 				// a row of 16 equal bytes (the common case away from the surface) has no value change inside it
 				const unsigned splat = (w[0] & 0xFFu) * 0x01010101u;
 				const bool flat = (w[0] == splat) & (w[1] == splat) & (w[2] == splat) & (w[3] == splat);
@@ -696,11 +693,24 @@ __global__ void __launch_bounds__(1024) vxb_plan_kernel(const VxbDev d)
 	__shared__ unsigned long long sums[32];
 	__shared__ unsigned long long sTotal;
 	const int nbs = (d.n >> 4) >> d.sbLevel;
-	const unsigned count = (unsigned)nbs * nbs * nbs;
-	const unsigned per = (count + 1023u) / 1024u;
+	const unsigned count = (unsigned)nbs * nbs * nbs;   // a power of 8: a multiple of 4
+	const unsigned per = ((count + 1023u) / 1024u + 3u) & ~3u;
 	const unsigned i0 = min(threadIdx.x * per, count), i1 = min(i0 + per, count);
+	// the chunk's weights in registers (independent 16-byte loads), used twice
+	uint4 w[8];
 	unsigned long long mine = 0;
-	for (unsigned i = i0; i < i1; ++i) mine += (unsigned long long)d.sbWeight[i] * 1024ull + 1ull; // + 1: a super-block without a mixed block still costs a look (about 1/1000 of a block)
+#pragma unroll
+	for (int q = 0; q < 8; ++q)
+	{
+		const unsigned i = i0 + 4u * q;
+		w[q] = (i < i1 && (unsigned)q * 4u < per) ? *reinterpret_cast<const uint4*>(d.sbWeight + i) : make_uint4(0, 0, 0, 0);
+	}
+#pragma unroll
+	for (int q = 0; q < 8; ++q)
+	{
+		const unsigned i = i0 + 4u * q;
+		if (i < i1) mine += ((unsigned long long)w[q].x + w[q].y + w[q].z + w[q].w) * 1024ull + 4ull; // + 1 each: a super-block without a mixed block still costs a look
+	}
 	unsigned long long inc = mine;
 	const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	for (int o = 1; o < 32; o <<= 1) { const unsigned long long t = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= (unsigned)o) inc += t; }
@@ -709,17 +719,30 @@ __global__ void __launch_bounds__(1024) vxb_plan_kernel(const VxbDev d)
 	if (threadIdx.x == 0)
 	{
 		unsigned long long acc = 0;
-		for (int w = 0; w < 32; ++w) { const unsigned long long v = sums[w]; sums[w] = acc; acc += v; }
+		for (int k = 0; k < 32; ++k) { const unsigned long long v = sums[k]; sums[k] = acc; acc += v; }
 		sTotal = acc;
 	}
 	__syncthreads();
 	unsigned long long run = sums[warp] + inc - mine; // exclusive prefix of this thread's chunk
 	const unsigned long long total = sTotal;
-	for (unsigned i = i0; i < i1; ++i)
+	// owner = floor(run * world / total) = the number of r in [1, world) with run >= ceil(r * total / world): my range is
+	// [lo, hi) without a division per super-block
+	const unsigned long long W = (unsigned long long)d.shardWorld, r = (unsigned long long)d.shardRank;
+	const unsigned long long lo = (r * total + W - 1) / W, hi = (r + 1 == W) ? ~0ull : ((r + 1) * total + W - 1) / W;
+#pragma unroll
+	for (int q = 0; q < 8; ++q)
 	{
-		const unsigned owner = (unsigned)min((unsigned long long)(d.shardWorld - 1), run * (unsigned long long)d.shardWorld / total);
-		d.sbMine[i] = owner == (unsigned)d.shardRank;
-		run += (unsigned long long)d.sbWeight[i] * 1024ull + 1ull;
+		const unsigned i = i0 + 4u * q;
+		if (i >= i1) continue;
+		const unsigned ws[4] = { w[q].x, w[q].y, w[q].z, w[q].w };
+		unsigned packed = 0;
+#pragma unroll
+		for (int k = 0; k < 4; ++k)
+		{
+			if (run >= lo && run < hi) packed |= 1u << (8 * k);
+			run += (unsigned long long)ws[k] * 1024ull + 1ull;
+		}
+		*reinterpret_cast<unsigned*>(d.sbMine + i) = packed;
 	}
 }
 
@@ -790,6 +813,7 @@ __global__ void __launch_bounds__(VXB_THREADS) vxb_publish_kernel(const VxbDev d
 __device__ __forceinline__ bool vxb_tile_uses_tma(const VxbDev& d, int level, int bx, int by, int bz)
 {
 	if (level == 0) return true;
+	if (level >= d.latticeLo) return true; // the level's own lattice (far-edge entries included)
 	if (level != 1 || !d.lattice1) return false;
 	const int nb = d.n / 32;
 	return bx != nb - 1 && by != nb - 1 && bz != nb - 1;
@@ -802,7 +826,7 @@ __device__ __forceinline__ void vxb_tile_issue(signed char* tile, unsigned long 
 	{
 		vxb_fence_proxy_async();
 		vxb_mbar_expect_tx(mbar, VXB_TILE_BYTES);
-		vxb_tma_load_3d(tile, level == 0 ? tmap0 : tmap1, bx * 16, by * 16, bz * 16, mbar);
+		vxb_tma_load_3d(tile, level == 0 ? tmap0 : (level >= d.latticeLo ? d.coarseMaps + level : tmap1), bx * 16, by * 16, bz * 16, mbar);
 	}
 }
 
@@ -815,6 +839,7 @@ __device__ __forceinline__ void vxb_tile_complete(signed char* tile, unsigned lo
 	{
 		vxb_mbar_wait(mbar, phase);
 		phase ^= 1;
+		if (level >= d.latticeLo) return; // lattice tiles need no fix-up
 		// level 0, far grid edge: the +1 plane is outside the volume (TMA zero-fills); the reference clamps (:1037-1047)
 		if (bx == nb - 1) { __syncthreads(); for (int i = tid; i < 17 * 17; i += (int)blockDim.x) tile[i * VXB_TILE_PITCH + 16] = tile[i * VXB_TILE_PITCH + 15]; }
 		if (by == nb - 1) { __syncthreads(); for (int i = tid; i < 17 * 17; i += (int)blockDim.x) { const int z = i / 17, x = i % 17; tile[(z * 17 + 16) * VXB_TILE_PITCH + x] = tile[(z * 17 + 15) * VXB_TILE_PITCH + x]; } }

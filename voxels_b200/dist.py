@@ -1,8 +1,8 @@
 """torch.distributed plumbing for the multi-GPU runs (one process per GPU; NCCL on the B200 box, gloo in the CPU tests).
 
 ONE grid polygonized by all ranks (`ShardedGrid`, SURVEY.md section 8e / BASELINE configs[3], include/vxb200.h "Sharded
-runs"): the cube lives in one virtual address range per rank whose z-pieces are the ranks' HBM (dealt cyclically), mapped
-into every peer over NVLink (file descriptors travel over Unix sockets, `exchange_fds`); work is dealt by blocks; the
+runs"): work is dealt by blocks; the read-only volumes are replicated in every rank's HBM (default) or sharded as a cube
+whose z-pieces are mapped into every peer over NVLink (file descriptors travel over Unix sockets, `exchange_fds`); the
 data path has two exchanges (an ncclAllGather of the per-block info, peer stores of the material pages ordered by a
 second tiny all-gather), both issued by libvxb200.so itself on the context's stream, so a step is one CUDA graph.
 torch.distributed carries the rendezvous: the NCCL id broadcast, barriers, the max-reduction of device times and the
@@ -198,51 +198,76 @@ def gather_directories(ranks, records):
 
 class ShardedGrid:
     """One n^3 grid polygonized by all ranks (one GPU each).  Usage:
-        sg = ShardedGrid(ranks, n)            # cube: local pieces + peers' pieces mapped over NVLink, page buffers, NCCL
-        for z0, z1, (d, m, b) in sg.piece_tensors():   # torch views [z1-z0, n, n] of the LOCAL pieces: fill them
-            ...
-        sg.ready()                            # barrier: every piece is filled
+        sg = ShardedGrid(ranks, n)            # mode "replicated" (default) or "cube"
+        sg.fill(surface)  |  sg.upload_packed(blob_ptr, nbytes)     # every rank: the whole grid (replicated) / its pieces (cube)
+        sg.ready()                            # page buffers exchanged, NCCL communicator, barrier: every rank's data is in place
         info = sg.polygonize()                # one stream-ordered step (two exchanges inside); this rank's blocks
         directory, owner = sg.directory()     # every rank's blocks (all-gather), reference order
+
+    replicated: every rank holds the three read-only volumes in its own HBM (24 GB at 2048^3) and the WORK is sharded - every
+                load of a kernel is local.  Default, because peer loads bypass the local L2 and cost ~2000 cycles
+                (B300_MICROARCH.md, NVLink): the sparse 1-byte taps of the vertex / vote / transition code run 2-3x slower
+                on remote data (measured: profiles/r02_sharded_*).
+    cube:       the volumes themselves are sharded: z-pieces of group_planes planes live in the ranks' HBM (cyclic deal) and
+                are mapped into every peer over NVLink.  For grids that do not fit one GPU.
     """
 
-    def __init__(self, ranks, n, device_index=None, key=None, group_planes=None):
+    def __init__(self, ranks, n, device_index=None, key=None, group_planes=None, mode="replicated"):
         import torch
         from . import capi
-        self.ranks, self.n = ranks, n
+        assert mode in ("replicated", "cube")
+        self.ranks, self.n, self.mode = ranks, n, mode
         self.rank, self.world = ranks.rank, ranks.world
-        self.group_planes = default_group_planes(n, self.world) if group_planes is None else int(group_planes)
+        self.group_planes = (default_group_planes(n, self.world) if mode == "cube" else min(32, n // self.world)) if group_planes is None else int(group_planes)
         self.device_index = ranks.local_rank if device_index is None else device_index
         self.device = torch.device("cuda", self.device_index)
+        self.key = "%s-%d-%s" % (key or os.environ.get("MASTER_PORT", "0"), n, mode)
         self.ctx = capi.Context(self.device_index)
-        self.ctx.cube_create(n, self.rank, self.world, self.group_planes)
-        self.pieces, self.channels, _ = self.ctx.cube_info()
+        self._configured = False
+        self.last_attempts = 0
+        if mode == "cube":
+            self.ctx.cube_create(n, self.rank, self.world, self.group_planes)
+            self.pieces, self.channels, _ = self.ctx.cube_info()
+            if self.world > 1:
+                mine = [p for p, _, _ in owned_pieces(n, self.rank, self.world, self.group_planes)]
+                fds = [self.ctx.cube_export(c, p) for p in mine for c in range(self.channels)]
+                got = exchange_fds(self.rank, self.world, fds, self.key + "-cube")
+                for peer, theirs in got.items():
+                    it = iter(theirs)
+                    for p, _, _ in owned_pieces(n, peer, self.world, self.group_planes):
+                        for c in range(self.channels):
+                            fd = next(it)
+                            self.ctx.cube_import(c, p, fd)
+                            os.close(fd)
+                for fd in fds:
+                    os.close(fd)
+
+    def fill(self, surface, start=(0.0, 0.0, 0.0), step=1.0):
+        """Grid::Create(..., &surface) on the device: the whole grid (replicated) or this rank's pieces (cube)."""
+        self.ctx.fill(self.n, surface, start, step)
+
+    def upload_packed(self, blob_ptr, nbytes):
+        """The grid's PackForSave bytes from (pinned) host memory: decoded on the GPU, whole (replicated) or this rank's pieces."""
+        self.ctx.upload_packed(blob_ptr, nbytes)
+
+    def _configure(self):
+        from . import capi
         self.ctx.shard_configure(self.rank, self.world, self.group_planes)
         if self.world > 1:
-            mine = [p for p, _, _ in owned_pieces(n, self.rank, self.world, self.group_planes)]
-            fds = [self.ctx.cube_export(c, p) for p in mine for c in range(self.channels)] + [self.ctx.shard_export()]
-            key = key or os.environ.get("MASTER_PORT", "0")
-            got = exchange_fds(self.rank, self.world, fds, "%s-%d" % (key, n))
+            fd = self.ctx.shard_export()
+            got = exchange_fds(self.rank, self.world, [fd], self.key + "-pages")
             for peer, theirs in got.items():
-                it = iter(theirs)
-                for p, _, _ in owned_pieces(n, peer, self.world, self.group_planes):
-                    for c in range(self.channels):
-                        fd = next(it)
-                        self.ctx.cube_import(c, p, fd)
-                        os.close(fd)
-                fd = next(it)
-                self.ctx.shard_import(peer, fd)
-                os.close(fd)
-            for fd in fds:
-                os.close(fd)
+                self.ctx.shard_import(peer, theirs[0])
+                os.close(theirs[0])
+            os.close(fd)
             # the communicator of the two in-step all-gathers: id from rank 0, carried by torch.distributed
             ids = [capi.nccl_unique_id() if self.rank == 0 else None]
-            ranks.td.broadcast_object_list(ids, src=0)
+            self.ranks.td.broadcast_object_list(ids, src=0)
             self.ctx.shard_nccl_init(ids[0], self.rank, self.world)
-        self.last_attempts = 0
+        self._configured = True
 
     def piece_tensors(self):
-        """[(z0, z1, (dist, mat, blend))]: torch views of this rank's pieces."""
+        """cube mode: [(z0, z1, (dist, mat, blend))] torch views of this rank's pieces."""
         import torch
         from . import capi
         out = []
@@ -255,24 +280,20 @@ class ShardedGrid:
 
     def ready(self):
         import torch
+        if not self._configured:
+            self._configure()
         torch.cuda.synchronize(self.device)
         self.ranks.barrier()
 
     def polygonize(self, flags=0, max_attempts=4):
         from . import capi
         for attempt in range(max_attempts):
-            rc = self.ctx.polygonize_sharded(3, flags) if self.world > 1 else self._single(flags)
+            rc = self.ctx.polygonize_sharded(3, flags)
             # an overflow on any rank repeats the run on every rank (the exchanges are collective)
             if self.ranks.max_over_ranks(1.0 if rc != 0 else 0.0) == 0.0:
                 self.last_attempts = attempt + 1
                 return self.ctx.info()
         raise capi.VxbError("sharded run: output arenas kept overflowing")
-
-    def _single(self, flags):
-        # world == 1: no peers, no communicator - the three pieces back to back
-        self.ctx.polygonize_sharded(0, flags)
-        self.ctx.polygonize_sharded(1, flags)
-        return self.ctx.polygonize_sharded(2, flags)
 
     def directory(self):
         import numpy as np
