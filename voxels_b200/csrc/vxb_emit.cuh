@@ -133,7 +133,7 @@ __device__ __forceinline__ bool vxb_overflowed(const VxbDev& d)
 }
 
 template <int MODE, int T>
-__global__ void __launch_bounds__(T, (MODE == 0 ? (T == 128 ? 5 : 3) : (MODE == 2 ? 3 : VXB_OCC))) vxb_block_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB, const VxbDev d, const int levelArg)
+__global__ void __launch_bounds__(T, (MODE == 0 ? (T == 128 ? 5 : 3) : (MODE == 2 ? 4 : VXB_OCC))) vxb_block_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB, const VxbDev d, const int levelArg)
 {
 	constexpr int PITCH = (MODE == 0) ? VXB_DTILE_PITCH : VXB_TILE_PITCH;
 	constexpr int ROWS = (MODE == 0) ? 19 : 17;
@@ -356,7 +356,10 @@ __global__ void __launch_bounds__(T, (MODE == 0 ? (T == 128 ? 5 : 3) : (MODE == 
 			if (tid < 128) s.wpre[tid] = ex;
 		}
 		__syncthreads();
-		const bool inCap = ntc <= (unsigned)CAP_C;
+		// MODE 2: the coarse blocks form a dependency chain, so an item only classifies and votes (short); the emission work
+		// of its blocks is left to vxb_decide_kernel<4096, 1> (the path of oversized blocks), off the chain
+		// (sharded runs only: there every rank walks the whole chain but emits 1/world of its blocks; on one GPU the in-item path is shorter overall)
+		const bool inCap = !(MODE == 2 && d.shardWorld > 1) && ntc <= (unsigned)CAP_C;
 		// sharded runs: every rank classifies the coarse levels (the votes feed the next level), one of them emits the block
 		const bool emitMine = MODE != 2 || vxb_coarse_emit_is_mine(d, level, coordId);
 
