@@ -656,7 +656,7 @@ int vxb_create(int device, vxb_context** out)
 		{ (const void*)vxb_block_kernel<1, 256>, sizeof(VxbBlockSmem<1, 256>), &ctx->gridBlock[1], "vxb_block_kernel<1>", VXB_THREADS },
 		{ (const void*)vxb_block_kernel<2, 256>, sizeof(VxbBlockSmem<2, 256>), &ctx->gridBlock[2], "vxb_block_kernel<2>", VXB_THREADS },
 		{ (const void*)vxb_decide_kernel<4096, 1>, sizeof(VxbDecideSmemBig), &ctx->gridDecideBig, "vxb_decide_kernel<4096>", VXB_THREADS },
-		{ (const void*)vxb_transition_kernel, sizeof(VxbTransSmem), &ctx->gridTransition, "vxb_transition_kernel", VXB_THREADS },
+		{ (const void*)vxb_transition_kernel, 0, &ctx->gridTransition, "vxb_transition_kernel", VXB_TR_THREADS },
 	};
 	for (const KernelSetup& k : setups)
 	{
@@ -1447,7 +1447,7 @@ static int runPolygonize(vxb_context* ctx, uint32_t maxLevels, uint32_t flags, c
 			{
 				cudaStream_t ts = fork ? ctx->stream2 : st;
 				timer.begin(6);
-				vxb_transition_kernel<<<ctx->gridTransition, VXB_THREADS, sizeof(VxbTransSmem), ts>>>(dev);
+				vxb_transition_kernel<<<ctx->gridTransition, VXB_TR_THREADS, 0, ts>>>(dev);
 				vxb_transition_vertex_kernel<<<flatGrid, VXB_THREADS, 0, ts>>>(dev);
 				timer.end(); launches += 2; ctx->kindLaunches[6] += 2;
 				if (fork)

@@ -1276,24 +1276,27 @@ __global__ void __launch_bounds__(VXB_THREADS) vxb_finish_kernel(const VxbDev d)
 }
 
 // ------------------------------------------------------------------------------------------------
-// transition cells (:1754-2131), one emitted mid-level block per CTA iteration, cell = face*256 + row*16 + col
+// transition cells (:1754-2131).  Work item = ONE FACE of one emitted mid-level block (the reference numbers the vertices
+// of every face from zero - TransitionVertices[face], :1293 - so the six faces of a block are independent): a 64-thread
+// CTA stages the face's 33 x 33 half-stride lattice, takes the 256 case codes, compacts the non-trivial cells and runs
+// the slot / reuse / scan / emit passes over them.  cell = row * 16 + col.
 // ------------------------------------------------------------------------------------------------
+#define VXB_TR_THREADS 64
 struct __align__(16) VxbTransSmem
 {
-	// per NON-TRIVIAL transition cell, in the reference's serial order (face, row, col) = compact index
-	unsigned long long slots[1536]; // 10 owned-slot nibbles
-	unsigned short cell[1536];      // face * 256 + row * 16 + col
-	unsigned short newMask[1536];
-	unsigned short vbase[1536];     // new-vertex count, then its exclusive scan (running over all faces)
-	unsigned short tbase[1536];     // triangle count, then its exclusive scan
-	unsigned char mat[1536];
-	unsigned short code[1536];      // per CELL (not compact): 9-bit transition case code, 0 = trivial / face without neighbour
-	signed char face[6][1092];      // the 33 x 33 half-stride sample lattice of each face plane (clamped reads)
-	unsigned int nt[48];            // non-trivial bits, cell order
-	unsigned int pre[49];           // exclusive prefix of popc(nt): compact index base of each word
+	// per NON-TRIVIAL transition cell of the face, in the reference's serial order (row, col) = compact index
+	unsigned long long slots[256]; // 10 owned-slot nibbles
+	unsigned short cell[256];      // row * 16 + col
+	unsigned short newMask[256];
+	unsigned short vbase[256];     // new-vertex count, then its exclusive scan
+	unsigned short tbase[256];     // triangle count, then its exclusive scan
+	unsigned char mat[256];
+	unsigned short code[256];      // per CELL (not compact): 9-bit transition case code, 0 = trivial
+	signed char face[1092];        // the 33 x 33 half-stride sample lattice of the face plane (clamped reads)
+	unsigned int nt[8];            // non-trivial bits, cell order
+	unsigned int pre[9];           // exclusive prefix of popc(nt): compact index base of each word
 	unsigned int warpSums[8];
-	unsigned int faceV[7], faceT[7]; // scan value at the first compact entry of each face (+ grand total)
-	unsigned int tvoff[6], tioff[6], tvcount[6], ticount[6];
+	unsigned int tvoff, tioff, tvcount, ticount;
 	unsigned int item;
 };
 
@@ -1320,43 +1323,51 @@ __device__ __forceinline__ VxbTransVertexDesc vxb_lattice_vertex_desc(unsigned v
 	return vxb_transition_vertex_desc_ab(vd, vxb_lattice_sample(p, (vd >> 4) & 0xF), vxb_lattice_sample(p, vd & 0xF), vxbGTransitionCornerData);
 }
 
-__global__ void __launch_bounds__(VXB_THREADS, VXB_OCC) vxb_transition_kernel(const VxbDev d)
+__global__ void __launch_bounds__(VXB_TR_THREADS, 16) vxb_transition_kernel(const VxbDev d)
 {
-	extern __shared__ __align__(128) unsigned char smemRaw[];
-	VxbTransSmem& s = *reinterpret_cast<VxbTransSmem*>(smemRaw);
+	__shared__ VxbTransSmem s;
 	if (vxb_overflowed(d)) return;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const VxbGrid g = d.grid;
-	const unsigned workCount = d.counters->transBlocks;
+	const unsigned workCount = d.counters->transBlocks * 6u;
 	for (;;)
 	{
 		if (tid == 0) s.item = atomicAdd(&d.counters->transCursor, 1u);
 		__syncthreads();
-		if (s.item >= workCount) break;
-		const unsigned slot = d.transList[s.item];
+		const unsigned item = s.item;
+		if (item >= workCount) break;
+		const unsigned slot = d.transList[item / 6u];
+		const int face = (int)(item % 6u);
 		const unsigned packed = d.blockRecs[slot].packed;
 		const int level = (int)(packed >> 28);
 		const unsigned coordId = packed & 0x0FFFFFFFu;
 		const int m = 1 << level, nb = d.n / 16 / m;
 		const int bx = coordId % nb, by = (coordId / nb) % nb, bz = coordId / (nb * nb);
+		int axis, ua, va;
+		vxb_face_axes(face, axis, ua, va);
+		const int bc = (axis == 0) ? bx : (axis == 1 ? by : bz);
+		if (face < 3 ? (bc == 0) : (bc == nb - 1)) // no neighbour block inside the grid (:1829-1835): the face stays empty (the record was zeroed by vxb_block_kernel)
+		{
+			__syncthreads();
+			continue;
+		}
 
-		// T0: stage the half-stride lattices of the six face planes (clamped reads; faces without a neighbour block are staged
-		// too and never used: T1 skips them)
+		// T0: stage the half-stride lattice of the face plane (clamped reads)
 		{
 			const int h = m >> 1, lim = d.n - 1;
 			const int origin[3] = { bx * 16 * m, by * 16 * m, bz * 16 * m };
-			if (level == 1)
+			const int f3 = face >= 3 ? face - 3 : face;
+			const int off = (face >= 3) ? 16 * m : 0;
+			if (level == 1 && f3 != 2)
 			{
-				// level 1: the lattice is the level-0 volume itself, so a row of the four faces normal to z or y is 33 CONTIGUOUS
-				// bytes starting on a 32-byte boundary: two 16-byte loads + one byte instead of 33 sector-sized byte loads
-				for (int q = tid; q < 4 * 33 * 3; q += VXB_THREADS)
+				// level 1: the lattice is the level-0 volume itself, so a row of a face normal to z or y is 33 CONTIGUOUS bytes
+				// starting on a 32-byte boundary: two 16-byte loads + one byte instead of 33 sector-sized byte loads
+				for (int q = tid; q < 33 * 3; q += VXB_TR_THREADS)
 				{
-					const int fi = q / 99, r = q - fi * 99, j = r / 3, part = r - j * 3; // fi: 0 = z-, 1 = y-, 2 = z+, 3 = y+
-					const int face = (fi & 1) + (fi >> 1) * 3;                               // internal face ids 0 (z-), 1 (y-), 3 (z+), 4 (y+)
-					const int off = (face >= 3) ? 32 : 0;
-					const int py = origin[1] + ((face % 3) == 1 ? off : j), pz = origin[2] + ((face % 3) == 0 ? off : j);
+					const int j = q / 3, part = q - j * 3;
+					const int py = origin[1] + (f3 == 1 ? off : j), pz = origin[2] + (f3 == 0 ? off : j);
 					const signed char* row = g.dist + ((size_t)min(pz, lim) * d.n + min(py, lim)) * d.n + origin[0];
-					signed char* dst = &s.face[face][j * 33];
+					signed char* dst = &s.face[j * 33];
 					if (part < 2)
 					{
 						const uint4 v = *reinterpret_cast<const uint4*>(row + part * 16);
@@ -1366,105 +1377,69 @@ __global__ void __launch_bounds__(VXB_THREADS, VXB_OCC) vxb_transition_kernel(co
 					}
 					else dst[32] = row[min(32, lim - origin[0])];
 				}
-				// the two faces normal to x: one sample per row of the volume
-				for (int idx0 = tid; idx0 < 2 * 1089; idx0 += 4 * VXB_THREADS)
-				{
-					signed char v[4];
-#pragma unroll
-					for (int u = 0; u < 4; ++u)
-					{
-						const int idx = min(idx0 + u * VXB_THREADS, 2 * 1089 - 1);
-						const int hi = idx / 1089, r = idx - hi * 1089, j = r / 33, i = r - j * 33;
-						const int px = origin[0] + (hi ? 32 : 0), py = origin[1] + i, pz = origin[2] + j;
-						v[u] = g.dist[((size_t)min(pz, lim) * d.n + min(py, lim)) * d.n + min(px, lim)];
-					}
-#pragma unroll
-					for (int u = 0; u < 4; ++u)
-					{
-						const int idx = idx0 + u * VXB_THREADS;
-						if (idx < 2 * 1089) s.face[idx < 1089 ? 2 : 5][idx % 1089] = v[u];
-					}
-				}
 			}
 			else
 			{
-				// four independent loads in flight per thread
-				for (int idx0 = tid; idx0 < 6 * 1089; idx0 += 4 * VXB_THREADS)
+				// vxb_face_axes: f3 = 0: axis z, (u, v) = (x, y); 1: axis y, (x, z); 2: axis x, (y, z); six independent loads in flight
+				for (int idx0 = tid; idx0 < 1089; idx0 += 6 * VXB_TR_THREADS)
 				{
-					signed char v[4];
+					signed char v[6];
 #pragma unroll
-					for (int u = 0; u < 4; ++u)
+					for (int u = 0; u < 6; ++u)
 					{
-						const int idx = min(idx0 + u * VXB_THREADS, 6 * 1089 - 1);
-						const int face = idx / 1089, r = idx - face * 1089;
-						const int f3 = face >= 3 ? face - 3 : face;
+						const int r = min(idx0 + u * VXB_TR_THREADS, 1088);
 						const int j = r / 33, i = r - j * 33;
-						const int off = (face >= 3) ? 16 * m : 0, cu = i * h, cv = j * h;
-						// vxb_face_axes: f3 = 0: axis z, (u, v) = (x, y); 1: axis y, (x, z); 2: axis x, (y, z)
+						const int cu = i * h, cv = j * h;
 						const int px = origin[0] + (f3 == 2 ? off : cu);
 						const int py = origin[1] + (f3 == 1 ? off : (f3 == 0 ? cv : cu));
 						const int pz = origin[2] + (f3 == 0 ? off : cv);
 						v[u] = g.dist[((size_t)min(pz, lim) * d.n + min(py, lim)) * d.n + min(px, lim)];
 					}
 #pragma unroll
-					for (int u = 0; u < 4; ++u)
+					for (int u = 0; u < 6; ++u)
 					{
-						const int idx = idx0 + u * VXB_THREADS;
-						if (idx < 6 * 1089) (&s.face[0][0])[(idx / 1089) * 1092 + (idx % 1089)] = v[u];
+						const int r = idx0 + u * VXB_TR_THREADS;
+						if (r < 1089) s.face[r] = v[u];
 					}
 				}
 			}
 		}
 		__syncthreads();
-		// T1: case code of every cell (cell = face * 256 + thread: thread order = the reference's row-major order)
-#pragma unroll 1
-		for (int face = 0; face < 6; ++face)
+		// T1: case code of every cell (cell order = the reference's row-major order)
+		for (int c0 = tid; c0 < 256; c0 += VXB_TR_THREADS)
 		{
-			int axis, ua, va;
-			vxb_face_axes(face, axis, ua, va);
-			const int bc = (axis == 0) ? bx : (axis == 1 ? by : bz);
-			unsigned code = 0;
-			if (!(face < 3 ? (bc == 0) : (bc == nb - 1))) // neighbour block inside the grid (:1829-1835)
-			{
-				signed char v[13];
-				vxb_face_cell_samples(s.face[face], tid >> 4, tid & 15, v);
-				code = vxb_transition_case_code(v);
-				if (code == 511u) code = 0;
-			}
+			signed char v[13];
+			vxb_face_cell_samples(s.face, c0 >> 4, c0 & 15, v);
+			unsigned code = vxb_transition_case_code(v);
+			if (code == 511u) code = 0;
 			const unsigned bal = __ballot_sync(0xFFFFFFFFu, code != 0u);
-			if (lane == 0) s.nt[face * 8 + warp] = bal;
-			s.code[face * 256 + tid] = (unsigned short)code;
+			if (lane == 0) s.nt[c0 >> 5] = bal;
+			s.code[c0] = (unsigned short)code;
 		}
 		__syncthreads();
 		unsigned ntc;
 		{
-			const unsigned cnt = (tid < 48) ? __popc(s.nt[tid]) : 0u;
+			const unsigned cnt = (tid < 8) ? __popc(s.nt[tid]) : 0u;
 			const unsigned ex = vxb_block_scan(cnt, s.warpSums, ntc);
-			if (tid < 48) s.pre[tid] = ex;
-			if (tid == 0) s.pre[48] = ntc;
+			if (tid < 8) s.pre[tid] = ex;
+			if (tid == 0) s.pre[8] = ntc;
 		}
 		__syncthreads();
-		if (tid < 6) { s.tvcount[tid] = 0; s.ticount[tid] = 0; s.tvoff[tid] = 0; s.tioff[tid] = 0; }
+		if (tid == 0) { s.tvcount = 0; s.ticount = 0; s.tvoff = 0; s.tioff = 0; }
 		if (ntc > 0) // block-uniform
 		{
 			// ordered compact list of the non-trivial cells
-#pragma unroll 1
-			for (int face = 0; face < 6; ++face)
-			{
-				const int ci = face * 256 + tid;
+			for (int ci = tid; ci < 256; ci += VXB_TR_THREADS)
 				if (s.code[ci]) s.cell[s.pre[ci >> 5] + __popc(s.nt[ci >> 5] & ((1u << (ci & 31)) - 1u))] = (unsigned short)ci;
-			}
 			__syncthreads();
 			// T2: owned slots + material, one thread per non-trivial cell
-			for (unsigned i = tid; i < ntc; i += VXB_THREADS)
+			for (unsigned i = tid; i < ntc; i += VXB_TR_THREADS)
 			{
-				const int ci = s.cell[i], face = ci >> 8, row = (ci >> 4) & 15, col = ci & 15;
+				const int ci = s.cell[i], row = ci >> 4, col = ci & 15;
 				const unsigned code = s.code[ci];
-				int axis, ua, va;
-				vxb_face_axes(face, axis, ua, va);
 				int local[3];
 				local[axis] = (face >= 3) ? 15 : 0; local[ua] = col; local[va] = row;
-				const signed char* lat = s.face[face] + (2 * row) * 33 + 2 * col;
+				const signed char* lat = s.face + (2 * row) * 33 + 2 * col;
 				unsigned long long slots = ~0ull;
 				const int nv = vxbGTransitionCellData[(vxbGTransitionCellClass[code] & 0x7F) * 40] >> 4;
 				for (int k = 0; k < nv; ++k)
@@ -1477,11 +1452,11 @@ __global__ void __launch_bounds__(VXB_THREADS, VXB_OCC) vxb_transition_kernel(co
 			}
 			__syncthreads();
 			// T3: new-vs-reuse decisions (owner = previous row / previous column of the same face, :1958-1978)
-			for (unsigned i = tid; i < ntc; i += VXB_THREADS)
+			for (unsigned i = tid; i < ntc; i += VXB_TR_THREADS)
 			{
-				const int ci = s.cell[i], face = ci >> 8, row = (ci >> 4) & 15, col = ci & 15;
+				const int ci = s.cell[i], row = ci >> 4, col = ci & 15;
 				const unsigned code = s.code[ci];
-				const signed char* lat = s.face[face] + (2 * row) * 33 + 2 * col;
+				const signed char* lat = s.face + (2 * row) * 33 + 2 * col;
 				const unsigned geo = vxbGTransitionCellData[(vxbGTransitionCellClass[code] & 0x7F) * 40];
 				const unsigned rowBits = (s.nt[ci >> 5] >> (ci & 16)) & 0xFFFFu;
 				const int mask = ((row > 0) ? 2 : 0) | ((rowBits & ((1u << col) - 1u)) ? 1 : 0);
@@ -1508,9 +1483,10 @@ __global__ void __launch_bounds__(VXB_THREADS, VXB_OCC) vxb_transition_kernel(co
 				s.tbase[i] = (unsigned short)(geo & 0xF);
 			}
 			__syncthreads();
-			// one exclusive scan over all non-trivial cells (serial order); per-face bases are differences to the face start
+			// exclusive scan over the face's non-trivial cells (serial order)
+			unsigned faceVerts, faceTris;
 			{
-				const unsigned per = (ntc + VXB_THREADS - 1) / VXB_THREADS;
+				const unsigned per = (ntc + VXB_TR_THREADS - 1) / VXB_TR_THREADS;
 				const unsigned i0 = min(tid * per, ntc), i1 = min(i0 + per, ntc);
 				unsigned sv = 0, st = 0;
 				for (unsigned i = i0; i < i1; ++i) { sv += s.vbase[i]; st += s.tbase[i]; }
@@ -1523,45 +1499,35 @@ __global__ void __launch_bounds__(VXB_THREADS, VXB_OCC) vxb_transition_kernel(co
 					s.vbase[i] = (unsigned short)bv; s.tbase[i] = (unsigned short)bt;
 					bv += cv; bt += ct;
 				}
-				if (tid == 0) { s.faceV[6] = total & 0xFFFF; s.faceT[6] = total >> 16; }
+				faceVerts = total & 0xFFFF; faceTris = total >> 16;
 			}
-			__syncthreads();
-			if (tid < 6)
+			if (tid == 0)
 			{
-				const unsigned first = s.pre[tid * 8]; // compact index of the face's first non-trivial cell
-				s.faceV[tid] = first < ntc ? s.vbase[first] : s.faceV[6];
-				s.faceT[tid] = first < ntc ? s.tbase[first] : s.faceT[6];
+				s.tvcount = faceVerts; s.ticount = faceTris * 3;
+				s.tvoff = faceVerts ? atomicAdd(&d.counters->transVertices, faceVerts) : 0u;
 			}
-			__syncthreads();
-			if (tid < 6)
-			{
-				const unsigned fv = s.faceV[tid + 1] - s.faceV[tid], fi = (s.faceT[tid + 1] - s.faceT[tid]) * 3;
-				s.tvcount[tid] = fv; s.ticount[tid] = fi;
-				s.tvoff[tid] = fv ? atomicAdd(&d.counters->transVertices, fv) : 0u;
-				s.tioff[tid] = fi ? atomicAdd(&d.counters->transIndices, fi) : 0u;
-			}
+			if (tid == 32) s.tioff = faceTris ? atomicAdd(&d.counters->transIndices, faceTris * 3) : 0u;
 			__syncthreads();
 			// T4: indices + the vertex work list
-			for (unsigned i = tid; i < ntc; i += VXB_THREADS)
+			const unsigned tvoff = s.tvoff, tioff = s.tioff;
+			const bool fits = (unsigned long long)tvoff + faceVerts <= d.tvcap && (unsigned long long)tioff + faceTris * 3ull <= d.ticap;
+			for (unsigned i = tid; fits && i < ntc; i += VXB_TR_THREADS)
 			{
-				const int ci = s.cell[i], face = ci >> 8, row = (ci >> 4) & 15, col = ci & 15;
-				const unsigned tvoff = s.tvoff[face], tioff = s.tioff[face];
-				if ((unsigned long long)tvoff + s.tvcount[face] > d.tvcap || (unsigned long long)tioff + s.ticount[face] > d.ticap) continue;
+				const int ci = s.cell[i], row = ci >> 4, col = ci & 15;
 				const unsigned code = s.code[ci];
-				const signed char* lat = s.face[face] + (2 * row) * 33 + 2 * col;
+				const signed char* lat = s.face + (2 * row) * 33 + 2 * col;
 				const unsigned cls = vxbGTransitionCellClass[code];
 				const unsigned char* cd = &vxbGTransitionCellData[(cls & 0x7F) * 40];
 				const int nv = cd[0] >> 4, ntri = cd[0] & 0xF;
 				const unsigned newMask = s.newMask[i];
-				const unsigned faceV = s.faceV[face];
 				unsigned vids[12];
-				unsigned nextNew = s.vbase[i] - faceV;
+				unsigned nextNew = s.vbase[i];
 				for (int k = 0; k < nv; ++k)
 				{
 					if ((newMask >> k) & 1u)
 					{
 						// the vertex itself is computed by vxb_transition_vertex_kernel, one thread per entry
-						d.tvlist[tvoff + nextNew] = make_uint2(slot, (code << 16) | ((unsigned)face << 12) | ((unsigned)(ci & 255) << 4) | (unsigned)k);
+						d.tvlist[tvoff + nextNew] = make_uint2(slot, (code << 16) | ((unsigned)face << 12) | ((unsigned)ci << 4) | (unsigned)k);
 						vids[k] = nextNew++;
 					}
 					else
@@ -1570,11 +1536,11 @@ __global__ void __launch_bounds__(VXB_THREADS, VXB_OCC) vxb_transition_kernel(co
 						const int oc = ci - ((td.dir >> 1) & 1) * 16 - (td.dir & 1);
 						const unsigned oi = s.pre[oc >> 5] + __popc(s.nt[oc >> 5] & ((1u << (oc & 31)) - 1u));
 						const unsigned ok = (unsigned)((s.slots[oi] >> (4 * td.slot)) & 0xF);
-						vids[k] = (s.vbase[oi] - faceV) + __popc((unsigned)s.newMask[oi] & ((1u << ok) - 1u));
+						vids[k] = (unsigned)s.vbase[oi] + __popc((unsigned)s.newMask[oi] & ((1u << ok) - 1u));
 					}
 				}
 				const bool flip = (((cls >> 7) & 1u) ^ (unsigned)(face & 1)) != 0;
-				unsigned* out = d.tidx + tioff + ((unsigned)s.tbase[i] - s.faceT[face]) * 3;
+				unsigned* out = d.tidx + tioff + (unsigned)s.tbase[i] * 3;
 				for (int tr = 0; tr < ntri; ++tr)
 				{
 					const unsigned a = vids[cd[1 + tr * 3]], b = vids[cd[2 + tr * 3]], cc = vids[cd[3 + tr * 3]];
@@ -1583,10 +1549,10 @@ __global__ void __launch_bounds__(VXB_THREADS, VXB_OCC) vxb_transition_kernel(co
 			}
 		}
 		__syncthreads();
-		if (tid < 6)
+		if (tid == 0)
 		{
 			VxbBlockRec* br = &d.blockRecs[slot];
-			br->tvoff[tid] = s.tvoff[tid]; br->tioff[tid] = s.tioff[tid]; br->tvcount[tid] = s.tvcount[tid]; br->ticount[tid] = s.ticount[tid];
+			br->tvoff[face] = s.tvoff; br->tioff[face] = s.tioff; br->tvcount[face] = s.tvcount; br->ticount[face] = s.ticount;
 		}
 		__syncthreads();
 	}
