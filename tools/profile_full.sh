@@ -5,7 +5,7 @@
 out=$1; shift
 mkdir -p "$(dirname "$out")"
 export VXB200_NO_GRAPH=1   # plain launches: one ncu record per kernel, in launch order
-ncu --set full --clock-control none --import-source on --kernel-name regex:vxb_ --launch-skip 17 --launch-count 15 -f -o "$out" \
+ncu --set full --clock-control none --import-source on --kernel-name regex:vxb_ --launch-skip 21 --launch-count 19 -f -o "$out" \
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --no-config4 "$@" > "$out.log" 2>&1
 ncu -i "$out.ncu-rep" --page raw --csv > "$out.raw.csv" 2>/dev/null
 ncu -i "$out.ncu-rep" --page details > "$out.details.txt" 2>/dev/null

@@ -119,6 +119,7 @@ struct vxb_context
 	bool haveLattice1 = false, latticeOff = false;
 	int gridBlock[3] = { 0, 0, 0 }, gridBlock0Small = 0, level0Threads = 256, gridDecideBig = 0, gridTransition = 0;
 	DevBuf<unsigned char> mixInfo, coarseDone;
+	DevBuf<unsigned short> mixCount;
 	// lattices of the coarse levels (VxbDev::coarseLattice): own buffer, or - sharded runs - an area of the buffer the peers map
 	DevBuf<unsigned char> coarseLatticeBuf;
 	DevBuf<CUtensorMap> coarseMaps;
@@ -687,7 +688,7 @@ void vxb_destroy(vxb_context* ctx)
 	releaseCube(ctx);
 	ctx->fillColumns.release(); ctx->packSizes.release(); ctx->packFlags.release();
 	ctx->drawCmd.release(); ctx->drawTCmd.release(); ctx->drawInfo.release(); ctx->drawTInfo.release(); ctx->drawCounts.release();
-	ctx->mixInfo.release(); ctx->coarseDone.release(); ctx->coarseLatticeBuf.release(); ctx->coarseMaps.release();
+	ctx->mixInfo.release(); ctx->coarseDone.release(); ctx->mixCount.release(); ctx->coarseLatticeBuf.release(); ctx->coarseMaps.release();
 	ctx->volDist.release(); ctx->volMat.release(); ctx->volBlend.release(); ctx->staging.release(); ctx->packOffsets.release(); ctx->updCoords.release(); ctx->lattice1.release();
 	ctx->scanFlags.release(); ctx->blockInfo.release(); ctx->consPages.release(); ctx->validFlags.release();
 	ctx->cachePages.release(); ctx->worklist.release(); ctx->emitList.release(); ctx->bigList.release(); ctx->transList.release(); ctx->ntScratch.release(); ctx->cellBlock.release(); ctx->vlist.release(); ctx->cellRecs.release(); ctx->blockRecs.release(); ctx->tvlist.release(); ctx->verts.release(); ctx->tverts.release();
@@ -1226,6 +1227,7 @@ static int runPolygonize(vxb_context* ctx, uint32_t maxLevels, uint32_t flags, c
 	VXB_CUDA(ctx, ctx->validFlags.ensure(validBytes));
 	VXB_CUDA(ctx, ctx->cachePages.ensure(cacheEntries ? cacheEntries : 1));
 	VXB_CUDA(ctx, ctx->mixInfo.ensure(mixBytes ? mixBytes : 16));
+	VXB_CUDA(ctx, ctx->mixCount.ensure(mixBytes ? mixBytes : 16));
 	VXB_CUDA(ctx, ctx->coarseDone.ensure(coarseBlocks ? coarseBlocks : 16));
 	VXB_CUDA(ctx, ctx->worklist.ensure(totalBlocks));
 	VXB_CUDA(ctx, ctx->records.ensure(totalBlocks));
@@ -1251,6 +1253,7 @@ static int runPolygonize(vxb_context* ctx, uint32_t maxLevels, uint32_t flags, c
 	{
 		dev.cachePages[l] = ctx->cachePages.p + cacheOff[l]; dev.cacheValid[l] = ctx->validFlags.p + validOff[l];
 		dev.mixInfo[l] = ctx->mixInfo.p + mixOff[l];
+		dev.mixCount[l] = ctx->mixCount.p + mixOff[l];
 	}
 	dev.coarseLo = coarseLo; dev.coarseDone = ctx->coarseDone.p;
 	VxbCoarseLattices scanLat;
@@ -1388,11 +1391,11 @@ static int runPolygonize(vxb_context* ctx, uint32_t maxLevels, uint32_t flags, c
 			if (levels > 1)
 			{
 				// sign-mix pyramid: the block walk of levels >= 2 and (sharded runs) the weights of the super-blocks
-				size_t threadsA = 0, ctasB = 0;
-				for (int l = 1; l < levels; ++l) { if (l <= 2) threadsA += blocksAtLevel(n, l); else ctasB += blocksAtLevel(n, l); }
-				const unsigned ctasA = (unsigned)((threadsA + 255) / 256);
+				size_t threadsA = 0;
+				for (int l = 1; l < levels && l <= 2; ++l) threadsA += blocksAtLevel(n, l);
 				timer.begin(1);
-				vxb_pyramid_kernel<<<ctasA + (unsigned)ctasB, 256, 0, st>>>(dev, ctasA);
+				vxb_pyramid_kernel<<<(unsigned)((threadsA + 255) / 256), 256, 0, st>>>(dev);
+				if (levels > 3) { vxb_pyramid_top_kernel<<<1, 1024, 0, st>>>(dev); ++launches; ++ctx->kindLaunches[1]; }
 				timer.end(); ++launches; ++ctx->kindLaunches[1];
 			}
 			if (sharded) { timer.begin(1); vxb_plan_kernel<<<1, 1024, 0, st>>>(dev); timer.end(); ++launches; ++ctx->kindLaunches[1]; }

@@ -356,10 +356,7 @@ __global__ void __launch_bounds__(T, (MODE == 0 ? (T == 128 ? 5 : 3) : (MODE == 
 			if (tid < 128) s.wpre[tid] = ex;
 		}
 		__syncthreads();
-		// MODE 2: the coarse blocks form a dependency chain, so an item only classifies and votes (short); the emission work
-		// of its blocks is left to vxb_decide_kernel<4096, 1> (the path of oversized blocks), off the chain
-		// (sharded runs only: there every rank walks the whole chain but emits 1/world of its blocks; on one GPU the in-item path is shorter overall)
-		const bool inCap = !(MODE == 2 && d.shardWorld > 1) && ntc <= (unsigned)CAP_C;
+		const bool inCap = ntc <= (unsigned)CAP_C;
 		// sharded runs: every rank classifies the coarse levels (the votes feed the next level), one of them emits the block
 		const bool emitMine = MODE != 2 || vxb_coarse_emit_is_mine(d, level, coordId);
 

@@ -106,6 +106,7 @@ struct VxbDev
 	// sign-mix pyramid (vxb_pyramid_kernel): per block of level l >= 1, bit 0 = some covered level-0 block holds a negative
 	// sample, bit 1 = a non-negative one.  Lets the block walk of levels >= 2 skip blocks that cannot have a non-trivial cell.
 	unsigned char* mixInfo[VXB_MAX_LEVELS];
+	unsigned short* mixCount[VXB_MAX_LEVELS];  // level-0 blocks with both signs under the block (saturating; exact up to level 5)
 	// coarse levels (one launch, vxb_block_kernel<2>): levels [coarseLo, computed); a block waits for the done flags of its children
 	int coarseLo;
 	// their sample lattices: level l holds the samples at multiples of 2^l plus, per axis, one extra entry for the clamped
@@ -401,63 +402,56 @@ __global__ void vxb_block_info_kernel(const signed char* __restrict__ dist, int 
 }
 
 // K1c: sign-mix pyramid over the level-0 blockInfo: mixInfo[l][b] = OR of (NEG, NONNEG) over the (2^l)^3 level-0 blocks that
-// block b of level l covers.  CTAs [0, ctasA): one thread per block of levels 1 and 2; then one CTA per block of levels >= 3.
-__global__ void __launch_bounds__(256) vxb_pyramid_kernel(const VxbDev d, const unsigned ctasA)
+// block b of level l covers; mixCount[l][b] = how many of them hold both signs (the weight of a super-block in sharded runs).
+// vxb_pyramid_kernel: levels 1 and 2 straight from blockInfo, one thread per block (8 / 64 byte reads).
+// vxb_pyramid_top_kernel: levels >= 3 from their eight children, level by level, in ONE CTA (<= 4681 blocks in total).
+__global__ void __launch_bounds__(256) vxb_pyramid_kernel(const VxbDev d)
 {
 	const int nb0 = d.n >> 4;
-	if (blockIdx.x < ctasA)
+	unsigned q = blockIdx.x * 256u + threadIdx.x;
+	int level = 0;
+	for (int l = 1; l <= 2 && l < d.levels; ++l)
 	{
-		unsigned q = blockIdx.x * 256u + threadIdx.x;
-		int level = 0;
-		for (int l = 1; l <= 2 && l < d.levels; ++l)
-		{
-			const unsigned cnt = (unsigned)(nb0 >> l) * (nb0 >> l) * (nb0 >> l);
-			if (q < cnt) { level = l; break; }
-			q -= cnt;
-		}
-		if (!level) return;
-		const int nb = nb0 >> level, span = 1 << level;
-		const int bx = q % nb, by = (q / nb) % nb, bz = q / (nb * nb);
-		unsigned u = 0, mixed = 0;
-		for (int z = 0; z < span; ++z) for (int y = 0; y < span; ++y)
-		{
-			const unsigned char* row = vxb_binfo_row(d, by * span + y, bz * span + z) + bx * span;
-			for (int x = 0; x < span; ++x) { u |= row[x]; mixed += (row[x] & 3u) == 3u; }
-		}
-		d.mixInfo[level][q] = (unsigned char)(u & 3u);
-		if (d.sbWeight && level == d.sbLevel) d.sbWeight[q] = mixed;
-		return;
-	}
-	unsigned q = blockIdx.x - ctasA;
-	int level = 3;
-	for (; level < d.levels; ++level)
-	{
-		const unsigned cnt = (unsigned)(nb0 >> level) * (nb0 >> level) * (nb0 >> level);
-		if (q < cnt) break;
+		const unsigned cnt = (unsigned)(nb0 >> l) * (nb0 >> l) * (nb0 >> l);
+		if (q < cnt) { level = l; break; }
 		q -= cnt;
 	}
-	if (level >= d.levels) return;
-	const int nb = nb0 >> level, span = 1 << level; // span >= 8: rows of whole 8-byte words
+	if (!level) return;
+	const int nb = nb0 >> level, span = 1 << level;
 	const int bx = q % nb, by = (q / nb) % nb, bz = q / (nb * nb);
 	unsigned u = 0, mixed = 0;
-	for (int r = threadIdx.x; r < span * span; r += 256)
+	for (int z = 0; z < span; ++z) for (int y = 0; y < span; ++y)
 	{
-		const uint2* row = reinterpret_cast<const uint2*>(vxb_binfo_row(d, by * span + r % span, bz * span + r / span) + bx * span);
-		for (int x = 0; x < span / 8; ++x)
-		{
-			const uint2 w = row[x];
-			u |= w.x | w.y;
-			mixed += __popc(w.x & (w.x >> 1) & 0x01010101u) + __popc(w.y & (w.y >> 1) & 0x01010101u);
-		}
+		const unsigned char* row = vxb_binfo_row(d, by * span + y, bz * span + z) + bx * span;
+		for (int x = 0; x < span; ++x) { u |= row[x]; mixed += (row[x] & 3u) == 3u; }
 	}
-	u |= u >> 16; u |= u >> 8;
-	const int neg = __syncthreads_or(u & 1u), nonneg = __syncthreads_or(u & 2u);
-	if (threadIdx.x == 0) d.mixInfo[level][q] = (unsigned char)((neg ? 1u : 0u) | (nonneg ? 2u : 0u));
-	if (d.sbWeight && level == d.sbLevel)
+	d.mixInfo[level][q] = (unsigned char)(u & 3u);
+	d.mixCount[level][q] = (unsigned short)mixed;
+	if (d.sbWeight && level == d.sbLevel) d.sbWeight[q] = mixed;
+}
+
+__global__ void __launch_bounds__(1024) vxb_pyramid_top_kernel(const VxbDev d)
+{
+	const int nb0 = d.n >> 4;
+	for (int level = 3; level < d.levels; ++level)
 	{
-		if (threadIdx.x == 0) d.sbWeight[q] = 0;
-		__syncthreads();
-		if (mixed) atomicAdd(&d.sbWeight[q], mixed);
+		const int nb = nb0 >> level, cnb = nb * 2;
+		const unsigned cnt = (unsigned)nb * nb * nb;
+		for (unsigned q = threadIdx.x; q < cnt; q += 1024u)
+		{
+			const int bx = q % nb, by = (q / nb) % nb, bz = q / (nb * nb);
+			unsigned u = 0, mixed = 0;
+			for (int c = 0; c < 8; ++c)
+			{
+				const size_t cb = ((size_t)(bz * 2 + (c >> 2)) * cnb + (by * 2 + ((c >> 1) & 1))) * cnb + (bx * 2 + (c & 1));
+				u |= d.mixInfo[level - 1][cb];
+				mixed += d.mixCount[level - 1][cb];
+			}
+			d.mixInfo[level][q] = (unsigned char)(u & 3u);
+			d.mixCount[level][q] = (unsigned short)min(mixed, 65535u);
+			if (d.sbWeight && level == d.sbLevel) d.sbWeight[q] = mixed;
+		}
+		__syncthreads(); // the next level reads what this one wrote (same CTA: visible after the barrier)
 	}
 }
 
