@@ -82,7 +82,7 @@ __device__ __forceinline__ unsigned vxb_rank_of(const unsigned int* nt32, const 
 // Capacities of the shared-memory path of vxb_block_kernel<MODE, T>: non-trivial cells of a block (larger blocks go to
 // vxb_decide_kernel<4096, 1>) and new vertices of a level-0 block generated inside the CTA (more => the flat kernels).
 // The 128-thread level-0 variant trades capacity and the second tile buffer for twice as many resident CTAs.
-template <int MODE, int T> struct VxbBlockCaps { static constexpr int CAP = 1024, VL = (MODE == 0 ? 2048 : 8), NBUF = 2; };
+template <int MODE, int T> struct VxbBlockCaps { static constexpr int CAP = 1024, VL = (MODE == 0 ? 2048 : 8), NBUF = (MODE == 0 ? 1 : 2); }; // level 0: one tile buffer => 4 CTAs per SM
 template <> struct VxbBlockCaps<0, 128> { static constexpr int CAP = 512, VL = 1024, NBUF = 1; };
 
 // ------------------------------------------------------------------------------------------------
@@ -133,7 +133,7 @@ __device__ __forceinline__ bool vxb_overflowed(const VxbDev& d)
 }
 
 template <int MODE, int T>
-__global__ void __launch_bounds__(T, (MODE == 0 ? (T == 128 ? 5 : 3) : (MODE == 2 ? 4 : VXB_OCC))) vxb_block_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB, const VxbDev d, const int levelArg)
+__global__ void __launch_bounds__(T, (MODE == 0 ? (T == 128 ? 5 : 4) : (MODE == 2 ? 4 : VXB_OCC))) vxb_block_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB, const VxbDev d, const int levelArg)
 {
 	constexpr int PITCH = (MODE == 0) ? VXB_DTILE_PITCH : VXB_TILE_PITCH;
 	constexpr int ROWS = (MODE == 0) ? 19 : 17;
@@ -196,9 +196,9 @@ __global__ void __launch_bounds__(T, (MODE == 0 ? (T == 128 ? 5 : 3) : (MODE == 
 		else
 		{
 			level = levelArg;
-			const int nbl = (d.n >> 4) >> level;
+			const int nbl = (d.n >> 4) >> level, sh = __ffs(nbl) - 1; // a power of two
 			const unsigned c = worklist[item];
-			bx = c % nbl; by = (c / nbl) % nbl; bz = c / (nbl * nbl);
+			bx = c & (nbl - 1); by = (c >> sh) & (nbl - 1); bz = c >> (2 * sh);
 		}
 	};
 	// tile of the block: issue (thread 0; asynchronous when TMA applies) ...
