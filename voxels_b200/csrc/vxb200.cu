@@ -1295,10 +1295,18 @@ static int runPolygonize(vxb_context* ctx, uint32_t maxLevels, uint32_t flags, c
 			if (p == sh.rank) continue;
 			if (!sh.peerSet[p]) return fail(ctx, VXB_ERR_STATE, "vxb_polygonize_sharded: a peer's page buffer is not set (vxb_shard_set_peer / vxb_shard_import)");
 			peers.pages[peers.count] = sh.peerPages[p]; peers.valid[peers.count] = sh.peerValid[p];
+			peers.peerSlots[peers.count] = reinterpret_cast<unsigned long long*>(sh.peerLattice[p] + sh.latticeBytes);
 			peerLat.base[peers.count] = sh.peerLattice[p];
 			++peers.count;
 		}
 		peerLat.count = peers.count;
+		{
+			unsigned char* area = sh.pagesBuf + sh.pagesBytes + sh.validBytes + sh.latticeBytes;
+			peers.mySlots = reinterpret_cast<unsigned long long*>(area);
+			peers.epoch = reinterpret_cast<unsigned long long*>(area + 64);
+			peers.arrived = reinterpret_cast<unsigned int*>(area + 128);
+			peers.rank = (int)sh.rank;
+		}
 		if (shardPhase == 3 && sh.world > 1 && (!sh.comm || !ncclApi().ok)) return fail(ctx, VXB_ERR_STATE, "vxb_polygonize_sharded: phase 3 needs vxb_shard_nccl_init");
 	}
 	const int scanWorld = sharded ? (int)sh.world : 1, scanRank = sharded ? (int)sh.rank : 0, scanGroup = sharded ? (int)sh.groupLayers : (int)nb0;
@@ -1481,10 +1489,11 @@ static int runPolygonize(vxb_context* ctx, uint32_t maxLevels, uint32_t flags, c
 			}
 			else
 			{
-				// the pages were written straight into the peers' buffers by vxb_publish_kernel; this all-gather (one word per
-				// rank) only orders every rank's coarse levels after every rank's publication
-				const int r = nccl.allGather(sh.barrierBuf.p + sh.rank, sh.barrierBuf.p, 8, /*ncclUint8*/ 1, sh.comm, st);
-				if (r != 0) return failNccl(ctx, "ncclAllGather (page exchange barrier)", r);
+				// the pages were written straight into the peers' buffers by vxb_publish_kernel, whose last CTA announced this
+				// step's epoch to every peer; waiting for the peers' epochs orders every rank's coarse levels after every rank's
+				// publication (a device-side barrier over the mapped buffers: ~5 us instead of a ~40 us one-word all-gather)
+				vxb_peer_wait_kernel<<<1, 32, 0, st>>>(peers, (int)sh.world);
+				++launches;
 			}
 			timer.end();
 			return VXB_OK;
@@ -1695,7 +1704,8 @@ int vxb_shard_configure(vxb_context* ctx, uint32_t rank, uint32_t world, uint32_
 		size_t offs[VXB_MAX_LEVELS];
 		sh.latticeBytes = coarseLatticeLayout(n, ctx->levels, offs);
 	}
-	sh.bufBytes = sh.pagesBytes + sh.validBytes + sh.latticeBytes;
+	sh.latticeBytes = (sh.latticeBytes + 255) & ~(size_t)255;
+	sh.bufBytes = sh.pagesBytes + sh.validBytes + sh.latticeBytes + 256; // pages | valid | lattices | barrier area (8 slots, epoch, CTA counter)
 	const VmmApi& api = vmmApi();
 	if (api.ok)
 	{
@@ -1716,6 +1726,7 @@ int vxb_shard_configure(vxb_context* ctx, uint32_t rank, uint32_t world, uint32_
 	{
 		VXB_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&sh.pagesBuf), sh.bufBytes));
 	}
+	VXB_CUDA(ctx, cudaMemset(sh.pagesBuf + sh.pagesBytes + sh.validBytes + sh.latticeBytes, 0, 256));
 	sh.on = true;
 	// virtual ranks over one shared upload: no shared even-lattice copy => level 1 gathers its tiles.  The coarse levels'
 	// lattices move into the buffer the peers map (buildTensorMap -> buildCoarseLattices).

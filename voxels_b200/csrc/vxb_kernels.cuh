@@ -747,6 +747,14 @@ struct VxbPeers
 	unsigned short* pages[8];
 	unsigned char* valid[8];
 	int count;
+	// the barrier that orders every rank's coarse levels after every rank's page stores: a slot per source rank in each
+	// rank's (peer-mapped) buffer; the LAST CTA of the publishing kernel - it has seen every other CTA's fenced stores -
+	// writes this step's epoch into slot [myRank] of every peer, vxb_peer_wait_kernel waits for the peers' epochs
+	unsigned long long* peerSlots[8];  // peers' slot arrays (remote)
+	unsigned long long* mySlots;       // [8] local: written by the peers
+	unsigned long long* epoch;         // local step counter
+	unsigned int* arrived;             // local CTA counter of the publishing kernel
+	int rank;
 };
 
 // Sharded runs: the planes of the coarse levels' lattices this rank wrote while scanning its pieces go to every peer
@@ -781,6 +789,7 @@ __global__ void __launch_bounds__(VXB_THREADS) vxb_publish_lattice_kernel(const 
 
 __global__ void __launch_bounds__(VXB_THREADS) vxb_publish_kernel(const VxbDev d, const VxbPeers peers)
 {
+	__shared__ unsigned sLast;
 	const int nbs = (d.n >> 4) >> d.sbLevel;
 	const unsigned count = (unsigned)nbs * nbs * nbs;
 	for (unsigned b = blockIdx.x; b < count; b += gridDim.x)
@@ -795,6 +804,35 @@ __global__ void __launch_bounds__(VXB_THREADS) vxb_publish_kernel(const VxbDev d
 			if (threadIdx.x == 0) peers.valid[p][b] = 1;
 		}
 	}
+	// signal: every thread's stores are fenced system-wide before its CTA counts itself in; the last CTA to arrive has
+	// therefore observed all of them and announces this step's epoch to the peers
+	__threadfence_system();
+	__syncthreads();
+	if (threadIdx.x == 0) sLast = (atomicAdd(peers.arrived, 1u) == gridDim.x - 1) ? 1u : 0u;
+	__syncthreads();
+	if (sLast && threadIdx.x < (unsigned)peers.count)
+	{
+		__threadfence_system();
+		const unsigned long long e = *peers.epoch + 1ull;
+		*(volatile unsigned long long*)(peers.peerSlots[threadIdx.x] + peers.rank) = e;
+	}
+	if (sLast)
+	{
+		__syncthreads();
+		if (threadIdx.x == 0) { *peers.epoch += 1ull; *peers.arrived = 0u; __threadfence(); }
+	}
+}
+
+// waits until every peer has announced the current epoch (vxb_publish_kernel): one lane per peer slot
+__global__ void vxb_peer_wait_kernel(const VxbPeers peers, const int world)
+{
+	const int p = threadIdx.x;
+	if (p >= world || p == peers.rank) return;
+	const unsigned long long e = *(volatile unsigned long long*)peers.epoch; // already advanced by this rank's publishing kernel
+	const volatile unsigned long long* slot = peers.mySlots + p;
+	unsigned spins = 0;
+	while (*slot < e) { __nanosleep(100); if (++spins > (1u << 26)) __trap(); } // a peer that never arrives must fail the step, not hang it
+	__threadfence_system();
 }
 
 // ------------------------------------------------------------------------------------------------
