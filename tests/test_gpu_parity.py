@@ -257,3 +257,31 @@ def test_config3_terrain_1024_all_levels_against_reference(reference, gpu_contex
     dist, mat, blend = _terrain_numpy(1024)
     problems, res = run_both(reference, gpu_context, dist, mat, blend)
     assert not problems, "\n".join(problems[:10])
+
+
+def test_packed_upload_rejects_malformed_blobs(reference):
+    """A blob whose size table, length or per-block flags are inconsistent must fail with an argument error (never read out
+    of bounds, never leave a half-decoded grid behind): the flags words are checked by the decoding kernel itself."""
+    import voxels_b200
+    from voxels_b200 import capi
+    dist, mat, blend = grids.SMALL["hostile64"]()
+    good = voxels_b200.pack_dense(dist, mat, blend).copy()
+    ctx = voxels_b200.Context(0)
+    try:
+        ctx.upload_packed(good)
+        nb = 4; table = 16; data0 = 16 + nb ** 3 * 12
+        sizes = good[table:data0].view(np.uint32).reshape(-1, 3)
+        cases = {}
+        b = good.copy(); b[table:table + 4].view(np.uint32)[0] = 5000; cases["size > 4096 in the table"] = b
+        cases["truncated"] = good[:len(good) - 100].copy()
+        b = good.copy(); b[data0:data0 + 4].view(np.uint32)[0] |= 2; cases["raw flag on a run-length coded channel"] = b   # block 0: BF_DistanceUncompressed but size < 4096
+        assert sizes[0, 0] < 4096
+        for what, blob in cases.items():
+            with pytest.raises(capi.VxbError):
+                ctx.upload_packed(blob)
+            with pytest.raises(capi.VxbError):   # no grid after a failed upload
+                ctx.polygonize()
+        ctx.upload_packed(good)                  # and the context still works
+        ctx.polygonize()
+    finally:
+        ctx.close()

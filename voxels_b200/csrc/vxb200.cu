@@ -83,7 +83,7 @@ struct vxb_context
 	DevBuf<unsigned int> drawCounts;
 	vxb_draw_lists drawLists;
 	VxbDev lastDev; // kernel-side view of the last run (records, arenas), for the consumer-side kernels
-	DevBuf<unsigned int> packSizes, packFlags;
+	DevBuf<unsigned int> packSizes, packFlags, packError;
 	struct PinnedBuf // page-locked host scratch (grows, never shrinks)
 	{
 		void* p = nullptr; size_t bytes = 0;
@@ -686,7 +686,7 @@ void vxb_destroy(vxb_context* ctx)
 	releaseShard(ctx);
 	if (ctx->shard.comm && ncclApi().ok) { ncclApi().commDestroy(ctx->shard.comm); ctx->shard.comm = nullptr; }
 	releaseCube(ctx);
-	ctx->fillColumns.release(); ctx->packSizes.release(); ctx->packFlags.release();
+	ctx->fillColumns.release(); ctx->packSizes.release(); ctx->packFlags.release(); ctx->packError.release();
 	ctx->drawCmd.release(); ctx->drawTCmd.release(); ctx->drawInfo.release(); ctx->drawTInfo.release(); ctx->drawCounts.release();
 	ctx->mixInfo.release(); ctx->coarseDone.release(); ctx->mixCount.release(); ctx->coarseLatticeBuf.release(); ctx->coarseMaps.release();
 	ctx->volDist.release(); ctx->volMat.release(); ctx->volBlend.release(); ctx->staging.release(); ctx->packOffsets.release(); ctx->updCoords.release(); ctx->lattice1.release();
@@ -789,60 +789,19 @@ int vxb_grid_upload_packed(vxb_context* ctx, const void* blob, size_t size)
 	bool corrupt = false, truncated = false;
 	unsigned long long off = head;
 	{
-		// per-block byte offsets = prefix sum of the size table, and a check of every block's flags word, on all host threads:
-		// chunk sums from the table, a short serial prefix over the chunks, then offsets + checks per chunk
+		// per-block byte offsets = prefix sum of the size table (sequential, 12 bytes per block).  The blocks' flag words lie
+		// scattered through the blob (one cache miss each on the host), so they are checked where they are read anyway:
+		// on the device, by vxb_unpack_rle_kernel (packError)
 		const unsigned char* table = bytes + 16;
-		const int chunks = 256;
-		const size_t per = (blocks + chunks - 1) / chunks;
-		unsigned long long chunkBytes[chunks + 1];
-		int bad = 0;
-		#pragma omp parallel for schedule(static) reduction(|:bad)
-		for (int c = 0; c < chunks; ++c)
+		for (size_t b = 0; b < blocks; ++b)
 		{
-			unsigned long long sum = 0;
-			const size_t b0 = std::min(blocks, per * c), b1 = std::min(blocks, b0 + per);
-			for (size_t b = b0; b < b1; ++b)
-			{
-				uint32_t sz[3];
-				memcpy(sz, table + b * 12, 12);
-				if (sz[0] > 4096 || sz[1] > 4096 || sz[2] > 4096) bad |= 1;
-				sum += 4ull + sz[0] + sz[1] + sz[2];
-			}
-			chunkBytes[c] = sum;
+			uint32_t sz[3];
+			memcpy(sz, table + b * 12, 12);
+			if (sz[0] > 4096 || sz[1] > 4096 || sz[2] > 4096) { corrupt = true; break; }
+			hostOffsets[b] = off;
+			off += 4ull + sz[0] + sz[1] + sz[2];
 		}
-		if (bad) corrupt = true;
-		if (!corrupt)
-		{
-			unsigned long long run = head;
-			for (int c = 0; c < chunks; ++c) { const unsigned long long v = chunkBytes[c]; chunkBytes[c] = run; run += v; }
-			off = run;
-			if (off > size) truncated = true;
-		}
-		if (!corrupt && !truncated)
-		{
-			#pragma omp parallel for schedule(static) reduction(|:bad)
-			for (int c = 0; c < chunks; ++c)
-			{
-				unsigned long long o = chunkBytes[c];
-				const size_t b0 = std::min(blocks, per * c), b1 = std::min(blocks, b0 + per);
-				for (size_t b = b0; b < b1; ++b)
-				{
-					uint32_t sz[3];
-					memcpy(sz, table + b * 12, 12);
-					hostOffsets[b] = o;
-					// the block's flags word: a raw channel holds exactly 4096 bytes, a run-length coded one whole (length, value) pairs
-					uint32_t bflags;
-					memcpy(&bflags, bytes + o, 4);
-					for (int ch = 0; ch < 3; ++ch)
-					{
-						const bool raw = (bflags >> (1 + ch)) & 1u;
-						if (raw ? (sz[ch] != 4096) : (sz[ch] == 0 || (sz[ch] & 1u))) bad |= 1;
-					}
-					o += 4ull + sz[0] + sz[1] + sz[2];
-				}
-			}
-			if (bad) corrupt = true;
-		}
+		if (!corrupt && off > size) truncated = true;
 	}
 	const double msTable = msSince(t0);
 	if (corrupt || truncated || off > size)
@@ -852,6 +811,8 @@ int vxb_grid_upload_packed(vxb_context* ctx, const void* blob, size_t size)
 		return fail(ctx, VXB_ERR_ARGUMENT, corrupt ? "vxb_grid_upload_packed: corrupt size table or block flags" : "vxb_grid_upload_packed: truncated block data");
 	}
 	VXB_CUDA(ctx, cudaMemcpyAsync(ctx->packOffsets.p, hostOffsets, blocks * sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream));
+	VXB_CUDA(ctx, ctx->packError.ensure(1));
+	VXB_CUDA(ctx, cudaMemsetAsync(ctx->packError.p, 0, sizeof(unsigned int), ctx->stream));
 	std::vector<std::pair<size_t, size_t> > ranges; // block layers [first, second)
 	if (pieces)
 	{
@@ -881,12 +842,19 @@ int vxb_grid_upload_packed(vxb_context* ctx, const void* blob, size_t size)
 		VXB_CUDA(ctx, cudaEventRecord(ctx->evChunks[c], ctx->stream));
 		VXB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->evChunks[c], 0));
 		vxb_unpack_rle_kernel<<<(unsigned)(groupsPerLayer * (layer1 - layer0)), VXB_THREADS, 0, ctx->stream2>>>(ctx->staging.p, ctx->packOffsets.p,
-			reinterpret_cast<const unsigned int*>(ctx->staging.p + 16), outDist, outMat, outBlend, (int)n, (int)layer0);
+			reinterpret_cast<const unsigned int*>(ctx->staging.p + 16), outDist, outMat, outBlend, (int)n, (int)layer0, ctx->packError.p);
 	}
 	VXB_CUDA(ctx, cudaGetLastError());
 	VXB_CUDA(ctx, cudaEventRecord(ctx->evJoin, ctx->stream2));
 	VXB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->evJoin, 0));
+	unsigned int packError = 0;
+	VXB_CUDA(ctx, cudaMemcpyAsync(&packError, ctx->packError.p, sizeof(packError), cudaMemcpyDeviceToHost, ctx->stream));
 	VXB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	if (packError)
+	{
+		ctx->haveGrid = false;
+		return fail(ctx, VXB_ERR_ARGUMENT, "vxb_grid_upload_packed: a block's flags word contradicts its sizes (a raw channel must hold 4096 bytes, a run-length coded one whole (length, value) pairs)");
+	}
 	const double msKernel = msSince(t0);
 	if (pieces) { ctx->haveResult = false; ctx->haveFullRun = false; r = VXB_OK; }
 	else r = finishUpload(ctx);

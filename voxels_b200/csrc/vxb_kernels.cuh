@@ -518,7 +518,8 @@ __device__ __forceinline__ void vxb_decode_channel(const unsigned char* src, uns
 
 __global__ void __launch_bounds__(VXB_THREADS) vxb_unpack_rle_kernel(const unsigned char* __restrict__ blob, const unsigned long long* __restrict__ blockOffsets,
 	const unsigned int* __restrict__ sizes, unsigned char* __restrict__ dist, unsigned char* __restrict__ mat, unsigned char* __restrict__ blend, int n,
-	int zLayer0 /* first block layer of this launch: the blob is decoded in z-chunks while the rest is still being copied */)
+	int zLayer0 /* first block layer of this launch: the blob is decoded in z-chunks while the rest is still being copied */,
+	unsigned int* __restrict__ error /* set when a block's flags word contradicts its sizes; such a channel is zero-filled */)
 {
 	__shared__ unsigned short start[2049];
 	__shared__ unsigned char value[2048];
@@ -543,7 +544,12 @@ __global__ void __launch_bounds__(VXB_THREADS) vxb_unpack_rle_kernel(const unsig
 			for (int c = 0; c < ch; ++c) off += sizes[b * 3 + c];
 			const unsigned size = sizes[b * 3 + ch];
 			sOff[j][ch] = off; sSize[j][ch] = size;
-			if ((flags >> (1 + ch)) & 1u) kind = -2;
+			if ((flags >> (1 + ch)) & 1u)
+			{
+				if (size == 4096u) kind = -2;
+				else { kind = 0; *error = 1u; } // a raw channel holds exactly 4096 bytes: never read past what the table says
+			}
+			else if (size == 0u || (size & 1u)) { kind = 0; *error = 1u; } // whole (length, value) pairs
 			else
 			{
 				const unsigned char* p = blob + off;
