@@ -105,6 +105,15 @@ int vxb_grid_upload_blocks(vxb_context* ctx, uint32_t n, const int8_t* dist_bloc
  * HOST memory.  The blob is copied to the device as is (typically 10-30x smaller than the dense volumes) and the
  * run-length decoding (VoxelGrid::DecompressBlock :674-694) happens on the GPU. */
 int vxb_grid_upload_packed(vxb_context* ctx, const void* blob, size_t size);
+/* The same upload fed slab by slab, for a caller that is still gathering the grid store's blocks into `blob` (the drop-in's
+ * Execute: VoxelGrid's per-block vectors -> one pinned blob).  At the call the 16-byte header and the COMPLETE size table
+ * must be in place; the block data is produced on demand: before the library copies the data of the block layers
+ * [layer0, layer1) (blocks layer0*nb*nb .. layer1*nb*nb-1 in VoxelGrid order) it calls produce(user, layer0, layer1) on the
+ * calling thread, which must have written those blocks' {flags, distance, material, blend} bytes on return.  The copy and the
+ * GPU decode of one slab run while the producer fills the next.  Layers are asked for in ascending order, each exactly once
+ * (a context with a cube: only the layers of the pieces this rank backs).  produce = NULL: vxb_grid_upload_packed. */
+typedef void (*vxb_pack_producer)(void* user, uint32_t layer0, uint32_t layer1);
+int vxb_grid_upload_packed_streamed(vxb_context* ctx, const void* blob, size_t size, vxb_pack_producer produce, void* user);
 /* Host-side helper (no GPU involved): writes the PackForSave form of dense n^3 volumes into `out` (capacity bytes).
  * Byte-identical to what the reference produces for the same voxels.  vxb_pack_dense_bound = worst-case size. */
 size_t vxb_pack_dense_bound(uint32_t n);
@@ -259,6 +268,13 @@ int vxb_cube_piece(vxb_context* ctx, uint32_t piece, int8_t** dist, uint8_t** ma
  * Voxels::PolygonVertex (include/Polygonizer.h:14-48).  Any pointer may be NULL to skip it. */
 int vxb_result_download(vxb_context* ctx, vxb_block_record* records, void* vertices, uint32_t* indices,
 	void* trans_vertices, uint32_t* trans_indices);
+/* The same download in two steps: _begin queues the copies of the arenas and returns as soon as the directory has arrived
+ * and been sorted (`records` is filled), so that the caller can build its per-block views (pointers into the arenas:
+ * PushBlocksToResult, src/TransVoxelImpl.cpp:1274-1293) while the arenas are still in flight; _end waits for them (and
+ * restores the all-zero textures of unmapped materials).  The arenas must not be read, and no run started, in between. */
+int vxb_result_download_begin(vxb_context* ctx, vxb_block_record* records, void* vertices, uint32_t* indices,
+                              void* trans_vertices, uint32_t* trans_indices);
+int vxb_result_download_end(vxb_context* ctx);
 
 /* ---- consumer side: the result as indirect draws, without leaving HBM (doc_source/Rendering.md:18-58) ------------------
  * The arenas are merged vertex / index buffers: a block is drawn with {index_count, first_index, base_vertex} (indices are

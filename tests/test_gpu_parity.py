@@ -285,3 +285,49 @@ def test_packed_upload_rejects_malformed_blobs(reference):
         ctx.polygonize()
     finally:
         ctx.close()
+
+
+def test_streamed_packed_upload_and_split_download():
+    """vxb_grid_upload_packed_streamed with a producer that writes each slab only when asked equals the plain packed upload,
+    every layer is asked for exactly once in ascending order; vxb_result_download_begin/_end equals vxb_result_download."""
+    import voxels_b200
+    from voxels_b200 import capi
+    dist, mat, blend = grids.MEDIUM["hostile128"]()
+    n = 128; nb = n // 16
+    good = voxels_b200.pack_dense(dist, mat, blend).copy()
+    head = 16 + nb ** 3 * 12
+    sizes = good[16:head].view(np.uint32).reshape(-1, 3).astype(np.int64)
+    offsets = head + np.concatenate([[0], np.cumsum(4 + sizes.sum(axis=1))])
+    ctx = voxels_b200.Context(0)
+    try:
+        ctx.upload_packed(good)
+        ctx.polygonize()
+        want = ctx.download()
+        want_dense = ctx.download_dense()
+        blob = good.copy()
+        blob[head:] = 0xEE                      # no block data yet
+        asked = []
+
+        def produce(l0, l1):
+            asked.append((l0, l1))
+            a, b = offsets[l0 * nb * nb], offsets[l1 * nb * nb]
+            blob[a:b] = good[a:b]
+        ctx.upload_packed_streamed(blob, produce)
+        assert asked and asked[0][0] == 0 and asked[-1][1] == nb and all(asked[i][1] == asked[i + 1][0] for i in range(len(asked) - 1))
+        got_dense = ctx.download_dense()
+        for a, b in zip(want_dense, got_dense):
+            assert np.array_equal(a, b)
+        info = ctx.polygonize()
+        res = ctx.download_begin()
+        assert np.array_equal(res.records, want.records)      # the directory is there before the arenas
+        with pytest.raises(capi.VxbError):                     # no run while a download is open
+            ctx.polygonize()
+        ctx.download_end()
+        problems = []
+        for l in range(info.levels_total):
+            problems += compare.level_diff(want.level(l), res.level(l), "L%d" % l)
+        assert not problems, "\n".join(problems[:10])
+        with pytest.raises(capi.VxbError):
+            ctx.download_end()
+    finally:
+        ctx.close()

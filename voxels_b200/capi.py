@@ -78,6 +78,9 @@ class NcclId(C.Structure):
 
 ERR_CAPACITY = -4
 
+# vxb_pack_producer (include/vxb200.h): void (*)(void* user, uint32_t layer0, uint32_t layer1)
+PackProducer = C.CFUNCTYPE(None, C.c_void_p, C.c_uint32, C.c_uint32)
+
 
 class DevicePointer:
     """A raw device range as a CUDA-array-interface object: torch.as_tensor(DevicePointer(p, nbytes), device=...) is a
@@ -120,6 +123,9 @@ def load_library():
         "vxb_grid_upload_blocks": (C.c_int, [vp, u32, vp, vp, vp]),
         "vxb_grid_set_device": (C.c_int, [vp, u32, vp, vp, vp]),
         "vxb_grid_upload_packed": (C.c_int, [vp, vp, C.c_size_t]),
+        "vxb_grid_upload_packed_streamed": (C.c_int, [vp, vp, C.c_size_t, PackProducer, vp]),
+        "vxb_result_download_begin": (C.c_int, [vp, vp, vp, vp, vp, vp]),
+        "vxb_result_download_end": (C.c_int, [vp]),
         "vxb_pack_dense_bound": (C.c_size_t, [u32]),
         "vxb_pack_dense": (C.c_int, [u32, vp, vp, vp, vp, C.c_size_t, C.POINTER(C.c_size_t)]),
         "vxb_grid_device_pointers": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),
@@ -170,7 +176,8 @@ EXPORTED_SYMBOLS = ["vxb_create", "vxb_destroy", "vxb_last_error", "vxb_stream",
                     "vxb_result_unmapped_materials", "vxb_host_alloc", "vxb_host_free", "vxb_polygonize_sharded", "vxb_shard_configure",
                     "vxb_shard_buffers_get", "vxb_shard_set_peer", "vxb_shard_export", "vxb_shard_import", "vxb_shard_nccl_unique_id",
                     "vxb_shard_nccl_init", "vxb_grid_fill", "vxb_grid_inject_surface", "vxb_grid_inject_material", "vxb_grid_pack",
-                    "vxb_grid_download_dense", "vxb_result_device_arenas", "vxb_result_select_lod", "vxb_result_download_draws", "vxb_cube_create", "vxb_cube_info", "vxb_cube_export", "vxb_cube_import", "vxb_cube_piece"]
+                    "vxb_grid_download_dense", "vxb_result_device_arenas", "vxb_result_select_lod", "vxb_result_download_draws", "vxb_cube_create", "vxb_cube_info", "vxb_cube_export", "vxb_cube_import", "vxb_cube_piece",
+                    "vxb_grid_upload_packed_streamed", "vxb_result_download_begin", "vxb_result_download_end"]
 
 
 def nccl_unique_id():
@@ -317,6 +324,13 @@ class Context:
             ptr, nbytes = _ptr(blob), blob.size
         self._check(self.L.vxb_grid_upload_packed(self.h, ptr, nbytes), "vxb_grid_upload_packed")
         self.n = int(np.frombuffer(C.string_at(ptr, 8), np.uint32)[1])
+
+    def upload_packed_streamed(self, blob, produce):
+        """vxb_grid_upload_packed_streamed: `blob` (numpy uint8) holds the header and the complete size table; produce(layer0,
+        layer1) is called on this thread before the data of those block layers is copied and must have written it."""
+        cb = PackProducer(lambda user, l0, l1: produce(int(l0), int(l1)))
+        self._check(self.L.vxb_grid_upload_packed_streamed(self.h, _ptr(blob), blob.size, cb, None), "vxb_grid_upload_packed_streamed")
+        self.n = int(blob[:8].view(np.uint32)[1])
 
     # ---- device-resident grid store (fill / edit / pack) ----
     def fill(self, n, surface, start=(0.0, 0.0, 0.0), step=1.0):
@@ -486,6 +500,20 @@ class Context:
         if n:
             self.L.vxb_result_unmapped_materials(self.h, _ptr(out), n)
         return out
+
+    def download_begin(self):
+        """vxb_result_download_begin into fresh numpy arrays: returns a Result whose records are valid at once and whose
+        arenas are valid after download_end()."""
+        info = self.info()
+        records = np.zeros(info.block_count, RECORD_DTYPE)
+        verts = np.zeros(info.vertex_span, VERTEX_DTYPE); idx = np.zeros(info.index_span, np.uint32)
+        tverts = np.zeros(info.trans_vertex_span, VERTEX_DTYPE); tidx = np.zeros(info.trans_index_span, np.uint32)
+        self._check(self.L.vxb_result_download_begin(self.h, _ptr(records), _ptr(verts), _ptr(idx), _ptr(tverts), _ptr(tidx)),
+                    "vxb_result_download_begin")
+        return Result(self.n, info, records, verts, idx, tverts, tidx)
+
+    def download_end(self):
+        self._check(self.L.vxb_result_download_end(self.h), "vxb_result_download_end")
 
     def download(self, into=None):
         """Device -> host copy of the directory and the arenas.  `into` may supply preallocated (pinned) buffers:

@@ -10,8 +10,11 @@
 // (same vtable order - they derive from the reference's own declarations).
 //
 // All computation happens on the GPU behind the C ABI of include/vxb200.h; this file only moves bytes:
-//   Grid --(public accessors Grid::GetBlockDistanceData / GetBlockMaterialData, include/Grid.h:127-139)-->
-//   pinned staging --> vxb_grid_upload_blocks --> vxb_polygonize --> vxb_result_download --> block views.
+//   full run:        the grid store's compressed blocks --(parallel gather, PackForSave layout)--> pinned blob
+//                    --> vxb_grid_upload_packed_streamed (copied and run-length decoded on the GPU while the next
+//                    slab is being gathered) --> vxb_polygonize --> vxb_result_download --> block views;
+//   incremental run: Grid::GetBlockDistanceData / GetBlockMaterialData (include/Grid.h:127-139) of the dirty blocks
+//                    --> vxb_grid_update_blocks --> vxb_polygonize_region --> download --> splice.
 // There is no CPU polygonization path: if the device or the CUDA library is unavailable Execute logs an
 // LS_Error and returns nullptr (the reference's own failure convention, TransVoxelImpl.cpp:2155-2164).
 #include "stdafx.h" // reference src/stdafx.h through the shim: Logger (VOXLOG), VOXELS_LOG_SIZE
@@ -35,6 +38,9 @@
 #include <new>
 #include <vector>
 #include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <omp.h>
 
 #include "../../include/vxb200.h"
 
@@ -217,6 +223,91 @@ struct ModificationImpl : public Modification
 };
 }
 
+namespace
+{
+// Threads for the gather of the compressed blocks (memory-bound: more than ~32 threads add nothing).  A container's CPU
+// quota (cgroup v2 cpu.max) caps it further: a team larger than the quota burns the period's budget while spinning at
+// the region's end and the whole process is then throttled for the rest of the period - measured on the B200 hosts as
+// 60 ms stalls in whatever stage came next.  VXB200_PACK_THREADS overrides.
+int packThreads()
+{
+	static const int threads = [] {
+		if (const char* e = getenv("VXB200_PACK_THREADS")) { const int v = atoi(e); if (v > 0) return v; }
+		int t = std::min(omp_get_max_threads(), 32);
+		if (FILE* f = fopen("/sys/fs/cgroup/cpu.max", "r"))
+		{
+			long long quota = 0, period = 0;
+			if (fscanf(f, "%lld %lld", &quota, &period) == 2 && quota > 0 && period > 0)
+				t = std::min<long long>(t, std::max<long long>(1, quota / period));
+			fclose(f);
+		}
+		return std::max(t, 1);
+	}();
+	return threads;
+}
+
+// Byte offset of every block in the PackForSave form (VoxelGrid.cpp:269-315: 16-byte header, 3 sizes per block, then per
+// block {flags, distance, material, blend}); returns the total size.
+size_t blobLayout(const std::vector<VoxelGrid::Block>& blocks, std::vector<size_t>& offsets)
+{
+	const size_t count = blocks.size();
+	offsets.resize(count + 1);
+	size_t off = 16 + count * 12;
+	for (size_t b = 0; b < count; ++b)
+	{
+		offsets[b] = off;
+		off += 4 + blocks[b].DistanceData.size() + blocks[b].MaterialData.size() + blocks[b].BlendData.size();
+	}
+	offsets[count] = off;
+	return off;
+}
+
+void packHeader(unsigned n, unsigned char* blob)
+{
+	const uint32_t header[4] = { 1u, n, n, n };
+	memcpy(blob, header, 16);
+}
+
+// size-table entries + data of blocks [first, last)
+void packBlocks(const std::vector<VoxelGrid::Block>& blocks, const std::vector<size_t>& offsets, size_t first, size_t last, unsigned char* blob)
+{
+	#pragma omp parallel for schedule(static) num_threads(packThreads())
+	for (long b = long(first); b < long(last); ++b)
+	{
+		if (b + 8 < long(last))
+		{
+			// the channels are separate heap allocations: a dependent miss each unless asked for a few blocks ahead
+			const auto& ahead = blocks[b + 8];
+			__builtin_prefetch(ahead.DistanceData.data()); __builtin_prefetch(ahead.MaterialData.data()); __builtin_prefetch(ahead.BlendData.data());
+		}
+		const auto& blk = blocks[b];
+		const uint32_t sz[3] = { uint32_t(blk.DistanceData.size()), uint32_t(blk.MaterialData.size()), uint32_t(blk.BlendData.size()) };
+		memcpy(blob + 16 + size_t(b) * 12, sz, 12);
+		unsigned char* out = blob + offsets[b];
+		const uint32_t flags = blk.Flags;
+		memcpy(out, &flags, 4); out += 4;
+		memcpy(out, blk.DistanceData.data(), sz[0]); out += sz[0];
+		memcpy(out, blk.MaterialData.data(), sz[1]); out += sz[1];
+		memcpy(out, blk.BlendData.data(), sz[2]);
+	}
+}
+}
+
+// The gather on its own (tests, tools): the grid in PackForSave form into `out`; returns the size it takes (also when
+// `out` is null or `capacity` too small: nothing is written then), 0 for a grid without block data.
+extern "C" size_t voxels_b200_pack_grid(const Grid* grid, unsigned char* out, size_t capacity)
+{
+	if (!grid) return 0;
+	const auto& blocks = grid->GetInternalRepresentation()->m_Blocks;
+	if (blocks.empty()) return 0;
+	std::vector<size_t> offsets;
+	const size_t total = blobLayout(blocks, offsets);
+	if (!out || capacity < total) return total;
+	packHeader(grid->GetWidth(), out);
+	packBlocks(blocks, offsets, 0, blocks.size(), out);
+	return total;
+}
+
 // The opaque implementation class Polygonizer holds (include/Polygonizer.h:238).
 class TransVoxelImpl
 {
@@ -248,7 +339,8 @@ bool downloadResult(vxb_context* ctx, unsigned n, const vxb_result_info& info, D
 		|| !arena->TransVerts.ensure(size_t(info.trans_vertex_span) * sizeof(PolygonVertex) + 16) || !arena->TransIdx.ensure(size_t(info.trans_index_span) * 4 + 16))
 		return false;
 	std::vector<vxb_block_record> records(info.block_count);
-	if (vxb_result_download(ctx, records.data(), arena->Verts.p, static_cast<uint32_t*>(arena->Idx.p), arena->TransVerts.p,
+	// the directory arrives first; the views are built while the arenas are still moving
+	if (vxb_result_download_begin(ctx, records.data(), arena->Verts.p, static_cast<uint32_t*>(arena->Idx.p), arena->TransVerts.p,
 		static_cast<uint32_t*>(arena->TransIdx.p)) != VXB_OK)
 		return false;
 	const PolygonVertex* verts = static_cast<const PolygonVertex*>(arena->Verts.p);
@@ -256,6 +348,11 @@ bool downloadResult(vxb_context* ctx, unsigned n, const vxb_result_info& info, D
 	const PolygonVertex* tverts = static_cast<const PolygonVertex*>(arena->TransVerts.p);
 	const unsigned* tidx = static_cast<const unsigned*>(arena->TransIdx.p);
 	out.Levels.assign(info.levels_total, std::vector<BlockView>());
+	{
+		std::vector<size_t> perLevel(info.levels_total, 0);
+		for (const vxb_block_record& r : records) if (r.level < info.levels_total) ++perLevel[r.level];
+		for (unsigned l = 0; l < info.levels_total; ++l) out.Levels[l].reserve(perLevel[l]);
+	}
 	for (const vxb_block_record& r : records)
 	{
 		BlockView b;
@@ -274,6 +371,7 @@ bool downloadResult(vxb_context* ctx, unsigned n, const vxb_result_info& info, D
 		b.MaximalCorner = float3(float(bx * m + m), float(bz * m + m), float(by * m + m));
 		out.Levels[r.level].push_back(b);
 	}
+	if (vxb_result_download_end(ctx) != VXB_OK) return false;
 	arena->Live = records.size();
 	out.Storage = std::move(arena);
 	return true;
@@ -382,44 +480,37 @@ PolygonSurface* TransVoxelImpl::Execute(const Grid& grid, const MaterialMap* mat
 
 	// ---- grid -> device: the grid store's compressed blocks, laid out as PackForSave does (VoxelGrid.cpp:269-315: header,
 	// 3 sizes per block, then per block {flags, distance, material, blend}) in page-locked staging - a parallel memcpy of
-	// ~0.2 bytes per voxel - copied as is and run-length decoded on the GPU (vxb_grid_upload_packed) ----
+	// ~0.2 bytes per voxel - copied as is and run-length decoded on the GPU (vxb_grid_upload_packed_streamed) ----
 	const unsigned nb = n / 16;
 	if (!m_Staging) m_Staging = acquireStaging();
 	{
-		const VoxelGrid* vg = grid.GetInternalRepresentation();
-		const auto& blocks = vg->m_Blocks;
+		const auto& blocks = grid.GetInternalRepresentation()->m_Blocks;
 		const size_t count = blocks.size();
 		if (count != size_t(nb) * nb * nb) return fail("the grid holds no block data (Grid::Create without a surface)");
-		std::vector<size_t> offsets(count + 1);
-		const size_t head = 16 + count * 12;
-		size_t off = head;
-		for (size_t b = 0; b < count; ++b)
-		{
-			offsets[b] = off;
-			off += 4 + blocks[b].DistanceData.size() + blocks[b].MaterialData.size() + blocks[b].BlendData.size();
-		}
-		offsets[count] = off;
-		if (!m_Staging->Blob.ensure(off)) return fail("pinned staging allocation failed");
-		clock.mark(1);
+		std::vector<size_t> offsets;
+		const size_t total = blobLayout(blocks, offsets);
+		if (!m_Staging->Blob.ensure(total)) return fail("pinned staging allocation failed");
 		unsigned char* blob = static_cast<unsigned char*>(m_Staging->Blob.p);
-		const uint32_t header[4] = { 1u, n, n, n };
-		memcpy(blob, header, 16);
-		#pragma omp parallel for schedule(static)
-		for (long b = 0; b < long(count); ++b)
+		packHeader(n, blob);
+		for (size_t b = 0; b < count; ++b) // the size table has to be complete before the first slab moves
 		{
-			const auto& blk = blocks[b];
-			const uint32_t sz[3] = { uint32_t(blk.DistanceData.size()), uint32_t(blk.MaterialData.size()), uint32_t(blk.BlendData.size()) };
-			memcpy(blob + 16 + size_t(b) * 12, sz, 12);
-			unsigned char* out = blob + offsets[b];
-			const uint32_t flags = blk.Flags;
-			memcpy(out, &flags, 4); out += 4;
-			memcpy(out, blk.DistanceData.data(), sz[0]); out += sz[0];
-			memcpy(out, blk.MaterialData.data(), sz[1]); out += sz[1];
-			memcpy(out, blk.BlendData.data(), sz[2]);
+			const uint32_t sz[3] = { uint32_t(blocks[b].DistanceData.size()), uint32_t(blocks[b].MaterialData.size()), uint32_t(blocks[b].BlendData.size()) };
+			memcpy(blob + 16 + b * 12, sz, 12);
 		}
-		clock.mark(2);
-		if (vxb_grid_upload_packed(ctx, blob, off) != VXB_OK) return fail("grid upload failed");
+		clock.mark(1);
+		// the gather of slab k+1 (host threads) runs while slab k is copied and decoded
+		struct Feed { const std::vector<VoxelGrid::Block>* blocks; const std::vector<size_t>* offsets; unsigned char* blob; size_t layer; double ms; };
+		Feed feed = { &blocks, &offsets, blob, size_t(nb) * nb, 0.0 };
+		vxb_pack_producer produce = [](void* user, uint32_t layer0, uint32_t layer1) {
+			Feed* f = static_cast<Feed*>(user);
+			const auto t0 = std::chrono::steady_clock::now();
+			packBlocks(*f->blocks, *f->offsets, layer0 * f->layer, layer1 * f->layer, f->blob);
+			f->ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+		};
+		if (vxb_grid_upload_packed_streamed(ctx, blob, total, produce, &feed) != VXB_OK) return fail("grid upload failed");
 		clock.mark(3);
+		g_LastStages[2] = feed.ms;  // the gather (inside the upload call)
+		g_LastStages[3] -= feed.ms; // what the upload call took on top of it: the last slab's copy + decode, maps
 	}
 
 	// ---- polygonize on the device ----

@@ -132,6 +132,9 @@ struct vxb_context
 	vxb_region_info region;
 	DevBuf<unsigned int> updCoords;
 	bool directoryFetched = false;
+	bool downloadOpen = false;            // between vxb_result_download_begin and _end
+	void* downloadVerts = nullptr;
+	void* downloadTransVerts = nullptr;
 	uint32_t shardLaunches = 0;
 	// sharded runs (vxb_shard_*)
 	struct Shard
@@ -755,6 +758,11 @@ int vxb_grid_upload_blocks(vxb_context* ctx, uint32_t n, const int8_t* distBlock
 
 int vxb_grid_upload_packed(vxb_context* ctx, const void* blob, size_t size)
 {
+	return vxb_grid_upload_packed_streamed(ctx, blob, size, nullptr, nullptr);
+}
+
+int vxb_grid_upload_packed_streamed(vxb_context* ctx, const void* blob, size_t size, vxb_pack_producer produce, void* user)
+{
 	if (!ctx) return VXB_ERR_ARGUMENT;
 	if (!blob || size < 16) return fail(ctx, VXB_ERR_ARGUMENT, "vxb_grid_upload_packed: null or truncated blob");
 	const unsigned char* bytes = static_cast<const unsigned char*>(blob);
@@ -821,7 +829,7 @@ int vxb_grid_upload_packed(vxb_context* ctx, const void* blob, size_t size)
 	}
 	else
 	{
-		const int chunks = nb >= 16 ? 4 : 1;
+		const int chunks = nb >= 32 && produce ? 8 : (nb >= 16 ? 4 : 1); // a producer overlaps with the copies: finer slabs
 		for (int c = 0; c < chunks; ++c) ranges.push_back(std::make_pair(nb * c / chunks, nb * (c + 1) / chunks));
 	}
 	while (ctx->evChunks.size() < ranges.size())
@@ -838,6 +846,7 @@ int vxb_grid_upload_packed(vxb_context* ctx, const void* blob, size_t size)
 	{
 		const size_t layer0 = ranges[c].first, layer1 = ranges[c].second;
 		const unsigned long long byte0 = hostOffsets[layer0 * nb * nb], byte1 = (layer1 == nb) ? off : hostOffsets[layer1 * nb * nb];
+		if (produce) produce(user, (uint32_t)layer0, (uint32_t)layer1); // the caller fills this slab while the previous one moves
 		VXB_CUDA(ctx, cudaMemcpyAsync(ctx->staging.p + byte0, bytes + byte0, (size_t)(byte1 - byte0), cudaMemcpyHostToDevice, ctx->stream));
 		VXB_CUDA(ctx, cudaEventRecord(ctx->evChunks[c], ctx->stream));
 		VXB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->evChunks[c], 0));
@@ -1161,6 +1170,7 @@ static int runPolygonize(vxb_context* ctx, uint32_t maxLevels, uint32_t flags, c
 	const bool incremental = region != nullptr;
 	if (!ctx) return VXB_ERR_ARGUMENT;
 	if (!ctx->haveGrid) return fail(ctx, VXB_ERR_STATE, "vxb_polygonize: no grid uploaded");
+	if (ctx->downloadOpen) return fail(ctx, VXB_ERR_STATE, "vxb_polygonize: a result download is open (vxb_result_download_end first)");
 	cudaSetDevice(ctx->device);
 	ctx->haveResult = false;
 	const uint32_t n = ctx->n;
@@ -1840,8 +1850,15 @@ int vxb_result_info_get(vxb_context* ctx, vxb_result_info* out)
 
 int vxb_result_download(vxb_context* ctx, vxb_block_record* records, void* vertices, uint32_t* indices, void* transVertices, uint32_t* transIndices)
 {
+	const int r = vxb_result_download_begin(ctx, records, vertices, indices, transVertices, transIndices);
+	return r != VXB_OK ? r : vxb_result_download_end(ctx);
+}
+
+int vxb_result_download_begin(vxb_context* ctx, vxb_block_record* records, void* vertices, uint32_t* indices, void* transVertices, uint32_t* transIndices)
+{
 	if (!ctx) return VXB_ERR_ARGUMENT;
 	if (!ctx->haveResult) return fail(ctx, VXB_ERR_STATE, "no result: call vxb_polygonize first");
+	if (ctx->downloadOpen) return fail(ctx, VXB_ERR_STATE, "vxb_result_download_begin: the previous download was not ended");
 	cudaSetDevice(ctx->device);
 	const vxb_result_info& info = ctx->info;
 	// directory first (small, into page-locked scratch), the arenas queued right behind it; the directory is sorted into the
@@ -1870,6 +1887,21 @@ int vxb_result_download(vxb_context* ctx, vxb_block_record* records, void* verti
 		ctx->directoryFetched = true;
 	}
 	if (records && info.block_count) memcpy(records, ctx->sortedRecords.data(), sizeof(vxb_block_record) * info.block_count);
+	ctx->downloadOpen = true;
+	ctx->downloadVerts = vertices;
+	ctx->downloadTransVerts = transVertices;
+	return VXB_OK;
+}
+
+int vxb_result_download_end(vxb_context* ctx)
+{
+	if (!ctx) return VXB_ERR_ARGUMENT;
+	if (!ctx->downloadOpen) return fail(ctx, VXB_ERR_STATE, "vxb_result_download_end without vxb_result_download_begin");
+	ctx->downloadOpen = false;
+	cudaSetDevice(ctx->device);
+	const vxb_result_info& info = ctx->info;
+	void* const vertices = ctx->downloadVerts;
+	void* const transVertices = ctx->downloadTransVerts;
 	VXB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 
 	// vertices of unmapped materials carry a marker (vxb_finish_vertex); restore the reference's all-zero textures
