@@ -104,6 +104,30 @@ def host_cpu():
     return model, len(cores)
 
 
+def cgroup_cpu():
+    """The container's CPU quota and throttling counters (cgroup v2): a reference run with more threads than the quota gets
+    throttled by the kernel, which the baseline record should show.  {} when the files are not there."""
+    out = {}
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        out["quota_cpus"] = None if quota == "max" else round(float(quota) / float(period), 2)
+        for line in open("/sys/fs/cgroup/cpu.stat"):
+            k, v = line.split()
+            if k in ("nr_periods", "nr_throttled", "throttled_usec"):
+                out[k] = int(v)
+    except Exception:
+        pass
+    return out
+
+
+def cgroup_delta(before, after):
+    if not after:
+        return None
+    return {"quota_cpus": after.get("quota_cpus"), "throttled_periods": after.get("nr_throttled", 0) - before.get("nr_throttled", 0),
+            "periods": after.get("nr_periods", 0) - before.get("nr_periods", 0),
+            "throttled_ms": round((after.get("throttled_usec", 0) - before.get("throttled_usec", 0)) / 1e3, 1)}
+
+
 class ClockSampler:
     """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
 
@@ -163,6 +187,7 @@ def reference_run(n, steps, warmup, dist, mat, blend, budget_s=150.0, keep_surfa
     threads = reference_threads(ref)
     grid = ref.grid_from_dense(dist, mat, blend)
     times, surface = [], None
+    cg0 = cgroup_cpu()
     warmup = max(1, warmup)
     want = warmup + steps
     done = 0
@@ -188,7 +213,8 @@ def reference_run(n, steps, warmup, dist, mat, blend, budget_s=150.0, keep_surfa
     per_step = sum(times) / len(times)
     model, phys = host_cpu()
     info = {"cores": threads, "physical_cores": phys, "cpu_model": model, "seconds_per_execute": per_step, "best_seconds": min(times),
-            "timed_executions": len(times), "warmup_executions": warmup, "n": n, "omp_proc_bind": os.environ.get("OMP_PROC_BIND")}
+            "timed_executions": len(times), "warmup_executions": warmup, "n": n, "omp_proc_bind": os.environ.get("OMP_PROC_BIND"),
+            "cgroup": cgroup_delta(cg0, cgroup_cpu())}
     return n ** 3 / per_step / 1e6, info, ref, grid, surface
 
 
@@ -239,7 +265,7 @@ def main():
                        "impl": "unmodified reference sources, g++ -O2 -fopenmp -msse2, OMP threads = %d, OMP_PROC_BIND=%s" % (info["cores"], info["omp_proc_bind"]),
                        "same_grid_as_b200_arm": True},
             "cpu_baseline": {"value": value, "unit": "Mvoxels/s", "cores": info["cores"], "physical_cores": info["physical_cores"], "cpu_model": info["cpu_model"],
-                             "kind": "reference", "best_value": n ** 3 / info["best_seconds"] / 1e6,
+                             "kind": "reference", "best_value": n ** 3 / info["best_seconds"] / 1e6, "cgroup": info["cgroup"],
                              "sample": "full %d^3 grid (never shrunk), Polygonizer::Execute only (grid build excluded), mean of %d timed executions after %d warm-up%s"
                                        % (n, info["timed_executions"], info["warmup_executions"],
                                           " (executions cut from --steps %d --warmup %d to fit the time budget)" % (args.steps, args.warmup) if cut else "")},
@@ -466,7 +492,7 @@ def main():
             v, ci, ref, rgrid, rsurf = reference_run(n, 3, 1, hd, hm, hb, budget_s=90.0, keep_surface=True)
             if v is not None:
                 cpu = {"value": n ** 3 / ci["best_seconds"] / 1e6, "mean_value": v, "unit": "Mvoxels/s", "cores": ci["cores"], "physical_cores": ci["physical_cores"],
-                       "cpu_model": ci["cpu_model"], "kind": "reference",
+                       "cpu_model": ci["cpu_model"], "kind": "reference", "cgroup": ci["cgroup"],
                        "sample": "full %d^3 terrain (the same bytes as the GPU step), Polygonizer::Execute only, best of %d after %d warm-up, OMP_PROC_BIND=%s, %.1f s wall incl. grid build"
                                  % (n, ci["timed_executions"], ci["warmup_executions"], ci["omp_proc_bind"], time.time() - t0)}
                 if args.levels == 0 and not args.no_transitions:
@@ -479,32 +505,40 @@ def main():
                 if os.path.exists(harness.B200_LIB) and args.levels == 0 and not args.no_transitions and not args.no_e2e:
                     dl = harness.load(harness.B200_LIB)
                     g2 = dl.grid_from_dense(hd, hm, hb)
-                    secs = []
+                    secs, stage_rows = [], []
                     dsurf = None
-                    for i in range(1 + 3):
+                    import ctypes
+                    stage_names = ("materials", "block_offsets", "gather_blocks", "upload_decode_tail", "kernels", "download_views")
+                    try:
+                        hostlib = ctypes.CDLL(os.path.join(REPO, "voxels_b200", "lib", "libvoxels_b200.so"))
+                    except Exception:
+                        hostlib = None
+                    cg0 = cgroup_cpu()
+                    for i in range(1 + 7):
                         if dsurf is not None:
                             dl.surface_destroy(dsurf)
                         dsurf, sec = dl.polygonize(g2)
                         if i:
                             secs.append(sec)
+                            if hostlib is not None:
+                                st6 = (ctypes.c_double * 6)()
+                                hostlib.voxels_b200_last_execute_stages(st6)
+                                stage_rows.append([round(v, 3) for v in st6])
+                    cg_dropin = cgroup_delta(cg0, cgroup_cpu())
                     import compare
                     problems = []
                     for l in range(ref.surface_levels(rsurf)):
                         problems += compare.level_diff(ref.surface_level(rsurf, l), dl.surface_level(dsurf, l), "L%d" % l)
-                    stages = None
-                    try:
-                        import ctypes
-                        lib = ctypes.CDLL(os.path.join(REPO, "voxels_b200", "lib", "libvoxels_b200.so"))
-                        st6 = (ctypes.c_double * 6)()
-                        lib.voxels_b200_last_execute_stages(st6)
-                        stages = dict(zip(("materials", "block_offsets", "pack_blob", "upload_decode", "kernels", "download_views"), (round(v, 3) for v in st6)))
-                    except Exception:
-                        pass
+                    order = sorted(range(len(secs)), key=lambda i: secs[i])
+                    med = order[len(order) // 2]
+                    stages = dict(zip(stage_names, stage_rows[med])) if stage_rows else None
                     dl.surface_destroy(dsurf); dl.grid_destroy(g2)
-                    ms_d = 1e3 * sum(secs) / len(secs)
-                    extra["e2e_dropin"] = {"value": float(n) ** 3 / (ms_d * 1e-3) / 1e6, "unit": "Mvoxels/s", "ms_per_step": ms_d, "best_ms": 1e3 * min(secs), "steps": len(secs),
-                                           "host_ms_last": stages, "path": "Voxels::Polygonizer::Execute of libvoxels_b200.so on a reference Grid (compressed blocks -> pinned blob -> GPU decode -> kernels -> "
-                                                   "arenas back to the host -> PolygonSurface), host clock around Execute only",
+                    ms_d = 1e3 * secs[med]
+                    extra["e2e_dropin"] = {"value": float(n) ** 3 / (ms_d * 1e-3) / 1e6, "unit": "Mvoxels/s", "ms_per_step": ms_d, "statistic": "median of %d executions after 1 warm-up" % len(secs),
+                                           "best_ms": 1e3 * min(secs), "mean_ms": 1e3 * sum(secs) / len(secs), "all_ms": [round(1e3 * v, 2) for v in secs], "steps": len(secs),
+                                           "host_ms_median_run": stages, "cgroup": cg_dropin,
+                                           "path": "Voxels::Polygonizer::Execute of libvoxels_b200.so on a reference Grid (compressed blocks gathered into a pinned blob slab by slab while the "
+                                                   "previous slab is copied and decoded on the GPU -> kernels -> arenas back to the host, block views built meanwhile -> PolygonSurface), host clock around Execute only",
                                            "parity": {"checked": True, "mismatches": len(problems), "first": problems[:3]},
                                            "vs_reference_same_run": (float(n) ** 3 / (ms_d * 1e-3) / 1e6) / v}
                 ref.surface_destroy(rsurf); ref.grid_destroy(rgrid)

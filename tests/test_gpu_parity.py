@@ -319,7 +319,8 @@ def test_streamed_packed_upload_and_split_download():
             assert np.array_equal(a, b)
         info = ctx.polygonize()
         res = ctx.download_begin()
-        assert np.array_equal(res.records, want.records)      # the directory is there before the arenas
+        for f in ("level", "coord_id", "id", "vertex_count", "index_count"):   # the directory is there before the arenas (offsets differ run to run)
+            assert np.array_equal(res.records[f], want.records[f]), f
         with pytest.raises(capi.VxbError):                     # no run while a download is open
             ctx.polygonize()
         ctx.download_end()

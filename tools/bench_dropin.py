@@ -34,7 +34,7 @@ def main():
     g = dl.grid_from_dense(hd, hm, hb)
     del hd, hm, hb
     lib = ctypes.CDLL(os.path.join(REPO, "voxels_b200", "lib", "libvoxels_b200.so"))
-    names = ("materials", "block_offsets", "pack_blob", "upload_decode", "kernels", "download_views")
+    names = ("materials", "block_offsets", "gather_blocks", "upload_decode_tail", "kernels", "download_views")
     runs = []
     surf = None
     for i in range(args.runs):

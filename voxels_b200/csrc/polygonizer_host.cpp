@@ -250,14 +250,15 @@ int packThreads()
 // block {flags, distance, material, blend}); returns the total size.
 size_t blobLayout(const std::vector<VoxelGrid::Block>& blocks, std::vector<size_t>& offsets)
 {
+	// the per-block sizes are read in parallel (a pass over the 80-byte Block records); the prefix sum is serial over 8 bytes
+	// per block
 	const size_t count = blocks.size();
 	offsets.resize(count + 1);
+	#pragma omp parallel for schedule(static) num_threads(packThreads())
+	for (long b = 0; b < long(count); ++b)
+		offsets[b] = size_t(4) + blocks[b].DistanceData.size() + blocks[b].MaterialData.size() + blocks[b].BlendData.size();
 	size_t off = 16 + count * 12;
-	for (size_t b = 0; b < count; ++b)
-	{
-		offsets[b] = off;
-		off += 4 + blocks[b].DistanceData.size() + blocks[b].MaterialData.size() + blocks[b].BlendData.size();
-	}
+	for (size_t b = 0; b < count; ++b) { const size_t bytes = offsets[b]; offsets[b] = off; off += bytes; }
 	offsets[count] = off;
 	return off;
 }
@@ -492,10 +493,11 @@ PolygonSurface* TransVoxelImpl::Execute(const Grid& grid, const MaterialMap* mat
 		if (!m_Staging->Blob.ensure(total)) return fail("pinned staging allocation failed");
 		unsigned char* blob = static_cast<unsigned char*>(m_Staging->Blob.p);
 		packHeader(n, blob);
-		for (size_t b = 0; b < count; ++b) // the size table has to be complete before the first slab moves
+		#pragma omp parallel for schedule(static) num_threads(packThreads())
+		for (long b = 0; b < long(count); ++b) // the size table has to be complete before the first slab moves
 		{
 			const uint32_t sz[3] = { uint32_t(blocks[b].DistanceData.size()), uint32_t(blocks[b].MaterialData.size()), uint32_t(blocks[b].BlendData.size()) };
-			memcpy(blob + 16 + b * 12, sz, 12);
+			memcpy(blob + 16 + size_t(b) * 12, sz, 12);
 		}
 		clock.mark(1);
 		// the gather of slab k+1 (host threads) runs while slab k is copied and decoded
