@@ -177,33 +177,42 @@ def reference_threads(ref):
 
 
 def reference_run(n, steps, warmup, dist, mat, blend, budget_s=150.0, keep_surface=False):
-    """Times the reference's own Polygonizer::Execute (all host threads) on the given n^3 grid (numpy [z,y,x] arrays).
-    The GRID is never shrunk; when warmup + steps executions would not fit the time budget the number of executions is
-    cut (never below 1 warm-up + 2 timed) and the line says so.  Returns (Mvoxels/s, info, ref, grid, surface)."""
+    """Times the reference's own Polygonizer::Execute on the given n^3 grid (numpy [z,y,x] arrays) with the thread count that
+    serves it best here: every host CPU, or - in a container with a CPU quota below that (cgroup cpu.max), where a larger
+    team is throttled by the kernel - one thread per quota CPU; both are tried once during the warm-up and the faster is
+    timed.  The GRID is never shrunk; when warmup + steps executions would not fit the time budget the number of
+    executions is cut (never below 1 warm-up + 2 timed) and the line says so.
+    Returns (Mvoxels/s, info, ref, grid, surface)."""
     import harness
     if not os.path.exists(harness.REF_LIB):
         return None, {"unavailable": "oracle/_ref/libvxh_ref.so not built (make -C oracle ref needs the reference checkout)"}, None, None, None
     ref = harness.reference()
-    threads = reference_threads(ref)
+    all_threads = reference_threads(ref)
     grid = ref.grid_from_dense(dist, mat, blend)
-    times, surface = [], None
     cg0 = cgroup_cpu()
-    warmup = max(1, warmup)
-    want = warmup + steps
-    done = 0
-    t_first = None
-    while done < want:
+    quota = cg0.get("quota_cpus")
+    candidates = [all_threads]
+    if quota and quota < all_threads:
+        candidates.append(max(1, int(quota + 0.999)))
+    trials, spent = {}, 0.0
+    for t in candidates:                         # the warm-up executions double as the thread-count trial
+        s, sec = ref.polygonize(grid, threads=t)
+        ref.surface_destroy(s)
+        trials[t] = sec; spent += sec
+    threads = min(trials, key=trials.get)
+    extra_warm = max(0, warmup - len(candidates))
+    per = trials[threads]
+    fit = int((budget_s - spent) / max(per, 1e-3))
+    want = extra_warm + steps
+    if fit < want:
+        extra_warm = 0
+        want = max(2, min(steps, fit))
+    times, surface = [], None
+    for i in range(want):
         s, sec = ref.polygonize(grid, threads=threads)
-        if t_first is None:
-            t_first = sec
-            fit = int(budget_s / max(sec, 1e-3))
-            if fit < want:
-                warmup = 1
-                want = max(1 + 2, min(want, fit))
-        if done >= warmup:
+        if i >= extra_warm:
             times.append(sec)
-        done += 1
-        if keep_surface and done == want:
+        if keep_surface and i == want - 1:
             surface = s
         else:
             ref.surface_destroy(s)
@@ -213,8 +222,8 @@ def reference_run(n, steps, warmup, dist, mat, blend, budget_s=150.0, keep_surfa
     per_step = sum(times) / len(times)
     model, phys = host_cpu()
     info = {"cores": threads, "physical_cores": phys, "cpu_model": model, "seconds_per_execute": per_step, "best_seconds": min(times),
-            "timed_executions": len(times), "warmup_executions": warmup, "n": n, "omp_proc_bind": os.environ.get("OMP_PROC_BIND"),
-            "cgroup": cgroup_delta(cg0, cgroup_cpu())}
+            "timed_executions": len(times), "warmup_executions": len(candidates) + extra_warm, "n": n, "omp_proc_bind": os.environ.get("OMP_PROC_BIND"),
+            "thread_trials_s": {str(k): round(v, 3) for k, v in trials.items()}, "cgroup": cgroup_delta(cg0, cgroup_cpu())}
     return n ** 3 / per_step / 1e6, info, ref, grid, surface
 
 
@@ -265,7 +274,7 @@ def main():
                        "impl": "unmodified reference sources, g++ -O2 -fopenmp -msse2, OMP threads = %d, OMP_PROC_BIND=%s" % (info["cores"], info["omp_proc_bind"]),
                        "same_grid_as_b200_arm": True},
             "cpu_baseline": {"value": value, "unit": "Mvoxels/s", "cores": info["cores"], "physical_cores": info["physical_cores"], "cpu_model": info["cpu_model"],
-                             "kind": "reference", "best_value": n ** 3 / info["best_seconds"] / 1e6, "cgroup": info["cgroup"],
+                             "kind": "reference", "best_value": n ** 3 / info["best_seconds"] / 1e6, "cgroup": info["cgroup"], "thread_trials_s": info["thread_trials_s"],
                              "sample": "full %d^3 grid (never shrunk), Polygonizer::Execute only (grid build excluded), mean of %d timed executions after %d warm-up%s"
                                        % (n, info["timed_executions"], info["warmup_executions"],
                                           " (executions cut from --steps %d --warmup %d to fit the time budget)" % (args.steps, args.warmup) if cut else "")},
@@ -492,7 +501,7 @@ def main():
             v, ci, ref, rgrid, rsurf = reference_run(n, 3, 1, hd, hm, hb, budget_s=90.0, keep_surface=True)
             if v is not None:
                 cpu = {"value": n ** 3 / ci["best_seconds"] / 1e6, "mean_value": v, "unit": "Mvoxels/s", "cores": ci["cores"], "physical_cores": ci["physical_cores"],
-                       "cpu_model": ci["cpu_model"], "kind": "reference", "cgroup": ci["cgroup"],
+                       "cpu_model": ci["cpu_model"], "kind": "reference", "cgroup": ci["cgroup"], "thread_trials_s": ci["thread_trials_s"],
                        "sample": "full %d^3 terrain (the same bytes as the GPU step), Polygonizer::Execute only, best of %d after %d warm-up, OMP_PROC_BIND=%s, %.1f s wall incl. grid build"
                                  % (n, ci["timed_executions"], ci["warmup_executions"], ci["omp_proc_bind"], time.time() - t0)}
                 if args.levels == 0 and not args.no_transitions:
