@@ -276,6 +276,7 @@ def test_packed_upload_rejects_malformed_blobs(reference):
         cases["truncated"] = good[:len(good) - 100].copy()
         b = good.copy(); b[data0:data0 + 4].view(np.uint32)[0] |= 2; cases["raw flag on a run-length coded channel"] = b   # block 0: BF_DistanceUncompressed but size < 4096
         assert sizes[0, 0] < 4096
+        b = good.copy(); b[data0 + 4] = (int(b[data0 + 4]) + 1) & 0xFF; cases["run lengths that do not add up to 4096"] = b   # first run of block 0's distance channel
         for what, blob in cases.items():
             with pytest.raises(capi.VxbError):
                 ctx.upload_packed(blob)

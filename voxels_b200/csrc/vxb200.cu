@@ -862,7 +862,7 @@ int vxb_grid_upload_packed_streamed(vxb_context* ctx, const void* blob, size_t s
 	if (packError)
 	{
 		ctx->haveGrid = false;
-		return fail(ctx, VXB_ERR_ARGUMENT, "vxb_grid_upload_packed: a block's flags word contradicts its sizes (a raw channel must hold 4096 bytes, a run-length coded one whole (length, value) pairs)");
+		return fail(ctx, VXB_ERR_ARGUMENT, "vxb_grid_upload_packed: malformed block data (a raw channel must hold 4096 bytes, a run-length coded one whole (length, value) pairs whose lengths add up to 4096)");
 	}
 	const double msKernel = msSince(t0);
 	if (pieces) { ctx->haveResult = false; ctx->haveFullRun = false; r = VXB_OK; }

@@ -481,7 +481,7 @@ __global__ void __launch_bounds__(VXB_THREADS) vxb_unpack_block_list_kernel(cons
 // runs of <= 255), those are written as full 128-byte lines (8 lanes x 16 bytes, the layout of vxb_scan_kernel's reads);
 // the others are decoded by the whole CTA, thread t producing row t by a binary search of the run covering its first byte.
 __device__ __forceinline__ void vxb_decode_channel(const unsigned char* src, unsigned size, bool raw, unsigned char* out, int n, int bx, int by, int bz,
-	unsigned short* start, unsigned char* value, unsigned* warpSums)
+	unsigned short* start, unsigned char* value, unsigned* warpSums, unsigned int* error)
 {
 	const int tid = threadIdx.x, y = tid & 15, z = tid >> 4;
 	uint4 row;
@@ -500,7 +500,7 @@ __device__ __forceinline__ void vxb_decode_channel(const unsigned char* src, uns
 		unsigned total;
 		unsigned base = vxb_block_scan(sum, warpSums, total);
 		for (unsigned r = r0; r < r1; ++r) { start[r] = (unsigned short)min(base, 4096u); value[r] = src[2 * r + 1]; base += src[2 * r]; }
-		if (tid == 0) start[runs] = 4096;
+		if (tid == 0) { start[runs] = 4096; if (total != 4096u) *error = 1u; } // the runs of a block cover exactly its 4096 voxels (:674-694)
 		__syncthreads();
 		const unsigned p0 = tid * 16;
 		unsigned lo = 0, hi = runs; // last run with start <= p0
@@ -555,8 +555,9 @@ __global__ void __launch_bounds__(VXB_THREADS) vxb_unpack_rle_kernel(const unsig
 				const unsigned char* p = blob + off;
 				const unsigned runs = size >> 1;
 				bool same = runs >= 1 && runs <= 64;
-				for (unsigned r = 1; r < runs && same; ++r) same = p[2 * r + 1] == p[1];
-				if (same) kind = p[1];
+				unsigned covered = same ? p[0] : 0u;
+				for (unsigned r = 1; r < runs && same; ++r) { same = p[2 * r + 1] == p[1]; covered += p[2 * r]; }
+				if (same) { kind = p[1]; if (covered != 4096u) *error = 1u; }
 			}
 		}
 		sKind[j][ch] = kind;
@@ -586,7 +587,7 @@ __global__ void __launch_bounds__(VXB_THREADS) vxb_unpack_rle_kernel(const unsig
 	{
 		const int j = e / 3, ch = e % 3;
 		if (bx0 + j >= nb || sKind[j][ch] >= 0) continue;
-		vxb_decode_channel(blob + sOff[j][ch], sSize[j][ch], sKind[j][ch] == -2, outs[ch], n, bx0 + j, by, bz, start, value, warpSums);
+		vxb_decode_channel(blob + sOff[j][ch], sSize[j][ch], sKind[j][ch] == -2, outs[ch], n, bx0 + j, by, bz, start, value, warpSums, error);
 	}
 }
 
