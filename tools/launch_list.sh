@@ -2,7 +2,7 @@
 # ncu launch list of one bench step (per-launch gpu__time_duration, cold-cache and serialised: shares, not absolutes).
 # usage: tools/launch_list.sh <out.csv> [bench args...]
 out=$1; shift
-ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name regex:vxb_ -c 400 --csv --log-file "$out" python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e "$@" > "${out%.csv}.log" 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name regex:vxb_ -c 400 --csv --log-file "$out" python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-config4 "$@" > "${out%.csv}.log" 2>&1
 python - "$out" <<'PY'
 import csv, sys
 rows = [r for r in csv.reader(open(sys.argv[1])) if len(r) > 5]
