@@ -365,7 +365,7 @@ def main():
         d0, dup, bm, bo = algorithmic_bytes(n, levels_computed, V, I, TV, TI)
         bytes_alg_total = d0 + dup + bm + bo
         kinds = ["vxb_scan_kernel (streams the level-0 distance volume once)",
-                 "vxb_block_info / vxb_pyramid / vxb_select kernels (block walk)",
+                 "vxb_coarse_lattice_kernel + vxb_block_info / vxb_pyramid / vxb_select kernels (lattices of levels >= 2 + block walk)",
                  "vxb_block_kernel<1>/<2> (levels >= 1: tiles, case codes, material votes, reuse decisions)",
                  "vxb_block_kernel<0> (level 0: tile -> case codes -> decisions -> vertices -> triangles in one pass)",
                  "vxb_vertex_kernel (levels >= 1, flat, one thread per new vertex)",
@@ -600,7 +600,7 @@ def main():
         config = {"workload": "%d^3 seeded Perlin terrain, ONE grid over %d GPUs (strong scaling), all LOD levels + transition cells" % (n, world),
                   "grid": ("dense int8 distance + uint8 material + uint8 blend, read-only, resident in EVERY rank's HBM (3 GiB at 1024^3): every kernel load is local" if args.shard_mode == "replicated"
                            else "dense int8 distance + uint8 material + uint8 blend; z-pieces of %d planes dealt cyclically to the ranks' HBM, mapped into every peer over NVLink" % sg.group_planes),
-                  "sharding": "work dealt by blocks: every rank scans 1/N of the layers; exchange 0 = ncclAllGather of the per-block info; super-blocks cut by surface weight; exchange 1 = peer stores of material pages + a one-word ncclAllGather; coarse levels classified by every rank; output stays on the rank",
+                  "sharding": "work dealt by blocks: every rank scans 1/N of the layers; exchange 0 = ncclAllGather of the per-block info; super-blocks cut by surface weight; exchange 1 = peer stores of material pages + a device-side barrier over the mapped buffers; coarse levels classified by every rank; output stays on the rank",
                   "l2": "inputs larger than the 126 MB L2; no flush", "vertices": V, "indices": I, "transition_vertices": TV, "transition_indices": TI,
                   "blocks_emitted": int(len(directory)), "blocks_per_rank": per_rank_blocks, "vertices_per_rank": per_rank_verts, "nccl_ranks": world,
                   "host_binding": "every rank pinned to the CPUs of its GPU's NUMA node (rank 0: node %s)" % numa_node}

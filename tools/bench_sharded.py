@@ -73,14 +73,14 @@ def main():
     out = {"metric": "Mvoxels/s polygonized (one grid over the GPUs)", "value": float(n) ** 3 / (ms * 1e-3) / 1e6, "unit": "Mvoxels/s",
            "n_gpus": ranks.world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "scaling": "strong",
            "config": {"workload": "%d^3 seeded Perlin terrain, all LOD levels + transition cells, volumes %s, scan groups / pieces of %d planes dealt cyclically" % (n, args.mode, sg.group_planes),
-                      "exchange": "ncclAllGather of the per-block info + peer stores of material pages (ordered by a one-word ncclAllGather), inside every step"},
+                      "exchange": "ncclAllGather of the per-block info + peer stores of material pages (ordered by a device-side barrier over the mapped buffers), inside every step"},
            "blocks_total": int(len(directory)), "blocks_per_rank": [int((owner == r).sum()) for r in range(ranks.world)],
            "vertices_per_rank": [int(directory["vertex_count"][owner == r].sum()) for r in range(ranks.world)],
            "device_ms_per_rank": [round(float(v), 3) for v in per_rank.cpu().numpy()], "launches_per_step": int(info.kernel_launches)}
 
     # where the step goes, per rank: one extra step with per-kernel events (plain launches, one stream)
-    kinds = ["scan+coarse lattice", "block walk (info, pyramid, plan, select)", "block kernels levels>=1 + coarse", "block kernel level 0", "vertices levels>=1",
-             "triangles levels>=1", "transitions", "finish", "exchange 0 (lattice publish + all-gather)", "exchange 1 (page publish + all-gather)"]
+    kinds = ["scan", "coarse lattices + block walk (info, pyramid, plan, select)", "block kernels levels>=1 + coarse", "block kernel level 0", "vertices levels>=1",
+             "triangles levels>=1", "transitions", "finish", "exchange 0 (lattice publish + all-gather)", "exchange 1 (page publish + peer barrier)"]
     ranks.barrier()
     sg.ctx.polygonize_sharded(3, voxels_b200.FLAG_KERNEL_TIMES)
     if True:
