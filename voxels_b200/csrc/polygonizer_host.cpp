@@ -184,7 +184,7 @@ typedef std::unique_ptr<Arena, ArenaReturn> ArenaPtr;
 // The polygonized surface: block views over host arenas (one per run: the full run + one small one per edit).
 // It owns the device context that holds the grid copy and the material caches of this surface, the way the
 // reference's PolygonMap owns its MaterialCache (TransVoxelImpl.h:81-95), so later incremental runs find them.
-struct SurfaceImpl : public PolygonSurface
+struct SurfaceImpl final : public PolygonSurface
 {
 	float3 Extents;
 	std::vector<std::vector<BlockView>> Levels;
@@ -214,7 +214,7 @@ struct SurfaceImpl : public PolygonSurface
 	virtual void Destroy() override { delete this; }
 };
 
-struct ModificationImpl : public Modification
+struct ModificationImpl final : public Modification
 {
 	std::vector<unsigned> ModifiedBlocks;
 	virtual const unsigned* GetModifiedBlocks(unsigned* count) const override
