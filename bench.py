@@ -104,14 +104,14 @@ def host_cpu():
     return model, len(cores)
 
 
-def cgroup_cpu():
+def cgroup_cpu(root="/sys/fs/cgroup"):
     """The container's CPU quota and throttling counters (cgroup v2): a reference run with more threads than the quota gets
     throttled by the kernel, which the baseline record should show.  {} when the files are not there."""
     out = {}
     try:
-        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        quota, period = open(os.path.join(root, "cpu.max")).read().split()[:2]
         out["quota_cpus"] = None if quota == "max" else round(float(quota) / float(period), 2)
-        for line in open("/sys/fs/cgroup/cpu.stat"):
+        for line in open(os.path.join(root, "cpu.stat")):
             k, v = line.split()
             if k in ("nr_periods", "nr_throttled", "throttled_usec"):
                 out[k] = int(v)
